@@ -1,0 +1,112 @@
+"""ctypes binding of libslfp_b200.so (the C ABI declared in include/slfp_b200.h).
+
+There is no CPU fallback and no other backend: if the library is missing or a tensor is not on a
+CUDA device, the callers raise.
+"""
+import ctypes
+import os
+
+import torch
+
+from .build import LIB_PATH
+
+FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT = 0, 1, 2, 3
+ACT_STL, ACT_SWISH, ACT_SIGMOID = 0, 1, 2
+SGD_NORMAL, SGD_DSGD, SGD_SSGD = 0, 1, 2
+Q_LAYEROUT_ZERO_IS_ZERO = 1
+
+c_vp, c_sz, c_f, c_i, c_ll, c_d = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
+                                   ctypes.c_longlong, ctypes.c_double)
+
+
+class SlfpConvDesc(ctypes.Structure):
+    _fields_ = [(n, c_i) for n in ("n", "h", "w", "c", "c_phys", "k", "r", "s", "stride_h", "stride_w", "pad_h",
+                                   "pad_w", "dil_h", "dil_w", "groups", "fmt")]
+
+
+class SlfpEpilogue(ctypes.Structure):
+    _fields_ = [("bias_q", c_vp), ("post_a", c_f), ("post_b", c_f), ("ch_scale", c_vp), ("ch_shift", c_vp),
+                ("residual", c_vp), ("residual_f16", c_i), ("relu", c_i), ("y_f32", c_vp), ("y_f16", c_vp),
+                ("y_codes", c_vp), ("next_k_div", c_f), ("next_fmt", c_i), ("k_phys_out", c_i),
+                ("y_codes2", c_vp), ("next_k_div2", c_f)]
+
+
+_SIGS = {
+    "slfp_version": (c_i, []),
+    "slfp_last_error": (ctypes.c_char_p, []),
+    "slfp_quantize_f32": (c_i, [c_vp, c_sz, c_f, c_i, ctypes.c_uint, c_vp, c_vp, c_vp, c_vp]),
+    "slfp_quantize_nhwc_f32": (c_i, [c_vp, c_sz, c_i, c_i, c_f, c_i, c_vp, c_vp]),
+    "slfp_dequantize": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
+    "slfp_absmax_f32": (c_i, [c_vp, c_sz, c_vp, c_i, c_vp]),
+    "slfp_conv_wpitch": (c_sz, [ctypes.POINTER(SlfpConvDesc)]),
+    "slfp_prepare_weights": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_ll, c_ll, c_ll, c_ll, c_f, c_i, c_vp, c_vp,
+                                   c_vp, c_vp]),
+    "slfp_conv2d_fwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, ctypes.POINTER(SlfpEpilogue), c_vp]),
+    "slfp_conv2d_bwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, c_vp, c_i, c_f, c_f, c_vp, c_vp, c_ll, c_ll,
+                              c_ll, c_ll, c_vp, c_vp]),
+    "slfp_act_fwd": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
+    "slfp_act_bwd": (c_i, [c_vp, c_vp, c_sz, c_i, c_vp, c_vp]),
+    "slfp_sgd_step": (c_i, [c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_vp]),
+    "slfp_maxpool_codes": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp]),
+    "slfp_avgpool_nhwc": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_vp, c_vp]),
+    "slfp_quantize_host_f32": (c_i, [c_vp, c_sz, c_f, c_i, c_vp, c_vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+_lib = None
+
+
+def lib():
+    """Load the native library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m cnns_slfp_quantization_b200.build` "
+                "(nvcc, sm_100a).  There is no CPU / PyTorch fallback for the SLFP hot path.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().slfp_last_error()
+        raise RuntimeError(f"libslfp_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t, who):
+    if not t.is_cuda:
+        raise RuntimeError(f"{who}: expected a CUDA tensor (the SLFP hot path has hand-written sm_100a kernels only; "
+                           "there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{who}: expected float32, got {t.dtype}")
+
+
+def fmt_for(q_bit, kind):
+    """q_bit in {7, 8}; kind in {'act', 'weight'} -> storage format of the 8-bit codes."""
+    if q_bit == 7:
+        return FMT_SFP33
+    if q_bit == 8:
+        return FMT_SLFP34_ACT if kind == "act" else FMT_SLFP34_WGT
+    raise ValueError(f"no 8-bit code format for q_bit={q_bit}")
+
+
+def dense_flat(t):
+    """A tensor whose storage can be processed as a flat array in memory order (any dense layout)."""
+    if t.is_contiguous():
+        return t
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    return t.contiguous()

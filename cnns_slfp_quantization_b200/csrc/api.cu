@@ -1,0 +1,40 @@
+// api.cu -- C-ABI dispatch for the convolution entry points (include/slfp_b200.h).
+#include "slfp_common.cuh"
+
+namespace slfp {
+int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st);
+int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_codes, const SlfpEpilogue* epi, cudaStream_t st);
+int conv2d_bwd_direct(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes, int wfmt,
+                      float ka, float kw, float* dx, float* dwt, long long so, long long sc, long long sr, long long ss,
+                      float* db, cudaStream_t st);
+}  // namespace slfp
+
+using namespace slfp;
+
+static int check_desc(const SlfpConvDesc* d, const char* who) {
+    if (!d) return set_error(SLFP_ERR_BAD_ARG, "%s: null descriptor", who);
+    if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->c <= 0 || d->k <= 0 || d->r <= 0 || d->s <= 0 || d->stride_h <= 0 ||
+        d->stride_w <= 0 || d->dil_h <= 0 || d->dil_w <= 0 || d->pad_h < 0 || d->pad_w < 0 || d->groups <= 0 ||
+        d->c_phys < d->c)
+        return set_error(SLFP_ERR_BAD_ARG, "%s: invalid convolution descriptor", who);
+    return 0;
+}
+
+extern "C" int slfp_conv2d_fwd(const SlfpConvDesc* desc, const uint8_t* x_codes, const void* w_prepared,
+                               const SlfpEpilogue* epi, slfp_stream_t stream) {
+    int rc = check_desc(desc, "slfp_conv2d_fwd");
+    if (rc) return rc;
+    if (!x_codes || !w_prepared || !epi) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_fwd: null pointer");
+    if (!epi->y_f32 && !epi->y_f16 && !epi->y_codes) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_fwd: no output");
+    if (desc->groups == 1) return conv2d_fwd_dense(desc, x_codes, w_prepared, epi, (cudaStream_t)stream);
+    return conv2d_fwd_grouped(desc, x_codes, w_prepared, epi, (cudaStream_t)stream);
+}
+
+extern "C" int slfp_conv2d_bwd(const SlfpConvDesc* desc, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes,
+                               int wfmt, float ka, float kw, float* dx, float* dw, long long so, long long sc,
+                               long long sr, long long ss, float* db, slfp_stream_t stream) {
+    int rc = check_desc(desc, "slfp_conv2d_bwd");
+    if (rc) return rc;
+    if (!gy) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_bwd: null gy");
+    return conv2d_bwd_direct(desc, gy, x_codes, w_codes, wfmt, ka, kw, dx, dw, so, sc, sr, ss, db, (cudaStream_t)stream);
+}

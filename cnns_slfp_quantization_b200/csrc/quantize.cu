@@ -1,0 +1,393 @@
+// quantize.cu -- fused SLFP / SFP quantizer, de-quantizer, abs-max and weight preparation.
+//
+// Replaces the ~25-kernel ATen chains of utils/sfp_quant.py:14-47, 63-96, 111-126 plus the
+// pre-scale division of utils/conv2d_func.py:21-22 with ONE pass over HBM:
+//   4 B read + 1 B (codes) / 4 B (fake-quant fp32) / 2 B (fp16) written per element.
+// The kernel is HBM-bound: every warp-level load is one contiguous 512 B request (128-bit per lane,
+// L1 no-allocate), a thread keeps four of them in flight, and the grid is a multiple of the SM count.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "slfp_common.cuh"
+
+namespace slfp {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+            cudaGetLastError();
+            sms = 148;
+        }
+    }
+    return sms;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr int kQThreads = 256;
+constexpr int kQVec = 4;                       // float4 loads in flight per thread
+constexpr int kQTile = kQThreads * 4 * kQVec;  // 4096 elements per CTA iteration
+
+struct QuantArgs {
+    const float* x;
+    size_t n;
+    float k_div;
+    uint8_t* codes;
+    float* fakeq;
+    __half* f16;
+    int zero_is_zero;
+};
+
+template <int FMT>
+__device__ __forceinline__ void quant_elem(float x, float k_div, bool zz, const uint32_t* tab,
+                                           uint32_t& code, float& fq) {
+    const float v = div_rn(x, k_div);          // IEEE division, like `input / self.Ka` on the CPU
+    if (FMT == SLFP_FMT_SFP44_OUT) {
+        code = 0;
+        fq = layerout_quantize(v, zz);
+    } else {
+        code = encode<FMT>(v);
+        fq = decode<FMT == SLFP_FMT_SFP33>(code, tab);
+    }
+}
+
+template <int FMT, bool CODES, bool FAKEQ, bool F16>
+__global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
+    __shared__ uint32_t s_tab[16];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    const bool zz = a.zero_is_zero != 0;
+    const size_t n_tiles = a.n / kQTile;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t base = tile * kQTile;
+        float4 v[kQVec];
+#pragma unroll
+        for (int j = 0; j < kQVec; ++j)
+            v[j] = ldg_stream(reinterpret_cast<const float4*>(a.x + base) + j * kQThreads + threadIdx.x);
+#pragma unroll
+        for (int j = 0; j < kQVec; ++j) {
+            const size_t off = base + (size_t)(j * kQThreads + threadIdx.x) * 4;
+            uint32_t c[4];
+            float q[4];
+            quant_elem<FMT>(v[j].x, a.k_div, zz, s_tab, c[0], q[0]);
+            quant_elem<FMT>(v[j].y, a.k_div, zz, s_tab, c[1], q[1]);
+            quant_elem<FMT>(v[j].z, a.k_div, zz, s_tab, c[2], q[2]);
+            quant_elem<FMT>(v[j].w, a.k_div, zz, s_tab, c[3], q[3]);
+            if (CODES)
+                *reinterpret_cast<uint32_t*>(a.codes + off) = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+            if (FAKEQ) stg_stream(reinterpret_cast<float4*>(a.fakeq + off), make_float4(q[0], q[1], q[2], q[3]));
+            if (F16) {
+                __half2 h0 = __floats2half2_rn(q[0], q[1]), h1 = __floats2half2_rn(q[2], q[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(a.f16 + off) = pk;
+            }
+        }
+    }
+    // ragged tail (< one tile): scalar, first CTA only
+    if (blockIdx.x == 0) {
+        for (size_t i = n_tiles * kQTile + threadIdx.x; i < a.n; i += kQThreads) {
+            uint32_t c;
+            float q;
+            quant_elem<FMT>(a.x[i], a.k_div, zz, s_tab, c, q);
+            if (CODES) a.codes[i] = (uint8_t)c;
+            if (FAKEQ) a.fakeq[i] = q;
+            if (F16) a.f16[i] = __float2half_rn(q);
+        }
+    }
+}
+
+// fully scalar variant for mis-aligned pointers (sliced tensors); same arithmetic
+template <int FMT>
+__global__ void __launch_bounds__(kQThreads) quantize_scalar_kernel(QuantArgs a) {
+    __shared__ uint32_t s_tab[16];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * kQThreads + threadIdx.x; i < a.n; i += (size_t)gridDim.x * kQThreads) {
+        uint32_t c;
+        float q;
+        quant_elem<FMT>(a.x[i], a.k_div, a.zero_is_zero != 0, s_tab, c, q);
+        if (a.codes) a.codes[i] = (uint8_t)c;
+        if (a.fakeq) a.fakeq[i] = q;
+        if (a.f16) a.f16[i] = __float2half_rn(q);
+    }
+}
+
+template <int FMT>
+static int launch_quantize(const QuantArgs& a, cudaStream_t st) {
+    const bool aligned = (((uintptr_t)a.x | (uintptr_t)a.fakeq) & 15u) == 0 && ((uintptr_t)a.codes & 3u) == 0 &&
+                         ((uintptr_t)a.f16 & 7u) == 0;
+    const int sms = num_sms();
+    if (!aligned) {
+        int grid = (int)min((size_t)sms * 8, ceil_div_sz(a.n, kQThreads));
+        quantize_scalar_kernel<FMT><<<grid, kQThreads, 0, st>>>(a);
+        return check_launch("quantize_scalar_kernel");
+    }
+    const size_t tiles = a.n / kQTile;
+    int grid = (int)max((size_t)1, min(tiles, (size_t)sms * 8));
+    const int sel = (a.codes ? 1 : 0) | (a.fakeq ? 2 : 0) | (a.f16 ? 4 : 0);
+    switch (sel) {
+        case 1: quantize_kernel<FMT, true, false, false><<<grid, kQThreads, 0, st>>>(a); break;
+        case 2: quantize_kernel<FMT, false, true, false><<<grid, kQThreads, 0, st>>>(a); break;
+        case 3: quantize_kernel<FMT, true, true, false><<<grid, kQThreads, 0, st>>>(a); break;
+        case 4: quantize_kernel<FMT, false, false, true><<<grid, kQThreads, 0, st>>>(a); break;
+        case 5: quantize_kernel<FMT, true, false, true><<<grid, kQThreads, 0, st>>>(a); break;
+        case 6: quantize_kernel<FMT, false, true, true><<<grid, kQThreads, 0, st>>>(a); break;
+        default: quantize_kernel<FMT, true, true, true><<<grid, kQThreads, 0, st>>>(a); break;
+    }
+    return check_launch("quantize_kernel");
+}
+
+// NHWC tensor whose channel count is not the physical (padded) one: thread per output code.
+template <int FMT>
+__global__ void __launch_bounds__(256) quantize_pad_kernel(const float* __restrict__ x, size_t npix, int C, int Cp,
+                                                           float k_div, uint8_t* __restrict__ codes) {
+    const size_t total = npix * (size_t)Cp;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const size_t pix = i / (size_t)Cp;
+        const int c = (int)(i - pix * (size_t)Cp);
+        codes[i] = (c < C) ? (uint8_t)encode<FMT>(div_rn(x[pix * (size_t)C + c], k_div)) : (uint8_t)0;
+    }
+}
+
+// ---- de-quantize ------------------------------------------------------------------------------
+template <bool SFP33>
+__global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t* __restrict__ codes, size_t n,
+                                                         float* __restrict__ out) {
+    __shared__ uint32_t s_tab[16];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    const bool vec = (((uintptr_t)codes & 3u) | ((uintptr_t)out & 15u)) == 0;
+    const size_t n4 = vec ? n / 4 : 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+        const uint32_t w = reinterpret_cast<const uint32_t*>(codes)[i];
+        float4 o;
+        o.x = decode<SFP33>(w & 0xffu, s_tab);
+        o.y = decode<SFP33>((w >> 8) & 0xffu, s_tab);
+        o.z = decode<SFP33>((w >> 16) & 0xffu, s_tab);
+        o.w = decode<SFP33>(w >> 24, s_tab);
+        reinterpret_cast<float4*>(out)[i] = o;
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        out[i] = decode<SFP33>(codes[i], s_tab);
+}
+
+// ---- abs-max ------------------------------------------------------------------------------------
+// warp shuffles, then a block reduction in shared memory, then one atomicMax per CTA on the bit
+// pattern (non-negative floats order like unsigned integers).
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n,
+                                                     unsigned int* __restrict__ out) {
+    float m = 0.0f;
+    const bool vec = ((uintptr_t)x & 15u) == 0;
+    const size_t n4 = vec ? n / 4 : 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+        const float4 v = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+        m = fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < 8 ? s_m[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(out, __float_as_uint(m));
+    }
+}
+
+// ---- weight preparation ---------------------------------------------------------------------------
+// One thread per KRSC destination element (k, r, s, c_phys); weights are small (<= 2.4 M / layer).
+struct WPrepArgs {
+    const float* w;
+    long long so, sc, sr, ss;
+    int K, C, Cp, R, S;
+    size_t pitch;  // elements per output-channel row of the KRSC operand (>= R*S*Cp, multiple of 64)
+    float kw;
+    __half* w_f16;
+    uint8_t* w_codes;
+    float* w_fakeq;  // OIHW contiguous
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
+    __shared__ uint32_t s_tab[16];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    const size_t total = (size_t)a.K * a.pitch;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int k = (int)(i / a.pitch);
+        const size_t j = i - (size_t)k * a.pitch;
+        const int c = (int)(j % a.Cp);
+        const int rs = (int)(j / a.Cp);
+        uint32_t code = 0;
+        float fq = 0.0f;
+        if (c < a.C && rs < a.R * a.S) {
+            const int r = rs / a.S, s = rs - r * a.S;
+            const float x = a.w[k * a.so + c * a.sc + r * a.sr + s * a.ss];
+            const float v = div_rn(x, a.kw);
+            if (FMT < 0) {
+                fq = v;
+            } else {
+                code = encode<FMT < 0 ? 0 : FMT>(v);
+                fq = decode<FMT == SLFP_FMT_SFP33>(code, s_tab);
+            }
+            if (a.w_fakeq) a.w_fakeq[(((size_t)k * a.C + c) * a.R + r) * a.S + s] = fq;
+        }
+        if (a.w_f16) a.w_f16[i] = __float2half_rn(fq);
+        if (a.w_codes) a.w_codes[i] = (uint8_t)code;
+    }
+}
+
+}  // namespace slfp
+
+using namespace slfp;
+
+extern "C" int slfp_version(void) { return SLFP_B200_VERSION; }
+extern "C" const char* slfp_last_error(void) { return g_err; }
+
+extern "C" int slfp_quantize_f32(const float* x, size_t n, float k_div, int fmt, unsigned flags, uint8_t* codes,
+                                 float* fakeq, void* f16, slfp_stream_t stream) {
+    if (n == 0) return 0;
+    if (!x || (!codes && !fakeq && !f16)) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: null pointer");
+    if (fmt == SLFP_FMT_SFP44_OUT && codes)
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: SFP<4,4> layer-out has no 8-bit code");
+    QuantArgs a{x, n, k_div, codes, fakeq, (__half*)f16, (flags & SLFP_Q_LAYEROUT_ZERO_IS_ZERO) ? 1 : 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (fmt) {
+        case SLFP_FMT_SFP33: return launch_quantize<SLFP_FMT_SFP33>(a, st);
+        case SLFP_FMT_SLFP34_ACT: return launch_quantize<SLFP_FMT_SLFP34_ACT>(a, st);
+        case SLFP_FMT_SLFP34_WGT: return launch_quantize<SLFP_FMT_SLFP34_WGT>(a, st);
+        case SLFP_FMT_SFP44_OUT: return launch_quantize<SLFP_FMT_SFP44_OUT>(a, st);
+    }
+    return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: unknown format %d", fmt);
+}
+
+extern "C" int slfp_quantize_nhwc_f32(const float* x, size_t npix, int c, int c_phys, float k_div, int fmt,
+                                      uint8_t* codes, slfp_stream_t stream) {
+    if (npix == 0) return 0;
+    if (!x || !codes || c <= 0 || c_phys < c) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nhwc_f32: bad arguments");
+    if (c == c_phys) return slfp_quantize_f32(x, npix * (size_t)c, k_div, fmt, 0, codes, nullptr, nullptr, stream);
+    const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(npix * (size_t)c_phys, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (fmt) {
+        case SLFP_FMT_SFP33: quantize_pad_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, npix, c, c_phys, k_div, codes); break;
+        case SLFP_FMT_SLFP34_ACT: quantize_pad_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, k_div, codes); break;
+        case SLFP_FMT_SLFP34_WGT: quantize_pad_kernel<SLFP_FMT_SLFP34_WGT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, k_div, codes); break;
+        default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nhwc_f32: format %d has no codes", fmt);
+    }
+    return check_launch("quantize_pad_kernel");
+}
+
+extern "C" int slfp_dequantize(const uint8_t* codes, size_t n, int fmt, float* out, slfp_stream_t stream) {
+    if (n == 0) return 0;
+    if (!codes || !out) return set_error(SLFP_ERR_BAD_ARG, "slfp_dequantize: null pointer");
+    int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(n, 1024));
+    if (fmt == SLFP_FMT_SFP33)
+        dequantize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, n, out);
+    else if (fmt == SLFP_FMT_SLFP34_ACT || fmt == SLFP_FMT_SLFP34_WGT)
+        dequantize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, n, out);
+    else
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_dequantize: format %d has no codes", fmt);
+    return check_launch("dequantize_kernel");
+}
+
+extern "C" int slfp_absmax_f32(const float* x, size_t n, float* max_out, int init_zero, slfp_stream_t stream) {
+    if (!max_out) return set_error(SLFP_ERR_BAD_ARG, "slfp_absmax_f32: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (init_zero) {
+        cudaError_t e = cudaMemsetAsync(max_out, 0, sizeof(float), st);
+        if (e != cudaSuccess) return set_error((int)e, "slfp_absmax_f32: memset: %s", cudaGetErrorString(e));
+    }
+    if (n == 0) return 0;
+    if (!x) return set_error(SLFP_ERR_BAD_ARG, "slfp_absmax_f32: null input");
+    int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(n, 256 * 16));
+    absmax_kernel<<<grid, 256, 0, st>>>(x, n, reinterpret_cast<unsigned int*>(max_out));
+    return check_launch("absmax_kernel");
+}
+
+extern "C" size_t slfp_conv_wpitch(const SlfpConvDesc* d) {
+    if (!d) return 0;
+    const int cg = d->groups > 1 ? (d->c / d->groups) : d->c_phys;
+    size_t k = (size_t)d->r * d->s * cg;
+    return d->groups > 1 ? k : (k + 63) / 64 * 64;
+}
+
+extern "C" int slfp_prepare_weights(const SlfpConvDesc* d, const float* w, long long so, long long sc,
+                                    long long sr, long long ss, float kw, int wfmt, void* w_f16,
+                                    uint8_t* w_codes, float* w_fakeq, slfp_stream_t stream) {
+    if (!d || !w) return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights: null pointer");
+    WPrepArgs a;
+    a.w = w; a.so = so; a.sc = sc; a.sr = sr; a.ss = ss;
+    a.K = d->k; a.R = d->r; a.S = d->s;
+    if (d->groups > 1) { a.C = d->c / d->groups; a.Cp = a.C; }
+    else { a.C = d->c; a.Cp = d->c_phys; }
+    a.pitch = slfp_conv_wpitch(d);
+    a.kw = kw; a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
+    const size_t total = (size_t)a.K * a.pitch;
+    if (total == 0) return 0;
+    int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(total, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (wfmt) {
+        case SLFP_FMT_SFP33: wprep_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(a); break;
+        case SLFP_FMT_SLFP34_WGT: wprep_kernel<SLFP_FMT_SLFP34_WGT><<<grid, 256, 0, st>>>(a); break;
+        case SLFP_FMT_SLFP34_ACT: wprep_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(a); break;
+        case -1: wprep_kernel<-1><<<grid, 256, 0, st>>>(a); break;
+        default: return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights: bad weight format %d", wfmt);
+    }
+    return check_launch("wprep_kernel");
+}
+
+extern "C" int slfp_quantize_host_f32(const float* host_x, size_t n, float k_div, int fmt, uint8_t* host_codes,
+                                      float* host_fakeq) {
+    if (n == 0) return 0;
+    if (!host_x || (!host_codes && !host_fakeq)) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_host_f32: null");
+    float* dx = nullptr; uint8_t* dc = nullptr; float* dq = nullptr;
+    cudaStream_t st = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    int rc = 0;
+    if (e == cudaSuccess) e = cudaMalloc(&dx, n * 4);
+    if (e == cudaSuccess && host_codes) e = cudaMalloc(&dc, n);
+    if (e == cudaSuccess && host_fakeq) e = cudaMalloc(&dq, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx, host_x, n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = slfp_quantize_f32(dx, n, k_div, fmt, 0, dc, dq, nullptr, st);
+    if (e == cudaSuccess && rc == 0 && host_codes) e = cudaMemcpyAsync(host_codes, dc, n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == 0 && host_fakeq) e = cudaMemcpyAsync(host_fakeq, dq, n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dx); cudaFree(dc); cudaFree(dq);
+    if (st) cudaStreamDestroy(st);
+    if (e != cudaSuccess) return set_error((int)e, "slfp_quantize_host_f32: %s", cudaGetErrorString(e));
+    return rc;
+}

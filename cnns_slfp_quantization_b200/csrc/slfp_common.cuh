@@ -1,0 +1,181 @@
+// slfp_common.cuh -- shared device code of libslfp_b200: the SLFP / SFP number formats.
+//
+// encode<FMT>(v): float32 -> 8-bit storage code, bit-exact with the reference quantizers
+//   utils/sfp_quant.py:14-30,63-78 (SFP<3,3>), :80-96 (SLFP<3,4> activations),
+//   :32-47 (SLFP<3,4> weights).  The reference rounds with float32 log2/pow; here the same
+//   decision is taken in integer arithmetic on the IEEE-754 bit pattern (its log2f/powf results
+//   were characterised exhaustively, see tests/golden/make_golden.log), so the device libm never
+//   enters the result.
+// decode: code -> the exact float32 the reference's fake-quant tensor holds.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/slfp_b200.h"
+
+namespace slfp {
+
+constexpr uint32_t kBitsTiny = 0x2edbe6ffu;  // float32(1e-10)      sfp_quant.py:26,43,74,92
+constexpr uint32_t kBitsSat8 = 0x4175257au;  // float32(15.32165)   sfp_quant.py:46,95
+constexpr uint32_t kBits0625 = 0x3d800000u;
+constexpr uint32_t kBits0125 = 0x3e000000u;
+constexpr uint32_t kBits15 = 0x41700000u;
+constexpr uint32_t kBits248 = 0x43780000u;
+constexpr uint32_t kBitsInf = 0x7f800000u;
+constexpr uint32_t kCodeZero = 0, kCodeTiny = 1, kCodeSat = 2, kCodeNaN = 3;
+
+// float32(2^(j/16)): what the reference's pow(2, e + j/16) returns (make_golden.log).
+#define SLFP_POW2FRAC_TABLE                                                                       \
+    {0x3f800000u, 0x3f85aac3u, 0x3f8b95c2u, 0x3f91c3d3u, 0x3f9837f0u, 0x3f9ef532u, 0x3fa5fed7u,   \
+     0x3fad583fu, 0x3fb504f3u, 0x3fbd08a4u, 0x3fc5672au, 0x3fce248cu, 0x3fd744fdu, 0x3fe0ccdfu,   \
+     0x3feac0c7u, 0x3ff5257du}
+// first float32 mantissa pattern in [1,2) that quantize_weight(8) maps to log-code j = 1..16.
+#define SLFP_WGT_THRESH_TABLE                                                                     \
+    {0x3f82cd87u, 0x3f88980fu, 0x3f8ea43au, 0x3f94f4f0u, 0x3f9b8d3au, 0x3fa27043u, 0x3fa9a15bu,   \
+     0x3fb123f6u, 0x3fb8fbb0u, 0x3fc12c4du, 0x3fc9b9beu, 0x3fd2a81eu, 0x3fdbfbb8u, 0x3fe5b907u,   \
+     0x3fefe4bau, 0x3ffa83b3u}
+
+static __device__ __constant__ uint32_t c_pow2frac[16] = SLFP_POW2FRAC_TABLE;
+static const uint32_t h_pow2frac[16] = SLFP_POW2FRAC_TABLE;   // host copy (host-compiled checks)
+
+// bit casts / clz usable from host-compiled code too: the encode/decode logic below is compiled
+// for the host by tests/host_check.cu and swept against the oracle without a GPU.
+__host__ __device__ __forceinline__ uint32_t f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+__host__ __device__ __forceinline__ float u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+__host__ __device__ __forceinline__ int clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+
+// IEEE-754 round-to-nearest float32 division: `input / self.Ka` on the reference's CPU path is a
+// true division by float32(K) (not a multiply by the reciprocal); SURVEY.md section 8c.
+__host__ __device__ __forceinline__ float div_rn(float x, float k) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(x, k);
+#else
+    return x / k;
+#endif
+}
+
+// ---- encode ------------------------------------------------------------------------------------
+template <int FMT>
+__host__ __device__ __forceinline__ uint32_t encode(float v) {
+    constexpr uint32_t kThresh[16] = SLFP_WGT_THRESH_TABLE;
+    const uint32_t b = f2u(v);
+    const uint32_t a = b & 0x7fffffffu;
+    const uint32_t sg = (b >> 24) & 0x80u;
+    uint32_t u;
+    if (FMT == SLFP_FMT_SFP33) {
+        // round-half-even of 8*m at mantissa bit 20; the carry runs into the exponent field
+        const uint32_t r = a + 0x7ffffu + ((a >> 20) & 1u);
+        u = (r >> 20) - ((127u - 4u) << 3);
+        u = (a >= kBits15) ? 63u : u;                        // a >= 15 -> 15      (:29,:77)
+        u = (a < kBits0125) ? 8u : u;                        // [0.0625,0.125) -> 0.125
+    } else {
+        const uint32_t mant = a & 0x7fffffu;
+        uint32_t L;
+        if (FMT == SLFP_FMT_SLFP34_ACT) {
+            // m_q = rne(16 m)/16 (:88), then the log converter (:89): 0,1,3,4,...,15,15,16
+            uint32_t i = mant >> 19;
+            const uint32_t frac = mant & 0x7ffffu;
+            i += (frac > 0x40000u || (frac == 0x40000u && (i & 1u))) ? 1u : 0u;
+            L = i + ((i >= 2u && i <= 14u) ? 1u : 0u);
+        } else {
+            // L = round(16 log2 m) (:40) == number of thresholds <= m (16 immediate compares)
+            const uint32_t mb = mant | 0x3f800000u;
+            L = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) L += (mb >= kThresh[j]) ? 1u : 0u;
+        }
+        u = (((a >> 23) - (127u - 4u)) << 4) + L;            // L == 16 carries into E
+        u = (a > kBitsSat8) ? kCodeSat : u;                  // a > 15.32165 -> literal (:46,:95)
+        u = (a < kBits0125) ? 16u : u;
+    }
+    u = (a < kBits0625) ? kCodeTiny : u;                     // a < 0.0625 -> 1e-10
+    u |= sg;
+    u = (a == 0u) ? kCodeZero : u;                           // sign(+-0) = 0
+    u = (a > kBitsInf) ? kCodeNaN : u;
+    return u;
+}
+
+__host__ __device__ __forceinline__ uint32_t encode_rt(float v, int fmt) {
+    if (fmt == SLFP_FMT_SFP33) return encode<SLFP_FMT_SFP33>(v);
+    if (fmt == SLFP_FMT_SLFP34_ACT) return encode<SLFP_FMT_SLFP34_ACT>(v);
+    return encode<SLFP_FMT_SLFP34_WGT>(v);
+}
+
+// quantize_layerout, SFP<4,4> (sfp_quant.py:111-126).  Lines 122-123 of the reference use '^'
+// (XOR), so there is no low clamp and exact 0 gives NaN; zero_is_zero selects the intended value.
+__host__ __device__ __forceinline__ float layerout_quantize(float v, bool zero_is_zero) {
+    const uint32_t b = f2u(v);
+    const uint32_t a = b & 0x7fffffffu, s = b & 0x80000000u;
+    uint32_t r;
+    if (a >= 0x00800000u) {
+        r = (a + 0x3ffffu + ((a >> 19) & 1u)) & ~0x7ffffu;
+    } else {                                                  // denormal input
+        const int sh = (31 - clz32(a | 1u)) - 4;
+        r = a;
+        if (sh > 0) r = (a + ((1u << (sh - 1)) - 1u) + ((a >> sh) & 1u)) & ~((1u << sh) - 1u);
+    }
+    r = (a >= kBits248) ? kBits248 : r;
+    r |= s;
+    if (a == 0u) r = zero_is_zero ? 0u : 0xffc00000u;
+    if (a > kBitsInf) r = 0x7fc00000u;
+    return u2f(r);
+}
+
+// ---- decode ------------------------------------------------------------------------------------
+// tab: the 16-entry pow2frac table (shared or constant memory)
+template <bool SFP33>
+__host__ __device__ __forceinline__ float decode(uint32_t code, const uint32_t* __restrict__ tab) {
+    const uint32_t s = (code & 0x80u) << 24;
+    const uint32_t u = code & 0x7fu;
+    uint32_t r;
+    if (SFP33) {
+        r = (((u >> 3) + 123u) << 23) | ((u & 7u) << 20);
+        r = (u < 8u) ? 0x7fc00000u : r;
+    } else {
+        r = tab[u & 15u] + (((u >> 4) - 4u) << 23);
+        r = (u < 16u) ? 0x7fc00000u : r;
+        r = (u == kCodeSat) ? kBitsSat8 : r;
+    }
+    r = (u == kCodeTiny) ? kBitsTiny : r;
+    r |= s;
+    r = (u == kCodeZero) ? 0u : r;
+    r = (u == kCodeNaN) ? 0x7fc00000u : r;
+    return u2f(r);
+}
+
+// Operand value fed to the tensor cores for a code: RN_fp16(decode(code)).  +-1e-10 underflows to
+// +-0 and the saturation literal rounds to the same half as the top grid value.
+template <bool SFP33>
+__device__ __forceinline__ uint16_t decode_f16_bits(uint32_t code, const uint32_t* __restrict__ tab) {
+    const float f = decode<SFP33>(code, tab);
+    return __half_as_ushort(__float2half_rn(f));
+}
+
+// ---- host-side error plumbing ---------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+int num_sms();
+
+static inline __host__ __device__ size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
+
+}  // namespace slfp

@@ -1,0 +1,259 @@
+"""Drop-in for the reference's utils/conv2d_func.py: the class factories conv2d_Q (:8-26),
+conv2d_Q_bias (:28-48) and linear_Q (:50-66) with the reference's constructor order
+(in, out, kernel, Kw, Ka, stride, ...) and attributes (.q_bit .Kw .Ka .quantize_weight
+.quantize_act, and after a forward .input_q .weight_q .output).
+
+forward(input) computes   F.conv2d(qa(input/Ka), qw(weight/Kw), bias/Ka/Kw) * Ka * Kw
+as three launches of hand-written sm_100a kernels through the C ABI (include/slfp_b200.h):
+  1. fused pre-scale + quantize of the activations into 8-bit NHWC codes   (csrc/quantize.cu)
+  2. fused pre-scale + quantize + KRSC re-layout of the weights            (csrc/quantize.cu)
+  3. implicit-GEMM convolution on tcgen05 tensor cores with the post-scale and bias in the
+     epilogue (csrc/conv_igemm_sm100.cu), or the depthwise / grouped stencil (csrc/conv_direct.cu)
+Backward is the straight-through estimator of the reference (utils/sfp_quant.py:50-53): dgrad /
+wgrad on the saved 8-bit codes with the constant scale factors fused (csrc/conv_direct.cu).
+
+The returned tensors are channels-last in memory (NCHW logical shape), so BatchNorm / ReLU /
+pooling between quantized layers keep running on the NHWC layout without transposes.
+Star-import leaks torch / nn / F / np exactly like the reference module does.
+"""
+import ctypes as _ctypes
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import numpy as np
+from .sfp_quant import *
+
+from .. import _native as _nv
+
+
+def _ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def _k32(K):
+    """float32 value the reference's arithmetic uses for a scale (K is a 0-dim float64 tensor)."""
+    return float(np.float32(float(K)))
+
+
+class _ConvCfg:
+    __slots__ = ("q_bit", "ka", "kw", "stride", "padding", "dilation", "groups", "post_a", "post_b", "keep")
+
+    def __init__(self, q_bit, ka, kw, stride, padding, dilation, groups, post_a, post_b, keep):
+        self.q_bit, self.ka, self.kw = q_bit, ka, kw
+        self.stride, self.padding, self.dilation, self.groups = stride, padding, dilation, groups
+        self.post_a, self.post_b, self.keep = post_a, post_b, keep
+
+
+class _QConvNHWC(torch.autograd.Function):
+    """x: [N,H,W,C] float32 contiguous; weight: [K, C/groups, R, S] (any strides); bias_q: [K] or None.
+    Returns y: [N,Ho,Wo,K] float32 contiguous."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias_q, cfg):
+        lib = _nv.lib()
+        _nv.require_cuda(x, "Conv2d_Q / Linear_Q input")
+        _nv.require_cuda(weight, "Conv2d_Q / Linear_Q weight")
+        x = x.detach().contiguous()
+        N, H, W, C = x.shape
+        K, Cg, R, S = weight.shape
+        groups = cfg.groups
+        if Cg * groups != C:
+            raise RuntimeError(f"Conv2d_Q: weight {tuple(weight.shape)} does not match input channels {C} (groups={groups})")
+        dense = groups == 1
+        Cp = (4 if C <= 4 else _ceil_to(C, 16)) if dense else _ceil_to(C, 4)
+        afmt, wfmt = _nv.fmt_for(cfg.q_bit, "act"), _nv.fmt_for(cfg.q_bit, "weight")
+        d = _nv.SlfpConvDesc(N, H, W, C, Cp, K, R, S, cfg.stride[0], cfg.stride[1], cfg.padding[0], cfg.padding[1],
+                             cfg.dilation[0], cfg.dilation[1], groups, afmt)
+        Ho = (H + 2 * cfg.padding[0] - cfg.dilation[0] * (R - 1) - 1) // cfg.stride[0] + 1
+        Wo = (W + 2 * cfg.padding[1] - cfg.dilation[1] * (S - 1) - 1) // cfg.stride[1] + 1
+        if Ho <= 0 or Wo <= 0:
+            raise RuntimeError("Conv2d_Q: output size is too small")
+        st = _nv.stream()
+        # 1. activations: x / Ka -> 8-bit codes (NHWC, channel-padded)
+        x_codes = torch.empty((N, H, W, Cp), dtype=torch.uint8, device=x.device)
+        _nv.check(lib.slfp_quantize_nhwc_f32(x.data_ptr(), N * H * W, C, Cp, cfg.ka, afmt, x_codes.data_ptr(), st))
+        # 2. weights: w / Kw -> codes (+ the float16 tensor-core operand), KRSC
+        pitch = lib.slfp_conv_wpitch(ctypes_byref(d))
+        w_codes = torch.empty((K * pitch,), dtype=torch.uint8, device=x.device)
+        w_f16 = torch.empty((K * pitch,), dtype=torch.float16, device=x.device) if dense else None
+        so, sc, sr, ss = weight.stride()
+        _nv.check(lib.slfp_prepare_weights(ctypes_byref(d), weight.data_ptr(), so, sc, sr, ss, cfg.kw, wfmt,
+                                           _nv.ptr(w_f16), w_codes.data_ptr(), None, st))
+        # 3. convolution with the reference's post-scale (and bias) in the epilogue
+        y = torch.empty((N, Ho, Wo, K), dtype=torch.float32, device=x.device)
+        epi = _nv.SlfpEpilogue()
+        epi.bias_q = _nv.ptr(bias_q.detach().contiguous()) if bias_q is not None else None
+        epi.post_a, epi.post_b = cfg.post_a, cfg.post_b
+        epi.y_f32 = y.data_ptr()
+        _nv.check(lib.slfp_conv2d_fwd(ctypes_byref(d), x_codes.data_ptr(), (w_f16 if dense else w_codes).data_ptr(),
+                                      ctypes_byref(epi), st))
+        ctx.save_for_backward(x_codes, w_codes)
+        ctx.cfg, ctx.desc, ctx.wfmt = cfg, d, wfmt
+        ctx.wshape, ctx.has_bias = tuple(weight.shape), bias_q is not None
+        if cfg.keep is not None:                      # calibration taps read the codes lazily
+            cfg.keep["x_codes"], cfg.keep["w_codes"] = x_codes, w_codes
+            cfg.keep["meta"] = (N, H, W, C, Cp, K, Cg, R, S, pitch, afmt, wfmt, dense)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _nv.lib()
+        x_codes, w_codes = ctx.saved_tensors
+        cfg, d = ctx.cfg, ctx.desc
+        gy = gy.contiguous()
+        K, Cg, R, S = ctx.wshape
+        need_x, need_w, _, _ = ctx.needs_input_grad
+        dx = torch.empty((d.n, d.h, d.w, d.c), dtype=torch.float32, device=gy.device) if need_x else None
+        dw = torch.empty(ctx.wshape, dtype=torch.float32, device=gy.device) if need_w else None
+        db = torch.empty((K,), dtype=torch.float32, device=gy.device) if ctx.has_bias else None
+        so, sc, sr, ss = (dw.stride() if dw is not None else (0, 0, 0, 0))
+        _nv.check(lib.slfp_conv2d_bwd(ctypes_byref(d), gy.data_ptr(), x_codes.data_ptr(), w_codes.data_ptr(), ctx.wfmt,
+                                      cfg.ka, cfg.kw, _nv.ptr(dx), _nv.ptr(dw), so, sc, sr, ss,
+                                      _nv.ptr(db), _nv.stream()))
+        if db is not None:                             # y = (acc + bias_q) * post_a * post_b
+            db = (db * cfg.post_b) * cfg.post_a
+        return dx, dw, db, None
+
+
+def ctypes_byref(obj):
+    return _ctypes.byref(obj)
+
+
+def _dequant_tap(keep, which):
+    """Materialise the reference's `input_q` / `weight_q` fake-quant tensors from the kept codes."""
+    if not keep or "meta" not in keep:
+        raise AttributeError(f"'{which}' is only available after a forward pass")
+    lib = _nv.lib()
+    N, H, W, C, Cp, K, Cg, R, S, pitch, afmt, wfmt, dense = keep["meta"]
+    lead = keep.get("lead")                     # Linear_Q: leading shape of the 2-D+ input
+    if which == "input_q":
+        codes = keep["x_codes"]
+        out = torch.empty(codes.shape, dtype=torch.float32, device=codes.device)
+        _nv.check(lib.slfp_dequantize(codes.data_ptr(), codes.numel(), afmt, out.data_ptr(), _nv.stream()))
+        if lead is not None:
+            return out[..., :C].reshape(*lead, C)
+        return out[..., :C].permute(0, 3, 1, 2)
+    codes = keep["w_codes"]
+    out = torch.empty(codes.shape, dtype=torch.float32, device=codes.device)
+    _nv.check(lib.slfp_dequantize(codes.data_ptr(), codes.numel(), wfmt, out.data_ptr(), _nv.stream()))
+    cw = Cp if dense else Cg
+    wq = out.view(K, pitch)[:, :R * S * cw].reshape(K, R, S, cw)[..., :Cg].permute(0, 3, 1, 2)
+    return wq.reshape(K, Cg) if lead is not None else wq
+
+
+class _QuantTapsMixin:
+    """`.input_q` / `.weight_q`: the tensors the reference keeps alive after every forward (read by
+    the calibration taps of the nets, e.g. nets_cifar/vgg16.py:136-182).  Here they are decoded on
+    demand from the 8-bit codes the last forward produced."""
+
+    @property
+    def input_q(self):
+        eager = self.__dict__.get("_eager_input_q")
+        return eager if eager is not None else _dequant_tap(self.__dict__.get("_keep"), "input_q")
+
+    @input_q.setter
+    def input_q(self, v):
+        self.__dict__["_eager_input_q"] = v
+
+    @property
+    def weight_q(self):
+        eager = self.__dict__.get("_eager_weight_q")
+        return eager if eager is not None else _dequant_tap(self.__dict__.get("_keep"), "weight_q")
+
+    @weight_q.setter
+    def weight_q(self, v):
+        self.__dict__["_eager_weight_q"] = v
+
+
+def _conv_forward(self, input, bias_q):
+    if self.q_bit == 32:
+        # identity quantizers: the reference's own float32 expression (conv2d_func.py:21-24)
+        self.input_q = self.quantize_act(input / self.Ka)
+        self.weight_q = self.quantize_weight(self.weight / self.Kw)
+        return F.conv2d(self.input_q, self.weight_q, bias_q, self.stride, self.padding, self.dilation,
+                        self.groups) * self.Ka * self.Kw
+    if self.q_bit not in (7, 8):
+        raise UnboundLocalError("cannot access local variable 'act_q' where it is not associated with a value")
+    if isinstance(self.padding, str) or self.padding_mode != "zeros":
+        raise NotImplementedError("Conv2d_Q: only numeric zero padding is supported")
+    if input.dim() != 4:
+        raise RuntimeError("Conv2d_Q: expected a 4-D NCHW input")
+    self.__dict__["_eager_input_q"] = self.__dict__["_eager_weight_q"] = None
+    keep = self.__dict__.setdefault("_keep", {})
+    ka, kw = _k32(self.Ka), _k32(self.Kw)
+    cfg = _ConvCfg(self.q_bit, ka, kw, tuple(self.stride), tuple(self.padding), tuple(self.dilation), self.groups,
+                   ka, kw, keep)
+    y = _QConvNHWC.apply(input.permute(0, 2, 3, 1), self.weight, bias_q, cfg)
+    return y.permute(0, 3, 1, 2)
+
+
+def conv2d_Q(q_bit, Kw, Ka):
+    """utils/conv2d_func.py:8-26."""
+    class Conv2d_Q(_QuantTapsMixin, nn.Conv2d):
+        def __init__(self, in_channels, out_channels, kernel_size, Kw=Kw, Ka=Ka,
+                     stride=1, padding=0, dilation=1, groups=1, bias=False):
+            super(Conv2d_Q, self).__init__(in_channels, out_channels, kernel_size, stride,
+                                           padding, dilation, groups, bias)
+            self.q_bit = q_bit
+            self.quantize_weight = weight_quantize_func(q_bit=q_bit)
+            self.quantize_act = act_quantize_func(q_bit=q_bit)
+            self.Kw = torch.tensor(Kw)
+            self.Ka = torch.tensor(Ka)
+
+        def forward(self, input, order=None):
+            # the reference passes self.bias straight into F.conv2d (no /Ka/Kw) in this variant (:23)
+            self.output = _conv_forward(self, input, self.bias)
+            return self.output
+    return Conv2d_Q
+
+
+def conv2d_Q_bias(q_bit, Kw, Ka):
+    """utils/conv2d_func.py:28-48."""
+    class Conv2d_Q(_QuantTapsMixin, nn.Conv2d):
+        def __init__(self, in_channels, out_channels, kernel_size, Kw=Kw, Ka=Ka, stride=1, padding=0, dilation=1,
+                     groups=1, bias=True):
+            super(Conv2d_Q, self).__init__(in_channels, out_channels, kernel_size, stride,
+                                           padding, dilation, groups, bias)
+            self.q_bit = q_bit
+            self.quantize_weight = weight_quantize_func(q_bit=q_bit)
+            self.quantize_act = act_quantize_func(q_bit=q_bit)
+            self.Kw = torch.tensor(Kw)
+            self.Ka = torch.tensor(Ka)
+
+        def forward(self, input, order=None):
+            self.bias_q = self.bias / self.Ka / self.Kw                    # (:44)
+            self.output = _conv_forward(self, input, self.bias_q)
+            return self.output
+    return Conv2d_Q
+
+
+def linear_Q(q_bit, Kw, Ka):
+    """utils/conv2d_func.py:50-66: F.linear(qa(x/Ka), qw(W/Kw), bias/Kw/Ka) * Kw * Ka."""
+    class Linear_Q(_QuantTapsMixin, nn.Linear):
+        def __init__(self, in_features, out_features, Kw=Kw, Ka=Ka, bias=True):
+            super(Linear_Q, self).__init__(in_features, out_features, bias)
+            self.q_bit = q_bit
+            self.quantize_weight = weight_quantize_func(q_bit=q_bit)
+            self.quantize_act = act_quantize_func(q_bit=q_bit)
+            self.Kw = torch.tensor(Kw)
+            self.Ka = torch.tensor(Ka)
+
+        def forward(self, input):
+            self.bias_q = self.bias / self.Kw / self.Ka                    # (:63)
+            if self.q_bit == 32:
+                self.input_q = self.quantize_act(input / self.Ka)
+                self.weight_q = self.quantize_weight(self.weight / self.Kw)
+                return F.linear(self.input_q, self.weight_q, self.bias_q) * self.Kw * self.Ka
+            if self.q_bit not in (7, 8):
+                raise UnboundLocalError("cannot access local variable 'act_q' where it is not associated with a value")
+            self.__dict__["_eager_input_q"] = self.__dict__["_eager_weight_q"] = None
+            keep = self.__dict__.setdefault("_keep", {})
+            ka, kw = _k32(self.Ka), _k32(self.Kw)
+            cfg = _ConvCfg(self.q_bit, ka, kw, (1, 1), (0, 0), (1, 1), 1, kw, ka, keep)
+            lead = tuple(input.shape[:-1])
+            keep["lead"] = lead
+            x = input.reshape(-1, 1, 1, self.in_features)
+            y = _QConvNHWC.apply(x, self.weight.view(self.out_features, self.in_features, 1, 1), self.bias_q, cfg)
+            return y.reshape(*lead, self.out_features)
+    return Linear_Q

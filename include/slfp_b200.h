@@ -1,0 +1,196 @@
+/*
+ * slfp_b200.h -- C ABI of libslfp_b200.so: the SLFP/SFP quantized-convolution hot path of
+ * happyxtt/CNNs_SLFP_quantization, as hand-written sm_100a (B200) CUDA kernels.
+ *
+ * This is the drop-in boundary.  The reference has no native layer: its hot
+ * path is Python (utils/sfp_quant.py, utils/conv2d_func.py, utils/activation_func.py,
+ * utils/optimizer.py) on top of ATen/cuDNN.  Each entry point below names the reference
+ * interface (file:line under the reference root) whose arithmetic it replaces.  The Python
+ * mirror of the reference's callables (cnns_slfp_quantization_b200/utils/...) binds these
+ * symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never allocates device memory,
+ *     never synchronises (the *_host helpers in the "host buffer" section excepted).
+ *   - return value: 0 = ok, otherwise a cudaError_t value or one of the SLFP_ERR_* codes;
+ *     slfp_last_error() returns a thread-local message for the last failing call.
+ *   - activations are NHWC ("channels last"), weights are KRSC (out-ch, filter row, filter col,
+ *     in-ch).  8-bit storage codes are defined in the table below; they are ours (the reference
+ *     only ever materialises fake-quant float32) and decode bit-exactly to the reference's values.
+ *
+ * 8-bit codes:  bit 7 = sign, low 7 bits u
+ *     SLFP<3,4> (q_bit 8): u = E*16 + M, E = 1..7, M = 0..15   ->  2^(E-4 + M/16)
+ *     SFP<3,3>  (q_bit 7): u = E*8  + m, E = 1..7, m = 0..7    ->  (1 + m/8) * 2^(E-4)
+ *     escapes: u = 0 -> 0.0 ; u = 1 -> +-1e-10 ; u = 2 -> +-15.32165 (SLFP saturation literal) ;
+ *              u = 3 -> NaN
+ */
+#ifndef SLFP_B200_H_
+#define SLFP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLFP_B200_VERSION 100
+
+typedef void *slfp_stream_t; /* cudaStream_t */
+
+enum {
+    SLFP_FMT_SFP33 = 0,      /* utils/sfp_quant.py:14-30, 63-78   q_bit 7, weights and activations */
+    SLFP_FMT_SLFP34_ACT = 1, /* utils/sfp_quant.py:80-96          q_bit 8 activations              */
+    SLFP_FMT_SLFP34_WGT = 2, /* utils/sfp_quant.py:32-47          q_bit 8 weights                  */
+    SLFP_FMT_SFP44_OUT = 3   /* utils/sfp_quant.py:105-127        layer-out quantizer (fp32 only)  */
+};
+
+enum { SLFP_ACT_STL = 0, SLFP_ACT_SWISH = 1, SLFP_ACT_SIGMOID = 2 };
+enum { SLFP_SGD_NORMAL = 0, SLFP_SGD_DSGD = 1, SLFP_SGD_SSGD = 2 };
+
+enum {
+    SLFP_ERR_BAD_ARG = 10001,
+    SLFP_ERR_UNSUPPORTED = 10002,
+    SLFP_ERR_NO_DEVICE = 10003,
+    SLFP_ERR_DRIVER = 10004
+};
+
+/* flags of slfp_quantize_f32 */
+#define SLFP_Q_LAYEROUT_ZERO_IS_ZERO 1u /* SFP44_OUT: map exact 0 to 0 instead of the reference's NaN */
+
+int slfp_version(void);
+const char *slfp_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Quantizers.  Replaces quantize_weight(k)/quantize_act(k)/quantize_layerout(k).forward
+ * (utils/sfp_quant.py:7-48, 56-97, 105-127) together with the pre-scale division
+ * `input/self.Ka`, `self.weight/self.Kw` of utils/conv2d_func.py:21-22.
+ *   y = x / k_div (IEEE float32 division), then round onto the format's grid.
+ *   codes (n bytes) and/or fakeq (n floats) and/or f16 (n halves) may be NULL; at least one is not.
+ * One fused pass: 4 B read + (1 | 4 | 2) B written per element.
+ * ------------------------------------------------------------------------------------------- */
+int slfp_quantize_f32(const float *x, size_t n, float k_div, int fmt, unsigned flags,
+                      uint8_t *codes, float *fakeq, void *f16, slfp_stream_t stream);
+
+/* Same quantizer for an NHWC activation tensor whose code tensor has a padded channel count
+ * (c_phys >= c; pad channels receive code 0 = exact zero): npix pixels of c floats -> npix * c_phys
+ * codes.  This is the layout slfp_conv2d_fwd consumes. */
+int slfp_quantize_nhwc_f32(const float *x, size_t npix, int c, int c_phys, float k_div, int fmt,
+                           uint8_t *codes, slfp_stream_t stream);
+
+/* codes -> float32 (exactly the value the reference's fake-quant tensor would hold) */
+int slfp_dequantize(const uint8_t *codes, size_t n, int fmt, float *out, slfp_stream_t stream);
+
+/* max(|x|) into *max_out (device float).  Replaces torch.max(torch.abs(torch.cat(list))) of the
+ * calibration pass, cifar100_train_eval.py:261-271.  The kernel folds its result into *max_out
+ * with an atomic max, so a caller accumulating over batches zeroes it once; init_zero != 0 makes
+ * the call zero it first. */
+int slfp_absmax_f32(const float *x, size_t n, float *max_out, int init_zero, slfp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution.  Replaces Conv2d_Q.forward, utils/conv2d_func.py:20-25 (no bias) and :41-47
+ * (bias), and Linear_Q.forward :60-65 (a linear layer is the 1x1 case with h = w = 1).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n, h, w, c;       /* input  NHWC; c = logical input channels                          */
+    int c_phys;           /* physical (padded) channel count of the code tensor, multiple of 16
+                             (4 allowed when c <= 4: the 3-channel stem)                        */
+    int k;                /* output channels                                                   */
+    int r, s;             /* filter height / width                                             */
+    int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+    int groups;           /* 1 = dense implicit GEMM (tcgen05); c == k == groups = depthwise     */
+    int fmt;              /* SLFP_FMT_SLFP34_ACT (q_bit 8) or SLFP_FMT_SFP33 (q_bit 7): code layout
+                             of the activation codes                                            */
+} SlfpConvDesc;
+
+typedef struct {
+    const float *bias_q;   /* [k] added to the accumulator BEFORE the post-scale (bias/Ka/Kw,
+                              conv2d_func.py:44), or NULL                                        */
+    float post_a, post_b;  /* y = ((acc + bias_q) * post_a) * post_b   (Ka then Kw, :24 / :46)   */
+    const float *ch_scale; /* optional per-channel affine applied after the post-scale (an eval */
+    const float *ch_shift; /* BatchNorm folded by the caller): y = y*ch_scale[k] + ch_shift[k]    */
+    const void *residual;  /* optional NHWC tensor added after the affine, or NULL               */
+    int residual_f16;      /* 0: residual is float32, 1: float16                                 */
+    int relu;              /* apply max(y, 0) last                                               */
+    /* outputs: any subset, all NHWC with k channels (codes: k_phys_out channels, zero padded)  */
+    float *y_f32;
+    void *y_f16;
+    uint8_t *y_codes;      /* quantize-on-store for the next layer: encode(y / next_k_div)       */
+    float next_k_div;
+    int next_fmt;
+    int k_phys_out;        /* physical channel count of y_codes (>= k, multiple of 16)           */
+    uint8_t *y_codes2;     /* second consumer with a different Ka (e.g. a downsample branch)     */
+    float next_k_div2;
+} SlfpEpilogue;
+
+/* Weight preparation: replaces `self.quantize_weight(self.weight/self.Kw)` (conv2d_func.py:22):
+ * quantizes the OIHW float32 parameter, and emits any of
+ *   w_f16   : KRSC float16 operand for the tensor-core path, row pitch slfp_conv_wpitch(desc) halves
+ *   w_codes : KRSC 8-bit codes (same pitch, in bytes)
+ *   w_fakeq : OIHW float32 fake-quant tensor (the reference's `weight_q` calibration tap)
+ * w_stride_{o,c,r,s}: element strides of the input parameter (so channels_last params work). */
+size_t slfp_conv_wpitch(const SlfpConvDesc *desc);
+int slfp_prepare_weights(const SlfpConvDesc *desc, const float *w, long long w_stride_o,
+                         long long w_stride_c, long long w_stride_r, long long w_stride_s,
+                         float kw, int wfmt, void *w_f16, uint8_t *w_codes, float *w_fakeq,
+                         slfp_stream_t stream);
+
+/* Forward on codes.  x_codes NHWC [n,h,w,c_phys]; w_f16 from slfp_prepare_weights (dense) or
+ * w_f32 KRSC float32 for the depthwise / grouped stencil path. */
+int slfp_conv2d_fwd(const SlfpConvDesc *desc, const uint8_t *x_codes, const void *w_prepared,
+                    const SlfpEpilogue *epi, slfp_stream_t stream);
+
+/* Backward of Conv2d_Q.forward with the identity STE (utils/sfp_quant.py:50-53, 99-102):
+ *   dx = dgrad(gy*Ka*Kw, w_q)/Ka      dw = wgrad(gy*Ka*Kw, x_q)/Kw      db = sum(gy)
+ * gy NHWC float32 [n,ho,wo,k]; x_codes NHWC; w_codes KRSC (pitch slfp_conv_wpitch);
+ * dx NHWC float32 [n,h,w,c]; dw float32 with the given element strides; any output may be NULL. */
+int slfp_conv2d_bwd(const SlfpConvDesc *desc, const float *gy, const uint8_t *x_codes,
+                    const uint8_t *w_codes, int wfmt, float ka, float kw, float *dx, float *dw,
+                    long long dw_stride_o, long long dw_stride_c, long long dw_stride_r,
+                    long long dw_stride_s, float *db, slfp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Activations: STLFunction / STL, Swish, Sigmoid (utils/activation_func.py:6-36).
+ * bwd: STL clips the incoming gradient to [-1,1] by its own magnitude (:16); Swish / Sigmoid are
+ * the autograd derivatives and need x.
+ * ------------------------------------------------------------------------------------------- */
+int slfp_act_fwd(const float *x, size_t n, int kind, float *y, slfp_stream_t stream);
+int slfp_act_bwd(const float *x, const float *gy, size_t n, int kind, float *gx, slfp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Revised SGD: DSGD.step / SSGD.step / NormalSGD.step (utils/optimizer.py:30-73, 98-132,
+ * 154-190), one fused multi-tensor launch for a whole parameter group.
+ * host_* arrays have n_tensors entries and are read before the call returns.  grad is updated in
+ * place by the weight-decay term like the reference (:46).  Hyper-parameters are doubles (Python
+ * floats) and are rounded to float32 the way the reference's tensor-scalar ops round them:
+ * float32(-lr), float32(momentum), float32(1 - dampening), float32(weight_decay).  q_fmt: SLFP_FMT_SLFP34_WGT,
+ * SLFP_FMT_SFP33, or -1 for q_bit 32 (identity quantizer).
+ * ------------------------------------------------------------------------------------------- */
+int slfp_sgd_step(int n_tensors, float *const *host_params, float *const *host_grads,
+                  float *const *host_bufs, const size_t *host_sizes, int mode, int q_fmt,
+                  double lr, double momentum, double dampening, double weight_decay, int nesterov,
+                  int first_step, slfp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small NHWC helpers used between quantized layers by the fused eval pipeline.
+ * ------------------------------------------------------------------------------------------- */
+/* 2-D max pooling directly on activation codes (the quantizer is monotone, so
+ * quantize(maxpool(x)) == maxpool(quantize(x)) bit for bit).  pad positions never win. */
+int slfp_maxpool_codes(const uint8_t *x, int n, int h, int w, int c_phys, int kh, int kw_,
+                       int stride, int pad, uint8_t *y, slfp_stream_t stream);
+/* global average pool NHWC float16/float32 -> [n, c] float32 */
+int slfp_avgpool_nhwc(const void *x, int is_f16, int n, int hw, int c, float *y, slfp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry (the end-to-end path a non-torch caller binds): quantizes a HOST
+ * float32 buffer into HOST codes through a device round trip on an internal stream and
+ * synchronises.  Used by the C smoke program and by bench.py's e2e leg for the quantizer metric.
+ * ------------------------------------------------------------------------------------------- */
+int slfp_quantize_host_f32(const float *host_x, size_t n, float k_div, int fmt,
+                           uint8_t *host_codes, float *host_fakeq);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLFP_B200_H_ */

@@ -186,7 +186,7 @@ def sgd_step(p, grad, buf, mode, q_bit, lr, momentum=0.0, dampening=0.0, weight_
         buf = np.zeros_like(p)
     lib().slfp_oracle_sgd_step(_p(p, ctypes.c_float), _p(grad, ctypes.c_float), _p(buf, ctypes.c_float),
                                ctypes.c_size_t(p.size), ctypes.c_int(mode), ctypes.c_int(qfmt),
-                               ctypes.c_float(lr), ctypes.c_float(momentum), ctypes.c_float(dampening),
-                               ctypes.c_float(weight_decay), ctypes.c_int(1 if nesterov else 0),
+                               ctypes.c_double(lr), ctypes.c_double(momentum), ctypes.c_double(dampening),
+                               ctypes.c_double(weight_decay), ctypes.c_int(1 if nesterov else 0),
                                ctypes.c_int(1 if first_step else 0))
     return buf

@@ -1,0 +1,134 @@
+"""GPU: the fused quantizer / de-quantizer / abs-max kernels through the C ABI, bit-exact against the
+oracle and against the reference-generated fixtures."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits, same_bits
+
+pytestmark = pytest.mark.gpu
+
+FMTS = {"sfp33_act": 0, "slfp34_act": 1, "slfp34_wgt": 2, "sfp44_out": 3}
+
+
+@pytest.mark.parametrize("name", list(FMTS))
+def test_golden_samples_bit_exact(g_quant, name):
+    from gpu_util import quantize_gpu
+    codes, fq, _ = quantize_gpu(g_quant["x"], FMTS[name])
+    assert same_bits(g_quant[name], fq).all()
+
+
+@pytest.mark.parametrize("name", ["slfp34_act", "slfp34_wgt", "sfp33_act"])
+def test_prescale_is_ieee_division(g_quant, name):
+    from gpu_util import quantize_gpu
+    for i, k in enumerate(g_quant["prescale_k"]):
+        _, fq, _ = quantize_gpu(g_quant["prescale_x"], FMTS[name], kdiv=k)
+        assert same_bits(g_quant["scaled_" + name][i], fq).all()
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+def test_exhaustive_mantissas_vs_oracle(orc, fmt):
+    """All 2^23 mantissas at several exponents (vector path + ragged tail), codes and fake-quant."""
+    from gpu_util import quantize_gpu
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    for e in ([-5, -4, -1, 3] + ([-127, 7] if fmt == 3 else [])):
+        x = (mant | np.uint32(max(e + 127, 0) << 23)).view(np.float32)[: (1 << 23) - 5]   # ragged length
+        if e == -1:
+            x = -x
+        codes, fq, f16 = quantize_gpu(x, fmt, want_f16=True)
+        oc, oq = orc.quantize(x, fmt)
+        assert same_bits(oq, fq).all(), (fmt, e)
+        if fmt != 3:
+            assert (codes == oc).all(), (fmt, e)
+        assert (f16 == oq.astype(np.float16)).all() or np.isnan(oq).any()
+
+
+def test_sizes_alignment_and_empty(orc):
+    from cnns_slfp_quantization_b200 import _native as nv
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 3, 4095, 4096, 4097, 12289, 1 << 20):
+        x = (rng.standard_normal(n + 3) * 4).astype(np.float32)
+        xt = torch.from_numpy(x).cuda()
+        for off in (0, 1):                       # off=1: mis-aligned pointer -> scalar kernel
+            xs = xt[off:off + n]
+            codes = torch.empty(n + 1, dtype=torch.uint8, device="cuda")[off:off + n]
+            fq = torch.empty(n + 3, dtype=torch.float32, device="cuda")[off:off + n]
+            nv.check(nv.lib().slfp_quantize_f32(xs.data_ptr(), n, 0.37, 1, 0, codes.data_ptr(), fq.data_ptr(), None, nv.stream()))
+            torch.cuda.synchronize()
+            oc, oq = orc.quantize(x[off:off + n], 1, kdiv=0.37)
+            assert (codes.cpu().numpy() == oc).all() and same_bits(oq, fq.cpu().numpy()).all(), (n, off)
+
+
+def test_dequantize_all_codes(orc):
+    from cnns_slfp_quantization_b200 import _native as nv
+    codes = torch.arange(256, dtype=torch.uint8, device="cuda").repeat(37)[:-3].contiguous()
+    for fmt in (0, 1, 2):
+        out = torch.empty(codes.numel(), dtype=torch.float32, device="cuda")
+        nv.check(nv.lib().slfp_dequantize(codes.data_ptr(), codes.numel(), fmt, out.data_ptr(), nv.stream()))
+        torch.cuda.synchronize()
+        assert same_bits(orc.decode(codes.cpu().numpy(), fmt), out.cpu().numpy()).all()
+
+
+def test_roundtrip_idempotent_at_full_size():
+    """Size-independent properties at the BASELINE layer size (256x256x56x56 = 205.5 M elements):
+    decode(encode(x)) is a fixed point of the quantizer and |q| never exceeds the format's top."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    n = 256 * 256 * 56 * 56
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(n, device="cuda", generator=g) * 4
+    codes = torch.empty(n, dtype=torch.uint8, device="cuda")
+    fq = torch.empty(n, dtype=torch.float32, device="cuda")
+    lib = nv.lib()
+    nv.check(lib.slfp_quantize_f32(x.data_ptr(), n, 1.0, 1, 0, codes.data_ptr(), fq.data_ptr(), None, nv.stream()))
+    dq = torch.empty_like(fq)
+    nv.check(lib.slfp_dequantize(codes.data_ptr(), n, 1, dq.data_ptr(), nv.stream()))
+    assert torch.equal(dq.view(torch.int32), fq.view(torch.int32))
+    codes2 = torch.empty_like(codes)
+    nv.check(lib.slfp_quantize_f32(fq.data_ptr(), n, 1.0, 1, 0, codes2.data_ptr(), None, None, nv.stream()))
+    # idempotent except the saturation literal, which re-quantizes to the top grid value (3 ulp above it)
+    same = codes2 == codes
+    sat = (codes & 0x7f) == 2
+    assert bool((same | sat).all())
+    assert float(fq.abs().max()) <= 15.3216553
+    assert bool(((fq == 0) == (x == 0)).all())
+    assert bool((torch.sign(fq) == torch.sign(x)).all())
+
+
+def test_absmax(orc):
+    from cnns_slfp_quantization_b200 import _native as nv
+    rng = np.random.default_rng(5)
+    for n in (1, 1000, 1 << 20, (1 << 22) + 7):
+        x = rng.standard_normal(n).astype(np.float32) * 3
+        x[rng.integers(n)] = -77.25
+        xt = torch.from_numpy(x).cuda()
+        out = torch.full((1,), 123.0, device="cuda")
+        nv.check(nv.lib().slfp_absmax_f32(xt.data_ptr(), n, out.data_ptr(), 1, nv.stream()))
+        assert float(out) == orc.absmax(x) == 77.25
+        nv.check(nv.lib().slfp_absmax_f32(xt.data_ptr(), n, out.data_ptr(), 0, nv.stream()))   # accumulates
+        assert float(out) == 77.25
+
+
+def test_quantize_nhwc_padded(orc):
+    from cnns_slfp_quantization_b200 import _native as nv
+    rng = np.random.default_rng(9)
+    for C, Cp in ((3, 4), (24, 32), (58, 64), (16, 16)):
+        x = (rng.standard_normal((50, C)) * 3).astype(np.float32)
+        xt = torch.from_numpy(x).cuda()
+        codes = torch.full((50, Cp), 0x77, dtype=torch.uint8, device="cuda")
+        nv.check(nv.lib().slfp_quantize_nhwc_f32(xt.data_ptr(), 50, C, Cp, 0.5, 1, codes.data_ptr(), nv.stream()))
+        oc, _ = orc.quantize(x, 1, kdiv=0.5)
+        got = codes.cpu().numpy()
+        assert (got[:, :C] == oc).all() and (got[:, C:] == 0).all()
+
+
+def test_host_buffer_entry(orc):
+    from cnns_slfp_quantization_b200 import _native as nv
+    x = (np.random.default_rng(2).standard_normal(100001) * 5).astype(np.float32)
+    codes = np.empty(x.size, np.uint8)
+    fq = np.empty_like(x)
+    nv.check(nv.lib().slfp_quantize_host_f32(x.ctypes.data_as(ctypes.c_void_p), x.size, 0.9, 1,
+                                             codes.ctypes.data_as(ctypes.c_void_p), fq.ctypes.data_as(ctypes.c_void_p)))
+    oc, oq = orc.quantize(x, 1, kdiv=0.9)
+    assert (codes == oc).all() and same_bits(oq, fq).all()
