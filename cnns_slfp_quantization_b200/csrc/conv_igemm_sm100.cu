@@ -67,7 +67,9 @@ struct IgemmParams {
     int num_kb, taps;
     int m_tiles, n_tiles, num_tiles;
     FastDiv div_hw, div_w, div_cpt, div_s;
+    int cblocks;               // Cp / 64 when Cp % 64 == 0 (uniform-tap gather), else 0
     SlfpEpilogue epi;
+    DivK next_div, next_div2;  // quantize-on-store divisors with their host-computed reciprocals
 };
 
 template <int BLOCK_N>
@@ -128,12 +130,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams 
         const int row = tid & 127, half = tid >> 7;
         const uint32_t a_row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const uint32_t land_base = ptx::smem_u32(s_land);
-        const uint32_t lane4 = (uint32_t)lane * 4u;
-        const uint8_t* lut_b = reinterpret_cast<const uint8_t*>(s_lut);
+        const uint32_t lut_lane = ptx::smem_u32(s_lut) + (uint32_t)lane * 4u;
+        const uint32_t a_base = ptx::smem_u32(s_a);
         const int total = my_tiles * p.num_kb;
 
         // gather cursor (runs kLand items ahead of the decode cursor)
         int g_tile_i = 0, g_kb = 0;
+        int g_cb = 0, g_r = 0, g_s = 0;              // uniform-tap mode: channel block / filter row / col
         const uint8_t* g_xn = p.x;
         int g_hi0 = 0, g_wi0 = 0;
         bool g_rowok = false;
@@ -149,9 +152,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams 
             g_hi0 = (int)ho * p.sh - p.ph;
             g_wi0 = (int)wo * p.sw - p.pw;
             g_xn = p.x + (size_t)n * p.H * p.W * p.Cp;
+            g_cb = g_r = g_s = 0;
         };
         auto g_issue = [&](int slot) {
-            if (GRAN == 16) {
+            if (GRAN == 64) {
+                // Cp % 64 == 0: the whole K block is one filter tap (warp-uniform), 64 contiguous channels
+                const int hi = g_hi0 + g_r * p.dh, wi = g_wi0 + g_s * p.dw;
+                const bool ok = g_rowok && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+                const uint8_t* src = ok ? g_xn + ((size_t)(hi * p.W + wi) * p.Cp + g_cb * 64 + half * 32) : p.x;
+                const uint32_t dst = land_base + (uint32_t)(slot * kLandBytes + tid * 16);
+                ptx::cp_async16(dst, src, ok ? 16u : 0u);
+                ptx::cp_async16(dst + 4096u, ok ? src + 16 : p.x, ok ? 16u : 0u);
+            } else if (GRAN == 16) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const uint32_t q = (uint32_t)g_kb * 4u + (uint32_t)half * 2u + (uint32_t)j;
@@ -178,6 +190,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams 
             }
         };
         auto g_advance = [&]() {
+            if (GRAN == 64) {
+                if (++g_cb == p.cblocks) { g_cb = 0; if (++g_s == p.S) { g_s = 0; ++g_r; } }
+            }
             if (++g_kb == p.num_kb) { g_kb = 0; ++g_tile_i; if (g_tile_i < my_tiles) g_setup(); }
         };
 
@@ -187,49 +202,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams 
             ptx::cp_async_commit();
         }
         uint32_t stage = 0, phase = 0;
+        int slot = 0;
         for (int it = 0; it < total; ++it) {
-            const int slot = it % kLand;
             ptx::cp_async_wait<kLand - 1>();                 // this thread's copies of item `it` landed
             uint32_t w[8];
-            if (GRAN == 16) {
+            const uint32_t land_slot = land_base + (uint32_t)(slot * kLandBytes);
+            if (GRAN != 4) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(s_land + slot * kLandBytes + (j * 256 + tid) * 16);
+                    const uint4 v = ptx::lds128_volatile(land_slot + (uint32_t)((j * 256 + tid) * 16));
                     w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    w[j] = *reinterpret_cast<const uint32_t*>(s_land + slot * kLandBytes + (j * 256 + tid) * 4);
+                for (int j = 0; j < 8; ++j) w[j] = ptx::lds32_volatile(land_slot + (uint32_t)((j * 256 + tid) * 4));
             }
             // code -> float16 through the per-bank table: entry (code, lane) lives in bank `lane`
             uint32_t h[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint32_t c = w[j];
-                const uint32_t e0 = *reinterpret_cast<const uint32_t*>(lut_b + (((c << 7) & 0x7f80u) | lane4));
-                const uint32_t e1 = *reinterpret_cast<const uint32_t*>(lut_b + (((c >> 1) & 0x7f80u) | lane4));
-                const uint32_t e2 = *reinterpret_cast<const uint32_t*>(lut_b + (((c >> 9) & 0x7f80u) | lane4));
-                const uint32_t e3 = *reinterpret_cast<const uint32_t*>(lut_b + (((c >> 17) & 0x7f80u) | lane4));
-                h[2 * j] = e0 | (e1 << 16);
-                h[2 * j + 1] = e2 | (e3 << 16);
+                const uint32_t e0 = ptx::lds32(lut_lane + ((c << 7) & 0x7f80u));
+                const uint32_t e1 = ptx::lds32(lut_lane + ((c >> 1) & 0x7f80u));
+                const uint32_t e2 = ptx::lds32(lut_lane + ((c >> 9) & 0x7f80u));
+                const uint32_t e3 = ptx::lds32(lut_lane + ((c >> 17) & 0x7f80u));
+                h[2 * j] = __byte_perm(e0, e1, 0x5410);
+                h[2 * j + 1] = __byte_perm(e2, e3, 0x5410);
             }
             // refill the landing slot for item it + kLand (its previous content is in registers now)
             if (it + kLand < total) { g_issue(slot); g_advance(); }
             ptx::cp_async_commit();
 
             ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u);   // MMA done with this stage
-            uint8_t* a_dst = s_a + stage * kABytes + a_row_off;
+            const uint32_t a_dst = a_base + stage * kABytes + a_row_off;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int cj = half * 4 + i;
-                *reinterpret_cast<uint4*>(a_dst + ((cj ^ (row & 7)) << 4)) =
-                    make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                ptx::sts128(a_dst + (uint32_t)((cj ^ (row & 7)) << 4), h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
             }
             ptx::fence_proxy_async_smem();                   // generic-proxy writes -> async proxy (UMMA)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_full[stage]));
             if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
+            if (++slot == kLand) slot = 0;
         }
         ptx::cp_async_wait<0>();
     } else if (warp == kTmaWarp) {
@@ -240,7 +255,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams 
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const int n0 = (tile % p.n_tiles) * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u);
+                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 64);
                     const uint32_t full = ptx::smem_u32(&bar_full[stage]);
                     ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
                     ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBlockK, n0);
@@ -288,7 +303,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams 
             const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBlockM + (uint32_t)(quad * 32 + lane);
             const int n_base = (tile % p.n_tiles) * BLOCK_N + chalf * (BLOCK_N / 2);
             const uint32_t buf = (uint32_t)ti & 1u;
-            ptx::mbar_wait(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u);
+            ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u, 256);
             ptx::tc_fence_after();
             const bool row_ok = m < p.M;
 #pragma unroll 1
@@ -365,13 +380,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams 
                         for (int pass = 0; pass < 2; ++pass) {
                             uint8_t* yc = pass ? e.y_codes2 : e.y_codes;
                             if (!yc) continue;
-                            const float kd = pass ? e.next_k_div2 : e.next_k_div;
+                            const DivK kd = pass ? p.next_div2 : p.next_div;
                             uint32_t pk[4] = {0, 0, 0, 0};
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 uint32_t c = 0;
                                 if (n0 + i < Kout) {
-                                    const float q = div_rn(v[i], kd);
+                                    const float q = div_k(v[i], kd);
                                     c = (e.next_fmt == SLFP_FMT_SFP33) ? encode<SLFP_FMT_SFP33>(q) : encode<SLFP_FMT_SLFP34_ACT>(q);
                                 }
                                 pk[i >> 2] |= c << ((i & 3) * 8);
@@ -460,7 +475,10 @@ int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* 
     p.div_w = make_fastdiv((uint32_t)p.Wo);
     p.div_cpt = make_fastdiv((uint32_t)(d->c_phys >= 16 ? d->c_phys / 16 : 1));
     p.div_s = make_fastdiv((uint32_t)d->s);
+    p.cblocks = (d->c_phys % 64 == 0) ? d->c_phys / 64 : 0;
     p.epi = *epi;
+    p.next_div = make_divk(epi->y_codes ? epi->next_k_div : 1.0f);
+    p.next_div2 = make_divk(epi->y_codes2 ? epi->next_k_div2 : 1.0f);
 
     auto enc = get_encode_fn();
     if (!enc) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled not available");
@@ -475,9 +493,10 @@ int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* 
     if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
     const bool sfp = d->fmt == SLFP_FMT_SFP33;
-    const int gran = d->c_phys == 4 ? 4 : 16;
+    const int gran = d->c_phys == 4 ? 4 : (p.cblocks ? 64 : 16);
 #define SLFP_IGEMM_CASE(BN)                                                                          \
     if (bn == BN) {                                                                                  \
+        if (gran == 64) return sfp ? launch_igemm<BN, 64, true>(tmap, p, st) : launch_igemm<BN, 64, false>(tmap, p, st); \
         if (gran == 16) return sfp ? launch_igemm<BN, 16, true>(tmap, p, st) : launch_igemm<BN, 16, false>(tmap, p, st); \
         return sfp ? launch_igemm<BN, 4, true>(tmap, p, st) : launch_igemm<BN, 4, false>(tmap, p, st);  \
     }

@@ -59,7 +59,7 @@ constexpr int kQTile = kQThreads * 4 * kQVec;  // 4096 elements per CTA iteratio
 struct QuantArgs {
     const float* x;
     size_t n;
-    float k_div;
+    DivK k_div;
     uint8_t* codes;
     float* fakeq;
     __half* f16;
@@ -67,9 +67,9 @@ struct QuantArgs {
 };
 
 template <int FMT>
-__device__ __forceinline__ void quant_elem(float x, float k_div, bool zz, const uint32_t* tab,
+__device__ __forceinline__ void quant_elem(float x, const DivK& k_div, bool zz, const uint32_t* tab,
                                            uint32_t& code, float& fq) {
-    const float v = div_rn(x, k_div);          // IEEE division, like `input / self.Ka` on the CPU
+    const float v = div_k(x, k_div);           // == IEEE x / K, like `input / self.Ka` on the CPU
     if (FMT == SLFP_FMT_SFP44_OUT) {
         code = 0;
         fq = layerout_quantize(v, zz);
@@ -170,12 +170,12 @@ static int launch_quantize(const QuantArgs& a, cudaStream_t st) {
 // NHWC tensor whose channel count is not the physical (padded) one: thread per output code.
 template <int FMT>
 __global__ void __launch_bounds__(256) quantize_pad_kernel(const float* __restrict__ x, size_t npix, int C, int Cp,
-                                                           float k_div, uint8_t* __restrict__ codes) {
+                                                           DivK k_div, uint8_t* __restrict__ codes) {
     const size_t total = npix * (size_t)Cp;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
         const size_t pix = i / (size_t)Cp;
         const int c = (int)(i - pix * (size_t)Cp);
-        codes[i] = (c < C) ? (uint8_t)encode<FMT>(div_rn(x[pix * (size_t)C + c], k_div)) : (uint8_t)0;
+        codes[i] = (c < C) ? (uint8_t)encode<FMT>(div_k(x[pix * (size_t)C + c], k_div)) : (uint8_t)0;
     }
 }
 
@@ -284,7 +284,7 @@ extern "C" int slfp_quantize_f32(const float* x, size_t n, float k_div, int fmt,
     if (!x || (!codes && !fakeq && !f16)) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: null pointer");
     if (fmt == SLFP_FMT_SFP44_OUT && codes)
         return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: SFP<4,4> layer-out has no 8-bit code");
-    QuantArgs a{x, n, k_div, codes, fakeq, (__half*)f16, (flags & SLFP_Q_LAYEROUT_ZERO_IS_ZERO) ? 1 : 0};
+    QuantArgs a{x, n, make_divk(k_div), codes, fakeq, (__half*)f16, (flags & SLFP_Q_LAYEROUT_ZERO_IS_ZERO) ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (fmt) {
         case SLFP_FMT_SFP33: return launch_quantize<SLFP_FMT_SFP33>(a, st);
@@ -302,10 +302,11 @@ extern "C" int slfp_quantize_nhwc_f32(const float* x, size_t npix, int c, int c_
     if (c == c_phys) return slfp_quantize_f32(x, npix * (size_t)c, k_div, fmt, 0, codes, nullptr, nullptr, stream);
     const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(npix * (size_t)c_phys, 256));
     cudaStream_t st = (cudaStream_t)stream;
+    const DivK dk = make_divk(k_div);
     switch (fmt) {
-        case SLFP_FMT_SFP33: quantize_pad_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, npix, c, c_phys, k_div, codes); break;
-        case SLFP_FMT_SLFP34_ACT: quantize_pad_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, k_div, codes); break;
-        case SLFP_FMT_SLFP34_WGT: quantize_pad_kernel<SLFP_FMT_SLFP34_WGT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, k_div, codes); break;
+        case SLFP_FMT_SFP33: quantize_pad_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes); break;
+        case SLFP_FMT_SLFP34_ACT: quantize_pad_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes); break;
+        case SLFP_FMT_SLFP34_WGT: quantize_pad_kernel<SLFP_FMT_SLFP34_WGT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes); break;
         default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nhwc_f32: format %d has no codes", fmt);
     }
     return check_launch("quantize_pad_kernel");

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <string.h>
+#include <math.h>
 
 #include "../../include/slfp_b200.h"
 
@@ -72,6 +73,37 @@ __host__ __device__ __forceinline__ float div_rn(float x, float k) {
 #else
     return x / k;
 #endif
+}
+
+// The same correctly rounded quotient without the division instruction sequence: the divisor K is a
+// per-layer constant, so rk = RN(1/K) is computed once on the host (`1.0f / k`, IEEE) and
+//      q0 = RN(x * rk);  r = x - q0*K (exact, one FMA);  q1 = RN(q0 + r * rk)
+// is RN(x / K) (Markstein's final-step theorem: q0 is within one ulp and rk is the correctly rounded
+// reciprocal).  The argument needs q0, r and q1 to stay inside the normal range, so anything with an
+// extreme exponent (|x| outside [2^-60, 2^60], Inf, NaN, 0) takes the true division.  `valid` is
+// decided on the host: K normal and 2^-30 <= K <= 2^30.  tests/test_host_compiled_kernels.py sweeps
+// this against x / K for every float32 mantissa.
+struct DivK {
+    float k, rk;
+    int fast;
+};
+static inline DivK make_divk(float k) {
+    DivK d;
+    d.k = k;
+    d.rk = 1.0f / k;
+    const float a = k < 0 ? -k : k;
+    d.fast = (a >= 9.3132257e-10f && a <= 1.0737418e9f) ? 1 : 0;
+    return d;
+}
+__host__ __device__ __forceinline__ float div_k(float x, const DivK& d) {
+    const uint32_t ax = f2u(x) & 0x7fffffffu;
+    // 2^-60 = 0x21800000, 2^60 = 0x5d800000
+    if (d.fast && (ax - 0x21800000u) < (0x5d800000u - 0x21800000u)) {
+        const float q0 = x * d.rk;
+        const float r = fmaf(-q0, d.k, x);
+        return fmaf(r, d.rk, q0);
+    }
+    return div_rn(x, d.k);
 }
 
 // ---- encode ------------------------------------------------------------------------------------

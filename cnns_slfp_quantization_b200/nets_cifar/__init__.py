@@ -1,0 +1,2 @@
+from .vgg16 import VGG16_Q                             # noqa: F401
+from .mobilenetv1 import MobileNetV1_Q                 # noqa: F401

@@ -1,0 +1,115 @@
+"""Shared plumbing of the caller nets (nets_imgnet/, nets_cifar/).
+
+The nets are the CALLERS of the hot path: small table-driven re-statements of
+the reference's model graphs with the reference's parameter names (so its state_dict files load
+unchanged), built from an `ops` namespace that supplies the quantized-module factories:
+  * default: this package's drop-in modules (sm_100a kernels);
+  * tests / bench.py's CPU baseline pass the oracle's torch port instead (oracle/torch_port.py).
+"""
+import json
+import os
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def product_ops():
+    from .utils import conv2d_func, sfp_quant, activation_func
+    return types.SimpleNamespace(conv2d_Q=conv2d_func.conv2d_Q, conv2d_Q_bias=conv2d_func.conv2d_Q_bias,
+                                 linear_Q=conv2d_func.linear_Q, layerout_quantize_func=sfp_quant.layerout_quantize_func,
+                                 Swish=activation_func.Swish)
+
+
+def reference_scales(name):
+    """Per-layer Ka / Kw = max|.| / 15.5 the reference hard-codes in its nets (calibrated on its
+    private checkpoints); data extracted to ref_scales.json, source lines recorded there."""
+    with open(os.path.join(_HERE, "ref_scales.json")) as f:
+        t = json.load(f)[name]
+    return np.array(t["ka_max"]) / t["divisor"], np.array(t["kw_max"]) / t["divisor"]
+
+
+def quantized_layers(model):
+    """Quantized conv / linear modules in forward-definition order."""
+    return [m for m in model.modules() if hasattr(m, "Ka") and hasattr(m, "Kw") and hasattr(m, "q_bit")]
+
+
+def set_scales(model, ka=None, kw=None):
+    """Re-assign the per-layer scales (plain attributes in the reference: not buffers, not in the
+    state_dict)."""
+    for i, m in enumerate(quantized_layers(model)):
+        if ka is not None:
+            m.Ka = torch.tensor(float(ka[i]), dtype=torch.float64)
+        if kw is not None:
+            m.Kw = torch.tensor(float(kw[i]), dtype=torch.float64)
+
+
+def synth_state_dict(model, seed=0):
+    """Deterministic synthetic parameters keyed by parameter NAME (independent of construction order,
+    so the reference's own model classes can load the very same values for golden generation).
+    Conv / linear weights ~ N(0, sqrt(2/fan_in)); BatchNorm weight ~ U(0.5, 1.5), bias ~ N(0, 0.2),
+    running_mean ~ N(0, 0.2), running_var ~ U(0.5, 1.5)  (SURVEY.md section 8c caveat 3)."""
+    import zlib
+    out = {}
+    for name, t in model.state_dict().items():
+        rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+        shape = tuple(t.shape)
+        if name.endswith("num_batches_tracked"):
+            v = np.zeros(shape, np.int64)
+        elif name.endswith("running_var"):
+            v = rng.uniform(0.5, 1.5, shape)
+        elif name.endswith("running_mean"):
+            v = rng.normal(0.0, 0.2, shape)
+        elif t.dim() == 1 and name.endswith("bn3.weight"):
+            v = rng.uniform(0.1, 0.3, shape)          # last BN of a residual branch: keep the stream bounded
+        elif t.dim() == 1 and name.endswith("weight"):
+            v = rng.uniform(0.5, 1.5, shape)
+        elif t.dim() == 1:
+            v = rng.normal(0.0, 0.2, shape)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            v = rng.normal(0.0, np.sqrt(2.0 / fan_in), shape)
+        out[name] = torch.from_numpy(np.asarray(v)).to(t.dtype)
+    return out
+
+
+def classifier_module(model):
+    """The final classifier layer (quantized or plain nn.Linear)."""
+    last = None
+    for m in model.modules():
+        if isinstance(m, nn.Linear):
+            last = m
+    return last
+
+
+def recenter_classifier(model, x, gain=1.0, seed=7):
+    """Random-init nets predict one class for every image (SURVEY.md section 8c caveat 1).  Make top-1
+    image dependent: weight ~ N(0, gain/sqrt(fan_in)), bias = -W . mean(feature) over the probe batch
+    x.  Call on a float32 (q_bit 32) instance; returns (weight, bias) to copy into other instances."""
+    fc = classifier_module(model)
+    feats = []
+    h = fc.register_forward_hook(lambda mod, inp, out: feats.append(inp[0].detach()))
+    with torch.no_grad():
+        model(x)
+    h.remove()
+    f = feats[0].reshape(-1, fc.in_features).double()
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(fc.out_features, fc.in_features, generator=g, dtype=torch.float64) * gain / np.sqrt(fc.in_features)
+    f_c = f - f.mean(0, keepdim=True)
+    w = w / (f_c @ w.T).std().clamp_min(1e-12)               # unit-variance logits on the probe batch
+    b = -(w @ f.mean(0))
+    return w.float().to(fc.weight.device), b.float().to(fc.weight.device)
+
+
+def synth_images(batch, size, seed=1234, channels=3):
+    """Synthetic input batch: N(0,1) noise plus a low-frequency per-image pattern (gives the
+    classifier something image-dependent)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, channels, size, size, generator=g)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, size), torch.linspace(-1, 1, size), indexing="ij")
+    ph = torch.rand(batch, channels, 3, generator=g) * 6.28318
+    pat = torch.sin(3.0 * xx[None, None] + ph[..., 0:1, None]) * torch.cos(2.0 * yy[None, None] + ph[..., 1:2, None])
+    return x + 1.5 * pat * (0.5 + ph[..., 2:3, None] / 6.28318)

@@ -1,0 +1,2 @@
+from .resnet50 import ResNet50, Bottleneck            # noqa: F401
+from .mobilenetv1 import MobileNetV1_Q                # noqa: F401

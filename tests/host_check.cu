@@ -25,3 +25,16 @@ extern "C" void hostcheck_decode(const uint8_t* codes, size_t n, int fmt, float*
     for (size_t i = 0; i < n; ++i)
         out[i] = fmt == SLFP_FMT_SFP33 ? decode<true>(codes[i], h_pow2frac) : decode<false>(codes[i], h_pow2frac);
 }
+
+// div_k (reciprocal + two FMAs) against the IEEE quotient; returns the number of mismatching elements.
+extern "C" size_t hostcheck_divk_mismatches(const float* x, size_t n, float k) {
+    const DivK d = make_divk(k);
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float a = div_k(x[i], d), b = x[i] / k;
+        uint32_t ua, ub;
+        memcpy(&ua, &a, 4); memcpy(&ub, &b, 4);
+        bad += (ua != ub) && !(a != a && b != b);
+    }
+    return bad;
+}

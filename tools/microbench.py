@@ -71,10 +71,12 @@ RESNET50_LAYERS = [
 ]
 
 
-def bench_conv(batch=256, mode="f32"):
+def bench_conv(batch=256, mode="f32", only=None, iters=10):
     lib = nv.lib()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for name, C, K, k, st, pad, H in RESNET50_LAYERS:
+        if only and only not in name:
+            continue
         Cp = 4 if C <= 4 else (C + 15) // 16 * 16
         d = nv.SlfpConvDesc(batch, H, H, C, Cp, K, k, k, st, st, pad, pad, 1, 1, 1, nv.FMT_SLFP34_ACT)
         Ho = (H + 2 * pad - (k - 1) - 1) // st + 1
@@ -96,7 +98,7 @@ def bench_conv(batch=256, mode="f32"):
             epi.y_codes, epi.next_k_div, epi.next_fmt, epi.k_phys_out, epi.relu = y.data_ptr(), 0.2, nv.FMT_SLFP34_ACT, K, 1
             out_b = 1
         fn = lambda: nv.check(lib.slfp_conv2d_fwd(ctypes.byref(d), xc.data_ptr(), wh.data_ptr(), ctypes.byref(epi), nv.stream()))
-        med, best = timeit(fn, iters=10, flush=flush)
+        med, best = timeit(fn, iters=iters, flush=flush)
         flops = 2.0 * batch * Ho * Ho * K * C * k * k
         byts = xc.numel() + y.numel() * out_b + wh.numel() * 2
         print(json.dumps({"kernel": "conv_igemm", "layer": name, "out": mode, "ms": round(med, 4),
@@ -109,4 +111,13 @@ if __name__ == "__main__":
     if what == "quant":
         bench_quant()
     elif what == "conv":
-        bench_conv(mode=sys.argv[2] if len(sys.argv) > 2 else "f32")
+        bench_conv(mode=sys.argv[2] if len(sys.argv) > 2 else "f32", only=sys.argv[3] if len(sys.argv) > 3 else None,
+                   iters=int(sys.argv[4]) if len(sys.argv) > 4 else 10)
+    elif what == "quant1":
+        lib = nv.lib()
+        n = 205520896
+        x = torch.randn(n, device="cuda") * 4
+        codes = torch.empty(n, dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            nv.check(lib.slfp_quantize_f32(x.data_ptr(), n, 0.7, 1, 0, codes.data_ptr(), None, None, nv.stream()))
+        torch.cuda.synchronize()
