@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: SLFP-8 ResNet-50 inference, 224x224, batch 256 per GPU (BASELINE.json
+configs[2]: the configuration the metric "SLFP-8 ResNet-50 images/sec" is quoted on; it fits one GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+                --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one forward pass of the whole network over one synthetic batch (random-init weights of the
+ResNet-50 v1.5 architecture, N(0,1)+pattern images; weights re-quantized every step like the reference).
+`value` is whole-job images/s with inputs resident in HBM (data-parallel over the batch, weak scaling: 256
+images per GPU, no data-path collective); `e2e` is the same through the public API with HOST (pinned)
+float32 input buffers: H2D copy of every batch and D2H read of the logits inside the timed region.
+`roofline` is the dominant kernel (the tcgen05 implicit-GEMM conv) timed per launch with CUDA events on the
+launching stream in a separate instrumented pass; `cpu_baseline` / `--impl reference` time the reference's
+CPU implementation of the same path (oracle/torch_port.py, a torch-CPU port: the reference is pure Python
+and cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+METRIC = "slfp8_resnet50_inference_images_per_sec"
+UNIT = "images/s"
+WORKLOAD = "ResNet-50 ImageNet SLFP-8 inference 224x224, batch 256 per GPU"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p.update(json.load(f))
+            p["src"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_resnet50(qbit, size, ops, device, calibrate):
+    """ResNet-50 with synthetic weights and calibrated scales (max|.|/15.5 over one float32 pass, the
+    reference's calibration workflow), so the quantizers see a meaningful dynamic range."""
+    from cnns_slfp_quantization_b200 import nets_common as nc
+    from cnns_slfp_quantization_b200.nets_imgnet import ResNet50
+    m32 = ResNet50(32, ops=ops, scales=(np.ones(54), np.ones(54))).eval()
+    sd = nc.synth_state_dict(m32)
+    m32.load_state_dict(sd)
+    m32 = m32.to(device)
+    ka, kw = calibrate(m32, nc.synth_images(4, min(size, 96)).to(device))
+    m = ResNet50(qbit, ops=ops, scales=(ka, kw)).eval()
+    m.load_state_dict(sd)
+    return m.to(device)
+
+
+def build_model_gpu(size, device):
+    """Product path: calibration through the fused abs-max kernel (cnns_slfp_quantization_b200.calibration)."""
+    from cnns_slfp_quantization_b200 import calibration
+    return synth_resnet50(8, size, None, device, lambda m, x: calibration.calibrate_scales(m, [x]))
+
+
+def build_model_cpu(size):
+    """CPU baseline: the torch-CPU port of the reference modules; calibration by the reference's recipe."""
+    from cnns_slfp_quantization_b200 import nets_common as nc
+    from oracle import torch_port
+
+    def cal(m, x):
+        with torch.no_grad():
+            m(x)
+        layers = nc.quantized_layers(m)
+        return (np.array([float(l.input_q.abs().max()) for l in layers]) / 15.5,
+                np.array([float(l.weight_q.abs().max()) for l in layers]) / 15.5)
+    return synth_resnet50(8, size, torch_port.ops(), "cpu", cal)
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path (torch-CPU port), bounded sample per step."""
+    if rank != 0:
+        return
+    from cnns_slfp_quantization_b200 import nets_common as nc
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample_batch = args.cpu_batch
+    m = build_model_cpu(224)
+    x = nc.synth_images(sample_batch, 224)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            m(x)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    v = sample_batch * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{sample_batch} images per step on the host CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{len(times)} forward passes of {sample_batch} images (224x224) through oracle/torch_port.py"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from cnns_slfp_quantization_b200 import _native as nv, engine, nets_common as nc
+    nv.lib()                                   # fail loudly if the CUDA library is missing
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = build_model_gpu(args.size, dev)
+    plan = engine.compile_resnet50(model, args.batch, args.size, device=dev)
+    x_host = nc.synth_images(args.batch, args.size, seed=1234 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    plan.input.copy_(x_dev)
+    plan.prepare_weights()
+    plan.run()
+    torch.cuda.synchronize()
+    if not args.no_graph:
+        plan.capture()
+
+    # ---- timed region: K steps, inputs resident in HBM ------------------------------------------------------
+    for _ in range(args.warmup):
+        plan()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    nv.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * args.batch * args.steps / (ms * 1e-3)
+    launches = plan.launches_per_step * args.steps
+
+    # ---- e2e: pinned host float32 batch -> H2D -> forward -> logits D2H, every step -----------------------------
+    logits_host = torch.empty((args.batch, plan.output.shape[1]), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_loop(n):
+        # double-buffered: the copy of batch i+1 overlaps the forward of batch i
+        with torch.cuda.stream(copy_stream):
+            staged[0].copy_(x_host, non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n):
+            cur, nxt = i & 1, (i + 1) & 1
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(done[nxt])
+                    staged[nxt].copy_(x_host, non_blocking=True)
+                    ready[nxt].record(copy_stream)
+            torch.cuda.current_stream().wait_event(ready[cur])
+            plan.input.copy_(staged[cur], non_blocking=True)
+            plan()
+            done[cur].record()
+            logits_host.copy_(plan.output, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.batch * args.steps / float(t.item())
+
+    # ---- roofline: the dominant kernel, per-launch CUDA-event timing in an instrumented eager pass -------------
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        plan.run(); torch.cuda.synchronize()
+        nv.profile = {}
+        plan.run()
+        torch.cuda.synchronize()
+        prof, nv.profile = nv.profile, None
+        conv = prof.get("slfp_conv2d_fwd", [])
+        dense = [(a.elapsed_time(b), fl) for (a, b, _), (fl, is_dense, _) in zip(conv, plan.conv_flops) if is_dense]
+        conv_ms = sum(d[0] for d in dense)
+        conv_fl = sum(d[1] for d in dense)
+        all_ms = {k: sum(a.elapsed_time(b) for a, b, _ in v) for k, v in prof.items()}
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all dense conv launches of one step)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
+                "traffic": None, "launches": len(dense), "avg_launch_ms": conv_ms / max(len(dense), 1),
+                "share_of_step": conv_ms / max(sum(all_ms.values()), 1e-9),
+                "per_entry_point_ms": {k: round(v, 4) for k, v in all_ms.items()}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cm = build_model_cpu(args.size)
+        cx = nc.synth_images(args.cpu_batch, args.size)
+        with torch.no_grad():
+            cm(cx[:2])
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 8):
+                cm(cx)
+                reps += 1
+            dt = time.perf_counter() - t0
+        cpu = {"value": args.cpu_batch * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{reps} forward passes of {args.cpu_batch} images (224x224) through oracle/torch_port.py"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands (decoded SLFP<3,4> codes) x f32 accumulate; u8 codes between layers", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "images_per_gpu": args.batch, "parallelism": f"dp{world}",
+                           "l2": "inputs (154 MB/batch) and per-layer activations exceed the 126 MB L2; no explicit flush",
+                           "cuda_graph": not args.no_graph, "weights_requantized_every_step": not plan.static_weights,
+                           "residual_stream": "f16"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+                        "d2h_bytes_per_step": int(logits_host.numel() * 4)},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

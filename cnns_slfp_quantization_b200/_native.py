@@ -36,6 +36,7 @@ _SIGS = {
     "slfp_last_error": (ctypes.c_char_p, []),
     "slfp_quantize_f32": (c_i, [c_vp, c_sz, c_f, c_i, ctypes.c_uint, c_vp, c_vp, c_vp, c_vp]),
     "slfp_quantize_nhwc_f32": (c_i, [c_vp, c_sz, c_i, c_i, c_f, c_i, c_vp, c_vp]),
+    "slfp_quantize_nchw_f32": (c_i, [c_vp, c_i, c_i, c_sz, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_dequantize": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
     "slfp_absmax_f32": (c_i, [c_vp, c_sz, c_vp, c_i, c_vp]),
     "slfp_conv_wpitch": (c_sz, [ctypes.POINTER(SlfpConvDesc)]),
@@ -55,6 +56,39 @@ _SIGS = {
 EXPORTED_SYMBOLS = tuple(_SIGS)
 _lib = None
 
+# Every entry point that launches kernels on the caller's stream.  The proxy below counts those calls
+# (bench.py reports them as `gpu_launches`) and, when a profile dict is installed, brackets each call
+# with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
+_LAUNCHING = {"slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
+              "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
+              "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32"}
+launch_count = 0
+profile = None          # None, or {name: [(start_event, end_event, tag), ...]}
+profile_tag = None
+
+
+class _Lib:
+    def __init__(self, handle):
+        self._h = handle
+        for name in _SIGS:
+            fn = getattr(handle, name)
+            setattr(self, name, self._wrap(name, fn) if name in _LAUNCHING else fn)
+
+    @staticmethod
+    def _wrap(name, fn):
+        def call(*args):
+            global launch_count
+            launch_count += 1
+            if profile is None:
+                return fn(*args)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            profile.setdefault(name, []).append((a, b, profile_tag))
+            return rc
+        return call
+
 
 def lib():
     """Load the native library; fail loudly if it has not been built."""
@@ -68,7 +102,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        _lib = handle
+        _lib = _Lib(handle)
     return _lib
 
 

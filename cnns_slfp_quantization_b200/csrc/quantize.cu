@@ -179,6 +179,29 @@ __global__ void __launch_bounds__(256) quantize_pad_kernel(const float* __restri
     }
 }
 
+// NCHW float32 image -> NHWC codes with padded channels (the network input: C = 3 -> c_phys = 4).
+// Thread = (pixel, group of 4 channels): plane reads are coalesced across the warp, the store is one
+// 32-bit word per thread.
+template <int FMT>
+__global__ void __launch_bounds__(256) quantize_nchw_kernel(const float* __restrict__ x, int N, int C, size_t HW, int Cp,
+                                                            DivK k_div, uint8_t* __restrict__ codes) {
+    const int groups = Cp >> 2;
+    const size_t total = (size_t)N * HW * groups;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const size_t pix = i % HW;
+        const size_t ng = i / HW;
+        const int g = (int)(ng % groups);
+        const size_t n = ng / groups;
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = g * 4 + j;
+            if (c < C) w |= encode<FMT>(div_k(__ldg(x + (n * C + c) * HW + pix), k_div)) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(codes + (n * HW + pix) * Cp + g * 4) = w;
+    }
+}
+
 // ---- de-quantize ------------------------------------------------------------------------------
 template <bool SFP33>
 __global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t* __restrict__ codes, size_t n,
@@ -310,6 +333,23 @@ extern "C" int slfp_quantize_nhwc_f32(const float* x, size_t npix, int c, int c_
         default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nhwc_f32: format %d has no codes", fmt);
     }
     return check_launch("quantize_pad_kernel");
+}
+
+extern "C" int slfp_quantize_nchw_f32(const float* x, int n, int c, size_t hw, int c_phys, float k_div, int fmt,
+                                      uint8_t* codes, slfp_stream_t stream) {
+    if (n <= 0 || hw == 0) return 0;
+    if (!x || !codes || c <= 0 || c_phys < c || (c_phys & 3) || ((uintptr_t)codes & 3u))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_f32: bad arguments");
+    const size_t total = (size_t)n * hw * (c_phys / 4);
+    const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(total, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DivK dk = make_divk(k_div);
+    switch (fmt) {
+        case SLFP_FMT_SFP33: quantize_nchw_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, n, c, hw, c_phys, dk, codes); break;
+        case SLFP_FMT_SLFP34_ACT: quantize_nchw_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, n, c, hw, c_phys, dk, codes); break;
+        default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_f32: format %d", fmt);
+    }
+    return check_launch("quantize_nchw_kernel");
 }
 
 extern "C" int slfp_dequantize(const uint8_t* codes, size_t n, int fmt, float* out, slfp_stream_t stream) {

@@ -1,0 +1,365 @@
+"""Fused eval pipeline: whole-network inference where quantized layers exchange
+8-bit codes and everything between two convolutions lives in the producing conv's epilogue.
+
+The module-level drop-in (utils/conv2d_func.py) keeps float32 tensors between layers because
+BatchNorm / ReLU / pooling / the residual add are stock PyTorch modules of the caller nets.  In eval
+mode those are pure per-channel affine maps and elementwise ops, so a compiled plan can fold them:
+
+    conv epilogue:  acc (+bias_q) *Ka *Kw -> *bn_scale + bn_shift -> (+ residual) -> ReLU
+                    -> next layer's quantizer (x / Ka_next -> SLFP/SFP code)   [quantize-on-store]
+                    -> float16 copy where a later residual add needs the un-quantized value
+
+exactly the reference's arithmetic order (nets_imgnet/resnet50.py:71-90: bn -> relu, out += identity,
+relu; utils/conv2d_func.py:21: the next layer quantizes its input / Ka), except that eval BatchNorm
+is applied as one fused multiply-add (scale = gamma / sqrt(var + eps), shift = beta - mean * scale)
+and the residual stream is carried in float16.  Max-pooling runs directly on codes (the quantizer is
+monotone, so pooling commutes with it bit for bit).
+
+A Plan is a flat list of pre-bound C-ABI calls on pre-allocated buffers; `capture()` records it into
+a CUDA graph.  Weights are re-quantized on every forward like the reference does
+(utils/conv2d_func.py:22) unless `static_weights=True`.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as nv
+
+
+def _k32(K):
+    return float(np.float32(float(K)))
+
+
+class _T:
+    """A device tensor of the plan: NHWC, kind in {'codes', 'f16', 'f32'}."""
+    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv")
+
+    def __init__(self, buf, n, h, w, c, cp, kind, kdiv=None):
+        self.buf, self.n, self.h, self.w, self.c, self.cp, self.kind, self.kdiv = buf, n, h, w, c, cp, kind, kdiv
+
+
+def _ceil(v, m):
+    return (v + m - 1) // m * m
+
+
+def fold_bn(bn):
+    """Eval BatchNorm as y = x * scale + shift (float64 arithmetic, rounded once to float32)."""
+    g = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(bn.running_mean, dtype=torch.float64)
+    b = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(bn.running_mean, dtype=torch.float64)
+    scale = g / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    shift = b - bn.running_mean.detach().double() * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+class Plan:
+    def __init__(self, batch, device, q_bit, static_weights=False):
+        self.lib = nv.lib()
+        self.batch, self.dev, self.q_bit = batch, device, q_bit
+        self.afmt, self.wfmt = nv.fmt_for(q_bit, "act"), nv.fmt_for(q_bit, "weight")
+        self.static_weights = static_weights
+        self.weight_ops, self.ops, self.keep = [], [], []
+        self.input = None
+        self.output = None
+        self.graph = None
+        self.flops = 0.0
+        self.conv_flops = []          # per conv launch, in launch order (bench.py's roofline pass)
+        self.bytes_hbm = 0
+
+    # ---- buffers ----------------------------------------------------------------------------------------
+    def _alloc(self, n, h, w, c, kind, kdiv=None, cp=None):
+        if kind == "codes":
+            cp = cp or _ceil(c, 16)
+            buf = torch.zeros((n, h, w, cp), dtype=torch.uint8, device=self.dev)
+        else:
+            cp = c
+            buf = torch.empty((n, h, w, c), dtype=torch.float16 if kind == "f16" else torch.float32, device=self.dev)
+        self.bytes_hbm += buf.numel() * buf.element_size()
+        self.keep.append(buf)               # the pre-bound calls hold raw pointers: the plan owns the storage
+        return _T(buf, n, h, w, c, cp, kind, kdiv)
+
+    def _call(self, fn, *args):
+        def op(st):
+            nv.check(fn(*args, st))
+        return op
+
+    # ---- ops ----------------------------------------------------------------------------------------------
+    def input_nchw(self, c, h, w):
+        self.input = torch.zeros((self.batch, c, h, w), dtype=torch.float32, device=self.dev)
+        return self.input
+
+    def quantize_input(self, x_nchw, kdiv):
+        n, c, h, w = x_nchw.shape
+        cp = 4 if c <= 4 else _ceil(c, 16)
+        t = self._alloc(n, h, w, c, "codes", kdiv, cp=cp)
+        self.ops.append(self._call(self.lib.slfp_quantize_nchw_f32, x_nchw.data_ptr(), n, c, h * w, cp, kdiv, self.afmt,
+                                   t.buf.data_ptr()))
+        return t
+
+    def quantize_flat(self, x_f32, c, kdiv):
+        """[n, c] float32 features -> codes [n,1,1,cp] (classifier input)."""
+        n = x_f32.shape[0]
+        t = self._alloc(n, 1, 1, c, "codes", kdiv)
+        self.ops.append(self._call(self.lib.slfp_quantize_nhwc_f32, x_f32.data_ptr(), n, c, t.cp, kdiv, self.afmt,
+                                   t.buf.data_ptr()))
+        return t
+
+    def conv(self, x, mod, bn=None, relu=False, residual=None, codes=(), f16=False, f32=False, linear=False):
+        """One fused convolution / linear layer.  `codes`: divisors (Ka of the consumers) to quantize-on-store
+        with (at most two distinct).  Returns {'codes': {kdiv: _T}, 'f16': _T | None, 'f32': _T | None}."""
+        assert x.kind == "codes"
+        if linear:
+            K, C = mod.weight.shape
+            R = S = 1
+            stride, pad, dil, groups = (1, 1), (0, 0), (1, 1), 1
+            wview = mod.weight.view(K, C, 1, 1)
+        else:
+            K, Cg, R, S = mod.weight.shape
+            stride, pad, dil, groups = mod.stride, mod.padding, mod.dilation, mod.groups
+            C = Cg * groups
+            wview = mod.weight
+        assert C == x.c, (C, x.c)
+        ka, kw = _k32(mod.Ka), _k32(mod.Kw)
+        assert abs(ka - x.kdiv) == 0.0, "input codes were quantized with a different Ka"
+        d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
+                            self.afmt)
+        Ho = (x.h + 2 * pad[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
+        Wo = (x.w + 2 * pad[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
+        pitch = self.lib.slfp_conv_wpitch(ctypes.byref(d))
+        dense = groups == 1
+        wbuf = torch.empty((K * pitch,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
+        so, sc, sr, ss = wview.stride()
+        self.weight_ops.append(self._call(self.lib.slfp_prepare_weights, ctypes.byref(d), wview.data_ptr(), so, sc, sr, ss,
+                                          kw, self.wfmt, wbuf.data_ptr() if dense else None,
+                                          None if dense else wbuf.data_ptr(), None))
+        epi = nv.SlfpEpilogue()
+        if mod.bias is not None:
+            # conv2d_Q_bias: bias/Ka/Kw (conv2d_func.py:44); linear_Q: bias/Kw/Ka (:63); plain conv2d_Q: raw bias
+            b = mod.bias.detach()
+            if linear:
+                bq = b / mod.Kw / mod.Ka
+            elif getattr(mod, "_slfp_bias_scaled", True):
+                bq = b / mod.Ka / mod.Kw
+            else:
+                bq = b
+            bq = bq.float().contiguous()
+            self.keep.append(bq)
+            epi.bias_q = bq.data_ptr()
+        epi.post_a, epi.post_b = (kw, ka) if linear else (ka, kw)
+        if bn is not None:
+            sc_, sh_ = fold_bn(bn)
+            sc_, sh_ = sc_.to(self.dev), sh_.to(self.dev)
+            self.keep += [sc_, sh_]
+            epi.ch_scale, epi.ch_shift = sc_.data_ptr(), sh_.data_ptr()
+        if residual is not None:
+            assert residual.kind in ("f16", "f32") and (residual.n, residual.h, residual.w, residual.c) == (x.n, Ho, Wo, K)
+            epi.residual, epi.residual_f16 = residual.buf.data_ptr(), 1 if residual.kind == "f16" else 0
+        epi.relu = 1 if relu else 0
+        out = {"codes": {}, "f16": None, "f32": None}
+        kds = []
+        for kd in codes:
+            if kd not in kds:
+                kds.append(kd)
+        assert len(kds) <= 2
+        kp = _ceil(K, 16)
+        for i, kd in enumerate(kds):
+            t = self._alloc(x.n, Ho, Wo, K, "codes", kd, cp=kp)
+            out["codes"][kd] = t
+            if i == 0:
+                epi.y_codes, epi.next_k_div = t.buf.data_ptr(), kd
+            else:
+                epi.y_codes2, epi.next_k_div2 = t.buf.data_ptr(), kd
+        epi.next_fmt, epi.k_phys_out = self.afmt, kp
+        if f16:
+            out["f16"] = self._alloc(x.n, Ho, Wo, K, "f16")
+            epi.y_f16 = out["f16"].buf.data_ptr()
+        if f32:
+            out["f32"] = self._alloc(x.n, Ho, Wo, K, "f32")
+            epi.y_f32 = out["f32"].buf.data_ptr()
+        self.keep += [d, epi, wbuf]
+        self.ops.append(self._call(self.lib.slfp_conv2d_fwd, ctypes.byref(d), x.buf.data_ptr(), wbuf.data_ptr(),
+                                   ctypes.byref(epi)))
+        fl = 2.0 * x.n * Ho * Wo * K * (C // groups) * R * S
+        self.flops += fl
+        self.conv_flops.append((fl, groups == 1, f"{C}->{K} {R}x{S} s{stride[0]} @{x.h}"))
+        return out
+
+    def maxpool(self, x, k, stride, pad):
+        assert x.kind == "codes"
+        Ho = (x.h + 2 * pad - k) // stride + 1
+        Wo = (x.w + 2 * pad - k) // stride + 1
+        t = self._alloc(x.n, Ho, Wo, x.c, "codes", x.kdiv, cp=x.cp)
+        self.ops.append(self._call(self.lib.slfp_maxpool_codes, x.buf.data_ptr(), x.n, x.h, x.w, x.cp, k, k, stride, pad,
+                                   t.buf.data_ptr()))
+        return t
+
+    def avgpool(self, x):
+        """Global average pool of an f16 / f32 NHWC tensor -> [n, c] float32."""
+        out = torch.empty((x.n, x.c), dtype=torch.float32, device=self.dev)
+        self.keep.append(out)
+        self.ops.append(self._call(self.lib.slfp_avgpool_nhwc, x.buf.data_ptr(), 1 if x.kind == "f16" else 0, x.n,
+                                   x.h * x.w, x.c, out.data_ptr()))
+        return out
+
+    def torch_op(self, fn):
+        """Escape hatch for plain (un-quantized) library layers of the caller net, e.g. MobileNetV1's nn.Linear."""
+        self.ops.append(lambda st: fn())
+
+    # ---- execution ----------------------------------------------------------------------------------------
+    def prepare_weights(self):
+        st = nv.stream()
+        for op in self.weight_ops:
+            op(st)
+
+    @torch.no_grad()
+    def run(self):
+        st = nv.stream()
+        if not self.static_weights:
+            for op in self.weight_ops:
+                op(st)
+        for op in self.ops:
+            op(st)
+        return self.output
+
+    @property
+    def launches_per_step(self):
+        return len(self.ops) + (0 if self.static_weights else len(self.weight_ops))
+
+    def capture(self):
+        """Record the plan into a CUDA graph (after one eager warm-up so kernel attributes are set)."""
+        self.prepare_weights()
+        self.run()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+        return g
+
+    def __call__(self, x=None):
+        if x is not None and x.data_ptr() != self.input.data_ptr():
+            self.input.copy_(x, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run()
+        return self.output
+
+
+# ---- per-architecture compilers -------------------------------------------------------------------------------
+def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", static_weights=False):
+    """nets_imgnet.ResNet50 (or the reference's own class: same attribute names) -> Plan."""
+    assert not model.training, "the fused pipeline folds BatchNorm: call model.eval() first"
+    P = Plan(batch, device, model.qbit if hasattr(model, "qbit") else model.conv1.q_bit, static_weights)
+    res_f16 = residual == "f16"
+    x = P.input_nchw(3, size, size)
+    blocks = [b for li in range(1, 5) for b in getattr(model, f"layer{li}")]
+
+    def consumers(block):
+        ks = [_k32(block.conv1.Ka)]
+        if block.downsample is not None:
+            ks.append(_k32(block.downsample[0].Ka))
+        return ks
+
+    xc = P.quantize_input(x, _k32(model.conv1.Ka))
+    stem = P.conv(xc, model.conv1, bn=model.bn1, relu=True, codes=consumers(blocks[0]))
+    mp = model.maxpool
+    k_, s_, p_ = (mp.kernel_size, mp.stride, mp.padding)
+    cur_codes = {kd: P.maxpool(t, k_, s_, p_) for kd, t in stem["codes"].items()}
+    cur_res = None
+    for i, b in enumerate(blocks):
+        nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+        o1 = P.conv(cur_codes[_k32(b.conv1.Ka)], b.conv1, bn=b.bn1, relu=True, codes=[_k32(b.conv2.Ka)])
+        o2 = P.conv(o1["codes"][_k32(b.conv2.Ka)], b.conv2, bn=b.bn2, relu=True, codes=[_k32(b.conv3.Ka)])
+        if b.downsample is not None:
+            ds = P.conv(cur_codes[_k32(b.downsample[0].Ka)], b.downsample[0], bn=b.downsample[1], relu=False,
+                        f16=res_f16, f32=not res_f16)
+            res = ds["f16"] if res_f16 else ds["f32"]
+        else:
+            res = cur_res
+        need_val = nxt is None or nxt.downsample is None        # someone adds / pools the un-quantized value
+        o3 = P.conv(o2["codes"][_k32(b.conv3.Ka)], b.conv3, bn=b.bn3, relu=True, residual=res,
+                    codes=consumers(nxt) if nxt is not None else [], f16=need_val and res_f16, f32=need_val and not res_f16)
+        cur_codes = o3["codes"]
+        cur_res = o3["f16"] if res_f16 else o3["f32"]
+    feat = P.avgpool(cur_res)
+    fcq = P.quantize_flat(feat, model.fc.in_features, _k32(model.fc.Ka))
+    out = P.conv(fcq, model.fc, f32=True, linear=True)
+    P.output = out["f32"].buf.view(batch, -1)
+    return P
+
+
+def compile_vgg16(model, batch, size=32, device="cuda", static_weights=False):
+    """nets_cifar.VGG16_Q -> Plan (conv+bias -> BN -> ReLU chains, 2x2 max-pools on codes, 3 quantized FCs)."""
+    assert not model.training
+    first = model.layer1[0]
+    P = Plan(batch, device, first.q_bit, static_weights)
+    x = P.input_nchw(3, size, size)
+    seq = []
+    for li in range(1, 6):
+        seq += list(getattr(model, f"layer{li}"))
+    fcs = [model.fc1[2], model.fc2[0], model.fc3]
+    convs = [m for m in seq if isinstance(m, nn.Conv2d)]
+    cur = P.quantize_input(x, _k32(convs[0].Ka))
+    i = 0
+    while i < len(seq):
+        m = seq[i]
+        if isinstance(m, nn.Conv2d):
+            bn = seq[i + 1]
+            assert isinstance(bn, nn.BatchNorm2d) and isinstance(seq[i + 2], nn.ReLU)
+            ci = convs.index(m)
+            nxt_k = _k32(convs[ci + 1].Ka) if ci + 1 < len(convs) else _k32(fcs[0].Ka)
+            cur = P.conv(cur, m, bn=bn, relu=True, codes=[nxt_k])["codes"][nxt_k]
+            i += 3
+        elif isinstance(m, nn.MaxPool2d):
+            cur = P.maxpool(cur, m.kernel_size, m.stride, m.padding)
+            i += 1
+        else:
+            raise NotImplementedError(type(m))
+    assert cur.h == 1 and cur.w == 1, "VGG16_Q plan expects a 1x1 map before the classifier (32x32 input)"
+    for j, fc in enumerate(fcs):
+        last = j == len(fcs) - 1
+        nk = None if last else _k32(fcs[j + 1].Ka)
+        o = P.conv(cur, fc, relu=not last, codes=[] if last else [nk], f32=last, linear=True)
+        cur = o["f32"] if last else o["codes"][nk]
+    P.output = cur.buf.view(batch, -1)
+    return P
+
+
+def compile_mobilenetv1(model, batch, size, device="cuda", static_weights=False):
+    """nets_imgnet / nets_cifar MobileNetV1_Q -> Plan (stem, 13 depthwise + pointwise pairs, pool, classifier)."""
+    assert not model.training
+    feats = list(model.model)
+    pool = feats[-1]
+    blocks = feats[:-1]
+    stem = blocks[0]
+    P = Plan(batch, device, stem[0].q_bit, static_weights)
+    x = P.input_nchw(3, size, size)
+    layers = []                                   # (conv, bn) in order
+    for blk in blocks:
+        mods = list(blk)
+        for j in range(0, len(mods), 3):
+            layers.append((mods[j], mods[j + 1]))
+    quant_fc = hasattr(model.fc, "Ka")
+    cur = P.quantize_input(x, _k32(layers[0][0].Ka))
+    for j, (conv, bn) in enumerate(layers):
+        last = j == len(layers) - 1
+        if last:
+            o = P.conv(cur, conv, bn=bn, relu=True, f16=True)
+            cur = o["f16"]
+        else:
+            nk = _k32(layers[j + 1][0].Ka)
+            cur = P.conv(cur, conv, bn=bn, relu=True, codes=[nk])["codes"][nk]
+    if isinstance(pool, nn.AvgPool2d):
+        assert cur.h == pool.kernel_size and cur.w == pool.kernel_size, "AvgPool2d(7) expects a 7x7 map (224x224 input)"
+    feat = P.avgpool(cur)
+    if quant_fc:
+        fcq = P.quantize_flat(feat, model.fc.in_features, _k32(model.fc.Ka))
+        P.output = P.conv(fcq, model.fc, f32=True, linear=True)["f32"].buf.view(batch, -1)
+    else:
+        out = torch.empty((batch, model.fc.out_features), dtype=torch.float32, device=device)
+        P.keep.append(out)
+        P.torch_op(lambda: torch.addmm(model.fc.bias, feat, model.fc.weight.t(), out=out))
+        P.output = out
+    return P

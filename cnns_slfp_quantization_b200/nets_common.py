@@ -85,23 +85,37 @@ def classifier_module(model):
     return last
 
 
-def recenter_classifier(model, x, gain=1.0, seed=7):
+def classifier_weight(fc, scale, seed=7):
+    """Seeded N(0,1) classifier weight times `scale` (the fixture stores only the scalar and the bias)."""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(fc.out_features, fc.in_features, generator=g, dtype=torch.float64)
+    return (w * float(scale)).float()
+
+
+def recenter_classifier(model, x, seed=7):
     """Random-init nets predict one class for every image (SURVEY.md section 8c caveat 1).  Make top-1
-    image dependent: weight ~ N(0, gain/sqrt(fan_in)), bias = -W . mean(feature) over the probe batch
-    x.  Call on a float32 (q_bit 32) instance; returns (weight, bias) to copy into other instances."""
+    image dependent: weight = scale * N(0,1) with unit-variance logits on the probe batch x, and
+    bias = -W . mean(feature).  Call on a float32 (q_bit 32) instance; returns (scale, bias)."""
     fc = classifier_module(model)
     feats = []
     h = fc.register_forward_hook(lambda mod, inp, out: feats.append(inp[0].detach()))
     with torch.no_grad():
         model(x)
     h.remove()
-    f = feats[0].reshape(-1, fc.in_features).double()
-    g = torch.Generator().manual_seed(seed)
-    w = torch.randn(fc.out_features, fc.in_features, generator=g, dtype=torch.float64) * gain / np.sqrt(fc.in_features)
+    f = feats[0].reshape(-1, fc.in_features).double().cpu()
+    w = classifier_weight(fc, 1.0, seed).double()
     f_c = f - f.mean(0, keepdim=True)
-    w = w / (f_c @ w.T).std().clamp_min(1e-12)               # unit-variance logits on the probe batch
-    b = -(w @ f.mean(0))
-    return w.float().to(fc.weight.device), b.float().to(fc.weight.device)
+    scale = 1.0 / float((f_c @ w.T).std().clamp_min(1e-12))
+    w = classifier_weight(fc, scale, seed)
+    b = -(w.double() @ f.mean(0)).float()
+    return scale, b
+
+
+def apply_classifier(model, scale, bias, seed=7):
+    fc = classifier_module(model)
+    with torch.no_grad():
+        fc.weight.copy_(classifier_weight(fc, scale, seed).to(fc.weight.device))
+        fc.bias.copy_(torch.as_tensor(bias, dtype=torch.float32).to(fc.bias.device))
 
 
 def synth_images(batch, size, seed=1234, channels=3):

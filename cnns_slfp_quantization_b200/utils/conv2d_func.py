@@ -191,6 +191,8 @@ def _conv_forward(self, input, bias_q):
 def conv2d_Q(q_bit, Kw, Ka):
     """utils/conv2d_func.py:8-26."""
     class Conv2d_Q(_QuantTapsMixin, nn.Conv2d):
+        _slfp_bias_scaled = False       # bias goes into the conv un-scaled (conv2d_func.py:23)
+
         def __init__(self, in_channels, out_channels, kernel_size, Kw=Kw, Ka=Ka,
                      stride=1, padding=0, dilation=1, groups=1, bias=False):
             super(Conv2d_Q, self).__init__(in_channels, out_channels, kernel_size, stride,
@@ -211,6 +213,8 @@ def conv2d_Q(q_bit, Kw, Ka):
 def conv2d_Q_bias(q_bit, Kw, Ka):
     """utils/conv2d_func.py:28-48."""
     class Conv2d_Q(_QuantTapsMixin, nn.Conv2d):
+        _slfp_bias_scaled = True        # bias / Ka / Kw (conv2d_func.py:44)
+
         def __init__(self, in_channels, out_channels, kernel_size, Kw=Kw, Ka=Ka, stride=1, padding=0, dilation=1,
                      groups=1, bias=True):
             super(Conv2d_Q, self).__init__(in_channels, out_channels, kernel_size, stride,

@@ -79,6 +79,11 @@ int slfp_quantize_f32(const float *x, size_t n, float k_div, int fmt, unsigned f
 int slfp_quantize_nhwc_f32(const float *x, size_t npix, int c, int c_phys, float k_div, int fmt,
                            uint8_t *codes, slfp_stream_t stream);
 
+/* Same quantizer reading an NCHW float32 tensor (the network input as the reference's DataLoader
+ * delivers it: n x c x hw) and writing NHWC codes with c_phys (multiple of 4) channels. */
+int slfp_quantize_nchw_f32(const float *x, int n, int c, size_t hw, int c_phys, float k_div, int fmt,
+                           uint8_t *codes, slfp_stream_t stream);
+
 /* codes -> float32 (exactly the value the reference's fake-quant tensor would hold) */
 int slfp_dequantize(const uint8_t *codes, size_t n, int fmt, float *out, slfp_stream_t stream);
 

@@ -65,10 +65,11 @@ if __name__ == "__main__":
         sd = nc.synth_state_dict(m0)
         m0.load_state_dict(sd, strict=False)
         nc.set_scales(m0, np.ones(64), np.ones(64))
-        fcw, fcb = nc.recenter_classifier(m0, x)
+        fc_scale, fcb = nc.recenter_classifier(m0, x)
         fc_name = [n for n, mod in m0.named_modules() if mod is nc.classifier_module(m0)][0]
-        sd[fc_name + ".weight"], sd[fc_name + ".bias"] = fcw, fcb
-        out[f"{name}.fc_weight"], out[f"{name}.fc_bias"] = fcw.numpy(), fcb.numpy()
+        sd[fc_name + ".weight"] = nc.classifier_weight(nc.classifier_module(m0), fc_scale)
+        sd[fc_name + ".bias"] = fcb
+        out[f"{name}.fc_scale"], out[f"{name}.fc_bias"] = np.float64(fc_scale), fcb.numpy()
         ka, kw = calibrate(name, sd, x)
         m = ref_net(name, qbit).eval()
         m.load_state_dict(sd, strict=False)
