@@ -28,7 +28,7 @@ class SlfpEpilogue(ctypes.Structure):
     _fields_ = [("bias_q", c_vp), ("post_a", c_f), ("post_b", c_f), ("ch_scale", c_vp), ("ch_shift", c_vp),
                 ("residual", c_vp), ("residual_f16", c_i), ("relu", c_i), ("y_f32", c_vp), ("y_f16", c_vp),
                 ("y_codes", c_vp), ("next_k_div", c_f), ("next_fmt", c_i), ("k_phys_out", c_i),
-                ("y_codes2", c_vp), ("next_k_div2", c_f)]
+                ("y_codes2", c_vp), ("next_k_div2", c_f), ("ch_mul", c_vp), ("ch_add", c_vp)]
 
 
 _SIGS = {

@@ -19,10 +19,14 @@ struct DirectParams {
 __device__ __forceinline__ void epilogue_store(const SlfpEpilogue& e, float t, size_t pix, int k, int Kout,
                                                const uint32_t* tab) {
     (void)tab;
-    if (e.bias_q) t += __ldg(e.bias_q + k);
-    t = t * e.post_a;
-    t = t * e.post_b;
-    if (e.ch_scale) t = fmaf(t, __ldg(e.ch_scale + k), __ldg(e.ch_shift + k));
+    if (e.ch_mul) {
+        t = fmaf(t, __ldg(e.ch_mul + k), __ldg(e.ch_add + k));        // folded affine (fused eval pipeline)
+    } else {
+        if (e.bias_q) t += __ldg(e.bias_q + k);
+        t = t * e.post_a;
+        t = t * e.post_b;
+        if (e.ch_scale) t = fmaf(t, __ldg(e.ch_scale + k), __ldg(e.ch_shift + k));
+    }
     const size_t off = pix * Kout + k;
     if (e.residual)
         t += e.residual_f16 ? __half2float(reinterpret_cast<const __half*>(e.residual)[off])

@@ -79,6 +79,18 @@ __device__ __forceinline__ void quant_elem(float x, const DivK& k_div, bool zz, 
     }
 }
 
+// Fast element: reciprocal division (3 FMA-pipe ops, exact inside the normal range) + encode_q.  The
+// caller checks `needs_exact` (dividend so small that the quotient could round to exactly 0, where only
+// the true division classifies "zero" vs "tiny" correctly) and redoes those rare elements with div_k.
+template <int FMT>
+__device__ __forceinline__ uint32_t quant_code_fast(float x, const DivK& k) {
+    return encode_q<FMT>(div_k_fused(x, k), x);
+}
+__device__ __forceinline__ bool needs_exact(float x) {
+    const uint32_t ax = __float_as_uint(x) & 0x7fffffffu;
+    return (ax - 1u) < 0x04000000u - 1u;                 // 0 < |x| < 2^-119
+}
+
 template <int FMT, bool CODES, bool FAKEQ, bool F16>
 __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
     __shared__ uint32_t s_tab[16];
@@ -95,14 +107,28 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
 #pragma unroll
         for (int j = 0; j < kQVec; ++j) {
             const size_t off = base + (size_t)(j * kQThreads + threadIdx.x) * 4;
+            const float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
             uint32_t c[4];
             float q[4];
-            quant_elem<FMT>(v[j].x, a.k_div, zz, s_tab, c[0], q[0]);
-            quant_elem<FMT>(v[j].y, a.k_div, zz, s_tab, c[1], q[1]);
-            quant_elem<FMT>(v[j].z, a.k_div, zz, s_tab, c[2], q[2]);
-            quant_elem<FMT>(v[j].w, a.k_div, zz, s_tab, c[3], q[3]);
+            if (FMT == SLFP_FMT_SFP44_OUT || !a.k_div.fast) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) quant_elem<FMT>(xs[i], a.k_div, zz, s_tab, c[i], q[i]);
+            } else {
+                constexpr int F = FMT == SLFP_FMT_SFP44_OUT ? SLFP_FMT_SFP33 : FMT;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c[i] = quant_code_fast<F>(xs[i], a.k_div);
+                if (needs_exact(xs[0]) | needs_exact(xs[1]) | needs_exact(xs[2]) | needs_exact(xs[3])) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c[i] = encode<F>(div_k(xs[i], a.k_div));
+                }
+                if (FAKEQ || F16) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = decode<F == SLFP_FMT_SFP33>(c[i], s_tab);
+                }
+            }
             if (CODES)
-                *reinterpret_cast<uint32_t*>(a.codes + off) = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+                *reinterpret_cast<uint32_t*>(a.codes + off) =
+                    __byte_perm(__byte_perm(c[0], c[1], 0x0040), __byte_perm(c[2], c[3], 0x0040), 0x5410);
             if (FAKEQ) stg_stream(reinterpret_cast<float4*>(a.fakeq + off), make_float4(q[0], q[1], q[2], q[3]));
             if (F16) {
                 __half2 h0 = __floats2half2_rn(q[0], q[1]), h1 = __floats2half2_rn(q[2], q[3]);

@@ -106,6 +106,18 @@ __host__ __device__ __forceinline__ float div_k(float x, const DivK& d) {
     return div_rn(x, d.k);
 }
 
+// Branch-free variant for the fused conv epilogue: always the reciprocal sequence.  Outside the range
+// where the sequence is exact the quotient only decides a CLASS (saturated / tiny / zero / NaN), which it
+// still gets right: an overflowing intermediate yields NaN or Inf (encode_q maps both to "saturated"
+// unless the dividend itself was NaN) and a vanishing one yields a sub-0.0625 value ("tiny") or 0 for 0.
+// (Only a dividend below 2^-119 whose true quotient rounds to exactly 0 can be classed "tiny" instead of
+// "zero"; conv outputs that small do not occur and the stand-alone quantizer uses div_k.)
+__host__ __device__ __forceinline__ float div_k_fused(float x, const DivK& d) {
+    const float q0 = x * d.rk;
+    const float r = fmaf(-q0, d.k, x);
+    return fmaf(r, d.rk, q0);
+}
+
 // ---- encode ------------------------------------------------------------------------------------
 template <int FMT>
 __host__ __device__ __forceinline__ uint32_t encode(float v) {
@@ -144,6 +156,55 @@ __host__ __device__ __forceinline__ uint32_t encode(float v) {
     u |= sg;
     u = (a == 0u) ? kCodeZero : u;                           // sign(+-0) = 0
     u = (a > kBitsInf) ? kCodeNaN : u;
+    return u;
+}
+
+// encode() for a quotient q = div_k_fused(src, K): NaN is decided by the dividend; a NaN / Inf quotient
+// produced by overflow inside the reciprocal sequence falls into the saturation class.
+template <int FMT>
+__host__ __device__ __forceinline__ uint32_t encode_q(float q, float src) {
+    const uint32_t bq = f2u(q);
+    uint32_t u;
+    if ((bq & 0x7fffffffu) > kBitsInf) {        // quotient NaN (overflow artefact or NaN dividend)
+        const uint32_t bs = f2u(src);
+        u = ((bs & 0x7fffffffu) > kBitsInf) ? kCodeNaN : ((FMT == SLFP_FMT_SFP33 ? 63u : kCodeSat) | ((bs >> 24) & 0x80u));
+    } else {
+        u = encode<FMT>(q);
+    }
+    return u;
+}
+
+// encode() specialised for q >= +0 and not NaN (every quantize-on-store in the nets follows a ReLU):
+// no sign / NaN handling, and the SLFP round-half-even of 16 m plus the log-converter correction are done
+// with float adds on the FMA pipe (magic-number rounding, saturating adds) instead of integer-ALU ops.
+__host__ __device__ __forceinline__ float sat01(float x) {
+#ifdef __CUDA_ARCH__
+    return __saturatef(x);
+#else
+    return x < 0.f ? 0.f : (x > 1.f ? 1.f : x);
+#endif
+}
+template <int FMT>
+__host__ __device__ __forceinline__ uint32_t encode_relu(float q) {
+    const uint32_t b = f2u(q);
+    uint32_t u;
+    if (FMT == SLFP_FMT_SFP33) {
+        const uint32_t r = b + 0x7ffffu + ((b >> 20) & 1u);
+        u = (r >> 20) - ((127u - 4u) << 3);
+        u = (b >= kBits15) ? 63u : u;
+        u = (b < kBits0125) ? 8u : u;
+    } else {
+        const float m16 = u2f((b & 0x007fffffu) | 0x41800000u);          // 16 m in [16, 32)
+        const float r = m16 + 12582912.0f;                               // rne(16 m) in the low mantissa bits
+        const float c1 = sat01(r - 12582929.0f);                         // 1 if rne >= 18  (i >= 2)
+        const float c2 = sat01(r - 12582942.0f);                         // 1 if rne >= 31  (i >= 15)
+        const float r2 = (r + c1) - c2;                                  // + log-converter correction
+        u = ((b >> 19) & 0xff0u) + f2u(r2) - (0x4b400000u + 1984u);
+        u = (b > kBitsSat8) ? kCodeSat : u;
+        u = (b < kBits0125) ? 16u : u;
+    }
+    const uint32_t tz = b < 1u ? b : 1u;                                 // 0 for +0, else "tiny"
+    u = (b < kBits0625) ? tz : u;
     return u;
 }
 

@@ -68,6 +68,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+// [reg + compile-time-unknown base]: lets ptxas keep `base` as the instruction's address offset register
+__device__ __forceinline__ uint32_t lds32_off(uint32_t off, uint32_t base) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(off + base));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

@@ -134,24 +134,32 @@ class Plan:
                                           kw, self.wfmt, wbuf.data_ptr() if dense else None,
                                           None if dense else wbuf.data_ptr(), None))
         epi = nv.SlfpEpilogue()
+        # Fold bias, post-scale and eval BatchNorm into one per-channel affine y = acc * mul + add
+        # (float64, rounded once): mul = Ka*Kw*bn_scale, add = bias_q*Ka*Kw*bn_scale + bn_shift.
+        pa, pb = ((kw, ka) if linear else (ka, kw))
+        post = torch.full((K,), float(np.float32(pa)) * float(np.float32(pb)), dtype=torch.float64, device=self.dev)
+        mul = post.clone()
+        add = torch.zeros((K,), dtype=torch.float64, device=self.dev)
         if mod.bias is not None:
             # conv2d_Q_bias: bias/Ka/Kw (conv2d_func.py:44); linear_Q: bias/Kw/Ka (:63); plain conv2d_Q: raw bias
-            b = mod.bias.detach()
+            b = mod.bias.detach().double().to(self.dev)
             if linear:
-                bq = b / mod.Kw / mod.Ka
+                bq = b / float(mod.Kw) / float(mod.Ka)
             elif getattr(mod, "_slfp_bias_scaled", True):
-                bq = b / mod.Ka / mod.Kw
+                bq = b / float(mod.Ka) / float(mod.Kw)
             else:
                 bq = b
-            bq = bq.float().contiguous()
-            self.keep.append(bq)
-            epi.bias_q = bq.data_ptr()
-        epi.post_a, epi.post_b = (kw, ka) if linear else (ka, kw)
+            add = bq * post
         if bn is not None:
-            sc_, sh_ = fold_bn(bn)
-            sc_, sh_ = sc_.to(self.dev), sh_.to(self.dev)
-            self.keep += [sc_, sh_]
-            epi.ch_scale, epi.ch_shift = sc_.data_ptr(), sh_.data_ptr()
+            g = bn.weight.detach().double() if bn.weight is not None else torch.ones(K, dtype=torch.float64, device=self.dev)
+            be = bn.bias.detach().double() if bn.bias is not None else torch.zeros(K, dtype=torch.float64, device=self.dev)
+            sc_ = (g / torch.sqrt(bn.running_var.detach().double() + bn.eps)).to(self.dev)
+            sh_ = (be.to(self.dev) - bn.running_mean.detach().double().to(self.dev) * sc_)
+            mul, add = mul * sc_, add * sc_ + sh_
+        mul32, add32 = mul.float().contiguous(), add.float().contiguous()
+        self.keep += [mul32, add32]
+        epi.ch_mul, epi.ch_add = mul32.data_ptr(), add32.data_ptr()
+        epi.post_a, epi.post_b = pa, pb
         if residual is not None:
             assert residual.kind in ("f16", "f32") and (residual.n, residual.h, residual.w, residual.c) == (x.n, Ho, Wo, K)
             epi.residual, epi.residual_f16 = residual.buf.data_ptr(), 1 if residual.kind == "f16" else 0

@@ -127,6 +127,13 @@ typedef struct {
     int k_phys_out;        /* physical channel count of y_codes (>= k, multiple of 16)           */
     uint8_t *y_codes2;     /* second consumer with a different Ka (e.g. a downsample branch)     */
     float next_k_div2;
+    /* Folded form used by the fused eval pipeline: when ch_mul != NULL the per-channel affine
+     *     y = acc * ch_mul[k] + ch_add[k]
+     * REPLACES bias_q / post_a / post_b / ch_scale / ch_shift (the caller folds them in float64:
+     * ch_mul = Ka*Kw*bn_scale, ch_add = bias_q*Ka*Kw*bn_scale + bn_shift).  One FMA per element;
+     * differs from the unfolded order by float32 rounding only. */
+    const float *ch_mul;
+    const float *ch_add;
 } SlfpEpilogue;
 
 /* Weight preparation: replaces `self.quantize_weight(self.weight/self.Kw)` (conv2d_func.py:22):

@@ -38,3 +38,26 @@ extern "C" size_t hostcheck_divk_mismatches(const float* x, size_t n, float k) {
     }
     return bad;
 }
+
+// encode_relu(q) must equal encode(q) for every q >= +0 that is not NaN; returns the mismatch count.
+extern "C" size_t hostcheck_encode_relu_mismatches(const float* q, size_t n, int fmt) {
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t a = fmt == SLFP_FMT_SFP33 ? encode_relu<SLFP_FMT_SFP33>(q[i]) : encode_relu<SLFP_FMT_SLFP34_ACT>(q[i]);
+        const uint32_t b = fmt == SLFP_FMT_SFP33 ? encode<SLFP_FMT_SFP33>(q[i]) : encode<SLFP_FMT_SLFP34_ACT>(q[i]);
+        bad += a != b;
+    }
+    return bad;
+}
+// encode_q(div_k_fused(x, K), x) against encode(x / K)
+extern "C" size_t hostcheck_fused_quant_mismatches(const float* x, size_t n, float k, int fmt) {
+    const DivK d = make_divk(k);
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float q = div_k_fused(x[i], d);
+        const uint32_t a = fmt == SLFP_FMT_SFP33 ? encode_q<SLFP_FMT_SFP33>(q, x[i]) : encode_q<SLFP_FMT_SLFP34_ACT>(q, x[i]);
+        const uint32_t b = fmt == SLFP_FMT_SFP33 ? encode<SLFP_FMT_SFP33>(x[i] / k) : encode<SLFP_FMT_SLFP34_ACT>(x[i] / k);
+        bad += a != b;
+    }
+    return bad;
+}
