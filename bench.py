@@ -269,6 +269,11 @@ def main():
         conv_ms = sum(d[0] for d in dense)
         conv_fl = sum(d[1] for d in dense)
         all_ms = {k: sum(a.elapsed_time(b) for a, b, _ in v) for k, v in prof.items()}
+        if os.environ.get("SLFP_BENCH_LAYERS"):            # per-layer dump for kernel work (not part of the JSON line)
+            with open(os.environ["SLFP_BENCH_LAYERS"], "w") as f:
+                for (a, b, _), (fl, is_dense, desc) in zip(conv, plan.conv_flops):
+                    ms_ = a.elapsed_time(b)
+                    f.write(f"{desc:32s} {ms_ * 1e3:9.1f} us {fl / ms_ / 1e9:8.1f} TFLOP/s\n")
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
         roof = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all dense conv launches of one step)",

@@ -10,7 +10,7 @@ import torch
 
 from .build import LIB_PATH
 
-FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT = 0, 1, 2, 3
+FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU = 0, 1, 2, 3, 4, 5
 ACT_STL, ACT_SWISH, ACT_SIGMOID = 0, 1, 2
 SGD_NORMAL, SGD_DSGD, SGD_SSGD = 0, 1, 2
 Q_LAYEROUT_ZERO_IS_ZERO = 1
@@ -48,7 +48,7 @@ _SIGS = {
     "slfp_act_fwd": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
     "slfp_act_bwd": (c_i, [c_vp, c_vp, c_sz, c_i, c_vp, c_vp]),
     "slfp_sgd_step": (c_i, [c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_vp]),
-    "slfp_maxpool_codes": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp]),
+    "slfp_maxpool_codes": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp]),
     "slfp_avgpool_nhwc": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_vp, c_vp]),
     "slfp_quantize_host_f32": (c_i, [c_vp, c_sz, c_f, c_i, c_vp, c_vp]),
 }
@@ -135,6 +135,11 @@ def fmt_for(q_bit, kind):
     if q_bit == 8:
         return FMT_SLFP34_ACT if kind == "act" else FMT_SLFP34_WGT
     raise ValueError(f"no 8-bit code format for q_bit={q_bit}")
+
+
+def relu_fmt(fmt):
+    """The unsigned post-ReLU code format with the same grid as the signed activation format `fmt`."""
+    return FMT_SFP33_RELU if fmt in (FMT_SFP33, FMT_SFP33_RELU) else FMT_SLFP34_RELU
 
 
 def dense_flat(t):

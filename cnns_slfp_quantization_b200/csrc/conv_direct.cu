@@ -128,6 +128,9 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
     if (p.Ho <= 0 || p.Wo <= 0 || d->n <= 0) return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd(grouped): empty output");
     if (d->groups <= 0 || d->c % d->groups || d->k % d->groups)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd(grouped): channels not divisible by groups");
+    if ((d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_ACT) ||
+        (epi->y_codes && epi->next_fmt != SLFP_FMT_SFP33 && epi->next_fmt != SLFP_FMT_SLFP34_ACT))
+        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): the stencil kernels read and write the signed code formats only");
     const bool sfp = d->fmt == SLFP_FMT_SFP33;
     const bool depthwise = d->groups == d->c && d->k == d->c && (d->c_phys % 4) == 0 && (((uintptr_t)x_codes) & 3u) == 0;
     const size_t total = depthwise ? (size_t)d->n * p.Ho * p.Wo * (d->c_phys / 4) : (size_t)d->n * p.Ho * p.Wo * d->k;
@@ -254,6 +257,8 @@ int conv2d_bwd_direct(const SlfpConvDesc* d, const float* gy, const uint8_t* x_c
     p.Cw = d->groups > 1 ? d->c / d->groups : d->c_phys;
     p.ka = ka; p.kw = kw; p.dx = dx; p.dwt = dwt; p.so = so; p.sc = sc; p.sr = sr; p.ss = ss; p.db = db;
     const size_t npix = (size_t)d->n * p.Ho * p.Wo;
+    if (d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_ACT)
+        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_bwd: activation codes must be in a signed quantizer format");
     const bool sfp_w = wfmt == SLFP_FMT_SFP33, sfp_a = d->fmt == SLFP_FMT_SFP33;
     int rc = 0;
     if (dx) {
@@ -326,6 +331,33 @@ __global__ void __launch_bounds__(256) maxpool_codes_kernel(const uint8_t* __res
     }
 }
 
+// Post-ReLU (unsigned, monotone) codes: byte-wise unsigned max, 16 channels per thread.  HBM-bound: each
+// input byte is read once from DRAM (window overlap hits L1/L2), one 16-byte store per thread.
+__global__ void __launch_bounds__(256) maxpool_ucodes_kernel(const uint8_t* __restrict__ x, int N, int H, int W, int Cp,
+                                                             int kh, int kw, int stride, int pad, int Ho, int Wo,
+                                                             uint8_t* __restrict__ y) {
+    const int cq = Cp >> 4;
+    const size_t total = (size_t)N * Ho * Wo * cq;
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+        const int c0 = (int)(idx % cq) * 16;
+        const size_t pix = idx / cq;
+        const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
+        uint4 best = make_uint4(0u, 0u, 0u, 0u);
+        for (int r = 0; r < kh; ++r) {
+            const int hi = ho * stride - pad + r;
+            if (hi < 0 || hi >= H) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int wi = wo * stride - pad + s;
+                if (wi < 0 || wi >= W) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * Cp + c0));
+                best.x = __vmaxu4(best.x, v.x); best.y = __vmaxu4(best.y, v.y);
+                best.z = __vmaxu4(best.z, v.z); best.w = __vmaxu4(best.w, v.w);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + pix * Cp + c0) = best;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, int hw, int C, float* __restrict__ y) {
     const int n = blockIdx.y;
@@ -341,11 +373,20 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, i
 
 using namespace slfp;
 
-extern "C" int slfp_maxpool_codes(const uint8_t* x, int n, int h, int w, int c_phys, int kh, int kw_, int stride,
+extern "C" int slfp_maxpool_codes(const uint8_t* x, int n, int h, int w, int c_phys, int fmt, int kh, int kw_, int stride,
                                   int pad, uint8_t* y, slfp_stream_t stream) {
     if (!x || !y || (c_phys & 3) || (((uintptr_t)x | (uintptr_t)y) & 3u))
         return set_error(SLFP_ERR_BAD_ARG, "slfp_maxpool_codes: bad arguments");
     const int Ho = (h + 2 * pad - kh) / stride + 1, Wo = (w + 2 * pad - kw_) / stride + 1;
+    if (fmt == SLFP_FMT_SLFP34_RELU || fmt == SLFP_FMT_SFP33_RELU) {
+        if ((c_phys & 15) || (((uintptr_t)x | (uintptr_t)y) & 15u))
+            return set_error(SLFP_ERR_BAD_ARG, "slfp_maxpool_codes: post-ReLU codes need c_phys %% 16 == 0 and 16-byte alignment");
+        const size_t tot = (size_t)n * Ho * Wo * (c_phys / 16);
+        if (tot == 0) return 0;
+        const int g = (int)min((size_t)num_sms() * 32, ceil_div_sz(tot, 256));
+        maxpool_ucodes_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c_phys, kh, kw_, stride, pad, Ho, Wo, y);
+        return check_launch("maxpool_ucodes_kernel");
+    }
     const size_t total = (size_t)n * Ho * Wo * (c_phys / 4);
     if (total == 0) return 0;
     const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(total, 256));

@@ -552,8 +552,16 @@ static int launch_igemm(const CUtensorMap& tmap, const IgemmParams& p, cudaStrea
     return check_launch("conv_igemm_kernel");
 }
 
+bool conv2d_fwd_dense_v2_supported(const SlfpConvDesc* d);
+int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st);
+
 int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi,
                      cudaStream_t st) {
+    // c_phys % 16 == 0: the warp-specialised TMA-im2col kernel (conv_igemm_v2.cu); this file keeps the
+    // 4-channel network-input layout (the 7x7 / 3x3 stems), whose taps are narrower than a TMA box row.
+    if (conv2d_fwd_dense_v2_supported(d)) return conv2d_fwd_dense_v2(d, x_codes, w_f16, epi, st);
+    if (epi->y_codes && epi->next_fmt != SLFP_FMT_SLFP34_ACT && epi->next_fmt != SLFP_FMT_SFP33)
+        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: the 4-channel-input kernel writes signed code formats only");
     if (d->c_phys != 4 && (d->c_phys % 16) != 0)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: c_phys=%d must be 4 or a multiple of 16", d->c_phys);
     if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33)

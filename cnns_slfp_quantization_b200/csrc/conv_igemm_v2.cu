@@ -1,0 +1,789 @@
+// conv_igemm_v2.cu -- dense SLFP/SFP convolution forward, warp-specialised implicit GEMM for sm_100a.
+//
+// Replaces Conv2d_Q.forward / Linear_Q.forward of the reference (utils/conv2d_func.py:20-25, 41-47,
+// 60-65).  Same math as conv_igemm_sm100.cu (which stays as the path for the 4-channel stem layout):
+//      D[m, n] = sum_k A[m, k] * B[n, k]     m = output pixel, n = output channel, k = (r, s, c)
+// with A = the float16 image of the 8-bit activation codes (NHWC, c_phys % 16 == 0) and B = the float16
+// image of weight_q (KRSC).  What changed is who does what - the first kernel was bound by CUDA-core
+// instruction issue (profiles/r01_launches_baseline.md), so every role below is as thin as it can be:
+//
+//   warp 0      code producer: ONE thread issues TMA im2col loads (cp.async.bulk.tensor.4d...im2col) of the
+//               128 pixels x 64 channels code tile of a K block - stride, padding, dilation, image borders
+//               (zero fill = code 0 = 0.0) and the M tail are the TMA unit's business - into a 4-deep ring
+//   warp 1      weight producer: TMA tile loads of the BLOCK_N x 64 float16 weight tile, 128B swizzle
+//   warp 2      MMA issuer: one thread, 4 x tcgen05.mma (M128 x BLOCK_N x K16, kind::f16) per K block,
+//               accumulators double-buffered in TMEM; tcgen05.commit frees the smem stage
+//   warps 4-11  decode: codes (smem) -> float16 through a bank-conflict-free lookup table (one 32-bit
+//               LDS per code; the table also applies the SLFP log converter for the post-ReLU code
+//               formats) -> the 128B-swizzled K-major A tile (smem) the UMMA descriptor reads
+//   warps 12-19 epilogue: tcgen05.ld -> folded per-channel affine (+ residual, ReLU) -> float32 / float16
+//               and quantize-on-store.  For the post-ReLU code formats the encoder is 2 integer
+//               instructions per element plus a saturating pack (slfp_common.cuh encode_relu_fast).
+// Barriers: code_full/empty[4], ab_full/empty[stages], tmem_full/empty[2].
+#include <cudaTypedefs.h>
+
+#include <stdlib.h>
+
+#include "slfp_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace slfp {
+namespace v2 {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kCodeStages = 4;
+constexpr int kCodeBytes = kBM * kBK;                  // 8 KB of codes per K block
+constexpr int kABytes = kBM * kBK * 2;                 // 16 KB float16 A tile
+constexpr int kLutBytes = 256 * 32 * 4;                // code -> f16, one copy per bank
+constexpr int kWarpCode = 0, kWarpWgt = 1, kWarpMma = 2;
+constexpr int kDecWarp0 = 4, kDecWarps = 8;
+constexpr int kEpiWarp0 = 12, kEpiWarps = 8;     // warpgroups 3-4; 8 consecutive warps cover every TMEM lane quadrant twice
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 640: launched with 96 registers per thread, re-balanced with setmaxnreg
+constexpr int kRegsLean = 64, kRegsEpi = 144;          // 12 warps x 64 + 8 warps x 144 = 61 440 <= 65 536 registers per SM
+
+struct Params {
+    uint32_t M;
+    int Kout;
+    int HoWo, Wo;
+    int S, sh, sw, ph, pw, dh, dw;
+    int num_kb, taps;
+    int cblocks;                // c_phys / 64 when c_phys % 64 == 0, else 0 (16-channel pieces)
+    int c16s;                   // c_phys / 16
+    int m_tiles, n_tiles, num_tiles;
+    int act_fmt;
+    SlfpEpilogue epi;
+    DivK next_div, next_div2;   // exact quantize-on-store (signed code formats)
+    float rk1, rk2;             // 1 / next_k_div{,2} for the post-ReLU formats
+    int epi_mode;               // 0 generic; 1 codes-only fast path; 2 fast path with float16 residual / float16 output / two consumers
+    float sc1, sc2;             // rk / 16 (fast paths quantize clamp(q/16, 0, 1))
+};
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int kBBytes = BLOCK_N * kBK * 2;
+    static constexpr int kStages = (BLOCK_N >= 256) ? 3 : 4;
+    static constexpr int kTmemCols = 2 * BLOCK_N;
+    static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
+    static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 512 + 1024;
+};
+
+// ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_t tmem_acc, int quad, int half, int lane) {
+    const SlfpEpilogue& e = p.epi;
+    const int Kout = p.Kout;
+    const bool vec4 = (Kout & 3) == 0, vec8 = (Kout & 7) == 0;
+    constexpr int kCols = BLOCK_N / 2;
+    const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
+    const int n_base = (tile % p.n_tiles) * BLOCK_N + half * kCols;
+    const bool row_ok = m < p.M;
+    const bool folded = e.ch_mul != nullptr;
+    const bool fast_codes = e.next_fmt == SLFP_FMT_SLFP34_RELU || e.next_fmt == SLFP_FMT_SFP33_RELU;
+#pragma unroll 1
+    for (int ch = 0; ch < kCols / 16; ++ch) {
+        const int n0 = n_base + ch * 16;
+        const bool store_f = n0 < Kout;                                      // warp-uniform
+        const bool store_c = (e.y_codes != nullptr) && n0 < e.k_phys_out;     // warp-uniform
+        if (!store_f && !store_c) continue;
+        uint32_t acc[16];
+        ptx::tmem_ld16(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols + ch * 16), acc);
+        const bool full = n0 + 16 <= Kout;                                     // warp-uniform
+        const size_t off = (size_t)m * Kout + n0;
+        // residual: issued before the TMEM wait so its latency overlaps
+        float res[16];
+        const bool has_res = e.residual != nullptr;
+        if (has_res) {
+            if (row_ok && full && vec8 && e.residual_f16) {
+                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(e.residual) + off);
+                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                    res[2 * i] = f.x; res[2 * i + 1] = f.y;
+                }
+            } else if (row_ok && full && vec4 && !e.residual_f16) {
+                const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.residual) + off);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 f = __ldg(rp + i);
+                    res[4 * i] = f.x; res[4 * i + 1] = f.y; res[4 * i + 2] = f.z; res[4 * i + 3] = f.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    res[i] = 0.f;
+                    if (row_ok && n0 + i < Kout)
+                        res[i] = e.residual_f16 ? __half2float(reinterpret_cast<const __half*>(e.residual)[off + i])
+                                                : reinterpret_cast<const float*>(e.residual)[off + i];
+                }
+            }
+        }
+        float v[16];
+        if (full && folded) {
+            // per-channel vectors: warp-uniform 16-byte loads (L1 broadcast), issued before the TMEM wait
+            float4 m4[4], a4[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                m4[g] = __ldg(reinterpret_cast<const float4*>(e.ch_mul + n0) + g);
+                a4[g] = __ldg(reinterpret_cast<const float4*>(e.ch_add + n0) + g);
+            }
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                v[4 * g + 0] = fmaf(__uint_as_float(acc[4 * g + 0]), m4[g].x, a4[g].x);
+                v[4 * g + 1] = fmaf(__uint_as_float(acc[4 * g + 1]), m4[g].y, a4[g].y);
+                v[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), m4[g].z, a4[g].z);
+                v[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), m4[g].w, a4[g].w);
+            }
+        } else {
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = n0 + i;
+                const int nc = n < Kout ? n : Kout - 1;
+                float t = __uint_as_float(acc[i]);
+                if (folded) {
+                    t = fmaf(t, __ldg(e.ch_mul + nc), __ldg(e.ch_add + nc));
+                } else {
+                    // the reference's order: (acc + bias_q) * Ka * Kw  (conv2d_func.py:24, :46), then the caller's affine
+                    if (e.bias_q) t += __ldg(e.bias_q + nc);
+                    t = t * e.post_a;
+                    t = t * e.post_b;
+                    if (e.ch_scale) t = fmaf(t, __ldg(e.ch_scale + nc), __ldg(e.ch_shift + nc));
+                }
+                v[i] = t;
+            }
+        }
+        if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += res[i];
+        }
+        if (e.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (!row_ok) continue;
+        if (e.y_f32 && store_f) {
+            float* yp = e.y_f32 + off;
+            if (vec4) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    if (n0 + i < Kout) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (n0 + i < Kout) yp[i] = v[i];
+            }
+        }
+        if (e.y_f16 && store_f) {
+            __half* yp = reinterpret_cast<__half*>(e.y_f16) + off;
+            if (vec8) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                    if (n0 + i < Kout) {
+                        __half2 h0 = __floats2half2_rn(v[i], v[i + 1]), h1 = __floats2half2_rn(v[i + 2], v[i + 3]);
+                        __half2 h2 = __floats2half2_rn(v[i + 4], v[i + 5]), h3 = __floats2half2_rn(v[i + 6], v[i + 7]);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(yp + i) = pk;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (n0 + i < Kout) yp[i] = __float2half_rn(v[i]);
+            }
+        }
+        if (store_c) {
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                uint8_t* yc = pass ? e.y_codes2 : e.y_codes;
+                if (!yc) continue;
+                uint32_t pk[4];
+                if (fast_codes) {
+                    // post-ReLU codes (v >= +0 here: the host requires relu for these formats): re-based
+                    // rounded bit pattern, saturating pack.  slfp_common.cuh encode_relu_fast.
+                    const float rk = pass ? p.rk2 : p.rk1;
+                    int32_t t[16];
+                    if (e.next_fmt == SLFP_FMT_SFP33_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw<true>(v[i] * rk);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw<false>(v[i] * rk);
+                    }
+                    if (!full) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) t[i] = (n0 + i < Kout) ? t[i] : 0;   // zero code in pad channels
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) pk[g] = ptx::pack_sat_u8x4(t[4 * g], t[4 * g + 1], t[4 * g + 2], t[4 * g + 3]);
+                } else {
+                    // signed code formats: the exact quantizer (IEEE quotient via the reciprocal sequence)
+                    const DivK kd = pass ? p.next_div2 : p.next_div;
+                    uint32_t c[16];
+                    const bool relu_path = e.relu && kd.k > 0.f;
+                    if (e.next_fmt == SLFP_FMT_SFP33) {
+                        if (relu_path) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) c[i] = encode_relu<SLFP_FMT_SFP33>(div_k_fused(v[i], kd));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) c[i] = encode_q<SLFP_FMT_SFP33>(div_k_fused(v[i], kd), v[i]);
+                        }
+                    } else {
+                        if (relu_path) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) c[i] = encode_relu<SLFP_FMT_SLFP34_ACT>(div_k_fused(v[i], kd));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) c[i] = encode_q<SLFP_FMT_SLFP34_ACT>(div_k_fused(v[i], kd), v[i]);
+                        }
+                    }
+                    if (!full) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) c[i] = (n0 + i < Kout) ? c[i] : 0u;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        pk[g] = __byte_perm(__byte_perm(c[4 * g], c[4 * g + 1], 0x0040), __byte_perm(c[4 * g + 2], c[4 * g + 3], 0x0040), 0x5410);
+                }
+                *reinterpret_cast<uint4*>(yc + (size_t)m * e.k_phys_out + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    }
+}
+
+// ---- fast epilogues (the fused pipeline's common cases; chosen on the host, Params::epi_mode) -----------------
+// Requirements: folded per-channel affine, ReLU, Kout % 16 == 0, no float32 output, post-ReLU code format.
+//   MODE 1: one code tensor, nothing else.  The per-channel vectors staged in shared memory are pre-scaled by
+//           1/(16 Ka_next), so ONE saturating FMA yields clamp(relu(y)/Ka_next/16, 0, 1); 2 integer ops + half a
+//           pack instruction turn it into the code (slfp_common.cuh encode_relu_fast_raw16).
+//   MODE 2: optional float16 residual, optional float16 output of relu(y), one or two code tensors.
+//
+// Stores.  A thread owns one output pixel (TMEM lane = row), so a plain store instruction would write 16 bytes
+// of 32 different rows: half-filled 32-byte sectors, measured at ~40 % of the write bandwidth of full sectors
+// (tools/ubench/store_pattern.cu).  Lane pairs therefore swap one 16-byte piece (4 SHFL) so that every store
+// instruction writes 32 contiguous bytes per row: lanes 2i / 2i+1 hold pieces (A, B) = 32 contiguous bytes of
+// rows 2i / 2i+1; afterwards `first` belongs to row 2i and `second` to row 2i+1, both at piece index lane & 1.
+__device__ __forceinline__ void pair_exchange(const uint4& A, const uint4& B, bool odd, uint4& first, uint4& second) {
+    uint4 send, recv;
+    send.x = odd ? A.x : B.x; send.y = odd ? A.y : B.y; send.z = odd ? A.z : B.z; send.w = odd ? A.w : B.w;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+    recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+    recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+    first.x = odd ? recv.x : A.x; first.y = odd ? recv.y : A.y; first.z = odd ? recv.z : A.z; first.w = odd ? recv.w : A.w;
+    second.x = odd ? B.x : recv.x; second.y = odd ? B.y : recv.y; second.z = odd ? B.z : recv.z; second.w = odd ? B.w : recv.w;
+}
+
+template <int BLOCK_N, int MODE, bool SFP33>
+__device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int next_tile, uint32_t tmem_acc, int quad, int half,
+                                              int lane, uint32_t s_mul, uint32_t s_add) {
+    constexpr int kCols = BLOCK_N / 2;
+    const int Kout = p.Kout;
+    const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
+    const int n_tile0 = (tile % p.n_tiles) * BLOCK_N;
+    const bool odd = (lane & 1) != 0;
+    // rows this lane STORES to after the pair exchange (m's parity is the lane's)
+    const uint32_t m_first = m & ~1u, m_second = m | 1u;
+    const bool ok_first = m_first < p.M, ok_second = m_second < p.M, row_ok = m < p.M;
+    const size_t row = (size_t)m * (size_t)Kout;
+    const size_t row_first = (size_t)m_first * (size_t)Kout, row_second = (size_t)m_second * (size_t)Kout;
+    const __half* resp = MODE == 2 ? reinterpret_cast<const __half*>(p.epi.residual) : nullptr;
+    __half* y16 = MODE == 2 ? reinterpret_cast<__half*>(p.epi.y_f16) : nullptr;
+    uint8_t* yc1 = p.epi.y_codes;
+    uint8_t* yc2 = MODE == 2 ? p.epi.y_codes2 : nullptr;
+    const float sc1 = p.sc1, sc2 = p.sc2;
+    if (MODE == 2 && resp != nullptr && next_tile < p.num_tiles) {
+        // push this lane's row segment of the NEXT tile's residual towards L2 (no register, no scoreboard)
+        const uint32_t mn = (uint32_t)(next_tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
+        const int nb = (next_tile % p.n_tiles) * BLOCK_N + half * kCols;
+        if (mn < p.M) {
+#pragma unroll
+            for (int c = 0; c < kCols; c += 64)
+                if (nb + c < Kout) ptx::prefetch_l2(resp + (size_t)mn * Kout + nb + c);
+        }
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < kCols / 32; ++ch) {
+        const int col = half * kCols + ch * 32;
+        const int n0 = n_tile0 + col;
+        if (n0 >= Kout) break;                                   // warp-uniform
+        const bool two = n0 + 32 <= Kout;                        // else 16 valid columns (Kout % 16 == 0)
+        uint32_t acc[32];
+        ptx::tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, acc);
+        uint4 rr[4];
+        if (MODE == 2 && resp != nullptr) {
+            rr[0] = rr[1] = rr[2] = rr[3] = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok) {
+                const uint4* rp = reinterpret_cast<const uint4*>(resp + row + n0);
+                rr[0] = __ldg(rp); rr[1] = __ldg(rp + 1);
+                if (two) { rr[2] = __ldg(rp + 2); rr[3] = __ldg(rp + 3); }
+            }
+        }
+        ptx::tmem_ld_wait();
+        uint4 pk1[2], pk2[2];                                    // code pieces of the two 16-column halves
+#pragma unroll
+        for (int o = 0; o < 32; o += 16) {
+            if (o == 16 && !two) break;
+            float v[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4 m4 = ptx::lds128_f4(s_mul + (uint32_t)(col + o + 4 * g) * 4u);
+                const float4 a4 = ptx::lds128_f4(s_add + (uint32_t)(col + o + 4 * g) * 4u);
+                v[4 * g + 0] = fmaf(__uint_as_float(acc[o + 4 * g + 0]), m4.x, a4.x);
+                v[4 * g + 1] = fmaf(__uint_as_float(acc[o + 4 * g + 1]), m4.y, a4.y);
+                v[4 * g + 2] = fmaf(__uint_as_float(acc[o + 4 * g + 2]), m4.z, a4.z);
+                v[4 * g + 3] = fmaf(__uint_as_float(acc[o + 4 * g + 3]), m4.w, a4.w);
+            }
+            if (MODE == 1) {
+                int32_t t[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i]));
+                pk1[o / 16] = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
+                                         ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+            } else {
+                if (resp != nullptr) {
+                    const uint4 ra = rr[o / 8], rb = rr[o / 8 + 1];
+                    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                        v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                    }
+                }
+                if (y16 != nullptr) {
+                    uint32_t hw[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __half2 h = __floats2half2_rn(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f));
+                        hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    uint4 f1, f2;
+                    pair_exchange(make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]), odd, f1, f2);
+                    if (ok_first) *reinterpret_cast<uint4*>(y16 + row_first + n0 + o + (odd ? 8 : 0)) = f1;
+                    if (ok_second) *reinterpret_cast<uint4*>(y16 + row_second + n0 + o + (odd ? 8 : 0)) = f2;
+                }
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((pass ? yc2 : yc1) == nullptr) continue;
+                    const float sc = pass ? sc2 : sc1;
+                    int32_t t[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i] * sc));
+                    const uint4 pk = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
+                                                ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+                    if (pass) pk2[o / 16] = pk; else pk1[o / 16] = pk;
+                }
+            }
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            uint8_t* yc = pass ? yc2 : yc1;
+            if (yc == nullptr) continue;
+            const uint4 pa = pass ? pk2[0] : pk1[0];
+            if (two) {
+                uint4 f1, f2;
+                pair_exchange(pa, pass ? pk2[1] : pk1[1], odd, f1, f2);
+                if (ok_first) *reinterpret_cast<uint4*>(yc + row_first + n0 + (odd ? 16 : 0)) = f1;
+                if (ok_second) *reinterpret_cast<uint4*>(yc + row_second + n0 + (odd ? 16 : 0)) = f2;
+            } else if (row_ok) {
+                *reinterpret_cast<uint4*>(yc + row + n0) = pa;
+            }
+        }
+    }
+}
+
+template <int BLOCK_N, int GRAN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // SW128 operand tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_a = smem;                                   // [stages][128 rows][128 B]
+    uint8_t* s_b = s_a + C::kStages * kABytes;             // [stages][BLOCK_N rows][128 B]
+    uint8_t* s_code = s_b + C::kStages * C::kBBytes;       // [kCodeStages][128 pixels][64 B]
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_code + kCodeStages * kCodeBytes);
+    float* s_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_lut) + kLutBytes);   // [2][BLOCK_N]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + C::kParBytes);
+    uint64_t* bar_cfull = s_bar;                           // [kCodeStages]  1 arrive.expect_tx
+    uint64_t* bar_cempty = bar_cfull + kCodeStages;        // [kCodeStages]  8 decode warps
+    uint64_t* bar_full = bar_cempty + kCodeStages;         // [stages]  8 decode warps + 1 weight-TMA arrive
+    uint64_t* bar_empty = bar_full + C::kStages;           // [stages]  1 tcgen05.commit
+    uint64_t* bar_tfull = bar_empty + C::kStages;          // [2]       1 tcgen05.commit
+    uint64_t* bar_tempty = bar_tfull + 2;                  // [2]       8 epilogue warps
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup ---------------------------------------------------------------------------
+    for (int i = tid; i < 256 * 32; i += kThreads) {
+        const float f = decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac);
+        s_lut[i] = (uint32_t)__half_as_ushort(__float2half_rn(f));
+    }
+    if (warp == kWarpCode && lane == 0) {
+        ptx::prefetch_tmap(&tmap_x);
+        ptx::prefetch_tmap(&tmap_w);
+        for (int s = 0; s < kCodeStages; ++s) {
+            ptx::mbar_init(ptx::smem_u32(&bar_cfull[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bar_cempty[s]), kDecWarps);
+        }
+        for (int s = 0; s < C::kStages; ++s) {
+            ptx::mbar_init(ptx::smem_u32(&bar_full[s]), kDecWarps + 1);
+            ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(ptx::smem_u32(&bar_tfull[b]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bar_tempty[b]), kEpiWarps);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == kWarpMma) ptx::tmem_alloc<C::kTmemCols>(ptx::smem_u32(s_tmem));
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const int my_tiles = ((int)blockIdx.x < p.num_tiles)
+                             ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    // register re-balance (warpgroup granularity; first statement of every role so that ptxas allocates each
+    // region against its own budget): producers / MMA / decode need few registers, the epilogue many
+    if (warp < kDecWarp0) {
+      ptx::setmaxnreg_dec<kRegsLean>();
+      if (warp == kWarpCode) {
+        // =========================== code producer: TMA im2col ===========================================
+        if (lane == 0) {
+            uint32_t cs = 0, cphase = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const uint32_t m0 = (uint32_t)(tile / p.n_tiles) * kBM;
+                const int n = (int)(m0 / (uint32_t)p.HoWo);
+                const int rem = (int)(m0 - (uint32_t)n * (uint32_t)p.HoWo);
+                const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
+                const int w0 = wo * p.sw - p.pw, h0 = ho * p.sh - p.ph;
+                int tap = 0, r = 0, s = 0, cb = 0;       // GRAN 64: cb = 64-channel block; GRAN 16: 16-channel block
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 32);
+                    const uint32_t full = ptx::smem_u32(&bar_cfull[cs]);
+                    const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
+                    if (GRAN == 64) {
+                        ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes);
+                        ptx::tma_load_im2col_4d(dst, &tmap_x, full, cb * 64, w0, h0, n, (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
+                        if (++cb == p.cblocks) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
+                    } else {
+                        int valid = p.taps * p.c16s - kb * 4;          // 16-channel pieces left in K
+                        valid = valid > 4 ? 4 : valid;
+                        ptx::mbar_arrive_expect_tx(full, (uint32_t)(valid * (kCodeBytes / 4)));
+                        for (int j = 0; j < valid; ++j) {
+                            ptx::tma_load_im2col_4d(dst + (uint32_t)(j * (kCodeBytes / 4)), &tmap_x, full, cb * 16, w0, h0, n,
+                                                    (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
+                            if (++cb == p.c16s) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
+                        }
+                    }
+                    if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kWarpWgt) {
+        // =========================== weight producer: TMA tiles (B operand) ================================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const int n0 = (tile % p.n_tiles) * BLOCK_N;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 32);
+                    const uint32_t full = ptx::smem_u32(&bar_full[stage]);
+                    ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
+                    ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
+                    if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kWarpMma) {
+        // =========================== MMA issuer ===================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc(0u, kBM, BLOCK_N);
+            uint32_t stage = 0, phase = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const uint32_t buf = (uint32_t)ti & 1u;
+                ptx::mbar_wait(ptx::smem_u32(&bar_tempty[buf]), (((uint32_t)ti >> 1) & 1u) ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(ptx::smem_u32(&bar_full[stage]), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(s_a + stage * kABytes);
+                    const uint32_t b_addr = ptx::smem_u32(s_b + stage * C::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32),
+                                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::mma_commit(ptx::smem_u32(&bar_empty[stage]));     // frees the smem stage
+                    if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
+                }
+                ptx::mma_commit(ptx::smem_u32(&bar_tfull[buf]));            // accumulator ready
+            }
+        }
+        __syncwarp();
+      }
+    } else if (warp < kDecWarp0 + kDecWarps) {
+        ptx::setmaxnreg_dec<kRegsLean>();
+        // =========================== decode: codes -> float16 A tile ==========================================
+        const int dtid = tid - kDecWarp0 * 32;                 // 0..255; chunk ids dtid and dtid + 256
+        const uint32_t lut_base = ptx::smem_u32(s_lut);        // 128-byte aligned: (code << 7) | lane*4 never carries
+        const uint32_t lane4 = (uint32_t)lane * 4u;
+        const uint32_t code_base = ptx::smem_u32(s_code) + (uint32_t)dtid * 16u;
+        uint32_t a_off[2][2];                                  // [chunk][16-byte half] byte offset inside the A stage
+        int quarter[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int id = dtid + 256 * j;
+            const int row = GRAN == 64 ? (id >> 2) : (id & 127);
+            const int q = GRAN == 64 ? (id & 3) : (id >> 7);
+            quarter[j] = q;
+            const uint32_t base = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+            a_off[j][0] = base + (uint32_t)(((q * 2) ^ (row & 7)) << 4);
+            a_off[j][1] = base + (uint32_t)(((q * 2 + 1) ^ (row & 7)) << 4);
+        }
+        const uint32_t a_base = ptx::smem_u32(s_a);
+        const int k16_total = p.taps * p.c16s;
+        uint32_t cs = 0, cphase = 0, stage = 0, phase = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                ptx::mbar_wait(ptx::smem_u32(&bar_cfull[cs]), cphase);
+                uint32_t h[2][8];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    // 16-channel pieces beyond the last filter tap (K padding) are not loaded: zeros
+                    const bool valid = GRAN == 64 || (kb * 4 + quarter[j] < k16_total);
+                    uint4 cw = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) cw = ptx::lds128_volatile(code_base + cs * kCodeBytes + (uint32_t)(j * 4096));
+                    const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t c = w[i];
+                        const uint32_t e0 = ptx::lds32_off(((c << 7) & 0x7f80u) | lane4, lut_base);
+                        const uint32_t e1 = ptx::lds32_off(((c >> 1) & 0x7f80u) | lane4, lut_base);
+                        const uint32_t e2 = ptx::lds32_off(((c >> 9) & 0x7f80u) | lane4, lut_base);
+                        const uint32_t e3 = ptx::lds32_off(((c >> 17) & 0x7f80u) | lane4, lut_base);
+                        h[j][2 * i] = __byte_perm(e0, e1, 0x5410);
+                        h[j][2 * i + 1] = __byte_perm(e2, e3, 0x5410);
+                    }
+                }
+                // the codes are in registers (the table look-ups consumed them): release the code stage
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_cempty[cs]));
+                if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
+
+                ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u);   // MMA done with this stage
+                const uint32_t a_dst = a_base + stage * kABytes;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    ptx::sts128(a_dst + a_off[j][0], h[j][0], h[j][1], h[j][2], h[j][3]);
+                    ptx::sts128(a_dst + a_off[j][1], h[j][4], h[j][5], h[j][6], h[j][7]);
+                }
+                ptx::fence_proxy_async_smem();               // generic-proxy writes -> async proxy (UMMA)
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_full[stage]));
+                if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        ptx::setmaxnreg_inc<kRegsEpi>();
+        // =========================== epilogue ===================================================================
+        const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+        const int half = (warp - kEpiWarp0) >> 2;
+        const int etid = tid - kEpiWarp0 * 32;
+        const int mode = p.epi_mode;
+        const bool sfp33 = p.epi.next_fmt == SLFP_FMT_SFP33_RELU;
+        const uint32_t s_mul = ptx::smem_u32(s_par), s_add = s_mul + BLOCK_N * 4;
+        int staged_n0 = -1;
+        // per tile: stage the per-channel vectors when the channel tile changes, then wait for the accumulator
+        auto tile_begin = [&](int ti, int tile) -> uint32_t {
+            const uint32_t buf = (uint32_t)ti & 1u;
+            if (mode != 0) {
+                // the fast modes read the folded affine from shared memory (mode 1: pre-scaled by 1/(16 Ka_next))
+                const int n_tile0 = (tile % p.n_tiles) * BLOCK_N;
+                if (n_tile0 != staged_n0) {
+                    ptx::bar_sync(1, kEpiWarps * 32);          // every epilogue warp is done with the previous vectors
+                    const float sc = mode == 1 ? p.sc1 : 1.0f;      // mode 2 keeps relu(y) itself for the float16 output
+                    for (int i = etid; i < BLOCK_N; i += kEpiWarps * 32) {
+                        const int n = n_tile0 + i;
+                        s_par[i] = n < p.Kout ? __ldg(p.epi.ch_mul + n) * sc : 0.0f;
+                        s_par[BLOCK_N + i] = n < p.Kout ? __ldg(p.epi.ch_add + n) * sc : 0.0f;
+                    }
+                    ptx::bar_sync(1, kEpiWarps * 32);
+                    staged_n0 = n_tile0;
+                }
+            }
+            ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u, 64);
+            ptx::tc_fence_after();
+            return tmem_base + buf * BLOCK_N;
+        };
+        auto tile_end = [&](int ti) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_tempty[(uint32_t)ti & 1u]));
+        };
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int next_tile = ti + 1 < my_tiles ? tile + (int)gridDim.x : p.num_tiles;
+            const uint32_t tacc = tile_begin(ti, tile);
+            if (mode == 1) {
+                if (sfp33) epilogue_fast<BLOCK_N, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                else epilogue_fast<BLOCK_N, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+            } else if (mode == 2) {
+                if (sfp33) epilogue_fast<BLOCK_N, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                else epilogue_fast<BLOCK_N, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+            } else {
+                epilogue_slab<BLOCK_N>(p, tile, tacc, quad, half, lane);
+            }
+            tile_end(ti);
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------------
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == kWarpMma) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+template <typename PFN>
+static PFN driver_fn(const char* name) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<PFN>(ptr);
+    cudaGetLastError();
+    return nullptr;
+}
+
+template <int BLOCK_N, int GRAN>
+static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const Params& p, cudaStream_t st) {
+    using C = Cfg<BLOCK_N>;
+    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        if (e != cudaSuccess) return set_error((int)e, "conv_igemm_v2: smem attribute (%d B): %s", C::kSmemBytes, cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    kern<<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, p);
+    return check_launch("conv_igemm_v2_kernel");
+}
+
+}  // namespace v2
+
+bool conv2d_fwd_dense_v2_supported(const SlfpConvDesc* d) {
+    static const bool disabled = getenv("SLFP_CONV_V1") != nullptr;
+    return !disabled && d->groups == 1 && d->c_phys % 16 == 0 && d->pad_h < 128 && d->pad_w < 128 &&
+           (d->r - 1) * d->dil_h < 256 && (d->s - 1) * d->dil_w < 256 && d->stride_h <= 8 && d->stride_w <= 8;
+}
+
+int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi,
+                        cudaStream_t st) {
+    using namespace v2;
+    const bool fast = epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU;
+    if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_RELU && d->fmt != SLFP_FMT_SFP33_RELU)
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: activation code format %d", d->fmt);
+    if (epi->y_codes && (epi->k_phys_out % 16 != 0 || epi->k_phys_out < d->k))
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: k_phys_out=%d", epi->k_phys_out);
+    if (epi->y_codes && fast && !epi->relu)
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: post-ReLU code formats need relu=1");
+    if (epi->y_codes && !fast && epi->next_fmt != SLFP_FMT_SLFP34_ACT && epi->next_fmt != SLFP_FMT_SFP33)
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: next_fmt=%d", epi->next_fmt);
+    if ((((uintptr_t)x_codes | (uintptr_t)w_f16 | (uintptr_t)epi->y_f32 | (uintptr_t)epi->y_f16 |
+          (uintptr_t)epi->y_codes | (uintptr_t)epi->y_codes2) & 15u) != 0)
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: tensors must be 16-byte aligned");
+    Params p;
+    const int Ho = (d->h + 2 * d->pad_h - d->dil_h * (d->r - 1) - 1) / d->stride_h + 1;
+    const int Wo = (d->w + 2 * d->pad_w - d->dil_w * (d->s - 1) - 1) / d->stride_w + 1;
+    if (Ho <= 0 || Wo <= 0 || d->n <= 0) return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: empty output");
+    const unsigned long long M64 = (unsigned long long)d->n * Ho * Wo;
+    if (M64 >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: more than 2^31 output pixels");
+    p.M = (uint32_t)M64;
+    p.Kout = d->k;
+    p.HoWo = Ho * Wo; p.Wo = Wo;
+    p.S = d->s; p.sh = d->stride_h; p.sw = d->stride_w; p.ph = d->pad_h; p.pw = d->pad_w; p.dh = d->dil_h; p.dw = d->dil_w;
+    p.taps = d->r * d->s;
+    const size_t pitch = slfp_conv_wpitch(d);
+    p.num_kb = (int)(pitch / kBK);
+    p.cblocks = (d->c_phys % 64 == 0) ? d->c_phys / 64 : 0;
+    p.c16s = d->c_phys / 16;
+    const int bn = d->k > 128 ? 256 : (d->k > 64 ? 128 : 64);
+    p.m_tiles = (int)((p.M + kBM - 1) / kBM);
+    p.n_tiles = (d->k + bn - 1) / bn;
+    p.num_tiles = p.m_tiles * p.n_tiles;
+    p.act_fmt = d->fmt;
+    p.epi = *epi;
+    p.next_div = make_divk(epi->y_codes ? epi->next_k_div : 1.0f);
+    p.next_div2 = make_divk(epi->y_codes2 ? epi->next_k_div2 : 1.0f);
+    p.rk1 = (float)(1.0 / (double)(epi->y_codes ? epi->next_k_div : 1.0f));
+    p.rk2 = (float)(1.0 / (double)(epi->y_codes2 ? epi->next_k_div2 : 1.0f));
+
+    p.sc1 = (float)(1.0 / (16.0 * (double)(epi->y_codes ? epi->next_k_div : 1.0f)));
+    p.sc2 = (float)(1.0 / (16.0 * (double)(epi->y_codes2 ? epi->next_k_div2 : 1.0f)));
+    p.epi_mode = 0;
+    {
+        static const bool no_fast = getenv("SLFP_EPI_GENERIC") != nullptr;
+        const bool common = !no_fast && epi->ch_mul && epi->ch_add && epi->relu && d->k % 16 == 0 && !epi->y_f32 &&
+                            (!epi->y_codes || (fast && epi->k_phys_out == d->k && epi->next_k_div > 0.f)) &&
+                            (!epi->y_codes2 || (epi->y_codes && epi->next_k_div2 > 0.f)) &&
+                            (!epi->residual || epi->residual_f16);
+        if (common) p.epi_mode = (epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->residual) ? 1 : 2;
+    }
+
+    static auto enc_tiled = driver_fn<PFN_cuTensorMapEncodeTiled_v12000>("cuTensorMapEncodeTiled");
+    static auto enc_im2col = driver_fn<PFN_cuTensorMapEncodeIm2col_v12000>("cuTensorMapEncodeIm2col");
+    if (!enc_tiled || !enc_im2col) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncode{Tiled,Im2col} not available");
+    CUtensorMap tmap_w, tmap_x;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)d->k};
+        const cuuint64_t gstr[1] = {(cuuint64_t)pitch * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc_tiled(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_f16), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    }
+    {
+        // NHWC codes as a (C, W, H, N) tensor; the pixel bounding box is the set of filter-window origins:
+        // lower corner = -pad, upper corner = pad - (filter - 1) * dilation (relative to the tensor's far edge),
+        // traversed with the convolution stride; the filter tap (r, s) is the per-load offset.
+        const cuuint64_t gdim[4] = {(cuuint64_t)d->c_phys, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+        const cuuint64_t gstr[3] = {(cuuint64_t)d->c_phys, (cuuint64_t)d->c_phys * d->w, (cuuint64_t)d->c_phys * d->w * d->h};
+        const int lower[2] = {-d->pad_w, -d->pad_h};
+        const int upper[2] = {d->pad_w - (d->s - 1) * d->dil_w, d->pad_h - (d->r - 1) * d->dil_h};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
+        CUresult cr = enc_im2col(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x_codes), gdim, gstr, lower, upper,
+                                 (cuuint32_t)(p.cblocks ? 64 : 16), (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeIm2col failed (%d)", (int)cr);
+    }
+#define SLFP_V2_CASE(BN)                                              \
+    if (bn == BN) {                                                   \
+        if (p.cblocks) return launch<BN, 64>(tmap_x, tmap_w, p, st);  \
+        return launch<BN, 16>(tmap_x, tmap_w, p, st);                 \
+    }
+    SLFP_V2_CASE(64)
+    SLFP_V2_CASE(128)
+    SLFP_V2_CASE(256)
+#undef SLFP_V2_CASE
+    return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: no tile for k=%d", d->k);
+}
+
+}  // namespace slfp

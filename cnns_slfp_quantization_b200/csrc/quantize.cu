@@ -322,6 +322,24 @@ __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
 
 }  // namespace slfp
 
+namespace slfp {
+__global__ void __launch_bounds__(256) dequantize_any_kernel(const uint8_t* __restrict__ codes, size_t n, int fmt,
+                                                             float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        out[i] = decode_act_any(codes[i], fmt, c_pow2frac);
+}
+// post-ReLU code formats, stand-alone (tests / feeding a fused layer by hand): x / K -> encode_relu_fast
+__global__ void __launch_bounds__(256) quantize_relu_kernel(const float* __restrict__ x, size_t n, DivK k, int sfp33,
+                                                            uint8_t* __restrict__ codes, float* __restrict__ fakeq) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float q = div_k(x[i], k);
+        const uint32_t c = sfp33 ? encode_relu_fast<true>(q) : encode_relu_fast<false>(q);
+        if (codes) codes[i] = (uint8_t)c;
+        if (fakeq) fakeq[i] = sfp33 ? decode_relu<true>(c, c_pow2frac) : decode_relu<false>(c, c_pow2frac);
+    }
+}
+}  // namespace slfp
+
 using namespace slfp;
 
 extern "C" int slfp_version(void) { return SLFP_B200_VERSION; }
@@ -333,6 +351,12 @@ extern "C" int slfp_quantize_f32(const float* x, size_t n, float k_div, int fmt,
     if (!x || (!codes && !fakeq && !f16)) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: null pointer");
     if (fmt == SLFP_FMT_SFP44_OUT && codes)
         return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: SFP<4,4> layer-out has no 8-bit code");
+    if (fmt == SLFP_FMT_SLFP34_RELU || fmt == SLFP_FMT_SFP33_RELU) {
+        if (f16) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_quantize_f32: post-ReLU formats have no float16 output");
+        const int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(n, 256));
+        quantize_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, make_divk(k_div), fmt == SLFP_FMT_SFP33_RELU, codes, fakeq);
+        return check_launch("quantize_relu_kernel");
+    }
     QuantArgs a{x, n, make_divk(k_div), codes, fakeq, (__half*)f16, (flags & SLFP_Q_LAYEROUT_ZERO_IS_ZERO) ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (fmt) {
@@ -382,6 +406,10 @@ extern "C" int slfp_dequantize(const uint8_t* codes, size_t n, int fmt, float* o
     if (n == 0) return 0;
     if (!codes || !out) return set_error(SLFP_ERR_BAD_ARG, "slfp_dequantize: null pointer");
     int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(n, 1024));
+    if (fmt == SLFP_FMT_SLFP34_RELU || fmt == SLFP_FMT_SFP33_RELU) {
+        dequantize_any_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(codes, n, fmt, out);
+        return check_launch("dequantize_any_kernel");
+    }
     if (fmt == SLFP_FMT_SFP33)
         dequantize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, n, out);
     else if (fmt == SLFP_FMT_SLFP34_ACT || fmt == SLFP_FMT_SLFP34_WGT)

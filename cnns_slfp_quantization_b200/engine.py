@@ -34,10 +34,11 @@ def _k32(K):
 
 class _T:
     """A device tensor of the plan: NHWC, kind in {'codes', 'f16', 'f32'}."""
-    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv")
+    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt")
 
-    def __init__(self, buf, n, h, w, c, cp, kind, kdiv=None):
+    def __init__(self, buf, n, h, w, c, cp, kind, kdiv=None, fmt=None):
         self.buf, self.n, self.h, self.w, self.c, self.cp, self.kind, self.kdiv = buf, n, h, w, c, cp, kind, kdiv
+        self.fmt = fmt                  # code format of a 'codes' tensor (signed quantizer codes or post-ReLU codes)
 
 
 def _ceil(v, m):
@@ -68,7 +69,7 @@ class Plan:
         self.bytes_hbm = 0
 
     # ---- buffers ----------------------------------------------------------------------------------------
-    def _alloc(self, n, h, w, c, kind, kdiv=None, cp=None):
+    def _alloc(self, n, h, w, c, kind, kdiv=None, cp=None, fmt=None):
         if kind == "codes":
             cp = cp or _ceil(c, 16)
             buf = torch.zeros((n, h, w, cp), dtype=torch.uint8, device=self.dev)
@@ -77,7 +78,7 @@ class Plan:
             buf = torch.empty((n, h, w, c), dtype=torch.float16 if kind == "f16" else torch.float32, device=self.dev)
         self.bytes_hbm += buf.numel() * buf.element_size()
         self.keep.append(buf)               # the pre-bound calls hold raw pointers: the plan owns the storage
-        return _T(buf, n, h, w, c, cp, kind, kdiv)
+        return _T(buf, n, h, w, c, cp, kind, kdiv, (fmt if fmt is not None else self.afmt) if kind == "codes" else None)
 
     def _call(self, fn, *args):
         def op(st):
@@ -105,9 +106,12 @@ class Plan:
                                    t.buf.data_ptr()))
         return t
 
-    def conv(self, x, mod, bn=None, relu=False, residual=None, codes=(), f16=False, f32=False, linear=False):
+    def conv(self, x, mod, bn=None, relu=False, residual=None, codes=(), f16=False, f32=False, linear=False,
+             relu_codes=True):
         """One fused convolution / linear layer.  `codes`: divisors (Ka of the consumers) to quantize-on-store
-        with (at most two distinct).  Returns {'codes': {kdiv: _T}, 'f16': _T | None, 'f32': _T | None}."""
+        with (at most two distinct).  Returns {'codes': {kdiv: _T}, 'f16': _T | None, 'f32': _T | None}.
+        relu_codes: the consumers are dense layers / max-pools (which read the unsigned post-ReLU code format,
+        written by the 2-instruction encoder); pass False when a depthwise / grouped layer consumes the codes."""
         assert x.kind == "codes"
         if linear:
             K, C = mod.weight.shape
@@ -123,7 +127,7 @@ class Plan:
         ka, kw = _k32(mod.Ka), _k32(mod.Kw)
         assert abs(ka - x.kdiv) == 0.0, "input codes were quantized with a different Ka"
         d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
-                            self.afmt)
+                            x.fmt)
         Ho = (x.h + 2 * pad[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
         Wo = (x.w + 2 * pad[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
         pitch = self.lib.slfp_conv_wpitch(ctypes.byref(d))
@@ -171,14 +175,16 @@ class Plan:
                 kds.append(kd)
         assert len(kds) <= 2
         kp = _ceil(K, 16)
+        # post-ReLU codes: dense producer (the tcgen05 kernel with the TMA-im2col gather) ending in a ReLU
+        ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and groups == 1 and x.cp % 16 == 0) else self.afmt
         for i, kd in enumerate(kds):
-            t = self._alloc(x.n, Ho, Wo, K, "codes", kd, cp=kp)
+            t = self._alloc(x.n, Ho, Wo, K, "codes", kd, cp=kp, fmt=ofmt)
             out["codes"][kd] = t
             if i == 0:
                 epi.y_codes, epi.next_k_div = t.buf.data_ptr(), kd
             else:
                 epi.y_codes2, epi.next_k_div2 = t.buf.data_ptr(), kd
-        epi.next_fmt, epi.k_phys_out = self.afmt, kp
+        epi.next_fmt, epi.k_phys_out = ofmt, kp
         if f16:
             out["f16"] = self._alloc(x.n, Ho, Wo, K, "f16")
             epi.y_f16 = out["f16"].buf.data_ptr()
@@ -197,8 +203,8 @@ class Plan:
         assert x.kind == "codes"
         Ho = (x.h + 2 * pad - k) // stride + 1
         Wo = (x.w + 2 * pad - k) // stride + 1
-        t = self._alloc(x.n, Ho, Wo, x.c, "codes", x.kdiv, cp=x.cp)
-        self.ops.append(self._call(self.lib.slfp_maxpool_codes, x.buf.data_ptr(), x.n, x.h, x.w, x.cp, k, k, stride, pad,
+        t = self._alloc(x.n, Ho, Wo, x.c, "codes", x.kdiv, cp=x.cp, fmt=x.fmt)
+        self.ops.append(self._call(self.lib.slfp_maxpool_codes, x.buf.data_ptr(), x.n, x.h, x.w, x.cp, x.fmt, k, k, stride, pad,
                                    t.buf.data_ptr()))
         return t
 
@@ -358,7 +364,8 @@ def compile_mobilenetv1(model, batch, size, device="cuda", static_weights=False)
             cur = o["f16"]
         else:
             nk = _k32(layers[j + 1][0].Ka)
-            cur = P.conv(cur, conv, bn=bn, relu=True, codes=[nk])["codes"][nk]
+            # the depthwise stencil kernel reads the signed code formats only
+            cur = P.conv(cur, conv, bn=bn, relu=True, codes=[nk], relu_codes=layers[j + 1][0].groups == 1)["codes"][nk]
     if isinstance(pool, nn.AvgPool2d):
         assert cur.h == pool.kernel_size and cur.w == pool.kernel_size, "AvgPool2d(7) expects a 7x7 map (224x224 input)"
     feat = P.avgpool(cur)

@@ -24,6 +24,15 @@
  *     SFP<3,3>  (q_bit 7): u = E*8  + m, E = 1..7, m = 0..7    ->  (1 + m/8) * 2^(E-4)
  *     escapes: u = 0 -> 0.0 ; u = 1 -> +-1e-10 ; u = 2 -> +-15.32165 (SLFP saturation literal) ;
  *              u = 3 -> NaN
+ *
+ * post-ReLU codes (SLFP_FMT_SLFP34_RELU / SLFP_FMT_SFP33_RELU), unsigned byte c, value >= 0:
+ *     c = ((float32_bits(q) + half) >> (23 - mbits)) - base, saturated to [0, 255]  (mbits 4 / 3)
+ *     c = 0 -> 0.0 (|q| < 0.0625) ; c = 1..2^mbits -> 0.125 ; above the top code -> the top value ;
+ *     otherwise u = c - 1 = E*2^mbits + i with i the LINEAR mantissa index round(2^mbits * m): the
+ *     SLFP log converter i -> M = [0,1,3,4,...,15,15] (utils/sfp_quant.py:88-89) is applied by the
+ *     consumer's decode table.  Values decode onto the same grid as the signed codes; +-1e-10 and the
+ *     15.32165 literal are represented by 0 and the top grid value (equal after float16 rounding of
+ *     the tensor-core operand).
  */
 #ifndef SLFP_B200_H_
 #define SLFP_B200_H_
@@ -43,7 +52,11 @@ enum {
     SLFP_FMT_SFP33 = 0,      /* utils/sfp_quant.py:14-30, 63-78   q_bit 7, weights and activations */
     SLFP_FMT_SLFP34_ACT = 1, /* utils/sfp_quant.py:80-96          q_bit 8 activations              */
     SLFP_FMT_SLFP34_WGT = 2, /* utils/sfp_quant.py:32-47          q_bit 8 weights                  */
-    SLFP_FMT_SFP44_OUT = 3   /* utils/sfp_quant.py:105-127        layer-out quantizer (fp32 only)  */
+    SLFP_FMT_SFP44_OUT = 3,  /* utils/sfp_quant.py:105-127        layer-out quantizer (fp32 only)  */
+    /* Unsigned post-ReLU activation codes exchanged by FUSED layers (quantize-on-store of a conv
+     * whose epilogue ends in a ReLU; see "post-ReLU codes" below).  Same grids as SLFP34_ACT / SFP33. */
+    SLFP_FMT_SLFP34_RELU = 4,
+    SLFP_FMT_SFP33_RELU = 5
 };
 
 enum { SLFP_ACT_STL = 0, SLFP_ACT_SWISH = 1, SLFP_ACT_SIGMOID = 2 };
@@ -105,8 +118,8 @@ typedef struct {
     int r, s;             /* filter height / width                                             */
     int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
     int groups;           /* 1 = dense implicit GEMM (tcgen05); c == k == groups = depthwise     */
-    int fmt;              /* SLFP_FMT_SLFP34_ACT (q_bit 8) or SLFP_FMT_SFP33 (q_bit 7): code layout
-                             of the activation codes                                            */
+    int fmt;              /* code layout of the activation codes: SLFP_FMT_SLFP34_ACT (q_bit 8) or
+                             SLFP_FMT_SFP33 (q_bit 7); dense convs also take the post-ReLU formats  */
 } SlfpConvDesc;
 
 typedef struct {
@@ -189,7 +202,7 @@ int slfp_sgd_step(int n_tensors, float *const *host_params, float *const *host_g
  * ------------------------------------------------------------------------------------------- */
 /* 2-D max pooling directly on activation codes (the quantizer is monotone, so
  * quantize(maxpool(x)) == maxpool(quantize(x)) bit for bit).  pad positions never win. */
-int slfp_maxpool_codes(const uint8_t *x, int n, int h, int w, int c_phys, int kh, int kw_,
+int slfp_maxpool_codes(const uint8_t *x, int n, int h, int w, int c_phys, int fmt, int kh, int kw_,
                        int stride, int pad, uint8_t *y, slfp_stream_t stream);
 /* global average pool NHWC float16/float32 -> [n, c] float32 */
 int slfp_avgpool_nhwc(const void *x, int is_f16, int n, int hw, int c, float *y, slfp_stream_t stream);

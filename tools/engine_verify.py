@@ -13,8 +13,9 @@ m, comp, batch, size = prepare(name)
 x = nc.synth_images(batch, size).cuda()
 recs = []
 orig_conv = engine.Plan.conv
-def conv_spy(self, xt, mod, bn=None, relu=False, residual=None, codes=(), f16=False, f32=False, linear=False):
-    out = orig_conv(self, xt, mod, bn=bn, relu=relu, residual=residual, codes=codes, f16=f16, f32=f32, linear=linear)
+def conv_spy(self, xt, mod, bn=None, relu=False, residual=None, codes=(), f16=False, f32=False, linear=False, relu_codes=True):
+    out = orig_conv(self, xt, mod, bn=bn, relu=relu, residual=residual, codes=codes, f16=f16, f32=f32, linear=linear,
+                    relu_codes=relu_codes)
     recs.append((xt, mod, bn, relu, residual, out, linear))
     return out
 engine.Plan.conv = conv_spy
@@ -30,7 +31,7 @@ def deq(t, fmt):
 
 from oracle import slfp_oracle as orc
 for i, (xt, mod, bn, relu, residual, out, linear) in enumerate(recs):
-    xq = deq(xt, plan.afmt).double().permute(0, 3, 1, 2)
+    xq = deq(xt, xt.fmt).double().permute(0, 3, 1, 2)
     ka, kw = engine._k32(mod.Ka), engine._k32(mod.Kw)
     w = mod.weight.detach().float().cpu().numpy()
     _, wq = orc.quantize(w, 2 if plan.q_bit == 8 else 0, kdiv=kw, want_codes=False)
@@ -59,10 +60,10 @@ for i, (xt, mod, bn, relu, residual, out, linear) in enumerate(recs):
             d = (out[kind].buf.double() - y).abs().max().item()
             msgs.append(f"{kind} max|d|/max|y| {d / scale:.2e}")
     for kd, t in out["codes"].items():
-        got = deq(t, plan.afmt)
+        got = deq(t, t.fmt)
         _, want = orc.quantize(y.float().cpu().numpy(), 1 if plan.q_bit == 8 else 0, kdiv=kd, want_codes=False)
         want = torch.from_numpy(want).cuda()
-        mism = (got != want).float().mean().item()
+        mism = (got.half() != want.half()).float().mean().item()      # compared as tensor-core operands (float16)
         big = ((got - want).abs() > 0.1 * want.abs() + 1e-6).float().mean().item()
         msgs.append(f"codes(k={kd:.4f}) mismatch {mism:.4f} gross {big:.5f}")
     print(f"op {i:2d} {'lin' if linear else 'conv'} in{tuple(xt.buf.shape)} K={mod.weight.shape[0]} g={getattr(mod,'groups',1)} res={residual is not None}: " + "; ".join(msgs))

@@ -93,9 +93,22 @@ def bench_conv(batch=256, mode="f32", only=None, iters=10):
             y = torch.empty((batch, Ho, Ho, K), dtype=torch.float32, device="cuda")
             epi.y_f32 = y.data_ptr()
             out_b = 4
+        elif mode == "res":                 # bottleneck tail: + float16 residual, ReLU, float16 out, post-ReLU codes
+            y = torch.empty((batch, Ho, Ho, K), dtype=torch.uint8, device="cuda")
+            y16 = torch.empty((batch, Ho, Ho, K), dtype=torch.float16, device="cuda")
+            res = torch.randn((batch, Ho, Ho, K), dtype=torch.float16, device="cuda")
+            mul = torch.full((K,), 0.006, device="cuda"); add = torch.zeros(K, device="cuda")
+            epi.ch_mul, epi.ch_add = mul.data_ptr(), add.data_ptr()
+            epi.residual, epi.residual_f16, epi.y_f16 = res.data_ptr(), 1, y16.data_ptr()
+            epi.y_codes, epi.next_k_div, epi.next_fmt, epi.k_phys_out, epi.relu = y.data_ptr(), 0.2, 4, K, 1
+            out_b = 5
         else:
             y = torch.empty((batch, Ho, Ho, K), dtype=torch.uint8, device="cuda")
-            epi.y_codes, epi.next_k_div, epi.next_fmt, epi.k_phys_out, epi.relu = y.data_ptr(), 0.2, nv.FMT_SLFP34_ACT, K, 1
+            nfmt = 4 if (mode == "rcodes" and Cp >= 16) else nv.FMT_SLFP34_ACT
+            epi.y_codes, epi.next_k_div, epi.next_fmt, epi.k_phys_out, epi.relu = y.data_ptr(), 0.2, nfmt, K, 1
+            if mode == "rcodes":            # the fused pipeline's form: folded per-channel affine, post-ReLU codes
+                mul = torch.full((K,), 0.006, device="cuda"); add = torch.zeros(K, device="cuda")
+                epi.ch_mul, epi.ch_add = mul.data_ptr(), add.data_ptr()
             out_b = 1
         fn = lambda: nv.check(lib.slfp_conv2d_fwd(ctypes.byref(d), xc.data_ptr(), wh.data_ptr(), ctypes.byref(epi), nv.stream()))
         med, best = timeit(fn, iters=iters, flush=flush)
