@@ -21,7 +21,7 @@ c_vp, c_sz, c_f, c_i, c_ll, c_d = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_fl
 
 class SlfpConvDesc(ctypes.Structure):
     _fields_ = [(n, c_i) for n in ("n", "h", "w", "c", "c_phys", "k", "r", "s", "stride_h", "stride_w", "pad_h",
-                                   "pad_w", "dil_h", "dil_w", "groups", "fmt")]
+                                   "pad_w", "dil_h", "dil_w", "groups", "fmt", "pad_h_extra", "pad_w_extra")]
 
 
 class SlfpEpilogue(ctypes.Structure):
@@ -37,11 +37,13 @@ _SIGS = {
     "slfp_quantize_f32": (c_i, [c_vp, c_sz, c_f, c_i, ctypes.c_uint, c_vp, c_vp, c_vp, c_vp]),
     "slfp_quantize_nhwc_f32": (c_i, [c_vp, c_sz, c_i, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_quantize_nchw_f32": (c_i, [c_vp, c_i, c_i, c_sz, c_i, c_f, c_i, c_vp, c_vp]),
+    "slfp_quantize_nchw_s2d_f32": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_dequantize": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
     "slfp_absmax_f32": (c_i, [c_vp, c_sz, c_vp, c_i, c_vp]),
     "slfp_conv_wpitch": (c_sz, [ctypes.POINTER(SlfpConvDesc)]),
     "slfp_prepare_weights": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_ll, c_ll, c_ll, c_ll, c_f, c_i, c_vp, c_vp,
                                    c_vp, c_vp]),
+    "slfp_prepare_weights_batch": (c_i, [c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
     "slfp_conv2d_fwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, ctypes.POINTER(SlfpEpilogue), c_vp]),
     "slfp_conv2d_bwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, c_vp, c_i, c_f, c_f, c_vp, c_vp, c_ll, c_ll,
                               c_ll, c_ll, c_vp, c_vp]),
@@ -59,9 +61,9 @@ _lib = None
 # Every entry point that launches kernels on the caller's stream.  The proxy below counts those calls
 # (bench.py reports them as `gpu_launches`) and, when a profile dict is installed, brackets each call
 # with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
-_LAUNCHING = {"slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
+_LAUNCHING = {"slfp_prepare_weights_batch", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
               "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
-              "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32"}
+              "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32"}
 launch_count = 0
 profile = None          # None, or {name: [(start_event, end_event, tag), ...]}
 profile_tag = None

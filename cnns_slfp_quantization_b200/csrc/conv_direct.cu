@@ -128,6 +128,8 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
     if (p.Ho <= 0 || p.Wo <= 0 || d->n <= 0) return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd(grouped): empty output");
     if (d->groups <= 0 || d->c % d->groups || d->k % d->groups)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd(grouped): channels not divisible by groups");
+    if (d->pad_h_extra || d->pad_w_extra)
+        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): asymmetric padding is a dense-path feature");
     if ((d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_ACT) ||
         (epi->y_codes && epi->next_fmt != SLFP_FMT_SFP33 && epi->next_fmt != SLFP_FMT_SLFP34_ACT))
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): the stencil kernels read and write the signed code formats only");
@@ -259,6 +261,7 @@ int conv2d_bwd_direct(const SlfpConvDesc* d, const float* gy, const uint8_t* x_c
     const size_t npix = (size_t)d->n * p.Ho * p.Wo;
     if (d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_ACT)
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_bwd: activation codes must be in a signed quantizer format");
+    if (d->pad_h_extra || d->pad_w_extra) return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_bwd: asymmetric padding");
     const bool sfp_w = wfmt == SLFP_FMT_SFP33, sfp_a = d->fmt == SLFP_FMT_SFP33;
     int rc = 0;
     if (dx) {

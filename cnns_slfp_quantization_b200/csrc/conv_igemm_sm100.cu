@@ -560,6 +560,8 @@ int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* 
     // c_phys % 16 == 0: the warp-specialised TMA-im2col kernel (conv_igemm_v2.cu); this file keeps the
     // 4-channel network-input layout (the 7x7 / 3x3 stems), whose taps are narrower than a TMA box row.
     if (conv2d_fwd_dense_v2_supported(d)) return conv2d_fwd_dense_v2(d, x_codes, w_f16, epi, st);
+    if (d->pad_h_extra || d->pad_w_extra)
+        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: asymmetric padding needs c_phys %% 16 == 0");
     if (epi->y_codes && epi->next_fmt != SLFP_FMT_SLFP34_ACT && epi->next_fmt != SLFP_FMT_SFP33)
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: the 4-channel-input kernel writes signed code formats only");
     if (d->c_phys != 4 && (d->c_phys % 16) != 0)

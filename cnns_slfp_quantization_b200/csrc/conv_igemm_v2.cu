@@ -65,7 +65,7 @@ struct Cfg {
     static constexpr int kStages = (BLOCK_N >= 256) ? 3 : 4;
     static constexpr int kTmemCols = 2 * BLOCK_N;
     static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
-    static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 512 + 1024;
+    static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 512;
 };
 
 // ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
@@ -400,9 +400,10 @@ template <int BLOCK_N, int GRAN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     using C = Cfg<BLOCK_N>;
-    extern __shared__ uint8_t smem_raw[];
-    // SW128 operand tiles need 1024-byte alignment
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // SW128 operand tiles need 1024-byte alignment.  The kernel has no static shared memory, so the dynamic
+    // window starts at a link-time constant that honours __align__ (checked below): every shared address in
+    // this kernel is then a compile-time offset and the table look-up needs no base-address add.
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_a = smem;                                   // [stages][128 rows][128 B]
     uint8_t* s_b = s_a + C::kStages * kABytes;             // [stages][BLOCK_N rows][128 B]
     uint8_t* s_code = s_b + C::kStages * C::kBBytes;       // [kCodeStages][128 pixels][64 B]
@@ -418,6 +419,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();     // would break the swizzle: fail loudly, never silently
 
     // ---- one-time setup ---------------------------------------------------------------------------
     for (int i = tid; i < 256 * 32; i += kThreads) {
@@ -570,10 +572,11 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t c = w[i];
-                        const uint32_t e0 = ptx::lds32_off(((c << 7) & 0x7f80u) | lane4, lut_base);
-                        const uint32_t e1 = ptx::lds32_off(((c >> 1) & 0x7f80u) | lane4, lut_base);
-                        const uint32_t e2 = ptx::lds32_off(((c >> 9) & 0x7f80u) | lane4, lut_base);
-                        const uint32_t e3 = ptx::lds32_off(((c >> 17) & 0x7f80u) | lane4, lut_base);
+                        // per code: shift, one LOP3 ((x & 0x7f80) | lane*4), one LDS [reg + constant table base]
+                        const uint32_t e0 = ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base);
+                        const uint32_t e1 = ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base);
+                        const uint32_t e2 = ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base);
+                        const uint32_t e3 = ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base);
                         h[j][2 * i] = __byte_perm(e0, e1, 0x5410);
                         h[j][2 * i + 1] = __byte_perm(e2, e3, 0x5410);
                     }
@@ -709,9 +712,11 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
           (uintptr_t)epi->y_codes | (uintptr_t)epi->y_codes2) & 15u) != 0)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: tensors must be 16-byte aligned");
     Params p;
-    const int Ho = (d->h + 2 * d->pad_h - d->dil_h * (d->r - 1) - 1) / d->stride_h + 1;
-    const int Wo = (d->w + 2 * d->pad_w - d->dil_w * (d->s - 1) - 1) / d->stride_w + 1;
+    const int Ho = (d->h + 2 * d->pad_h + d->pad_h_extra - d->dil_h * (d->r - 1) - 1) / d->stride_h + 1;
+    const int Wo = (d->w + 2 * d->pad_w + d->pad_w_extra - d->dil_w * (d->s - 1) - 1) / d->stride_w + 1;
     if (Ho <= 0 || Wo <= 0 || d->n <= 0) return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: empty output");
+    if (d->pad_h + d->pad_h_extra < 0 || d->pad_w + d->pad_w_extra < 0)
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: negative end padding");
     const unsigned long long M64 = (unsigned long long)d->n * Ho * Wo;
     if (M64 >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: more than 2^31 output pixels");
     p.M = (uint32_t)M64;
@@ -767,7 +772,7 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
         const cuuint64_t gdim[4] = {(cuuint64_t)d->c_phys, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
         const cuuint64_t gstr[3] = {(cuuint64_t)d->c_phys, (cuuint64_t)d->c_phys * d->w, (cuuint64_t)d->c_phys * d->w * d->h};
         const int lower[2] = {-d->pad_w, -d->pad_h};
-        const int upper[2] = {d->pad_w - (d->s - 1) * d->dil_w, d->pad_h - (d->r - 1) * d->dil_h};
+        const int upper[2] = {d->pad_w + d->pad_w_extra - (d->s - 1) * d->dil_w, d->pad_h + d->pad_h_extra - (d->r - 1) * d->dil_h};
         const cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
         CUresult cr = enc_im2col(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x_codes), gdim, gstr, lower, upper,
                                  (cuuint32_t)(p.cblocks ? 64 : 16), (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

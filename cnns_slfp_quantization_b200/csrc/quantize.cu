@@ -228,6 +228,33 @@ __global__ void __launch_bounds__(256) quantize_nchw_kernel(const float* __restr
     }
 }
 
+// NCHW float32 image -> space-to-depth NHWC codes [N, H/2, W/2, Cp], channel (dy*2+dx)*C + c.  Thread = one
+// folded pixel: 2 x float2 reads per plane (coalesced across the warp), one 16-byte store per 16 channels.
+template <int FMT>
+__global__ void __launch_bounds__(256) quantize_nchw_s2d_kernel(const float* __restrict__ x, int N, int C, int H, int W, int Cp,
+                                                                DivK k_div, uint8_t* __restrict__ codes) {
+    const int H2 = H >> 1, W2 = W >> 1;
+    const size_t total = (size_t)N * H2 * W2;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int x2 = (int)(i % W2), y2 = (int)((i / W2) % H2);
+        const size_t n = i / ((size_t)W2 * H2);
+        uint8_t* dst = codes + i * (size_t)Cp;
+        for (int c0 = 0; c0 < Cp; c0 += 16) {
+            uint32_t wds[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int ch = c0 + j;                       // folded channel = q*C + c, q = dy*2 + dx
+                if (ch < 4 * C) {
+                    const int q = ch / C, c = ch - q * C;
+                    const float v = __ldg(x + ((n * C + c) * H + (2 * y2 + (q >> 1))) * (size_t)W + 2 * x2 + (q & 1));
+                    wds[j >> 2] |= encode<FMT>(div_k(v, k_div)) << (8 * (j & 3));
+                }
+            }
+            *reinterpret_cast<uint4*>(dst + c0) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+    }
+}
+
 // ---- de-quantize ------------------------------------------------------------------------------
 template <bool SFP33>
 __global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t* __restrict__ codes, size_t n,
@@ -291,32 +318,68 @@ struct WPrepArgs {
 };
 
 template <int FMT>
+__device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, const uint32_t* s_tab) {
+    const int k = (int)(i / a.pitch);
+    const size_t j = i - (size_t)k * a.pitch;
+    const int c = (int)(j % a.Cp);
+    const int rs = (int)(j / a.Cp);
+    uint32_t code = 0;
+    float fq = 0.0f;
+    if (c < a.C && rs < a.R * a.S) {
+        const int r = rs / a.S, s = rs - r * a.S;
+        const float x = a.w[k * a.so + c * a.sc + r * a.sr + s * a.ss];
+        const float v = div_rn(x, a.kw);
+        if (FMT < 0) {
+            fq = v;
+        } else {
+            code = encode<FMT < 0 ? 0 : FMT>(v);
+            fq = decode<FMT == SLFP_FMT_SFP33>(code, s_tab);
+        }
+        if (a.w_fakeq) a.w_fakeq[(((size_t)k * a.C + c) * a.R + r) * a.S + s] = fq;
+    }
+    if (a.w_f16) a.w_f16[i] = __float2half_rn(fq);
+    if (a.w_codes) a.w_codes[i] = (uint8_t)code;
+}
+
+template <int FMT>
 __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
     __shared__ uint32_t s_tab[16];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
     __syncthreads();
     const size_t total = (size_t)a.K * a.pitch;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        const int k = (int)(i / a.pitch);
-        const size_t j = i - (size_t)k * a.pitch;
-        const int c = (int)(j % a.Cp);
-        const int rs = (int)(j / a.Cp);
-        uint32_t code = 0;
-        float fq = 0.0f;
-        if (c < a.C && rs < a.R * a.S) {
-            const int r = rs / a.S, s = rs - r * a.S;
-            const float x = a.w[k * a.so + c * a.sc + r * a.sr + s * a.ss];
-            const float v = div_rn(x, a.kw);
-            if (FMT < 0) {
-                fq = v;
-            } else {
-                code = encode<FMT < 0 ? 0 : FMT>(v);
-                fq = decode<FMT == SLFP_FMT_SFP33>(code, s_tab);
-            }
-            if (a.w_fakeq) a.w_fakeq[(((size_t)k * a.C + c) * a.R + r) * a.S + s] = fq;
-        }
-        if (a.w_f16) a.w_f16[i] = __float2half_rn(fq);
-        if (a.w_codes) a.w_codes[i] = (uint8_t)code;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256)
+        wprep_element<FMT>(a, i, s_tab);
+}
+
+// Every layer of a network in ONE launch (the reference re-quantizes all weights on every forward,
+// conv2d_func.py:22; 54 separate launches cost more than the 25 M weights themselves).  The table travels as
+// a kernel parameter; block b works on kWBatchChunk consecutive elements of the tensor whose block range holds b.
+constexpr int kWBatchMax = 160;
+constexpr int kWBatchChunk = 2048;
+struct WPrepBatch {
+    int n;
+    unsigned blk_end[kWBatchMax];      // exclusive prefix sums of blocks per tensor
+    WPrepArgs a[kWBatchMax];
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256) wprep_batch_kernel(const __grid_constant__ WPrepBatch b) {
+    __shared__ uint32_t s_tab[16];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    int lo = 0, hi = b.n - 1;                                 // first tensor with blk_end > blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (b.blk_end[mid] > blockIdx.x) hi = mid; else lo = mid + 1;
+    }
+    const WPrepArgs& a = b.a[lo];
+    const unsigned first = lo ? b.blk_end[lo - 1] : 0u;
+    const size_t total = (size_t)a.K * a.pitch;
+    const size_t base = (size_t)(blockIdx.x - first) * kWBatchChunk;
+#pragma unroll 2
+    for (int j = 0; j < kWBatchChunk / 256; ++j) {
+        const size_t i = base + (size_t)j * 256 + threadIdx.x;
+        if (i < total) wprep_element<FMT>(a, i, s_tab);
     }
 }
 
@@ -402,6 +465,23 @@ extern "C" int slfp_quantize_nchw_f32(const float* x, int n, int c, size_t hw, i
     return check_launch("quantize_nchw_kernel");
 }
 
+extern "C" int slfp_quantize_nchw_s2d_f32(const float* x, int n, int c, int h, int w, int c_phys, float k_div, int fmt,
+                                          uint8_t* codes, slfp_stream_t stream) {
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    if (!x || !codes || c <= 0 || (h & 1) || (w & 1) || c_phys < 4 * c || (c_phys & 15) || ((uintptr_t)codes & 15u))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_s2d_f32: bad arguments (h, w even; c_phys >= 4c, multiple of 16)");
+    const size_t total = (size_t)n * (h / 2) * (w / 2);
+    const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(total, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DivK dk = make_divk(k_div);
+    switch (fmt) {
+        case SLFP_FMT_SFP33: quantize_nchw_s2d_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, n, c, h, w, c_phys, dk, codes); break;
+        case SLFP_FMT_SLFP34_ACT: quantize_nchw_s2d_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, n, c, h, w, c_phys, dk, codes); break;
+        default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_s2d_f32: format %d", fmt);
+    }
+    return check_launch("quantize_nchw_s2d_kernel");
+}
+
 extern "C" int slfp_dequantize(const uint8_t* codes, size_t n, int fmt, float* out, slfp_stream_t stream) {
     if (n == 0) return 0;
     if (!codes || !out) return set_error(SLFP_ERR_BAD_ARG, "slfp_dequantize: null pointer");
@@ -463,6 +543,54 @@ extern "C" int slfp_prepare_weights(const SlfpConvDesc* d, const float* w, long 
         default: return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights: bad weight format %d", wfmt);
     }
     return check_launch("wprep_kernel");
+}
+
+static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long long sc, long long sr, long long ss, float kw,
+                      void* w_f16, uint8_t* w_codes, float* w_fakeq, WPrepArgs& a) {
+    if (!d || !w) return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights: null pointer");
+    a.w = w; a.so = so; a.sc = sc; a.sr = sr; a.ss = ss;
+    a.K = d->k; a.R = d->r; a.S = d->s;
+    if (d->groups > 1) { a.C = d->c / d->groups; a.Cp = a.C; }
+    else { a.C = d->c; a.Cp = d->c_phys; }
+    a.pitch = slfp_conv_wpitch(d);
+    a.kw = kw; a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
+    return 0;
+}
+
+extern "C" int slfp_prepare_weights_batch(int n, const SlfpConvDesc* const* host_descs, const float* const* host_w,
+                                          const long long* host_strides, const float* host_kw, int wfmt,
+                                          void* const* host_w_f16, uint8_t* const* host_w_codes, slfp_stream_t stream) {
+    if (n <= 0) return 0;
+    if (!host_descs || !host_w || !host_strides || !host_kw)
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_batch: null table");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t0 = 0; t0 < n; t0 += kWBatchMax) {
+        static thread_local WPrepBatch b;
+        b.n = 0;
+        unsigned blocks = 0;
+        for (int t = t0; t < n && t < t0 + kWBatchMax; ++t) {
+            WPrepArgs& a = b.a[b.n];
+            int rc = fill_wprep(host_descs[t], host_w[t], host_strides[4 * t], host_strides[4 * t + 1], host_strides[4 * t + 2],
+                                host_strides[4 * t + 3], host_kw[t], host_w_f16 ? host_w_f16[t] : nullptr,
+                                host_w_codes ? host_w_codes[t] : nullptr, nullptr, a);
+            if (rc) return rc;
+            const size_t total = (size_t)a.K * a.pitch;
+            if (total == 0) continue;
+            blocks += (unsigned)ceil_div_sz(total, kWBatchChunk);
+            b.blk_end[b.n++] = blocks;
+        }
+        if (b.n == 0) continue;
+        switch (wfmt) {
+            case SLFP_FMT_SFP33: wprep_batch_kernel<SLFP_FMT_SFP33><<<blocks, 256, 0, st>>>(b); break;
+            case SLFP_FMT_SLFP34_WGT: wprep_batch_kernel<SLFP_FMT_SLFP34_WGT><<<blocks, 256, 0, st>>>(b); break;
+            case SLFP_FMT_SLFP34_ACT: wprep_batch_kernel<SLFP_FMT_SLFP34_ACT><<<blocks, 256, 0, st>>>(b); break;
+            case -1: wprep_batch_kernel<-1><<<blocks, 256, 0, st>>>(b); break;
+            default: return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_batch: bad weight format %d", wfmt);
+        }
+        int rc = check_launch("wprep_batch_kernel");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int slfp_quantize_host_f32(const float* host_x, size_t n, float k_div, int fmt, uint8_t* host_codes,

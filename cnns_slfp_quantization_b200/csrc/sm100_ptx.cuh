@@ -74,6 +74,12 @@ __device__ __forceinline__ uint32_t lds32_off(uint32_t off, uint32_t base) {
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(off + base));
     return v;
 }
+// (a & b) | c in ONE LOP3 (nvvm canonicalises the disjoint `|` into an add, which costs an extra instruction)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

@@ -60,7 +60,9 @@ class Plan:
         self.batch, self.dev, self.q_bit = batch, device, q_bit
         self.afmt, self.wfmt = nv.fmt_for(q_bit, "act"), nv.fmt_for(q_bit, "weight")
         self.static_weights = static_weights
-        self.weight_ops, self.ops, self.keep = [], [], []
+        self.weight_table, self.ops, self.keep = [], [], []
+        self.pre_weight_ops = []          # torch-side weight re-layouts run before the batched re-quantization
+        self._wbatch = None
         self.input = None
         self.output = None
         self.graph = None
@@ -98,6 +100,41 @@ class Plan:
                                    t.buf.data_ptr()))
         return t
 
+    def quantize_input_s2d(self, x_nchw, kdiv):
+        """Network input -> codes of the 2x2 space-to-depth image [n, h/2, w/2, round_up(4c, 16)]."""
+        n, c, h, w = x_nchw.shape
+        cp = _ceil(4 * c, 16)
+        t = self._alloc(n, h // 2, w // 2, 4 * c, "codes", kdiv, cp=cp)
+        self.ops.append(self._call(self.lib.slfp_quantize_nchw_s2d_f32, x_nchw.data_ptr(), n, c, h, w, cp, kdiv, self.afmt,
+                                   t.buf.data_ptr()))
+        return t
+
+    def s2d_stem(self, conv):
+        """A stride-2 RxR convolution (padding P) on c channels == a stride-1 convolution on the 2x2-folded image
+        with 4c channels: row 2*ho - P + r = 2*(ho - ceil(P/2)) + (r + off), off = 2*ceil(P/2) - P, so the folded
+        filter tap is a = (r + off) // 2 with parity dy = (r + off) % 2; taps outside the original filter are 0.
+        Returns a module-like object whose .weight is refreshed from conv.weight before every re-quantization."""
+        K, C, R, S = conv.weight.shape
+        assert conv.stride == (2, 2) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
+        P = conv.padding
+        lo = [(p + 1) // 2 for p in P]
+        off = [2 * l - p for l, p in zip(lo, P)]
+        R2, S2 = (R - 1 + off[0]) // 2 + 1, (S - 1 + off[1]) // 2 + 1
+        w2 = torch.zeros((K, 4 * C, R2, S2), dtype=torch.float32, device=self.dev)
+
+        def refresh():
+            wp = torch.zeros((K, C, 2 * R2, 2 * S2), dtype=torch.float32, device=self.dev)
+            wp[:, :, off[0]:off[0] + R, off[1]:off[1] + S] = conv.weight.detach()
+            # [k, c, a, dy, b, dx] -> [k, (dy, dx, c), a, b]
+            w2.copy_(wp.view(K, C, R2, 2, S2, 2).permute(0, 3, 5, 1, 2, 4).reshape(K, 4 * C, R2, S2))
+        self.pre_weight_ops.append(refresh)
+
+        shim = type("S2DStem", (), {})()
+        shim.weight, shim.bias, shim.Ka, shim.Kw = w2, None, conv.Ka, conv.Kw
+        shim.stride, shim.padding, shim.dilation, shim.groups = (1, 1), tuple(lo), (1, 1), 1
+        shim.fold = (lo, off, R2, S2)
+        return shim
+
     def quantize_flat(self, x_f32, c, kdiv):
         """[n, c] float32 features -> codes [n,1,1,cp] (classifier input)."""
         n = x_f32.shape[0]
@@ -126,17 +163,18 @@ class Plan:
         assert C == x.c, (C, x.c)
         ka, kw = _k32(mod.Ka), _k32(mod.Kw)
         assert abs(ka - x.kdiv) == 0.0, "input codes were quantized with a different Ka"
+        pex = getattr(mod, "pad_extra", (0, 0))          # bottom/right minus top/left padding (space-to-depth stem)
         d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
-                            x.fmt)
-        Ho = (x.h + 2 * pad[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
-        Wo = (x.w + 2 * pad[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
+                            x.fmt, pex[0], pex[1])
+        Ho = (x.h + 2 * pad[0] + pex[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
+        Wo = (x.w + 2 * pad[1] + pex[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
         pitch = self.lib.slfp_conv_wpitch(ctypes.byref(d))
         dense = groups == 1
         wbuf = torch.empty((K * pitch,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
-        so, sc, sr, ss = wview.stride()
-        self.weight_ops.append(self._call(self.lib.slfp_prepare_weights, ctypes.byref(d), wview.data_ptr(), so, sc, sr, ss,
-                                          kw, self.wfmt, wbuf.data_ptr() if dense else None,
-                                          None if dense else wbuf.data_ptr(), None))
+        # weight re-quantization: one table entry; Plan.prepare_weights() runs the whole table in ONE launch
+        self.weight_table.append((d, wview.data_ptr(), tuple(wview.stride()), kw, wbuf.data_ptr() if dense else None,
+                                  None if dense else wbuf.data_ptr()))
+        self._wbatch = None
         epi = nv.SlfpEpilogue()
         # Fold bias, post-scale and eval BatchNorm into one per-channel affine y = acc * mul + add
         # (float64, rounded once): mul = Ka*Kw*bn_scale, add = bias_q*Ka*Kw*bn_scale + bn_shift.
@@ -222,23 +260,35 @@ class Plan:
 
     # ---- execution ----------------------------------------------------------------------------------------
     def prepare_weights(self):
-        st = nv.stream()
-        for op in self.weight_ops:
-            op(st)
+        """Re-quantize every layer's weights (utils/conv2d_func.py:22 does it on every forward): one launch."""
+        n = len(self.weight_table)
+        if n == 0:
+            return
+        for op in self.pre_weight_ops:
+            op()
+        if self._wbatch is None:
+            descs = (ctypes.POINTER(nv.SlfpConvDesc) * n)(*[ctypes.pointer(t[0]) for t in self.weight_table])
+            ws = (ctypes.c_void_p * n)(*[t[1] for t in self.weight_table])
+            strides = (ctypes.c_longlong * (4 * n))(*[v for t in self.weight_table for v in t[2]])
+            kws = (ctypes.c_float * n)(*[t[3] for t in self.weight_table])
+            f16 = (ctypes.c_void_p * n)(*[t[4] for t in self.weight_table])
+            codes = (ctypes.c_void_p * n)(*[t[5] for t in self.weight_table])
+            self._wbatch = (descs, ws, strides, kws, f16, codes)
+        descs, ws, strides, kws, f16, codes = self._wbatch
+        nv.check(self.lib.slfp_prepare_weights_batch(n, descs, ws, strides, kws, self.wfmt, f16, codes, nv.stream()))
 
     @torch.no_grad()
     def run(self):
         st = nv.stream()
         if not self.static_weights:
-            for op in self.weight_ops:
-                op(st)
+            self.prepare_weights()
         for op in self.ops:
             op(st)
         return self.output
 
     @property
     def launches_per_step(self):
-        return len(self.ops) + (0 if self.static_weights else len(self.weight_ops))
+        return len(self.ops) + (0 if self.static_weights or not self.weight_table else 1)
 
     def capture(self):
         """Record the plan into a CUDA graph (after one eager warm-up so kernel attributes are set)."""
@@ -276,8 +326,19 @@ def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", stat
             ks.append(_k32(block.downsample[0].Ka))
         return ks
 
-    xc = P.quantize_input(x, _k32(model.conv1.Ka))
-    stem = P.conv(xc, model.conv1, bn=model.bn1, relu=True, codes=consumers(blocks[0]))
+    c1 = model.conv1
+    if c1.stride == (2, 2) and size % 2 == 0 and c1.groups == 1 and c1.bias is None and c1.dilation == (1, 1):
+        # 7x7/2 stem on 3 channels -> 4x4/1 on the space-to-depth image (16-byte channel vectors: TMA im2col path)
+        shim = P.s2d_stem(c1)
+        lo, off, R2, S2 = shim.fold
+        ho = (size + 2 * c1.padding[0] - (c1.kernel_size[0] - 1) - 1) // 2 + 1
+        wo = (size + 2 * c1.padding[1] - (c1.kernel_size[1] - 1) - 1) // 2 + 1
+        shim.pad_extra = (ho - size // 2 + (R2 - 1) - 2 * lo[0], wo - size // 2 + (S2 - 1) - 2 * lo[1])
+        xc = P.quantize_input_s2d(x, _k32(c1.Ka))
+        stem = P.conv(xc, shim, bn=model.bn1, relu=True, codes=consumers(blocks[0]))
+    else:
+        xc = P.quantize_input(x, _k32(c1.Ka))
+        stem = P.conv(xc, c1, bn=model.bn1, relu=True, codes=consumers(blocks[0]))
     mp = model.maxpool
     k_, s_, p_ = (mp.kernel_size, mp.stride, mp.padding)
     cur_codes = {kd: P.maxpool(t, k_, s_, p_) for kd, t in stem["codes"].items()}

@@ -97,6 +97,14 @@ int slfp_quantize_nhwc_f32(const float *x, size_t npix, int c, int c_phys, float
 int slfp_quantize_nchw_f32(const float *x, int n, int c, size_t hw, int c_phys, float k_div, int fmt,
                            uint8_t *codes, slfp_stream_t stream);
 
+/* Space-to-depth variant for a stride-2 stem (ResNet's 7x7/2 on 3 channels): writes NHWC codes of the
+ * 2x2-folded image, [n, h/2, w/2, c_phys] with channel (dy*2 + dx)*c + ch for pixel (2y+dy, 2x+dx) and
+ * c_phys = round_up(4c, 16).  The stride-2 RxR convolution on c channels is then a stride-1
+ * ceil((R+1)/2)^2 convolution on 4c channels whose 16-byte channel vectors the TMA im2col path can fetch
+ * (see DESIGN.md "stem").  h and w must be even. */
+int slfp_quantize_nchw_s2d_f32(const float *x, int n, int c, int h, int w, int c_phys, float k_div, int fmt,
+                               uint8_t *codes, slfp_stream_t stream);
+
 /* codes -> float32 (exactly the value the reference's fake-quant tensor would hold) */
 int slfp_dequantize(const uint8_t *codes, size_t n, int fmt, float *out, slfp_stream_t stream);
 
@@ -120,6 +128,9 @@ typedef struct {
     int groups;           /* 1 = dense implicit GEMM (tcgen05); c == k == groups = depthwise     */
     int fmt;              /* code layout of the activation codes: SLFP_FMT_SLFP34_ACT (q_bit 8) or
                              SLFP_FMT_SFP33 (q_bit 7); dense convs also take the post-ReLU formats  */
+    int pad_h_extra;      /* bottom / right padding minus top / left padding (0 = symmetric, as in      */
+    int pad_w_extra;      /* PyTorch).  Non-zero only for the space-to-depth form of a strided stem:     */
+                          /* dense, c_phys % 16 == 0.                                                   */
 } SlfpConvDesc;
 
 typedef struct {
@@ -160,6 +171,13 @@ int slfp_prepare_weights(const SlfpConvDesc *desc, const float *w, long long w_s
                          long long w_stride_c, long long w_stride_r, long long w_stride_s,
                          float kw, int wfmt, void *w_f16, uint8_t *w_codes, float *w_fakeq,
                          slfp_stream_t stream);
+
+/* The same for n layers in ONE launch (the reference re-quantizes every layer's weights on every forward,
+ * conv2d_func.py:22).  host_* arrays have n entries and are read before the call returns; host_strides holds
+ * 4 element strides (o, c, r, s) per layer; host_w_f16 / host_w_codes may be NULL or hold NULL entries. */
+int slfp_prepare_weights_batch(int n, const SlfpConvDesc *const *host_descs, const float *const *host_w,
+                               const long long *host_strides, const float *host_kw, int wfmt,
+                               void *const *host_w_f16, uint8_t *const *host_w_codes, slfp_stream_t stream);
 
 /* Forward on codes.  x_codes NHWC [n,h,w,c_phys]; w_f16 from slfp_prepare_weights (dense) or
  * w_f32 KRSC float32 for the depthwise / grouped stencil path. */
