@@ -266,28 +266,31 @@ __device__ __forceinline__ uint16_t decode_f16_bits(uint32_t code, const uint32_
 
 // ---- post-ReLU activation codes of the fused pipeline (SLFP_FMT_SLFP34_RELU / SLFP_FMT_SFP33_RELU) ----
 // Between two fused layers the producer's epilogue has already applied the ReLU, so the value is >= +0 and
-// the code needs no sign.  The unsigned code is the rounded float32 bit pattern itself, re-based:
-//     SLFP<3,4>:  c = ((bits(q) + 2^18) >> 19) - 0x7AF      q = 0.0625 -> 1, 0.125 -> 17, top (15.32..) -> 128
-//     SFP<3,3> :  c = ((bits(q) + 2^19) >> 20) - 0x3D7      q = 0.0625 -> 1, 0.125 -> 9,  top (15)     -> 64
-// saturated to [0, 255]: i.e. (octave, linear mantissa index) - the reference's linear pre-round
-// `round(16 m)/16` (sfp_quant.py:88) - and the log converter of :89 lives in the CONSUMER's decode table.
-//     c = 0           -> 0         (everything below 0.0625: the reference's 1e-10 is 0 in float16)
-//     c = 1 .. 16/8   -> 0.125     ([0.0625, 0.125) -> 0.125, :93 / :75)
-//     c above the top -> top value (a > 15.32165 -> 15.32165, :95; a >= 15 -> 15, :77)
-// Two deviations from encode<>, both invisible after the float16 rounding of the tensor-core operand or
-// below the float32 noise of the convolution itself: ties of the mantissa rounding go up instead of to
-// even, and the quotient q = y * (1/Ka) is a reciprocal multiply.
+// the code needs no sign.  The unsigned code is the TRUNCATED float32 bit pattern, re-based, with one more
+// mantissa bit than the format keeps (a half step):
+//     SLFP<3,4>:  c = (bits(q) >> 18) - 0xF5F      q = 0.0625 -> 1, 0.125 -> 33, 15.25.. -> 255
+//     SFP<3,3> :  c = (bits(q) >> 19) - 0x7AF      q = 0.0625 -> 1, 0.125 -> 17, 15      -> 127
+// saturated to [0, 255].  Truncation keeps every class boundary of the reference exact (a < 0.0625, a < 0.125,
+// the saturation thresholds compare the UN-rounded value, sfp_quant.py:92-95 / :74-77); the rounding itself
+// - the reference's linear pre-round `round(2^mbits m)` (:88 / :69) - is finished by the CONSUMER's decode
+// table from the half-step bit, which also applies the SLFP log converter of :89:
+//     c = 0               -> 0         (everything below 0.0625: the reference's 1e-10 is 0 in float16)
+//     u = c - 1 = E*2H+h  -> E = 0: 0.125 ([0.0625, 0.125) -> 0.125, :93 / :75); E >= 1: mantissa index
+//                            i = (h + 1) >> 1, value 2^(E-4) * grid[i], clamped to the top value (:95 / :77)
+// Two deviations from encode<>, both far below the float32 noise of the convolution that feeds the encoder:
+// exact ties of the mantissa rounding (all 18 / 19 dropped bits equal to 10...0) go up instead of to even,
+// and the quotient q = y * (1/Ka) is a reciprocal multiply.
 template <bool SFP33>
 __host__ __device__ __forceinline__ int32_t encode_relu_fast_raw(float q_nonneg) {
     const int32_t b = (int32_t)f2u(q_nonneg);
-    return SFP33 ? ((b + (int32_t)(0x80000u - (0x3D7u << 20))) >> 20) : ((b + (int32_t)(0x40000u - (0x7AFu << 19))) >> 19);
+    return SFP33 ? ((b >> 19) - 0x7AF) : ((b >> 18) - 0xF5F);
 }
-// The same on q/16 (the epilogue computes clamp(q/16, 0, 1) with one saturating FMA: ReLU, the
-// scale by 1/Ka and the upper clamp in a single instruction); top -> 128 / 64, 1.0 -> 129 / 65 (alias of top).
+// The same on q/16 (the epilogue computes clamp(q/16, 0, 1) with one saturating FMA: ReLU, the scale by 1/Ka
+// and an upper clamp in a single instruction); 1.0 lands above the top code and saturates in the pack.
 template <bool SFP33>
 __host__ __device__ __forceinline__ int32_t encode_relu_fast_raw16(float q16_sat) {
     const int32_t b = (int32_t)f2u(q16_sat);
-    return SFP33 ? ((b + (int32_t)(0x80000u - (0x3B7u << 20))) >> 20) : ((b + (int32_t)(0x40000u - (0x76Fu << 19))) >> 19);
+    return SFP33 ? ((b >> 19) - 0x76F) : ((b >> 18) - 0xEDF);
 }
 template <bool SFP33>
 __host__ __device__ __forceinline__ uint32_t encode_relu_fast(float q) {
@@ -298,14 +301,19 @@ template <bool SFP33>
 __host__ __device__ __forceinline__ float decode_relu(uint32_t code, const uint32_t* __restrict__ tab) {
     const uint32_t c = code & 0xffu;
     if (c == 0u) return 0.0f;
+    const uint32_t u = c - 1u;
     if (SFP33) {
-        const uint32_t u = c > 64u ? 63u : (c < 9u ? 8u : c - 1u);
-        return u2f((((u >> 3) + 123u) << 23) | ((u & 7u) << 20));
+        const uint32_t E = u >> 4, i = ((u & 15u) + 1u) >> 1;            // i in 0..8
+        if (E == 0u) return 0.125f;
+        const uint32_t r = ((E + 123u) << 23) + (i << 20);               // i = 8 carries into the exponent
+        return u2f(r > kBits15 ? kBits15 : r);
     }
-    const uint32_t u = c > 128u ? 127u : (c < 17u ? 16u : c - 1u);
-    const uint32_t i = u & 15u;
-    const uint32_t L = i + ((i >= 2u && i <= 14u) ? 1u : 0u);
-    return u2f(tab[L] + (((u >> 4) - 4u) << 23));
+    const uint32_t E = u >> 5, i = ((u & 31u) + 1u) >> 1;                // i in 0..16
+    if (E == 0u) return 0.125f;
+    const uint32_t L = i + ((i >= 2u && i <= 14u) ? 1u : 0u);            // log converter; 16 = next octave
+    const uint32_t r = (L == 16u ? 0x40000000u : tab[L]) + ((E - 4u) << 23);
+    const uint32_t top = tab[15] + (3u << 23);                           // 2^(3 + 15/16)
+    return u2f(r > top ? top : r);
 }
 
 // value of an activation code in any of the four code formats a dense conv accepts

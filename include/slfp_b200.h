@@ -26,13 +26,13 @@
  *              u = 3 -> NaN
  *
  * post-ReLU codes (SLFP_FMT_SLFP34_RELU / SLFP_FMT_SFP33_RELU), unsigned byte c, value >= 0:
- *     c = ((float32_bits(q) + half) >> (23 - mbits)) - base, saturated to [0, 255]  (mbits 4 / 3)
- *     c = 0 -> 0.0 (|q| < 0.0625) ; c = 1..2^mbits -> 0.125 ; above the top code -> the top value ;
- *     otherwise u = c - 1 = E*2^mbits + i with i the LINEAR mantissa index round(2^mbits * m): the
- *     SLFP log converter i -> M = [0,1,3,4,...,15,15] (utils/sfp_quant.py:88-89) is applied by the
- *     consumer's decode table.  Values decode onto the same grid as the signed codes; +-1e-10 and the
- *     15.32165 literal are represented by 0 and the top grid value (equal after float16 rounding of
- *     the tensor-core operand).
+ *     c = (float32_bits(q) >> (22 - mbits)) - base, saturated to [0, 255]   (mbits 4 / 3; base 0xF5F / 0x7AF)
+ *     i.e. the truncated bit pattern with ONE more mantissa bit than the grid keeps.  c = 0 -> 0.0 (q < 0.0625);
+ *     u = c - 1 = E * 2^(mbits+1) + h:  E = 0 -> 0.125;  E >= 1 -> 2^(E-4) * grid[(h + 1) >> 1], clamped to the top
+ *     grid value.  Class boundaries (0.0625, 0.125, saturation) are exact; the mantissa rounding (ties up) and the
+ *     SLFP log converter [0,1,3,4,...,15,15] (utils/sfp_quant.py:88-89) are applied by the consumer's decode
+ *     table.  +-1e-10 and the 15.32165 literal are represented by 0 and the top grid value (equal after the
+ *     float16 rounding of the tensor-core operand).
  */
 #ifndef SLFP_B200_H_
 #define SLFP_B200_H_

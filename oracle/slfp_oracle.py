@@ -76,6 +76,29 @@ def decode(codes, fmt):
     return out
 
 
+def decode_relu(codes, sfp33=False):
+    """Value of the fused pipeline's unsigned post-ReLU codes (include/slfp_b200.h, SLFP_FMT_*_RELU), restated
+    from the reference's grids.  c = 0 -> 0 (sfp_quant.py:92 / :74: |x| < 0.0625 -> 1e-10, which is 0 as a float16
+    tensor-core operand); u = c - 1 = E * 2H + h (H = 16 / 8 mantissa steps, h a HALF-step index): E = 0 -> 0.125
+    (:93 / :75); E >= 1 -> mantissa index i = (h + 1) >> 1 = round(H m) of :88 / :69 (ties up), pushed through the
+    log converter of :89 for SLFP (log index = i + [2 <= i <= 14]); clamped to the top value (:95 / :77)."""
+    c = np.asarray(codes).astype(np.int64)
+    u = np.maximum(c - 1, 0)
+    if sfp33:
+        E, i = u >> 4, ((u & 15) + 1) >> 1
+        val = np.minimum((1.0 + i / 8.0) * np.exp2(E - 4.0), 15.0)
+    else:
+        E, i = u >> 5, ((u & 31) + 1) >> 1
+        L = i + ((i >= 2) & (i <= 14))
+        # float32(2^(j/16)) as the reference's pow() returns it (tests/golden/make_golden.log); index 16 = 2.0
+        tab = np.array([0x3f800000, 0x3f85aac3, 0x3f8b95c2, 0x3f91c3d3, 0x3f9837f0, 0x3f9ef532, 0x3fa5fed7, 0x3fad583f,
+                        0x3fb504f3, 0x3fbd08a4, 0x3fc5672a, 0x3fce248c, 0x3fd744fd, 0x3fe0ccdf, 0x3feac0c7, 0x3ff5257d,
+                        0x40000000], dtype=np.uint32).view(np.float32).astype(np.float64)
+        val = np.minimum(tab[L] * np.exp2(E - 4.0), tab[15] * 8.0)
+    val = np.where(E == 0, 0.125, val)
+    return np.where(c == 0, 0.0, val).astype(np.float32)
+
+
 def absmax(x):
     """max(|x|) -- cifar100_train_eval.py:261-271 (calibration)."""
     x = np.ascontiguousarray(x, dtype=np.float32)

@@ -61,3 +61,17 @@ extern "C" size_t hostcheck_fused_quant_mismatches(const float* x, size_t n, flo
     }
     return bad;
 }
+
+// post-ReLU code formats: codes and their values through the product's encode_relu_fast / decode_relu
+extern "C" void hostcheck_relu_codes(const float* q, size_t n, int sfp33, uint8_t* codes, float* values, uint8_t* codes16) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t c = sfp33 ? encode_relu_fast<true>(q[i]) : encode_relu_fast<false>(q[i]);
+        codes[i] = (uint8_t)c;
+        values[i] = sfp33 ? decode_relu<true>(c, h_pow2frac) : decode_relu<false>(c, h_pow2frac);
+        // the epilogue's form: clamp(q/16, 0, 1) -> raw16 -> saturating pack
+        float q16 = q[i] * 0.0625f;
+        q16 = q16 > 0.f ? (q16 > 1.f ? 1.f : q16) : 0.f;
+        int32_t t = sfp33 ? encode_relu_fast_raw16<true>(q16) : encode_relu_fast_raw16<false>(q16);
+        codes16[i] = (uint8_t)(t < 0 ? 0 : (t > 255 ? 255 : t));
+    }
+}

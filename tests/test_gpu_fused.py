@@ -1,0 +1,252 @@
+"""GPU: the fused eval pipeline's pieces - post-ReLU code formats written by the conv epilogue, the
+space-to-depth stem (asymmetric padding), batched weight re-quantization, max-pool on unsigned codes -
+and whole-net parity of the compiled plans against the reference-generated fixture."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _h(a):
+    return np.asarray(a, np.float32).astype(np.float16)
+
+
+def _conv_fast(x, w, ka, kw, mul, add, stride, pad, residual=None, want_f16=False, next_ks=(0.21,), qbit=8, pad_extra=0,
+               in_codes=None, in_fmt=None):
+    """conv through the C ABI with the folded epilogue; returns dict(y32 from a second launch, y16, codes...)."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    dev = torch.device("cuda:0")
+    xt = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev).permute(0, 2, 3, 1).contiguous()
+    wt = torch.from_numpy(np.ascontiguousarray(w, np.float32)).to(dev)
+    N, H, W, C = xt.shape
+    K, _, R, S = wt.shape
+    Cp = (C + 15) // 16 * 16
+    afmt, wfmt = nv.fmt_for(qbit, "act"), nv.fmt_for(qbit, "weight")
+    st = nv.stream()
+    if in_codes is None:
+        xc = torch.empty((N, H, W, Cp), dtype=torch.uint8, device=dev)
+        nv.check(lib.slfp_quantize_nhwc_f32(xt.data_ptr(), N * H * W, C, Cp, float(np.float32(ka)), afmt, xc.data_ptr(), st))
+        fmt_in = afmt
+    else:
+        xc, fmt_in = in_codes, in_fmt
+    d = nv.SlfpConvDesc(N, H, W, C, Cp, K, R, S, stride, stride, pad, pad, 1, 1, 1, fmt_in, pad_extra, pad_extra)
+    Ho = (H + 2 * pad + pad_extra - (R - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad + pad_extra - (S - 1) - 1) // stride + 1
+    pitch = lib.slfp_conv_wpitch(ctypes.byref(d))
+    wh = torch.empty((K * pitch,), dtype=torch.float16, device=dev)
+    so, sc, sr, ss = wt.stride()
+    nv.check(lib.slfp_prepare_weights(ctypes.byref(d), wt.data_ptr(), so, sc, sr, ss, float(np.float32(kw)), wfmt, wh.data_ptr(),
+                                      None, None, st))
+    mul_t = torch.from_numpy(np.asarray(mul, np.float32)).to(dev)
+    add_t = torch.from_numpy(np.asarray(add, np.float32)).to(dev)
+    res_t = None if residual is None else torch.from_numpy(np.ascontiguousarray(residual.transpose(0, 2, 3, 1))).to(dev)
+    out = {}
+    # launch 1: float32 output of the same folded arithmetic (generic epilogue) = the quantizer's input
+    e = nv.SlfpEpilogue()
+    e.ch_mul, e.ch_add, e.relu = mul_t.data_ptr(), add_t.data_ptr(), 1
+    y32 = torch.empty((N, Ho, Wo, K), dtype=torch.float32, device=dev)
+    e.y_f32 = y32.data_ptr()
+    if res_t is not None:
+        e.residual, e.residual_f16 = res_t.data_ptr(), 1
+    nv.check(lib.slfp_conv2d_fwd(ctypes.byref(d), xc.data_ptr(), wh.data_ptr(), ctypes.byref(e), st))
+    # launch 2: the fast epilogue (post-ReLU codes, optional float16)
+    e2 = nv.SlfpEpilogue()
+    e2.ch_mul, e2.ch_add, e2.relu = mul_t.data_ptr(), add_t.data_ptr(), 1
+    if res_t is not None:
+        e2.residual, e2.residual_f16 = res_t.data_ptr(), 1
+    rfmt = nv.relu_fmt(afmt)
+    codes = [torch.full((N, Ho, Wo, K), 77, dtype=torch.uint8, device=dev) for _ in next_ks]
+    e2.y_codes, e2.next_k_div, e2.next_fmt, e2.k_phys_out = codes[0].data_ptr(), float(np.float32(next_ks[0])), rfmt, K
+    if len(next_ks) > 1:
+        e2.y_codes2, e2.next_k_div2 = codes[1].data_ptr(), float(np.float32(next_ks[1]))
+    y16 = None
+    if want_f16:
+        y16 = torch.empty((N, Ho, Wo, K), dtype=torch.float16, device=dev)
+        e2.y_f16 = y16.data_ptr()
+    nv.check(lib.slfp_conv2d_fwd(ctypes.byref(d), xc.data_ptr(), wh.data_ptr(), ctypes.byref(e2), st))
+    torch.cuda.synchronize()
+    out["y32"] = y32.cpu().numpy()
+    out["y16"] = None if y16 is None else y16.cpu().numpy()
+    out["codes"] = [c.cpu().numpy() for c in codes]
+    out["codes_dev"], out["rfmt"] = codes, rfmt
+    return out
+
+
+def _check_codes(orc, y32, codes, kd, sfp33):
+    """decode(code), as the float16 tensor-core operand, equals the reference quantizer of y / Ka - evaluated at
+    y/Ka * (1 -+ 2^-21) to admit the epilogue's reciprocal multiply and FMA-folded scale near a class boundary."""
+    got = _h(orc.decode_relu(codes, sfp33))
+    q = y32.astype(np.float64) / float(np.float32(kd))
+    fmt = 0 if sfp33 else 1
+    ok = np.zeros(q.shape, bool)
+    for eps in (0.0, -5e-7, 5e-7):
+        _, want = orc.quantize((q * (1.0 + eps)).astype(np.float32), fmt, want_codes=False)
+        ok |= got == _h(want)
+    assert ok.all(), f"{(~ok).sum()} of {ok.size} codes off the reference grid value"
+    # and away from boundaries it is exact: at most a sliver may need the +-eps alternatives
+    _, want0 = orc.quantize(q.astype(np.float32), fmt, want_codes=False)
+    assert (got != _h(want0)).mean() < 2e-4
+
+
+@pytest.mark.parametrize("qbit", [8, 7])
+def test_fast_epilogue_codes_only(orc, qbit):
+    rng = np.random.default_rng(5)
+    for (N, C, H, K, k, st, pad) in [(2, 64, 12, 96, 3, 1, 1), (3, 128, 9, 64, 1, 1, 0), (2, 32, 10, 272, 3, 2, 1)]:
+        x = (rng.standard_normal((N, C, H, H)) * 2).astype(np.float32)
+        w = (rng.standard_normal((K, C, k, k)) * 0.2).astype(np.float32)
+        ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+        mul = (rng.uniform(0.5, 1.5, K) * ka * kw).astype(np.float32)
+        add = (rng.standard_normal(K) * 0.5).astype(np.float32)
+        nk = 0.19
+        o = _conv_fast(x, w, ka, kw, mul, add, st, pad, next_ks=(nk,), qbit=qbit)
+        assert (o["y32"] >= 0).all()
+        _check_codes(orc, o["y32"], o["codes"][0], nk, qbit == 7)
+
+
+def test_fast_epilogue_residual_f16_two_consumers(orc):
+    rng = np.random.default_rng(6)
+    N, C, H, K = 2, 64, 11, 256
+    x = (rng.standard_normal((N, C, H, H)) * 2).astype(np.float32)
+    w = (rng.standard_normal((K, C, 1, 1)) * 0.2).astype(np.float32)
+    ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+    mul = (rng.uniform(0.1, 0.3, K) * ka * kw).astype(np.float32)
+    add = (rng.standard_normal(K) * 0.2).astype(np.float32)
+    res = np.abs(rng.standard_normal((N, K, H, H))).astype(np.float16)
+    o = _conv_fast(x, w, ka, kw, mul, add, 1, 0, residual=res, want_f16=True, next_ks=(0.17, 0.31))
+    y = o["y32"]
+    assert (o["y16"] == _h(y)).all()                       # the float16 copy is RN(float32 result)
+    _check_codes(orc, y, o["codes"][0], 0.17, False)
+    _check_codes(orc, y, o["codes"][1], 0.31, False)
+    # a dense layer consumes the post-ReLU codes: its output equals the conv of their decoded values
+    from cnns_slfp_quantization_b200 import _native as nv
+    xq = orc.decode_relu(o["codes"][0], False).transpose(0, 3, 1, 2)
+    w2 = (rng.standard_normal((64, K, 3, 3)) * 0.1).astype(np.float32)
+    kw2 = float(np.abs(w2).max() / 15.5)
+    o2 = _conv_fast(xq, w2, 0.17, kw2, np.full(64, 0.17 * kw2, np.float32), np.zeros(64, np.float32), 1, 1,
+                    in_codes=o["codes_dev"][0], in_fmt=o["rfmt"])
+    _, wq = orc.quantize(w2, 2, kw2, want_codes=False)
+    x16, w16 = _h(xq).astype(np.float64), _h(wq).astype(np.float64)
+    want = torch.nn.functional.conv2d(torch.from_numpy(x16), torch.from_numpy(w16), None, 1, 1).numpy() * (0.17 * kw2)
+    l1 = torch.nn.functional.conv2d(torch.from_numpy(np.abs(x16)), torch.from_numpy(np.abs(w16)), None, 1, 1).numpy() * 0.17 * kw2
+    got = o2["y32"].transpose(0, 3, 1, 2)
+    assert (np.abs(got - np.maximum(want, 0)) <= 3e-6 * l1 + 1e-6).all()
+
+
+def test_space_to_depth_stem_equals_strided_conv(orc):
+    """7x7 / stride 2 / pad 3 on 3 channels through the folded 4x4 / stride 1 form (asymmetric padding, TMA
+    im2col kernel) against the same layer through the 4-channel-input kernel."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    from gpu_util import conv_fwd_gpu
+    lib = nv.lib()
+    rng = np.random.default_rng(8)
+    N, C, H, K = 3, 3, 32, 64
+    x = (rng.standard_normal((N, C, H, H)) * 2).astype(np.float32)
+    w = (rng.standard_normal((K, C, 7, 7)) * 0.2).astype(np.float32)
+    ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+    ref = conv_fwd_gpu(x, w, None, ka, kw, 8, 2, 3, 1, 1)["y"]
+    dev = torch.device("cuda:0")
+    xt = torch.from_numpy(x).to(dev)
+    cp = 16
+    xs = torch.empty((N, H // 2, H // 2, cp), dtype=torch.uint8, device=dev)
+    nv.check(lib.slfp_quantize_nchw_s2d_f32(xt.data_ptr(), N, C, H, H, cp, float(np.float32(ka)), nv.FMT_SLFP34_ACT, xs.data_ptr(),
+                                            nv.stream()))
+    torch.cuda.synchronize()
+    # the folded codes are the plain quantizer's codes, re-arranged
+    codes, _ = orc.quantize(x, 1, ka)
+    want = np.zeros((N, H // 2, H // 2, cp), np.uint8)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(C):
+                want[..., (dy * 2 + dx) * C + c] = codes[:, c, dy::2, dx::2]
+    assert (xs.cpu().numpy() == want).all()
+    wp = np.zeros((K, C, 8, 8), np.float32)
+    wp[:, :, 1:, 1:] = w
+    w2 = wp.reshape(K, C, 4, 2, 4, 2).transpose(0, 3, 5, 1, 2, 4).reshape(K, 4 * C, 4, 4)
+    xq = orc.decode(want, 1)[..., :4 * C].transpose(0, 3, 1, 2)
+    o = _conv_fast(xq, w2, ka, kw, np.full(K, np.float32(ka) * np.float32(kw), np.float32), np.zeros(K, np.float32), 1, 2,
+                   pad_extra=-1, in_codes=xs, in_fmt=nv.FMT_SLFP34_ACT)
+    got = o["y32"].transpose(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    scale = np.abs(ref).max()
+    assert np.abs(got - np.maximum(ref, 0)).max() <= 2e-5 * scale
+
+
+def test_batched_weight_preparation_equals_per_layer(orc):
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(9)
+    shapes = [(64, 3, 7, 7, 4), (96, 64, 3, 3, 64), (1000, 80, 1, 1, 80), (24, 24, 3, 3, 32)]
+    descs, ws, singles, batch_out, strides, kws = [], [], [], [], [], []
+    for (K, C, R, S, Cp) in shapes:
+        d = nv.SlfpConvDesc(1, 8, 8, C, Cp, K, R, S, 1, 1, 0, 0, 1, 1, 1, nv.FMT_SLFP34_ACT)
+        w = torch.from_numpy((rng.standard_normal((K, C, R, S)) * 0.3).astype(np.float32)).to(dev)
+        pitch = lib.slfp_conv_wpitch(ctypes.byref(d))
+        a = torch.zeros(K * pitch, dtype=torch.float16, device=dev)
+        b = torch.ones(K * pitch, dtype=torch.float16, device=dev)
+        kw = float(np.float32(0.3 * 3 / 15.5))
+        nv.check(lib.slfp_prepare_weights(ctypes.byref(d), w.data_ptr(), *w.stride(), kw, nv.FMT_SLFP34_WGT, a.data_ptr(), None, None,
+                                          nv.stream()))
+        descs.append(d); ws.append(w); singles.append(a); batch_out.append(b); strides += list(w.stride()); kws.append(kw)
+    n = len(shapes)
+    nv.check(lib.slfp_prepare_weights_batch(
+        n, (ctypes.POINTER(nv.SlfpConvDesc) * n)(*[ctypes.pointer(d) for d in descs]),
+        (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws]), (ctypes.c_longlong * (4 * n))(*strides), (ctypes.c_float * n)(*kws),
+        nv.FMT_SLFP34_WGT, (ctypes.c_void_p * n)(*[b.data_ptr() for b in batch_out]), None, nv.stream()))
+    torch.cuda.synchronize()
+    for a, b in zip(singles, batch_out):
+        assert torch.equal(a, b)
+
+
+def test_maxpool_on_post_relu_codes(orc):
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    rng = np.random.default_rng(10)
+    N, H, W, C = 2, 13, 14, 32
+    codes = rng.integers(0, 256, (N, H, W, C), dtype=np.uint8)
+    x = torch.from_numpy(codes).cuda()
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device="cuda")
+    nv.check(lib.slfp_maxpool_codes(x.data_ptr(), N, H, W, C, nv.FMT_SLFP34_RELU, 3, 3, 2, 1, y.data_ptr(), nv.stream()))
+    torch.cuda.synchronize()
+    vals = torch.from_numpy(orc.decode_relu(codes, False)).permute(0, 3, 1, 2)
+    want = torch.nn.functional.max_pool2d(vals, 3, 2, 1).permute(0, 2, 3, 1).numpy()
+    assert (orc.decode_relu(y.cpu().numpy(), False) == want).all()    # pooling commutes with decoding (monotone codes)
+
+
+@pytest.mark.parametrize("name", ["resnet50", "vgg16", "mobilenetv1_cifar", "mobilenetv1_imgnet"])
+def test_whole_net_against_reference_fixture(name):
+    """Compiled plan (codes between layers, CUDA graph) and the module-level drop-in against logits computed by
+    the REFERENCE nets on CPU (tests/golden/net_cases.npz).  Tolerance: the tensor-core operands are float16
+    images of the SLFP grid (relative error <= 2^-12 per operand), which moves about 0.5 % of the next layer's
+    codes by one grid step; through 16-54 quantized layers of a random-weight net that accumulates to the stated
+    logit RMS.  top-1 must agree wherever the reference's own margin is clear of that noise."""
+    sys.path.insert(0, ROOT)
+    from tools.netcheck import prepare, G
+    from cnns_slfp_quantization_b200 import nets_common as nc
+    m, comp, batch, size = prepare(name)
+    x = nc.synth_images(batch, size).cuda()
+    ref = G[f"{name}.logits"]
+    with torch.no_grad():
+        ym = m(x.contiguous(memory_format=torch.channels_last)).float().cpu().numpy()
+    plan = comp(m, batch, size)
+    ye = plan(x).float().cpu().numpy().copy()
+    plan.capture()
+    yg = plan(x).float().cpu().numpy()
+    assert (ye == yg).all(), "CUDA-graph replay differs from the eager plan"
+    srt = np.sort(ref, 1)
+    margin = srt[:, -1] - srt[:, -2]
+    for what, y in (("modules", ym), ("engine", ye)):
+        rms = float(np.sqrt(((y - ref) ** 2).mean()))
+        assert rms <= 0.45 * float(ref.std()), (name, what, rms, float(ref.std()))
+        clear = margin > 4.0 * rms
+        assert (y.argmax(1)[clear] == ref.argmax(1)[clear]).all(), (name, what, y.argmax(1).tolist(), ref.argmax(1).tolist())
+    # both of our paths see the same operand rounding: they agree with each other at least as well as with the fixture
+    assert float(np.sqrt(((ye - ym) ** 2).mean())) <= 0.45 * float(ref.std())

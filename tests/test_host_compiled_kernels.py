@@ -57,3 +57,44 @@ def test_decode_all_codes(hostcheck, orc):
                                    out.ctypes.data_as(ctypes.c_void_p))
         ref = orc.decode(codes, fmt)
         assert ((bits(out) == bits(ref)) | (np.isnan(out) & np.isnan(ref))).all()
+
+
+def _relu_codes(lib, q, sfp33):
+    q = np.ascontiguousarray(q, np.float32)
+    c, c16 = np.empty(q.shape, np.uint8), np.empty(q.shape, np.uint8)
+    v = np.empty_like(q)
+    lib.hostcheck_relu_codes(q.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(q.size), ctypes.c_int(sfp33),
+                             c.ctypes.data_as(ctypes.c_void_p), v.ctypes.data_as(ctypes.c_void_p),
+                             c16.ctypes.data_as(ctypes.c_void_p))
+    return c, v, c16
+
+
+@pytest.mark.parametrize("sfp33", [0, 1])
+def test_post_relu_codes_match_the_reference_quantizer(hostcheck, orc, sfp33):
+    """The fused pipeline's unsigned post-ReLU codes (2-instruction encoder) against the reference quantizer:
+    for every float32 mantissa in every octave the decoded value, as the float16 tensor-core operand, equals the
+    reference's fake-quant value - except exact ties of the mantissa rounding, which go up instead of to even
+    (documented in include/slfp_b200.h) - and negative inputs give code 0 (the ReLU)."""
+    fmt = 0 if sfp33 else 1
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    tie_mask = np.uint32((1 << (20 if sfp33 else 19)) - 1)       # bits below the kept mantissa
+    tie_val = np.uint32(1 << (19 if sfp33 else 18))              # exactly one half
+    for e in (-9, -5, -4, -3, -1, 0, 2, 3, 4, 9):
+        q = (mant | np.uint32((e + 127) << 23)).view(np.float32)
+        c, v, c16 = _relu_codes(hostcheck, q, sfp33)
+        _, want = orc.quantize(q, fmt)
+        same = v.astype(np.float16) == want.astype(np.float16)
+        ties = (mant & tie_mask) == tie_val
+        assert same[~ties].all(), (sfp33, e, int((~same & ~ties).sum()))
+        # a tie rounds up: one grid step above (or equal to) the reference's round-half-even value
+        assert (v[ties].astype(np.float16) >= want[ties].astype(np.float16)).all()
+        # decode agrees with the oracle's numpy restatement of the code table
+        assert (bits(v) == bits(orc.decode_relu(c, bool(sfp33)))).all()
+        # the epilogue's clamp(q/16, 0, 1) form yields the same code (or an alias of the top value)
+        assert (orc.decode_relu(c16, bool(sfp33)) == v).all(), (sfp33, e)
+    neg = -np.abs(np.random.default_rng(0).standard_normal(1000).astype(np.float32))
+    c, v, c16 = _relu_codes(hostcheck, np.concatenate([neg, [0.0, -0.0]]).astype(np.float32), sfp33)
+    assert (c == 0).all() and (v == 0).all() and (c16 == 0).all()
+    # all 256 codes decode monotonically (max-pooling on codes commutes with decoding)
+    allv = orc.decode_relu(np.arange(256, dtype=np.uint8), bool(sfp33))
+    assert (np.diff(allv) >= 0).all()
