@@ -37,10 +37,20 @@ constexpr int kCodeBytes = kBM * kBK;                  // 8 KB of codes per K bl
 constexpr int kABytes = kBM * kBK * 2;                 // 16 KB float16 A tile
 constexpr int kLutBytes = 256 * 32 * 4;                // code -> f16, one copy per bank
 constexpr int kWarpCode = 0, kWarpWgt = 1, kWarpMma = 2;
-constexpr int kDecWarp0 = 4, kDecWarps = 8;
-constexpr int kEpiWarp0 = 12, kEpiWarps = 8;     // warpgroups 3-4; 8 consecutive warps cover every TMEM lane quadrant twice
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 640: launched with 96 registers per thread, re-balanced with setmaxnreg
-constexpr int kRegsLean = 64, kRegsEpi = 144;          // 12 warps x 64 + 8 warps x 144 = 61 440 <= 65 536 registers per SM
+// 28 warps: 4 control (2 producers, MMA issuer, spare) + DW decode + (24 - DW) epilogue.  Two role splits, chosen
+// per layer on the host: DW = 16 for decode-heavy layers (3x3, large K), DW = 8 for epilogue-heavy ones (the 1x1
+// block tails: residual + float16 + codes).  Launched with 72 registers per thread, re-balanced with setmaxnreg:
+//   DW 16:  4 x 40 + 16 x 48 +  8 x 136   (x 32 lanes) = 64 512 registers
+//   DW  8:  4 x 40 +  8 x 56 + 16 x  88                = 64 512
+constexpr int kCtrlWarps = 4, kDecWarp0 = 4, kWorkWarps = 24;
+constexpr int kThreads = (kCtrlWarps + kWorkWarps) * 32;   // 896
+constexpr int kRegsCtrl = 40;
+template <int DW> struct Roles {
+    static constexpr int kDecWarps = DW, kEpiWarps = kWorkWarps - DW, kEpiWarp0 = kDecWarp0 + DW;
+    static constexpr int kGroups = kEpiWarps / 4;                      // column groups per TMEM lane quadrant
+    static constexpr int kRegsDec = DW == 16 ? 48 : 56, kRegsEpi = DW == 16 ? 136 : 88;
+    static constexpr int kChunksPerThread = 512 / (32 * DW);           // 16-byte code chunks per decode thread per K block
+};
 
 struct Params {
     uint32_t M;
@@ -69,12 +79,12 @@ struct Cfg {
 };
 
 // ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int G>
 __device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_t tmem_acc, int quad, int half, int lane) {
     const SlfpEpilogue& e = p.epi;
     const int Kout = p.Kout;
     const bool vec4 = (Kout & 3) == 0, vec8 = (Kout & 7) == 0;
-    constexpr int kCols = BLOCK_N / 2;
+    constexpr int kCols = BLOCK_N / G;
     const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
     const int n_base = (tile % p.n_tiles) * BLOCK_N + half * kCols;
     const bool row_ok = m < p.M;
@@ -278,10 +288,11 @@ __device__ __forceinline__ void pair_exchange(const uint4& A, const uint4& B, bo
     second.x = odd ? B.x : recv.x; second.y = odd ? B.y : recv.y; second.z = odd ? B.z : recv.z; second.w = odd ? B.w : recv.w;
 }
 
-template <int BLOCK_N, int MODE, bool SFP33>
+template <int BLOCK_N, int G, int MODE, bool SFP33>
 __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int next_tile, uint32_t tmem_acc, int quad, int half,
                                               int lane, uint32_t s_mul, uint32_t s_add) {
-    constexpr int kCols = BLOCK_N / 2;
+    static_assert(BLOCK_N / G >= 32, "32-column steps");
+    constexpr int kCols = BLOCK_N / G;
     const int Kout = p.Kout;
     const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
     const int n_tile0 = (tile % p.n_tiles) * BLOCK_N;
@@ -396,10 +407,132 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
     }
 }
 
-template <int BLOCK_N, int GRAN>
+// The same epilogues in 16-column steps for the 16-epilogue-warp role split (88 registers per thread, 4 column
+// groups of BLOCK_N / 4 columns): the residual of the next chunk is requested before the current one is
+// processed, code pieces of two consecutive chunks pair up for the full-sector stores.
+template <int BLOCK_N, int G, int MODE, bool SFP33>
+__device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int next_tile, uint32_t tmem_acc, int quad, int cg,
+                                                int lane, uint32_t s_mul, uint32_t s_add) {
+    constexpr int kCols = BLOCK_N / G;
+    constexpr int kChunks = kCols / 16;
+    const int Kout = p.Kout;
+    const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
+    const int n_base = (tile % p.n_tiles) * BLOCK_N + cg * kCols;
+    const bool odd = (lane & 1) != 0;
+    const uint32_t m_first = m & ~1u, m_second = m | 1u;
+    const bool ok_first = m_first < p.M, ok_second = m_second < p.M, row_ok = m < p.M;
+    const size_t row = (size_t)m * (size_t)Kout + n_base;
+    const size_t row_first = (size_t)m_first * (size_t)Kout + n_base, row_second = (size_t)m_second * (size_t)Kout + n_base;
+    const __half* resp = MODE == 2 ? reinterpret_cast<const __half*>(p.epi.residual) : nullptr;
+    __half* y16 = MODE == 2 ? reinterpret_cast<__half*>(p.epi.y_f16) : nullptr;
+    uint8_t* yc1 = p.epi.y_codes;
+    uint8_t* yc2 = MODE == 2 ? p.epi.y_codes2 : nullptr;
+    const float sc1 = p.sc1, sc2 = p.sc2;
+    int nvalid = (Kout - n_base) >> 4;                           // chunks of this slab inside Kout
+    nvalid = nvalid > kChunks ? kChunks : nvalid;
+    if (MODE == 2 && resp != nullptr && next_tile < p.num_tiles) {
+        const uint32_t mn = (uint32_t)(next_tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
+        const int nb = (next_tile % p.n_tiles) * BLOCK_N + cg * kCols;
+        if (mn < p.M && nb < Kout) ptx::prefetch_l2(resp + (size_t)mn * Kout + nb);     // 32..128 bytes of one row
+    }
+    uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra, na = ra, nb4 = ra;
+    if (MODE == 2 && resp != nullptr && nvalid > 0 && row_ok) {
+        ra = __ldg(reinterpret_cast<const uint4*>(resp + row));
+        rb = __ldg(reinterpret_cast<const uint4*>(resp + row) + 1);
+    }
+    uint4 prev1 = ra, prev2 = ra;
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) {
+        if (ch >= nvalid) break;                                 // warp-uniform
+        uint32_t acc[16];
+        ptx::tmem_ld16(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * kCols + ch * 16), acc);
+        if (MODE == 2 && resp != nullptr && ch + 1 < kChunks) {
+            na = nb4 = make_uint4(0u, 0u, 0u, 0u);
+            if (ch + 1 < nvalid && row_ok) {
+                na = __ldg(reinterpret_cast<const uint4*>(resp + row + (ch + 1) * 16));
+                nb4 = __ldg(reinterpret_cast<const uint4*>(resp + row + (ch + 1) * 16) + 1);
+            }
+        }
+        ptx::tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 m4 = ptx::lds128_f4(s_mul + (uint32_t)(cg * kCols + ch * 16 + 4 * g) * 4u);
+            const float4 a4 = ptx::lds128_f4(s_add + (uint32_t)(cg * kCols + ch * 16 + 4 * g) * 4u);
+            v[4 * g + 0] = fmaf(__uint_as_float(acc[4 * g + 0]), m4.x, a4.x);
+            v[4 * g + 1] = fmaf(__uint_as_float(acc[4 * g + 1]), m4.y, a4.y);
+            v[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), m4.z, a4.z);
+            v[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), m4.w, a4.w);
+        }
+        uint4 pk1, pk2 = make_uint4(0u, 0u, 0u, 0u);
+        if (MODE == 1) {
+            int32_t t[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i]));
+            pk1 = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
+                             ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+        } else {
+            if (resp != nullptr) {
+                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                    v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                }
+                ra = na; rb = nb4;
+            }
+            if (y16 != nullptr) {
+                uint32_t hw[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __half2 h = __floats2half2_rn(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f));
+                    hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                uint4 f1, f2;
+                pair_exchange(make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]), odd, f1, f2);
+                if (ok_first) *reinterpret_cast<uint4*>(y16 + row_first + ch * 16 + (odd ? 8 : 0)) = f1;
+                if (ok_second) *reinterpret_cast<uint4*>(y16 + row_second + ch * 16 + (odd ? 8 : 0)) = f2;
+            }
+            pk1 = pk2;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                if ((pass ? yc2 : yc1) == nullptr) continue;
+                const float sc = pass ? sc2 : sc1;
+                int32_t t[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i] * sc));
+                const uint4 pk = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
+                                            ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+                if (pass) pk2 = pk; else pk1 = pk;
+            }
+        }
+        // code stores: odd chunk -> pair with the previous chunk's piece (32 contiguous bytes per row and lane pair);
+        // an even chunk without a successor goes out alone (16 bytes)
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            uint8_t* yc = pass ? yc2 : yc1;
+            if (yc == nullptr) continue;
+            const uint4 cur = pass ? pk2 : pk1;
+            if (ch & 1) {
+                uint4 f1, f2;
+                pair_exchange(pass ? prev2 : prev1, cur, odd, f1, f2);
+                if (ok_first) *reinterpret_cast<uint4*>(yc + row_first + (ch - 1) * 16 + (odd ? 16 : 0)) = f1;
+                if (ok_second) *reinterpret_cast<uint4*>(yc + row_second + (ch - 1) * 16 + (odd ? 16 : 0)) = f2;
+            } else if (ch + 1 >= nvalid) {
+                if (row_ok) *reinterpret_cast<uint4*>(yc + row + ch * 16) = cur;
+            } else {
+                if (pass) prev2 = cur; else prev1 = cur;
+            }
+        }
+    }
+}
+
+template <int BLOCK_N, int GRAN, int DW>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     using C = Cfg<BLOCK_N>;
+    using R = Roles<DW>;
+    constexpr int kDecWarps = R::kDecWarps, kEpiWarps = R::kEpiWarps, kEpiWarp0 = R::kEpiWarp0, kGroups = R::kGroups;
     // SW128 operand tiles need 1024-byte alignment.  The kernel has no static shared memory, so the dynamic
     // window starts at a link-time constant that honours __align__ (checked below): every shared address in
     // this kernel is then a compile-time offset and the table look-up needs no base-address add.
@@ -455,7 +588,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // register re-balance (warpgroup granularity; first statement of every role so that ptxas allocates each
     // region against its own budget): producers / MMA / decode need few registers, the epilogue many
     if (warp < kDecWarp0) {
-      ptx::setmaxnreg_dec<kRegsLean>();
+      ptx::setmaxnreg_dec<kRegsCtrl>();
       if (warp == kWarpCode) {
         // =========================== code producer: TMA im2col ===========================================
         if (lane == 0) {
@@ -537,17 +670,19 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         __syncwarp();
       }
     } else if (warp < kDecWarp0 + kDecWarps) {
-        ptx::setmaxnreg_dec<kRegsLean>();
+        ptx::setmaxnreg_dec<R::kRegsDec>();
         // =========================== decode: codes -> float16 A tile ==========================================
-        const int dtid = tid - kDecWarp0 * 32;                 // 0..255; chunk ids dtid and dtid + 256
+        constexpr int kCPT = R::kChunksPerThread;              // 1 (16 decode warps) or 2 (8 decode warps)
+        constexpr int kDecThreads = kDecWarps * 32;
+        const int dtid = tid - kDecWarp0 * 32;                 // chunk ids dtid + j * kDecThreads
         const uint32_t lut_base = ptx::smem_u32(s_lut);        // 128-byte aligned: (code << 7) | lane*4 never carries
         const uint32_t lane4 = (uint32_t)lane * 4u;
         const uint32_t code_base = ptx::smem_u32(s_code) + (uint32_t)dtid * 16u;
-        uint32_t a_off[2][2];                                  // [chunk][16-byte half] byte offset inside the A stage
-        int quarter[2];
+        uint32_t a_off[kCPT][2];                               // [chunk][16-byte half] byte offset inside the A stage
+        int quarter[kCPT];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int id = dtid + 256 * j;
+        for (int j = 0; j < kCPT; ++j) {
+            const int id = dtid + kDecThreads * j;
             const int row = GRAN == 64 ? (id >> 2) : (id & 127);
             const int q = GRAN == 64 ? (id & 3) : (id >> 7);
             quarter[j] = q;
@@ -561,13 +696,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         for (int ti = 0; ti < my_tiles; ++ti) {
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 ptx::mbar_wait(ptx::smem_u32(&bar_cfull[cs]), cphase);
-                uint32_t h[2][8];
+                uint32_t h[kCPT][8];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < kCPT; ++j) {
                     // 16-channel pieces beyond the last filter tap (K padding) are not loaded: zeros
                     const bool valid = GRAN == 64 || (kb * 4 + quarter[j] < k16_total);
                     uint4 cw = make_uint4(0u, 0u, 0u, 0u);
-                    if (valid) cw = ptx::lds128_volatile(code_base + cs * kCodeBytes + (uint32_t)(j * 4096));
+                    if (valid) cw = ptx::lds128_volatile(code_base + cs * kCodeBytes + (uint32_t)(j * kDecThreads * 16));
                     const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -589,7 +724,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u);   // MMA done with this stage
                 const uint32_t a_dst = a_base + stage * kABytes;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < kCPT; ++j) {
                     ptx::sts128(a_dst + a_off[j][0], h[j][0], h[j][1], h[j][2], h[j][3]);
                     ptx::sts128(a_dst + a_off[j][1], h[j][4], h[j][5], h[j][6], h[j][7]);
                 }
@@ -600,7 +735,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
         }
     } else {
-        ptx::setmaxnreg_inc<kRegsEpi>();
+        ptx::setmaxnreg_inc<R::kRegsEpi>();
         // =========================== epilogue ===================================================================
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
         const int half = (warp - kEpiWarp0) >> 2;
@@ -640,14 +775,26 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const int next_tile = ti + 1 < my_tiles ? tile + (int)gridDim.x : p.num_tiles;
             const uint32_t tacc = tile_begin(ti, tile);
-            if (mode == 1) {
-                if (sfp33) epilogue_fast<BLOCK_N, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
-                else epilogue_fast<BLOCK_N, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
-            } else if (mode == 2) {
-                if (sfp33) epilogue_fast<BLOCK_N, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
-                else epilogue_fast<BLOCK_N, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+            if (kGroups == 2) {
+                if (mode == 1) {
+                    if (sfp33) epilogue_fast<BLOCK_N, 2, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    else epilogue_fast<BLOCK_N, 2, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                } else if (mode == 2) {
+                    if (sfp33) epilogue_fast<BLOCK_N, 2, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    else epilogue_fast<BLOCK_N, 2, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                } else {
+                    epilogue_slab<BLOCK_N, 2>(p, tile, tacc, quad, half, lane);
+                }
             } else {
-                epilogue_slab<BLOCK_N>(p, tile, tacc, quad, half, lane);
+                if (mode == 1) {
+                    if (sfp33) epilogue_fast16<BLOCK_N, 4, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    else epilogue_fast16<BLOCK_N, 4, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                } else if (mode == 2) {
+                    if (sfp33) epilogue_fast16<BLOCK_N, 4, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    else epilogue_fast16<BLOCK_N, 4, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                } else {
+                    epilogue_slab<BLOCK_N, 4>(p, tile, tacc, quad, half, lane);
+                }
             }
             tile_end(ti);
         }
@@ -673,10 +820,10 @@ static PFN driver_fn(const char* name) {
     return nullptr;
 }
 
-template <int BLOCK_N, int GRAN>
+template <int BLOCK_N, int GRAN, int DW>
 static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const Params& p, cudaStream_t st) {
     using C = Cfg<BLOCK_N>;
-    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN>;
+    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -779,10 +926,18 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeIm2col failed (%d)", (int)cr);
     }
-#define SLFP_V2_CASE(BN)                                              \
-    if (bn == BN) {                                                   \
-        if (p.cblocks) return launch<BN, 64>(tmap_x, tmap_w, p, st);  \
-        return launch<BN, 16>(tmap_x, tmap_w, p, st);                 \
+    // role split: the epilogue-heavy split (16 epilogue warps) when the per-tile epilogue work (elements x
+    // instructions per element of the chosen epilogue) exceeds the per-tile decode work (codes x 3.5)
+    static const char* force = getenv("SLFP_CONV_ROLES");          // "dec" / "epi": tuning override
+    const double dec_work = (double)p.num_kb * kBM * kBK * 3.5;
+    const double epi_work = (double)kBM * bn * (p.epi_mode == 1 ? 6.5 : (p.epi_mode == 2 ? 13.0 : 0.0));
+    bool epi_heavy = p.epi_mode != 0 && epi_work > dec_work;
+    if (force && force[0] == 'd') epi_heavy = false;
+    if (force && force[0] == 'e' && p.epi_mode != 0) epi_heavy = true;
+#define SLFP_V2_CASE(BN)                                                                                         \
+    if (bn == BN) {                                                                                              \
+        if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, p, st); \
+        return epi_heavy ? launch<BN, 16, 8>(tmap_x, tmap_w, p, st) : launch<BN, 16, 16>(tmap_x, tmap_w, p, st);  \
     }
     SLFP_V2_CASE(64)
     SLFP_V2_CASE(128)

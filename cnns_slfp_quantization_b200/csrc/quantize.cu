@@ -115,11 +115,25 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
                 for (int i = 0; i < 4; ++i) quant_elem<FMT>(xs[i], a.k_div, zz, s_tab, c[i], q[i]);
             } else {
                 constexpr int F = FMT == SLFP_FMT_SFP44_OUT ? SLFP_FMT_SFP33 : FMT;
+                // common path: reciprocal division (exact inside the normal range) + the in-range encoder.  One
+                // group test sends the rare 4-element group to the general path: a NaN, or a dividend so small that
+                // only the true division classifies "zero" vs "tiny" correctly.
+                float qv[4];
+                uint32_t amax = 0u, xmin = 0xffffffffu;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) c[i] = quant_code_fast<F>(xs[i], a.k_div);
-                if (needs_exact(xs[0]) | needs_exact(xs[1]) | needs_exact(xs[2]) | needs_exact(xs[3])) {
+                for (int i = 0; i < 4; ++i) {
+                    qv[i] = div_k_fused(xs[i], a.k_div);
+                    const uint32_t aq = __float_as_uint(qv[i]) & 0x7fffffffu;
+                    amax = aq > amax ? aq : amax;
+                    const uint32_t ax1 = (__float_as_uint(xs[i]) & 0x7fffffffu) - 1u;      // +-0 -> 0xffffffff
+                    xmin = ax1 < xmin ? ax1 : xmin;
+                }
+                if (amax > kBitsInf || xmin < 0x04000000u - 1u) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) c[i] = encode<F>(div_k(xs[i], a.k_div));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c[i] = encode_inrange<F>(qv[i]);
                 }
                 if (FAKEQ || F16) {
 #pragma unroll

@@ -208,6 +208,51 @@ __host__ __device__ __forceinline__ uint32_t encode_relu(float q) {
     return u;
 }
 
+// encode<FMT>() for every v that is not NaN: ~19 instructions instead of ~30 (the stand-alone quantizer is
+// HBM-bound only if the encoder stays under ~22 instructions per element).  The caller checks max |v| of a
+// 4-element group and takes encode<>() for the rare group that contains a NaN.  Bit-exact with encode<FMT>() on
+// that domain: swept for every mantissa by
+// tests/test_host_compiled_kernels.py::test_fast_encoder_equals_reference_encoder.
+template <int FMT>
+__host__ __device__ __forceinline__ uint32_t encode_inrange(float v) {
+    const uint32_t b = f2u(v);
+    const uint32_t a = b & 0x7fffffffu;
+    const uint32_t sg = (b >> 24) & 0x80u;
+    uint32_t u;
+    if (FMT == SLFP_FMT_SFP33) {
+        const uint32_t r = a + 0x7ffffu + ((a >> 20) & 1u);          // round-half-even of 8 m, carry into the exponent
+        u = (r >> 20) - ((127u - 4u) << 3);
+        u = (int32_t)u < 8 ? 8u : u;                                 // [0.0625, 0.125) -> 0.125 (smaller handled below)
+        u = u > 63u ? 63u : u;                                       // a >= 15 -> 15
+    } else if (FMT == SLFP_FMT_SLFP34_ACT) {
+        const uint32_t r = a + 0x3ffffu + ((a >> 19) & 1u);          // round-half-even of 16 m
+        const uint32_t t = r >> 19;                                  // (exponent << 4) | i, i = 16 carried
+        // log converter 0,1,3,4,...,15,15,16: +1 for 2 <= i <= 14; bit (t & 31) of the mask (exponent parity x i)
+#ifdef __CUDA_ARCH__
+        const uint32_t corr = (__funnelshift_r(0x7ffc7ffcu, 0u, t) ) & 1u;
+#else
+        const uint32_t corr = (0x7ffc7ffcu >> (t & 31u)) & 1u;
+#endif
+        u = t + corr - ((127u - 4u) << 4);
+        u = (int32_t)u < 16 ? 16u : u;
+        u = (a > kBitsSat8) ? kCodeSat : u;                          // a > 15.32165 (and Inf) -> the literal
+    } else {
+        // weights: number of thresholds <= mantissa, found from the top 5 mantissa bits (each 1/32 bucket holds at
+        // most one of the 16 thresholds): (thresholds below the bucket, the threshold inside it or ~0)
+        constexpr uint32_t kThresh[16] = SLFP_WGT_THRESH_TABLE;
+        const uint32_t mb = (a & 0x007fffffu) | 0x3f800000u;
+        uint32_t L = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) L += (mb >= kThresh[j]) ? 1u : 0u;
+        u = (((a >> 23) - (127u - 4u)) << 4) + L;
+        u = (int32_t)u < 16 ? 16u : u;
+        u = (a > kBitsSat8) ? kCodeSat : u;
+    }
+    const uint32_t z = a < 1u ? a : 1u;                              // 0 for +-0, else 1
+    const uint32_t low = z * sg + z;                                 // +-0 -> 0 (sign dropped), tiny -> 1 | sign
+    return (a < kBits0625) ? low : (u | sg);
+}
+
 __host__ __device__ __forceinline__ uint32_t encode_rt(float v, int fmt) {
     if (fmt == SLFP_FMT_SFP33) return encode<SLFP_FMT_SFP33>(v);
     if (fmt == SLFP_FMT_SLFP34_ACT) return encode<SLFP_FMT_SLFP34_ACT>(v);

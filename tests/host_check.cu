@@ -75,3 +75,18 @@ extern "C" void hostcheck_relu_codes(const float* q, size_t n, int sfp33, uint8_
         codes16[i] = (uint8_t)(t < 0 ? 0 : (t > 255 ? 255 : t));
     }
 }
+
+// encode_inrange<FMT>(v) against encode<FMT>(v) for |v| <= limit; returns the mismatch count
+extern "C" size_t hostcheck_encode_inrange_mismatches(const float* v, size_t n, int fmt) {
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t a, b;
+        switch (fmt) {
+            case SLFP_FMT_SFP33: a = encode_inrange<SLFP_FMT_SFP33>(v[i]); b = encode<SLFP_FMT_SFP33>(v[i]); break;
+            case SLFP_FMT_SLFP34_ACT: a = encode_inrange<SLFP_FMT_SLFP34_ACT>(v[i]); b = encode<SLFP_FMT_SLFP34_ACT>(v[i]); break;
+            default: a = encode_inrange<SLFP_FMT_SLFP34_WGT>(v[i]); b = encode<SLFP_FMT_SLFP34_WGT>(v[i]); break;
+        }
+        bad += a != b;
+    }
+    return bad;
+}

@@ -98,3 +98,21 @@ def test_post_relu_codes_match_the_reference_quantizer(hostcheck, orc, sfp33):
     # all 256 codes decode monotonically (max-pooling on codes commutes with decoding)
     allv = orc.decode_relu(np.arange(256, dtype=np.uint8), bool(sfp33))
     assert (np.diff(allv) >= 0).all()
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_fast_encoder_equals_reference_encoder(hostcheck, fmt):
+    """encode_inrange<FMT> (the stand-alone quantizer's common path) == encode<FMT> for every float32 mantissa, both
+    signs, exponents from denormals to beyond the saturation thresholds, and Inf (only NaN takes the general path)."""
+    hostcheck.hostcheck_encode_inrange_mismatches.restype = ctypes.c_size_t
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    exps = [0, 1, 60, 100, 118, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130]
+    for e in exps:
+        x = (mant | np.uint32(e << 23)).view(np.float32)
+        for sgn in (1.0, -1.0):
+            v = np.ascontiguousarray(x * np.float32(sgn))
+            bad = hostcheck.hostcheck_encode_inrange_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size),
+                                                                ctypes.c_int(fmt))
+            assert bad == 0, (fmt, e, sgn, bad)
+    v = np.array([15.0, 15.32165, 15.5, 1e30, np.inf, -np.inf, 3e38, 0.0, -0.0, 1e-45, -1e-45], np.float32)   # everything but NaN
+    assert hostcheck.hostcheck_encode_inrange_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), fmt) == 0

@@ -39,7 +39,8 @@ def timeit(fn, iters=20, warm=3, flush=None):
     return ts[len(ts) // 2], ts[0]
 
 
-def bench_quant():
+def bench_quant(kdiv=1.0):
+    """x = 4 randn(n) with K = 1 (about 1 % flushed, 0.01 % clamped, every octave hit)."""
     lib = nv.lib()
     for n in (1 << 24, 205520896):
         x = torch.randn(n, device="cuda") * 4
@@ -48,7 +49,7 @@ def bench_quant():
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if n < (1 << 26) else None
         for label, c, f, bpe in (("codes", codes, None, 5), ("fakeq", None, fq, 8)):
             for fmt, fname in ((1, "slfp34_act"), (0, "sfp33"), (2, "slfp34_wgt")):
-                fn = lambda: nv.check(lib.slfp_quantize_f32(x.data_ptr(), n, 0.7, fmt, 0, nv.ptr(c), nv.ptr(f), None, nv.stream()))
+                fn = lambda: nv.check(lib.slfp_quantize_f32(x.data_ptr(), n, kdiv, fmt, 0, nv.ptr(c), nv.ptr(f), None, nv.stream()))
                 med, best = timeit(fn, flush=flush)
                 gbs = n * bpe / med / 1e6
                 print(json.dumps({"kernel": "quantize", "fmt": fname, "mode": label, "n": n, "ms": round(med, 4),
