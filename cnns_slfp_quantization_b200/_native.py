@@ -52,6 +52,7 @@ _SIGS = {
     "slfp_sgd_step": (c_i, [c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_vp]),
     "slfp_maxpool_codes": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_vp, c_vp]),
     "slfp_avgpool_nhwc": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_vp, c_vp]),
+    "slfp_debug_set_buffer": (c_i, [c_vp]),
     "slfp_quantize_host_f32": (c_i, [c_vp, c_sz, c_f, c_i, c_vp, c_vp]),
 }
 

@@ -40,7 +40,7 @@ constexpr int kWarpCode = 0, kWarpWgt = 1, kWarpMma = 2;
 // 28 warps: 4 control (2 producers, MMA issuer, spare) + DW decode + (24 - DW) epilogue.  Two role splits, chosen
 // per layer on the host: DW = 16 for decode-heavy layers (3x3, large K), DW = 8 for epilogue-heavy ones (the 1x1
 // block tails: residual + float16 + codes).  Launched with 72 registers per thread, re-balanced with setmaxnreg:
-//   DW 16:  4 x 40 + 16 x 48 +  8 x 136   (x 32 lanes) = 64 512 registers
+//   DW 16:  4 x 40 + 16 x 56 +  8 x 120   (x 32 lanes) = 64 512 registers
 //   DW  8:  4 x 40 +  8 x 56 + 16 x  88                = 64 512
 constexpr int kCtrlWarps = 4, kDecWarp0 = 4, kWorkWarps = 24;
 constexpr int kThreads = (kCtrlWarps + kWorkWarps) * 32;   // 896
@@ -48,7 +48,7 @@ constexpr int kRegsCtrl = 40;
 template <int DW> struct Roles {
     static constexpr int kDecWarps = DW, kEpiWarps = kWorkWarps - DW, kEpiWarp0 = kDecWarp0 + DW;
     static constexpr int kGroups = kEpiWarps / 4;                      // column groups per TMEM lane quadrant
-    static constexpr int kRegsDec = DW == 16 ? 48 : 56, kRegsEpi = DW == 16 ? 136 : 88;
+    static constexpr int kRegsDec = 56, kRegsEpi = DW == 16 ? 120 : 88;
     static constexpr int kChunksPerThread = 512 / (32 * DW);           // 16-byte code chunks per decode thread per K block
 };
 
@@ -71,11 +71,17 @@ struct Params {
 
 template <int BLOCK_N>
 struct Cfg {
+    // BLOCK_N <= 128: the decoded A tile goes to TENSOR memory (tcgen05.st; the MMA reads A from TMEM), which takes
+    // the A tile's write (16 KB) and the MMA's read of it (16 KB) per K block off the shared-memory pipe - the
+    // measured bottleneck of the decode-heavy layers (profiles/r01_conv_v2.md).  BLOCK_N = 256 needs all 512 TMEM
+    // columns for the double-buffered accumulator and keeps the A tile in shared memory.
+    static constexpr bool kATmem = BLOCK_N <= 128;
     static constexpr int kBBytes = BLOCK_N * kBK * 2;
     static constexpr int kStages = (BLOCK_N >= 256) ? 3 : 4;
-    static constexpr int kTmemCols = 2 * BLOCK_N;
+    static constexpr int kATmemCol = 2 * BLOCK_N;           // first TMEM column of the A ring (32 columns per stage)
+    static constexpr int kTmemCols = kATmem ? (2 * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
     static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
-    static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 512;
+    static constexpr int kSmemBytes = kStages * ((kATmem ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 512;
 };
 
 // ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
@@ -533,12 +539,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     using C = Cfg<BLOCK_N>;
     using R = Roles<DW>;
     constexpr int kDecWarps = R::kDecWarps, kEpiWarps = R::kEpiWarps, kEpiWarp0 = R::kEpiWarp0, kGroups = R::kGroups;
+    constexpr int kDecGroupWarps = (kDecWarps / 4 <= C::kStages) ? 4 : 8;     // warps that decode one K block together
     // SW128 operand tiles need 1024-byte alignment.  The kernel has no static shared memory, so the dynamic
     // window starts at a link-time constant that honours __align__ (checked below): every shared address in
     // this kernel is then a compile-time offset and the table look-up needs no base-address add.
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* s_a = smem;                                   // [stages][128 rows][128 B]
-    uint8_t* s_b = s_a + C::kStages * kABytes;             // [stages][BLOCK_N rows][128 B]
+    uint8_t* s_a = smem;                                   // [stages][128 rows][128 B]   (absent when A lives in TMEM)
+    uint8_t* s_b = s_a + (C::kATmem ? 0 : C::kStages * kABytes);   // [stages][BLOCK_N rows][128 B]
     uint8_t* s_code = s_b + C::kStages * C::kBBytes;       // [kCodeStages][128 pixels][64 B]
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_code + kCodeStages * kCodeBytes);
     float* s_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_lut) + kLutBytes);   // [2][BLOCK_N]
@@ -564,10 +571,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         ptx::prefetch_tmap(&tmap_w);
         for (int s = 0; s < kCodeStages; ++s) {
             ptx::mbar_init(ptx::smem_u32(&bar_cfull[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&bar_cempty[s]), kDecWarps);
+            ptx::mbar_init(ptx::smem_u32(&bar_cempty[s]), kDecGroupWarps);   // the warps of one decode group
         }
         for (int s = 0; s < C::kStages; ++s) {
-            ptx::mbar_init(ptx::smem_u32(&bar_full[s]), kDecWarps + 1);
+            ptx::mbar_init(ptx::smem_u32(&bar_full[s]), kDecGroupWarps + 1);  // decode group + the weight TMA's arrive
             ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -602,7 +609,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int w0 = wo * p.sw - p.pw, h0 = ho * p.sh - p.ph;
                 int tap = 0, r = 0, s = 0, cb = 0;       // GRAN 64: cb = 64-channel block; GRAN 16: 16-channel block
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 32);
+                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 32, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
                     const uint32_t full = ptx::smem_u32(&bar_cfull[cs]);
                     const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
                     if (GRAN == 64) {
@@ -632,7 +639,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const int n0 = (tile % p.n_tiles) * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 32);
+                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 32, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
                     const uint32_t full = ptx::smem_u32(&bar_full[stage]);
                     ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
                     ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
@@ -648,18 +655,22 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             uint32_t stage = 0, phase = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const uint32_t buf = (uint32_t)ti & 1u;
-                ptx::mbar_wait(ptx::smem_u32(&bar_tempty[buf]), (((uint32_t)ti >> 1) & 1u) ^ 1u);
+                ptx::mbar_wait(ptx::smem_u32(&bar_tempty[buf]), (((uint32_t)ti >> 1) & 1u) ^ 1u, 3u | ((uint32_t)ti << 16));
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait(ptx::smem_u32(&bar_full[stage]), phase);
+                    ptx::mbar_wait(ptx::smem_u32(&bar_full[stage]), phase, 4u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
                     ptx::tc_fence_after();
                     const uint32_t a_addr = ptx::smem_u32(s_a + stage * kABytes);
                     const uint32_t b_addr = ptx::smem_u32(s_b + stage * C::kBBytes);
+                    const uint32_t a_tmem = tmem_base + (uint32_t)C::kATmemCol + stage * 32u;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                        ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32),
-                                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (C::kATmem)
+                            ptx::mma_f16_ts(d_tmem, a_tmem + k * 8, ptx::smem_desc_sw128(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        else
+                            ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32),
+                                            idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     ptx::mma_commit(ptx::smem_u32(&bar_empty[stage]));     // frees the smem stage
                     if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
@@ -672,67 +683,86 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     } else if (warp < kDecWarp0 + kDecWarps) {
         ptx::setmaxnreg_dec<R::kRegsDec>();
         // =========================== decode: codes -> float16 A tile ==========================================
-        constexpr int kCPT = R::kChunksPerThread;              // 1 (16 decode warps) or 2 (8 decode warps)
-        constexpr int kDecThreads = kDecWarps * 32;
-        const int dtid = tid - kDecWarp0 * 32;                 // chunk ids dtid + j * kDecThreads
+        // Decode warps work in GROUPS of four (one warp per TMEM lane quadrant = 32 pixel rows each); group g owns
+        // the K blocks g, g + G, g + 2G, ... (G = groups), so G K blocks are in flight at once and a warp's
+        // wait -> load -> look-up -> store latency chain is paid once per G K blocks instead of on every one.
+        // thread = pixel row 32*(warp%4)+lane, all four 16-channel quarters of the K block.  The 64-byte code rows
+        // are read through the TMA's 64B swizzle (chunk ^= (row >> 1) & 3): 8 consecutive rows hit 8 bank groups.
+        // A waiter must never be two phases ahead of its mbarrier (a parity wait cannot tell phase n from n + 2):
+        // the group of K block j waits on empty[j % S] for MMA(j - S) and is only guaranteed MMA(j - G - S), so the
+        // number of groups G may not exceed the number of A stages S; with 3 stages the groups are 8 warps wide
+        // (two warps per quadrant, two quarters each).
+        constexpr int kWarpsPerGroup = (kDecWarps / 4 <= C::kStages) ? 4 : 8;
+        constexpr int kDecGroups = kDecWarps / kWarpsPerGroup;
+        constexpr int kQPW = 16 / kWarpsPerGroup;              // 16-channel quarters per warp: 4 or 2
+        static_assert(kDecGroups <= C::kStages && kDecGroups <= kCodeStages, "groups may not outrun the barrier phases");
+        const int grp = (warp - kDecWarp0) / kWarpsPerGroup;
+        const int q0 = (((warp - kDecWarp0) % kWarpsPerGroup) >> 2) * kQPW;   // first quarter of this warp
+        const int row = (warp & 3) * 32 + lane;
         const uint32_t lut_base = ptx::smem_u32(s_lut);        // 128-byte aligned: (code << 7) | lane*4 never carries
         const uint32_t lane4 = (uint32_t)lane * 4u;
-        const uint32_t code_base = ptx::smem_u32(s_code) + (uint32_t)dtid * 16u;
-        uint32_t a_off[kCPT][2];                               // [chunk][16-byte half] byte offset inside the A stage
-        int quarter[kCPT];
+        uint32_t c_off[kQPW], a_off[kQPW][2];
 #pragma unroll
-        for (int j = 0; j < kCPT; ++j) {
-            const int id = dtid + kDecThreads * j;
-            const int row = GRAN == 64 ? (id >> 2) : (id & 127);
-            const int q = GRAN == 64 ? (id & 3) : (id >> 7);
-            quarter[j] = q;
+        for (int qi = 0; qi < kQPW; ++qi) {
+            const int q = q0 + qi;
+            c_off[qi] = GRAN == 64 ? (uint32_t)(row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) : (uint32_t)(q * 2048 + row * 16);
             const uint32_t base = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-            a_off[j][0] = base + (uint32_t)(((q * 2) ^ (row & 7)) << 4);
-            a_off[j][1] = base + (uint32_t)(((q * 2 + 1) ^ (row & 7)) << 4);
+            a_off[qi][0] = base + (uint32_t)(((q * 2) ^ (row & 7)) << 4);
+            a_off[qi][1] = base + (uint32_t)(((q * 2 + 1) ^ (row & 7)) << 4);
         }
         const uint32_t a_base = ptx::smem_u32(s_a);
+        const uint32_t code_s = ptx::smem_u32(s_code);
+        const uint32_t a_tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)C::kATmemCol;
         const int k16_total = p.taps * p.c16s;
-        uint32_t cs = 0, cphase = 0, stage = 0, phase = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                ptx::mbar_wait(ptx::smem_u32(&bar_cfull[cs]), cphase);
-                uint32_t h[kCPT][8];
+        const int total_kb = my_tiles * p.num_kb;
+        int kb = grp % p.num_kb;                                // K block index inside its tile (for the K-padding test)
+        for (int it = grp; it < total_kb; it += kDecGroups) {
+            const uint32_t cs = (uint32_t)it % (uint32_t)kCodeStages, cphase = ((uint32_t)it / (uint32_t)kCodeStages) & 1u;
+            const uint32_t stage = (uint32_t)it % (uint32_t)C::kStages, phase = ((uint32_t)it / (uint32_t)C::kStages) & 1u;
+            ptx::mbar_wait(ptx::smem_u32(&bar_cfull[cs]), cphase, 5u | ((uint32_t)it << 8));
+            ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 6u | ((uint32_t)it << 8));   // MMA done with this A stage
+            if (C::kATmem) ptx::tc_fence_after();
+            const uint32_t a_dst = a_base + stage * kABytes;
 #pragma unroll
-                for (int j = 0; j < kCPT; ++j) {
-                    // 16-channel pieces beyond the last filter tap (K padding) are not loaded: zeros
-                    const bool valid = GRAN == 64 || (kb * 4 + quarter[j] < k16_total);
-                    uint4 cw = make_uint4(0u, 0u, 0u, 0u);
-                    if (valid) cw = ptx::lds128_volatile(code_base + cs * kCodeBytes + (uint32_t)(j * kDecThreads * 16));
-                    const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+            for (int qi = 0; qi < kQPW; ++qi) {
+                const int q = q0 + qi;
+                // 16-channel pieces beyond the last filter tap (K padding) are not loaded: zeros
+                const bool valid = GRAN == 64 || (kb * 4 + q < k16_total);
+                uint4 cw = make_uint4(0u, 0u, 0u, 0u);
+                if (valid) cw = ptx::lds128_volatile(code_s + cs * kCodeBytes + c_off[qi]);
+                const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+                uint32_t h[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t c = w[i];
-                        // per code: shift, one LOP3 ((x & 0x7f80) | lane*4), one LDS [reg + constant table base]
-                        const uint32_t e0 = ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base);
-                        const uint32_t e1 = ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base);
-                        const uint32_t e2 = ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base);
-                        const uint32_t e3 = ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base);
-                        h[j][2 * i] = __byte_perm(e0, e1, 0x5410);
-                        h[j][2 * i + 1] = __byte_perm(e2, e3, 0x5410);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t c = w[i];
+                    // per code: shift, one LOP3 ((x & 0x7f80) | lane*4), one LDS [reg + constant table base]
+                    const uint32_t e0 = ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base);
+                    const uint32_t e1 = ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base);
+                    const uint32_t e2 = ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base);
+                    const uint32_t e3 = ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base);
+                    h[2 * i] = __byte_perm(e0, e1, 0x5410);
+                    h[2 * i + 1] = __byte_perm(e2, e3, 0x5410);
                 }
-                // the codes are in registers (the table look-ups consumed them): release the code stage
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_cempty[cs]));
-                if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
-
-                ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u);   // MMA done with this stage
-                const uint32_t a_dst = a_base + stage * kABytes;
-#pragma unroll
-                for (int j = 0; j < kCPT; ++j) {
-                    ptx::sts128(a_dst + a_off[j][0], h[j][0], h[j][1], h[j][2], h[j][3]);
-                    ptx::sts128(a_dst + a_off[j][1], h[j][4], h[j][5], h[j][6], h[j][7]);
+                if (C::kATmem) {
+                    ptx::tmem_st8(a_tmem_lane + stage * 32u + (uint32_t)q * 8u, h);
+                } else {
+                    ptx::sts128(a_dst + a_off[qi][0], h[0], h[1], h[2], h[3]);
+                    ptx::sts128(a_dst + a_off[qi][1], h[4], h[5], h[6], h[7]);
                 }
-                ptx::fence_proxy_async_smem();               // generic-proxy writes -> async proxy (UMMA)
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_full[stage]));
-                if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
             }
+            if (C::kATmem) {
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+            } else {
+                ptx::fence_proxy_async_smem();               // generic-proxy writes -> async proxy (UMMA)
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ptx::mbar_arrive(ptx::smem_u32(&bar_cempty[cs]));   // the codes were consumed by the look-ups above
+                ptx::mbar_arrive(ptx::smem_u32(&bar_full[stage]));
+            }
+            kb += kDecGroups;
+            while (kb >= p.num_kb) kb -= p.num_kb;
         }
     } else {
         ptx::setmaxnreg_inc<R::kRegsEpi>();
@@ -762,7 +792,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     staged_n0 = n_tile0;
                 }
             }
-            ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u, 64);
+            ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u, 64, 7u | ((uint32_t)ti << 16));
             ptx::tc_fence_after();
             return tmem_base + buf * BLOCK_N;
         };
@@ -836,6 +866,18 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const Params& p,
 }
 
 }  // namespace v2
+
+}  // namespace slfp
+
+// Debug aid: install a host-mapped buffer (>= 2 x 8 bytes) that a timed-out barrier wait of the dense conv kernel
+// records (tag << 32 | block << 8 | warp) into before it traps.  NULL removes it.
+extern "C" int slfp_debug_set_buffer(void* host_mapped_device_ptr) {
+    unsigned long long* p = (unsigned long long*)host_mapped_device_ptr;
+    cudaError_t e = cudaMemcpyToSymbol(slfp::ptx::g_slfp_dbg, &p, sizeof(p));
+    return e == cudaSuccess ? 0 : slfp::set_error((int)e, "slfp_debug_set_buffer: %s", cudaGetErrorString(e));
+}
+
+namespace slfp {
 
 bool conv2d_fwd_dense_v2_supported(const SlfpConvDesc* d) {
     static const bool disabled = getenv("SLFP_CONV_V1") != nullptr;
@@ -923,7 +965,10 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
         const cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
         CUresult cr = enc_im2col(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x_codes), gdim, gstr, lower, upper,
                                  (cuuint32_t)(p.cblocks ? 64 : 16), (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                 // a decode thread owns a pixel row: 64-byte rows are swizzled so that the 16-byte chunks
+                                 // of 8 consecutive rows fall into 8 different bank groups
+                                 p.cblocks ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeIm2col failed (%d)", (int)cr);
     }
     // role split: the epilogue-heavy split (16 epilogue warps) when the per-tile epilogue work (elements x

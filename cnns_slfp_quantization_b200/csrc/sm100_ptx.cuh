@@ -44,21 +44,32 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
+// Optional post-mortem record for a timed-out wait: slfp_debug_set_buffer() installs a host-mapped word
+// array; the trapping thread writes (tag, block, warp) there before it traps.
+static __device__ unsigned long long* g_slfp_dbg = nullptr;     // one copy per translation unit
+static __device__ __noinline__ void mbar_timeout(uint32_t tag) {
+    if (g_slfp_dbg != nullptr) {
+        g_slfp_dbg[1] = ((unsigned long long)tag << 32) | ((unsigned long long)blockIdx.x << 8) | (threadIdx.x >> 5);
+        atomicAdd(g_slfp_dbg, 1ull);
+        __threadfence_system();
+    }
+    __trap();
+}
 // Bounded wait: a pipeline bug must trap (-> a CUDA error the host reports), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if (++spins > (1u << 22)) mbar_timeout(tag);
     }
 }
 
 // Waiters that are not on the critical path (epilogue warps, the TMA lane) back off between probes so
 // their spinning does not eat the issue slots the decode warps need.
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns = 128) {
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns = 128, uint32_t tag = 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(ns);
-        if (++spins > (1u << 22)) __trap();
+        if (++spins > (1u << 22)) mbar_timeout(tag);
     }
 }
 
@@ -212,6 +223,22 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same with the A operand in tensor memory (row m of A = TMEM lane m; K elements packed two per 32-bit
+// column, K = 16 -> 8 columns)
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns: thread i of the warp writes lane (base_lane + i)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -225,6 +225,10 @@ int slfp_maxpool_codes(const uint8_t *x, int n, int h, int w, int c_phys, int fm
 /* global average pool NHWC float16/float32 -> [n, c] float32 */
 int slfp_avgpool_nhwc(const void *x, int is_f16, int n, int hw, int c, float *y, slfp_stream_t stream);
 
+/* Debug aid: a host-mapped buffer (>= 16 bytes) into which a timed-out barrier wait of the dense conv kernel
+ * records which wait it was before it traps (the kernels never hang: every wait is bounded).  NULL removes it. */
+int slfp_debug_set_buffer(void *host_mapped_device_ptr);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (the end-to-end path a non-torch caller binds): quantizes a HOST
  * float32 buffer into HOST codes through a device round trip on an internal stream and
