@@ -32,7 +32,6 @@ namespace v2 {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kCodeStages = 4;
 constexpr int kCodeBytes = kBM * kBK;                  // 8 KB of codes per K block
 constexpr int kABytes = kBM * kBK * 2;                 // 16 KB float16 A tile
 constexpr int kLutBytes = 256 * 32 * 4;                // code -> f16, one copy per bank
@@ -62,6 +61,7 @@ struct Params {
     int c16s;                   // c_phys / 16
     int m_tiles, n_tiles, num_tiles;
     int act_fmt;
+    int plain_1x1;              // 1x1 / stride 1 / no padding: the code tile is a plain 2-D tile of the [M, C] matrix
     SlfpEpilogue epi;
     DivK next_div, next_div2;   // exact quantize-on-store (signed code formats)
     float rk1, rk2;             // 1 / next_k_div{,2} for the post-ReLU formats
@@ -77,11 +77,15 @@ struct Cfg {
     // columns for the double-buffered accumulator and keeps the A tile in shared memory.
     static constexpr bool kATmem = BLOCK_N <= 128;
     static constexpr int kBBytes = BLOCK_N * kBK * 2;
-    static constexpr int kStages = (BLOCK_N >= 256) ? 3 : 4;
+    // Ring depths.  The code tiles and weight tiles arrive through TMA with ~1.5-2 us of latency under load; the
+    // first version's 4 x 8 KB of codes in flight per SM left the decode warps waiting on the code barrier most
+    // of the time (profiles/r01_conv_v2.md).  With A in TMEM the freed shared memory deepens both rings.
+    static constexpr int kStages = BLOCK_N >= 256 ? 3 : 4;          // weight (and A) stages
+    static constexpr int kCodeStages = BLOCK_N >= 256 ? 5 : 6;
     static constexpr int kATmemCol = 2 * BLOCK_N;           // first TMEM column of the A ring (32 columns per stage)
     static constexpr int kTmemCols = kATmem ? (2 * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
     static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
-    static constexpr int kSmemBytes = kStages * ((kATmem ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 512;
+    static constexpr int kSmemBytes = kStages * ((kATmem ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 1024;
 };
 
 // ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
@@ -538,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     using C = Cfg<BLOCK_N>;
     using R = Roles<DW>;
+    constexpr int kCodeStages = C::kCodeStages;
     constexpr int kDecWarps = R::kDecWarps, kEpiWarps = R::kEpiWarps, kEpiWarp0 = R::kEpiWarp0, kGroups = R::kGroups;
     constexpr int kDecGroupWarps = (kDecWarps / 4 <= C::kStages) ? 4 : 8;     // warps that decode one K block together
     // SW128 operand tiles need 1024-byte alignment.  The kernel has no static shared memory, so the dynamic
@@ -609,12 +614,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int w0 = wo * p.sw - p.pw, h0 = ho * p.sh - p.ph;
                 int tap = 0, r = 0, s = 0, cb = 0;       // GRAN 64: cb = 64-channel block; GRAN 16: 16-channel block
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 32, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
+                    ptx::mbar_wait(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
                     const uint32_t full = ptx::smem_u32(&bar_cfull[cs]);
                     const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
                     if (GRAN == 64) {
                         ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes);
-                        ptx::tma_load_im2col_4d(dst, &tmap_x, full, cb * 64, w0, h0, n, (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
+                        if (p.plain_1x1) ptx::tma_load_2d(dst, &tmap_x, full, cb * 64, (int)m0);
+                        else ptx::tma_load_im2col_4d(dst, &tmap_x, full, cb * 64, w0, h0, n, (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
                         if (++cb == p.cblocks) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
                     } else {
                         int valid = p.taps * p.c16s - kb * 4;          // 16-channel pieces left in K
@@ -639,7 +645,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const int n0 = (tile % p.n_tiles) * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait_backoff(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 32, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
+                    ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
                     const uint32_t full = ptx::smem_u32(&bar_full[stage]);
                     ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
                     ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
@@ -954,7 +960,19 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
     }
-    {
+    p.plain_1x1 = (d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0 &&
+                   d->pad_h_extra == 0 && d->pad_w_extra == 0 && p.cblocks && getenv("SLFP_NO_PLAIN_1X1") == nullptr) ? 1 : 0;
+    if (p.plain_1x1) {
+        // 1x1 / stride 1: A is the [M, C] code matrix itself - a tiled 2-D load (rows beyond M zero-filled)
+        const cuuint64_t gdim[2] = {(cuuint64_t)d->c_phys, (cuuint64_t)p.M};
+        const cuuint64_t gstr[1] = {(cuuint64_t)d->c_phys};
+        const cuuint32_t box[2] = {64u, (cuuint32_t)kBM};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc_tiled(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(x_codes), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled(codes) failed (%d)", (int)cr);
+    } else {
         // NHWC codes as a (C, W, H, N) tensor; the pixel bounding box is the set of filter-window origins:
         // lower corner = -pad, upper corner = pad - (filter - 1) * dilation (relative to the tensor's far edge),
         // traversed with the convolution stride; the filter tap (r, s) is the per-load offset.
