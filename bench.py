@@ -264,7 +264,9 @@ def main():
         plan.run()
         torch.cuda.synchronize()
         prof, nv.profile = nv.profile, None
-        conv = prof.get("slfp_conv2d_fwd", [])
+        # every convolution launch of the step in launch order (plain and fused block-tail entry points)
+        conv = sorted(prof.get("slfp_conv2d_fwd", []) + prof.get("slfp_conv2d_fwd_dual", []), key=lambda t: t[2])
+        assert len(conv) == len(plan.conv_flops)
         dense = [(a.elapsed_time(b), fl) for (a, b, _), (fl, is_dense, _) in zip(conv, plan.conv_flops) if is_dense]
         conv_ms = sum(d[0] for d in dense)
         conv_fl = sum(d[1] for d in dense)
@@ -276,7 +278,7 @@ def main():
                     f.write(f"{desc:32s} {ms_ * 1e3:9.1f} us {fl / ms_ / 1e9:8.1f} TFLOP/s\n")
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
-        roof = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all dense conv launches of one step)",
+        roof = {"kernel": "conv_igemm_v2_kernel (warp-specialised tcgen05 implicit GEMM; all dense conv launches of one step)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
                 "traffic": None, "launches": len(dense), "avg_launch_ms": conv_ms / max(len(dense), 1),

@@ -31,6 +31,11 @@ class SlfpEpilogue(ctypes.Structure):
                 ("y_codes2", c_vp), ("next_k_div2", c_f), ("ch_mul", c_vp), ("ch_add", c_vp)]
 
 
+class SlfpWeightJob(ctypes.Structure):
+    _fields_ = [("desc", ctypes.POINTER(SlfpConvDesc)), ("w", c_vp), ("w_stride", c_ll * 4), ("kw", c_f), ("w_f16", c_vp),
+                ("w_codes", c_vp), ("out_pitch", c_sz), ("out_offset", c_sz), ("row_scale", c_vp)]
+
+
 _SIGS = {
     "slfp_version": (c_i, []),
     "slfp_last_error": (ctypes.c_char_p, []),
@@ -43,7 +48,9 @@ _SIGS = {
     "slfp_conv_wpitch": (c_sz, [ctypes.POINTER(SlfpConvDesc)]),
     "slfp_prepare_weights": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_ll, c_ll, c_ll, c_ll, c_f, c_i, c_vp, c_vp,
                                    c_vp, c_vp]),
-    "slfp_prepare_weights_batch": (c_i, [c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
+    "slfp_prepare_weights_jobs": (c_i, [c_i, c_vp, c_i, c_vp]),
+    "slfp_conv2d_fwd_dual": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, ctypes.POINTER(SlfpConvDesc), c_vp, c_vp,
+                                   ctypes.POINTER(SlfpEpilogue), c_vp]),
     "slfp_conv2d_fwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, ctypes.POINTER(SlfpEpilogue), c_vp]),
     "slfp_conv2d_bwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, c_vp, c_i, c_f, c_f, c_vp, c_vp, c_ll, c_ll,
                               c_ll, c_ll, c_vp, c_vp]),
@@ -62,7 +69,7 @@ _lib = None
 # Every entry point that launches kernels on the caller's stream.  The proxy below counts those calls
 # (bench.py reports them as `gpu_launches`) and, when a profile dict is installed, brackets each call
 # with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
-_LAUNCHING = {"slfp_prepare_weights_batch", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
+_LAUNCHING = {"slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
               "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
               "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32"}
 launch_count = 0
@@ -88,7 +95,7 @@ class _Lib:
             a.record()
             rc = fn(*args)
             b.record()
-            profile.setdefault(name, []).append((a, b, profile_tag))
+            profile.setdefault(name, []).append((a, b, launch_count))      # launch_count orders events across entry points
             return rc
         return call
 

@@ -3,6 +3,9 @@
 
 namespace slfp {
 int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st);
+bool conv2d_fwd_dense_v2_supported(const SlfpConvDesc* d);
+int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, const SlfpConvDesc* d2, const uint8_t* x2_codes,
+                             const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st);
 int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_codes, const SlfpEpilogue* epi, cudaStream_t st);
 int conv2d_bwd_direct(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes, int wfmt,
                       float ka, float kw, float* dx, float* dwt, long long so, long long sc, long long sr, long long ss,
@@ -28,6 +31,18 @@ extern "C" int slfp_conv2d_fwd(const SlfpConvDesc* desc, const uint8_t* x_codes,
     if (!epi->y_f32 && !epi->y_f16 && !epi->y_codes) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_fwd: no output");
     if (desc->groups == 1) return conv2d_fwd_dense(desc, x_codes, w_prepared, epi, (cudaStream_t)stream);
     return conv2d_fwd_grouped(desc, x_codes, w_prepared, epi, (cudaStream_t)stream);
+}
+
+extern "C" int slfp_conv2d_fwd_dual(const SlfpConvDesc* desc1, const uint8_t* x1_codes, const SlfpConvDesc* desc2,
+                                    const uint8_t* x2_codes, const void* w_cat, const SlfpEpilogue* epi, slfp_stream_t stream) {
+    int rc = check_desc(desc1, "slfp_conv2d_fwd_dual");
+    if (!rc) rc = check_desc(desc2, "slfp_conv2d_fwd_dual");
+    if (rc) return rc;
+    if (!x1_codes || !x2_codes || !w_cat || !epi) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_fwd_dual: null pointer");
+    if (!epi->y_f32 && !epi->y_f16 && !epi->y_codes) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_fwd_dual: no output");
+    if (desc1->groups != 1 || !conv2d_fwd_dense_v2_supported(desc1))
+        return set_error(SLFP_ERR_UNSUPPORTED, "slfp_conv2d_fwd_dual: dense convolutions with c_phys %% 64 == 0 only");
+    return conv2d_fwd_dense_v2_impl(desc1, x1_codes, desc2, x2_codes, w_cat, epi, (cudaStream_t)stream);
 }
 
 extern "C" int slfp_conv2d_bwd(const SlfpConvDesc* desc, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes,

@@ -62,6 +62,8 @@ struct Params {
     int m_tiles, n_tiles, num_tiles;
     int act_fmt;
     int plain_1x1;              // 1x1 / stride 1 / no padding: the code tile is a plain 2-D tile of the [M, C] matrix
+    int nkb1;                   // K blocks taken from input 1 (== num_kb unless a second input is concatenated along K)
+    int sh2, sw2;               // second input (fused downsample branch): 1x1, stride (sh2, sw2), no padding, Cp % 64 == 0
     SlfpEpilogue epi;
     DivK next_div, next_div2;   // exact quantize-on-store (signed code formats)
     float rk1, rk2;             // 1 / next_k_div{,2} for the post-ReLU formats
@@ -539,7 +541,8 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
 
 template <int BLOCK_N, int GRAN, int DW>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ CUtensorMap tmap_x2, const Params p) {
     using C = Cfg<BLOCK_N>;
     using R = Roles<DW>;
     constexpr int kCodeStages = C::kCodeStages;
@@ -574,6 +577,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if (warp == kWarpCode && lane == 0) {
         ptx::prefetch_tmap(&tmap_x);
         ptx::prefetch_tmap(&tmap_w);
+        ptx::prefetch_tmap(&tmap_x2);
         for (int s = 0; s < kCodeStages; ++s) {
             ptx::mbar_init(ptx::smem_u32(&bar_cfull[s]), 1);
             ptx::mbar_init(ptx::smem_u32(&bar_cempty[s]), kDecGroupWarps);   // the warps of one decode group
@@ -619,7 +623,9 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
                     if (GRAN == 64) {
                         ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes);
-                        if (p.plain_1x1) ptx::tma_load_2d(dst, &tmap_x, full, cb * 64, (int)m0);
+                        if (kb >= p.nkb1)           // concatenated second input: 1x1 window at (ho*sh2, wo*sw2)
+                            ptx::tma_load_im2col_4d(dst, &tmap_x2, full, (kb - p.nkb1) * 64, wo * p.sw2, ho * p.sh2, n, 0, 0);
+                        else if (p.plain_1x1) ptx::tma_load_2d(dst, &tmap_x, full, cb * 64, (int)m0);
                         else ptx::tma_load_im2col_4d(dst, &tmap_x, full, cb * 64, w0, h0, n, (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
                         if (++cb == p.cblocks) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
                     } else {
@@ -857,7 +863,7 @@ static PFN driver_fn(const char* name) {
 }
 
 template <int BLOCK_N, int GRAN, int DW>
-static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const Params& p, cudaStream_t st) {
+static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const Params& p, cudaStream_t st) {
     using C = Cfg<BLOCK_N>;
     auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW>;
     static bool attr_done = false;
@@ -867,7 +873,7 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const Params& p,
         attr_done = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, p);
+    kern<<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, tx2, p);
     return check_launch("conv_igemm_v2_kernel");
 }
 
@@ -891,8 +897,16 @@ bool conv2d_fwd_dense_v2_supported(const SlfpConvDesc* d) {
            (d->r - 1) * d->dil_h < 256 && (d->s - 1) * d->dil_w < 256 && d->stride_h <= 8 && d->stride_w <= 8;
 }
 
+int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, const SlfpConvDesc* d2, const uint8_t* x2_codes,
+                             const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st);
+
 int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi,
                         cudaStream_t st) {
+    return conv2d_fwd_dense_v2_impl(d, x_codes, nullptr, nullptr, w_f16, epi, st);
+}
+
+int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, const SlfpConvDesc* d2, const uint8_t* x2_codes,
+                             const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st) {
     using namespace v2;
     const bool fast = epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU;
     if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_RELU && d->fmt != SLFP_FMT_SFP33_RELU)
@@ -919,7 +933,19 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
     p.HoWo = Ho * Wo; p.Wo = Wo;
     p.S = d->s; p.sh = d->stride_h; p.sw = d->stride_w; p.ph = d->pad_h; p.pw = d->pad_w; p.dh = d->dil_h; p.dw = d->dil_w;
     p.taps = d->r * d->s;
-    const size_t pitch = slfp_conv_wpitch(d);
+    size_t pitch = slfp_conv_wpitch(d);
+    p.nkb1 = (int)(pitch / kBK);
+    p.sh2 = p.sw2 = 1;
+    if (d2) {
+        // second input concatenated along K: 1x1, stride only, same batch / output size / output channels / code format
+        const int Ho2 = (d2->h - 1) / d2->stride_h + 1, Wo2 = (d2->w - 1) / d2->stride_w + 1;
+        if (!x2_codes || d2->r != 1 || d2->s != 1 || d2->pad_h || d2->pad_w || d2->pad_h_extra || d2->pad_w_extra || d2->groups != 1 ||
+            d2->c_phys % 64 != 0 || d->c_phys % 64 != 0 || d2->n != d->n || d2->k != d->k || Ho2 != Ho || Wo2 != Wo || d2->fmt != d->fmt ||
+            ((uintptr_t)x2_codes & 15u))
+            return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd_dual: the second input must be a 1x1 / no-padding conv with the same n, k, output size and code format");
+        pitch += slfp_conv_wpitch(d2);
+        p.sh2 = d2->stride_h; p.sw2 = d2->stride_w;
+    }
     p.num_kb = (int)(pitch / kBK);
     p.cblocks = (d->c_phys % 64 == 0) ? d->c_phys / 64 : 0;
     p.c16s = d->c_phys / 16;
@@ -946,6 +972,7 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
         if (common) p.epi_mode = (epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->residual) ? 1 : 2;
     }
 
+    CUtensorMap tmap_x2;
     static auto enc_tiled = driver_fn<PFN_cuTensorMapEncodeTiled_v12000>("cuTensorMapEncodeTiled");
     static auto enc_im2col = driver_fn<PFN_cuTensorMapEncodeIm2col_v12000>("cuTensorMapEncodeIm2col");
     if (!enc_tiled || !enc_im2col) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncode{Tiled,Im2col} not available");
@@ -997,10 +1024,21 @@ int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const voi
     bool epi_heavy = p.epi_mode != 0 && epi_work > dec_work;
     if (force && force[0] == 'd') epi_heavy = false;
     if (force && force[0] == 'e' && p.epi_mode != 0) epi_heavy = true;
+    tmap_x2 = tmap_x;
+    if (d2) {
+        const cuuint64_t gdim[4] = {(cuuint64_t)d2->c_phys, (cuuint64_t)d2->w, (cuuint64_t)d2->h, (cuuint64_t)d2->n};
+        const cuuint64_t gstr[3] = {(cuuint64_t)d2->c_phys, (cuuint64_t)d2->c_phys * d2->w, (cuuint64_t)d2->c_phys * d2->w * d2->h};
+        const int lower[2] = {0, 0}, upper[2] = {0, 0};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)d2->stride_w, (cuuint32_t)d2->stride_h, 1};
+        CUresult cr = enc_im2col(&tmap_x2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x2_codes), gdim, gstr, lower, upper, 64u,
+                                 (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd_dual: cuTensorMapEncodeIm2col failed (%d)", (int)cr);
+    }
 #define SLFP_V2_CASE(BN)                                                                                         \
     if (bn == BN) {                                                                                              \
-        if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, p, st); \
-        return epi_heavy ? launch<BN, 16, 8>(tmap_x, tmap_w, p, st) : launch<BN, 16, 16>(tmap_x, tmap_w, p, st);  \
+        if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, tmap_x2, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, tmap_x2, p, st); \
+        return epi_heavy ? launch<BN, 16, 8>(tmap_x, tmap_w, tmap_x2, p, st) : launch<BN, 16, 16>(tmap_x, tmap_w, tmap_x2, p, st);  \
     }
     SLFP_V2_CASE(64)
     SLFP_V2_CASE(128)

@@ -329,14 +329,20 @@ struct WPrepArgs {
     __half* w_f16;
     uint8_t* w_codes;
     float* w_fakeq;  // OIHW contiguous
+    // placement of the row inside a wider (concatenated-K) operand and an optional per-output-channel factor
+    // applied to the float16 operand only (fused block tails, see slfp_conv2d_fwd_dual)
+    size_t out_pitch, out_off;
+    const float* row_scale;
 };
 
 template <int FMT>
 __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, const uint32_t* s_tab) {
-    const int k = (int)(i / a.pitch);
-    const size_t j = i - (size_t)k * a.pitch;
-    const int c = (int)(j % a.Cp);
-    const int rs = (int)(j / a.Cp);
+    // a prepared tensor has < 2^32 elements (checked on the host): 32-bit index arithmetic
+    const uint32_t i32 = (uint32_t)i, pitch = (uint32_t)a.pitch;
+    const int k = (int)(i32 / pitch);
+    const uint32_t j = i32 - (uint32_t)k * pitch;
+    const int rs = (int)(j / (uint32_t)a.Cp);
+    const int c = (int)(j - (uint32_t)rs * (uint32_t)a.Cp);
     uint32_t code = 0;
     float fq = 0.0f;
     if (c < a.C && rs < a.R * a.S) {
@@ -351,8 +357,9 @@ __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, cons
         }
         if (a.w_fakeq) a.w_fakeq[(((size_t)k * a.C + c) * a.R + r) * a.S + s] = fq;
     }
-    if (a.w_f16) a.w_f16[i] = __float2half_rn(fq);
-    if (a.w_codes) a.w_codes[i] = (uint8_t)code;
+    const size_t o = (size_t)k * a.out_pitch + a.out_off + j;
+    if (a.w_f16) a.w_f16[o] = __float2half_rn(a.row_scale ? fq * __ldg(a.row_scale + k) : fq);
+    if (a.w_codes) a.w_codes[o] = (uint8_t)code;
 }
 
 template <int FMT>
@@ -534,19 +541,27 @@ extern "C" size_t slfp_conv_wpitch(const SlfpConvDesc* d) {
     return d->groups > 1 ? k : (k + 63) / 64 * 64;
 }
 
-extern "C" int slfp_prepare_weights(const SlfpConvDesc* d, const float* w, long long so, long long sc,
-                                    long long sr, long long ss, float kw, int wfmt, void* w_f16,
-                                    uint8_t* w_codes, float* w_fakeq, slfp_stream_t stream) {
+static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long long sc, long long sr, long long ss, float kw,
+                      void* w_f16, uint8_t* w_codes, float* w_fakeq, WPrepArgs& a) {
     if (!d || !w) return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights: null pointer");
-    WPrepArgs a;
     a.w = w; a.so = so; a.sc = sc; a.sr = sr; a.ss = ss;
     a.K = d->k; a.R = d->r; a.S = d->s;
     if (d->groups > 1) { a.C = d->c / d->groups; a.Cp = a.C; }
     else { a.C = d->c; a.Cp = d->c_phys; }
     a.pitch = slfp_conv_wpitch(d);
     a.kw = kw; a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
+    a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr;
+    return 0;
+}
+
+extern "C" int slfp_prepare_weights(const SlfpConvDesc* d, const float* w, long long so, long long sc,
+                                    long long sr, long long ss, float kw, int wfmt, void* w_f16,
+                                    uint8_t* w_codes, float* w_fakeq, slfp_stream_t stream) {
+    WPrepArgs a;
+    if (int rc0 = fill_wprep(d, w, so, sc, sr, ss, kw, w_f16, w_codes, w_fakeq, a)) return rc0;
     const size_t total = (size_t)a.K * a.pitch;
     if (total == 0) return 0;
+    if (total >= (1ull << 32)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^32 or more elements");
     int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(total, 256));
     cudaStream_t st = (cudaStream_t)stream;
     switch (wfmt) {
@@ -559,37 +574,30 @@ extern "C" int slfp_prepare_weights(const SlfpConvDesc* d, const float* w, long 
     return check_launch("wprep_kernel");
 }
 
-static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long long sc, long long sr, long long ss, float kw,
-                      void* w_f16, uint8_t* w_codes, float* w_fakeq, WPrepArgs& a) {
-    if (!d || !w) return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights: null pointer");
-    a.w = w; a.so = so; a.sc = sc; a.sr = sr; a.ss = ss;
-    a.K = d->k; a.R = d->r; a.S = d->s;
-    if (d->groups > 1) { a.C = d->c / d->groups; a.Cp = a.C; }
-    else { a.C = d->c; a.Cp = d->c_phys; }
-    a.pitch = slfp_conv_wpitch(d);
-    a.kw = kw; a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
-    return 0;
-}
-
-extern "C" int slfp_prepare_weights_batch(int n, const SlfpConvDesc* const* host_descs, const float* const* host_w,
-                                          const long long* host_strides, const float* host_kw, int wfmt,
-                                          void* const* host_w_f16, uint8_t* const* host_w_codes, slfp_stream_t stream) {
+extern "C" int slfp_prepare_weights_jobs(int n, const SlfpWeightJob* host_jobs, int wfmt, slfp_stream_t stream) {
     if (n <= 0) return 0;
-    if (!host_descs || !host_w || !host_strides || !host_kw)
-        return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_batch: null table");
+    if (!host_jobs) return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_jobs: null table");
     cudaStream_t st = (cudaStream_t)stream;
     for (int t0 = 0; t0 < n; t0 += kWBatchMax) {
         static thread_local WPrepBatch b;
         b.n = 0;
         unsigned blocks = 0;
         for (int t = t0; t < n && t < t0 + kWBatchMax; ++t) {
+            const SlfpWeightJob& jb = host_jobs[t];
             WPrepArgs& a = b.a[b.n];
-            int rc = fill_wprep(host_descs[t], host_w[t], host_strides[4 * t], host_strides[4 * t + 1], host_strides[4 * t + 2],
-                                host_strides[4 * t + 3], host_kw[t], host_w_f16 ? host_w_f16[t] : nullptr,
-                                host_w_codes ? host_w_codes[t] : nullptr, nullptr, a);
+            int rc = fill_wprep(jb.desc, jb.w, jb.w_stride[0], jb.w_stride[1], jb.w_stride[2], jb.w_stride[3], jb.kw, jb.w_f16,
+                                jb.w_codes, nullptr, a);
             if (rc) return rc;
+            if (jb.out_pitch) {
+                if (jb.out_pitch < jb.out_offset + a.pitch)
+                    return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_jobs: out_pitch %zu < out_offset %zu + row %zu", jb.out_pitch,
+                                     jb.out_offset, a.pitch);
+                a.out_pitch = jb.out_pitch; a.out_off = jb.out_offset;
+            }
+            a.row_scale = jb.row_scale;
             const size_t total = (size_t)a.K * a.pitch;
             if (total == 0) continue;
+            if (total >= (1ull << 32)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights_jobs: tensor with 2^32 or more elements");
             blocks += (unsigned)ceil_div_sz(total, kWBatchChunk);
             b.blk_end[b.n++] = blocks;
         }
@@ -599,7 +607,7 @@ extern "C" int slfp_prepare_weights_batch(int n, const SlfpConvDesc* const* host
             case SLFP_FMT_SLFP34_WGT: wprep_batch_kernel<SLFP_FMT_SLFP34_WGT><<<blocks, 256, 0, st>>>(b); break;
             case SLFP_FMT_SLFP34_ACT: wprep_batch_kernel<SLFP_FMT_SLFP34_ACT><<<blocks, 256, 0, st>>>(b); break;
             case -1: wprep_batch_kernel<-1><<<blocks, 256, 0, st>>>(b); break;
-            default: return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_batch: bad weight format %d", wfmt);
+            default: return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_jobs: bad weight format %d", wfmt);
         }
         int rc = check_launch("wprep_batch_kernel");
         if (rc) return rc;

@@ -82,6 +82,12 @@ class Plan:
         self.keep.append(buf)               # the pre-bound calls hold raw pointers: the plan owns the storage
         return _T(buf, n, h, w, c, cp, kind, kdiv, (fmt if fmt is not None else self.afmt) if kind == "codes" else None)
 
+    def _weight_job(self, d, wview, kw, wbuf, dense, out_pitch=0, out_offset=0, row_scale=None):
+        self.weight_table.append((d, wview.data_ptr(), tuple(wview.stride()), kw, wbuf.data_ptr() if dense else None,
+                                  None if dense else wbuf.data_ptr(), out_pitch, out_offset,
+                                  None if row_scale is None else row_scale.data_ptr()))
+        self._wbatch = None
+
     def _call(self, fn, *args):
         def op(st):
             nv.check(fn(*args, st))
@@ -172,32 +178,12 @@ class Plan:
         dense = groups == 1
         wbuf = torch.empty((K * pitch,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
         # weight re-quantization: one table entry; Plan.prepare_weights() runs the whole table in ONE launch
-        self.weight_table.append((d, wview.data_ptr(), tuple(wview.stride()), kw, wbuf.data_ptr() if dense else None,
-                                  None if dense else wbuf.data_ptr()))
-        self._wbatch = None
+        self._weight_job(d, wview, kw, wbuf, dense)
         epi = nv.SlfpEpilogue()
         # Fold bias, post-scale and eval BatchNorm into one per-channel affine y = acc * mul + add
         # (float64, rounded once): mul = Ka*Kw*bn_scale, add = bias_q*Ka*Kw*bn_scale + bn_shift.
         pa, pb = ((kw, ka) if linear else (ka, kw))
-        post = torch.full((K,), float(np.float32(pa)) * float(np.float32(pb)), dtype=torch.float64, device=self.dev)
-        mul = post.clone()
-        add = torch.zeros((K,), dtype=torch.float64, device=self.dev)
-        if mod.bias is not None:
-            # conv2d_Q_bias: bias/Ka/Kw (conv2d_func.py:44); linear_Q: bias/Kw/Ka (:63); plain conv2d_Q: raw bias
-            b = mod.bias.detach().double().to(self.dev)
-            if linear:
-                bq = b / float(mod.Kw) / float(mod.Ka)
-            elif getattr(mod, "_slfp_bias_scaled", True):
-                bq = b / float(mod.Ka) / float(mod.Kw)
-            else:
-                bq = b
-            add = bq * post
-        if bn is not None:
-            g = bn.weight.detach().double() if bn.weight is not None else torch.ones(K, dtype=torch.float64, device=self.dev)
-            be = bn.bias.detach().double() if bn.bias is not None else torch.zeros(K, dtype=torch.float64, device=self.dev)
-            sc_ = (g / torch.sqrt(bn.running_var.detach().double() + bn.eps)).to(self.dev)
-            sh_ = (be.to(self.dev) - bn.running_mean.detach().double().to(self.dev) * sc_)
-            mul, add = mul * sc_, add * sc_ + sh_
+        mul, add = self._affine(mod, bn, K, linear)
         mul32, add32 = mul.float().contiguous(), add.float().contiguous()
         self.keep += [mul32, add32]
         epi.ch_mul, epi.ch_add = mul32.data_ptr(), add32.data_ptr()
@@ -237,6 +223,85 @@ class Plan:
         self.conv_flops.append((fl, groups == 1, f"{C}->{K} {R}x{S} s{stride[0]} @{x.h}"))
         return out
 
+    def _affine(self, mod, bn, K, linear=False):
+        """(mul, add) float64 per output channel: y = acc * mul + add folds bias, the post-scale Ka*Kw and eval BN."""
+        ka, kw = _k32(mod.Ka), _k32(mod.Kw)
+        pa, pb = ((kw, ka) if linear else (ka, kw))
+        post = torch.full((K,), float(np.float32(pa)) * float(np.float32(pb)), dtype=torch.float64, device=self.dev)
+        mul, add = post.clone(), torch.zeros((K,), dtype=torch.float64, device=self.dev)
+        if mod.bias is not None:
+            b = mod.bias.detach().double().to(self.dev)
+            # conv2d_Q_bias: bias/Ka/Kw (conv2d_func.py:44); linear_Q: bias/Kw/Ka (:63); plain conv2d_Q: raw bias (:23)
+            if linear:
+                bq = b / float(mod.Kw) / float(mod.Ka)
+            elif getattr(mod, "_slfp_bias_scaled", True):
+                bq = b / float(mod.Ka) / float(mod.Kw)
+            else:
+                bq = b
+            add = bq * post
+        if bn is not None:
+            g = bn.weight.detach().double() if bn.weight is not None else torch.ones(K, dtype=torch.float64, device=self.dev)
+            be = bn.bias.detach().double() if bn.bias is not None else torch.zeros(K, dtype=torch.float64, device=self.dev)
+            sc_ = (g / torch.sqrt(bn.running_var.detach().double() + bn.eps)).to(self.dev)
+            sh_ = be.to(self.dev) - bn.running_mean.detach().double().to(self.dev) * sc_
+            mul, add = mul * sc_, add * sc_ + sh_
+        return mul, add
+
+    def conv_dual(self, x1, mod1, bn1, x2, mod2, bn2, relu=True, codes=(), f16=False):
+        """Fused residual-block tail (nets_imgnet/resnet50.py:80-88 for a block with a downsample branch):
+        relu(bn1(conv1x1(x1)) + bn2(conv1x1_stride(x2))) as ONE GEMM over the concatenated K dimension.  Per output
+        channel the branch with the larger folded scale keeps its exact float16 weights and supplies the epilogue's
+        multiplier; the other branch's weights carry the ratio (<= 1 in magnitude)."""
+        assert x1.kind == "codes" and x2.kind == "codes" and x1.fmt == x2.fmt
+        K, C1 = mod1.weight.shape[:2]
+        K2, C2 = mod2.weight.shape[:2]
+        assert K == K2 and mod1.weight.shape[2:] == (1, 1) and mod2.weight.shape[2:] == (1, 1)
+        assert mod1.bias is None and mod2.bias is None and x1.cp % 64 == 0 and x2.cp % 64 == 0 and K % 16 == 0
+        assert abs(_k32(mod1.Ka) - x1.kdiv) == 0.0 and abs(_k32(mod2.Ka) - x2.kdiv) == 0.0
+        d1 = nv.SlfpConvDesc(x1.n, x1.h, x1.w, C1, x1.cp, K, 1, 1, 1, 1, 0, 0, 1, 1, 1, x1.fmt, 0, 0)
+        s2 = mod2.stride
+        d2 = nv.SlfpConvDesc(x2.n, x2.h, x2.w, C2, x2.cp, K, 1, 1, s2[0], s2[1], 0, 0, 1, 1, 1, x2.fmt, 0, 0)
+        Ho, Wo = x1.h, x1.w
+        assert ((x2.h - 1) // s2[0] + 1, (x2.w - 1) // s2[1] + 1) == (Ho, Wo) and x1.n == x2.n
+        p1 = self.lib.slfp_conv_wpitch(ctypes.byref(d1))
+        p2 = self.lib.slfp_conv_wpitch(ctypes.byref(d2))
+        wbuf = torch.empty((K * (p1 + p2),), dtype=torch.float16, device=self.dev)
+        mul1, add1 = self._affine(mod1, bn1, K)
+        mul2, add2 = self._affine(mod2, bn2, K)
+        ref = torch.where(mul1.abs() >= mul2.abs(), mul1, mul2)
+        ref = torch.where(ref == 0, torch.ones_like(ref), ref)
+        r1, r2 = (mul1 / ref).float().contiguous(), (mul2 / ref).float().contiguous()
+        self._weight_job(d1, mod1.weight, _k32(mod1.Kw), wbuf, True, p1 + p2, 0, r1)
+        self._weight_job(d2, mod2.weight, _k32(mod2.Kw), wbuf, True, p1 + p2, p1, r2)
+        epi = nv.SlfpEpilogue()
+        mul32, add32 = ref.float().contiguous(), (add1 + add2).float().contiguous()
+        epi.ch_mul, epi.ch_add, epi.relu = mul32.data_ptr(), add32.data_ptr(), 1 if relu else 0
+        out = {"codes": {}, "f16": None, "f32": None}
+        kds = []
+        for kd in codes:
+            if kd not in kds:
+                kds.append(kd)
+        assert len(kds) <= 2
+        ofmt = nv.relu_fmt(self.afmt) if relu else self.afmt
+        for i, kd in enumerate(kds):
+            t = self._alloc(x1.n, Ho, Wo, K, "codes", kd, cp=K, fmt=ofmt)
+            out["codes"][kd] = t
+            if i == 0:
+                epi.y_codes, epi.next_k_div = t.buf.data_ptr(), kd
+            else:
+                epi.y_codes2, epi.next_k_div2 = t.buf.data_ptr(), kd
+        epi.next_fmt, epi.k_phys_out = ofmt, K
+        if f16:
+            out["f16"] = self._alloc(x1.n, Ho, Wo, K, "f16")
+            epi.y_f16 = out["f16"].buf.data_ptr()
+        self.keep += [d1, d2, epi, wbuf, mul32, add32, r1, r2]
+        self.ops.append(self._call(self.lib.slfp_conv2d_fwd_dual, ctypes.byref(d1), x1.buf.data_ptr(), ctypes.byref(d2),
+                                   x2.buf.data_ptr(), wbuf.data_ptr(), ctypes.byref(epi)))
+        fl = 2.0 * x1.n * Ho * Wo * K * (C1 + C2)
+        self.flops += fl
+        self.conv_flops.append((fl, True, f"{C1}+{C2}->{K} 1x1 dual @{x1.h}"))
+        return out
+
     def maxpool(self, x, k, stride, pad):
         assert x.kind == "codes"
         Ho = (x.h + 2 * pad - k) // stride + 1
@@ -267,15 +332,13 @@ class Plan:
         for op in self.pre_weight_ops:
             op()
         if self._wbatch is None:
-            descs = (ctypes.POINTER(nv.SlfpConvDesc) * n)(*[ctypes.pointer(t[0]) for t in self.weight_table])
-            ws = (ctypes.c_void_p * n)(*[t[1] for t in self.weight_table])
-            strides = (ctypes.c_longlong * (4 * n))(*[v for t in self.weight_table for v in t[2]])
-            kws = (ctypes.c_float * n)(*[t[3] for t in self.weight_table])
-            f16 = (ctypes.c_void_p * n)(*[t[4] for t in self.weight_table])
-            codes = (ctypes.c_void_p * n)(*[t[5] for t in self.weight_table])
-            self._wbatch = (descs, ws, strides, kws, f16, codes)
-        descs, ws, strides, kws, f16, codes = self._wbatch
-        nv.check(self.lib.slfp_prepare_weights_batch(n, descs, ws, strides, kws, self.wfmt, f16, codes, nv.stream()))
+            jobs = (nv.SlfpWeightJob * n)()
+            for j, (d, w, strides, kw, f16, codes, out_pitch, out_offset, row_scale) in zip(jobs, self.weight_table):
+                j.desc, j.w, j.kw, j.w_f16, j.w_codes = ctypes.pointer(d), w, kw, f16, codes
+                j.w_stride[:] = strides
+                j.out_pitch, j.out_offset, j.row_scale = out_pitch, out_offset, row_scale
+            self._wbatch = jobs
+        nv.check(self.lib.slfp_prepare_weights_jobs(n, self._wbatch, self.wfmt, nv.stream()))
 
     @torch.no_grad()
     def run(self):
@@ -312,7 +375,7 @@ class Plan:
 
 
 # ---- per-architecture compilers -------------------------------------------------------------------------------
-def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", static_weights=False):
+def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", static_weights=False, fuse_downsample=True):
     """nets_imgnet.ResNet50 (or the reference's own class: same attribute names) -> Plan."""
     assert not model.training, "the fused pipeline folds BatchNorm: call model.eval() first"
     P = Plan(batch, device, model.qbit if hasattr(model, "qbit") else model.conv1.q_bit, static_weights)
@@ -347,13 +410,24 @@ def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", stat
         nxt = blocks[i + 1] if i + 1 < len(blocks) else None
         o1 = P.conv(cur_codes[_k32(b.conv1.Ka)], b.conv1, bn=b.bn1, relu=True, codes=[_k32(b.conv2.Ka)])
         o2 = P.conv(o1["codes"][_k32(b.conv2.Ka)], b.conv2, bn=b.bn2, relu=True, codes=[_k32(b.conv3.Ka)])
+        need_val = nxt is None or nxt.downsample is None        # someone adds / pools the un-quantized value
+        ds0 = b.downsample[0] if b.downsample is not None else None
+        fuse = (fuse_downsample and ds0 is not None and res_f16 and ds0.kernel_size == (1, 1) and ds0.padding == (0, 0)
+                and ds0.bias is None and b.conv3.bias is None and cur_codes[_k32(ds0.Ka)].cp % 64 == 0
+                and o2["codes"][_k32(b.conv3.Ka)].cp % 64 == 0 and b.conv3.out_channels % 16 == 0)
+        if fuse:
+            # block tail and downsample branch as ONE GEMM: no downsample launch, no float16 round trip of its output
+            o3 = P.conv_dual(o2["codes"][_k32(b.conv3.Ka)], b.conv3, b.bn3, cur_codes[_k32(ds0.Ka)], ds0, b.downsample[1],
+                             relu=True, codes=consumers(nxt) if nxt is not None else [], f16=need_val)
+            cur_codes = o3["codes"]
+            cur_res = o3["f16"]
+            continue
         if b.downsample is not None:
             ds = P.conv(cur_codes[_k32(b.downsample[0].Ka)], b.downsample[0], bn=b.downsample[1], relu=False,
                         f16=res_f16, f32=not res_f16)
             res = ds["f16"] if res_f16 else ds["f32"]
         else:
             res = cur_res
-        need_val = nxt is None or nxt.downsample is None        # someone adds / pools the un-quantized value
         o3 = P.conv(o2["codes"][_k32(b.conv3.Ka)], b.conv3, bn=b.bn3, relu=True, residual=res,
                     codes=consumers(nxt) if nxt is not None else [], f16=need_val and res_f16, f32=need_val and not res_f16)
         cur_codes = o3["codes"]

@@ -173,16 +173,38 @@ int slfp_prepare_weights(const SlfpConvDesc *desc, const float *w, long long w_s
                          slfp_stream_t stream);
 
 /* The same for n layers in ONE launch (the reference re-quantizes every layer's weights on every forward,
- * conv2d_func.py:22).  host_* arrays have n entries and are read before the call returns; host_strides holds
- * 4 element strides (o, c, r, s) per layer; host_w_f16 / host_w_codes may be NULL or hold NULL entries. */
-int slfp_prepare_weights_batch(int n, const SlfpConvDesc *const *host_descs, const float *const *host_w,
-                               const long long *host_strides, const float *host_kw, int wfmt,
-                               void *const *host_w_f16, uint8_t *const *host_w_codes, slfp_stream_t stream);
+ * conv2d_func.py:22).  The job table is host memory and is read before the call returns.  out_pitch / out_offset
+ * place a layer's rows inside a wider operand (0 = the layer's own pitch): the fused block tail concatenates the
+ * last conv of a residual block and its downsample conv along K; row_scale (device, [k], or NULL) multiplies the
+ * float16 operand of output channel k (the ratio of the two branches' folded BatchNorm scales). */
+typedef struct {
+    const SlfpConvDesc *desc;
+    const float *w;            /* device: the OIHW float32 parameter                                   */
+    long long w_stride[4];     /* element strides (o, c, r, s)                                          */
+    float kw;
+    void *w_f16;               /* device outputs, either may be NULL                                   */
+    uint8_t *w_codes;
+    size_t out_pitch, out_offset;
+    const float *row_scale;
+} SlfpWeightJob;
+int slfp_prepare_weights_jobs(int n, const SlfpWeightJob *host_jobs, int wfmt, slfp_stream_t stream);
 
 /* Forward on codes.  x_codes NHWC [n,h,w,c_phys]; w_f16 from slfp_prepare_weights (dense) or
  * w_f32 KRSC float32 for the depthwise / grouped stencil path. */
 int slfp_conv2d_fwd(const SlfpConvDesc *desc, const uint8_t *x_codes, const void *w_prepared,
                     const SlfpEpilogue *epi, slfp_stream_t stream);
+
+/* Fused residual-block tail: the last convolution of a block and the block's downsample convolution as ONE
+ * GEMM over the concatenated K dimension,
+ *     y = epilogue( sum_k A1[m,k] W1[n,k] + sum_k A2[m,k] W2'[n,k] ),
+ * desc1 / x1_codes: the main branch (e.g. conv3, 1x1); desc2 / x2_codes: the downsample branch (1x1, any stride,
+ * no padding) - same n, same output size, same k, same code format.  w_cat: [k, pitch1 + pitch2] float16 from
+ * slfp_prepare_weights_jobs (W2' carries the ratio of the two branches' scales; the epilogue's folded affine
+ * ch_mul / ch_add belongs to branch 1 with the two shifts added).  Removes the downsample launch, its float16
+ * output and the residual read of it.  Replaces nets_imgnet/resnet50.py:80-88 (`out = bn3(conv3(out))`,
+ * `identity = downsample(x)`, `out += identity`, `relu`). */
+int slfp_conv2d_fwd_dual(const SlfpConvDesc *desc1, const uint8_t *x1_codes, const SlfpConvDesc *desc2,
+                         const uint8_t *x2_codes, const void *w_cat, const SlfpEpilogue *epi, slfp_stream_t stream);
 
 /* Backward of Conv2d_Q.forward with the identity STE (utils/sfp_quant.py:50-53, 99-102):
  *   dx = dgrad(gy*Ka*Kw, w_q)/Ka      dw = wgrad(gy*Ka*Kw, x_q)/Kw      db = sum(gy)

@@ -196,13 +196,58 @@ def test_batched_weight_preparation_equals_per_layer(orc):
                                           nv.stream()))
         descs.append(d); ws.append(w); singles.append(a); batch_out.append(b); strides += list(w.stride()); kws.append(kw)
     n = len(shapes)
-    nv.check(lib.slfp_prepare_weights_batch(
-        n, (ctypes.POINTER(nv.SlfpConvDesc) * n)(*[ctypes.pointer(d) for d in descs]),
-        (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws]), (ctypes.c_longlong * (4 * n))(*strides), (ctypes.c_float * n)(*kws),
-        nv.FMT_SLFP34_WGT, (ctypes.c_void_p * n)(*[b.data_ptr() for b in batch_out]), None, nv.stream()))
+    jobs = (nv.SlfpWeightJob * n)()
+    for i, j in enumerate(jobs):
+        j.desc, j.w, j.kw, j.w_f16 = ctypes.pointer(descs[i]), ws[i].data_ptr(), kws[i], batch_out[i].data_ptr()
+        j.w_stride[:] = strides[4 * i:4 * i + 4]
+    nv.check(lib.slfp_prepare_weights_jobs(n, jobs, nv.FMT_SLFP34_WGT, nv.stream()))
     torch.cuda.synchronize()
     for a, b in zip(singles, batch_out):
         assert torch.equal(a, b)
+
+
+def test_fused_block_tail_equals_two_convs(orc):
+    """conv3 + downsample as one concatenated-K GEMM (slfp_conv2d_fwd_dual) against the two separate launches
+    (downsample -> float16, conv3 with that residual): same float16 output up to the ratio-scaled weights'
+    extra rounding, and the codes follow the output."""
+    from cnns_slfp_quantization_b200 import engine, _native as nv
+    import torch.nn as nn
+    from cnns_slfp_quantization_b200.utils import conv2d_func as cf
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    N, C1, C2, K, H = 2, 64, 128, 256, 12
+    for stride in (1, 2):
+        c3 = cf.conv2d_Q(8, 0.011, 0.4)(C1, K, 1).to(dev)
+        ds = cf.conv2d_Q(8, 0.013, 0.5)(C2, K, 1, stride=stride).to(dev)
+        bn3, bnd = nn.BatchNorm2d(K).to(dev).eval(), nn.BatchNorm2d(K).to(dev).eval()
+        for bn in (bn3, bnd):
+            bn.weight.data.uniform_(0.2, 1.5); bn.bias.data.normal_(0, 0.3)
+            bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5)
+        bn3.weight.data[:5] = 0.0                        # zero-initialised residual BN: the ratio must stay finite
+        outs = []
+        for fused in (True, False):
+            P = engine.Plan(N, dev, 8)
+            a2 = P._alloc(N, H, H, C1, "codes", engine._k32(c3.Ka), cp=C1, fmt=nv.FMT_SLFP34_RELU)
+            x = P._alloc(N, H * stride, H * stride, C2, "codes", engine._k32(ds.Ka), cp=C2, fmt=nv.FMT_SLFP34_RELU)
+            g = torch.Generator(device="cpu").manual_seed(5)
+            a2.buf.copy_(torch.randint(0, 200, a2.buf.shape, generator=g, dtype=torch.uint8))
+            x.buf.copy_(torch.randint(0, 200, x.buf.shape, generator=g, dtype=torch.uint8))
+            if fused:
+                o = P.conv_dual(a2, c3, bn3, x, ds, bnd, relu=True, codes=[0.3], f16=True)
+            else:
+                r = P.conv(x, ds, bn=bnd, relu=False, f16=True)["f16"]
+                o = P.conv(a2, c3, bn=bn3, relu=True, residual=r, codes=[0.3], f16=True)
+            P.run()
+            torch.cuda.synchronize()
+            outs.append((o["f16"].buf.float().cpu().numpy(), o["codes"][0.3].buf.cpu().numpy()))
+        (yf, cf_), (ys, cs_) = outs
+        scale = np.abs(ys).max()
+        assert np.abs(yf - ys).max() <= 4e-3 * scale, float(np.abs(yf - ys).max() / scale)
+        # codes: both are the quantizer of (their own) float32 y; where the float16 outputs agree the two float32
+        # values differ by < 2^-11 relative, which still straddles a code boundary (one per 4.4 %) now and then
+        same = yf == ys
+        assert same.mean() > 0.5
+        assert (orc.decode_relu(cf_, False)[same] == orc.decode_relu(cs_, False)[same]).mean() > 0.995
 
 
 def test_maxpool_on_post_relu_codes(orc):
