@@ -747,13 +747,14 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t c = w[i];
-                    // per code: shift, one LOP3 ((x & 0x7f80) | lane*4), one LDS [reg + constant table base]
+                    // per code: a shift (IMAD.HI measured slower than SHF), one LOP3 ((x & 0x7f80) | lane*4), one
+                    // LDS [reg + constant table base]; two table entries (float16 in the low half) merge with an IMAD
                     const uint32_t e0 = ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base);
                     const uint32_t e1 = ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base);
                     const uint32_t e2 = ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base);
                     const uint32_t e3 = ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base);
-                    h[2 * i] = __byte_perm(e0, e1, 0x5410);
-                    h[2 * i + 1] = __byte_perm(e2, e3, 0x5410);
+                    h[2 * i] = ptx::pack16_fma(e0, e1);
+                    h[2 * i + 1] = ptx::pack16_fma(e2, e3);
                 }
                 if (C::kATmem) {
                     ptx::tmem_st8(a_tmem_lane + stage * 32u + (uint32_t)q * 8u, h);

@@ -253,6 +253,22 @@ __global__ void __launch_bounds__(256) quantize_nchw_s2d_kernel(const float* __r
         const int x2 = (int)(i % W2), y2 = (int)((i / W2) % H2);
         const size_t n = i / ((size_t)W2 * H2);
         uint8_t* dst = codes + i * (size_t)Cp;
+        if (Cp == 16 && 4 * C <= 16) {
+            // the stem case (C <= 4): one float2 (both dx) per (channel, dy): consecutive threads read consecutive
+            // float2 of an image row (coalesced), one 16-byte store per thread
+            uint32_t wds[4] = {0u, 0u, 0u, 0u};
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(x + ((n * C + c) * H + (2 * y2 + dy)) * (size_t)W) + x2);
+                    const int ch0 = (dy * 2) * C + c, ch1 = (dy * 2 + 1) * C + c;
+                    wds[ch0 >> 2] |= encode<FMT>(div_k(v.x, k_div)) << (8 * (ch0 & 3));
+                    wds[ch1 >> 2] |= encode<FMT>(div_k(v.y, k_div)) << (8 * (ch1 & 3));
+                }
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            continue;
+        }
         for (int c0 = 0; c0 < Cp; c0 += 16) {
             uint32_t wds[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -333,20 +349,35 @@ struct WPrepArgs {
     // applied to the float16 operand only (fused block tails, see slfp_conv2d_fwd_dual)
     size_t out_pitch, out_off;
     const float* row_scale;
+    uint32_t mg_pitch, sh_pitch, mg_cp, sh_cp, mg_s, sh_s;   // n / d == umulhi(n, mg) >> sh for n < 2^31 (d > 1)
 };
+
+static void magic_u32(uint32_t d, uint32_t& mg, uint32_t& sh) {
+    mg = 0; sh = 0;
+    if (d > 1) {
+        uint32_t lg = 31 - __builtin_clz(d);
+        if (d & (d - 1)) ++lg;
+        const uint32_t p = 31 + lg;
+        mg = (uint32_t)(((1ull << p) + d - 1) / d);
+        sh = p - 32;
+    }
+}
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t d, uint32_t mg, uint32_t sh) {
+    return d == 1 ? n : (__umulhi(n, mg) >> sh);
+}
 
 template <int FMT>
 __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, const uint32_t* s_tab) {
     // a prepared tensor has < 2^32 elements (checked on the host): 32-bit index arithmetic
     const uint32_t i32 = (uint32_t)i, pitch = (uint32_t)a.pitch;
-    const int k = (int)(i32 / pitch);
+    const int k = (int)div_magic(i32, pitch, a.mg_pitch, a.sh_pitch);
     const uint32_t j = i32 - (uint32_t)k * pitch;
-    const int rs = (int)(j / (uint32_t)a.Cp);
+    const int rs = (int)div_magic(j, (uint32_t)a.Cp, a.mg_cp, a.sh_cp);
     const int c = (int)(j - (uint32_t)rs * (uint32_t)a.Cp);
     uint32_t code = 0;
     float fq = 0.0f;
     if (c < a.C && rs < a.R * a.S) {
-        const int r = rs / a.S, s = rs - r * a.S;
+        const int r = (int)div_magic((uint32_t)rs, (uint32_t)a.S, a.mg_s, a.sh_s), s = rs - r * a.S;
         const float x = a.w[k * a.so + c * a.sc + r * a.sr + s * a.ss];
         const float v = div_rn(x, a.kw);
         if (FMT < 0) {
@@ -551,6 +582,10 @@ static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long 
     a.pitch = slfp_conv_wpitch(d);
     a.kw = kw; a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
     a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr;
+    if ((size_t)a.K * a.pitch >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^31 or more elements");
+    magic_u32((uint32_t)a.pitch, a.mg_pitch, a.sh_pitch);
+    magic_u32((uint32_t)a.Cp, a.mg_cp, a.sh_cp);
+    magic_u32((uint32_t)a.S, a.mg_s, a.sh_s);
     return 0;
 }
 

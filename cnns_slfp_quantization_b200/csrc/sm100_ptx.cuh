@@ -91,6 +91,19 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// Pipe balance: the decode loop's integer work all landed on the ALU pipe (LOP3 / SHF / PRMT; 55 % busy with the FMA
+// pipe at 7 %, profiles/r01_conv_v2.md).  These two run on the FMA pipe instead: a right shift as the high half
+// of a multiply by 2^(32-s), and "lo | hi << 16" (disjoint halves) as one multiply-add.
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x, uint32_t pow2_32_minus_s) {
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(pow2_32_minus_s));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack16_fma(uint32_t lo, uint32_t hi) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
 __device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
