@@ -277,11 +277,19 @@ def main():
                     ms_ = a.elapsed_time(b)
                     f.write(f"{desc:32s} {ms_ * 1e3:9.1f} us {fl / ms_ / 1e9:8.1f} TFLOP/s\n")
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        traffic = None                     # DRAM bytes per launch from the committed ncu launch list (same command)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                t_ = json.load(f)
+            if args.batch == 256 and args.size == 224:
+                traffic = t_["dram_bytes_per_step"] / t_["launches_per_step"]
+        except Exception:
+            pass
         peak = pk["bf16_tflops_sustained"]
         roof = {"kernel": "conv_igemm_v2_kernel (warp-specialised tcgen05 implicit GEMM; all dense conv launches of one step)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step)",
-                "traffic": None, "launches": len(dense), "avg_launch_ms": conv_ms / max(len(dense), 1),
+                "traffic": traffic, "launches": len(dense), "avg_launch_ms": conv_ms / max(len(dense), 1),
                 "share_of_step": conv_ms / max(sum(all_ms.values()), 1e-9),
                 "per_entry_point_ms": {k: round(v, 4) for k, v in all_ms.items()}}
 
@@ -304,10 +312,11 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16 operands (decoded SLFP<3,4> codes) x f32 accumulate; u8 codes between layers", "data": "synthetic",
+                "dtype": "f16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "images_per_gpu": args.batch, "parallelism": f"dp{world}",
                            "l2": "inputs (154 MB/batch) and per-layer activations exceed the 126 MB L2; no explicit flush",
                            "cuda_graph": not args.no_graph, "weights_requantized_every_step": not plan.static_weights,
+                           "arithmetic": "u8 SLFP<3,4> codes between layers -> f16 tensor-core operands, f32 accumulate",
                            "residual_stream": "f16"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
