@@ -5,7 +5,10 @@
 //   * convolution backward with the identity straight-through estimator (utils/sfp_quant.py:50-53):
 //       dx = dgrad(gy*Ka*Kw, w_q)/Ka   dw = wgrad(gy*Ka*Kw, x_q)/Kw   db = sum(gy)
 //   * max-pool on codes and global average pool (glue of the fused eval pipeline).
+#include <stdlib.h>
+
 #include "slfp_common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace slfp {
 
@@ -84,6 +87,221 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(DirectParams p) {
     }
 }
 
+// ---- depthwise forward, fused-pipeline form (HBM-bound stencil) ------------------------------------------------
+// thread = (output pixel, 16 consecutive channels): one 16-byte code load per filter tap (coalesced across the
+// channel groups of a pixel), codes -> float32 through a bank-conflict-free table in shared memory (any of the four
+// activation code formats; 256 entries x 32 bank copies), float32 weights of all taps staged in shared memory once
+// per CTA, float32 accumulate; folded per-channel affine + ReLU + the 2-instruction post-ReLU encoder
+// (slfp_common.cuh encode_relu_fast_raw16), one 16-byte code store per thread.
+// Algorithmic bytes per output element: taps/stride^2 in (each input byte is fetched from DRAM once; the window
+// overlap hits L1/L2) + 1 out.
+struct DwFastParams {
+    const uint8_t* x;
+    const uint8_t* w;          // [C][R*S] weight codes
+    int N, H, W, Cp, C, R, S, sh, sw, ph, pw, dh, dw, Ho, Wo;
+    int act_fmt, wgt_sfp33, out_sfp33;
+    const float* ch_mul;
+    const float* ch_add;
+    float sc;                  // 1 / (16 Ka_next)
+    uint8_t* y;
+};
+
+// weight of (tap t, channel c = 16 q + 4 g + e) lives at s_w[t * Cp + (g * (Cp / 16) + q) * 4 + e]: the threads of a
+// warp differ in q, so their 16-byte weight loads for a fixed g are consecutive (bank-conflict free)
+template <int TAPS>       // R * S when it is 9 (3x3: all nine 16-byte loads are issued before the first use), else 0
+__global__ void __launch_bounds__(256) dwconv_fast_kernel(const DwFastParams p) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm);                 // [256 codes][32 banks] float32 bits
+    float* s_w = reinterpret_cast<float*>(dsm + 256 * 32 * 4);          // [taps][Cp], permuted as above
+    const int taps = p.R * p.S;
+    const int cg = p.Cp >> 4;
+    for (int i = threadIdx.x; i < 256 * 32; i += 256) s_lut[i] = __float_as_uint(decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac));
+    for (int i = threadIdx.x; i < taps * p.Cp; i += 256) {
+        const int t = i / p.Cp, c = i - t * p.Cp;
+        float wv = 0.0f;
+        if (c < p.C) {
+            const uint32_t code = p.w[(size_t)c * taps + t];
+            wv = p.wgt_sfp33 ? decode<true>(code, c_pow2frac) : decode<false>(code, c_pow2frac);
+        }
+        const int q = c >> 4, g = (c >> 2) & 3, e = c & 3;
+        s_w[t * p.Cp + (g * cg + q) * 4 + e] = wv;
+    }
+    __syncthreads();
+    const uint32_t lut_base = ptx::smem_u32(s_lut), w_base = ptx::smem_u32(s_w);
+    const uint32_t lane4 = (threadIdx.x & 31u) * 4u;
+    const size_t total = (size_t)p.N * p.Ho * p.Wo * cg;
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+        const int q = (int)(idx % cg), c0 = q * 16;
+        const size_t pix = idx / cg;
+        const int wo = (int)(pix % p.Wo), ho = (int)((pix / p.Wo) % p.Ho), n = (int)(pix / ((size_t)p.Wo * p.Ho));
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+        auto tap_fma = [&](const uint4& cw, int t) {
+            const uint32_t wds[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t c = wds[g];
+                const float4 w4 = ptx::lds128_f4(w_base + (uint32_t)(t * p.Cp + (g * cg + q) * 4) * 4u);
+                const float x0 = __uint_as_float(ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base));
+                const float x1 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base));
+                const float x2 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base));
+                const float x3 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base));
+                acc[4 * g + 0] = fmaf(x0, w4.x, acc[4 * g + 0]);
+                acc[4 * g + 1] = fmaf(x1, w4.y, acc[4 * g + 1]);
+                acc[4 * g + 2] = fmaf(x2, w4.z, acc[4 * g + 2]);
+                acc[4 * g + 3] = fmaf(x3, w4.w, acc[4 * g + 3]);
+            }
+        };
+        const uint8_t* xn = p.x + (size_t)n * p.H * p.W * p.Cp + c0;
+        if (TAPS == 9) {
+            uint4 cw[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int hi = ho * p.sh - p.ph + (t / 3) * p.dh, wi = wo * p.sw - p.pw + (t % 3) * p.dw;
+                cw[t] = make_uint4(0u, 0u, 0u, 0u);                                 // zero padding: code 0 = 0.0
+                if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)
+                    cw[t] = __ldg(reinterpret_cast<const uint4*>(xn + ((size_t)hi * p.W + wi) * p.Cp));
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) tap_fma(cw[t], t);
+        } else {
+            int t = 0;
+            for (int r = 0; r < p.R; ++r) {
+                const int hi = ho * p.sh - p.ph + r * p.dh;
+                for (int s = 0; s < p.S; ++s, ++t) {
+                    const int wi = wo * p.sw - p.pw + s * p.dw;
+                    if (hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) continue;
+                    tap_fma(__ldg(reinterpret_cast<const uint4*>(xn + ((size_t)hi * p.W + wi) * p.Cp)), t);
+                }
+            }
+        }
+        int32_t tq[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.ch_mul + c0) + g);
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.ch_add + c0) + g);
+            const float v0 = fmaf(acc[4 * g + 0], m4.x, a4.x), v1 = fmaf(acc[4 * g + 1], m4.y, a4.y);
+            const float v2 = fmaf(acc[4 * g + 2], m4.z, a4.z), v3 = fmaf(acc[4 * g + 3], m4.w, a4.w);
+            if (p.out_sfp33) {
+                tq[4 * g + 0] = encode_relu_fast_raw16<true>(__saturatef(v0 * p.sc)); tq[4 * g + 1] = encode_relu_fast_raw16<true>(__saturatef(v1 * p.sc));
+                tq[4 * g + 2] = encode_relu_fast_raw16<true>(__saturatef(v2 * p.sc)); tq[4 * g + 3] = encode_relu_fast_raw16<true>(__saturatef(v3 * p.sc));
+            } else {
+                tq[4 * g + 0] = encode_relu_fast_raw16<false>(__saturatef(v0 * p.sc)); tq[4 * g + 1] = encode_relu_fast_raw16<false>(__saturatef(v1 * p.sc));
+                tq[4 * g + 2] = encode_relu_fast_raw16<false>(__saturatef(v2 * p.sc)); tq[4 * g + 3] = encode_relu_fast_raw16<false>(__saturatef(v3 * p.sc));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) tq[j] = (c0 + j < p.C) ? tq[j] : 0;             // zero code in pad channels
+        uint4 pk;
+        pk.x = ptx::pack_sat_u8x4(tq[0], tq[1], tq[2], tq[3]);   pk.y = ptx::pack_sat_u8x4(tq[4], tq[5], tq[6], tq[7]);
+        pk.z = ptx::pack_sat_u8x4(tq[8], tq[9], tq[10], tq[11]); pk.w = ptx::pack_sat_u8x4(tq[12], tq[13], tq[14], tq[15]);
+        *reinterpret_cast<uint4*>(p.y + pix * p.Cp + c0) = pk;
+    }
+}
+
+// 3x3, stride 1 / 2, dilation 1: a thread computes a strip of 4 output pixels along W for its 16 channels.  Every
+// input vector (pixel x 16 channels) of the 3 x (3*stride+3) window is fetched and decoded ONCE for the strip
+// (4.5 table look-ups per output at stride 1 instead of 9) and every weight vector is read once per 4 outputs.
+template <int STRIDE>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastParams p) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm);
+    float* s_w = reinterpret_cast<float*>(dsm + 256 * 32 * 4);
+    const int cg = p.Cp >> 4;
+    for (int i = threadIdx.x; i < 256 * 32; i += 256) s_lut[i] = __float_as_uint(decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac));
+    for (int i = threadIdx.x; i < 9 * p.Cp; i += 256) {
+        const int t = i / p.Cp, c = i - t * p.Cp;
+        float wv = 0.0f;
+        if (c < p.C) {
+            const uint32_t code = p.w[(size_t)c * 9 + t];
+            wv = p.wgt_sfp33 ? decode<true>(code, c_pow2frac) : decode<false>(code, c_pow2frac);
+        }
+        s_w[t * p.Cp + (((c >> 2) & 3) * cg + (c >> 4)) * 4 + (c & 3)] = wv;
+    }
+    __syncthreads();
+    const uint32_t lut_base = ptx::smem_u32(s_lut), w_base = ptx::smem_u32(s_w);
+    const uint32_t lane4 = (threadIdx.x & 31u) * 4u;
+    constexpr int kOut = 4, kCols = (kOut - 1) * STRIDE + 3;      // 6 input columns at stride 1, 9 at stride 2
+    const int wstrips = (p.Wo + kOut - 1) / kOut;
+    const size_t total = (size_t)p.N * p.Ho * wstrips * cg;
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+        const int q = (int)(idx % cg), c0 = q * 16;
+        size_t rest = idx / cg;
+        const int ws = (int)(rest % wstrips); rest /= wstrips;
+        const int ho = (int)(rest % p.Ho), n = (int)(rest / p.Ho);
+        const int wo0 = ws * kOut;
+        float acc[kOut][16];
+#pragma unroll
+        for (int o = 0; o < kOut; ++o)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[o][j] = 0.0f;
+        const uint8_t* xn = p.x + (size_t)n * p.H * p.W * p.Cp + c0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int hi = ho * STRIDE - p.ph + r;
+            const bool hok = hi >= 0 && hi < p.H;
+            uint4 cw[kCols];
+#pragma unroll
+            for (int cidx = 0; cidx < kCols; ++cidx) {
+                const int wi = wo0 * STRIDE - p.pw + cidx;
+                cw[cidx] = make_uint4(0u, 0u, 0u, 0u);
+                if (hok && wi >= 0 && wi < p.W) cw[cidx] = __ldg(reinterpret_cast<const uint4*>(xn + ((size_t)hi * p.W + wi) * p.Cp));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float4 w4[3];
+#pragma unroll
+                for (int s = 0; s < 3; ++s) w4[s] = ptx::lds128_f4(w_base + (uint32_t)((r * 3 + s) * p.Cp + (g * cg + q) * 4) * 4u);
+#pragma unroll
+                for (int cidx = 0; cidx < kCols; ++cidx) {
+                    const uint32_t c = g == 0 ? cw[cidx].x : (g == 1 ? cw[cidx].y : (g == 2 ? cw[cidx].z : cw[cidx].w));
+                    const float x0 = __uint_as_float(ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base));
+                    const float x1 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base));
+                    const float x2 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base));
+                    const float x3 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base));
+#pragma unroll
+                    for (int o = 0; o < kOut; ++o) {
+                        const int s = cidx - o * STRIDE;                    // filter column this input column has for output o
+                        if (s >= 0 && s < 3) {
+                            acc[o][4 * g + 0] = fmaf(x0, w4[s].x, acc[o][4 * g + 0]);
+                            acc[o][4 * g + 1] = fmaf(x1, w4[s].y, acc[o][4 * g + 1]);
+                            acc[o][4 * g + 2] = fmaf(x2, w4[s].z, acc[o][4 * g + 2]);
+                            acc[o][4 * g + 3] = fmaf(x3, w4[s].w, acc[o][4 * g + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        float4 m4[4], a4[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            m4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_mul + c0) + g);
+            a4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_add + c0) + g);
+        }
+        const size_t pix0 = ((size_t)n * p.Ho + ho) * p.Wo + wo0;
+#pragma unroll
+        for (int o = 0; o < kOut; ++o) {
+            if (wo0 + o >= p.Wo) break;
+            int32_t tq[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float mm[4] = {m4[g].x, m4[g].y, m4[g].z, m4[g].w}, aa[4] = {a4[g].x, a4[g].y, a4[g].z, a4[g].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = __saturatef(fmaf(acc[o][4 * g + e], mm[e], aa[e]) * p.sc);
+                    tq[4 * g + e] = p.out_sfp33 ? encode_relu_fast_raw16<true>(v) : encode_relu_fast_raw16<false>(v);
+                    if (c0 + 4 * g + e >= p.C) tq[4 * g + e] = 0;
+                }
+            }
+            uint4 pk;
+            pk.x = ptx::pack_sat_u8x4(tq[0], tq[1], tq[2], tq[3]);   pk.y = ptx::pack_sat_u8x4(tq[4], tq[5], tq[6], tq[7]);
+            pk.z = ptx::pack_sat_u8x4(tq[8], tq[9], tq[10], tq[11]); pk.w = ptx::pack_sat_u8x4(tq[12], tq[13], tq[14], tq[15]);
+            *reinterpret_cast<uint4*>(p.y + (pix0 + o) * p.Cp + c0) = pk;
+        }
+    }
+}
+
 // Generic grouped convolution: thread = (pixel, output channel), loops over Cg x R x S.
 template <bool SFP33>
 __global__ void __launch_bounds__(256) gconv_fwd_kernel(DirectParams p) {
@@ -130,9 +348,60 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd(grouped): channels not divisible by groups");
     if (d->pad_h_extra || d->pad_w_extra)
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): asymmetric padding is a dense-path feature");
+    {
+        // fused-pipeline depthwise: folded affine + ReLU + post-ReLU codes only, 16-channel vectors
+        const bool relu_out = epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU;
+        const bool dw = d->groups == d->c && d->k == d->c;
+        const size_t smem = 256 * 32 * 4 + (size_t)d->r * d->s * d->c_phys * 4;
+        if (dw && relu_out && epi->ch_mul && epi->ch_add && epi->relu && epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->y_f32 &&
+            !epi->residual && epi->k_phys_out == d->c_phys && d->c_phys % 16 == 0 && epi->next_k_div > 0.f && smem <= 200 * 1024 &&
+            ((((uintptr_t)x_codes | (uintptr_t)epi->y_codes | (uintptr_t)epi->ch_mul | (uintptr_t)epi->ch_add) & 15u) == 0)) {
+            DwFastParams q;
+            q.x = x_codes; q.w = (const uint8_t*)w_codes;
+            q.N = d->n; q.H = d->h; q.W = d->w; q.Cp = d->c_phys; q.C = d->c; q.R = d->r; q.S = d->s;
+            q.sh = d->stride_h; q.sw = d->stride_w; q.ph = d->pad_h; q.pw = d->pad_w; q.dh = d->dil_h; q.dw = d->dil_w;
+            q.Ho = p.Ho; q.Wo = p.Wo;
+            q.act_fmt = d->fmt;
+            q.wgt_sfp33 = (d->fmt == SLFP_FMT_SFP33 || d->fmt == SLFP_FMT_SFP33_RELU) ? 1 : 0;    // weights: the q_bit's weight format
+            q.out_sfp33 = epi->next_fmt == SLFP_FMT_SFP33_RELU ? 1 : 0;
+            q.ch_mul = epi->ch_mul; q.ch_add = epi->ch_add;
+            q.sc = (float)(1.0 / (16.0 * (double)epi->next_k_div));
+            q.y = epi->y_codes;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t e = cudaFuncSetAttribute(dwconv_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                if (e != cudaSuccess) return set_error((int)e, "dwconv_fast: smem attribute: %s", cudaGetErrorString(e));
+                attr_done = true;
+            }
+            const size_t tot = (size_t)d->n * p.Ho * p.Wo * (d->c_phys / 16);
+            int blocks_per_sm = (int)((220 * 1024) / (smem + 1024));
+            blocks_per_sm = blocks_per_sm > 6 ? 6 : (blocks_per_sm < 1 ? 1 : blocks_per_sm);
+            const int g = (int)min((size_t)num_sms() * blocks_per_sm, ceil_div_sz(tot, 256));
+            const bool strip = d->r == 3 && d->s == 3 && d->dil_h == 1 && d->dil_w == 1 && d->stride_h == d->stride_w &&
+                               (d->stride_h == 1 || d->stride_h == 2) && p.Wo >= 4 && getenv("SLFP_DW_NO_STRIP") == nullptr;
+            if (strip) {
+                static bool attr2 = false;
+                if (!attr2) {
+                    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                    if (e != cudaSuccess) return set_error((int)e, "dwconv3x3_strip: smem attribute: %s", cudaGetErrorString(e));
+                    attr2 = true;
+                }
+                const size_t tot4 = (size_t)d->n * p.Ho * ((p.Wo + 3) / 4) * (d->c_phys / 16);
+                const int g4 = (int)min((size_t)num_sms() * min(blocks_per_sm, 3), ceil_div_sz(tot4, 256));
+                if (d->stride_h == 1) dwconv3x3_strip_kernel<1><<<g4, 256, smem, st>>>(q);
+                else dwconv3x3_strip_kernel<2><<<g4, 256, smem, st>>>(q);
+                return check_launch("dwconv3x3_strip_kernel");
+            }
+            if (d->r == 3 && d->s == 3) dwconv_fast_kernel<9><<<g, 256, smem, st>>>(q);
+            else dwconv_fast_kernel<0><<<g, 256, smem, st>>>(q);
+            return check_launch("dwconv_fast_kernel");
+        }
+    }
     if ((d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_ACT) ||
         (epi->y_codes && epi->next_fmt != SLFP_FMT_SFP33 && epi->next_fmt != SLFP_FMT_SLFP34_ACT))
-        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): the stencil kernels read and write the signed code formats only");
+        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): the generic stencil kernels read and write the signed code formats only");
     const bool sfp = d->fmt == SLFP_FMT_SFP33;
     const bool depthwise = d->groups == d->c && d->k == d->c && (d->c_phys % 4) == 0 && (((uintptr_t)x_codes) & 3u) == 0;
     const size_t total = depthwise ? (size_t)d->n * p.Ho * p.Wo * (d->c_phys / 4) : (size_t)d->n * p.Ho * p.Wo * d->k;

@@ -200,7 +200,10 @@ class Plan:
         assert len(kds) <= 2
         kp = _ceil(K, 16)
         # post-ReLU codes: dense producer (the tcgen05 kernel with the TMA-im2col gather) ending in a ReLU
-        ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and groups == 1 and x.cp % 16 == 0) else self.afmt
+        depthwise = groups > 1 and groups == C == K
+        fast_dw = depthwise and relu and bn is not None and len(kds) == 1 and not f16 and not f32 and residual is None \
+            and x.cp % 16 == 0 and mod.bias is None
+        ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and x.cp % 16 == 0 and (groups == 1 or fast_dw)) else self.afmt
         for i, kd in enumerate(kds):
             t = self._alloc(x.n, Ho, Wo, K, "codes", kd, cp=kp, fmt=ofmt)
             out["codes"][kd] = t
@@ -499,8 +502,7 @@ def compile_mobilenetv1(model, batch, size, device="cuda", static_weights=False)
             cur = o["f16"]
         else:
             nk = _k32(layers[j + 1][0].Ka)
-            # the depthwise stencil kernel reads the signed code formats only
-            cur = P.conv(cur, conv, bn=bn, relu=True, codes=[nk], relu_codes=layers[j + 1][0].groups == 1)["codes"][nk]
+            cur = P.conv(cur, conv, bn=bn, relu=True, codes=[nk])["codes"][nk]
     if isinstance(pool, nn.AvgPool2d):
         assert cur.h == pool.kernel_size and cur.w == pool.kernel_size, "AvgPool2d(7) expects a 7x7 map (224x224 input)"
     feat = P.avgpool(cur)

@@ -250,6 +250,52 @@ def test_fused_block_tail_equals_two_convs(orc):
         assert (orc.decode_relu(cf_, False)[same] == orc.decode_relu(cs_, False)[same]).mean() > 0.995
 
 
+@pytest.mark.parametrize("qbit,stride,C,H", [(8, 1, 32, 20), (7, 2, 64, 19), (8, 1, 144, 7), (7, 1, 16, 3)])
+def test_depthwise_fused_kernels(orc, qbit, stride, C, H):
+    """Depthwise 3x3 through the fused-pipeline stencil kernels (strip-mined 3x3 and the per-pixel variant for
+    tiny maps): signed input codes -> folded affine + ReLU -> post-ReLU codes, against a float64 depthwise
+    convolution of the decoded operands pushed through the reference quantizer."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(40 + C)
+    N = 3
+    x = (rng.standard_normal((N, C, H, H)) * 2).astype(np.float32)
+    w = (rng.standard_normal((C, 1, 3, 3)) * 0.3).astype(np.float32)
+    ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+    afmt, wfmt = nv.fmt_for(qbit, "act"), nv.fmt_for(qbit, "weight")
+    xt = torch.from_numpy(x).to(dev).permute(0, 2, 3, 1).contiguous()
+    xc = torch.empty((N, H, H, C), dtype=torch.uint8, device=dev)
+    nv.check(lib.slfp_quantize_nhwc_f32(xt.data_ptr(), N * H * H, C, C, float(np.float32(ka)), afmt, xc.data_ptr(), nv.stream()))
+    d = nv.SlfpConvDesc(N, H, H, C, C, C, 3, 3, stride, stride, 1, 1, 1, 1, C, afmt)
+    wt = torch.from_numpy(w).to(dev)
+    wc = torch.empty((C * 9,), dtype=torch.uint8, device=dev)
+    nv.check(lib.slfp_prepare_weights(ctypes.byref(d), wt.data_ptr(), *wt.stride(), float(np.float32(kw)), wfmt, None, wc.data_ptr(), None,
+                                      nv.stream()))
+    Ho = (H + 2 - 3) // stride + 1
+    mul = (rng.uniform(0.5, 1.5, C) * np.float32(ka) * np.float32(kw)).astype(np.float32)
+    add = (rng.standard_normal(C) * 0.4).astype(np.float32)
+    mul_t, add_t = torch.from_numpy(mul).to(dev), torch.from_numpy(add).to(dev)
+    nk = 0.23
+    y = torch.full((N, Ho, Ho, C), 99, dtype=torch.uint8, device=dev)
+    e = nv.SlfpEpilogue()
+    e.ch_mul, e.ch_add, e.relu = mul_t.data_ptr(), add_t.data_ptr(), 1
+    e.y_codes, e.next_k_div, e.next_fmt, e.k_phys_out = y.data_ptr(), float(np.float32(nk)), nv.relu_fmt(afmt), C
+    nv.check(lib.slfp_conv2d_fwd(ctypes.byref(d), xc.data_ptr(), wc.data_ptr(), ctypes.byref(e), nv.stream()))
+    torch.cuda.synchronize()
+    _, xq = orc.quantize(x, 0 if qbit == 7 else 1, ka, want_codes=False)
+    _, wq = orc.quantize(w, 0 if qbit == 7 else 2, kw, want_codes=False)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(xq).double(), torch.from_numpy(wq).double(), None, stride, 1, 1, C).numpy()
+    yref = np.maximum(ref * mul[None, :, None, None].astype(np.float64) + add[None, :, None, None], 0).transpose(0, 2, 3, 1)
+    got = _h(orc.decode_relu(y.cpu().numpy(), qbit == 7))
+    q = yref / float(np.float32(nk))
+    ok = np.zeros(q.shape, bool)
+    for eps in (0.0, -3e-6, 3e-6):                   # float32 accumulation of 9 products + the epilogue's folded scale
+        _, want = orc.quantize((q * (1.0 + eps)).astype(np.float32), 0 if qbit == 7 else 1, want_codes=False)
+        ok |= got == _h(want)
+    assert ok.all(), int((~ok).sum())
+
+
 def test_maxpool_on_post_relu_codes(orc):
     from cnns_slfp_quantization_b200 import _native as nv
     lib = nv.lib()
