@@ -116,24 +116,28 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
             } else {
                 constexpr int F = FMT == SLFP_FMT_SFP44_OUT ? SLFP_FMT_SFP33 : FMT;
                 // common path: reciprocal division (exact inside the normal range) + the in-range encoder.  One
-                // group test sends the rare 4-element group to the general path: a NaN, or a dividend so small that
-                // only the true division classifies "zero" vs "tiny" correctly.
+                // group test sends the rare 4-element group to the general path: a NaN / Inf quotient, or a dividend so
+                // small that only the true division classifies "zero" vs "tiny" correctly.
                 float qv[4];
-                uint32_t amax = 0u, xmin = 0xffffffffu;
+                float nan_probe = 0.0f;                       // q * 0 accumulates to NaN iff a quotient is NaN or Inf (FMA pipe)
+                uint32_t xmin = 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     qv[i] = div_k_fused(xs[i], a.k_div);
-                    const uint32_t aq = __float_as_uint(qv[i]) & 0x7fffffffu;
-                    amax = aq > amax ? aq : amax;
+                    nan_probe = fmaf(qv[i], 0.0f, nan_probe);
                     const uint32_t ax1 = (__float_as_uint(xs[i]) & 0x7fffffffu) - 1u;      // +-0 -> 0xffffffff
                     xmin = ax1 < xmin ? ax1 : xmin;
                 }
-                if (amax > kBitsInf || xmin < 0x04000000u - 1u) {
+                if (nan_probe != nan_probe || xmin < 0x04000000u - 1u) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) c[i] = encode<F>(div_k(xs[i], a.k_div));
-                } else {
+                } else if (F == SLFP_FMT_SLFP34_WGT) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) c[i] = encode_inrange<F>(qv[i]);
+                } else {
+                    constexpr int FA = F == SLFP_FMT_SLFP34_WGT ? SLFP_FMT_SLFP34_ACT : F;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c[i] = encode_balanced<FA>(qv[i]);
                 }
                 if (FAKEQ || F16) {
 #pragma unroll

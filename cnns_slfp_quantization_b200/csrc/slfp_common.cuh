@@ -253,6 +253,49 @@ __host__ __device__ __forceinline__ uint32_t encode_inrange(float v) {
     return (a < kBits0625) ? low : (u | sg);
 }
 
+// The same encoder with its work split between the two CUDA-core pipes.  ALU (LOP3 / SHF / IMNMX / ISETP / SEL /
+// FMNMX) and FMA (FADD / FMUL / FFMA / IMAD) each issue one warp instruction per two cycles and sub-partition: an
+// integer-only encoder is ALU-bound at 64 lanes/clk/SM and holds the stand-alone quantizer at ~0.6 of the HBM
+// peak.  Here the mantissa rounding is a Veltkamp split on the FMA pipe - t = |v| (2^s + 1); hi = t - (t - |v|)
+// is |v| rounded to nearest-even at 23 - s mantissa bits, verified against the integer rounding for every
+// mantissa - and the sign / bias arithmetic are IMADs.  Domain: v not NaN (Inf is fine: it is clamped first).
+template <int FMT>
+__host__ __device__ __forceinline__ uint32_t encode_balanced(float v) {
+    static_assert(FMT == SLFP_FMT_SFP33 || FMT == SLFP_FMT_SLFP34_ACT, "activation formats");
+    const uint32_t b = f2u(v);
+    const float av = fabsf(v);
+    const uint32_t sbit = b >> 31;
+    uint32_t u;
+    float avc;
+    if (FMT == SLFP_FMT_SFP33) {
+        avc = av < 15.0f ? av : 15.0f;                                // a >= 15 -> 15 (:29 / :77); also tames Inf
+        const float t = avc * 1048577.0f;                              // 2^20 + 1
+        const float d = t - avc;
+        const float hi = t - d;                                        // round-half-even at 3 mantissa bits
+        u = (f2u(hi) >> 20) - ((127u - 4u) << 3);
+        u = (int32_t)u < 8 ? 8u : u;                                   // [0.0625, 0.125) -> 0.125
+    } else {
+        avc = av < 16.0f ? av : 16.0f;                                 // keeps the split finite; saturation is decided on av
+        const float t = avc * 524289.0f;                               // 2^19 + 1
+        const float d = t - avc;
+        const float hi = t - d;                                        // round-half-even of 16 m (:88)
+        const uint32_t tt = f2u(hi) >> 19;                             // (exponent << 4) | i, i = 16 carried
+#ifdef __CUDA_ARCH__
+        const uint32_t corr = __funnelshift_r(0x7ffc7ffcu, 0u, tt) & 1u;   // log converter (:89): +1 for 2 <= i <= 14
+#else
+        const uint32_t corr = (0x7ffc7ffcu >> (tt & 31u)) & 1u;
+#endif
+        u = tt + corr - ((127u - 4u) << 4);
+        u = (int32_t)u < 16 ? 16u : u;
+        u = (f2u(av) > kBitsSat8) ? kCodeSat : u;                      // a > 15.32165 (and Inf) -> the literal (:95)
+    }
+    const uint32_t a = f2u(avc);
+    const uint32_t z = a < 1u ? a : 1u;                                // 0 for +-0, else 1
+    const uint32_t hi_code = sbit * 128u + u;
+    const uint32_t lo_code = (z * sbit) * 128u + z;                    // +-0 -> 0 (sign dropped), tiny -> 1 | sign
+    return (a < kBits0625) ? lo_code : hi_code;
+}
+
 __host__ __device__ __forceinline__ uint32_t encode_rt(float v, int fmt) {
     if (fmt == SLFP_FMT_SFP33) return encode<SLFP_FMT_SFP33>(v);
     if (fmt == SLFP_FMT_SLFP34_ACT) return encode<SLFP_FMT_SLFP34_ACT>(v);

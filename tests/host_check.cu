@@ -90,3 +90,14 @@ extern "C" size_t hostcheck_encode_inrange_mismatches(const float* v, size_t n, 
     }
     return bad;
 }
+
+// encode_balanced<FMT>(v) against encode<FMT>(v); returns the mismatch count
+extern "C" size_t hostcheck_encode_balanced_mismatches(const float* v, size_t n, int fmt) {
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t a = fmt == SLFP_FMT_SFP33 ? encode_balanced<SLFP_FMT_SFP33>(v[i]) : encode_balanced<SLFP_FMT_SLFP34_ACT>(v[i]);
+        const uint32_t b = fmt == SLFP_FMT_SFP33 ? encode<SLFP_FMT_SFP33>(v[i]) : encode<SLFP_FMT_SLFP34_ACT>(v[i]);
+        bad += a != b;
+    }
+    return bad;
+}

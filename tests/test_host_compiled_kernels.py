@@ -116,3 +116,19 @@ def test_fast_encoder_equals_reference_encoder(hostcheck, fmt):
             assert bad == 0, (fmt, e, sgn, bad)
     v = np.array([15.0, 15.32165, 15.5, 1e30, np.inf, -np.inf, 3e38, 0.0, -0.0, 1e-45, -1e-45], np.float32)   # everything but NaN
     assert hostcheck.hostcheck_encode_inrange_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), fmt) == 0
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_pipe_balanced_encoder_equals_reference_encoder(hostcheck, fmt):
+    """encode_balanced<FMT> (Veltkamp-split rounding on the FMA pipe + IMAD sign / bias arithmetic) == encode<FMT>
+    for every float32 mantissa, both signs, exponents from denormals past the saturation thresholds, and Inf."""
+    hostcheck.hostcheck_encode_balanced_mismatches.restype = ctypes.c_size_t
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    for e in [0, 1, 60, 100, 118, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 140, 200, 254]:
+        x = (mant | np.uint32(e << 23)).view(np.float32)
+        for sgn in (1.0, -1.0):
+            v = np.ascontiguousarray(x * np.float32(sgn))
+            bad = hostcheck.hostcheck_encode_balanced_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), ctypes.c_int(fmt))
+            assert bad == 0, (fmt, e, sgn, bad)
+    v = np.array([15.0, 15.32165, 15.5, 16.0, 1e30, np.inf, -np.inf, 3e38, 0.0, -0.0, 1e-45, -1e-45, 0.0625, 0.125, -0.0625], np.float32)
+    assert hostcheck.hostcheck_encode_balanced_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), fmt) == 0
