@@ -23,6 +23,7 @@
 #include <cudaTypedefs.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include "slfp_common.cuh"
 #include "sm100_ptx.cuh"
@@ -71,7 +72,7 @@ struct Params {
     float sc1, sc2;             // rk / 16 (fast paths quantize clamp(q/16, 0, 1))
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STG = false>
 struct Cfg {
     // BLOCK_N <= 128: the decoded A tile goes to TENSOR memory (tcgen05.st; the MMA reads A from TMEM), which takes
     // the A tile's write (16 KB) and the MMA's read of it (16 KB) per K block off the shared-memory pipe - the
@@ -82,12 +83,16 @@ struct Cfg {
     // Ring depths.  The code tiles and weight tiles arrive through TMA with ~1.5-2 us of latency under load; the
     // first version's 4 x 8 KB of codes in flight per SM left the decode warps waiting on the code barrier most
     // of the time (profiles/r01_conv_v2.md).  With A in TMEM the freed shared memory deepens both rings.
-    static constexpr int kStages = BLOCK_N >= 256 ? 3 : 4;          // weight (and A) stages
-    static constexpr int kCodeStages = BLOCK_N >= 256 ? 5 : 6;
+    static constexpr int kStages = (BLOCK_N >= 256 || STG) ? 3 : 4;          // weight (and A) stages
+    static constexpr int kCodeStages = (BLOCK_N >= 256 || STG) ? 5 : 6;
+    // STG: the epilogue's global traffic goes through shared-memory staging + TMA (see the staged epilogue below):
+    // two float16 [128 x BLOCK_N] buffers (residual in / float16 out, in place) and two code tiles.
+    static constexpr int kIoBytes = kBM * BLOCK_N * 2, kCoBytes = kBM * BLOCK_N;
+    static constexpr int kStageBytes = STG ? 2 * kIoBytes + 2 * kCoBytes : 0;
     static constexpr int kATmemCol = 2 * BLOCK_N;           // first TMEM column of the A ring (32 columns per stage)
     static constexpr int kTmemCols = kATmem ? (2 * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
     static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
-    static constexpr int kSmemBytes = kStages * ((kATmem ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kLutBytes + kParBytes + 1024;
+    static constexpr int kSmemBytes = kStages * ((kATmem ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kStageBytes + kLutBytes + kParBytes + 1024;
 };
 
 // ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
@@ -539,11 +544,18 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
     }
 }
 
-template <int BLOCK_N, int GRAN, int DW>
+// The four output-side tensor maps (residual, float16 output, two code outputs; [M, Kout] matrices, boxes of
+// 128 rows x BLOCK_N/4 columns) are only dereferenced by the STG instantiation.
+struct OutMaps {
+    CUtensorMap res, y16, c1, c2;
+};
+
+template <int BLOCK_N, int GRAN, int DW, bool STG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                     const __grid_constant__ CUtensorMap tmap_x2, const Params p) {
-    using C = Cfg<BLOCK_N>;
+                     const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ OutMaps omaps, const Params p) {
+    using C = Cfg<BLOCK_N, STG>;
+    static_assert(!STG || (BLOCK_N == 128 && DW == 8 && GRAN == 64), "staged epilogue: 128-column tiles, 16 epilogue warps");
     using R = Roles<DW>;
     constexpr int kCodeStages = C::kCodeStages;
     constexpr int kDecWarps = R::kDecWarps, kEpiWarps = R::kEpiWarps, kEpiWarp0 = R::kEpiWarp0, kGroups = R::kGroups;
@@ -555,7 +567,8 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     uint8_t* s_a = smem;                                   // [stages][128 rows][128 B]   (absent when A lives in TMEM)
     uint8_t* s_b = s_a + (C::kATmem ? 0 : C::kStages * kABytes);   // [stages][BLOCK_N rows][128 B]
     uint8_t* s_code = s_b + C::kStages * C::kBBytes;       // [kCodeStages][128 pixels][64 B]
-    uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_code + kCodeStages * kCodeBytes);
+    uint8_t* s_stage = s_code + kCodeStages * kCodeBytes;  // STG: [2][4 groups][128][64 B] float16 + [2][4][128][32 B] codes
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stage + C::kStageBytes);
     float* s_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_lut) + kLutBytes);   // [2][BLOCK_N]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + C::kParBytes);
     uint64_t* bar_cfull = s_bar;                           // [kCodeStages]  1 arrive.expect_tx
@@ -564,7 +577,8 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     uint64_t* bar_empty = bar_full + C::kStages;           // [stages]  1 tcgen05.commit
     uint64_t* bar_tfull = bar_empty + C::kStages;          // [2]       1 tcgen05.commit
     uint64_t* bar_tempty = bar_tfull + 2;                  // [2]       8 epilogue warps
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    uint64_t* bar_res = bar_tempty + 2;                    // [4 groups][2]  STG: residual slab landed (1 arrive.expect_tx)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_res + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();     // would break the swizzle: fail loudly, never silently
@@ -590,6 +604,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             ptx::mbar_init(ptx::smem_u32(&bar_tfull[b]), 1);
             ptx::mbar_init(ptx::smem_u32(&bar_tempty[b]), kEpiWarps);
         }
+        for (int b = 0; b < 8; ++b) ptx::mbar_init(ptx::smem_u32(&bar_res[b]), 1);
         ptx::fence_mbar_init();
     }
     if (warp == kWarpMma) ptx::tmem_alloc<C::kTmemCols>(ptx::smem_u32(s_tmem));
@@ -814,6 +829,128 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_tempty[(uint32_t)ti & 1u]));
         };
+        if constexpr (STG) {
+            // ---- staged epilogue (mode 2 only): every global access of the epilogue is a TMA transfer ----------
+            // A thread owns one output pixel (TMEM lane = row), so direct loads / stores touch 32 different rows per
+            // instruction and the block tails (float16 residual in, float16 + codes out) were bound by L1TEX
+            // wavefronts, not by HBM (profiles/r01_conv_v2.md).  Here each column group (4 warps = 128 rows x 32
+            // columns) owns private staging slabs: the residual slab arrives by TMA one tile ahead (double
+            // buffered), is updated IN PLACE to the float16 output and leaves by TMA store together with the code
+            // slabs.  Swizzled slabs (64 B rows: chunk ^= (row >> 1) & 3; 32 B rows: chunk ^= (row >> 2) & 1) keep
+            // the per-row 16-byte shared accesses conflict free.  Rows >= M and columns >= Kout are clipped by TMA.
+            const int cg = half;
+            const int r = quad * 32 + lane;
+            const bool leader = quad == 0 && lane == 0;
+            const bool has_res = p.epi.residual != nullptr, has_y16 = p.epi.y_f16 != nullptr;
+            const bool has_c1 = p.epi.y_codes != nullptr, has_c2 = p.epi.y_codes2 != nullptr;
+            constexpr int kSlabIo = kBM * 64, kSlabCo = kBM * 32;                     // bytes per group slab
+            const uint32_t io0 = ptx::smem_u32(s_stage) + (uint32_t)(cg * kSlabIo);   // buffer b at + b * kIoBytes
+            const uint32_t co1 = ptx::smem_u32(s_stage) + 2u * C::kIoBytes + (uint32_t)(cg * kSlabCo);
+            const uint32_t co2 = co1 + C::kCoBytes;
+            const uint32_t io_t = (uint32_t)(r * 64), sw64 = (uint32_t)((r >> 1) & 3);
+            const uint32_t co_t = (uint32_t)(r * 32), sw32 = (uint32_t)((r >> 2) & 1);
+            const uint32_t bres = ptx::smem_u32(&bar_res[cg * 2]);
+            const float sc1 = p.sc1, sc2 = p.sc2;
+            const uint32_t enc_sh = sfp33 ? 19u : 18u;
+            const int32_t enc_base = sfp33 ? 0x76F : 0xEDF;
+            uint32_t res_phase = 0u;                                                   // bit b: parity of buffer b's next landing
+            auto slab_chunks = [&](int tile) -> int {
+                const int left = (p.Kout - ((tile % p.n_tiles) * BLOCK_N + cg * 32)) >> 4;
+                return left > 2 ? 2 : (left < 0 ? 0 : left);
+            };
+            auto load_res = [&](int tile, uint32_t buf) {
+                if (!has_res || slab_chunks(tile) == 0) return;
+                ptx::mbar_arrive_expect_tx(bres + buf * 8u, (uint32_t)kSlabIo);
+                ptx::tma_load_2d(io0 + buf * C::kIoBytes, &omaps.res, bres + buf * 8u, (tile % p.n_tiles) * BLOCK_N + cg * 32,
+                                 (tile / p.n_tiles) * kBM);
+            };
+            if (leader && my_tiles > 0) load_res((int)blockIdx.x, 0u);
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const uint32_t buf = (uint32_t)ti & 1u;
+                const uint32_t tacc = tile_begin(ti, tile);
+                const int nvalid = slab_chunks(tile);                               // group-uniform
+                const uint32_t io = io0 + buf * C::kIoBytes + io_t;
+                if (nvalid > 0) {
+                    if (has_res) {
+                        ptx::mbar_wait(bres + buf * 8u, (res_phase >> buf) & 1u, 8u | ((uint32_t)ti << 16));
+                        res_phase ^= 1u << buf;
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        if (ch >= nvalid) break;
+                        uint32_t acc[16];
+                        ptx::tmem_ld16(tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32 + ch * 16), acc);
+                        const uint32_t ioa = io + (((uint32_t)(2 * ch) ^ sw64) << 4), iob = io + (((uint32_t)(2 * ch + 1) ^ sw64) << 4);
+                        uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+                        if (has_res) { ra = ptx::lds128_volatile(ioa); rb = ptx::lds128_volatile(iob); }
+                        ptx::tmem_ld_wait();
+                        float v[16];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 m4 = ptx::lds128_f4(s_mul + (uint32_t)(cg * 32 + ch * 16 + 4 * g) * 4u);
+                            const float4 a4 = ptx::lds128_f4(s_add + (uint32_t)(cg * 32 + ch * 16 + 4 * g) * 4u);
+                            v[4 * g + 0] = fmaf(__uint_as_float(acc[4 * g + 0]), m4.x, a4.x);
+                            v[4 * g + 1] = fmaf(__uint_as_float(acc[4 * g + 1]), m4.y, a4.y);
+                            v[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), m4.z, a4.z);
+                            v[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), m4.w, a4.w);
+                        }
+                        if (has_res) {
+                            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                                v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                            }
+                        }
+                        if (ch == 0) {
+                            // the previous tile's stores must have drained the staging slabs before anything is
+                            // written; the same moment frees the other float16 buffer for the next tile's residual
+                            if (leader) {
+                                ptx::bulk_wait_read0();
+                                if (ti + 1 < my_tiles) load_res(tile + (int)gridDim.x, buf ^ 1u);
+                            }
+                            ptx::bar_sync(2 + cg, 128);
+                        }
+                        if (has_y16) {
+                            uint32_t hw[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __half2 h = __floats2half2_rn(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f));
+                                hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            ptx::sts128(ioa, hw[0], hw[1], hw[2], hw[3]);
+                            ptx::sts128(iob, hw[4], hw[5], hw[6], hw[7]);
+                        }
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            if (!(pass ? has_c2 : has_c1)) continue;
+                            const float sc = pass ? sc2 : sc1;
+                            int32_t t[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)      // encode_relu_fast_raw16 with run-time format constants
+                                t[i] = (int32_t)(__float_as_uint(__saturatef(v[i] * sc)) >> enc_sh) - enc_base;
+                            ptx::sts128((pass ? co2 : co1) + co_t + (((uint32_t)ch ^ sw32) << 4), ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]),
+                                        ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]), ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]),
+                                        ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+                        }
+                    }
+                }
+                tile_end(ti);
+                if (nvalid > 0) {
+                    ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
+                    ptx::bar_sync(2 + cg, 128);
+                    if (leader) {
+                        const int c0 = (tile % p.n_tiles) * BLOCK_N + cg * 32, r0 = (tile / p.n_tiles) * kBM;
+                        if (has_y16) ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes, c0, r0);
+                        if (has_c1) ptx::tma_store_2d(&omaps.c1, co1, c0, r0);
+                        if (has_c2) ptx::tma_store_2d(&omaps.c2, co2, c0, r0);
+                        ptx::bulk_commit();
+                    }
+                }
+            }
+            if (leader) ptx::bulk_wait0();
+        } else
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const int next_tile = ti + 1 < my_tiles ? tile + (int)gridDim.x : p.num_tiles;
@@ -863,10 +1000,10 @@ static PFN driver_fn(const char* name) {
     return nullptr;
 }
 
-template <int BLOCK_N, int GRAN, int DW>
-static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const Params& p, cudaStream_t st) {
-    using C = Cfg<BLOCK_N>;
-    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW>;
+template <int BLOCK_N, int GRAN, int DW, bool STG = false>
+static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const OutMaps& om, const Params& p, cudaStream_t st) {
+    using C = Cfg<BLOCK_N, STG>;
+    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -874,7 +1011,7 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMa
         attr_done = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, tx2, p);
+    kern<<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, tx2, om, p);
     return check_launch("conv_igemm_v2_kernel");
 }
 
@@ -950,10 +1087,6 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     p.num_kb = (int)(pitch / kBK);
     p.cblocks = (d->c_phys % 64 == 0) ? d->c_phys / 64 : 0;
     p.c16s = d->c_phys / 16;
-    const int bn = d->k > 128 ? 256 : (d->k > 64 ? 128 : 64);
-    p.m_tiles = (int)((p.M + kBM - 1) / kBM);
-    p.n_tiles = (d->k + bn - 1) / bn;
-    p.num_tiles = p.m_tiles * p.n_tiles;
     p.act_fmt = d->fmt;
     p.epi = *epi;
     p.next_div = make_divk(epi->y_codes ? epi->next_k_div : 1.0f);
@@ -972,6 +1105,14 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
                             (!epi->residual || epi->residual_f16);
         if (common) p.epi_mode = (epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->residual) ? 1 : 2;
     }
+    // Staged (TMA) epilogue for the epilogue-bound mode-2 layers (block tails, short-K fused tails): 128-column tiles.
+    static const int stg_max_kb = getenv("SLFP_STG_MAXKB") ? atoi(getenv("SLFP_STG_MAXKB")) : 8;
+    const bool stg = p.epi_mode == 2 && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
+                     (((uintptr_t)epi->residual) & 15u) == 0;
+    const int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
+    p.m_tiles = (int)((p.M + kBM - 1) / kBM);
+    p.n_tiles = (d->k + bn - 1) / bn;
+    p.num_tiles = p.m_tiles * p.n_tiles;
 
     CUtensorMap tmap_x2;
     static auto enc_tiled = driver_fn<PFN_cuTensorMapEncodeTiled_v12000>("cuTensorMapEncodeTiled");
@@ -1036,10 +1177,30 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd_dual: cuTensorMapEncodeIm2col failed (%d)", (int)cr);
     }
+    OutMaps om;
+    memset(&om, 0, sizeof(om));
+    if (stg) {
+        auto out_map = [&](CUtensorMap* m, const void* ptr, bool f16) -> bool {
+            const cuuint64_t gdim[2] = {(cuuint64_t)d->k, (cuuint64_t)p.M};
+            const cuuint64_t gstr[1] = {(cuuint64_t)d->k * (f16 ? 2u : 1u)};
+            const cuuint32_t box[2] = {32u, (cuuint32_t)kBM};
+            const cuuint32_t estr[2] = {1, 1};
+            return enc_tiled(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstr,
+                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        bool ok = true;
+        if (epi->residual) ok = ok && out_map(&om.res, epi->residual, true);
+        if (epi->y_f16) ok = ok && out_map(&om.y16, epi->y_f16, true);
+        if (epi->y_codes) ok = ok && out_map(&om.c1, epi->y_codes, false);
+        if (epi->y_codes2) ok = ok && out_map(&om.c2, epi->y_codes2, false);
+        if (!ok) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled(outputs) failed");
+        return launch<128, 64, 8, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
+    }
 #define SLFP_V2_CASE(BN)                                                                                         \
     if (bn == BN) {                                                                                              \
-        if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, tmap_x2, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, tmap_x2, p, st); \
-        return epi_heavy ? launch<BN, 16, 8>(tmap_x, tmap_w, tmap_x2, p, st) : launch<BN, 16, 16>(tmap_x, tmap_w, tmap_x2, p, st);  \
+        if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, tmap_x2, om, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, tmap_x2, om, p, st); \
+        return epi_heavy ? launch<BN, 16, 8>(tmap_x, tmap_w, tmap_x2, om, p, st) : launch<BN, 16, 16>(tmap_x, tmap_w, tmap_x2, om, p, st);  \
     }
     SLFP_V2_CASE(64)
     SLFP_V2_CASE(128)
