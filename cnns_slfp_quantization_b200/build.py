@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("SLFP_EXTRA_NVCC_FLAGS", "").split() + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

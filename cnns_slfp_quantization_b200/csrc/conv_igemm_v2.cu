@@ -28,6 +28,19 @@
 #include "slfp_common.cuh"
 #include "sm100_ptx.cuh"
 
+// Role profiler (build with -DSLFP_ROLE_PROFILE, tools/role_profile.py): clock64() around the pipeline waits of
+// each role's lead thread, summed over CTAs into the slfp_debug_set_buffer() array from word 8 on.
+#ifdef SLFP_ROLE_PROFILE
+#define PROF_VARS unsigned long long prof_a = 0, prof_b = 0, prof_c = 0; const long long prof_t0 = clock64()
+#define PROF(n, ...) { const long long prof_t = clock64(); __VA_ARGS__; prof_##n += (unsigned long long)(clock64() - prof_t); }
+#define PROF_FLUSH(slot) if (ptx::g_slfp_dbg) { atomicAdd(ptx::g_slfp_dbg + (slot), prof_a); atomicAdd(ptx::g_slfp_dbg + (slot) + 1, prof_b); \
+        atomicAdd(ptx::g_slfp_dbg + (slot) + 2, prof_c); atomicAdd(ptx::g_slfp_dbg + (slot) + 3, (unsigned long long)(clock64() - prof_t0)); }
+#else
+#define PROF_VARS
+#define PROF(n, ...) { __VA_ARGS__; }
+#define PROF_FLUSH(slot)
+#endif
+
 namespace slfp {
 namespace v2 {
 
@@ -580,7 +593,9 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     uint64_t* bar_res = bar_tempty + 2;                    // [4 groups][2]  STG: residual slab landed (1 arrive.expect_tx)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_res + 8);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so role branches, barrier addresses and
+    // the tcgen05 operands stay in uniform registers (no per-lane waterfall loops around UTCHMMA / UTCBAR)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();     // would break the swizzle: fail loudly, never silently
 
     // ---- one-time setup ---------------------------------------------------------------------------
@@ -623,6 +638,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
       if (warp == kWarpCode) {
         // =========================== code producer: TMA im2col ===========================================
         if (lane == 0) {
+            PROF_VARS;
             uint32_t cs = 0, cphase = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -633,7 +649,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int w0 = wo * p.sw - p.pw, h0 = ho * p.sh - p.ph;
                 int tap = 0, r = 0, s = 0, cb = 0;       // GRAN 64: cb = 64-channel block; GRAN 16: 16-channel block
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
+                    PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                     const uint32_t full = ptx::smem_u32(&bar_cfull[cs]);
                     const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
                     if (GRAN == 64) {
@@ -656,56 +672,75 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
                 }
             }
+            PROF_FLUSH(8);
         }
         __syncwarp();
     } else if (warp == kWarpWgt) {
         // =========================== weight producer: TMA tiles (B operand) ================================
         if (lane == 0) {
+            PROF_VARS;
             uint32_t stage = 0, phase = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const int n0 = (tile % p.n_tiles) * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
+                    PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                     const uint32_t full = ptx::smem_u32(&bar_full[stage]);
                     ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
                     ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
                     if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
+            PROF_FLUSH(12);
         }
         __syncwarp();
     } else if (warp == kWarpMma) {
         // =========================== MMA issuer ===================================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc(0u, kBM, BLOCK_N);
-            uint32_t stage = 0, phase = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const uint32_t buf = (uint32_t)ti & 1u;
-                ptx::mbar_wait(ptx::smem_u32(&bar_tempty[buf]), (((uint32_t)ti >> 1) & 1u) ^ 1u, 3u | ((uint32_t)ti << 16));
+        // The whole warp runs the loop converged and ONE elected lane issues: with 7 warps per scheduler every
+        // instruction of this warp waits its turn, and the per-lane form (divergent `lane == 0` branch: R2UR moves,
+        // an ELECT waterfall loop around every tcgen05 instruction, descriptors rebuilt per MMA; ~75 instructions
+        // per K block) made this thread the slowest stage of the pipeline - 51 % of its life between the first MMA
+        // and the commit of a K block (tools/role_profile.py).  Descriptors differ only in their low word.
+        constexpr uint32_t idesc = ptx::make_idesc(0u, kBM, BLOCK_N);
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+        const uint32_t a_lo0 = ((ptx::smem_u32(s_a) >> 4) & 0x3fffu) | (1u << 16);
+        const uint32_t b_lo0 = ((ptx::smem_u32(s_b) >> 4) & 0x3fffu) | (1u << 16);
+        PROF_VARS;
+        uint32_t stage = 0, phase = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const uint32_t buf = (uint32_t)ti & 1u;
+            PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_tempty[buf]), (((uint32_t)ti >> 1) & 1u) ^ 1u, 3u | ((uint32_t)ti << 16)));
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                PROF(b, ptx::mbar_wait(ptx::smem_u32(&bar_full[stage]), phase, 4u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait(ptx::smem_u32(&bar_full[stage]), phase, 4u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16));
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(s_a + stage * kABytes);
-                    const uint32_t b_addr = ptx::smem_u32(s_b + stage * C::kBBytes);
+#ifdef SLFP_ROLE_PROFILE
+                const long long prof_t = clock64();
+#endif
+                if (ptx::elect_one()) {
+                    const uint32_t a_lo = a_lo0 + stage * (uint32_t)(kABytes >> 4);
+                    const uint32_t b_lo = b_lo0 + stage * (uint32_t)(C::kBBytes >> 4);
                     const uint32_t a_tmem = tmem_base + (uint32_t)C::kATmemCol + stage * 32u;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + 2u * k);
                         if (C::kATmem)
-                            ptx::mma_f16_ts(d_tmem, a_tmem + k * 8, ptx::smem_desc_sw128(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            ptx::mma_f16_ts(d_tmem, a_tmem + k * 8, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         else
-                            ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a_addr + k * 32), ptx::smem_desc_sw128(b_addr + k * 32),
-                                            idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            ptx::mma_f16_ss(d_tmem, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * k), bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    ptx::mma_commit(ptx::smem_u32(&bar_empty[stage]));     // frees the smem stage
-                    if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
+                    ptx::mma_commit(ptx::smem_u32(&bar_empty[stage]));     // frees the stage
+                    if (kb == p.num_kb - 1) ptx::mma_commit(ptx::smem_u32(&bar_tfull[buf]));   // accumulator ready
                 }
-                ptx::mma_commit(ptx::smem_u32(&bar_tfull[buf]));            // accumulator ready
+                __syncwarp();
+#ifdef SLFP_ROLE_PROFILE
+                prof_c += (unsigned long long)(clock64() - prof_t);
+#endif
+                if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
             }
         }
-        __syncwarp();
+        if (lane == 0) { PROF_FLUSH(16); }
       }
     } else if (warp < kDecWarp0 + kDecWarps) {
         ptx::setmaxnreg_dec<R::kRegsDec>();
@@ -742,12 +777,16 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const uint32_t a_tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)C::kATmemCol;
         const int k16_total = p.taps * p.c16s;
         const int total_kb = my_tiles * p.num_kb;
+        PROF_VARS;
         int kb = grp % p.num_kb;                                // K block index inside its tile (for the K-padding test)
         for (int it = grp; it < total_kb; it += kDecGroups) {
             const uint32_t cs = (uint32_t)it % (uint32_t)kCodeStages, cphase = ((uint32_t)it / (uint32_t)kCodeStages) & 1u;
             const uint32_t stage = (uint32_t)it % (uint32_t)C::kStages, phase = ((uint32_t)it / (uint32_t)C::kStages) & 1u;
-            ptx::mbar_wait(ptx::smem_u32(&bar_cfull[cs]), cphase, 5u | ((uint32_t)it << 8));
-            ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 6u | ((uint32_t)it << 8));   // MMA done with this A stage
+            PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_cfull[cs]), cphase, 5u | ((uint32_t)it << 8)));
+            PROF(b, ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 6u | ((uint32_t)it << 8)));   // MMA done with this A stage
+#ifdef SLFP_ROLE_PROFILE
+            const long long prof_t = clock64();
+#endif
             if (C::kATmem) ptx::tc_fence_after();
             const uint32_t a_dst = a_base + stage * kABytes;
 #pragma unroll
@@ -791,7 +830,11 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
             kb += kDecGroups;
             while (kb >= p.num_kb) kb -= p.num_kb;
+#ifdef SLFP_ROLE_PROFILE
+            prof_c += (unsigned long long)(clock64() - prof_t);
+#endif
         }
+        if (warp == kDecWarp0 && lane == 0) { PROF_FLUSH(20); }
     } else {
         ptx::setmaxnreg_inc<R::kRegsEpi>();
         // =========================== epilogue ===================================================================
@@ -802,10 +845,11 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const bool sfp33 = p.epi.next_fmt == SLFP_FMT_SFP33_RELU;
         const uint32_t s_mul = ptx::smem_u32(s_par), s_add = s_mul + BLOCK_N * 4;
         int staged_n0 = -1;
+        PROF_VARS;
         // per tile: stage the per-channel vectors when the channel tile changes, then wait for the accumulator
         auto tile_begin = [&](int ti, int tile) -> uint32_t {
             const uint32_t buf = (uint32_t)ti & 1u;
-            if (mode != 0) {
+            if (!STG && mode != 0) {
                 // the fast modes read the folded affine from shared memory (mode 1: pre-scaled by 1/(16 Ka_next))
                 const int n_tile0 = (tile % p.n_tiles) * BLOCK_N;
                 if (n_tile0 != staged_n0) {
@@ -820,7 +864,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     staged_n0 = n_tile0;
                 }
             }
-            ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u, 64, 7u | ((uint32_t)ti << 16));
+            PROF(a, ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u, 64, 7u | ((uint32_t)ti << 16)));
             ptx::tc_fence_after();
             return tmem_base + buf * BLOCK_N;
         };
@@ -872,28 +916,36 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int nvalid = slab_chunks(tile);                               // group-uniform
                 const uint32_t io = io0 + buf * C::kIoBytes + io_t;
                 if (nvalid > 0) {
+                    // both 16-column chunks of the slab leave TMEM at once; the accumulator buffer is released
+                    // before any arithmetic
+                    uint32_t acc[2][16];
+                    const uint32_t tcol = tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32);
+                    ptx::tmem_ld16(tcol, acc[0]);
+                    if (nvalid > 1) ptx::tmem_ld16(tcol + 16u, acc[1]);
                     if (has_res) {
                         ptx::mbar_wait(bres + buf * 8u, (res_phase >> buf) & 1u, 8u | ((uint32_t)ti << 16));
                         res_phase ^= 1u << buf;
                     }
+                    const int n_slab = (tile % p.n_tiles) * BLOCK_N + cg * 32;
+                    ptx::tmem_ld_wait();
+                    tile_end(ti);
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
                         if (ch >= nvalid) break;
-                        uint32_t acc[16];
-                        ptx::tmem_ld16(tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32 + ch * 16), acc);
                         const uint32_t ioa = io + (((uint32_t)(2 * ch) ^ sw64) << 4), iob = io + (((uint32_t)(2 * ch + 1) ^ sw64) << 4);
                         uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
                         if (has_res) { ra = ptx::lds128_volatile(ioa); rb = ptx::lds128_volatile(iob); }
-                        ptx::tmem_ld_wait();
                         float v[16];
+                        // per-channel affine: warp-uniform 16-byte loads (L1 broadcast; L1TEX is idle in this variant)
+                        const float4* mp = reinterpret_cast<const float4*>(p.epi.ch_mul + n_slab + ch * 16);
+                        const float4* ap = reinterpret_cast<const float4*>(p.epi.ch_add + n_slab + ch * 16);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            const float4 m4 = ptx::lds128_f4(s_mul + (uint32_t)(cg * 32 + ch * 16 + 4 * g) * 4u);
-                            const float4 a4 = ptx::lds128_f4(s_add + (uint32_t)(cg * 32 + ch * 16 + 4 * g) * 4u);
-                            v[4 * g + 0] = fmaf(__uint_as_float(acc[4 * g + 0]), m4.x, a4.x);
-                            v[4 * g + 1] = fmaf(__uint_as_float(acc[4 * g + 1]), m4.y, a4.y);
-                            v[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), m4.z, a4.z);
-                            v[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), m4.w, a4.w);
+                            const float4 m4 = __ldg(mp + g), a4 = __ldg(ap + g);
+                            v[4 * g + 0] = fmaf(__uint_as_float(acc[ch][4 * g + 0]), m4.x, a4.x);
+                            v[4 * g + 1] = fmaf(__uint_as_float(acc[ch][4 * g + 1]), m4.y, a4.y);
+                            v[4 * g + 2] = fmaf(__uint_as_float(acc[ch][4 * g + 2]), m4.z, a4.z);
+                            v[4 * g + 3] = fmaf(__uint_as_float(acc[ch][4 * g + 3]), m4.w, a4.w);
                         }
                         if (has_res) {
                             const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -915,10 +967,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         if (has_y16) {
                             uint32_t hw[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const __half2 h = __floats2half2_rn(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f));
-                                hw[i] = *reinterpret_cast<const uint32_t*>(&h);
-                            }
+                            for (int i = 0; i < 8; ++i) hw[i] = ptx::pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
                             ptx::sts128(ioa, hw[0], hw[1], hw[2], hw[3]);
                             ptx::sts128(iob, hw[4], hw[5], hw[6], hw[7]);
                         }
@@ -935,8 +984,9 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                                         ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
                         }
                     }
+                } else {
+                    tile_end(ti);
                 }
-                tile_end(ti);
                 if (nvalid > 0) {
                     ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
                     ptx::bar_sync(2 + cg, 128);
@@ -978,6 +1028,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             }
             tile_end(ti);
         }
+        if (warp == kEpiWarp0 && lane == 0) { PROF_FLUSH(24); }
     }
 
     // ---- teardown ---------------------------------------------------------------------------------

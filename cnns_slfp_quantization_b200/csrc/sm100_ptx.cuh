@@ -206,6 +206,12 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
         : "memory");
 }
 
+// {relu(lo), relu(hi)} -> packed float16 pair, round to nearest even, in one instruction
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 // four int32 -> four bytes, each saturated to [0, 255]; a lands in byte 0
 __device__ __forceinline__ uint32_t pack_sat_u8x4(int32_t a, int32_t b, int32_t c, int32_t d) {
     uint32_t r;
