@@ -558,7 +558,7 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
 }
 
 // The four output-side tensor maps (residual, float16 output, two code outputs; [M, Kout] matrices, boxes of
-// 128 rows x BLOCK_N/4 columns) are only dereferenced by the STG instantiation.
+// 128 rows x 128 bytes) are only dereferenced by the STG instantiation.
 struct OutMaps {
     CUtensorMap res, y16, c1, c2;
 };
@@ -590,7 +590,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     uint64_t* bar_empty = bar_full + C::kStages;           // [stages]  1 tcgen05.commit
     uint64_t* bar_tfull = bar_empty + C::kStages;          // [2]       1 tcgen05.commit
     uint64_t* bar_tempty = bar_tfull + 2;                  // [2]       8 epilogue warps
-    uint64_t* bar_res = bar_tempty + 2;                    // [4 groups][2]  STG: residual slab landed (1 arrive.expect_tx)
+    uint64_t* bar_res = bar_tempty + 2;                    // [2]  STG: residual tile landed (1 arrive.expect_tx); 8 words reserved
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_res + 8);
 
     // warp index through a shuffle: tells the compiler it is warp-uniform, so role branches, barrier addresses and
@@ -877,65 +877,61 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             // ---- staged epilogue (mode 2 only): every global access of the epilogue is a TMA transfer ----------
             // A thread owns one output pixel (TMEM lane = row), so direct loads / stores touch 32 different rows per
             // instruction and the block tails (float16 residual in, float16 + codes out) were bound by L1TEX
-            // wavefronts, not by HBM (profiles/r01_conv_v2.md).  Here each column group (4 warps = 128 rows x 32
-            // columns) owns private staging slabs: the residual slab arrives by TMA one tile ahead (double
-            // buffered), is updated IN PLACE to the float16 output and leaves by TMA store together with the code
-            // slabs.  Swizzled slabs (64 B rows: chunk ^= (row >> 1) & 3; 32 B rows: chunk ^= (row >> 2) & 1) keep
-            // the per-row 16-byte shared accesses conflict free.  Rows >= M and columns >= Kout are clipped by TMA.
-            const int cg = half;
+            // wavefronts, not by HBM (profiles/r01_conv_v2.md).  Here the residual tile arrives by TMA one tile
+            // ahead (double buffered), is updated IN PLACE to the float16 output and leaves by TMA store together
+            // with the code tiles.  The TMA unit's cost is per box ROW (~4-5 cycles for any row <= 128 B, measured:
+            // 32 / 64-byte rows made these transfers the bottleneck), so every box has 128-byte rows: the float16
+            // tile is two [128 rows x 64 columns] halves, a code tile one [128 x 128] box, all with the 128-byte
+            // swizzle (16-byte chunk ^= row & 7), which also keeps the per-row shared accesses conflict free.
+            // Rows >= M and columns >= Kout are clipped by TMA.
+            const int cg = half;                                                      // 32-column group 0..3
             const int r = quad * 32 + lane;
-            const bool leader = quad == 0 && lane == 0;
+            const bool leader = warp == kEpiWarp0 && lane == 0;
             const bool has_res = p.epi.residual != nullptr, has_y16 = p.epi.y_f16 != nullptr;
             const bool has_c1 = p.epi.y_codes != nullptr, has_c2 = p.epi.y_codes2 != nullptr;
-            constexpr int kSlabIo = kBM * 64, kSlabCo = kBM * 32;                     // bytes per group slab
-            const uint32_t io0 = ptx::smem_u32(s_stage) + (uint32_t)(cg * kSlabIo);   // buffer b at + b * kIoBytes
-            const uint32_t co1 = ptx::smem_u32(s_stage) + 2u * C::kIoBytes + (uint32_t)(cg * kSlabCo);
-            const uint32_t co2 = co1 + C::kCoBytes;
-            const uint32_t io_t = (uint32_t)(r * 64), sw64 = (uint32_t)((r >> 1) & 3);
-            const uint32_t co_t = (uint32_t)(r * 32), sw32 = (uint32_t)((r >> 2) & 1);
-            const uint32_t bres = ptx::smem_u32(&bar_res[cg * 2]);
+            constexpr uint32_t kHalfIo = kBM * 128;                                   // one [128 x 64] float16 half
+            const uint32_t io0 = ptx::smem_u32(s_stage);                              // buffer b at + b * kIoBytes
+            const uint32_t co1 = io0 + 2u * C::kIoBytes, co2 = co1 + C::kCoBytes;
+            const uint32_t row_off = (uint32_t)(r * 128), sw = (uint32_t)(r & 7);
+            const uint32_t io_t = (uint32_t)(cg >> 1) * kHalfIo + row_off;
+            const uint32_t bres = ptx::smem_u32(&bar_res[0]);
             const float sc1 = p.sc1, sc2 = p.sc2;
             const uint32_t enc_sh = sfp33 ? 19u : 18u;
             const int32_t enc_base = sfp33 ? 0x76F : 0xEDF;
-            uint32_t res_phase = 0u;                                                   // bit b: parity of buffer b's next landing
-            auto slab_chunks = [&](int tile) -> int {
-                const int left = (p.Kout - ((tile % p.n_tiles) * BLOCK_N + cg * 32)) >> 4;
-                return left > 2 ? 2 : (left < 0 ? 0 : left);
-            };
             auto load_res = [&](int tile, uint32_t buf) {
-                if (!has_res || slab_chunks(tile) == 0) return;
-                ptx::mbar_arrive_expect_tx(bres + buf * 8u, (uint32_t)kSlabIo);
-                ptx::tma_load_2d(io0 + buf * C::kIoBytes, &omaps.res, bres + buf * 8u, (tile % p.n_tiles) * BLOCK_N + cg * 32,
-                                 (tile / p.n_tiles) * kBM);
+                if (!has_res) return;
+                const int c0 = (tile % p.n_tiles) * BLOCK_N, r0 = (tile / p.n_tiles) * kBM;
+                const bool two = c0 + 64 < p.Kout;
+                ptx::mbar_arrive_expect_tx(bres + buf * 8u, two ? 2u * kHalfIo : kHalfIo);
+                ptx::tma_load_2d(io0 + buf * C::kIoBytes, &omaps.res, bres + buf * 8u, c0, r0);
+                if (two) ptx::tma_load_2d(io0 + buf * C::kIoBytes + kHalfIo, &omaps.res, bres + buf * 8u, c0 + 64, r0);
             };
             if (leader && my_tiles > 0) load_res((int)blockIdx.x, 0u);
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const uint32_t buf = (uint32_t)ti & 1u;
                 const uint32_t tacc = tile_begin(ti, tile);
-                const int nvalid = slab_chunks(tile);                               // group-uniform
+                const int n_slab = (tile % p.n_tiles) * BLOCK_N + cg * 32;
+                int nvalid = (p.Kout - n_slab) >> 4;                                 // 16-column chunks of this group inside Kout
+                nvalid = nvalid > 2 ? 2 : (nvalid < 0 ? 0 : nvalid);
                 const uint32_t io = io0 + buf * C::kIoBytes + io_t;
-                if (nvalid > 0) {
-                    // both 16-column chunks of the slab leave TMEM at once; the accumulator buffer is released
-                    // before any arithmetic
-                    uint32_t acc[2][16];
-                    const uint32_t tcol = tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32);
-                    ptx::tmem_ld16(tcol, acc[0]);
-                    if (nvalid > 1) ptx::tmem_ld16(tcol + 16u, acc[1]);
-                    if (has_res) {
-                        ptx::mbar_wait(bres + buf * 8u, (res_phase >> buf) & 1u, 8u | ((uint32_t)ti << 16));
-                        res_phase ^= 1u << buf;
-                    }
-                    const int n_slab = (tile % p.n_tiles) * BLOCK_N + cg * 32;
-                    ptx::tmem_ld_wait();
-                    tile_end(ti);
+                // both 16-column chunks leave TMEM at once; the accumulator buffer is released before any arithmetic
+                uint32_t acc[2][16];
+                const uint32_t tcol = tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32);
+                if (nvalid > 0) ptx::tmem_ld16(tcol, acc[0]);
+                if (nvalid > 1) ptx::tmem_ld16(tcol + 16u, acc[1]);
+                if (has_res) ptx::mbar_wait(bres + buf * 8u, ((uint32_t)ti >> 1) & 1u, 8u | ((uint32_t)ti << 16));
+                ptx::tmem_ld_wait();
+                tile_end(ti);
 #pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        if (ch >= nvalid) break;
-                        const uint32_t ioa = io + (((uint32_t)(2 * ch) ^ sw64) << 4), iob = io + (((uint32_t)(2 * ch + 1) ^ sw64) << 4);
+                for (int ch = 0; ch < 2; ++ch) {
+                    const bool live = ch < nvalid;                                   // group-uniform
+                    const uint32_t ci = (uint32_t)((cg & 1) * 4 + 2 * ch);          // chunk index inside the 128-byte row
+                    const uint32_t ioa = io + ((ci ^ sw) << 4), iob = io + (((ci + 1u) ^ sw) << 4);
+                    float v[16];
+                    if (live) {
                         uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
                         if (has_res) { ra = ptx::lds128_volatile(ioa); rb = ptx::lds128_volatile(iob); }
-                        float v[16];
                         // per-channel affine: warp-uniform 16-byte loads (L1 broadcast; L1TEX is idle in this variant)
                         const float4* mp = reinterpret_cast<const float4*>(p.epi.ch_mul + n_slab + ch * 16);
                         const float4* ap = reinterpret_cast<const float4*>(p.epi.ch_add + n_slab + ch * 16);
@@ -955,48 +951,48 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                                 v[2 * i] += f.x; v[2 * i + 1] += f.y;
                             }
                         }
-                        if (ch == 0) {
-                            // the previous tile's stores must have drained the staging slabs before anything is
-                            // written; the same moment frees the other float16 buffer for the next tile's residual
-                            if (leader) {
-                                ptx::bulk_wait_read0();
-                                if (ti + 1 < my_tiles) load_res(tile + (int)gridDim.x, buf ^ 1u);
-                            }
-                            ptx::bar_sync(2 + cg, 128);
-                        }
-                        if (has_y16) {
-                            uint32_t hw[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) hw[i] = ptx::pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
-                            ptx::sts128(ioa, hw[0], hw[1], hw[2], hw[3]);
-                            ptx::sts128(iob, hw[4], hw[5], hw[6], hw[7]);
-                        }
-#pragma unroll
-                        for (int pass = 0; pass < 2; ++pass) {
-                            if (!(pass ? has_c2 : has_c1)) continue;
-                            const float sc = pass ? sc2 : sc1;
-                            int32_t t[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)      // encode_relu_fast_raw16 with run-time format constants
-                                t[i] = (int32_t)(__float_as_uint(__saturatef(v[i] * sc)) >> enc_sh) - enc_base;
-                            ptx::sts128((pass ? co2 : co1) + co_t + (((uint32_t)ch ^ sw32) << 4), ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]),
-                                        ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]), ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]),
-                                        ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
-                        }
                     }
-                } else {
-                    tile_end(ti);
+                    if (ch == 0) {
+                        // the previous tile's stores must have drained the staging tiles before anything is written;
+                        // the same moment frees the other float16 buffer for the next tile's residual
+                        if (leader) {
+                            ptx::bulk_wait_read0();
+                            if (ti + 1 < my_tiles) load_res(tile + (int)gridDim.x, buf ^ 1u);
+                        }
+                        ptx::bar_sync(1, kEpiWarps * 32);
+                    }
+                    if (!live) continue;
+                    if (has_y16) {
+                        uint32_t hw[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) hw[i] = ptx::pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
+                        ptx::sts128(ioa, hw[0], hw[1], hw[2], hw[3]);
+                        ptx::sts128(iob, hw[4], hw[5], hw[6], hw[7]);
+                    }
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (!(pass ? has_c2 : has_c1)) continue;
+                        const float sc = pass ? sc2 : sc1;
+                        int32_t t[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)      // encode_relu_fast_raw16 with run-time format constants
+                            t[i] = (int32_t)(__float_as_uint(__saturatef(v[i] * sc)) >> enc_sh) - enc_base;
+                        ptx::sts128((pass ? co2 : co1) + row_off + (((uint32_t)(cg * 2 + ch) ^ sw) << 4), ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]),
+                                    ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]), ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]),
+                                    ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+                    }
                 }
-                if (nvalid > 0) {
-                    ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
-                    ptx::bar_sync(2 + cg, 128);
-                    if (leader) {
-                        const int c0 = (tile % p.n_tiles) * BLOCK_N + cg * 32, r0 = (tile / p.n_tiles) * kBM;
-                        if (has_y16) ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes, c0, r0);
-                        if (has_c1) ptx::tma_store_2d(&omaps.c1, co1, c0, r0);
-                        if (has_c2) ptx::tma_store_2d(&omaps.c2, co2, c0, r0);
-                        ptx::bulk_commit();
+                ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
+                ptx::bar_sync(1, kEpiWarps * 32);
+                if (leader) {
+                    const int c0 = (tile % p.n_tiles) * BLOCK_N, r0 = (tile / p.n_tiles) * kBM;
+                    if (has_y16) {
+                        ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes, c0, r0);
+                        if (c0 + 64 < p.Kout) ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes + kHalfIo, c0 + 64, r0);
                     }
+                    if (has_c1) ptx::tma_store_2d(&omaps.c1, co1, c0, r0);
+                    if (has_c2) ptx::tma_store_2d(&omaps.c2, co2, c0, r0);
+                    ptx::bulk_commit();
                 }
             }
             if (leader) ptx::bulk_wait0();
@@ -1234,10 +1230,10 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         auto out_map = [&](CUtensorMap* m, const void* ptr, bool f16) -> bool {
             const cuuint64_t gdim[2] = {(cuuint64_t)d->k, (cuuint64_t)p.M};
             const cuuint64_t gstr[1] = {(cuuint64_t)d->k * (f16 ? 2u : 1u)};
-            const cuuint32_t box[2] = {32u, (cuuint32_t)kBM};
+            const cuuint32_t box[2] = {f16 ? 64u : 128u, (cuuint32_t)kBM};          // 128-byte rows
             const cuuint32_t estr[2] = {1, 1};
             return enc_tiled(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstr,
-                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         };
         bool ok = true;
