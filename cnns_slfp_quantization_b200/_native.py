@@ -54,6 +54,9 @@ _SIGS = {
     "slfp_conv2d_fwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, ctypes.POINTER(SlfpEpilogue), c_vp]),
     "slfp_conv2d_bwd": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, c_vp, c_i, c_f, c_f, c_vp, c_vp, c_ll, c_ll,
                               c_ll, c_ll, c_vp, c_vp]),
+    "slfp_conv2d_bwd_workspace_size": (c_sz, [ctypes.POINTER(SlfpConvDesc), c_i, c_i]),
+    "slfp_conv2d_bwd_ws": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_vp, c_vp, c_i, c_f, c_f, c_vp, c_vp, c_ll, c_ll,
+                                 c_ll, c_ll, c_vp, c_vp, c_sz, c_vp]),
     "slfp_act_fwd": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
     "slfp_act_bwd": (c_i, [c_vp, c_vp, c_sz, c_i, c_vp, c_vp]),
     "slfp_sgd_step": (c_i, [c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_vp]),
@@ -70,7 +73,7 @@ _lib = None
 # (bench.py reports them as `gpu_launches`) and, when a profile dict is installed, brackets each call
 # with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
 _LAUNCHING = {"slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
-              "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
+              "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_conv2d_bwd_ws", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
               "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32"}
 launch_count = 0
 profile = None          # None, or {name: [(start_event, end_event, tag), ...]}

@@ -10,6 +10,10 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
 int conv2d_bwd_direct(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes, int wfmt,
                       float ka, float kw, float* dx, float* dwt, long long so, long long sc, long long sr, long long ss,
                       float* db, cudaStream_t st);
+size_t conv2d_bwd_tc_workspace(const SlfpConvDesc* d, int need_dx, int need_dw);
+int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes, int wfmt,
+                  float ka, float kw, float* dx, float* dwt, long long so, long long sc, long long sr, long long ss,
+                  float* db, void* workspace, size_t ws_bytes, cudaStream_t st);
 }  // namespace slfp
 
 using namespace slfp;
@@ -52,4 +56,20 @@ extern "C" int slfp_conv2d_bwd(const SlfpConvDesc* desc, const float* gy, const 
     if (rc) return rc;
     if (!gy) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_bwd: null gy");
     return conv2d_bwd_direct(desc, gy, x_codes, w_codes, wfmt, ka, kw, dx, dw, so, sc, sr, ss, db, (cudaStream_t)stream);
+}
+
+extern "C" size_t slfp_conv2d_bwd_workspace_size(const SlfpConvDesc* desc, int need_dx, int need_dw) {
+    if (check_desc(desc, "slfp_conv2d_bwd_workspace_size")) return 0;
+    return conv2d_bwd_tc_workspace(desc, need_dx, need_dw);
+}
+
+extern "C" int slfp_conv2d_bwd_ws(const SlfpConvDesc* desc, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes,
+                                  int wfmt, float ka, float kw, float* dx, float* dw, long long so, long long sc,
+                                  long long sr, long long ss, float* db, void* workspace, size_t workspace_bytes,
+                                  slfp_stream_t stream) {
+    int rc = check_desc(desc, "slfp_conv2d_bwd_ws");
+    if (rc) return rc;
+    if (!gy) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_bwd_ws: null gy");
+    return conv2d_bwd_tc(desc, gy, x_codes, w_codes, wfmt, ka, kw, dx, dw, so, sc, sr, ss, db, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
 }

@@ -498,6 +498,67 @@ __global__ void __launch_bounds__(128) wgrad_kernel(BwdParams p) {
     else atomicAdd(dst, div_rn(acc, p.kw));
 }
 
+// Dense layers with few input channels (network stems, C = 3): the reduction over output pixels is long and
+// the weight tensor tiny, so one thread owns one (r, s, c) weight column with 64 output channels in registers and
+// a block streams its range of output pixels, staging 32 pixels x 64 gy values in shared memory (read back as
+// broadcast float4s: 16 LDS per 64 FMAs).  Partial sums are added with atomics (dw zeroed by the caller).
+template <bool SFP33A>
+__global__ void __launch_bounds__(256) wgrad_smallc_kernel(BwdParams p) {
+    __shared__ uint32_t s_tab[16];
+    __shared__ __align__(16) float s_g[32][64];
+    __shared__ int s_pn[32], s_ph[32], s_pw[32];
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    const int cols = p.R * p.S * p.C;
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool active = col < cols;
+    const int c = col % p.C, rs = col / p.C, s = rs % p.S, r = rs / p.S;
+    const int k0 = blockIdx.z * 64;
+    const size_t npix = (size_t)p.N * p.Ho * p.Wo;
+    const size_t per = ceil_div_sz(ceil_div_sz(npix, (size_t)gridDim.x), 32) * 32;
+    const size_t p0 = per * blockIdx.x, p1 = min(npix, p0 + per);
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (size_t pix0 = p0; pix0 < p1; pix0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+            const int pp = i >> 6, kk = i & 63;
+            const size_t pix = pix0 + pp;
+            s_g[pp][kk] = (pix < p1 && k0 + kk < p.K) ? __ldg(p.gy + pix * p.K + k0 + kk) : 0.f;
+        }
+        if (threadIdx.x < 32) {
+            const size_t pix = pix0 + threadIdx.x;
+            const int wo = (int)(pix % p.Wo), ho = (int)((pix / p.Wo) % p.Ho);
+            s_pn[threadIdx.x] = pix < p1 ? (int)(pix / ((size_t)p.Wo * p.Ho)) : -1;
+            s_ph[threadIdx.x] = ho * p.sh - p.ph;
+            s_pw[threadIdx.x] = wo * p.sw - p.pw;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 1
+            for (int pp = 0; pp < 32; ++pp) {
+                const int n = s_pn[pp];
+                const int hi = s_ph[pp] + r * p.dh, wi = s_pw[pp] + s * p.dw;
+                if (n < 0 || hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) continue;
+                const float xv = decode<SFP33A>(p.x[(((size_t)n * p.H + hi) * p.W + wi) * p.Cp + c], s_tab);
+#pragma unroll
+                for (int kq = 0; kq < 16; ++kq) {
+                    const float4 g = *reinterpret_cast<const float4*>(&s_g[pp][kq * 4]);
+                    acc[kq * 4] = fmaf(g.x, xv, acc[kq * 4]);
+                    acc[kq * 4 + 1] = fmaf(g.y, xv, acc[kq * 4 + 1]);
+                    acc[kq * 4 + 2] = fmaf(g.z, xv, acc[kq * 4 + 2]);
+                    acc[kq * 4 + 3] = fmaf(g.w, xv, acc[kq * 4 + 3]);
+                }
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int kk = 0; kk < 64; ++kk)
+            if (k0 + kk < p.K) atomicAdd(p.dwt + (k0 + kk) * p.so + c * p.sc + r * p.sr + s * p.ss, acc[kk] * p.ka);
+    }
+}
+
 __global__ void __launch_bounds__(256) dbias_kernel(const float* __restrict__ gy, size_t npix, int K, float* __restrict__ db) {
     const int k = blockIdx.x;
     float acc = 0.f;
@@ -544,6 +605,22 @@ int conv2d_bwd_direct(const SlfpConvDesc* d, const float* gy, const uint8_t* x_c
         if (!x_codes) return set_error(SLFP_ERR_BAD_ARG, "conv2d_bwd: dw needs x_codes");
         const int Cg = d->c / d->groups;
         const int krs = d->k * d->r * d->s, cb = (Cg + 127) / 128;
+        const bool contiguous_dw = ss == 1 && sr == d->s && sc == (long long)d->r * d->s && so == (long long)Cg * d->r * d->s;
+        if (d->groups == 1 && d->c <= 16 && contiguous_dw && getenv("SLFP_WGRAD_GENERIC") == nullptr) {
+            const int cols = d->r * d->s * d->c;
+            const int threads = min(256, (cols + 31) / 32 * 32);
+            const int cblocks = (cols + threads - 1) / threads, ktiles = (d->k + 63) / 64;
+            const int splits = (int)max((size_t)1, min(ceil_div_sz(npix, 64), (size_t)(num_sms() * 6 / (cblocks * ktiles))));
+            cudaMemsetAsync(dwt, 0, (size_t)d->k * Cg * d->r * d->s * sizeof(float), st);
+            dim3 grid(splits, cblocks, ktiles);
+            if (sfp_a) wgrad_smallc_kernel<true><<<grid, threads, 0, st>>>(p); else wgrad_smallc_kernel<false><<<grid, threads, 0, st>>>(p);
+            if ((rc = check_launch("wgrad_smallc_kernel"))) return rc;
+            if (db) {
+                dbias_kernel<<<d->k, 256, 0, st>>>(gy, npix, d->k, db);
+                if ((rc = check_launch("dbias_kernel"))) return rc;
+            }
+            return 0;
+        }
         int splits = 1;
         while ((size_t)krs * cb * splits < (size_t)num_sms() * 8 && (size_t)splits * 256 < npix && splits < 1024) splits *= 2;
         p.pix_splits = splits;

@@ -108,9 +108,19 @@ class _QConvNHWC(torch.autograd.Function):
         dw = torch.empty(ctx.wshape, dtype=torch.float32, device=gy.device) if need_w else None
         db = torch.empty((K,), dtype=torch.float32, device=gy.device) if ctx.has_bias else None
         so, sc, sr, ss = (dw.stride() if dw is not None else (0, 0, 0, 0))
-        _nv.check(lib.slfp_conv2d_bwd(ctypes_byref(d), gy.data_ptr(), x_codes.data_ptr(), w_codes.data_ptr(), ctx.wfmt,
-                                      cfg.ka, cfg.kw, _nv.ptr(dx), _nv.ptr(dw), so, sc, sr, ss,
-                                      _nv.ptr(db), _nv.stream()))
+        # dgrad / wgrad as tcgen05 implicit GEMMs (csrc/conv_bwd_sm100.cu); the library never allocates, so the
+        # float16 operand images and the split-K accumulator live in a scratch tensor from torch's caching allocator.
+        # Shapes the tensor-core path does not cover (grouped, > 32 taps) report 0 bytes and run the direct kernels.
+        ws_bytes = lib.slfp_conv2d_bwd_workspace_size(ctypes_byref(d), int(need_x), int(need_w))
+        if ws_bytes:
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device)
+            _nv.check(lib.slfp_conv2d_bwd_ws(ctypes_byref(d), gy.data_ptr(), x_codes.data_ptr(), w_codes.data_ptr(), ctx.wfmt,
+                                             cfg.ka, cfg.kw, _nv.ptr(dx), _nv.ptr(dw), so, sc, sr, ss,
+                                             _nv.ptr(db), ws.data_ptr(), ws_bytes, _nv.stream()))
+        else:
+            _nv.check(lib.slfp_conv2d_bwd(ctypes_byref(d), gy.data_ptr(), x_codes.data_ptr(), w_codes.data_ptr(), ctx.wfmt,
+                                          cfg.ka, cfg.kw, _nv.ptr(dx), _nv.ptr(dw), so, sc, sr, ss,
+                                          _nv.ptr(db), _nv.stream()))
         if db is not None:                             # y = (acc + bias_q) * post_a * post_b
             db = (db * cfg.post_b) * cfg.post_a
         return dx, dw, db, None

@@ -215,6 +215,21 @@ int slfp_conv2d_bwd(const SlfpConvDesc *desc, const float *gy, const uint8_t *x_
                     long long dw_stride_o, long long dw_stride_c, long long dw_stride_r,
                     long long dw_stride_s, float *db, slfp_stream_t stream);
 
+/* The same backward as two implicit GEMMs on tcgen05 tensor cores (csrc/conv_bwd_sm100.cu): float16 operands
+ * (gy scaled by a power of two taken from max|gy|, the float16 images of the saved codes), float32 accumulation.
+ * dgrad splits a strided convolution into its output-parity classes (no zero-dilated gradient); wgrad reduces
+ * over output pixels with both NHWC operands MN-major and split-K partial sums added by red.global.v4.f32, so dw
+ * is not bit-reproducible run to run.  The library never allocates: the caller passes a 256-byte-aligned scratch
+ * buffer of slfp_conv2d_bwd_workspace_size() bytes (0 = shape not covered: grouped convolutions, more than 32
+ * filter taps; slfp_conv2d_bwd_ws then runs the direct kernels of slfp_conv2d_bwd, as it does for a dw whose
+ * c_phys is not a multiple of 64). */
+size_t slfp_conv2d_bwd_workspace_size(const SlfpConvDesc *desc, int need_dx, int need_dw);
+int slfp_conv2d_bwd_ws(const SlfpConvDesc *desc, const float *gy, const uint8_t *x_codes,
+                       const uint8_t *w_codes, int wfmt, float ka, float kw, float *dx, float *dw,
+                       long long dw_stride_o, long long dw_stride_c, long long dw_stride_r,
+                       long long dw_stride_s, float *db, void *workspace, size_t workspace_bytes,
+                       slfp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Activations: STLFunction / STL, Swish, Sigmoid (utils/activation_func.py:6-36).
  * bwd: STL clips the incoming gradient to [-1,1] by its own magnitude (:16); Swish / Sigmoid are

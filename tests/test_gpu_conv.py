@@ -184,3 +184,81 @@ def test_golden_conv_cases_backward(orc, g_conv):
             np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * np.abs(want).max(), err_msg=f"{name} {what}")
         if has_bias:
             np.testing.assert_allclose(db.cpu().numpy(), d["db"], rtol=1e-4, atol=1e-4, err_msg=name)
+
+
+def _bwd_both(out, gy, N, H, W, C, O, k, groups, qbit, ka, kw, use_ws):
+    """dx / dw through slfp_conv2d_bwd (direct CUDA-core kernels) or slfp_conv2d_bwd_ws (tcgen05 implicit GEMMs)."""
+    import ctypes
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    dx = torch.full((N, H, W, C), float("nan"), dtype=torch.float32, device="cuda")
+    dw = torch.full((O, C // groups, k, k), float("nan"), dtype=torch.float32, device="cuda")
+    so, sc, sr, ss = dw.stride()
+    args = (ctypes.byref(out["desc"]), gy.data_ptr(), out["dev"]["xc"].data_ptr(), out["dev"]["wc"].data_ptr(),
+            nv.fmt_for(qbit, "weight"), float(np.float32(ka)), float(np.float32(kw)), dx.data_ptr(), dw.data_ptr(), so, sc, sr, ss, None)
+    if use_ws:
+        nbytes = lib.slfp_conv2d_bwd_workspace_size(ctypes.byref(out["desc"]), 1, 1)
+        assert nbytes > 0, "shape not covered by the tensor-core backward"
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
+        nv.check(lib.slfp_conv2d_bwd_ws(*args, ws.data_ptr(), nbytes, nv.stream()))
+    else:
+        nv.check(lib.slfp_conv2d_bwd(*args, nv.stream()))
+    torch.cuda.synchronize()
+    return dx.cpu().numpy(), dw.cpu().numpy()
+
+
+# Tensor-core backward (csrc/conv_bwd_sm100.cu).  Tolerance, stated: float16 operands (gy scaled by a power of two,
+# float16 images of the codes) -> relative rounding 2^-11 per operand, so |d - d_ref| <= 1.2e-3 * L1 where L1 is the same
+# sum with every term replaced by its magnitude (computed by the direct float32 kernels on |gy| and sign-stripped codes).
+@pytest.mark.parametrize("qbit", [8, 7])
+@pytest.mark.parametrize("shape", [
+    # N, C, H, W, K, k, stride, pad
+    (2, 64, 14, 14, 64, 1, 1, 0),        # plain 1x1, single unit
+    (3, 64, 9, 11, 128, 3, 1, 1),        # 3x3, 9 units (groups of 3), ragged pixel tail
+    (2, 128, 12, 12, 64, 3, 2, 1),       # strided 3x3: four parity classes (1 / 2 / 2 / 4 taps)
+    (2, 256, 10, 10, 320, 1, 2, 0),      # strided 1x1: empty parity classes, K not a multiple of 64, three k tiles
+    (2, 192, 7, 7, 96, 3, 1, 1),         # C = 192: 27 units, K = 96 (padded to 128)
+    (1, 64, 20, 20, 64, 5, 1, 2),        # 25 taps
+    (2, 64, 13, 13, 72, 3, 2, 0),        # stride 2 without padding, odd sizes
+    (4, 512, 7, 7, 512, 3, 1, 1),        # ResNet stage-4 shape (small batch)
+])
+def test_tensor_core_backward_matches_direct(orc, qbit, shape):
+    from gpu_util import conv_fwd_gpu
+    N, C, H, W, K, k, st, pad = shape
+    rng = np.random.default_rng(hash(shape) % (2 ** 31))
+    x = (rng.standard_normal((N, C, H, W)) * 2).astype(np.float32)
+    w = (rng.standard_normal((K, C, k, k)) * 0.3).astype(np.float32)
+    ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+    out = conv_fwd_gpu(x, w, None, ka, kw, qbit, st, pad, 1, 1)
+    Ho, Wo = out["y"].shape[2], out["y"].shape[3]
+    gy = torch.from_numpy((rng.standard_normal((N, Ho, Wo, K)) * 3e-6 * np.exp(rng.standard_normal((N, Ho, Wo, K)))).astype(np.float32)).cuda()
+    dx0, dw0 = _bwd_both(out, gy, N, H, W, C, K, k, 1, qbit, ka, kw, False)
+    dx1, dw1 = _bwd_both(out, gy, N, H, W, C, K, k, 1, qbit, ka, kw, True)
+    # magnitude sums: |gy| and codes with the sign bit cleared
+    out["dev"]["xc"].bitwise_and_(0x7f)
+    out["dev"]["wc"].bitwise_and_(0x7f)
+    dxa, dwa = _bwd_both(out, gy.abs(), N, H, W, C, K, k, 1, qbit, ka, kw, False)
+    assert np.isfinite(dx1).all() and np.isfinite(dw1).all()
+    for got, want, l1, what in ((dx1, dx0, dxa, "dx"), (dw1, dw0, dwa, "dw")):
+        err = np.abs(got - want)
+        assert (err <= 1.2e-3 * l1 + 1e-30).all(), (what, shape, float((err / (l1 + 1e-30)).max()))
+
+
+def test_tensor_core_backward_zero_and_huge_gradients(orc):
+    """The power-of-two scaling of gy: an all-zero gradient gives exact zeros, a 1e30-sized one stays finite."""
+    from gpu_util import conv_fwd_gpu
+    rng = np.random.default_rng(5)
+    N, C, H, W, K, k = 2, 64, 8, 8, 64, 3
+    x = (rng.standard_normal((N, C, H, W)) * 2).astype(np.float32)
+    w = (rng.standard_normal((K, C, k, k)) * 0.3).astype(np.float32)
+    ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+    out = conv_fwd_gpu(x, w, None, ka, kw, 8, 1, 1, 1, 1)
+    gy = torch.zeros((N, H, W, K), dtype=torch.float32, device="cuda")
+    dx, dw = _bwd_both(out, gy, N, H, W, C, K, k, 1, 8, ka, kw, True)
+    assert (dx == 0).all() and (dw == 0).all()
+    gy = torch.from_numpy((rng.standard_normal((N, H, W, K)) * 1e30).astype(np.float32)).cuda()
+    dx0, dw0 = _bwd_both(out, gy, N, H, W, C, K, k, 1, 8, ka, kw, False)
+    dx1, dw1 = _bwd_both(out, gy, N, H, W, C, K, k, 1, 8, ka, kw, True)
+    assert np.isfinite(dx1).all() and np.isfinite(dw1).all()
+    np.testing.assert_allclose(dx1, dx0, rtol=0, atol=2e-3 * np.abs(dx0).max())
+    np.testing.assert_allclose(dw1, dw0, rtol=0, atol=2e-3 * np.abs(dw0).max())
