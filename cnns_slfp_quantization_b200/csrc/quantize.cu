@@ -94,8 +94,20 @@ __device__ __forceinline__ bool needs_exact(float x) {
 template <int FMT, bool CODES, bool FAKEQ, bool F16>
 __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
     __shared__ uint32_t s_tab[16];
+    constexpr bool kLut = FMT == SLFP_FMT_SFP33 || FMT == SLFP_FMT_SLFP34_ACT;
+    constexpr int FL = FMT == SLFP_FMT_SFP33 ? SLFP_FMT_SFP33 : SLFP_FMT_SLFP34_ACT;
+    __shared__ uint8_t s_enc[kLut && CODES ? kEncLutBytes : 16];
+    __shared__ uint32_t s_encf[kLut && (FAKEQ || F16) ? kEncLutBytes : 4];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
     __syncthreads();
+    if (kLut) {
+        for (int i = threadIdx.x; i < kEncLutBytes; i += kQThreads) {
+            const uint32_t u = enc_lut_entry<FL>((uint32_t)i);
+            if (CODES) s_enc[i] = (uint8_t)u;
+            if (FAKEQ || F16) s_encf[i] = __float_as_uint(decode<FL == SLFP_FMT_SFP33>(u, s_tab));
+        }
+        __syncthreads();
+    }
     const bool zz = a.zero_is_zero != 0;
     const size_t n_tiles = a.n / kQTile;
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -125,10 +137,41 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
                 for (int i = 0; i < 4; ++i) {
                     qv[i] = div_k_fused(xs[i], a.k_div);
                     nan_probe = fmaf(qv[i], 0.0f, nan_probe);
-                    const uint32_t ax1 = (__float_as_uint(xs[i]) & 0x7fffffffu) - 1u;      // +-0 -> 0xffffffff
+                    // rotate the sign to bit 0: 2|x| + s.  +0 -> 0 (wraps to 0xffffffff: stays on the fast path), -0 -> 1 and
+                    // 0 < |x| < 2^-119 -> below 0x08000000: both take the general path (a zero code carries no sign)
+                    const uint32_t ax1 = __funnelshift_l(__float_as_uint(xs[i]), __float_as_uint(xs[i]), 1) - 1u;
                     xmin = ax1 < xmin ? ax1 : xmin;
                 }
-                if (nan_probe != nan_probe || xmin < 0x04000000u - 1u) {
+                if (kLut && !(nan_probe != nan_probe || xmin < 0x08000000u - 1u)) {
+                    uint32_t idx[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) idx[i] = enc_lut_index<FL>(qv[i], xs[i]);
+                    if (CODES) {
+                        uint32_t u[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) u[i] = s_enc[idx[i]];
+                        const uint32_t sg = __byte_perm(__byte_perm(__float_as_uint(qv[0]), __float_as_uint(qv[1]), 0x0073),
+                                                        __byte_perm(__float_as_uint(qv[2]), __float_as_uint(qv[3]), 0x0073), 0x5410);
+                        const uint32_t pk = __byte_perm(__byte_perm(u[0], u[1], 0x0040), __byte_perm(u[2], u[3], 0x0040), 0x5410);
+                        *reinterpret_cast<uint32_t*>(a.codes + off) = (sg & 0x80808080u) | pk;
+                    }
+                    if (FAKEQ || F16) {
+                        // |fake-quant value| straight from the float table, sign of the quotient OR-ed in (a zero stays +0)
+                        float fq[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) fq[i] = __uint_as_float(s_encf[idx[i]] | (__float_as_uint(qv[i]) & 0x80000000u));
+                        if (FAKEQ) stg_stream(reinterpret_cast<float4*>(a.fakeq + off), make_float4(fq[0], fq[1], fq[2], fq[3]));
+                        if (F16) {
+                            __half2 h0 = __floats2half2_rn(fq[0], fq[1]), h1 = __floats2half2_rn(fq[2], fq[3]);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            *reinterpret_cast<uint2*>(a.f16 + off) = pk;
+                        }
+                    }
+                    continue;
+                }
+                if (nan_probe != nan_probe || xmin < 0x08000000u - 1u) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) c[i] = encode<F>(div_k(xs[i], a.k_div));
                 } else if (F == SLFP_FMT_SLFP34_WGT) {
@@ -197,17 +240,34 @@ static int launch_quantize(const QuantArgs& a, cudaStream_t st) {
         return check_launch("quantize_scalar_kernel");
     }
     const size_t tiles = a.n / kQTile;
-    int grid = (int)max((size_t)1, min(tiles, (size_t)sms * 8));
     const int sel = (a.codes ? 1 : 0) | (a.fakeq ? 2 : 0) | (a.f16 ? 4 : 0);
+    // persistent grid-stride CTAs: exactly one resident wave (a grid larger than what fits leaves a second, thin wave
+    // running alone at a fraction of the memory-level parallelism)
+#define SLFP_QLAUNCH(C_, F_, H_)                                                                                   \
+    {                                                                                                              \
+        static int per_sm = 0;                                                                                     \
+        if (!per_sm) {                                                                                             \
+            int b = 0;                                                                                             \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, quantize_kernel<FMT, C_, F_, H_>, kQThreads, 0) != cudaSuccess) { \
+                cudaGetLastError();                                                                                \
+                b = 0;                                                                                             \
+            }                                                                                                      \
+            per_sm = b > 0 ? b : 4;                                                                                \
+        }                                                                                                          \
+        const int grid = (int)max((size_t)1, min(tiles, (size_t)sms * per_sm));                                    \
+        quantize_kernel<FMT, C_, F_, H_><<<grid, kQThreads, 0, st>>>(a);                                           \
+    }                                                                                                              \
+    break;
     switch (sel) {
-        case 1: quantize_kernel<FMT, true, false, false><<<grid, kQThreads, 0, st>>>(a); break;
-        case 2: quantize_kernel<FMT, false, true, false><<<grid, kQThreads, 0, st>>>(a); break;
-        case 3: quantize_kernel<FMT, true, true, false><<<grid, kQThreads, 0, st>>>(a); break;
-        case 4: quantize_kernel<FMT, false, false, true><<<grid, kQThreads, 0, st>>>(a); break;
-        case 5: quantize_kernel<FMT, true, false, true><<<grid, kQThreads, 0, st>>>(a); break;
-        case 6: quantize_kernel<FMT, false, true, true><<<grid, kQThreads, 0, st>>>(a); break;
-        default: quantize_kernel<FMT, true, true, true><<<grid, kQThreads, 0, st>>>(a); break;
+        case 1: SLFP_QLAUNCH(true, false, false)
+        case 2: SLFP_QLAUNCH(false, true, false)
+        case 3: SLFP_QLAUNCH(true, true, false)
+        case 4: SLFP_QLAUNCH(false, false, true)
+        case 5: SLFP_QLAUNCH(true, false, true)
+        case 6: SLFP_QLAUNCH(false, true, true)
+        default: SLFP_QLAUNCH(true, true, true)
     }
+#undef SLFP_QLAUNCH
     return check_launch("quantize_kernel");
 }
 

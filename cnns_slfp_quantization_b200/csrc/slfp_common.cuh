@@ -92,7 +92,7 @@ static inline DivK make_divk(float k) {
     d.k = k;
     d.rk = 1.0f / k;
     const float a = k < 0 ? -k : k;
-    d.fast = (a >= 9.3132257e-10f && a <= 1.0737418e9f) ? 1 : 0;
+    d.fast = (k >= 9.3132257e-10f && k <= 1.0737418e9f) ? 1 : 0;     // positive scales only (sign of a zero quotient)
     return d;
 }
 __host__ __device__ __forceinline__ float div_k(float x, const DivK& d) {
@@ -294,6 +294,56 @@ __host__ __device__ __forceinline__ uint32_t encode_balanced(float v) {
     const uint32_t hi_code = sbit * 128u + u;
     const uint32_t lo_code = (z * sbit) * 128u + z;                    // +-0 -> 0 (sign dropped), tiny -> 1 | sign
     return (a < kBits0625) ? lo_code : hi_code;
+}
+
+// ---- table encoder (stand-alone activation quantizer, codes output) ------------------------------------------
+// encode_balanced<> still spends ~15 ALU-pipe instructions per element on class selection (clamps, tiny / zero /
+// saturation selects, the log-converter correction, sign insertion) and that pipe issues 64 lanes/clk/SM: the kernel
+// sat at 0.64 of the HBM peak.  Here EVERY class decision is folded into the value that gets rounded, with
+// saturating FMA-pipe arithmetic, and the unsigned code is one byte load from a shared-memory table indexed by the
+// top bits of the rounded float:
+//     m    = |q| * 2^100                                   (exact, may overflow to +Inf)
+//     nz   = sat(|x| * 2^126)                              1 unless the dividend is +-0
+//     tiny = sat(nz * 2^96 - m)                            1 iff 0 < |q| < 0.0625          (:92 / :74)
+//     sat  = sat(m - 15.32165 * 2^100)                     1 iff |q| > 15.32165            (:95; SLFP only)
+//     a'   = min(|q|, 16 | 15) + 48 sat + 128 tiny         saturated -> 64, tiny -> 128, +-0 -> 0, else unchanged
+//     hi   = Veltkamp split of a' at 4 | 3 mantissa bits   (round-half-even, :88 / :69)
+//     code = table[bits(hi) >> 19 | 20]                    table holds the log converter (:89) and [0.0625,0.125) -> 0.125
+// 13 FMA-pipe + 2 ALU-pipe instructions per element; sign bits are gathered four at a time (PRMT) and OR-ed into the
+// packed word.  Domain (the quantizer's group probe guarantees it): q finite, x == +0 or |x| >= 2^-119, never -0
+// (a zero code carries no sign).  Swept against encode<> for every mantissa by tests/test_host_compiled_kernels.py.
+constexpr int kEncLutBytes = 2176;
+template <int FMT>
+__host__ __device__ __forceinline__ uint32_t enc_lut_entry(uint32_t idx) {
+    static_assert(FMT == SLFP_FMT_SFP33 || FMT == SLFP_FMT_SLFP34_ACT, "activation formats");
+    constexpr uint32_t mb = FMT == SLFP_FMT_SFP33 ? 3u : 4u;
+    if (idx == 0u) return kCodeZero;
+    if (idx == (134u << mb)) return kCodeTiny;                    // 128.0
+    if (idx >= (133u << mb)) return kCodeSat;                     // 64.0 (and the unreachable rest)
+    const uint32_t eb = idx >> mb, i = idx & ((1u << mb) - 1u);
+    if (eb < 123u) return kCodeTiny;                              // unreachable (tiny values were moved to 128)
+    const uint32_t E = eb - 123u;
+    if (E == 0u) return 1u << mb;                                 // [0.0625, 0.125) -> 0.125
+    if (FMT == SLFP_FMT_SFP33) return (E << 3) + i;
+    return (E << 4) + i + ((i >= 2u && i <= 14u) ? 1u : 0u);      // log converter 0,1,3,4,...,15,15,(16 = carried)
+}
+template <int FMT>
+__host__ __device__ __forceinline__ uint32_t enc_lut_index(float q, float x) {
+    const float av = fabsf(q);
+    const float nz = sat01(fabsf(x) * 0x1p126f);
+    const float m = av * 0x1p100f;
+    const float tiny = sat01(fmaf(nz, 0x1p96f, -m));
+    float a;
+    if (FMT == SLFP_FMT_SFP33) {
+        a = fmaf(tiny, 128.0f, fminf(av, 15.0f));                 // a >= 15 -> 15 (:77)
+    } else {
+        const float st = sat01(m - u2f(kBitsSat8 + (100u << 23)));
+        a = fmaf(tiny, 128.0f, fmaf(st, 48.0f, fminf(av, 16.0f)));
+    }
+    const float t = a * (FMT == SLFP_FMT_SFP33 ? 1048577.0f : 524289.0f);
+    const float d = t - a;
+    const float hi = t - d;
+    return f2u(hi) >> (FMT == SLFP_FMT_SFP33 ? 20 : 19);
 }
 
 __host__ __device__ __forceinline__ uint32_t encode_rt(float v, int fmt) {

@@ -101,3 +101,27 @@ extern "C" size_t hostcheck_encode_balanced_mismatches(const float* v, size_t n,
     }
     return bad;
 }
+
+// the table encoder of the stand-alone quantizer (enc_lut_index + enc_lut_entry + sign) against encode<FMT>(q); the
+// dividend only tells zero from non-zero on that path.  Returns the mismatch count.
+extern "C" size_t hostcheck_encode_lut_mismatches(const float* q, size_t n, int fmt) {
+    static uint8_t tab[2][kEncLutBytes];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < kEncLutBytes; ++i) {
+            tab[0][i] = (uint8_t)enc_lut_entry<SLFP_FMT_SFP33>((uint32_t)i);
+            tab[1][i] = (uint8_t)enc_lut_entry<SLFP_FMT_SLFP34_ACT>((uint32_t)i);
+        }
+        init = true;
+    }
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float x = q[i] == 0.0f ? 0.0f : 1.0f;
+        const uint32_t idx = fmt == SLFP_FMT_SFP33 ? enc_lut_index<SLFP_FMT_SFP33>(q[i], x) : enc_lut_index<SLFP_FMT_SLFP34_ACT>(q[i], x);
+        if (idx >= (uint32_t)kEncLutBytes) { ++bad; continue; }
+        const uint32_t a = (uint32_t)tab[fmt == SLFP_FMT_SFP33 ? 0 : 1][idx] | ((f2u(q[i]) >> 24) & 0x80u);
+        const uint32_t b = fmt == SLFP_FMT_SFP33 ? encode<SLFP_FMT_SFP33>(q[i]) : encode<SLFP_FMT_SLFP34_ACT>(q[i]);
+        bad += a != b;
+    }
+    return bad;
+}

@@ -132,3 +132,22 @@ def test_pipe_balanced_encoder_equals_reference_encoder(hostcheck, fmt):
             assert bad == 0, (fmt, e, sgn, bad)
     v = np.array([15.0, 15.32165, 15.5, 16.0, 1e30, np.inf, -np.inf, 3e38, 0.0, -0.0, 1e-45, -1e-45, 0.0625, 0.125, -0.0625], np.float32)
     assert hostcheck.hostcheck_encode_balanced_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), fmt) == 0
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_table_encoder_equals_reference_encoder(hostcheck, fmt):
+    """The stand-alone quantizer's table encoder (class decisions folded into the rounded value by saturating FMA-pipe
+    arithmetic, code = one byte from a shared-memory table) == encode<FMT> for every float32 mantissa, both signs,
+    exponents from denormal quotients to 3e38.  Its domain excludes only NaN / Inf quotients and -0 (group probe)."""
+    hostcheck.hostcheck_encode_lut_mismatches.restype = ctypes.c_size_t
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    for e in [0, 1, 27, 60, 100, 118, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 132, 133, 134, 140, 153, 154, 155, 200, 254]:
+        x = (mant | np.uint32(e << 23)).view(np.float32)
+        if e == 0:
+            x = x[1:]                                  # +-0 are checked below (-0 is outside the domain)
+        for sgn in (1.0, -1.0):
+            v = np.ascontiguousarray(x * np.float32(sgn))
+            bad = hostcheck.hostcheck_encode_lut_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), ctypes.c_int(fmt))
+            assert bad == 0, (fmt, e, sgn, bad)
+    v = np.array([15.0, 15.32165, 15.5, 16.0, 1e30, 3e38, -3e38, 0.0, 1e-45, -1e-45, 0.0625, 0.125, -0.0625, 14.75, 15.25, 15.75], np.float32)
+    assert hostcheck.hostcheck_encode_lut_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), fmt) == 0

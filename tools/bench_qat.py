@@ -50,8 +50,10 @@ out = {"net": "resnet50_slfp8_qat", "batch": batch, "size": size, "ms_per_step":
        "images_per_s": round(batch / ms * 1e3, 1), "loss": float(loss)}
 if os.environ.get("SLFP_QAT_PROFILE"):
     nv.profile = {}
+    torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly this step
     step()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     prof, nv.profile = nv.profile, None
     out["per_entry_point_ms"] = {k: round(sum(p.elapsed_time(q) for p, q, _ in v), 3) for k, v in prof.items()}
 print(json.dumps(out), flush=True)
