@@ -414,7 +414,24 @@ struct WPrepArgs {
     size_t out_pitch, out_off;
     const float* row_scale;
     uint32_t mg_pitch, sh_pitch, mg_cp, sh_cp, mg_s, sh_s;   // n / d == umulhi(n, mg) >> sh for n < 2^31 (d > 1)
+    DivK dk;                                                 // kw with its reciprocal: exact x / kw without the division sequence
 };
+
+// shared-memory tables of the weight-preparation kernels: bucket table of the SLFP weight encoder, code -> float32
+struct WPrepTables {
+    uint2 bucket[32];
+    float dec[256];
+};
+template <int FMT>
+__device__ __forceinline__ void wprep_tables_init(WPrepTables& t, const uint32_t* s_tab) {
+    if (FMT < 0) return;
+    if (threadIdx.x < 32) {
+        uint32_t cnt, thr;
+        wgt_bucket_entry(threadIdx.x, cnt, thr);
+        t.bucket[threadIdx.x] = make_uint2(cnt, thr);
+    }
+    t.dec[threadIdx.x] = decode<FMT == SLFP_FMT_SFP33>(threadIdx.x, s_tab);      // 256 threads
+}
 
 static void magic_u32(uint32_t d, uint32_t& mg, uint32_t& sh) {
     mg = 0; sh = 0;
@@ -431,7 +448,7 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t d, uint32_t m
 }
 
 template <int FMT>
-__device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, const uint32_t* s_tab) {
+__device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, const WPrepTables& tb) {
     // a prepared tensor has < 2^32 elements (checked on the host): 32-bit index arithmetic
     const uint32_t i32 = (uint32_t)i, pitch = (uint32_t)a.pitch;
     const int k = (int)div_magic(i32, pitch, a.mg_pitch, a.sh_pitch);
@@ -443,12 +460,12 @@ __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, cons
     if (c < a.C && rs < a.R * a.S) {
         const int r = (int)div_magic((uint32_t)rs, (uint32_t)a.S, a.mg_s, a.sh_s), s = rs - r * a.S;
         const float x = a.w[k * a.so + c * a.sc + r * a.sr + s * a.ss];
-        const float v = div_rn(x, a.kw);
+        const float v = div_k(x, a.dk);                      // == IEEE x / kw
         if (FMT < 0) {
             fq = v;
         } else {
-            code = encode<FMT < 0 ? 0 : FMT>(v);
-            fq = decode<FMT == SLFP_FMT_SFP33>(code, s_tab);
+            code = FMT == SLFP_FMT_SLFP34_WGT ? encode_wgt_bucket(v, tb.bucket) : encode<FMT < 0 ? 0 : FMT>(v);
+            fq = tb.dec[code];
         }
         if (a.w_fakeq) a.w_fakeq[(((size_t)k * a.C + c) * a.R + r) * a.S + s] = fq;
     }
@@ -460,11 +477,14 @@ __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, cons
 template <int FMT>
 __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
     __shared__ uint32_t s_tab[16];
+    __shared__ WPrepTables tb;
     if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    wprep_tables_init<FMT>(tb, s_tab);
     __syncthreads();
     const size_t total = (size_t)a.K * a.pitch;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256)
-        wprep_element<FMT>(a, i, s_tab);
+        wprep_element<FMT>(a, i, tb);
 }
 
 // Every layer of a network in ONE launch (the reference re-quantizes all weights on every forward,
@@ -478,10 +498,15 @@ struct WPrepBatch {
     WPrepArgs a[kWBatchMax];
 };
 
+static_assert(sizeof(WPrepBatch) <= 32000, "kernel parameter space");
+
 template <int FMT>
 __global__ void __launch_bounds__(256) wprep_batch_kernel(const __grid_constant__ WPrepBatch b) {
     __shared__ uint32_t s_tab[16];
+    __shared__ WPrepTables tb;
     if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    wprep_tables_init<FMT>(tb, s_tab);
     __syncthreads();
     int lo = 0, hi = b.n - 1;                                 // first tensor with blk_end > blockIdx.x
     while (lo < hi) {
@@ -495,7 +520,7 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const __grid_constant_
 #pragma unroll 2
     for (int j = 0; j < kWBatchChunk / 256; ++j) {
         const size_t i = base + (size_t)j * 256 + threadIdx.x;
-        if (i < total) wprep_element<FMT>(a, i, s_tab);
+        if (i < total) wprep_element<FMT>(a, i, tb);
     }
 }
 
@@ -644,7 +669,7 @@ static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long 
     if (d->groups > 1) { a.C = d->c / d->groups; a.Cp = a.C; }
     else { a.C = d->c; a.Cp = d->c_phys; }
     a.pitch = slfp_conv_wpitch(d);
-    a.kw = kw; a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
+    a.kw = kw; a.dk = make_divk(kw); a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
     a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr;
     if ((size_t)a.K * a.pitch >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^31 or more elements");
     magic_u32((uint32_t)a.pitch, a.mg_pitch, a.sh_pitch);

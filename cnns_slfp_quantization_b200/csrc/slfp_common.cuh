@@ -346,6 +346,37 @@ __host__ __device__ __forceinline__ uint32_t enc_lut_index(float q, float x) {
     return f2u(hi) >> (FMT == SLFP_FMT_SFP33 ? 20 : 19);
 }
 
+// ---- SLFP<3,4> weight encoder, threshold search by table ----------------------------------------------------------
+// quantize_weight(8) has no linear pre-round (sfp_quant.py:40): L = number of the 16 thresholds 2^((2j-1)/32) that are
+// <= the mantissa.  Consecutive thresholds are >= 0.043 apart, so each 1/32-wide mantissa bucket holds at most one:
+// entry b = (thresholds at or below the bucket's start, the threshold inside the bucket or ~0) and
+// L = cnt + (mantissa >= thr): one 8-byte load and a compare instead of 16 compares.  Bit-exact with encode<>
+// (swept for every mantissa by tests/test_host_compiled_kernels.py).
+__host__ __device__ __forceinline__ void wgt_bucket_entry(uint32_t b, uint32_t& cnt, uint32_t& thr) {
+    constexpr uint32_t kThresh[16] = SLFP_WGT_THRESH_TABLE;
+    const uint32_t lo = 0x3f800000u | (b << 18), hi = lo + (1u << 18);
+    cnt = 0; thr = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (kThresh[j] <= lo) ++cnt;
+        else if (kThresh[j] < hi) thr = kThresh[j];
+    }
+}
+__host__ __device__ __forceinline__ uint32_t encode_wgt_bucket(float v, const uint2* __restrict__ tbl) {
+    const uint32_t b = f2u(v);
+    const uint32_t a = b & 0x7fffffffu;
+    const uint32_t mb = (a & 0x007fffffu) | 0x3f800000u;
+    const uint2 e = tbl[(a >> 18) & 31u];
+    uint32_t u = (((a >> 23) - (127u - 4u)) << 4) + e.x + (mb >= e.y ? 1u : 0u);   // L == 16 carries into E
+    u = (int32_t)u < 16 ? 16u : u;                           // [0.0625, 0.125) -> 0.125
+    u = (a > kBitsSat8) ? kCodeSat : u;
+    u = (a < kBits0625) ? kCodeTiny : u;
+    u |= (b >> 24) & 0x80u;
+    u = (a == 0u) ? kCodeZero : u;
+    u = (a > kBitsInf) ? kCodeNaN : u;
+    return u;
+}
+
 __host__ __device__ __forceinline__ uint32_t encode_rt(float v, int fmt) {
     if (fmt == SLFP_FMT_SFP33) return encode<SLFP_FMT_SFP33>(v);
     if (fmt == SLFP_FMT_SLFP34_ACT) return encode<SLFP_FMT_SLFP34_ACT>(v);

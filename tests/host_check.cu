@@ -125,3 +125,16 @@ extern "C" size_t hostcheck_encode_lut_mismatches(const float* q, size_t n, int 
     }
     return bad;
 }
+
+// encode_wgt_bucket (threshold search by bucket table) against encode<SLFP_FMT_SLFP34_WGT>; returns the mismatch count
+extern "C" size_t hostcheck_encode_wgt_bucket_mismatches(const float* v, size_t n) {
+    static uint2 tbl[32];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t b = 0; b < 32; ++b) wgt_bucket_entry(b, tbl[b].x, tbl[b].y);
+        init = true;
+    }
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) bad += encode_wgt_bucket(v[i], tbl) != encode<SLFP_FMT_SLFP34_WGT>(v[i]);
+    return bad;
+}

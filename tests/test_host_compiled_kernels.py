@@ -151,3 +151,16 @@ def test_table_encoder_equals_reference_encoder(hostcheck, fmt):
             assert bad == 0, (fmt, e, sgn, bad)
     v = np.array([15.0, 15.32165, 15.5, 16.0, 1e30, 3e38, -3e38, 0.0, 1e-45, -1e-45, 0.0625, 0.125, -0.0625, 14.75, 15.25, 15.75], np.float32)
     assert hostcheck.hostcheck_encode_lut_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size), fmt) == 0
+
+
+def test_weight_bucket_encoder_equals_reference_encoder(hostcheck):
+    """encode_wgt_bucket (the 16-threshold search of quantize_weight(8) as one bucket-table look-up, used by the
+    weight-preparation kernels) == encode<SLFP34_WGT> for every float32 mantissa, both signs, all classes, NaN / Inf."""
+    hostcheck.hostcheck_encode_wgt_bucket_mismatches.restype = ctypes.c_size_t
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    for e in [0, 1, 100, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 200, 254, 255]:
+        x = (mant | np.uint32(e << 23)).view(np.float32)
+        for sgn in (0, 1):
+            v = np.ascontiguousarray((x.view(np.uint32) | np.uint32(sgn << 31)).view(np.float32))
+            bad = hostcheck.hostcheck_encode_wgt_bucket_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size))
+            assert bad == 0, (e, sgn, bad)
