@@ -94,8 +94,11 @@ def synth_resnet50(qbit, size, ops, device, calibrate):
     m32.load_state_dict(sd)
     m32 = m32.to(device)
     ka, kw = calibrate(m32, nc.synth_images(4, min(size, 96)).to(device))
-    m = ResNet50(qbit, ops=ops, scales=(ka, kw)).eval()
+    m = ResNet50(qbit, ops=ops, scales=(np.ones(54), np.ones(54))).eval()
     m.load_state_dict(sd)
+    # calibration returns the scales in module-traversal order (nc.quantized_layers); the constructor's `scales`
+    # argument is indexed like the reference's hard-coded lists (downsample = stage offset), so assign by traversal
+    nc.set_scales(m, ka, kw)
     return m.to(device)
 
 

@@ -97,7 +97,13 @@ struct Cfg {
     // first version's 4 x 8 KB of codes in flight per SM left the decode warps waiting on the code barrier most
     // of the time (profiles/r01_conv_v2.md).  With A in TMEM the freed shared memory deepens both rings.
     static constexpr int kStages = (BLOCK_N >= 256 || STG) ? 3 : 4;          // weight (and A) stages
-    static constexpr int kCodeStages = (BLOCK_N >= 256 || STG) ? 5 : 6;
+    // The code ring depth must be a MULTIPLE of the number of decode groups (2 or 4), so that a code stage is always
+    // consumed by the same group: TMA loads of different stages may land out of order, and a group that moved on to
+    // K block j + CS while the load of K block j (same stage, other group) was still in flight would find the stage's
+    // `full` barrier one phase behind - a parity wait then passes immediately (it cannot tell "phase n - 1 done" from
+    // "phase n + 1 done"), the group decodes stale codes and its arrivals desynchronise the ring (seen as a rare
+    // `unspecified launch failure` once the weights were re-quantized between steps, ~1 step in 1000).
+    static constexpr int kCodeStages = (BLOCK_N >= 256 || STG) ? 6 : 8;
     // STG: the epilogue's global traffic goes through shared-memory staging + TMA (see the staged epilogue below):
     // two float16 [128 x BLOCK_N] buffers (residual in / float16 out, in place) and two code tiles.
     static constexpr int kIoBytes = kBM * BLOCK_N * 2, kCoBytes = kBM * BLOCK_N;
@@ -758,6 +764,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         constexpr int kDecGroups = kDecWarps / kWarpsPerGroup;
         constexpr int kQPW = 16 / kWarpsPerGroup;              // 16-channel quarters per warp: 4 or 2
         static_assert(kDecGroups <= C::kStages && kDecGroups <= kCodeStages, "groups may not outrun the barrier phases");
+        static_assert(kCodeStages % kDecGroups == 0, "a code stage must always be consumed by the same decode group");
         const int grp = (warp - kDecWarp0) / kWarpsPerGroup;
         const int q0 = (((warp - kDecWarp0) % kWarpsPerGroup) >> 2) * kQPW;   // first quarter of this warp
         const int row = (warp & 3) * 32 + lane;

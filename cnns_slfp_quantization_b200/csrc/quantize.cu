@@ -306,11 +306,29 @@ __global__ void __launch_bounds__(256) quantize_nchw_kernel(const float* __restr
     }
 }
 
+// One element through the table encoder (enc_lut_index + shared-memory table), the generic encoder for the values
+// outside its domain (NaN / Inf quotient, -0, dividends below 2^-119) or when K is outside the reciprocal's range.
+template <int FMT>
+__device__ __forceinline__ uint32_t encode_elem_lut(float x, const DivK& k, const uint8_t* s_enc) {
+    const float q = div_k_fused(x, k);
+    const uint32_t xb = __float_as_uint(x);
+    const uint32_t probe = __funnelshift_l(xb, xb, 1) - 1u;
+    if (!k.fast || probe < 0x08000000u - 1u || !(fabsf(q) < INFINITY)) return encode<FMT>(div_k(x, k));
+    return (uint32_t)s_enc[enc_lut_index<FMT>(q, x)] | ((__float_as_uint(q) >> 24) & 0x80u);
+}
+
 // NCHW float32 image -> space-to-depth NHWC codes [N, H/2, W/2, Cp], channel (dy*2+dx)*C + c.  Thread = one
 // folded pixel: 2 x float2 reads per plane (coalesced across the warp), one 16-byte store per 16 channels.
 template <int FMT>
 __global__ void __launch_bounds__(256) quantize_nchw_s2d_kernel(const float* __restrict__ x, int N, int C, int H, int W, int Cp,
                                                                 DivK k_div, uint8_t* __restrict__ codes) {
+    constexpr bool kLut = FMT == SLFP_FMT_SFP33 || FMT == SLFP_FMT_SLFP34_ACT;
+    constexpr int FL = FMT == SLFP_FMT_SFP33 ? SLFP_FMT_SFP33 : SLFP_FMT_SLFP34_ACT;
+    __shared__ uint8_t s_enc[kLut ? kEncLutBytes : 16];
+    if (kLut) {
+        for (int i = threadIdx.x; i < kEncLutBytes; i += 256) s_enc[i] = (uint8_t)enc_lut_entry<FL>((uint32_t)i);
+        __syncthreads();
+    }
     const int H2 = H >> 1, W2 = W >> 1;
     const size_t total = (size_t)N * H2 * W2;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
@@ -326,8 +344,13 @@ __global__ void __launch_bounds__(256) quantize_nchw_s2d_kernel(const float* __r
                 for (int dy = 0; dy < 2; ++dy) {
                     const float2 v = __ldg(reinterpret_cast<const float2*>(x + ((n * C + c) * H + (2 * y2 + dy)) * (size_t)W) + x2);
                     const int ch0 = (dy * 2) * C + c, ch1 = (dy * 2 + 1) * C + c;
-                    wds[ch0 >> 2] |= encode<FMT>(div_k(v.x, k_div)) << (8 * (ch0 & 3));
-                    wds[ch1 >> 2] |= encode<FMT>(div_k(v.y, k_div)) << (8 * (ch1 & 3));
+                    if (kLut) {
+                        wds[ch0 >> 2] |= encode_elem_lut<FL>(v.x, k_div, s_enc) << (8 * (ch0 & 3));
+                        wds[ch1 >> 2] |= encode_elem_lut<FL>(v.y, k_div, s_enc) << (8 * (ch1 & 3));
+                    } else {
+                        wds[ch0 >> 2] |= encode<FMT>(div_k(v.x, k_div)) << (8 * (ch0 & 3));
+                        wds[ch1 >> 2] |= encode<FMT>(div_k(v.y, k_div)) << (8 * (ch1 & 3));
+                    }
                 }
             }
             *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);

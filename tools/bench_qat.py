@@ -19,8 +19,9 @@ sd = nc.synth_state_dict(m32)
 m32.load_state_dict(sd)
 m32 = m32.to(dev)
 ka, kw = calibration.calibrate_scales(m32, [nc.synth_images(4, min(size, 96)).to(dev)])
-m = ResNet50(8, scales=(ka, kw))
+m = ResNet50(8, scales=(np.ones(54), np.ones(54)))
 m.load_state_dict(sd)
+nc.set_scales(m, ka, kw)                 # calibration order = module traversal order
 m = m.to(dev).train()
 opt = DSGD(m.parameters(), 8, lr=1e-3, momentum=0.9, weight_decay=5e-4)
 x = nc.synth_images(batch, size).to(dev)
