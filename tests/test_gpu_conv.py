@@ -221,6 +221,9 @@ def _bwd_both(out, gy, N, H, W, C, O, k, groups, qbit, ka, kw, use_ws):
     (1, 64, 20, 20, 64, 5, 1, 2),        # 25 taps
     (2, 64, 13, 13, 72, 3, 2, 0),        # stride 2 without padding, odd sizes
     (4, 512, 7, 7, 512, 3, 1, 1),        # ResNet stage-4 shape (small batch)
+    (2, 30, 9, 9, 40, 3, 1, 1),          # c_phys = 32: dgrad on tensor cores (scalar stores, C % 4 != 0), wgrad direct
+    (3, 24, 8, 8, 64, 1, 2, 0),          # c_phys = 32, strided 1x1
+    (5, 128, 1, 1, 1000, 1, 1, 0),       # classifier-like: one pixel per image, K = 1000
 ])
 def test_tensor_core_backward_matches_direct(orc, qbit, shape):
     from gpu_util import conv_fwd_gpu
