@@ -47,7 +47,7 @@ struct Params {
     int units, cchunks, ugroups, splits, pb_total, pb_per_split;
     float* wacc;
     int K, Cp;
-    const float* scale;          // device: [0] = 2^e applied to G, [1] = 2^-e
+    const float* scale;          // device: max|gy| (grad_scale() derives 2^e and 2^-e from it)
     float post;
 };
 
@@ -56,11 +56,26 @@ template <int BN> struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);
     static constexpr int kBufCols = kTmemCols / 2;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 4 * 4096;   // + barriers + epilogue staging
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// 2^e with max|gy| * 2^e in [2^14, 2^15) and 2^-e, from the abs-max word the reduction kernel left in the workspace;
+// (1, 1) when the maximum is 0 / Inf / NaN.  Every kernel that needs the scale recomputes it (two instructions)
+// instead of a separate one-thread launch per layer.
+__device__ __forceinline__ float2 grad_scale(const float* __restrict__ amax) {
+    const float m = __ldg(amax);
+    float s = 1.f, inv = 1.f;
+    if (m > 0.f && m < INFINITY) {
+        int e = 14 - (int)((__float_as_uint(m) >> 23) & 0xffu) + 127;       // exponent that moves m into [2^14, 2^15)
+        e = e > 120 ? 120 : (e < -120 ? -120 : e);
+        s = __uint_as_float((uint32_t)(e + 127) << 23);
+        inv = __uint_as_float((uint32_t)(127 - e) << 23);
+    }
+    return make_float2(s, inv);
 }
 
 // MODE 0: dgrad (both operands K-major), MODE 1: wgrad (both operands MN-major)
@@ -199,7 +214,9 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // =========================== epilogue: TMEM -> global ============================================
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const float inv = p.scale[1];
+        const float inv = grad_scale(p.scale).y;
+        uint8_t* stg = smem + kStages * C::kStageBytes + 256 + (warp & 3) * 4096;      // 32 rows x 128 B per warp
+        const uint32_t stg_u = ptx::smem_u32(stg);
         for (int it = 0; it < my_items; ++it) {
             const int item = (int)blockIdx.x + it * (int)gridDim.x;
             const uint32_t buf = (uint32_t)it & 1u;
@@ -221,18 +238,32 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     uint32_t v[32];
                     ptx::tmem_ld32(t_row + (uint32_t)c0, v);
                     ptx::tmem_ld_wait();
-                    if (valid) {
-                        if (p.vec_ok && n0 + c0 + 32 <= p.C) {
+                    if (p.vec_ok) {
+                        // A thread owns one pixel row, so direct stores would touch 32 rows per instruction (half-filled
+                        // sectors: 2.7 TB/s measured).  Stage the warp's 32 x 32 block in shared memory (16-byte chunks
+                        // XOR-swizzled by row: conflict-free both ways) and write it back 4 rows per instruction, 8 lanes
+                        // covering one 128-byte row piece.
 #pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                *reinterpret_cast<float4*>(dst + c0 + q * 4) =
-                                    make_float4(__uint_as_float(v[q * 4]) * sc, __uint_as_float(v[q * 4 + 1]) * sc,
-                                                __uint_as_float(v[q * 4 + 2]) * sc, __uint_as_float(v[q * 4 + 3]) * sc);
-                        } else {
+                        for (int q = 0; q < 8; ++q)
+                            ptx::sts128(stg_u + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4)),
+                                        __float_as_uint(__uint_as_float(v[q * 4]) * sc), __float_as_uint(__uint_as_float(v[q * 4 + 1]) * sc),
+                                        __float_as_uint(__uint_as_float(v[q * 4 + 2]) * sc), __float_as_uint(__uint_as_float(v[q * 4 + 3]) * sc));
+                        __syncwarp();
+                        const unsigned long long my_row = valid ? (unsigned long long)(uintptr_t)dst : 0ull;
+                        const int cch = lane & 7;
+                        const bool col_ok = n0 + c0 + cch * 4 + 4 <= p.C;
 #pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (n0 + c0 + q < p.C) dst[c0 + q] = __uint_as_float(v[q]) * sc;
+                        for (int k = 0; k < 8; ++k) {
+                            const int r = k * 4 + (lane >> 3);
+                            const unsigned long long rp = __shfl_sync(0xffffffffu, my_row, r);
+                            const float4 val = ptx::lds128_f4(stg_u + (uint32_t)(r * 128 + ((cch ^ (r & 7)) << 4)));
+                            if (rp != 0ull && col_ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(rp) + c0 + cch * 4) = val;
                         }
+                        __syncwarp();
+                    } else if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (n0 + c0 + q < p.C) dst[c0 + q] = __uint_as_float(v[q]) * sc;
                     }
                 }
             } else {
@@ -271,24 +302,10 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 }
 
 // ---- operand preparation (HBM-bound element-wise passes) ------------------------------------------------------
-// scale[0] = 2^e with max|gy| * 2^e in [2^14, 2^15), scale[1] = 2^-e; 1 when the maximum is 0 / Inf / NaN.
-__global__ void grad_scale_kernel(const float* __restrict__ amax, float* __restrict__ scale) {
-    const float m = *amax;
-    float s = 1.f, inv = 1.f;
-    if (m > 0.f && m < INFINITY) {
-        int e = 14 - (int)((__float_as_uint(m) >> 23) & 0xffu) + 127;       // exponent that moves m into [2^14, 2^15)
-        e = e > 120 ? 120 : (e < -120 ? -120 : e);
-        s = __uint_as_float((uint32_t)(e + 127) << 23);
-        inv = __uint_as_float((uint32_t)(127 - e) << 23);
-    }
-    scale[0] = s;
-    scale[1] = inv;
-}
-
 // gy [rows][K] float32 -> G [rows][Kp] float16 (scaled, zero-padded columns); 8 outputs per thread
 __global__ void __launch_bounds__(256) grad_to_f16_kernel(const float* __restrict__ gy, size_t rows, int K, int Kp,
                                                           const float* __restrict__ scale, __half* __restrict__ g) {
-    const float s = scale[0];
+    const float s = grad_scale(scale).x;
     const int k8 = Kp >> 3;
     const size_t total = rows * (size_t)k8;
     const bool vec = (K & 3) == 0;
@@ -358,7 +375,7 @@ __global__ void __launch_bounds__(256) wt_prep_kernel(const uint8_t* __restrict_
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ wacc, int K, int C, int Cp, int R, int S,
                                                              const float* __restrict__ scale, float post, float* __restrict__ dw,
                                                              long long so, long long sc, long long sr, long long ss) {
-    const float f = post * scale[1];
+    const float f = post * grad_scale(scale).y;
     const size_t total = (size_t)K * C * R * S;
     for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
         // idx enumerates the destination in (k, c, r, s) order (coalesced writes for a contiguous OIHW tensor)
@@ -458,8 +475,7 @@ int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes
     const size_t mout = (size_t)d->n * Ho * Wo;
     int rc;
     // G = float16(gy * 2^e)
-    if ((rc = slfp_absmax_f32(gy, mout * d->k, scale + 2, 1, (slfp_stream_t)st))) return rc;
-    grad_scale_kernel<<<1, 1, 0, st>>>(scale + 2, scale);
+    if ((rc = slfp_absmax_f32(gy, mout * d->k, scale, 1, (slfp_stream_t)st))) return rc;
     {
         const size_t tot = mout * (Kp / 8);
         const int grid = (int)std::min<size_t>((size_t)num_sms() * 16, ceil_div_sz(tot, 256));
