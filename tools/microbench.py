@@ -61,7 +61,7 @@ def bench_quant(kdiv=1.0):
 
 RESNET50_LAYERS = [
     # name, Cin, Cout, k, stride, pad, Hin
-    ("stem7x7", 3, 64, 7, 2, 3, 224), ("l1.c1 64-64 1x1", 64, 64, 1, 1, 0, 56), ("l1.c2 64-64 3x3", 64, 64, 3, 1, 1, 56),
+    ("stem7x7", 3, 64, 7, 2, 3, 224), ("s2dstem 16-64 4x4", 16, 64, 4, 1, 2, 112), ("l1.c1 64-64 1x1", 64, 64, 1, 1, 0, 56), ("l1.c2 64-64 3x3", 64, 64, 3, 1, 1, 56),
     ("l1.c3 64-256 1x1", 64, 256, 1, 1, 0, 56), ("l1.c1b 256-64 1x1", 256, 64, 1, 1, 0, 56),
     ("l2.c1 256-128 1x1", 256, 128, 1, 1, 0, 56), ("l2.c2 128-128 3x3 s2", 128, 128, 3, 2, 1, 56),
     ("l2.c3 128-512 1x1", 128, 512, 1, 1, 0, 28), ("l2.ds 256-512 1x1 s2", 256, 512, 1, 2, 0, 56),
