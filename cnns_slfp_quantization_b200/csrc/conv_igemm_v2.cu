@@ -49,7 +49,7 @@ constexpr int kBK = 64;
 constexpr int kCodeBytes = kBM * kBK;                  // 8 KB of codes per K block
 constexpr int kABytes = kBM * kBK * 2;                 // 16 KB float16 A tile
 constexpr int kLutBytes = 256 * 32 * 4;                // code -> f16, one copy per bank
-constexpr int kWarpCode = 0, kWarpWgt = 1, kWarpMma = 2;
+constexpr int kWarpCode = 0, kWarpWgt = 1, kWarpMma = 2, kWarpCode2 = 3;
 // 28 warps: 4 control (2 producers, MMA issuer, spare) + DW decode + (24 - DW) epilogue.  Two role splits, chosen
 // per layer on the host: DW = 16 for decode-heavy layers (3x3, large K), DW = 8 for epilogue-heavy ones (the 1x1
 // block tails: residual + float16 + codes).  Launched with 72 registers per thread, re-balanced with setmaxnreg:
@@ -641,11 +641,16 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // region against its own budget): producers / MMA / decode need few registers, the epilogue many
     if (warp < kDecWarp0) {
       ptx::setmaxnreg_dec<kRegsCtrl>();
-      if (warp == kWarpCode) {
-        // =========================== code producer: TMA im2col ===========================================
+      if (warp == kWarpCode || warp == kWarpCode2) {
+        // =========================== code producers: TMA im2col ==========================================
+        // TWO producer threads (warps 0 and 3), alternating K blocks.  One thread was the slowest stage of the
+        // stage-1 layers and the stem: its ~50 dependent instructions per K block (barrier probe, expect_tx, address
+        // arithmetic, up to four TMA issues) share a scheduler with six busy warps and took ~800 cycles per K block,
+        // while the decode warps idled on the `full` barrier (tools/role_profile.py: 58-78 % of their life).
         if (lane == 0) {
             PROF_VARS;
-            uint32_t cs = 0, cphase = 0;
+            const uint32_t mine = warp == kWarpCode ? 0u : 1u;
+            uint32_t cs = 0, cphase = 0, g = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const uint32_t m0 = (uint32_t)(tile / p.n_tiles) * kBM;
@@ -654,7 +659,19 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
                 const int w0 = wo * p.sw - p.pw, h0 = ho * p.sh - p.ph;
                 int tap = 0, r = 0, s = 0, cb = 0;       // GRAN 64: cb = 64-channel block; GRAN 16: 16-channel block
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+                    if ((g & 1u) != mine) {                 // the other producer's K block: only advance the counters
+                        if (GRAN == 64) {
+                            if (++cb == p.cblocks) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
+                        } else {
+                            int valid = p.taps * p.c16s - kb * 4;
+                            valid = valid > 4 ? 4 : valid;
+                            for (int j = 0; j < valid; ++j)
+                                if (++cb == p.c16s) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
+                        }
+                        if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
+                        continue;
+                    }
                     PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                     const uint32_t full = ptx::smem_u32(&bar_cfull[cs]);
                     const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
@@ -678,7 +695,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
                 }
             }
-            PROF_FLUSH(8);
+            if (mine == 0u) { PROF_FLUSH(8); }
         }
         __syncwarp();
     } else if (warp == kWarpWgt) {
