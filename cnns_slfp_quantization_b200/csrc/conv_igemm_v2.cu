@@ -601,7 +601,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 
     // warp index through a shuffle: tells the compiler it is warp-uniform, so role branches, barrier addresses and
     // the tcgen05 operands stay in uniform registers (no per-lane waterfall loops around UTCHMMA / UTCBAR)
-    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    // Role index `warp` = physical warp rotated by four: the control roles (0..3: TMA producers, MMA issuer) run on the
+    // PHYSICAL warps 24..27.  A scheduler picks the highest warp id among its eligible warps, so as warps 0..3 the
+    // single-thread roles only got the issue slots the decode / epilogue warps left over (the producers needed
+    // ~1 400 cycles per K block for ~50 instructions, tools/role_profile.py).  The rotation keeps warp % 4, i.e. the
+    // TMEM lane quadrant a warp may touch, and warpgroup alignment for setmaxnreg.
+    const int tid = threadIdx.x, pwarp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    const int warp = pwarp >= kWorkWarps ? pwarp - kWorkWarps : pwarp + kCtrlWarps;
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();     // would break the swizzle: fail loudly, never silently
 
     // ---- one-time setup ---------------------------------------------------------------------------
@@ -647,7 +653,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         // stage-1 layers and the stem: its ~50 dependent instructions per K block (barrier probe, expect_tx, address
         // arithmetic, up to four TMA issues) share a scheduler with six busy warps and took ~800 cycles per K block,
         // while the decode warps idled on the `full` barrier (tools/role_profile.py: 58-78 % of their life).
-        if (lane == 0) {
+        // The whole warp runs the loop converged and one elected lane issues (like the MMA issuer): every operand of
+        // the TMA / mbarrier instructions then lives in uniform registers - the per-lane form cost ~45 instructions
+        // per K block in R2UR moves and an ELECT waterfall loop around each UTMALDG.
+        {
             PROF_VARS;
             const uint32_t mine = warp == kWarpCode ? 0u : 1u;
             uint32_t cs = 0, cphase = 0, g = 0;
@@ -676,31 +685,37 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     const uint32_t full = ptx::smem_u32(&bar_cfull[cs]);
                     const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
                     if (GRAN == 64) {
-                        ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes);
-                        if (kb >= p.nkb1)           // concatenated second input: 1x1 window at (ho*sh2, wo*sw2)
-                            ptx::tma_load_im2col_4d(dst, &tmap_x2, full, (kb - p.nkb1) * 64, wo * p.sw2, ho * p.sh2, n, 0, 0);
-                        else if (p.plain_1x1) ptx::tma_load_2d(dst, &tmap_x, full, cb * 64, (int)m0);
-                        else ptx::tma_load_im2col_4d(dst, &tmap_x, full, cb * 64, w0, h0, n, (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
+                        if (ptx::elect_one()) {
+                            ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes);
+                            if (kb >= p.nkb1)           // concatenated second input: 1x1 window at (ho*sh2, wo*sw2)
+                                ptx::tma_load_im2col_4d(dst, &tmap_x2, full, (kb - p.nkb1) * 64, wo * p.sw2, ho * p.sh2, n, 0, 0);
+                            else if (p.plain_1x1) ptx::tma_load_2d(dst, &tmap_x, full, cb * 64, (int)m0);
+                            else ptx::tma_load_im2col_4d(dst, &tmap_x, full, cb * 64, w0, h0, n, (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
+                        }
+                        __syncwarp();
                         if (++cb == p.cblocks) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
                     } else {
                         int valid = p.taps * p.c16s - kb * 4;          // 16-channel pieces left in K
                         valid = valid > 4 ? 4 : valid;
-                        ptx::mbar_arrive_expect_tx(full, (uint32_t)(valid * (kCodeBytes / 4)));
+                        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full, (uint32_t)(valid * (kCodeBytes / 4)));
+                        __syncwarp();
                         for (int j = 0; j < valid; ++j) {
-                            ptx::tma_load_im2col_4d(dst + (uint32_t)(j * (kCodeBytes / 4)), &tmap_x, full, cb * 16, w0, h0, n,
-                                                    (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
+                            if (ptx::elect_one())
+                                ptx::tma_load_im2col_4d(dst + (uint32_t)(j * (kCodeBytes / 4)), &tmap_x, full, cb * 16, w0, h0, n,
+                                                        (uint16_t)(s * p.dw), (uint16_t)(r * p.dh));
+                            __syncwarp();
                             if (++cb == p.c16s) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
                         }
                     }
                     if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
                 }
             }
-            if (mine == 0u) { PROF_FLUSH(8); }
+            if (mine == 0u && lane == 0) { PROF_FLUSH(8); }
         }
         __syncwarp();
     } else if (warp == kWarpWgt) {
         // =========================== weight producer: TMA tiles (B operand) ================================
-        if (lane == 0) {
+        {
             PROF_VARS;
             uint32_t stage = 0, phase = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
@@ -709,12 +724,15 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                     const uint32_t full = ptx::smem_u32(&bar_full[stage]);
-                    ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
-                    ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
+                        ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
+                    }
+                    __syncwarp();
                     if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
-            PROF_FLUSH(12);
+            if (lane == 0) { PROF_FLUSH(12); }
         }
         __syncwarp();
     } else if (warp == kWarpMma) {
@@ -864,7 +882,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         // =========================== epilogue ===================================================================
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
         const int half = (warp - kEpiWarp0) >> 2;
-        const int etid = tid - kEpiWarp0 * 32;
+        const int etid = (warp - kEpiWarp0) * 32 + lane;
         const int mode = p.epi_mode;
         const bool sfp33 = p.epi.next_fmt == SLFP_FMT_SFP33_RELU;
         const uint32_t s_mul = ptx::smem_u32(s_par), s_add = s_mul + BLOCK_N * 4;

@@ -19,7 +19,7 @@ assert rt.cudaHostGetDevicePointer(ctypes.byref(dptr), ctypes.c_void_p(buf.data_
 nv.check(lib.slfp_debug_set_buffer(dptr))
 mb.bench_conv(mode=sys.argv[1], only=sys.argv[2], iters=1)
 torch.cuda.synchronize()
-names = {8: ("code producer", "wait cempty", "-", "-"), 12: ("weight producer", "wait empty", "-", "-"),
+names = {8: ("code producer", "wait cempty", "expect_tx", "tma issue"), 12: ("weight producer", "wait empty", "-", "-"),
          16: ("mma issuer", "wait tempty", "wait full", "issue+commit"), 20: ("decode warp 0", "wait cfull", "wait empty", "work"),
          24: ("epilogue warp 0", "wait tfull", "-", "-")}
 for slot, (role, a, b, c) in names.items():
