@@ -928,7 +928,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             // Rows >= M and columns >= Kout are clipped by TMA.
             const int cg = half;                                                      // 32-column group 0..3
             const int r = quad * 32 + lane;
-            const bool leader = warp == kEpiWarp0 && lane == 0;
+            // the staging TMA traffic is issued by ONE elected lane of the first epilogue warp, which reaches these points
+            // converged: operands stay in uniform registers (no R2UR / ELECT waterfall around every UTMALDG / UTMASTG)
+            const bool lead_warp = warp == kEpiWarp0;
+#define SLFP_LEADER (lead_warp && ptx::elect_one())
             const bool has_res = p.epi.residual != nullptr, has_y16 = p.epi.y_f16 != nullptr;
             const bool has_c1 = p.epi.y_codes != nullptr, has_c2 = p.epi.y_codes2 != nullptr;
             constexpr uint32_t kHalfIo = kBM * 128;                                   // one [128 x 64] float16 half
@@ -948,7 +951,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 ptx::tma_load_2d(io0 + buf * C::kIoBytes, &omaps.res, bres + buf * 8u, c0, r0);
                 if (two) ptx::tma_load_2d(io0 + buf * C::kIoBytes + kHalfIo, &omaps.res, bres + buf * 8u, c0 + 64, r0);
             };
-            if (leader && my_tiles > 0) load_res((int)blockIdx.x, 0u);
+            if (my_tiles > 0 && SLFP_LEADER) load_res((int)blockIdx.x, 0u);
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const uint32_t buf = (uint32_t)ti & 1u;
@@ -997,7 +1000,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     if (ch == 0) {
                         // the previous tile's stores must have drained the staging tiles before anything is written;
                         // the same moment frees the other float16 buffer for the next tile's residual
-                        if (leader) {
+                        if (SLFP_LEADER) {
                             ptx::bulk_wait_read0();
                             if (ti + 1 < my_tiles) load_res(tile + (int)gridDim.x, buf ^ 1u);
                         }
@@ -1026,7 +1029,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
                 ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
                 ptx::bar_sync(1, kEpiWarps * 32);
-                if (leader) {
+                if (SLFP_LEADER) {
                     const int c0 = (tile % p.n_tiles) * BLOCK_N, r0 = (tile / p.n_tiles) * kBM;
                     if (has_y16) {
                         ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes, c0, r0);
@@ -1037,7 +1040,8 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     ptx::bulk_commit();
                 }
             }
-            if (leader) ptx::bulk_wait0();
+            if (SLFP_LEADER) ptx::bulk_wait0();
+#undef SLFP_LEADER
         } else
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
