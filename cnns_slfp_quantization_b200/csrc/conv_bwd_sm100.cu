@@ -125,8 +125,8 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     };
 
     if (warp == 0) {
-        // =========================== TMA producer =========================================================
-        if (lane == 0) {
+        // =========================== TMA producer (converged warp, one elected lane issues) ===============
+        {
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < my_items; ++it) {
                 const int item = (int)blockIdx.x + it * (int)gridDim.x;
@@ -144,9 +144,12 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 1u | ((uint32_t)kb << 8));
                         const uint32_t full = ptx::smem_u32(&bar_full[stage]);
                         const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-                        ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kStageBytes);
-                        ptx::tma_load_im2col_4d(sa, &tmap_a, full, kc * 64, w0, h0, n, p.off_w[t], p.off_h[t]);
-                        ptx::tma_load_2d(sa + kABytes, &tmap_b, full, kb * kBK, n0);
+                        if (ptx::elect_one()) {
+                            ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kStageBytes);
+                            ptx::tma_load_im2col_4d(sa, &tmap_a, full, kc * 64, w0, h0, n, p.off_w[t], p.off_h[t]);
+                            ptx::tma_load_2d(sa + kABytes, &tmap_b, full, kb * kBK, n0);
+                        }
+                        __syncwarp();
                         if (++kc == p.kchunks) { kc = 0; ++t; }
                         if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
                     }
@@ -164,12 +167,17 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 1u | ((uint32_t)kb << 8));
                         const uint32_t full = ptx::smem_u32(&bar_full[stage]);
                         const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-                        ptx::mbar_arrive_expect_tx(full, (uint32_t)(kABytes + nu * 8192));
-                        ptx::tma_load_2d(sa, &tmap_a, full, ko0, (int)pix0);
-                        ptx::tma_load_2d(sa + 8192, &tmap_a, full, ko0 + 64, (int)pix0);
+                        if (ptx::elect_one()) {
+                            ptx::mbar_arrive_expect_tx(full, (uint32_t)(kABytes + nu * 8192));
+                            ptx::tma_load_2d(sa, &tmap_a, full, ko0, (int)pix0);
+                            ptx::tma_load_2d(sa + 8192, &tmap_a, full, ko0 + 64, (int)pix0);
+                        }
+                        __syncwarp();
                         for (int u = 0; u < nu; ++u) {
                             const int unit = u0 + u, tap = unit / p.cchunks, cc = unit - tap * p.cchunks;
-                            ptx::tma_load_im2col_4d(sa + kABytes + u * 8192, &tmap_b, full, cc * 64, w0, h0, n, p.off_w[tap], p.off_h[tap]);
+                            if (ptx::elect_one())
+                                ptx::tma_load_im2col_4d(sa + kABytes + u * 8192, &tmap_b, full, cc * 64, w0, h0, n, p.off_w[tap], p.off_h[tap]);
+                            __syncwarp();
                         }
                         if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
                     }
