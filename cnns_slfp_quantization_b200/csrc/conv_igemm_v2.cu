@@ -962,6 +962,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const uint32_t io = io0 + buf * C::kIoBytes + io_t;
                 // both 16-column chunks leave TMEM at once; the accumulator buffer is released before any arithmetic
                 uint32_t acc[2][16];
+                uint32_t cw[2][2][4];                                                // packed codes [consumer][chunk]
                 const uint32_t tcol = tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32);
                 if (nvalid > 0) ptx::tmem_ld16(tcol, acc[0]);
                 if (nvalid > 1) ptx::tmem_ld16(tcol + 16u, acc[1]);
@@ -998,13 +999,16 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         }
                     }
                     if (ch == 0) {
-                        // the previous tile's stores must have drained the staging tiles before anything is written;
-                        // the same moment frees the other float16 buffer for the next tile's residual
+                        // The previous tile's stores must have drained the other float16 buffer before the next tile's
+                        // residual lands in it, and the code staging tiles before this tile's codes are written.  Only the
+                        // leader's warp waits here; everybody else goes on with the arithmetic and the in-place float16
+                        // update (this tile's float16 buffer is not read by any pending store) and meets the leader at the
+                        // barrier below, by which time the drain is long over.
                         if (SLFP_LEADER) {
                             ptx::bulk_wait_read0();
                             if (ti + 1 < my_tiles) load_res(tile + (int)gridDim.x, buf ^ 1u);
                         }
-                        ptx::bar_sync(1, kEpiWarps * 32);
+                        __syncwarp();
                     }
                     if (!live) continue;
                     if (has_y16) {
@@ -1022,9 +1026,19 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #pragma unroll
                         for (int i = 0; i < 16; ++i)      // encode_relu_fast_raw16 with run-time format constants
                             t[i] = (int32_t)(__float_as_uint(__saturatef(v[i] * sc)) >> enc_sh) - enc_base;
-                        ptx::sts128((pass ? co2 : co1) + row_off + (((uint32_t)(cg * 2 + ch) ^ sw) << 4), ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]),
-                                    ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]), ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]),
-                                    ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) cw[pass][ch][i] = ptx::pack_sat_u8x4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+                    }
+                }
+                ptx::bar_sync(1, kEpiWarps * 32);          // the leader has seen the code staging tiles drained
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    if (ch >= nvalid) continue;
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (!(pass ? has_c2 : has_c1)) continue;
+                        ptx::sts128((pass ? co2 : co1) + row_off + (((uint32_t)(cg * 2 + ch) ^ sw) << 4), cw[pass][ch][0], cw[pass][ch][1],
+                                    cw[pass][ch][2], cw[pass][ch][3]);
                     }
                 }
                 ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
