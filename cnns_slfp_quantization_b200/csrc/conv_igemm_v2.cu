@@ -1005,7 +1005,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         // update (this tile's float16 buffer is not read by any pending store) and meets the leader at the
                         // barrier below, by which time the drain is long over.
                         if (SLFP_LEADER) {
-                            ptx::bulk_wait_read0();
+                            PROF(b, ptx::bulk_wait_read0());
                             if (ti + 1 < my_tiles) load_res(tile + (int)gridDim.x, buf ^ 1u);
                         }
                         __syncwarp();
@@ -1030,7 +1030,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         for (int i = 0; i < 4; ++i) cw[pass][ch][i] = ptx::pack_sat_u8x4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
                     }
                 }
-                ptx::bar_sync(1, kEpiWarps * 32);          // the leader has seen the code staging tiles drained
+                PROF(c, ptx::bar_sync(1, kEpiWarps * 32));          // the leader has seen the code staging tiles drained
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     if (ch >= nvalid) continue;
@@ -1042,7 +1042,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     }
                 }
                 ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
-                ptx::bar_sync(1, kEpiWarps * 32);
+                PROF(c, ptx::bar_sync(1, kEpiWarps * 32));
                 if (SLFP_LEADER) {
                     const int c0 = (tile % p.n_tiles) * BLOCK_N, r0 = (tile / p.n_tiles) * kBM;
                     if (has_y16) {

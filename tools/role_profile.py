@@ -21,7 +21,7 @@ mb.bench_conv(mode=sys.argv[1], only=sys.argv[2], iters=1)
 torch.cuda.synchronize()
 names = {8: ("code producer", "wait cempty", "expect_tx", "tma issue"), 12: ("weight producer", "wait empty", "-", "-"),
          16: ("mma issuer", "wait tempty", "wait full", "issue+commit"), 20: ("decode warp 0", "wait cfull", "wait empty", "work"),
-         24: ("epilogue warp 0", "wait tfull", "-", "-")}
+         24: ("epilogue warp 0", "wait tfull", "leader: store drain (staged)", "barriers (staged)")}
 for slot, (role, a, b, c) in names.items():
     va, vb, vc, tot = [int(buf[slot + i]) for i in range(4)]
     if tot == 0:
