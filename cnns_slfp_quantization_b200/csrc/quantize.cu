@@ -438,6 +438,7 @@ struct WPrepArgs {
     const float* row_scale;
     uint32_t mg_pitch, sh_pitch, mg_cp, sh_cp, mg_s, sh_s;   // n / d == umulhi(n, mg) >> sh for n < 2^31 (d > 1)
     DivK dk;                                                 // kw with its reciprocal: exact x / kw without the division sequence
+    int vec8_ok;                                             // rows, offsets and pointers allow the 8-element vector path
 };
 
 // shared-memory tables of the weight-preparation kernels: bucket table of the SLFP weight encoder, code -> float32
@@ -497,6 +498,45 @@ __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, cons
     if (a.w_codes) a.w_codes[o] = (uint8_t)code;
 }
 
+// Eight consecutive destination elements (same k and tap, eight channels: c_phys % 8 == 0) per thread: the index
+// arithmetic - three magic divisions and the 64-bit strided source address, ~150 of the ~175 instructions the
+// per-element form spent (ncu: the batched kernel was issue-bound at 85 % SM throughput, not memory-bound) - is done
+// once, the eight gathers are independent, and the float16 / code rows leave as one 16-byte / 8-byte store.  Padding
+// channels and K-padding taps read as 0, which every format encodes as code 0 / value 0.
+template <int FMT>
+__device__ __forceinline__ void wprep_vec8(const WPrepArgs& a, size_t i, const WPrepTables& tb) {
+    const uint32_t i32 = (uint32_t)i, pitch = (uint32_t)a.pitch;
+    const int k = (int)div_magic(i32, pitch, a.mg_pitch, a.sh_pitch);
+    const uint32_t j = i32 - (uint32_t)k * pitch;
+    const int rs = (int)div_magic(j, (uint32_t)a.Cp, a.mg_cp, a.sh_cp);
+    const int c0 = (int)(j - (uint32_t)rs * (uint32_t)a.Cp);
+    const bool tap_in = rs < a.R * a.S;
+    const int r = (int)div_magic((uint32_t)rs, (uint32_t)a.S, a.mg_s, a.sh_s), s_ = rs - r * a.S;
+    const float* src = a.w + (k * a.so + r * a.sr + s_ * a.ss);
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = (tap_in && c0 + e < a.C) ? __ldg(src + (c0 + e) * a.sc) : 0.0f;
+    const float rsk = a.row_scale ? __ldg(a.row_scale + k) : 1.0f;
+    uint32_t hw[4], cw[2] = {0u, 0u};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float v = div_k(x[e], a.dk);                   // == IEEE x / kw
+        uint32_t code = 0;
+        float fq = v;
+        if (FMT >= 0) {
+            code = FMT == SLFP_FMT_SLFP34_WGT ? encode_wgt_bucket(v, tb.bucket) : encode<FMT < 0 ? 0 : FMT>(v);
+            fq = tb.dec[code];
+        }
+        if (a.w_fakeq && tap_in && c0 + e < a.C) a.w_fakeq[(((size_t)k * a.C + c0 + e) * a.R + r) * a.S + s_] = fq;
+        const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(a.row_scale ? fq * rsk : fq));
+        if (e & 1) hw[e >> 1] |= h << 16; else hw[e >> 1] = h;
+        cw[e >> 2] |= code << (8 * (e & 3));
+    }
+    const size_t o = (size_t)k * a.out_pitch + a.out_off + j;
+    if (a.w_f16) *reinterpret_cast<uint4*>(a.w_f16 + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (a.w_codes) *reinterpret_cast<uint2*>(a.w_codes + o) = make_uint2(cw[0], cw[1]);
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
     __shared__ uint32_t s_tab[16];
@@ -540,6 +580,14 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const __grid_constant_
     const unsigned first = lo ? b.blk_end[lo - 1] : 0u;
     const size_t total = (size_t)a.K * a.pitch;
     const size_t base = (size_t)(blockIdx.x - first) * kWBatchChunk;
+    // 16-byte / 8-byte vector stores need 8-element alignment of every output row and pointer (checked on the host
+    // side of the jobs call: vec8_ok), and eight consecutive elements inside one tap need c_phys % 8 == 0
+    if (a.vec8_ok) {
+        static_assert(kWBatchChunk == 256 * 8, "one 8-element vector per thread");
+        const size_t i = base + (size_t)threadIdx.x * 8;
+        if (i < total) wprep_vec8<FMT>(a, i, tb);
+        return;
+    }
 #pragma unroll 2
     for (int j = 0; j < kWBatchChunk / 256; ++j) {
         const size_t i = base + (size_t)j * 256 + threadIdx.x;
@@ -693,7 +741,7 @@ static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long 
     else { a.C = d->c; a.Cp = d->c_phys; }
     a.pitch = slfp_conv_wpitch(d);
     a.kw = kw; a.dk = make_divk(kw); a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
-    a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr;
+    a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr; a.vec8_ok = 0;
     if ((size_t)a.K * a.pitch >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^31 or more elements");
     magic_u32((uint32_t)a.pitch, a.mg_pitch, a.sh_pitch);
     magic_u32((uint32_t)a.Cp, a.mg_cp, a.sh_cp);
@@ -742,6 +790,9 @@ extern "C" int slfp_prepare_weights_jobs(int n, const SlfpWeightJob* host_jobs, 
                 a.out_pitch = jb.out_pitch; a.out_off = jb.out_offset;
             }
             a.row_scale = jb.row_scale;
+            a.vec8_ok = ((a.Cp & 7) == 0 && (a.pitch & 7) == 0 && (a.out_pitch & 7) == 0 && (a.out_off & 7) == 0 &&
+                         (((uintptr_t)a.w_f16) & 15u) == 0 && (((uintptr_t)a.w_codes) & 7u) == 0 &&
+                         getenv("SLFP_WPREP_SCALAR") == nullptr) ? 1 : 0;
             const size_t total = (size_t)a.K * a.pitch;
             if (total == 0) continue;
             if (total >= (1ull << 32)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights_jobs: tensor with 2^32 or more elements");
