@@ -546,6 +546,11 @@ __global__ void __launch_bounds__(256) wprep_kernel(WPrepArgs a) {
     wprep_tables_init<FMT>(tb, s_tab);
     __syncthreads();
     const size_t total = (size_t)a.K * a.pitch;
+    if (a.vec8_ok) {
+        for (size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 8; i < total; i += (size_t)gridDim.x * 256 * 8)
+            wprep_vec8<FMT>(a, i, tb);
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256)
         wprep_element<FMT>(a, i, tb);
 }
@@ -583,9 +588,12 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const __grid_constant_
     // 16-byte / 8-byte vector stores need 8-element alignment of every output row and pointer (checked on the host
     // side of the jobs call: vec8_ok), and eight consecutive elements inside one tap need c_phys % 8 == 0
     if (a.vec8_ok) {
-        static_assert(kWBatchChunk == 256 * 8, "one 8-element vector per thread");
-        const size_t i = base + (size_t)threadIdx.x * 8;
-        if (i < total) wprep_vec8<FMT>(a, i, tb);
+        static_assert(kWBatchChunk % (256 * 8) == 0, "whole 8-element vectors per thread");
+#pragma unroll 1
+        for (int j = 0; j < kWBatchChunk / (256 * 8); ++j) {
+            const size_t i = base + ((size_t)j * 256 + threadIdx.x) * 8;
+            if (i < total) wprep_vec8<FMT>(a, i, tb);
+        }
         return;
     }
 #pragma unroll 2
@@ -741,7 +749,9 @@ static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long 
     else { a.C = d->c; a.Cp = d->c_phys; }
     a.pitch = slfp_conv_wpitch(d);
     a.kw = kw; a.dk = make_divk(kw); a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
-    a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr; a.vec8_ok = 0;
+    a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr;
+    a.vec8_ok = ((a.Cp & 7) == 0 && (a.pitch & 7) == 0 && (((uintptr_t)a.w_f16) & 15u) == 0 && (((uintptr_t)a.w_codes) & 7u) == 0 &&
+                 getenv("SLFP_WPREP_SCALAR") == nullptr) ? 1 : 0;
     if ((size_t)a.K * a.pitch >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^31 or more elements");
     magic_u32((uint32_t)a.pitch, a.mg_pitch, a.sh_pitch);
     magic_u32((uint32_t)a.Cp, a.mg_cp, a.sh_cp);
