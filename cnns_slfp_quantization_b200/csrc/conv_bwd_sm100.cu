@@ -28,8 +28,11 @@
 namespace slfp {
 namespace bwd {
 
-constexpr int kBM = 128, kBK = 64, kStages = 4;
-constexpr int kABytes = kBM * kBK * 2;
+constexpr int kBM = 128, kBK = 64, kMaxStages = 4;
+// wgrad stages hold 128 reduction pixels (dgrad: 64 k elements = one 128-byte row): every TMA load costs >= ~190 cycles
+// whatever its size (tools/ubench/tma_box.cu), and a wgrad stage needs six of them (2 gy boxes + up to 4 im2col boxes) -
+// with 64 pixels per stage that was 1 140 TMA cycles against 512 MMA cycles.
+constexpr int kWgradPix = 128;
 constexpr int kMaxTaps = 32;
 constexpr int kThreads = 192;
 
@@ -51,8 +54,12 @@ struct Params {
     float post;
 };
 
-template <int BN> struct Cfg {
-    static constexpr int kBBytes = BN * kBK * 2;
+template <int BN, int MODE> struct Cfg {
+    static constexpr int kKB = MODE == 1 ? kWgradPix : kBK;                  // reduction elements per stage
+    static constexpr int kStages = MODE == 1 ? (BN > 128 ? 2 : (BN > 64 ? 3 : 4)) : 4;
+    static constexpr int kABytes = kBM * kKB * 2;
+    static constexpr int kBBytes = BN * kKB * 2;
+    static constexpr int kBoxBytes = 64 * kKB * 2;                           // one 64-wide MN-major box (wgrad)
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);
     static constexpr int kBufCols = kTmemCols / 2;
@@ -82,12 +89,13 @@ __device__ __forceinline__ float2 grad_scale(const float* __restrict__ amax) {
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, MODE>;
+    constexpr int kStages = C::kStages, kABytes = C::kABytes;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes);
     uint64_t* bar_full = s_bar;                 // [kStages] 1 arrive.expect_tx
-    uint64_t* bar_empty = bar_full + kStages;   // [kStages] 1 tcgen05.commit
-    uint64_t* bar_tfull = bar_empty + kStages;  // [2]
+    uint64_t* bar_empty = bar_full + kMaxStages;   // [kStages] 1 tcgen05.commit
+    uint64_t* bar_tfull = bar_empty + kMaxStages;  // [2]
     uint64_t* bar_tempty = bar_tfull + 2;       // [2] 4 epilogue warps
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
 
@@ -159,7 +167,7 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const int u0 = (tile % p.ugroups) * (BN / 64);
                     const int nu = min(BN / 64, p.units - u0);
                     for (int kb = 0; kb < nkb; ++kb) {
-                        const uint32_t pix0 = (uint32_t)(kb0 + kb) * (uint32_t)kBK;
+                        const uint32_t pix0 = (uint32_t)(kb0 + kb) * (uint32_t)C::kKB;
                         const int n = (int)(pix0 / (uint32_t)p.HiWj);
                         const int rem = (int)(pix0 - (uint32_t)n * (uint32_t)p.HiWj);
                         const int ho = rem / p.Wj, wo = rem - ho * p.Wj;
@@ -168,15 +176,15 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         const uint32_t full = ptx::smem_u32(&bar_full[stage]);
                         const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
                         if (ptx::elect_one()) {
-                            ptx::mbar_arrive_expect_tx(full, (uint32_t)(kABytes + nu * 8192));
+                            ptx::mbar_arrive_expect_tx(full, (uint32_t)(kABytes + nu * C::kBoxBytes));
                             ptx::tma_load_2d(sa, &tmap_a, full, ko0, (int)pix0);
-                            ptx::tma_load_2d(sa + 8192, &tmap_a, full, ko0 + 64, (int)pix0);
+                            ptx::tma_load_2d(sa + C::kBoxBytes, &tmap_a, full, ko0 + 64, (int)pix0);
                         }
                         __syncwarp();
                         for (int u = 0; u < nu; ++u) {
                             const int unit = u0 + u, tap = unit / p.cchunks, cc = unit - tap * p.cchunks;
                             if (ptx::elect_one())
-                                ptx::tma_load_im2col_4d(sa + kABytes + u * 8192, &tmap_b, full, cc * 64, w0, h0, n, p.off_w[tap], p.off_h[tap]);
+                                ptx::tma_load_im2col_4d(sa + kABytes + u * C::kBoxBytes, &tmap_b, full, cc * 64, w0, h0, n, p.off_w[tap], p.off_h[tap]);
                             __syncwarp();
                         }
                         if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
@@ -189,7 +197,7 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // =========================== MMA issuer (converged warp, one elected lane) ========================
         constexpr uint32_t idesc = ptx::make_idesc(0u, kBM, BN) | (MODE == 1 ? ((1u << 15) | (1u << 16)) : 0u);
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
-        constexpr uint32_t kLbo = MODE == 1 ? (8192u >> 4) : 1u;                 // MN-major: next 64-element atom along M / N
+        constexpr uint32_t kLbo = MODE == 1 ? ((uint32_t)C::kBoxBytes >> 4) : 1u;  // MN-major: next 64-element atom along M / N
         constexpr uint32_t kStep = MODE == 1 ? (2048u >> 4) : 2u;                // start-address advance per K = 16
         const uint32_t base_lo = ((ptx::smem_u32(smem) >> 4) & 0x3fffu) | (kLbo << 16);
         uint32_t stage = 0, phase = 0;
@@ -208,7 +216,7 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const uint32_t a_lo = base_lo + stage * (uint32_t)(C::kStageBytes >> 4);
                     const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)
+                    for (int k = 0; k < C::kKB / 16; ++k)
                         ptx::mma_f16_ss(d_tmem, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + kStep * k),
                                         ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + kStep * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     ptx::mma_commit(ptx::smem_u32(&bar_empty[stage]));
@@ -407,7 +415,7 @@ static PFN driver_fn(const char* name) {
 
 template <int BN, int MODE>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, MODE>;
     auto kern = conv_bwd_kernel<BN, MODE>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -603,7 +611,7 @@ int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes
         p.ugroups = (p.units + upt - 1) / upt;
         const int ko_tiles = (d->k + kBM - 1) / kBM;
         const int tiles = ko_tiles * p.ugroups;
-        p.pb_total = (int)((mout + kBK - 1) / kBK);
+        p.pb_total = (int)((mout + kWgradPix - 1) / kWgradPix);
         int splits = std::max(1, (2 * num_sms()) / tiles);
         splits = std::min(splits, p.pb_total);
         p.pb_per_split = (p.pb_total + splits - 1) / splits;
@@ -618,7 +626,7 @@ int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes
             // G as [pixels][Kp]; the buffer carries 64 zeroed rows of slack so the last 64-pixel box stays inside it
             const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)mout};
             const cuuint64_t gstr[1] = {(cuuint64_t)Kp * 2};
-            const cuuint32_t box[2] = {64u, (cuuint32_t)kBK};
+            const cuuint32_t box[2] = {64u, (cuuint32_t)kWgradPix};
             const cuuint32_t estr[2] = {1, 1};
             CUresult cr = enc_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, G, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -630,7 +638,7 @@ int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes
             const int lower[2] = {-d->pad_w, -d->pad_h};
             const int upper[2] = {d->pad_w - (d->s - 1) * d->dil_w, d->pad_h - (d->r - 1) * d->dil_h};
             const cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
-            CUresult cr = enc_im2col(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, Xh, gdim, gstr, lower, upper, 64u, (cuuint32_t)kBK, estr,
+            CUresult cr = enc_im2col(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, Xh, gdim, gstr, lower, upper, 64u, (cuuint32_t)kWgradPix, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_bwd: cuTensorMapEncodeIm2col(X) failed (%d)", (int)cr);
