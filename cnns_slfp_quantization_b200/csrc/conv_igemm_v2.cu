@@ -718,13 +718,21 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         {
             PROF_VARS;
             uint32_t stage = 0, phase = 0;
+            // Resident weights: with a single N tile and a K-block count that divides the ring depth, stage s always holds
+            // K block s % num_kb of the same filter - after the first pass over the ring the producer only arrives on the
+            // barrier.  Every TMA load costs >= ~190 cycles of the TMA unit whatever its size (tools/ubench/tma_box.cu), and
+            // the space-to-depth stem, at 4 code loads + 1 weight load per K block, ran exactly at that floor.
+            const bool w_res = p.n_tiles == 1 && p.num_kb <= C::kStages && (C::kStages % p.num_kb) == 0;
+            uint32_t issued = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const int n0 = (tile % p.n_tiles) * BLOCK_N;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = 0; kb < p.num_kb; ++kb, ++issued) {
                     PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                     const uint32_t full = ptx::smem_u32(&bar_full[stage]);
-                    if (ptx::elect_one()) {
+                    if (w_res && issued >= (uint32_t)C::kStages) {
+                        if (ptx::elect_one()) ptx::mbar_arrive(full);
+                    } else if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
                         ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
                     }
