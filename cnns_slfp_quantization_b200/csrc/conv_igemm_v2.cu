@@ -658,6 +658,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         // per K block in R2UR moves and an ELECT waterfall loop around each UTMALDG.
         {
             PROF_VARS;
+            static_assert(kCodeStages % 2 == 0, "the two producers alternate K blocks: a stage must always be filled by the same one");
             const uint32_t mine = warp == kWarpCode ? 0u : 1u;
             uint32_t cs = 0, cphase = 0, g = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
