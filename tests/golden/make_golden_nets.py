@@ -39,6 +39,12 @@ def ref_net(name, qbit):
     if name == "mobilenetv1_imgnet":
         from nets_imgnet.mobilenetv1 import MobileNetV1_Q
         return MobileNetV1_Q(3, qbit)
+    if name == "shufflenetv2":
+        from nets_cifar.shufflenet_v2 import ShuffleNetV2
+        m = ShuffleNetV2(qbit)
+        m.reset_layer_inputs_outputs()            # the reference's forward needs these dicts (shufflenet_v2.py:175-183, :197)
+        m.reset_layer_weights()
+        return m
     raise KeyError(name)
 
 
@@ -55,11 +61,17 @@ def calibrate(name, sd, x):
     return ka, kw
 
 
-CASES = [("resnet50", 8, 8, 64), ("vgg16", 8, 8, 32), ("mobilenetv1_cifar", 8, 8, 32), ("mobilenetv1_imgnet", 7, 4, 224)]
+CASES = [("resnet50", 8, 8, 64), ("vgg16", 8, 8, 32), ("mobilenetv1_cifar", 8, 8, 32), ("mobilenetv1_imgnet", 7, 4, 224),
+         ("shufflenetv2", 7, 8, 32)]
 
 if __name__ == "__main__":
-    out = {}
+    # `make_golden_nets.py NAME ...` regenerates only the named cases and keeps the others of the existing fixture
+    only = sys.argv[1:]
+    path = os.path.join(HERE, "net_cases.npz")
+    out = dict(np.load(path)) if only and os.path.exists(path) else {}
     for name, qbit, batch, size in CASES:
+        if only and name not in only:
+            continue
         x = nc.synth_images(batch, size)
         m0 = ref_net(name, 32).eval()
         sd = nc.synth_state_dict(m0)

@@ -343,6 +343,33 @@ def test_whole_net_against_reference_fixture(name):
     assert float(np.sqrt(((ye - ym) ** 2).mean())) <= 0.45 * float(ref.std())
 
 
+def test_shufflenetv2_modules_against_reference_fixture():
+    """ShuffleNetV2 x1 (57 quantized layers: depthwise 3x3 at 24 / 58 / 116 / 232 channels, 1x1 convs with channel
+    counts that are not multiples of 16, layerout_quantize after BatchNorm, channel shuffle) through the module-level
+    drop-in at SFP-7, against logits computed by the REFERENCE net on CPU.  Same criteria as the other nets."""
+    sys.path.insert(0, ROOT)
+    from tools.netcheck import prepare, G
+    from cnns_slfp_quantization_b200 import nets_common as nc
+    m, comp, batch, size = prepare("shufflenetv2")
+    assert comp is None
+    x = nc.synth_images(batch, size).cuda()
+    ref = G["shufflenetv2.logits"]
+    with torch.no_grad():
+        y = m(x.contiguous(memory_format=torch.channels_last)).float().cpu().numpy()
+    assert np.isfinite(y).all()
+    rms = float(np.sqrt(((y - ref) ** 2).mean()))
+    assert rms <= 0.45 * float(ref.std()), (rms, float(ref.std()))
+    srt = np.sort(ref, 1)
+    clear = (srt[:, -1] - srt[:, -2]) > 4.0 * rms
+    assert (y.argmax(1)[clear] == ref.argmax(1)[clear]).all(), (y.argmax(1).tolist(), ref.argmax(1).tolist())
+    # calibration taps: recorded only after the reset calls (the reference requires them; here forward() works without)
+    assert not hasattr(m, "layer_inputs")
+    m.reset_layer_inputs_outputs(); m.reset_layer_weights()
+    with torch.no_grad():
+        m(x)
+    assert len(m.get_layer_inputs()) == 57 and len(m.get_layer_weights()) == 57 and 55 in m.get_layer_outputs()
+
+
 def test_plan_is_stable_and_deterministic_over_many_steps():
     """Regression for the code-ring hazard (a decode group one barrier phase ahead of a TMA load that landed late: stale
     codes, then an `unspecified launch failure` about once per 1 000 steps, only with the weights re-quantized between

@@ -49,3 +49,31 @@ for name, ctor, qbit, batch, size, comp in CASES:
         print("  ", {k: round(sum(x.elapsed_time(y) for x, y, _ in v), 4) for k, v in prof.items()})
     print(json.dumps({"net": name, "batch": batch, "size": size, "ms_per_step": round(ms, 4), "images_per_s": round(batch / ms * 1e3, 1),
                       "launches": plan.launches_per_step, "tflops": round(plan.flops / ms / 1e9, 1)}), flush=True)
+
+# ShuffleNetV2 x1 (BASELINE config 5's second net): no fused plan yet - the module-level drop-in (float32 between layers,
+# stock BatchNorm / ReLU / channel shuffle), SFP-7, calibrated scales, eager launches timed with CUDA events.
+from cnns_slfp_quantization_b200.nets_cifar import ShuffleNetV2
+for batch, size in ((512, 32), (64, 224)):
+    m32 = ShuffleNetV2(32).eval()
+    sd = nc.synth_state_dict(m32)
+    m32.load_state_dict(sd)
+    nc.set_scales(m32, np.ones(57), np.ones(57))
+    m32 = m32.to(dev)
+    ka, kw = calibration.calibrate_scales(m32, [nc.synth_images(8, size).to(dev)])
+    m = ShuffleNetV2(7).eval()
+    m.load_state_dict(sd)
+    nc.set_scales(m, ka, kw)
+    m = m.to(dev)
+    x = nc.synth_images(batch, size).to(dev).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        for _ in range(3):
+            m(x)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            m(x)
+        b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    print(json.dumps({"net": "shufflenetv2_sfp7_modules", "batch": batch, "size": size, "ms_per_step": round(ms, 4),
+                      "images_per_s": round(batch / ms * 1e3, 1)}), flush=True)

@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cnns_slfp_quantization_b200 import nets_common as nc, engine   # noqa: E402
 from cnns_slfp_quantization_b200.nets_imgnet import ResNet50, MobileNetV1_Q as MobileNetImg   # noqa: E402
-from cnns_slfp_quantization_b200.nets_cifar import VGG16_Q, MobileNetV1_Q as MobileNetCifar     # noqa: E402
+from cnns_slfp_quantization_b200.nets_cifar import VGG16_Q, MobileNetV1_Q as MobileNetCifar, ShuffleNetV2     # noqa: E402
 
 G = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "net_cases.npz"))
 
@@ -22,6 +22,8 @@ def build(name, qbit):
         return VGG16_Q(qbit), lambda m, b, s: engine.compile_vgg16(m, b, s)
     if name == "mobilenetv1_cifar":
         return MobileNetCifar(3, qbit), lambda m, b, s: engine.compile_mobilenetv1(m, b, s)
+    if name == "shufflenetv2":
+        return ShuffleNetV2(qbit), None            # module-level drop-in only (no fused plan yet)
     return MobileNetImg(3, qbit), lambda m, b, s: engine.compile_mobilenetv1(m, b, s)
 
 
