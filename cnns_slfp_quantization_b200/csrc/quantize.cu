@@ -271,15 +271,54 @@ static int launch_quantize(const QuantArgs& a, cudaStream_t st) {
     return check_launch("quantize_kernel");
 }
 
-// NHWC tensor whose channel count is not the physical (padded) one: thread per output code.
+// One element through the table encoder (enc_lut_index + shared-memory table), the generic encoder for the values
+// outside its domain (NaN / Inf quotient, -0, dividends below 2^-119) or when K is outside the reciprocal's range.
+template <int FMT>
+__device__ __forceinline__ uint32_t encode_elem_lut(float x, const DivK& k, const uint8_t* s_enc) {
+    const float q = div_k_fused(x, k);
+    const uint32_t xb = __float_as_uint(x);
+    const uint32_t probe = __funnelshift_l(xb, xb, 1) - 1u;
+    if (!k.fast || probe < 0x08000000u - 1u || !(fabsf(q) < INFINITY)) return encode<FMT>(div_k(x, k));
+    return (uint32_t)s_enc[enc_lut_index<FMT>(q, x)] | ((__float_as_uint(q) >> 24) & 0x80u);
+}
+
+// NHWC tensor whose channel count is not the physical (padded) one (ShuffleNetV2's 24 / 58 / 116 / 232 channels, C = 3
+// inputs): thread = four consecutive padded channels of a pixel (c_phys % 4 == 0 and 4-byte aligned codes, else one),
+// table encoder for the activation formats, one 32-bit store.  Was one generic encode<> and one byte store per thread.
 template <int FMT>
 __global__ void __launch_bounds__(256) quantize_pad_kernel(const float* __restrict__ x, size_t npix, int C, int Cp,
-                                                           DivK k_div, uint8_t* __restrict__ codes) {
+                                                           DivK k_div, uint8_t* __restrict__ codes, int vec4) {
+    constexpr bool kLut = FMT == SLFP_FMT_SFP33 || FMT == SLFP_FMT_SLFP34_ACT;
+    constexpr int FL = FMT == SLFP_FMT_SFP33 ? SLFP_FMT_SFP33 : SLFP_FMT_SLFP34_ACT;
+    __shared__ uint8_t s_enc[kLut ? kEncLutBytes : 16];
+    if (kLut) {
+        for (int i = threadIdx.x; i < kEncLutBytes; i += 256) s_enc[i] = (uint8_t)enc_lut_entry<FL>((uint32_t)i);
+        __syncthreads();
+    }
+    auto enc1 = [&](float v) -> uint32_t {
+        if (kLut) return encode_elem_lut<FL>(v, k_div, s_enc);
+        return encode<FMT>(div_k(v, k_div));
+    };
+    if (vec4) {
+        const int q = Cp >> 2;
+        const size_t total = npix * (size_t)q;
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+            const size_t pix = i / (size_t)q;
+            const int c0 = (int)(i - pix * (size_t)q) * 4;
+            const float* src = x + pix * (size_t)C + c0;
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + j < C) w |= enc1(__ldg(src + j)) << (8 * j);
+            *reinterpret_cast<uint32_t*>(codes + pix * (size_t)Cp + c0) = w;
+        }
+        return;
+    }
     const size_t total = npix * (size_t)Cp;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
         const size_t pix = i / (size_t)Cp;
         const int c = (int)(i - pix * (size_t)Cp);
-        codes[i] = (c < C) ? (uint8_t)encode<FMT>(div_k(x[pix * (size_t)C + c], k_div)) : (uint8_t)0;
+        codes[i] = (c < C) ? (uint8_t)enc1(x[pix * (size_t)C + c]) : (uint8_t)0;
     }
 }
 
@@ -304,17 +343,6 @@ __global__ void __launch_bounds__(256) quantize_nchw_kernel(const float* __restr
         }
         *reinterpret_cast<uint32_t*>(codes + (n * HW + pix) * Cp + g * 4) = w;
     }
-}
-
-// One element through the table encoder (enc_lut_index + shared-memory table), the generic encoder for the values
-// outside its domain (NaN / Inf quotient, -0, dividends below 2^-119) or when K is outside the reciprocal's range.
-template <int FMT>
-__device__ __forceinline__ uint32_t encode_elem_lut(float x, const DivK& k, const uint8_t* s_enc) {
-    const float q = div_k_fused(x, k);
-    const uint32_t xb = __float_as_uint(x);
-    const uint32_t probe = __funnelshift_l(xb, xb, 1) - 1u;
-    if (!k.fast || probe < 0x08000000u - 1u || !(fabsf(q) < INFINITY)) return encode<FMT>(div_k(x, k));
-    return (uint32_t)s_enc[enc_lut_index<FMT>(q, x)] | ((__float_as_uint(q) >> 24) & 0x80u);
 }
 
 // NCHW float32 image -> space-to-depth NHWC codes [N, H/2, W/2, Cp], channel (dy*2+dx)*C + c.  Thread = one
@@ -656,13 +684,14 @@ extern "C" int slfp_quantize_nhwc_f32(const float* x, size_t npix, int c, int c_
     if (npix == 0) return 0;
     if (!x || !codes || c <= 0 || c_phys < c) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nhwc_f32: bad arguments");
     if (c == c_phys) return slfp_quantize_f32(x, npix * (size_t)c, k_div, fmt, 0, codes, nullptr, nullptr, stream);
-    const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(npix * (size_t)c_phys, 256));
+    const int vec4 = ((c_phys & 3) == 0 && (((uintptr_t)codes) & 3u) == 0) ? 1 : 0;
+    const int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(npix * (size_t)(vec4 ? c_phys / 4 : c_phys), 256));
     cudaStream_t st = (cudaStream_t)stream;
     const DivK dk = make_divk(k_div);
     switch (fmt) {
-        case SLFP_FMT_SFP33: quantize_pad_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes); break;
-        case SLFP_FMT_SLFP34_ACT: quantize_pad_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes); break;
-        case SLFP_FMT_SLFP34_WGT: quantize_pad_kernel<SLFP_FMT_SLFP34_WGT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes); break;
+        case SLFP_FMT_SFP33: quantize_pad_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes, vec4); break;
+        case SLFP_FMT_SLFP34_ACT: quantize_pad_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes, vec4); break;
+        case SLFP_FMT_SLFP34_WGT: quantize_pad_kernel<SLFP_FMT_SLFP34_WGT><<<grid, 256, 0, st>>>(x, npix, c, c_phys, dk, codes, vec4); break;
         default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nhwc_f32: format %d has no codes", fmt);
     }
     return check_launch("quantize_pad_kernel");
