@@ -51,10 +51,19 @@ __device__ __forceinline__ void epilogue_store(const SlfpEpilogue& e, float t, s
 
 // Depthwise (C == K == groups): thread = (pixel, 4 consecutive channels).  Loads are one 32-bit word
 // of codes per tap; a warp covers 128 contiguous channels (or several pixels when C < 128).
+// Code -> float32 through a 256-entry shared table and the filter decoded once per CTA into shared memory
+// ([C][R*S] float32, dynamic shared memory): the per-tap arithmetic decode of both operands was ~250 instructions
+// per output.
 template <bool SFP33>
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(DirectParams p) {
     __shared__ uint32_t s_tab[16];
+    __shared__ float s_dec[256];
+    extern __shared__ float s_wf[];                           // [C][R*S]
     if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    s_dec[threadIdx.x] = decode<SFP33>(threadIdx.x, s_tab);
+    const int taps = p.R * p.S;
+    for (int i = threadIdx.x; i < p.C * taps; i += 256) s_wf[i] = decode<SFP33>(__ldg(p.w + i), s_tab);
     __syncthreads();
     const int cq = p.Cp >> 2;                                 // channel quads per pixel
     const size_t total = (size_t)p.N * p.Ho * p.Wo * cq;
@@ -74,10 +83,8 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(DirectParams p) {
                 const uint32_t wd = __ldg(reinterpret_cast<const uint32_t*>(p.x + (((size_t)n * p.H + hi) * p.W + wi) * p.Cp + c0));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (c0 + j < p.C) {
-                        const float xv = decode<SFP33>((wd >> (8 * j)) & 0xffu, s_tab);
-                        acc[j] = fmaf(xv, decode<SFP33>(__ldg(p.w + ((size_t)(c0 + j) * p.R + r) * p.S + s), s_tab), acc[j]);
-                    }
+                    if (c0 + j < p.C)
+                        acc[j] = fmaf(s_dec[(wd >> (8 * j)) & 0xffu], s_wf[(c0 + j) * taps + r * p.S + s], acc[j]);
                 }
             }
         }
@@ -407,7 +414,9 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
     const size_t total = depthwise ? (size_t)d->n * p.Ho * p.Wo * (d->c_phys / 4) : (size_t)d->n * p.Ho * p.Wo * d->k;
     const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(total, 256));
     if (depthwise) {
-        if (sfp) dwconv_fwd_kernel<true><<<grid, 256, 0, st>>>(p); else dwconv_fwd_kernel<false><<<grid, 256, 0, st>>>(p);
+        const size_t wsm = (size_t)d->c * d->r * d->s * sizeof(float);
+        if (wsm > 40000) return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(depthwise): filter of %zu bytes does not fit shared memory", wsm);
+        if (sfp) dwconv_fwd_kernel<true><<<grid, 256, wsm, st>>>(p); else dwconv_fwd_kernel<false><<<grid, 256, wsm, st>>>(p);
     } else {
         if (sfp) gconv_fwd_kernel<true><<<grid, 256, 0, st>>>(p); else gconv_fwd_kernel<false><<<grid, 256, 0, st>>>(p);
     }
