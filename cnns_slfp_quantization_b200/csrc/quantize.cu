@@ -367,6 +367,35 @@ __global__ void __launch_bounds__(256) quantize_nchw_s2d_kernel(const float* __r
             // the stem case (C <= 4): one float2 (both dx) per (channel, dy): consecutive threads read consecutive
             // float2 of an image row (coalesced), one 16-byte store per thread
             uint32_t wds[4] = {0u, 0u, 0u, 0u};
+            if (C == 3) {
+                // RGB input (every net's stem): all six float2 loads issued first, channel positions known at compile time
+                // (the generic loop below indexes wds[] with run-time values: local memory, two loads in flight)
+                float2 v[3][2];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+                        v[c][dy] = __ldg(reinterpret_cast<const float2*>(x + ((n * 3 + c) * H + (2 * y2 + dy)) * (size_t)W) + x2);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy) {
+                        constexpr int kC = 3;
+                        const int ch0 = (dy * 2) * kC + c, ch1 = (dy * 2 + 1) * kC + c;
+                        uint32_t e0, e1;
+                        if (kLut) {
+                            e0 = encode_elem_lut<FL>(v[c][dy].x, k_div, s_enc);
+                            e1 = encode_elem_lut<FL>(v[c][dy].y, k_div, s_enc);
+                        } else {
+                            e0 = encode<FMT>(div_k(v[c][dy].x, k_div));
+                            e1 = encode<FMT>(div_k(v[c][dy].y, k_div));
+                        }
+                        wds[ch0 >> 2] |= e0 << (8 * (ch0 & 3));
+                        wds[ch1 >> 2] |= e1 << (8 * (ch1 & 3));
+                    }
+                *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                continue;
+            }
             for (int c = 0; c < C; ++c) {
 #pragma unroll
                 for (int dy = 0; dy < 2; ++dy) {
