@@ -173,7 +173,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from cnns_slfp_quantization_b200 import _native as nv, engine, nets_common as nc
+    from cnns_slfp_quantization_b200 import _native as nv, engine, nets_common as nc, parallel
     nv.lib()                                   # fail loudly if the CUDA library is missing
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -186,6 +186,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: each rank's pinned staging buffers live on its GPU's NUMA node (N = 1 keeps every core for the CPU baseline)
+    bound = parallel.bind_to_local_cpus(local) if world > 1 else None
     model = build_model_gpu(args.size, dev)
     plan = engine.compile_resnet50(model, args.batch, args.size, device=dev)
     x_host = nc.synth_images(args.batch, args.size, seed=1234 + rank).pin_memory()
@@ -320,7 +322,8 @@ def main():
                            "l2": "inputs (154 MB/batch) and per-layer activations exceed the 126 MB L2; no explicit flush",
                            "cuda_graph": not args.no_graph, "weights_requantized_every_step": not plan.static_weights,
                            "arithmetic": "u8 SLFP<3,4> codes between layers -> f16 tensor-core operands, f32 accumulate",
-                           "residual_stream": "f16"},
+                           "residual_stream": "f16",
+                           "host_cpus_rank0": (f"{len(bound)} CPUs local to the GPU" if bound else "unbound")},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                         "d2h_bytes_per_step": int(logits_host.numel() * 4)},

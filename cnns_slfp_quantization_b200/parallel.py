@@ -24,6 +24,31 @@ def init(backend=None):
     return dist.get_rank(), dist.get_world_size()
 
 
+def bind_to_local_cpus(device_index):
+    """Restrict this process to the CPUs NVML reports as local to its GPU, so that pinned host buffers allocated
+    afterwards are first-touched on the GPU's own NUMA node (eight ranks staging 154 MB per step each otherwise cross the
+    socket interconnect).  Returns the CPU list it bound to, or None when NVML has no answer or the local set does not
+    intersect the CPUs this process may use (cgroup cpuset); never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and not vis.split(",")[0].strip().isdigit():
+            return None
+        phys = int(vis.split(",")[device_index]) if vis else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        local = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = local & os.sched_getaffinity(0)
+        if not allowed or allowed == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception:
+        return None
+
+
 def shard_batch(n_items, rank, world):
     """Contiguous shard [lo, hi) of a batch of independent images for this rank."""
     per = (n_items + world - 1) // world
