@@ -207,15 +207,19 @@ __global__ void __launch_bounds__(256) dwconv_fast_kernel(const DwFastParams p) 
     }
 }
 
-// 3x3, stride 1 / 2, dilation 1: a thread computes a strip of 4 output pixels along W for its 16 channels.  Every
-// input vector (pixel x 16 channels) of the 3 x (3*stride+3) window is fetched and decoded ONCE for the strip
+// 3x3, stride 1 / 2, dilation 1: a thread computes a strip of 4 output pixels along W for its 4*VEC channels.  Every
+// input vector (pixel x 4*VEC channels) of the 3 x (3*stride+3) window is fetched and decoded ONCE for the strip
 // (4.5 table look-ups per output at stride 1 instead of 9) and every weight vector is read once per 4 outputs.
-template <int STRIDE>
-__global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastParams p) {
+// VEC = 4 (16 channels, 16-byte vectors) needs 128 registers: two CTAs = 16 warps per SM; VEC = 2 (8 channels, 8-byte
+// vectors; the same instructions per output) is built for three CTAs = 24 warps per SM but spills at 80 registers and
+// measured slower (MobileNetV1-ImageNet step 2.29 vs 2.18 ms); the host launches exactly one resident wave of either.
+template <int STRIDE, int VEC>
+__global__ void __launch_bounds__(256, VEC == 4 ? 2 : 3) dwconv3x3_strip_kernel(const DwFastParams p) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm);
     float* s_w = reinterpret_cast<float*>(dsm + 256 * 32 * 4);
-    const int cg = p.Cp >> 4;
+    constexpr int CH = 4 * VEC;
+    const int cg = p.Cp / CH;
     for (int i = threadIdx.x; i < 256 * 32; i += 256) s_lut[i] = __float_as_uint(decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac));
     for (int i = threadIdx.x; i < 9 * p.Cp; i += 256) {
         const int t = i / p.Cp, c = i - t * p.Cp;
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
             const uint32_t code = p.w[(size_t)c * 9 + t];
             wv = p.wgt_sfp33 ? decode<true>(code, c_pow2frac) : decode<false>(code, c_pow2frac);
         }
-        s_w[t * p.Cp + (((c >> 2) & 3) * cg + (c >> 4)) * 4 + (c & 3)] = wv;
+        s_w[t * p.Cp + (((c >> 2) & (VEC - 1)) * cg + c / CH) * 4 + (c & 3)] = wv;
     }
     __syncthreads();
     const uint32_t lut_base = ptx::smem_u32(s_lut), w_base = ptx::smem_u32(s_w);
@@ -232,37 +236,49 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
     constexpr int kOut = 4, kCols = (kOut - 1) * STRIDE + 3;      // 6 input columns at stride 1, 9 at stride 2
     const int wstrips = (p.Wo + kOut - 1) / kOut;
     const size_t total = (size_t)p.N * p.Ho * wstrips * cg;
+    const int enc_shift = p.out_sfp33 ? 19 : 18, enc_bias = p.out_sfp33 ? 0x76F : 0xEDF;    // encode_relu_fast_raw16<>
+    const bool pad_channels = p.C != p.Cp;
     for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
-        const int q = (int)(idx % cg), c0 = q * 16;
+        const int q = (int)(idx % cg), c0 = q * CH;
         size_t rest = idx / cg;
         const int ws = (int)(rest % wstrips); rest /= wstrips;
         const int ho = (int)(rest % p.Ho), n = (int)(rest / p.Ho);
         const int wo0 = ws * kOut;
-        float acc[kOut][16];
+        float acc[kOut][CH];
 #pragma unroll
         for (int o = 0; o < kOut; ++o)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[o][j] = 0.0f;
+            for (int j = 0; j < CH; ++j) acc[o][j] = 0.0f;
         const uint8_t* xn = p.x + (size_t)n * p.H * p.W * p.Cp + c0;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const int hi = ho * STRIDE - p.ph + r;
             const bool hok = hi >= 0 && hi < p.H;
-            uint4 cw[kCols];
+            uint32_t cw[kCols][VEC];
 #pragma unroll
             for (int cidx = 0; cidx < kCols; ++cidx) {
                 const int wi = wo0 * STRIDE - p.pw + cidx;
-                cw[cidx] = make_uint4(0u, 0u, 0u, 0u);
-                if (hok && wi >= 0 && wi < p.W) cw[cidx] = __ldg(reinterpret_cast<const uint4*>(xn + ((size_t)hi * p.W + wi) * p.Cp));
+#pragma unroll
+                for (int g = 0; g < VEC; ++g) cw[cidx][g] = 0u;
+                if (hok && wi >= 0 && wi < p.W) {
+                    const uint8_t* src = xn + ((size_t)hi * p.W + wi) * p.Cp;
+                    if (VEC == 4) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+                        cw[cidx][0] = v.x; cw[cidx][1] = v.y; cw[cidx][VEC - 2] = v.z; cw[cidx][VEC - 1] = v.w;
+                    } else {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
+                        cw[cidx][0] = v.x; cw[cidx][1] = v.y;
+                    }
+                }
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < VEC; ++g) {
                 float4 w4[3];
 #pragma unroll
                 for (int s = 0; s < 3; ++s) w4[s] = ptx::lds128_f4(w_base + (uint32_t)((r * 3 + s) * p.Cp + (g * cg + q) * 4) * 4u);
 #pragma unroll
                 for (int cidx = 0; cidx < kCols; ++cidx) {
-                    const uint32_t c = g == 0 ? cw[cidx].x : (g == 1 ? cw[cidx].y : (g == 2 ? cw[cidx].z : cw[cidx].w));
+                    const uint32_t c = cw[cidx][g];
                     const float x0 = __uint_as_float(ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base));
                     const float x1 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base));
                     const float x2 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base));
@@ -280,9 +296,9 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
                 }
             }
         }
-        float4 m4[4], a4[4];
+        float4 m4[VEC], a4[VEC];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < VEC; ++g) {
             m4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_mul + c0) + g);
             a4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_add + c0) + g);
         }
@@ -290,21 +306,26 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
 #pragma unroll
         for (int o = 0; o < kOut; ++o) {
             if (wo0 + o >= p.Wo) break;
-            int32_t tq[16];
+            int32_t tq[CH];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < VEC; ++g) {
                 const float mm[4] = {m4[g].x, m4[g].y, m4[g].z, m4[g].w}, aa[4] = {a4[g].x, a4[g].y, a4[g].z, a4[g].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float v = __saturatef(fmaf(acc[o][4 * g + e], mm[e], aa[e]) * p.sc);
-                    tq[4 * g + e] = p.out_sfp33 ? encode_relu_fast_raw16<true>(v) : encode_relu_fast_raw16<false>(v);
-                    if (c0 + 4 * g + e >= p.C) tq[4 * g + e] = 0;
+                    tq[4 * g + e] = ((int32_t)__float_as_uint(v) >> enc_shift) - enc_bias;
                 }
             }
-            uint4 pk;
-            pk.x = ptx::pack_sat_u8x4(tq[0], tq[1], tq[2], tq[3]);   pk.y = ptx::pack_sat_u8x4(tq[4], tq[5], tq[6], tq[7]);
-            pk.z = ptx::pack_sat_u8x4(tq[8], tq[9], tq[10], tq[11]); pk.w = ptx::pack_sat_u8x4(tq[12], tq[13], tq[14], tq[15]);
-            *reinterpret_cast<uint4*>(p.y + (pix0 + o) * p.Cp + c0) = pk;
+            if (pad_channels) {                                                      // zero code in pad channels
+#pragma unroll
+                for (int j = 0; j < CH; ++j) tq[j] = (c0 + j < p.C) ? tq[j] : 0;
+            }
+            uint32_t pk[VEC];
+#pragma unroll
+            for (int g = 0; g < VEC; ++g) pk[g] = ptx::pack_sat_u8x4(tq[4 * g], tq[4 * g + 1], tq[4 * g + 2], tq[4 * g + 3]);
+            uint8_t* dst = p.y + (pix0 + o) * p.Cp + c0;
+            if (VEC == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[VEC - 2], pk[VEC - 1]);
+            else *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
         }
     }
 }
@@ -388,17 +409,35 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
             const bool strip = d->r == 3 && d->s == 3 && d->dil_h == 1 && d->dil_w == 1 && d->stride_h == d->stride_w &&
                                (d->stride_h == 1 || d->stride_h == 2) && p.Wo >= 4 && getenv("SLFP_DW_NO_STRIP") == nullptr;
             if (strip) {
-                static bool attr2 = false;
-                if (!attr2) {
-                    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-                    if (e != cudaSuccess) return set_error((int)e, "dwconv3x3_strip: smem attribute: %s", cudaGetErrorString(e));
-                    attr2 = true;
+                // VEC = 4 (16 channels per thread) by default: measured 3-12 % faster than the 8-channel form on every
+                // MobileNetV1 layer (its 80-register build spills); SLFP_DW_VEC=2 selects the 8-channel form
+                static int vec = 0;
+                if (!vec) {
+                    const char* ev = getenv("SLFP_DW_VEC");
+                    vec = (ev && ev[0] == '2') ? 2 : 4;
+                    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+                    if (e != cudaSuccess) { vec = 0; return set_error((int)e, "dwconv3x3_strip: smem attribute: %s", cudaGetErrorString(e)); }
                 }
-                const size_t tot4 = (size_t)d->n * p.Ho * ((p.Wo + 3) / 4) * (d->c_phys / 16);
-                const int g4 = (int)min((size_t)num_sms() * min(blocks_per_sm, 3), ceil_div_sz(tot4, 256));
-                if (d->stride_h == 1) dwconv3x3_strip_kernel<1><<<g4, 256, smem, st>>>(q);
-                else dwconv3x3_strip_kernel<2><<<g4, 256, smem, st>>>(q);
+                // exactly one resident wave: the occupancy the kernel really gets with this layer's shared memory
+                int per_sm = 0;
+                cudaError_t eo;
+                if (vec == 4) eo = d->stride_h == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<1, 4>, 256, smem)
+                                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<2, 4>, 256, smem);
+                else eo = d->stride_h == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<1, 2>, 256, smem)
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<2, 2>, 256, smem);
+                if (eo != cudaSuccess || per_sm < 1) return set_error((int)eo, "dwconv3x3_strip: occupancy query failed");
+                const size_t tot4 = (size_t)d->n * p.Ho * ((p.Wo + 3) / 4) * (d->c_phys / (4 * vec));
+                const int g4 = (int)min((size_t)num_sms() * per_sm, ceil_div_sz(tot4, 256));
+                if (vec == 4) {
+                    if (d->stride_h == 1) dwconv3x3_strip_kernel<1, 4><<<g4, 256, smem, st>>>(q);
+                    else dwconv3x3_strip_kernel<2, 4><<<g4, 256, smem, st>>>(q);
+                } else {
+                    if (d->stride_h == 1) dwconv3x3_strip_kernel<1, 2><<<g4, 256, smem, st>>>(q);
+                    else dwconv3x3_strip_kernel<2, 2><<<g4, 256, smem, st>>>(q);
+                }
                 return check_launch("dwconv3x3_strip_kernel");
             }
             if (d->r == 3 && d->s == 3) dwconv_fast_kernel<9><<<g, 256, smem, st>>>(q);
