@@ -220,15 +220,23 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 2 : 3) dwconv3x3_strip_kernel(
     float* s_w = reinterpret_cast<float*>(dsm + 256 * 32 * 4);
     constexpr int CH = 4 * VEC;
     const int cg = p.Cp / CH;
-    for (int i = threadIdx.x; i < 256 * 32; i += 256) s_lut[i] = __float_as_uint(decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac));
-    for (int i = threadIdx.x; i < 9 * p.Cp; i += 256) {
-        const int t = i / p.Cp, c = i - t * p.Cp;
-        float wv = 0.0f;
-        if (c < p.C) {
-            const uint32_t code = p.w[(size_t)c * 9 + t];
-            wv = p.wgt_sfp33 ? decode<true>(code, c_pow2frac) : decode<false>(code, c_pow2frac);
+    {   // lane-replicated decode table: each thread decodes ONE code, the warp broadcasts it into the 32 lane copies
+        const uint32_t mine = __float_as_uint(decode_act_any((uint32_t)threadIdx.x, p.act_fmt, c_pow2frac));
+        const int lane = threadIdx.x & 31, code0 = threadIdx.x & ~31;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) s_lut[(code0 + j) * 32 + lane] = __shfl_sync(0xffffffffu, mine, j);
+    }
+    for (int c = threadIdx.x; c < p.Cp; c += 256) {            // a thread decodes the nine contiguous taps of its channels
+        const int dst = (((c >> 2) & (VEC - 1)) * cg + c / CH) * 4 + (c & 3);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float wv = 0.0f;
+            if (c < p.C) {
+                const uint32_t code = p.w[(size_t)c * 9 + t];
+                wv = p.wgt_sfp33 ? decode<true>(code, c_pow2frac) : decode<false>(code, c_pow2frac);
+            }
+            s_w[t * p.Cp + dst] = wv;
         }
-        s_w[t * p.Cp + (((c >> 2) & (VEC - 1)) * cg + c / CH) * 4 + (c & 3)] = wv;
     }
     __syncthreads();
     const uint32_t lut_base = ptx::smem_u32(s_lut), w_base = ptx::smem_u32(s_w);
