@@ -345,6 +345,32 @@ __global__ void __launch_bounds__(256) quantize_nchw_kernel(const float* __restr
     }
 }
 
+// The network-input case of the above (c_phys = 4, HW a multiple of 4, fewer than 2^31 pixel quads): a thread takes FOUR
+// consecutive pixels - one float4 per plane (all C loads issued first), 32-bit index arithmetic (the generic kernel
+// pays three 64-bit divisions per pixel), one 16-byte store of 4 pixels x 4 codes.
+template <int FMT>
+__global__ void __launch_bounds__(256) quantize_nchw_c4_kernel(const float* __restrict__ x, uint32_t total, int C, uint32_t HW4,
+                                                               DivK k_div, uint8_t* __restrict__ codes) {
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const uint32_t n = i / HW4, q = i - n * HW4;
+        const float4* src = reinterpret_cast<const float4*>(x) + (size_t)n * C * HW4 + q;
+        float4 v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = c < C ? __ldg(src + (size_t)c * HW4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < C) {
+                w[0] |= encode<FMT>(div_k(v[c].x, k_div)) << (8 * c);
+                w[1] |= encode<FMT>(div_k(v[c].y, k_div)) << (8 * c);
+                w[2] |= encode<FMT>(div_k(v[c].z, k_div)) << (8 * c);
+                w[3] |= encode<FMT>(div_k(v[c].w, k_div)) << (8 * c);
+            }
+        }
+        reinterpret_cast<uint4*>(codes)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // NCHW float32 image -> space-to-depth NHWC codes [N, H/2, W/2, Cp], channel (dy*2+dx)*C + c.  Thread = one
 // folded pixel: 2 x float2 reads per plane (coalesced across the warp), one 16-byte store per 16 channels.
 template <int FMT>
@@ -735,6 +761,16 @@ extern "C" int slfp_quantize_nchw_f32(const float* x, int n, int c, size_t hw, i
     const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(total, 256));
     cudaStream_t st = (cudaStream_t)stream;
     const DivK dk = make_divk(k_div);
+    const size_t quads = (size_t)n * (hw / 4);
+    if (c_phys == 4 && (hw & 3) == 0 && quads < (1ull << 31) && ((((uintptr_t)x) | ((uintptr_t)codes)) & 15u) == 0 &&
+        (fmt == SLFP_FMT_SFP33 || fmt == SLFP_FMT_SLFP34_ACT)) {
+        const int g4 = (int)min((size_t)num_sms() * 8, ceil_div_sz(quads, 256));
+        if (fmt == SLFP_FMT_SFP33)
+            quantize_nchw_c4_kernel<SLFP_FMT_SFP33><<<g4, 256, 0, st>>>(x, (uint32_t)quads, c, (uint32_t)(hw / 4), dk, codes);
+        else
+            quantize_nchw_c4_kernel<SLFP_FMT_SLFP34_ACT><<<g4, 256, 0, st>>>(x, (uint32_t)quads, c, (uint32_t)(hw / 4), dk, codes);
+        return check_launch("quantize_nchw_c4_kernel");
+    }
     switch (fmt) {
         case SLFP_FMT_SFP33: quantize_nchw_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, n, c, hw, c_phys, dk, codes); break;
         case SLFP_FMT_SLFP34_ACT: quantize_nchw_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, n, c, hw, c_phys, dk, codes); break;

@@ -126,6 +126,23 @@ def test_quantize_nhwc_padded(orc):
         assert (got[:, :C] == oc).all() and (got[:, C:] == 0).all()
 
 
+def test_quantize_nchw_input(orc):
+    """Network-input quantizer (NCHW float32 -> NHWC codes, padded channels): the 4-pixels-per-thread path (c_phys = 4,
+    HW % 4 == 0) and the generic path, both formats, bit-exact against the oracle on the permuted tensor."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    rng = np.random.default_rng(21)
+    for fmt in (0, 1):
+        for N, C, H, W, Cp in ((3, 3, 8, 12, 4), (2, 4, 6, 6, 4), (2, 3, 5, 7, 4), (1, 1, 4, 4, 4), (2, 6, 4, 4, 8), (5, 3, 32, 32, 4)):
+            x = (rng.standard_normal((N, C, H, W)) * 2.5).astype(np.float32)
+            x.flat[:: 17] = 0.0
+            xt = torch.from_numpy(x).cuda()
+            codes = torch.full((N, H, W, Cp), 0x77, dtype=torch.uint8, device="cuda")
+            nv.check(nv.lib().slfp_quantize_nchw_f32(xt.data_ptr(), N, C, H * W, Cp, 0.7, fmt, codes.data_ptr(), nv.stream()))
+            oc, _ = orc.quantize(np.ascontiguousarray(x.transpose(0, 2, 3, 1)), fmt, kdiv=0.7)
+            got = codes.cpu().numpy()
+            assert (got[..., :C] == oc.reshape(N, H, W, C)).all() and (got[..., C:] == 0).all(), (fmt, N, C, H, W)
+
+
 def test_host_buffer_entry(orc):
     from cnns_slfp_quantization_b200 import _native as nv
     x = (np.random.default_rng(2).standard_normal(100001) * 5).astype(np.float32)
