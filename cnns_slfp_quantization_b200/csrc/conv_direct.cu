@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(256) dwconv_fast_kernel(const DwFastParams p) 
 // 3x3, stride 1 / 2, dilation 1: a thread computes a strip of 4 output pixels along W for its 4*VEC channels.  Every
 // input vector (pixel x 4*VEC channels) of the 3 x (3*stride+3) window is fetched and decoded ONCE for the strip
 // (4.5 table look-ups per output at stride 1 instead of 9) and every weight vector is read once per 4 outputs.
-// VEC = 4 (16 channels, 16-byte vectors) needs 128 registers: two CTAs = 16 warps per SM; VEC = 2 (8 channels, 8-byte
-// vectors; the same instructions per output) is built for three CTAs = 24 warps per SM but spills at 80 registers and
-// measured slower (MobileNetV1-ImageNet step 2.29 vs 2.18 ms); the host launches exactly one resident wave of either.
+// Both forms hold 64 accumulators in 128 registers (two CTAs = 16 warps per SM, one resident wave): VEC = 4 is 4 outputs x 16
+// channels (16-byte vectors); VEC = 2 is 8 channels (8-byte vectors) x 8 outputs at stride 1 (3.75 instead of 4.5 table decodes and
+// half the weight reads per output) or x 4 outputs at stride 2 (no spills, where the 16-channel form spills its 9-column window).
 template <int STRIDE, int VEC>
-__global__ void __launch_bounds__(256, VEC == 4 ? 2 : 3) dwconv3x3_strip_kernel(const DwFastParams p) {
+__global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastParams p) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm);
     float* s_w = reinterpret_cast<float*>(dsm + 256 * 32 * 4);
@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(256, VEC == 4 ? 2 : 3) dwconv3x3_strip_kernel(
     __syncthreads();
     const uint32_t lut_base = ptx::smem_u32(s_lut), w_base = ptx::smem_u32(s_w);
     const uint32_t lane4 = (threadIdx.x & 31u) * 4u;
-    constexpr int kOut = 4, kCols = (kOut - 1) * STRIDE + 3;      // 6 input columns at stride 1, 9 at stride 2
+    // strip length: 4 outputs of 16 channels, or (VEC = 2) 8 outputs of 8 channels at stride 1 - the same 64 accumulators,
+    // 10 instead of 12 decoded input columns per 8 outputs and half the weight reads per output
+    constexpr int kOut = (VEC == 2 && STRIDE == 1) ? 8 : 4, kCols = (kOut - 1) * STRIDE + 3;
     const int wstrips = (p.Wo + kOut - 1) / kOut;
     const size_t total = (size_t)p.N * p.Ho * wstrips * cg;
     const int enc_shift = p.out_sfp33 ? 19 : 18, enc_bias = p.out_sfp33 ? 0x76F : 0xEDF;    // encode_relu_fast_raw16<>
@@ -417,12 +419,12 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
             const bool strip = d->r == 3 && d->s == 3 && d->dil_h == 1 && d->dil_w == 1 && d->stride_h == d->stride_w &&
                                (d->stride_h == 1 || d->stride_h == 2) && p.Wo >= 4 && getenv("SLFP_DW_NO_STRIP") == nullptr;
             if (strip) {
-                // VEC = 4 (16 channels per thread) by default: measured 3-12 % faster than the 8-channel form on every
-                // MobileNetV1 layer (its 80-register build spills); SLFP_DW_VEC=2 selects the 8-channel form
+                // VEC = 2 (8 channels per thread, 8-output strips at stride 1) by default: measured faster than the 16-channel
+                // form on every MobileNetV1 layer (step 2.08 -> 1.95 ms); SLFP_DW_VEC=4 selects the 16-channel form
                 static int vec = 0;
                 if (!vec) {
                     const char* ev = getenv("SLFP_DW_VEC");
-                    vec = (ev && ev[0] == '2') ? 2 : 4;
+                    vec = (ev && ev[0] == '4') ? 4 : 2;
                     cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
                     if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
                     if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
@@ -437,7 +439,8 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
                 else eo = d->stride_h == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<1, 2>, 256, smem)
                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<2, 2>, 256, smem);
                 if (eo != cudaSuccess || per_sm < 1) return set_error((int)eo, "dwconv3x3_strip: occupancy query failed");
-                const size_t tot4 = (size_t)d->n * p.Ho * ((p.Wo + 3) / 4) * (d->c_phys / (4 * vec));
+                const int k_out = (vec == 2 && d->stride_h == 1) ? 8 : 4;                     // kOut of the kernel
+                const size_t tot4 = (size_t)d->n * p.Ho * ((p.Wo + k_out - 1) / k_out) * (d->c_phys / (4 * vec));
                 const int g4 = (int)min((size_t)num_sms() * per_sm, ceil_div_sz(tot4, 256));
                 if (vec == 4) {
                     if (d->stride_h == 1) dwconv3x3_strip_kernel<1, 4><<<g4, 256, smem, st>>>(q);
