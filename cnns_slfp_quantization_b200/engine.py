@@ -67,6 +67,7 @@ class Plan:
         self.output = None
         self.graph = None
         self.flops = 0.0
+        self.taps = []                # (module, input code tensor _T, op index) of every quantized layer (parity tests)
         self.conv_flops = []          # per conv launch, in launch order (bench.py's roofline pass)
         self.bytes_hbm = 0
 
@@ -139,6 +140,7 @@ class Plan:
         shim.weight, shim.bias, shim.Ka, shim.Kw = w2, None, conv.Ka, conv.Kw
         shim.stride, shim.padding, shim.dilation, shim.groups = (1, 1), tuple(lo), (1, 1), 1
         shim.fold = (lo, off, R2, S2)
+        shim.orig = conv                 # Plan.taps: the module whose input this layer reads (in the folded layout)
         return shim
 
     def quantize_flat(self, x_f32, c, kdiv):
@@ -169,6 +171,7 @@ class Plan:
         assert C == x.c, (C, x.c)
         ka, kw = _k32(mod.Ka), _k32(mod.Kw)
         assert abs(ka - x.kdiv) == 0.0, "input codes were quantized with a different Ka"
+        self.taps.append((mod, x, len(self.ops)))       # (module, input codes, index of this layer's op in self.ops)
         pex = getattr(mod, "pad_extra", (0, 0))          # bottom/right minus top/left padding (space-to-depth stem)
         d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
                             x.fmt, pex[0], pex[1])
@@ -261,6 +264,7 @@ class Plan:
         assert K == K2 and mod1.weight.shape[2:] == (1, 1) and mod2.weight.shape[2:] == (1, 1)
         assert mod1.bias is None and mod2.bias is None and x1.cp % 64 == 0 and x2.cp % 64 == 0 and K % 16 == 0
         assert abs(_k32(mod1.Ka) - x1.kdiv) == 0.0 and abs(_k32(mod2.Ka) - x2.kdiv) == 0.0
+        self.taps += [(mod1, x1, len(self.ops)), (mod2, x2, len(self.ops))]
         d1 = nv.SlfpConvDesc(x1.n, x1.h, x1.w, C1, x1.cp, K, 1, 1, 1, 1, 0, 0, 1, 1, 1, x1.fmt, 0, 0)
         s2 = mod2.stride
         d2 = nv.SlfpConvDesc(x2.n, x2.h, x2.w, C2, x2.cp, K, 1, 1, s2[0], s2[1], 0, 0, 1, 1, 1, x2.fmt, 0, 0)

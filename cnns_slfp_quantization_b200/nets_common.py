@@ -127,3 +127,41 @@ def synth_images(batch, size, seed=1234, channels=3):
     ph = torch.rand(batch, channels, 3, generator=g) * 6.28318
     pat = torch.sin(3.0 * xx[None, None] + ph[..., 0:1, None]) * torch.cos(2.0 * yy[None, None] + ph[..., 1:2, None])
     return x + 1.5 * pat * (0.5 + ph[..., 2:3, None] / 6.28318)
+
+
+def prototype_classifier(feats, out_features, target=8.0, seed=11):
+    """Nearest-prototype classifier for decisive whole-net fixtures: class i (i < batch) is image i.
+
+    Row i = target * d_i / |d_i|^2 with d_i = f_i - mean(f) (so image i scores `target` on its own class and
+    target * <d_i, d_j> / |d_i|^2 on the others), rows >= batch are seeded random directions of comparable norm,
+    bias = -W . mean(f).  `feats` are the REFERENCE net's classifier inputs on the fixture batch; the fixture stores
+    the prototype rows, the scalar for the random rows and the bias (tests/golden/make_golden_net224.py).
+    Returns (protos [batch, in] float32, rest_scale float, bias [out] float32)."""
+    f = torch.as_tensor(feats).double()
+    fbar = f.mean(0, keepdim=True)
+    d = f - fbar
+    n2 = (d * d).sum(1, keepdim=True).clamp_min(1e-30)
+    protos = (target * d / n2).float()
+    rest_scale = float(0.5 * target / n2.sqrt().median())
+    w = prototype_weight(protos, out_features, rest_scale, seed)
+    bias = -(w.double() @ fbar[0]).float()
+    return protos, rest_scale, bias
+
+
+def prototype_weight(protos, out_features, rest_scale, seed=11):
+    protos = torch.as_tensor(protos, dtype=torch.float32)
+    b, cin = protos.shape
+    assert b <= out_features
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(out_features, cin, generator=g, dtype=torch.float64)
+    u = u / u.norm(dim=1, keepdim=True)
+    w = (u * float(rest_scale)).float()
+    w[:b] = protos
+    return w
+
+
+def apply_prototype_classifier(model, protos, rest_scale, bias, seed=11):
+    fc = classifier_module(model)
+    with torch.no_grad():
+        fc.weight.copy_(prototype_weight(protos, fc.out_features, rest_scale, seed).to(fc.weight.device))
+        fc.bias.copy_(torch.as_tensor(bias, dtype=torch.float32).to(fc.bias.device))

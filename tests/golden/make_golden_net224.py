@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Decisive whole-net fixtures from the REFERENCE nets (build container only; needs /root/reference).
+
+VERDICT r1 item 1: the 64x64 / batch-8 fixture of make_golden_nets.py has top-1 margins inside the float16
+operand noise, so "identical top-1" was untestable.  This script makes fixtures whose margins are decisive:
+
+  * `resnet50_224`: the headline configuration - ResNet-50, Qbits = 8, 224x224, 32 images;
+  * `<net>_taps`: the same net at a small size / batch 2 with the reference's `input_q` of EVERY quantized layer
+    stored as 8-bit codes (per-layer parity of the fused engine: how many codes differ, and by how many grid steps);
+  * every other net of BASELINE.json (VGG-16, MobileNetV1 CIFAR / ImageNet, ShuffleNetV2) with the same classifier.
+
+Classifier: nearest-prototype rows built from the reference's own features (nets_common.prototype_classifier): image i
+is class i, so the reference's top-1 is the identity permutation with margins of several logit units, and a
+wrong feature vector (mis-indexed scale, wrong BN fold, ...) lands on another prototype.
+Everything else as in make_golden_nets.py: parameters from nets_common.synth_state_dict (keyed by NAME), scales from
+the reference's calibration recipe (Qbits = 32, K = 1 forward, max|.| / 15.5; cifar100_train_eval.py:213-277).
+"""
+import os
+import sys
+import types
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.modules.setdefault("torchsummary", types.SimpleNamespace(summary=lambda *a, **k: None))
+
+import numpy as np
+import torch
+
+from cnns_slfp_quantization_b200 import nets_common as nc
+from oracle import slfp_oracle as orc
+from make_golden_nets import ref_net
+
+torch.set_num_threads(8)
+
+
+def features_and_logits(m, x, chunk=8):
+    fc = nc.classifier_module(m)
+    feats, outs = [], []
+    h = fc.register_forward_hook(lambda mod, inp, out: feats.append(inp[0].detach().clone()))
+    with torch.no_grad():
+        for i in range(0, x.shape[0], chunk):
+            outs.append(m(x[i:i + chunk]).detach().clone())
+    h.remove()
+    return torch.cat(feats).reshape(x.shape[0], -1), torch.cat(outs)
+
+
+def calibrate(name, sd, x, chunk=8):
+    """Qbits = 32, K = 1: input_q / weight_q are the raw tensors; running max over batch chunks."""
+    m = ref_net(name, 32).eval()
+    m.load_state_dict(sd, strict=False)
+    nc.set_scales(m, np.ones(64), np.ones(64))
+    layers = nc.quantized_layers(m)
+    amax = np.zeros(len(layers))
+    with torch.no_grad():
+        for i in range(0, x.shape[0], chunk):
+            m(x[i:i + chunk])
+            amax = np.maximum(amax, [float(l.input_q.abs().max()) for l in layers])
+    wmax = np.array([float(l.weight_q.abs().max()) for l in layers])
+    return amax / 15.5, wmax / 15.5
+
+
+def make_case(out, key, name, qbit, batch, size, taps=False):
+    x = nc.synth_images(batch, size)
+    m0 = ref_net(name, 32).eval()
+    sd = nc.synth_state_dict(m0)
+    fc_name = [n for n, mod in m0.named_modules() if mod is nc.classifier_module(m0)][0]
+    # pass 1: scales of everything but the classifier weight; features of the QUANTIZED reference net
+    ka, kw = calibrate(name, sd, x)
+    m = ref_net(name, qbit).eval()
+    m.load_state_dict(sd, strict=False)
+    nc.set_scales(m, ka, kw)
+    feats, _ = features_and_logits(m, x)
+    protos, rest_scale, bias = nc.prototype_classifier(feats, nc.classifier_module(m).out_features)
+    w = nc.prototype_weight(protos, nc.classifier_module(m).out_features, rest_scale)
+    sd[fc_name + ".weight"], sd[fc_name + ".bias"] = w, bias
+    # pass 2: the classifier's Kw from the prototype weight (the other scales do not change)
+    layers = nc.quantized_layers(m)
+    fc = nc.classifier_module(m)
+    if fc in layers:
+        kw[layers.index(fc)] = float(w.abs().max()) / 15.5
+    m = ref_net(name, qbit).eval()
+    m.load_state_dict(sd, strict=False)
+    nc.set_scales(m, ka, kw)
+    feats_q, y = features_and_logits(m, x)
+    m32 = ref_net(name, 32).eval()
+    m32.load_state_dict(sd, strict=False)
+    _, y32 = features_and_logits(m32, x)
+    out[f"{key}.cfg"] = np.array([qbit, batch, size])
+    out[f"{key}.ka"], out[f"{key}.kw"] = ka, kw
+    out[f"{key}.protos"], out[f"{key}.rest_scale"], out[f"{key}.fc_bias"] = protos.numpy(), np.float64(rest_scale), bias.numpy()
+    out[f"{key}.features"] = feats_q.numpy()
+    out[f"{key}.logits"] = y.numpy()
+    out[f"{key}.top1_fp32"] = y32.argmax(1).numpy()
+    if taps:
+        # the reference's input_q of every quantized layer (fake-quant float32 on the grid) as 8-bit codes
+        with torch.no_grad():
+            m(x)
+        fmt = orc.fmt_for(qbit, "act")
+        table = orc.decode(np.arange(256, dtype=np.uint8), fmt).view(np.uint32)       # code -> float32 bits
+        order = np.argsort(table, kind="stable")
+        for i, l in enumerate(nc.quantized_layers(m)):
+            q = np.ascontiguousarray(l.input_q.detach().numpy())
+            bits = q.view(np.uint32)
+            pos = np.clip(np.searchsorted(table[order], bits), 0, 255)
+            codes = order[pos].astype(np.uint8)
+            assert (table[codes] == bits).all(), (key, i)        # every reference value is a grid point with a code
+            out[f"{key}.tap{i:02d}"] = codes
+    srt = np.sort(y.numpy(), 1)
+    top = y.argmax(1).numpy()
+    print(key, "q", qbit, "top1 == identity:", bool((top == np.arange(batch)).all()), "fp32 agrees:",
+          int((y32.argmax(1).numpy() == top).sum()), "/", batch, "min margin", float((srt[:, -1] - srt[:, -2]).min()),
+          "logit std", float(y.std()), flush=True)
+
+
+CASES = [("resnet50_224", "resnet50", 8, 32, 224, False),
+         ("resnet50_taps", "resnet50", 8, 2, 64, True),
+         ("vgg16", "vgg16", 8, 16, 32, True),
+         ("mobilenetv1_cifar", "mobilenetv1_cifar", 8, 16, 32, True),
+         ("mobilenetv1_imgnet", "mobilenetv1_imgnet", 7, 8, 224, False),
+         ("mobilenetv1_imgnet_taps", "mobilenetv1_imgnet", 7, 2, 224, True),
+         ("shufflenetv2", "shufflenetv2", 7, 16, 32, False),
+         ("shufflenetv2_224", "shufflenetv2", 7, 8, 224, False)]
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    path = os.path.join(HERE, "net224_cases.npz")
+    out = dict(np.load(path)) if only and os.path.exists(path) else {}
+    for key, name, qbit, batch, size, taps in CASES:
+        if only and key not in only:
+            continue
+        for k in [k for k in out if k.startswith(key + ".")]:
+            del out[k]
+        make_case(out, key, name, qbit, batch, size, taps)
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KB")
