@@ -8,7 +8,7 @@ import os
 
 import torch
 
-from .build import LIB_PATH
+from .build import LIB_PATH, source_hash
 
 FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU = 0, 1, 2, 3, 4, 5
 ACT_STL, ACT_SWISH, ACT_SIGMOID = 0, 1, 2
@@ -39,6 +39,8 @@ class SlfpWeightJob(ctypes.Structure):
 _SIGS = {
     "slfp_version": (c_i, []),
     "slfp_last_error": (ctypes.c_char_p, []),
+    "slfp_build_id": (ctypes.c_char_p, []),
+    "slfp_quantize_dyn_f32": (c_i, [c_vp, c_sz, c_vp, c_d, c_i, ctypes.c_uint, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "slfp_quantize_f32": (c_i, [c_vp, c_sz, c_f, c_i, ctypes.c_uint, c_vp, c_vp, c_vp, c_vp]),
     "slfp_quantize_nhwc_f32": (c_i, [c_vp, c_sz, c_i, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_quantize_nchw_f32": (c_i, [c_vp, c_i, c_i, c_sz, c_i, c_f, c_i, c_vp, c_vp]),
@@ -72,7 +74,7 @@ _lib = None
 # Every entry point that launches kernels on the caller's stream.  The proxy below counts those calls
 # (bench.py reports them as `gpu_launches`) and, when a profile dict is installed, brackets each call
 # with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
-_LAUNCHING = {"slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
+_LAUNCHING = {"slfp_quantize_dyn_f32", "slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
               "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_conv2d_bwd_ws", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
               "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32"}
 launch_count = 0
@@ -115,6 +117,10 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
+        built, want = handle.slfp_build_id().decode(), source_hash()
+        if built != want and not os.environ.get("SLFP_ALLOW_STALE_LIB"):
+            raise ImportError(f"{LIB_PATH} was built from other sources (build id {built}, sources {want}): rebuild with "
+                              "`python -m cnns_slfp_quantization_b200.build`")
         _lib = _Lib(handle)
     return _lib
 

@@ -68,7 +68,43 @@ def calibrate_scales(model_fp32, batches, divisor=15.5, group=None):
     """Run `model_fp32` (a q_bit = 32 instance on a CUDA device) over the batches and return (Ka, Kw)."""
     cal = ScaleCalibrator(model_fp32, divisor)
     cal.observe_weights()
-    with cal, torch.no_grad():
-        for x in batches:
-            model_fp32(x)
+    # the Qbits = 32 pass runs stock cuDNN / cuBLAS: keep it in true float32 (PyTorch's default would be TF32 for
+    # convolutions), so the observed maxima are the reference's CPU float32 maxima up to summation order
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with cal, torch.no_grad():
+            for x in batches:
+                model_fp32(x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     return cal.scales(group)
+
+
+def quantize_dynamic(x, q_bit, kind="act", divisor=15.5, group=None, want="codes", absmax=None):
+    """Dynamic max-scaling quantizer (north_star: abs-max reduction -> max-scaling -> round to nearest), all on the
+    device: slfp_absmax_f32 -> [allreduce(MAX) when torch.distributed is initialised, so that every rank of a sharded
+    batch uses the bit-identical K] -> slfp_quantize_dyn_f32, which reads K = float32(max / divisor) from device memory.
+    Three asynchronous launches on the current stream, no host synchronisation, CUDA-graph capturable.
+    Returns (codes | fake-quant float32, K as a 0-dim device tensor).  Reference recipe: K = max|x| / 15.5
+    (cifar100_train_eval.py:261-271, nets_cifar/mobilenetv1.py:15)."""
+    import torch.distributed as dist
+    lib = nv.lib()
+    nv.require_cuda(x, "quantize_dynamic")
+    xf = nv.dense_flat(x.detach())
+    if absmax is None:
+        absmax = torch.empty((), dtype=torch.float32, device=x.device)
+        nv.check(lib.slfp_absmax_f32(xf.data_ptr(), xf.numel(), absmax.data_ptr(), 1, nv.stream()))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(absmax, op=dist.ReduceOp.MAX, group=group)
+    fmt = nv.fmt_for(q_bit, kind)
+    k = torch.empty((), dtype=torch.float32, device=x.device)
+    if want == "codes":
+        out = torch.empty(xf.shape, dtype=torch.uint8, device=x.device)
+        nv.check(lib.slfp_quantize_dyn_f32(xf.data_ptr(), xf.numel(), absmax.data_ptr(), float(divisor), fmt, 0, out.data_ptr(), None, None,
+                                           k.data_ptr(), nv.stream()))
+    else:
+        out = torch.empty_like(xf)
+        nv.check(lib.slfp_quantize_dyn_f32(xf.data_ptr(), xf.numel(), absmax.data_ptr(), float(divisor), fmt, 0, None, out.data_ptr(), None,
+                                           k.data_ptr(), nv.stream()))
+    return out, k

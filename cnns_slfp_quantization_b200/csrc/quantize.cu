@@ -64,7 +64,20 @@ struct QuantArgs {
     float* fakeq;
     __half* f16;
     int zero_is_zero;
+    // dynamic max-scaling (slfp_quantize_dyn_f32): K = float32(double(*k_src) / k_src_div) read from DEVICE memory when the
+    // kernel starts (abs-max kernel -> [allreduce(MAX)] -> this kernel, no host round trip, CUDA-graph capturable)
+    const float* k_src;
+    double k_src_div;
+    float* k_out;
 };
+
+__device__ __forceinline__ DivK resolve_divk(const QuantArgs& a) {
+    if (a.k_src == nullptr) return a.k_div;
+    // the reference computes the scale in Python float64 (np.array(max) / 15.5) and its arithmetic then uses float32(K)
+    const float k = (float)((double)__ldg(a.k_src) / a.k_src_div);
+    if (a.k_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.k_out = k;
+    return make_divk(k);
+}
 
 template <int FMT>
 __device__ __forceinline__ void quant_elem(float x, const DivK& k_div, bool zz, const uint32_t* tab,
@@ -109,6 +122,7 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
         __syncthreads();
     }
     const bool zz = a.zero_is_zero != 0;
+    const DivK kdiv = resolve_divk(a);
     const size_t n_tiles = a.n / kQTile;
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t base = tile * kQTile;
@@ -122,9 +136,9 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
             const float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
             uint32_t c[4];
             float q[4];
-            if (FMT == SLFP_FMT_SFP44_OUT || !a.k_div.fast) {
+            if (FMT == SLFP_FMT_SFP44_OUT || !kdiv.fast) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) quant_elem<FMT>(xs[i], a.k_div, zz, s_tab, c[i], q[i]);
+                for (int i = 0; i < 4; ++i) quant_elem<FMT>(xs[i], kdiv, zz, s_tab, c[i], q[i]);
             } else {
                 constexpr int F = FMT == SLFP_FMT_SFP44_OUT ? SLFP_FMT_SFP33 : FMT;
                 // common path: reciprocal division (exact inside the normal range) + the in-range encoder.  One
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
                 uint32_t xmin = 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    qv[i] = div_k_fused(xs[i], a.k_div);
+                    qv[i] = div_k_fused(xs[i], kdiv);
                     nan_probe = fmaf(qv[i], 0.0f, nan_probe);
                     // rotate the sign to bit 0: 2|x| + s.  +0 -> 0 (wraps to 0xffffffff: stays on the fast path), -0 -> 1 and
                     // 0 < |x| < 2^-119 -> below 0x08000000: both take the general path (a zero code carries no sign)
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
                 }
                 if (nan_probe != nan_probe || xmin < 0x08000000u - 1u) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) c[i] = encode<F>(div_k(xs[i], a.k_div));
+                    for (int i = 0; i < 4; ++i) c[i] = encode<F>(div_k(xs[i], kdiv));
                 } else if (F == SLFP_FMT_SLFP34_WGT) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) c[i] = encode_inrange<F>(qv[i]);
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(kQThreads) quantize_kernel(QuantArgs a) {
         for (size_t i = n_tiles * kQTile + threadIdx.x; i < a.n; i += kQThreads) {
             uint32_t c;
             float q;
-            quant_elem<FMT>(a.x[i], a.k_div, zz, s_tab, c, q);
+            quant_elem<FMT>(a.x[i], kdiv, zz, s_tab, c, q);
             if (CODES) a.codes[i] = (uint8_t)c;
             if (FAKEQ) a.fakeq[i] = q;
             if (F16) a.f16[i] = __float2half_rn(q);
@@ -219,10 +233,11 @@ __global__ void __launch_bounds__(kQThreads) quantize_scalar_kernel(QuantArgs a)
     __shared__ uint32_t s_tab[16];
     if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
     __syncthreads();
+    const DivK kdiv = resolve_divk(a);
     for (size_t i = (size_t)blockIdx.x * kQThreads + threadIdx.x; i < a.n; i += (size_t)gridDim.x * kQThreads) {
         uint32_t c;
         float q;
-        quant_elem<FMT>(a.x[i], a.k_div, a.zero_is_zero != 0, s_tab, c, q);
+        quant_elem<FMT>(a.x[i], kdiv, a.zero_is_zero != 0, s_tab, c, q);
         if (a.codes) a.codes[i] = (uint8_t)c;
         if (a.fakeq) a.fakeq[i] = q;
         if (a.f16) a.f16[i] = __float2half_rn(q);
@@ -709,6 +724,10 @@ __global__ void __launch_bounds__(256) quantize_relu_kernel(const float* __restr
 using namespace slfp;
 
 extern "C" int slfp_version(void) { return SLFP_B200_VERSION; }
+#ifndef SLFP_SOURCE_HASH
+#define SLFP_SOURCE_HASH "unknown"
+#endif
+extern "C" const char* slfp_build_id(void) { return SLFP_SOURCE_HASH; }
 extern "C" const char* slfp_last_error(void) { return g_err; }
 
 extern "C" int slfp_quantize_f32(const float* x, size_t n, float k_div, int fmt, unsigned flags, uint8_t* codes,
@@ -723,7 +742,7 @@ extern "C" int slfp_quantize_f32(const float* x, size_t n, float k_div, int fmt,
         quantize_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, make_divk(k_div), fmt == SLFP_FMT_SFP33_RELU, codes, fakeq);
         return check_launch("quantize_relu_kernel");
     }
-    QuantArgs a{x, n, make_divk(k_div), codes, fakeq, (__half*)f16, (flags & SLFP_Q_LAYEROUT_ZERO_IS_ZERO) ? 1 : 0};
+    QuantArgs a{x, n, make_divk(k_div), codes, fakeq, (__half*)f16, (flags & SLFP_Q_LAYEROUT_ZERO_IS_ZERO) ? 1 : 0, nullptr, 1.0, nullptr};
     cudaStream_t st = (cudaStream_t)stream;
     switch (fmt) {
         case SLFP_FMT_SFP33: return launch_quantize<SLFP_FMT_SFP33>(a, st);
@@ -732,6 +751,25 @@ extern "C" int slfp_quantize_f32(const float* x, size_t n, float k_div, int fmt,
         case SLFP_FMT_SFP44_OUT: return launch_quantize<SLFP_FMT_SFP44_OUT>(a, st);
     }
     return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_f32: unknown format %d", fmt);
+}
+
+extern "C" int slfp_quantize_dyn_f32(const float* x, size_t n, const float* absmax, double divisor, int fmt, unsigned flags,
+                                     uint8_t* codes, float* fakeq, void* f16, float* k_out, slfp_stream_t stream) {
+    if (n == 0) return 0;
+    if (!x || !absmax || (!codes && !fakeq && !f16)) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_dyn_f32: null pointer");
+    if (!(divisor > 0.0)) return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_dyn_f32: divisor must be positive");
+    if (fmt == SLFP_FMT_SFP44_OUT && codes)
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_dyn_f32: SFP<4,4> layer-out has no 8-bit code");
+    // k_div.fast = 1: the kernel re-derives the whole DivK from device memory; this value only selects the launch shape
+    QuantArgs a{x, n, make_divk(1.0f), codes, fakeq, (__half*)f16, (flags & SLFP_Q_LAYEROUT_ZERO_IS_ZERO) ? 1 : 0, absmax, divisor, k_out};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (fmt) {
+        case SLFP_FMT_SFP33: return launch_quantize<SLFP_FMT_SFP33>(a, st);
+        case SLFP_FMT_SLFP34_ACT: return launch_quantize<SLFP_FMT_SLFP34_ACT>(a, st);
+        case SLFP_FMT_SLFP34_WGT: return launch_quantize<SLFP_FMT_SLFP34_WGT>(a, st);
+        case SLFP_FMT_SFP44_OUT: return launch_quantize<SLFP_FMT_SFP44_OUT>(a, st);
+    }
+    return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_dyn_f32: format %d (signed code formats only)", fmt);
 }
 
 extern "C" int slfp_quantize_nhwc_f32(const float* x, size_t npix, int c, int c_phys, float k_div, int fmt,

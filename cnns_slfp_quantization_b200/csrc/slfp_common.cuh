@@ -87,7 +87,7 @@ struct DivK {
     float k, rk;
     int fast;
 };
-static inline DivK make_divk(float k) {
+__host__ __device__ static inline DivK make_divk(float k) {
     DivK d;
     d.k = k;
     d.rk = 1.0f / k;

@@ -225,8 +225,13 @@ class Plan:
         self.ops.append(self._call(self.lib.slfp_conv2d_fwd, ctypes.byref(d), x.buf.data_ptr(), wbuf.data_ptr(),
                                    ctypes.byref(epi)))
         fl = 2.0 * x.n * Ho * Wo * K * (C // groups) * R * S
+        if hasattr(mod, "orig"):        # space-to-depth stem: count the ALGORITHMIC taps (7x7x3 = 147), not the folded 4x4x12 = 192
+            fl = 2.0 * x.n * Ho * Wo * K * float(np.prod(mod.orig.weight.shape[1:]))
         self.flops += fl
-        self.conv_flops.append((fl, groups == 1, f"{C}->{K} {R}x{S} s{stride[0]} @{x.h}"))
+        # algorithmic HBM bytes of the launch: codes in, everything written, the weight operand, the residual read
+        by = x.buf.numel() + wbuf.numel() * wbuf.element_size() + (residual.buf.numel() * residual.buf.element_size() if residual is not None else 0)
+        by += sum(t.buf.numel() for t in out["codes"].values()) + sum(out[k].buf.numel() * out[k].buf.element_size() for k in ("f16", "f32") if out[k] is not None)
+        self.conv_flops.append((fl, groups == 1, f"{C}->{K} {R}x{S} s{stride[0]} @{x.h}", by))
         return out
 
     def _affine(self, mod, bn, K, linear=False):
@@ -306,7 +311,9 @@ class Plan:
                                    x2.buf.data_ptr(), wbuf.data_ptr(), ctypes.byref(epi)))
         fl = 2.0 * x1.n * Ho * Wo * K * (C1 + C2)
         self.flops += fl
-        self.conv_flops.append((fl, True, f"{C1}+{C2}->{K} 1x1 dual @{x1.h}"))
+        by = x1.buf.numel() + x2.buf.numel() + wbuf.numel() * 2 + sum(t.buf.numel() for t in out["codes"].values()) + \
+            (out["f16"].buf.numel() * 2 if out["f16"] is not None else 0)
+        self.conv_flops.append((fl, True, f"{C1}+{C2}->{K} 1x1 dual @{x1.h}", by))
         return out
 
     def maxpool(self, x, k, stride, pad):

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define SLFP_B200_VERSION 100
+#define SLFP_B200_VERSION 200
 
 typedef void *slfp_stream_t; /* cudaStream_t */
 
@@ -74,6 +74,9 @@ enum {
 
 int slfp_version(void);
 const char *slfp_last_error(void);
+/* sha256 prefix of the sources this binary was compiled from (cnns_slfp_quantization_b200/build.py: source_hash);
+ * the Python binding refuses a library whose id differs from the sources next to it. */
+const char *slfp_build_id(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Quantizers.  Replaces quantize_weight(k)/quantize_act(k)/quantize_layerout(k).forward
@@ -85,6 +88,16 @@ const char *slfp_last_error(void);
  * ------------------------------------------------------------------------------------------- */
 int slfp_quantize_f32(const float *x, size_t n, float k_div, int fmt, unsigned flags,
                       uint8_t *codes, float *fakeq, void *f16, slfp_stream_t stream);
+
+/* Dynamic max-scaling form of the same quantizer (north_star: "tensor abs-max reduction, max-scaling, round to
+ * nearest"; the reference derives K = max|x| / 15.5 offline, cifar100_train_eval.py:213-277, nets_cifar/mobilenetv1.py:15).
+ * K is NOT a host value here: the kernel reads *absmax (DEVICE float, e.g. written by slfp_absmax_f32 and optionally
+ * max-allreduced over ranks) when it starts and uses K = float32(double(*absmax) / divisor) - the reference's float64
+ * Python division rounded to the float32 its tensor arithmetic uses.  No host round trip: abs-max -> [allreduce(MAX)]
+ * -> quantize is three asynchronous launches on one stream and can be captured in a CUDA graph.  k_out (DEVICE float,
+ * may be NULL) receives the K that was used. */
+int slfp_quantize_dyn_f32(const float *x, size_t n, const float *absmax, double divisor, int fmt, unsigned flags,
+                          uint8_t *codes, float *fakeq, void *f16, float *k_out, slfp_stream_t stream);
 
 /* Same quantizer for an NHWC activation tensor whose code tensor has a padded channel count
  * (c_phys >= c; pad channels receive code 0 = exact zero): npix pixels of c floats -> npix * c_phys

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), n
     assert sorted(_native.EXPORTED_SYMBOLS) == names
-    assert _native.lib().slfp_version() == 100
+    assert _native.lib().slfp_version() == 200
 
 
 def test_struct_layout_matches_header():

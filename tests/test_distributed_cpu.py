@@ -50,9 +50,44 @@ def _worker(rank, world, port, out):
     assert calls >= 2
     for i, p in enumerate(params):
         assert torch.allclose(p.grad, torch.full_like(p, (i + 1) * (world + 1) / 2.0))
-    # 4. predictions gathered in rank order
+    # 3b. a parameter that got no gradient on this rank contributes zeros (same collectives on every rank)
+    q = [nn.Parameter(torch.zeros(5)), nn.Parameter(torch.zeros(3))]
+    q[0].grad = torch.full((5,), float(rank + 1))
+    if rank == 0:
+        q[1].grad = torch.full((3,), 4.0)
+    parallel.allreduce_gradients(q)
+    assert torch.allclose(q[0].grad, torch.full((5,), 1.5)) and torch.allclose(q[1].grad, torch.full((3,), 2.0))
+    # 3c. GradientArena: bucketed allreduce launched from grad hooks DURING backward, gradients as views of one arena
+    torch.manual_seed(1)
+    net = nn.Sequential(nn.Linear(16, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU(), nn.Linear(64, 8))
+    ref_net = nn.Sequential(nn.Linear(16, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU(), nn.Linear(64, 8))
+    ref_net.load_state_dict(net.state_dict())
+    arena = parallel.GradientArena(net.parameters(), bucket_bytes=2048)
+    assert len(arena.buckets) >= 3
+    xs = [torch.randn(4, 16, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    for step in range(2):
+        if step == 0:
+            arena.zero_grad()
+        else:
+            net.zero_grad(set_to_none=True)          # what optimizer.zero_grad() does by default: the hook restores the views
+        net(xs[rank]).square().sum().backward()
+        n_reduced = arena.finish()
+        assert n_reduced == len(arena.buckets)
+        ref_net.zero_grad()
+        for r in range(world):                        # the same average computed locally
+            (ref_net(xs[r]).square().sum() / world).backward()
+        for p, q_ in zip(net.parameters(), ref_net.parameters()):
+            assert p.grad.data_ptr() == arena.views[p].data_ptr()
+            assert torch.allclose(p.grad, q_.grad, rtol=1e-5, atol=1e-6)
+    arena.close()
+    # 4. predictions gathered in rank order; ragged shards (n_items % world != 0) are padded and trimmed
     top1 = parallel.gather_predictions(torch.tensor([rank * 10, rank * 10 + 1]))
     assert top1.tolist() == [0, 1, 10, 11]
+    lo5, hi5 = parallel.shard_batch(5, rank, world)
+    rag = parallel.gather_predictions(torch.arange(lo5, hi5), n_items=5)
+    assert rag.tolist() == [0, 1, 2, 3, 4]
+    lo1, hi1 = parallel.shard_batch(1, rank, world)          # rank 1 holds an empty shard
+    assert parallel.gather_predictions(torch.arange(lo1, hi1), n_items=1).tolist() == [0]
     out.put((rank, ka.tolist()))
     dist.destroy_process_group()
 

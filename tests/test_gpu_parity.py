@@ -92,9 +92,9 @@ def stats(y, ref):
 
 
 # logit RMS bounds: ~1.5x the values measured on a B200 with this tree (profiles/r02_parity.md)
-CASES = [("resnet50_224", "resnet50", 8, 0.60), ("vgg16", "vgg16", None, 0.60), ("mobilenetv1_cifar", "mobilenetv1_cifar", None, 0.60),
-         ("mobilenetv1_imgnet", "mobilenetv1_imgnet", None, 0.60), ("shufflenetv2", "shufflenetv2", None, 0.60),
-         ("shufflenetv2_224", "shufflenetv2", None, 0.60)]
+CASES = [("resnet50_224", "resnet50", 8, 0.06), ("vgg16", "vgg16", None, 0.33), ("mobilenetv1_cifar", "mobilenetv1_cifar", None, 0.46),
+         ("mobilenetv1_imgnet", "mobilenetv1_imgnet", None, 0.035), ("shufflenetv2", "shufflenetv2", None, 0.05),
+         ("shufflenetv2_224", "shufflenetv2", None, 0.37)]
 
 
 @pytest.mark.parametrize("key,net,chunk,rms_bound", CASES)
@@ -265,3 +265,27 @@ def test_reference_gpu_path_noise_floor(tf32):
     _report(f"{key}.reference_torch_gpu_tf32_{'on' if tf32 else 'off'}", st)
     print(json.dumps(st))
     assert np.isfinite(y).all()
+
+
+@pytest.mark.parametrize("key,net", [("resnet50_taps", "resnet50"), ("vgg16", "vgg16"), ("mobilenetv1_cifar", "mobilenetv1_cifar")])
+def test_calibration_reproduces_reference_scales(key, net):
+    """calibration.calibrate_scales (fused abs-max kernel over a Qbits = 32 forward, SURVEY f-1) against the scales the
+    REFERENCE's own recipe produced for the fixture (cifar100_train_eval.py:213-277 run on CPU by make_golden_net224.py):
+    Kw bit-exact (weights are inputs, max is exact); Ka within 1e-5 relative (the float32 forward of cuDNN vs oneDNN
+    differs by summation order only - TF32 is switched off inside calibrate_scales)."""
+    from cnns_slfp_quantization_b200 import nets_common as nc, calibration
+    qbit, batch, size = [int(v) for v in G[f"{key}.cfg"]]
+    m, _ = build(net, 32)
+    m.load_state_dict(nc.synth_state_dict(m))
+    nc.apply_prototype_classifier(m, G[f"{key}.protos"], float(G[f"{key}.rest_scale"]), G[f"{key}.fc_bias"])
+    n = len(nc.quantized_layers(m))
+    nc.set_scales(m, np.ones(n), np.ones(n))
+    m = m.cuda().eval()
+    x = nc.synth_images(batch, size).cuda()
+    ka, kw = calibration.calibrate_scales(m, [x])
+    ref_ka, ref_kw = G[f"{key}.ka"], G[f"{key}.kw"]
+    assert (kw == ref_kw).all(), np.abs(kw / ref_kw - 1).max()
+    assert ka[0] == ref_ka[0]                                   # the network input itself
+    rel = np.abs(ka / ref_ka - 1)
+    _report(key + ".calibration", {"ka_max_rel_err": float(rel.max()), "kw_bit_exact": True, "layers": int(n)})
+    assert rel.max() <= 1e-5, rel.max()

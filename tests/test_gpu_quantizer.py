@@ -152,3 +152,49 @@ def test_host_buffer_entry(orc):
                                              codes.ctypes.data_as(ctypes.c_void_p), fq.ctypes.data_as(ctypes.c_void_p)))
     oc, oq = orc.quantize(x, 1, kdiv=0.9)
     assert (codes == oc).all() and same_bits(oq, fq).all()
+
+
+@pytest.mark.parametrize("qbit,kind", [(8, "act"), (8, "weight"), (7, "act")])
+def test_dynamic_max_scaling_quantizer(orc, qbit, kind):
+    """abs-max -> max-scaling -> quantize entirely on the device (slfp_quantize_dyn_f32 reads K from device memory):
+    codes and fake-quant equal the oracle's quantizer run with K = float32(float64(max|x|) / 15.5), the reference's
+    recipe (nets_cifar/mobilenetv1.py:15); the whole sequence is capturable in a CUDA graph and follows the data."""
+    import torch
+    from cnns_slfp_quantization_b200 import calibration
+    rng = np.random.default_rng(21 + qbit)
+    x = (rng.standard_normal(300007) * rng.uniform(0.01, 30)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    codes, k = calibration.quantize_dynamic(xt, qbit, kind)
+    fq, k2 = calibration.quantize_dynamic(xt, qbit, kind, want="fakeq")
+    torch.cuda.synchronize()
+    k_want = np.float32(np.float64(np.abs(x).max()) / 15.5)
+    assert np.float32(k.item()) == k_want and np.float32(k2.item()) == k_want
+    want_codes, want_fq = orc.quantize(x, orc.fmt_for(qbit, kind), float(k_want))
+    assert (codes.cpu().numpy() == want_codes).all()
+    assert (fq.cpu().numpy().view(np.uint32) == want_fq.view(np.uint32)).all()
+    # graph capture: replaying after the INPUT changed re-derives K on the device
+    amax = torch.zeros((), dtype=torch.float32, device="cuda")
+    out = torch.empty(x.size, dtype=torch.uint8, device="cuda")
+    kd = torch.empty((), dtype=torch.float32, device="cuda")
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    fmt = nv.fmt_for(qbit, kind)
+
+    def seq():
+        st = nv.stream()
+        nv.check(lib.slfp_absmax_f32(xt.data_ptr(), xt.numel(), amax.data_ptr(), 1, st))
+        nv.check(lib.slfp_quantize_dyn_f32(xt.data_ptr(), xt.numel(), amax.data_ptr(), 15.5, fmt, 0, out.data_ptr(), None, None, kd.data_ptr(), st))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        seq()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        seq()
+    x2 = (x * 3.7).astype(np.float32)
+    xt.copy_(torch.from_numpy(x2))
+    g.replay()
+    torch.cuda.synchronize()
+    k2_want = np.float32(np.float64(np.abs(x2).max()) / 15.5)
+    assert np.float32(kd.item()) == k2_want
+    assert (out.cpu().numpy() == orc.quantize(x2, orc.fmt_for(qbit, kind), float(k2_want))[0]).all()

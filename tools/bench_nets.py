@@ -44,7 +44,7 @@ for name, ctor, qbit, batch, size, comp in CASES:
         plan.run(); torch.cuda.synchronize()
         prof, nv.profile = nv.profile, None
         conv = sorted(prof.get("slfp_conv2d_fwd", []) + prof.get("slfp_conv2d_fwd_dual", []), key=lambda t: t[2])
-        for (ea, eb, _), (fl, is_dense, desc) in zip(conv, plan.conv_flops):
+        for (ea, eb, _), (fl, is_dense, desc, _by) in zip(conv, plan.conv_flops):
             print(f"   {desc:34s} {'dense' if is_dense else 'dw   '} {ea.elapsed_time(eb) * 1e3:9.1f} us")
         print("  ", {k: round(sum(x.elapsed_time(y) for x, y, _ in v), 4) for k, v in prof.items()})
     print(json.dumps({"net": name, "batch": batch, "size": size, "ms_per_step": round(ms, 4), "images_per_s": round(batch / ms * 1e3, 1),
