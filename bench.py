@@ -122,7 +122,9 @@ def synth_model(config, qbit, size, ops, device, calibrate):
     n = len(nc.quantized_layers(m32))
     nc.set_scales(m32, np.ones(n), np.ones(n))
     m32 = m32.to(device)
-    ka, kw = calibrate(m32, nc.synth_images(4, min(size, 96) if size > 32 else size).to(device))
+    # calibration pass on a few small images (MobileNetV1-ImageNet ends in AvgPool2d(7): full size there)
+    cal_size = size if (size <= 32 or config == "mobilenetv1_imgnet") else min(size, 96)
+    ka, kw = calibrate(m32, nc.synth_images(4, cal_size).to(device))
     m = ctor(qbit, ops).eval()
     m.load_state_dict(sd)
     # calibration returns the scales in module-traversal order (nc.quantized_layers); the constructors' `scales`

@@ -10,7 +10,7 @@ import torch
 
 from .build import LIB_PATH, source_hash
 
-FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU = 0, 1, 2, 3, 4, 5
+FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU, FMT_SFP33_SFAST = 0, 1, 2, 3, 4, 5, 6
 ACT_STL, ACT_SWISH, ACT_SIGMOID = 0, 1, 2
 SGD_NORMAL, SGD_DSGD, SGD_SSGD = 0, 1, 2
 Q_LAYEROUT_ZERO_IS_ZERO = 1
@@ -28,7 +28,11 @@ class SlfpEpilogue(ctypes.Structure):
     _fields_ = [("bias_q", c_vp), ("post_a", c_f), ("post_b", c_f), ("ch_scale", c_vp), ("ch_shift", c_vp),
                 ("residual", c_vp), ("residual_f16", c_i), ("relu", c_i), ("y_f32", c_vp), ("y_f16", c_vp),
                 ("y_codes", c_vp), ("next_k_div", c_f), ("next_fmt", c_i), ("k_phys_out", c_i),
-                ("y_codes2", c_vp), ("next_k_div2", c_f), ("ch_mul", c_vp), ("ch_add", c_vp)]
+                ("y_codes2", c_vp), ("next_k_div2", c_f), ("ch_mul", c_vp), ("ch_add", c_vp), ("layerout", c_i)]
+
+
+class SlfpGatherChan(ctypes.Structure):
+    _fields_ = [("src", c_vp), ("stride", c_i), ("ch", c_i)]
 
 
 class SlfpWeightJob(ctypes.Structure):
@@ -46,6 +50,7 @@ _SIGS = {
     "slfp_quantize_nchw_f32": (c_i, [c_vp, c_i, c_i, c_sz, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_quantize_nchw_s2d_f32": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_dequantize": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
+    "slfp_gather_quantize_f16": (c_i, [c_vp, c_sz, c_i, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_absmax_f32": (c_i, [c_vp, c_sz, c_vp, c_i, c_vp]),
     "slfp_conv_wpitch": (c_sz, [ctypes.POINTER(SlfpConvDesc)]),
     "slfp_prepare_weights": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_ll, c_ll, c_ll, c_ll, c_f, c_i, c_vp, c_vp,
@@ -74,7 +79,7 @@ _lib = None
 # Every entry point that launches kernels on the caller's stream.  The proxy below counts those calls
 # (bench.py reports them as `gpu_launches`) and, when a profile dict is installed, brackets each call
 # with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
-_LAUNCHING = {"slfp_quantize_dyn_f32", "slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
+_LAUNCHING = {"slfp_gather_quantize_f16", "slfp_quantize_dyn_f32", "slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
               "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_conv2d_bwd_ws", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
               "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32"}
 launch_count = 0

@@ -34,7 +34,8 @@ __device__ __forceinline__ void epilogue_store(const SlfpEpilogue& e, float t, s
     if (e.residual)
         t += e.residual_f16 ? __half2float(reinterpret_cast<const __half*>(e.residual)[off])
                             : reinterpret_cast<const float*>(e.residual)[off];
-    if (e.relu) t = fmaxf(t, 0.0f);
+    if (e.layerout) t = layerout_quantize(t, e.layerout == 2);
+    if (e.relu) t = (t != t) ? t : fmaxf(t, 0.0f);             // torch.relu keeps NaN (fmaxf would drop it)
     if (e.y_f32) e.y_f32[off] = t;
     if (e.y_f16) reinterpret_cast<__half*>(e.y_f16)[off] = __float2half_rn(t);
     if (e.y_codes) {
@@ -107,6 +108,7 @@ struct DwFastParams {
     const uint8_t* w;          // [C][R*S] weight codes
     int N, H, W, Cp, C, R, S, sh, sw, ph, pw, dh, dw, Ho, Wo;
     int act_fmt, wgt_sfp33, out_sfp33;
+    int out_signed;            // 1: SLFP_FMT_SFP33_SFAST (no ReLU: sign bit + 7-bit magnitude code), 0: post-ReLU codes
     const float* ch_mul;
     const float* ch_add;
     float sc;                  // 1 / (16 Ka_next)
@@ -190,7 +192,14 @@ __global__ void __launch_bounds__(256) dwconv_fast_kernel(const DwFastParams p) 
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.ch_add + c0) + g);
             const float v0 = fmaf(acc[4 * g + 0], m4.x, a4.x), v1 = fmaf(acc[4 * g + 1], m4.y, a4.y);
             const float v2 = fmaf(acc[4 * g + 2], m4.z, a4.z), v3 = fmaf(acc[4 * g + 3], m4.w, a4.w);
-            if (p.out_sfp33) {
+            if (p.out_signed) {
+                const float vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int32_t m = encode_relu_fast_raw16<true>(__saturatef(fabsf(vv[e]) * p.sc));
+                    tq[4 * g + e] = (m < 0 ? 0 : (m > 127 ? 127 : m)) | (int32_t)((__float_as_uint(vv[e]) >> 24) & 0x80u);
+                }
+            } else if (p.out_sfp33) {
                 tq[4 * g + 0] = encode_relu_fast_raw16<true>(__saturatef(v0 * p.sc)); tq[4 * g + 1] = encode_relu_fast_raw16<true>(__saturatef(v1 * p.sc));
                 tq[4 * g + 2] = encode_relu_fast_raw16<true>(__saturatef(v2 * p.sc)); tq[4 * g + 3] = encode_relu_fast_raw16<true>(__saturatef(v3 * p.sc));
             } else {
@@ -322,8 +331,14 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
                 const float mm[4] = {m4[g].x, m4[g].y, m4[g].z, m4[g].w}, aa[4] = {a4[g].x, a4[g].y, a4[g].z, a4[g].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float v = __saturatef(fmaf(acc[o][4 * g + e], mm[e], aa[e]) * p.sc);
-                    tq[4 * g + e] = ((int32_t)__float_as_uint(v) >> enc_shift) - enc_bias;
+                    const float y = fmaf(acc[o][4 * g + e], mm[e], aa[e]);
+                    if (p.out_signed) {                 // sign bit + min(code(|y|), 127); a negative zero keeps magnitude code 0
+                        const int32_t m = ((int32_t)__float_as_uint(__saturatef(fabsf(y) * p.sc)) >> 19) - 0x76F;
+                        tq[4 * g + e] = (m < 0 ? 0 : (m > 127 ? 127 : m)) | (int32_t)((__float_as_uint(y) >> 24) & 0x80u);
+                    } else {
+                        const float v = __saturatef(y * p.sc);
+                        tq[4 * g + e] = ((int32_t)__float_as_uint(v) >> enc_shift) - enc_bias;
+                    }
                 }
             }
             if (pad_channels) {                                                      // zero code in pad channels
@@ -388,10 +403,11 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): asymmetric padding is a dense-path feature");
     {
         // fused-pipeline depthwise: folded affine + ReLU + post-ReLU codes only, 16-channel vectors
-        const bool relu_out = epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU;
+        const bool sfast = epi->next_fmt == SLFP_FMT_SFP33_SFAST && !epi->relu;
+        const bool relu_out = (epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU) && epi->relu;
         const bool dw = d->groups == d->c && d->k == d->c;
         const size_t smem = 256 * 32 * 4 + (size_t)d->r * d->s * d->c_phys * 4;
-        if (dw && relu_out && epi->ch_mul && epi->ch_add && epi->relu && epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->y_f32 &&
+        if (dw && (relu_out || sfast) && !epi->layerout && epi->ch_mul && epi->ch_add && epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->y_f32 &&
             !epi->residual && epi->k_phys_out == d->c_phys && d->c_phys % 16 == 0 && epi->next_k_div > 0.f && smem <= 200 * 1024 &&
             ((((uintptr_t)x_codes | (uintptr_t)epi->y_codes | (uintptr_t)epi->ch_mul | (uintptr_t)epi->ch_add) & 15u) == 0)) {
             DwFastParams q;
@@ -400,8 +416,9 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
             q.sh = d->stride_h; q.sw = d->stride_w; q.ph = d->pad_h; q.pw = d->pad_w; q.dh = d->dil_h; q.dw = d->dil_w;
             q.Ho = p.Ho; q.Wo = p.Wo;
             q.act_fmt = d->fmt;
-            q.wgt_sfp33 = (d->fmt == SLFP_FMT_SFP33 || d->fmt == SLFP_FMT_SFP33_RELU) ? 1 : 0;    // weights: the q_bit's weight format
-            q.out_sfp33 = epi->next_fmt == SLFP_FMT_SFP33_RELU ? 1 : 0;
+            q.wgt_sfp33 = (d->fmt == SLFP_FMT_SFP33 || d->fmt == SLFP_FMT_SFP33_RELU || d->fmt == SLFP_FMT_SFP33_SFAST) ? 1 : 0;    // weights: the q_bit's weight format
+            q.out_sfp33 = (epi->next_fmt == SLFP_FMT_SFP33_RELU || sfast) ? 1 : 0;
+            q.out_signed = sfast ? 1 : 0;
             q.ch_mul = epi->ch_mul; q.ch_add = epi->ch_add;
             q.sc = (float)(1.0 / (16.0 * (double)epi->next_k_div));
             q.y = epi->y_codes;

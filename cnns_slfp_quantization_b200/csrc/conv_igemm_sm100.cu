@@ -555,11 +555,16 @@ static int launch_igemm(const CUtensorMap& tmap, const IgemmParams& p, cudaStrea
 bool conv2d_fwd_dense_v2_supported(const SlfpConvDesc* d);
 int conv2d_fwd_dense_v2(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st);
 
+bool conv2d_fwd_stem_direct_supported(const SlfpConvDesc* d, const SlfpEpilogue* e);
+int conv2d_fwd_stem_direct(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* e, cudaStream_t st);
+
 int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* w_f16, const SlfpEpilogue* epi,
                      cudaStream_t st) {
     // c_phys % 16 == 0: the warp-specialised TMA-im2col kernel (conv_igemm_v2.cu); this file keeps the
     // 4-channel network-input layout (the 7x7 / 3x3 stems), whose taps are narrower than a TMA box row.
     if (conv2d_fwd_dense_v2_supported(d)) return conv2d_fwd_dense_v2(d, x_codes, w_f16, epi, st);
+    // 3x3 RGB stems of the fused pipeline: CUDA-core direct convolution (conv_stem_direct.cu)
+    if (conv2d_fwd_stem_direct_supported(d, epi)) return conv2d_fwd_stem_direct(d, x_codes, w_f16, epi, st);
     if (d->pad_h_extra || d->pad_w_extra)
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: asymmetric padding needs c_phys %% 16 == 0");
     if (epi->y_codes && epi->next_fmt != SLFP_FMT_SLFP34_ACT && epi->next_fmt != SLFP_FMT_SFP33)
@@ -568,6 +573,7 @@ int conv2d_fwd_dense(const SlfpConvDesc* d, const uint8_t* x_codes, const void* 
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: c_phys=%d must be 4 or a multiple of 16", d->c_phys);
     if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: activation code format %d", d->fmt);
+    if (epi->layerout) return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: layerout epilogue needs c_phys %% 16 == 0 (the 4-channel stem kernel has none)");
     if (epi->y_codes && (epi->k_phys_out % 16 != 0 || epi->k_phys_out < d->k))
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: k_phys_out=%d", epi->k_phys_out);
     if ((((uintptr_t)x_codes | (uintptr_t)w_f16 | (uintptr_t)epi->y_f32 | (uintptr_t)epi->y_f16 |

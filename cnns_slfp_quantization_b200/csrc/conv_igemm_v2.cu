@@ -206,7 +206,14 @@ __device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += res[i];
         }
-        if (e.relu) {
+        if (e.layerout) {
+            // conv -> BN -> layerout_quantize_func (SFP<4,4>) -> ReLU; torch.relu propagates the reference's NaN at exact 0
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = layerout_quantize(v[i], e.layerout == 2);
+                if (e.relu) v[i] = (v[i] != v[i]) ? v[i] : fmaxf(v[i], 0.0f);
+            }
+        } else if (e.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
@@ -269,7 +276,7 @@ __device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_
                     // signed code formats: the exact quantizer (IEEE quotient via the reciprocal sequence)
                     const DivK kd = pass ? p.next_div2 : p.next_div;
                     uint32_t c[16];
-                    const bool relu_path = e.relu && kd.k > 0.f;
+                    const bool relu_path = e.relu && kd.k > 0.f && !e.layerout;    // (layerout may hand a NaN through the ReLU)
                     if (e.next_fmt == SLFP_FMT_SFP33) {
                         if (relu_path) {
 #pragma unroll
@@ -313,6 +320,32 @@ __device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_
 // (tools/ubench/store_pattern.cu).  Lane pairs therefore swap one 16-byte piece (4 SHFL) so that every store
 // instruction writes 32 contiguous bytes per row: lanes 2i / 2i+1 hold pieces (A, B) = 32 contiguous bytes of
 // rows 2i / 2i+1; afterwards `first` belongs to row 2i and `second` to row 2i+1, both at piece index lane & 1.
+// sixteen relu'd values -> sixteen codes.  fast: the post-ReLU formats (saturating scale, re-based bit pattern, pack).
+// exact: the signed quantizer formats through the exact encoder (IEEE quotient, round-half-even) - used after
+// quantize_layerout, whose 5-bit values divided by a scale that is itself max / 15.5 of such values land EXACTLY on
+// rounding ties of the next grid (e.g. v = vmax / 2 -> 7.75), where the fast formats' ties-up would differ from the
+// reference's round-half-even on a visible share of the elements instead of a sliver.
+template <bool SFP33>
+__device__ __forceinline__ uint4 encode16_fast(const float (&v)[16], float sc) {
+    int32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i] * sc));
+    return make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
+                      ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+}
+template <bool SFP33>
+__device__ __forceinline__ uint4 encode16_exact(const float (&v)[16], const DivK& kd) {
+    uint32_t c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        c[i] = SFP33 ? encode_relu<SLFP_FMT_SFP33>(div_k_fused(v[i], kd)) : encode_relu<SLFP_FMT_SLFP34_ACT>(div_k_fused(v[i], kd));
+    uint32_t pk[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        pk[g] = __byte_perm(__byte_perm(c[4 * g], c[4 * g + 1], 0x0040), __byte_perm(c[4 * g + 2], c[4 * g + 3], 0x0040), 0x5410);
+    return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 __device__ __forceinline__ void pair_exchange(const uint4& A, const uint4& B, bool odd, uint4& first, uint4& second) {
     uint4 send, recv;
     send.x = odd ? A.x : B.x; send.y = odd ? A.y : B.y; send.z = odd ? A.z : B.z; send.w = odd ? A.w : B.w;
@@ -401,6 +434,10 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
                         v[2 * i] += f.x; v[2 * i + 1] += f.y;
                     }
                 }
+                if (p.epi.layerout) {                            // conv -> BN -> quantize_layerout -> ReLU
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = layerout_relu(v[i]);
+                }
                 if (y16 != nullptr) {
                     uint32_t hw[8];
 #pragma unroll
@@ -416,12 +453,8 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     if ((pass ? yc2 : yc1) == nullptr) continue;
-                    const float sc = pass ? sc2 : sc1;
-                    int32_t t[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i] * sc));
-                    const uint4 pk = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
-                                                ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+                    const uint4 pk = p.epi.layerout ? encode16_exact<SFP33>(v, pass ? p.next_div2 : p.next_div)
+                                                    : encode16_fast<SFP33>(v, pass ? sc2 : sc1);
                     if (pass) pk2[o / 16] = pk; else pk1[o / 16] = pk;
                 }
             }
@@ -517,6 +550,10 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
                 }
                 ra = na; rb = nb4;
             }
+            if (p.epi.layerout) {                                // conv -> BN -> quantize_layerout -> ReLU
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = layerout_relu(v[i]);
+            }
             if (y16 != nullptr) {
                 uint32_t hw[8];
 #pragma unroll
@@ -533,12 +570,8 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 if ((pass ? yc2 : yc1) == nullptr) continue;
-                const float sc = pass ? sc2 : sc1;
-                int32_t t[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i] * sc));
-                const uint4 pk = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
-                                            ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+                const uint4 pk = p.epi.layerout ? encode16_exact<SFP33>(v, pass ? p.next_div2 : p.next_div)
+                                                : encode16_fast<SFP33>(v, pass ? sc2 : sc1);
                 if (pass) pk2 = pk; else pk1 = pk;
             }
         }
@@ -639,6 +672,14 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+
+    // Programmatic dependent launch: everything above (decode table, barriers, tensor-memory allocation, tensor-map
+    // prefetch) touches no global memory written by an earlier kernel, so with the launch attribute set (launch()) it
+    // runs while the PREVIOUS kernel of the stream drains its last tiles; from here on we read its output.  Our own
+    // dependents may be scheduled as soon as SMs free up (they block at the same point until this grid has completed
+    // and flushed).  Without the launch attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int my_tiles = ((int)blockIdx.x < p.num_tiles)
                              ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -893,7 +934,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int half = (warp - kEpiWarp0) >> 2;
         const int etid = (warp - kEpiWarp0) * 32 + lane;
         const int mode = p.epi_mode;
-        const bool sfp33 = p.epi.next_fmt == SLFP_FMT_SFP33_RELU;
+        const bool sfp33 = p.epi.next_fmt == SLFP_FMT_SFP33_RELU || (p.epi.layerout && p.epi.next_fmt == SLFP_FMT_SFP33);
         const uint32_t s_mul = ptx::smem_u32(s_par), s_add = s_mul + BLOCK_N * 4;
         int staged_n0 = -1;
         PROF_VARS;
@@ -1005,6 +1046,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                                 const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
                                 v[2 * i] += f.x; v[2 * i + 1] += f.y;
                             }
+                        }
+                        if (p.epi.layerout) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = layerout_relu(v[i]);
                         }
                     }
                     if (ch == 0) {
@@ -1127,7 +1172,26 @@ static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMa
         attr_done = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, tx2, om, p);
+    static const bool no_pdl = getenv("SLFP_NO_PDL") != nullptr;
+    if (no_pdl) {
+        kern<<<grid, kThreads, C::kSmemBytes, st>>>(tx, tw, tx2, om, p);
+        return check_launch("conv_igemm_v2_kernel");
+    }
+    // programmatic stream serialization: this kernel's prologue may overlap the tail of the previous kernel in the
+    // stream (it waits with griddepcontrol.wait before its first dependent access); also captured into CUDA graphs
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tx, tw, tx2, om, p);
+    if (le != cudaSuccess) return set_error((int)le, "conv_igemm_v2_kernel: %s", cudaGetErrorString(le));
     return check_launch("conv_igemm_v2_kernel");
 }
 
@@ -1163,7 +1227,8 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
                              const void* w_f16, const SlfpEpilogue* epi, cudaStream_t st) {
     using namespace v2;
     const bool fast = epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU;
-    if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_RELU && d->fmt != SLFP_FMT_SFP33_RELU)
+    if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_RELU && d->fmt != SLFP_FMT_SFP33_RELU &&
+        d->fmt != SLFP_FMT_SFP33_SFAST)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: activation code format %d", d->fmt);
     if (epi->y_codes && (epi->k_phys_out % 16 != 0 || epi->k_phys_out < d->k))
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: k_phys_out=%d", epi->k_phys_out);
@@ -1215,15 +1280,17 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     p.epi_mode = 0;
     {
         static const bool no_fast = getenv("SLFP_EPI_GENERIC") != nullptr;
-        const bool common = !no_fast && epi->ch_mul && epi->ch_add && epi->relu && d->k % 16 == 0 && !epi->y_f32 &&
-                            (!epi->y_codes || (fast && epi->k_phys_out == d->k && epi->next_k_div > 0.f)) &&
+        // layerout: the fast epilogues implement relu(quantize_layerout(y)) with exact 0 -> 0 (layerout == 2); the reference's
+        // NaN at exact 0 (layerout == 1) stays with the generic epilogue
+        const bool common = !no_fast && epi->layerout != 1 && epi->ch_mul && epi->ch_add && epi->relu && d->k % 16 == 0 && !epi->y_f32 &&
+                            (!epi->y_codes || ((fast != (epi->layerout != 0)) && epi->k_phys_out == d->k && epi->next_k_div > 0.f)) &&
                             (!epi->y_codes2 || (epi->y_codes && epi->next_k_div2 > 0.f)) &&
                             (!epi->residual || epi->residual_f16);
-        if (common) p.epi_mode = (epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->residual) ? 1 : 2;
+        if (common) p.epi_mode = (epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->residual && !epi->layerout) ? 1 : 2;
     }
     // Staged (TMA) epilogue for the epilogue-bound mode-2 layers (block tails, short-K fused tails): 128-column tiles.
     static const int stg_max_kb = getenv("SLFP_STG_MAXKB") ? atoi(getenv("SLFP_STG_MAXKB")) : 8;
-    const bool stg = p.epi_mode == 2 && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
+    const bool stg = p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
                      (((uintptr_t)epi->residual) & 15u) == 0;
     const int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);

@@ -470,6 +470,141 @@ __global__ void __launch_bounds__(256) quantize_nchw_s2d_kernel(const float* __r
     }
 }
 
+// n / d == umulhi(n, mg) >> sh for n < 2^31 (d > 1): magic-number division by a run-time constant
+static void magic_u32(uint32_t d, uint32_t& mg, uint32_t& sh) {
+    mg = 0; sh = 0;
+    if (d > 1) {
+        uint32_t lg = 31 - __builtin_clz(d);
+        if (d & (d - 1)) ++lg;
+        const uint32_t p = 31 + lg;
+        mg = (uint32_t)(((1ull << p) + d - 1) / d);
+        sh = p - 32;
+    }
+}
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t d, uint32_t mg, uint32_t sh) {
+    return d == 1 ? n : (__umulhi(n, mg) >> sh);
+}
+
+// The stem case of the above (RGB image, c_phys = 16, w % 4 == 0, 16-byte aligned rows), HBM-bound form: a thread owns
+// TWO horizontally adjacent folded pixels = one float4 per (channel, dy) image row piece (six independent 16-byte
+// streaming loads in flight, 512 contiguous bytes per warp and load) and writes their 2 x 16 bytes of codes side by
+// side; 32-bit index arithmetic with magic-number division (the generic kernel's three 64-bit divisions per pixel made
+// it issue-bound at 0.34-0.46 of the HBM peak), table encoder with ONE group probe per thread for the rare general path.
+template <int FL>
+__global__ void __launch_bounds__(256) quantize_nchw_s2d_c3_kernel(const float* __restrict__ x, uint32_t total_pairs, int H, int W,
+                                                                   uint32_t Wp, uint32_t mg_wp, uint32_t sh_wp, uint32_t H2,
+                                                                   uint32_t mg_h2, uint32_t sh_h2, DivK k_div,
+                                                                   uint8_t* __restrict__ codes) {
+    __shared__ uint8_t s_enc[kEncLutBytes];
+    for (int i = threadIdx.x; i < kEncLutBytes; i += 256) s_enc[i] = (uint8_t)enc_lut_entry<FL>((uint32_t)i);
+    __syncthreads();
+    const size_t plane = (size_t)H * W;
+    for (uint32_t j = blockIdx.x * 256u + threadIdx.x; j < total_pairs; j += gridDim.x * 256u) {
+        const uint32_t row = div_magic(j, Wp, mg_wp, sh_wp), px = j - row * Wp;     // row = n * H2 + y2
+        const uint32_t n = div_magic(row, H2, mg_h2, sh_h2), y2 = row - n * H2;
+        const float* src = x + (size_t)n * 3 * plane + (size_t)(2 * y2) * W + 4 * px;
+        float4 v[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) v[c][dy] = ldg_stream(reinterpret_cast<const float4*>(src + c * plane + dy * W));
+        // element e of pixel p: channel ch = (dy * 2 + dx) * 3 + c  <-  v[c][dy].{x,y | z,w}[dx]
+        float xs[2][12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                xs[0][(dy * 2 + 0) * 3 + c] = v[c][dy].x; xs[0][(dy * 2 + 1) * 3 + c] = v[c][dy].y;
+                xs[1][(dy * 2 + 0) * 3 + c] = v[c][dy].z; xs[1][(dy * 2 + 1) * 3 + c] = v[c][dy].w;
+            }
+        float qv[2][12];
+        float nan_probe = 0.0f;
+        uint32_t xmin = 0xffffffffu;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                qv[p][e] = div_k_fused(xs[p][e], k_div);
+                nan_probe = fmaf(qv[p][e], 0.0f, nan_probe);
+                const uint32_t ax1 = __funnelshift_l(__float_as_uint(xs[p][e]), __float_as_uint(xs[p][e]), 1) - 1u;
+                xmin = ax1 < xmin ? ax1 : xmin;
+            }
+        const bool general = !k_div.fast || nan_probe != nan_probe || xmin < 0x08000000u - 1u;
+        uint32_t w[2][4];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            uint32_t c8[12];
+            if (!general) {
+#pragma unroll
+                for (int e = 0; e < 12; ++e)
+                    c8[e] = (uint32_t)s_enc[enc_lut_index<FL>(qv[p][e], xs[p][e])] | ((__float_as_uint(qv[p][e]) >> 24) & 0x80u);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 12; ++e) c8[e] = encode<FL>(div_k(xs[p][e], k_div));
+            }
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+                w[p][g] = __byte_perm(__byte_perm(c8[4 * g], c8[4 * g + 1], 0x0040), __byte_perm(c8[4 * g + 2], c8[4 * g + 3], 0x0040), 0x5410);
+            w[p][3] = 0u;                                        // pad channels 12..15: code 0 = exact zero
+        }
+        uint4* dst = reinterpret_cast<uint4*>(codes + (size_t)j * 32);
+        dst[0] = make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]);
+        dst[1] = make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]);
+    }
+}
+
+// ---- gather + quantize (split / cat / channel_shuffle as an index map) -------------------------------------------
+// thread = (four consecutive output channels, a lane of pixels): its four table entries (source pointer, pixel
+// stride, channel) stay in registers while it walks down the pixels of its CTA, so the inner loop is four 2-byte
+// gathers (consecutive channels of a run come from consecutive addresses of one source tensor: a warp's loads fall into
+// a few 128-byte lines), the table encoder and one 32-bit store per pixel; a warp's stores cover 128 contiguous bytes.
+// Pad channels (>= c) get code 0.  c_phys <= 1024.
+constexpr int kGatherPix = 64;                                   // pixels per thread
+template <int FMT>
+__global__ void __launch_bounds__(256) gather_quantize_kernel(const SlfpGatherChan* __restrict__ table, size_t npix, int C, int Cp,
+                                                              DivK k_div, uint8_t* __restrict__ codes) {
+    constexpr bool kLut = FMT == SLFP_FMT_SFP33 || FMT == SLFP_FMT_SLFP34_ACT;
+    constexpr int FL = FMT == SLFP_FMT_SFP33 ? SLFP_FMT_SFP33 : SLFP_FMT_SLFP34_ACT;
+    __shared__ uint8_t s_enc[kLut ? kEncLutBytes : 16];
+    if (kLut) {
+        for (int i = threadIdx.x; i < kEncLutBytes; i += 256) s_enc[i] = (uint8_t)enc_lut_entry<FL>((uint32_t)i);
+        __syncthreads();
+    }
+    const int cq = Cp >> 2, lanes = 256 / cq;                     // channel quads per pixel; pixels a CTA handles at once
+    const int q = (int)threadIdx.x % cq, pl = (int)threadIdx.x / cq;
+    if (pl >= lanes) return;                                      // c_phys / 4 does not divide 256: the last threads idle
+    const __half* src[4];
+    size_t stride[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = q * 4 + j;
+        src[j] = nullptr; stride[j] = 0;
+        if (c < C) {
+            const SlfpGatherChan t = table[c];
+            src[j] = reinterpret_cast<const __half*>(t.src) + t.ch;
+            stride[j] = (size_t)t.stride;
+        }
+    }
+    const size_t per_cta = (size_t)lanes * kGatherPix;
+    for (size_t base = (size_t)blockIdx.x * per_cta; base < npix; base += (size_t)gridDim.x * per_cta) {
+#pragma unroll 4
+        for (int i = 0; i < kGatherPix; ++i) {
+            const size_t pix = base + (size_t)i * lanes + pl;
+            if (pix >= npix) break;
+            uint32_t word = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (src[j] != nullptr) {
+                    const float v = __half2float(src[j][pix * stride[j]]);
+                    const uint32_t code = kLut ? encode_elem_lut<FL>(v, k_div, s_enc) : encode<FMT>(div_k(v, k_div));
+                    word |= code << (8 * j);
+                }
+            }
+            *reinterpret_cast<uint32_t*>(codes + pix * (size_t)Cp + q * 4) = word;
+        }
+    }
+}
+
 // ---- de-quantize ------------------------------------------------------------------------------
 template <bool SFP33>
 __global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t* __restrict__ codes, size_t n,
@@ -553,20 +688,6 @@ __device__ __forceinline__ void wprep_tables_init(WPrepTables& t, const uint32_t
         t.bucket[threadIdx.x] = make_uint2(cnt, thr);
     }
     t.dec[threadIdx.x] = decode<FMT == SLFP_FMT_SFP33>(threadIdx.x, s_tab);      // 256 threads
-}
-
-static void magic_u32(uint32_t d, uint32_t& mg, uint32_t& sh) {
-    mg = 0; sh = 0;
-    if (d > 1) {
-        uint32_t lg = 31 - __builtin_clz(d);
-        if (d & (d - 1)) ++lg;
-        const uint32_t p = 31 + lg;
-        mg = (uint32_t)(((1ull << p) + d - 1) / d);
-        sh = p - 32;
-    }
-}
-__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t d, uint32_t mg, uint32_t sh) {
-    return d == 1 ? n : (__umulhi(n, mg) >> sh);
 }
 
 template <int FMT>
@@ -826,12 +947,52 @@ extern "C" int slfp_quantize_nchw_s2d_f32(const float* x, int n, int c, int h, i
     const int grid = (int)min((size_t)num_sms() * 16, ceil_div_sz(total, 256));
     cudaStream_t st = (cudaStream_t)stream;
     const DivK dk = make_divk(k_div);
+    if (c == 3 && c_phys == 16 && (w & 3) == 0 && (((uintptr_t)x) & 15u) == 0 && total / 2 < (1ull << 31) &&
+        (fmt == SLFP_FMT_SFP33 || fmt == SLFP_FMT_SLFP34_ACT) && getenv("SLFP_S2D_GENERIC") == nullptr) {
+        const uint32_t pairs = (uint32_t)(total / 2), Wp = (uint32_t)(w / 4), H2 = (uint32_t)(h / 2);
+        uint32_t mg_wp, sh_wp, mg_h2, sh_h2;
+        magic_u32(Wp, mg_wp, sh_wp);
+        magic_u32(H2, mg_h2, sh_h2);
+        static int per_sm[2] = {0, 0};
+        const int fi = fmt == SLFP_FMT_SFP33 ? 0 : 1;
+        if (!per_sm[fi]) {
+            int b = 0;
+            cudaError_t oe = fi == 0
+                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, quantize_nchw_s2d_c3_kernel<SLFP_FMT_SFP33>, 256, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, quantize_nchw_s2d_c3_kernel<SLFP_FMT_SLFP34_ACT>, 256, 0);
+            if (oe != cudaSuccess) { cudaGetLastError(); b = 0; }
+            per_sm[fi] = b > 0 ? b : 4;
+        }
+        const int g3 = (int)min((size_t)num_sms() * per_sm[fi], ceil_div_sz(pairs, 256));      // one resident wave
+        if (fi == 0)
+            quantize_nchw_s2d_c3_kernel<SLFP_FMT_SFP33><<<g3, 256, 0, st>>>(x, pairs, h, w, Wp, mg_wp, sh_wp, H2, mg_h2, sh_h2, dk, codes);
+        else
+            quantize_nchw_s2d_c3_kernel<SLFP_FMT_SLFP34_ACT><<<g3, 256, 0, st>>>(x, pairs, h, w, Wp, mg_wp, sh_wp, H2, mg_h2, sh_h2, dk, codes);
+        return check_launch("quantize_nchw_s2d_c3_kernel");
+    }
     switch (fmt) {
         case SLFP_FMT_SFP33: quantize_nchw_s2d_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(x, n, c, h, w, c_phys, dk, codes); break;
         case SLFP_FMT_SLFP34_ACT: quantize_nchw_s2d_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(x, n, c, h, w, c_phys, dk, codes); break;
         default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_s2d_f32: format %d", fmt);
     }
     return check_launch("quantize_nchw_s2d_kernel");
+}
+
+extern "C" int slfp_gather_quantize_f16(const SlfpGatherChan* table, size_t npix, int c, int c_phys, float k_div, int fmt,
+                                        uint8_t* codes, slfp_stream_t stream) {
+    if (npix == 0) return 0;
+    if (!table || !codes || c <= 0 || c_phys < c || (c_phys & 3) || ((uintptr_t)codes & 3u) || c_phys > 1024)
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_gather_quantize_f16: bad arguments (c <= c_phys <= 1024, c_phys %% 4 == 0; codes 4-byte aligned)");
+    const size_t per_cta = (size_t)(256 / (c_phys / 4)) * kGatherPix;
+    const int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(npix, per_cta));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DivK dk = make_divk(k_div);
+    switch (fmt) {
+        case SLFP_FMT_SFP33: gather_quantize_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(table, npix, c, c_phys, dk, codes); break;
+        case SLFP_FMT_SLFP34_ACT: gather_quantize_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(table, npix, c, c_phys, dk, codes); break;
+        default: return set_error(SLFP_ERR_BAD_ARG, "slfp_gather_quantize_f16: format %d", fmt);
+    }
+    return check_launch("gather_quantize_kernel");
 }
 
 extern "C" int slfp_dequantize(const uint8_t* codes, size_t n, int fmt, float* out, slfp_stream_t stream) {

@@ -485,12 +485,29 @@ __host__ __device__ __forceinline__ float decode_relu(uint32_t code, const uint3
     return u2f(r > top ? top : r);
 }
 
-// value of an activation code in any of the four code formats a dense conv accepts
+// relu(quantize_layerout(y)) for the fused fast epilogues (conv -> BN -> layerout_quantize_func -> ReLU,
+// nets_cifar/shufflenet_v2.py:64-72): round-half-even to 4 mantissa bits, clamp at 248, negative -> 0.  The fast paths
+// map an exact 0 to 0 (the reference's XOR typo yields NaN there; the generic epilogue reproduces that when asked).
+__host__ __device__ __forceinline__ float layerout_relu(float y) {
+    // Veltkamp split at 2^19 + 1: hi = y rounded half-even to 5 significant bits (the same three FMA-pipe operations the
+    // table encoder uses, enc_lut_index); the library is compiled with -fmad=false, so nothing here is contracted.
+    // Bit-exact with relu(layerout_quantize(y, true)) for every normal float (tests/test_host_compiled_kernels.py).
+    const float t0 = fminf(fmaxf(y, 0.0f), 512.0f);
+    const float t = t0 * 524289.0f;
+    const float d = t - t0;
+    return fminf(t - d, 248.0f);
+}
+
+// value of an activation code in any of the code formats a dense conv accepts
 __host__ __device__ __forceinline__ float decode_act_any(uint32_t code, int fmt, const uint32_t* __restrict__ tab) {
     switch (fmt) {
         case SLFP_FMT_SFP33: return decode<true>(code, tab);
         case SLFP_FMT_SLFP34_RELU: return decode_relu<false>(code, tab);
         case SLFP_FMT_SFP33_RELU: return decode_relu<true>(code, tab);
+        case SLFP_FMT_SFP33_SFAST: {
+            const float m = decode_relu<true>(code & 0x7fu, tab);
+            return (code & 0x80u) ? -m : m;
+        }
         default: return decode<false>(code, tab);
     }
 }

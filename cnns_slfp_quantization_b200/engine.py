@@ -34,11 +34,12 @@ def _k32(K):
 
 class _T:
     """A device tensor of the plan: NHWC, kind in {'codes', 'f16', 'f32'}."""
-    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt")
+    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt", "c_logical")
 
     def __init__(self, buf, n, h, w, c, cp, kind, kdiv=None, fmt=None):
         self.buf, self.n, self.h, self.w, self.c, self.cp, self.kind, self.kdiv = buf, n, h, w, c, cp, kind, kdiv
         self.fmt = fmt                  # code format of a 'codes' tensor (signed quantizer codes or post-ReLU codes)
+        self.c_logical = c              # float16 outputs of a pad_k layer: c is the physical channel count
 
 
 def _ceil(v, m):
@@ -151,8 +152,17 @@ class Plan:
                                    t.buf.data_ptr()))
         return t
 
+    @staticmethod
+    def _cp(k):
+        """Physical channel count of a code tensor with k logical channels: k itself when it is a multiple of 16, else
+        padded to 16 (small) or to 64 (so that the consumer's TMA path moves whole 64-byte rows: ShuffleNetV2's 58 /
+        116 / 232 channels)."""
+        if k % 16 == 0:
+            return k
+        return _ceil(k, 16) if k < 48 else _ceil(k, 64)
+
     def conv(self, x, mod, bn=None, relu=False, residual=None, codes=(), f16=False, f32=False, linear=False,
-             relu_codes=True):
+             relu_codes=True, layerout=0, pad_k=False, signed_fast=False):
         """One fused convolution / linear layer.  `codes`: divisors (Ka of the consumers) to quantize-on-store
         with (at most two distinct).  Returns {'codes': {kdiv: _T}, 'f16': _T | None, 'f32': _T | None}.
         relu_codes: the consumers are dense layers / max-pools (which read the unsigned post-ReLU code format,
@@ -173,40 +183,66 @@ class Plan:
         assert abs(ka - x.kdiv) == 0.0, "input codes were quantized with a different Ka"
         self.taps.append((mod, x, len(self.ops)))       # (module, input codes, index of this layer's op in self.ops)
         pex = getattr(mod, "pad_extra", (0, 0))          # bottom/right minus top/left padding (space-to-depth stem)
-        d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
+        dense = groups == 1
+        # pad_k: present a dense layer whose output-channel count is not a multiple of 16 (ShuffleNetV2: 24 / 58 / 116 /
+        # 232) to the kernel with K rounded up - weight rows and affine entries of the pad channels are zero, so they
+        # produce exact zeros (code 0 / 0.0) - which makes it eligible for the vectorised fast epilogues.
+        Kk = self._cp(K) if (pad_k and dense and K % 16 != 0) else K
+        d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, Kk, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
                             x.fmt, pex[0], pex[1])
+        dw_ = d if Kk == K else nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0],
+                                                 dil[1], groups, x.fmt, pex[0], pex[1])       # the weight job writes K rows
         Ho = (x.h + 2 * pad[0] + pex[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
         Wo = (x.w + 2 * pad[1] + pex[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
         pitch = self.lib.slfp_conv_wpitch(ctypes.byref(d))
-        dense = groups == 1
-        wbuf = torch.empty((K * pitch,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
+        wbuf = torch.zeros((Kk * pitch,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
         # weight re-quantization: one table entry; Plan.prepare_weights() runs the whole table in ONE launch
-        self._weight_job(d, wview, kw, wbuf, dense)
+        self._weight_job(dw_, wview, kw, wbuf, dense)
         epi = nv.SlfpEpilogue()
         # Fold bias, post-scale and eval BatchNorm into one per-channel affine y = acc * mul + add
         # (float64, rounded once): mul = Ka*Kw*bn_scale, add = bias_q*Ka*Kw*bn_scale + bn_shift.
         pa, pb = ((kw, ka) if linear else (ka, kw))
         mul, add = self._affine(mod, bn, K, linear)
-        mul32, add32 = mul.float().contiguous(), add.float().contiguous()
+        mul32, add32 = torch.zeros(Kk, dtype=torch.float32, device=self.dev), torch.zeros(Kk, dtype=torch.float32, device=self.dev)
+        mul32[:K], add32[:K] = mul.float(), add.float()
         self.keep += [mul32, add32]
         epi.ch_mul, epi.ch_add = mul32.data_ptr(), add32.data_ptr()
         epi.post_a, epi.post_b = pa, pb
         if residual is not None:
-            assert residual.kind in ("f16", "f32") and (residual.n, residual.h, residual.w, residual.c) == (x.n, Ho, Wo, K)
+            assert residual.kind in ("f16", "f32") and (residual.n, residual.h, residual.w, residual.c) == (x.n, Ho, Wo, Kk)
             epi.residual, epi.residual_f16 = residual.buf.data_ptr(), 1 if residual.kind == "f16" else 0
         epi.relu = 1 if relu else 0
+        epi.layerout = layerout            # conv -> BN -> layerout_quantize_func -> ReLU (0 = none, 1 = NaN at 0, 2 = 0 stays 0)
+        if layerout:
+            # codes after quantize_layerout are written with the EXACT encoder in the signed formats: 5-bit layer-out values
+            # over a scale that is max / 15.5 of such values sit exactly on rounding ties of the next grid, where the fast
+            # post-ReLU formats (ties up) would differ from the reference (ties to even) on a visible share of elements
+            relu_codes = False
         out = {"codes": {}, "f16": None, "f32": None}
         kds = []
         for kd in codes:
             if kd not in kds:
                 kds.append(kd)
         assert len(kds) <= 2
-        kp = _ceil(K, 16)
+        kp = self._cp(K)
         # post-ReLU codes: dense producer (the tcgen05 kernel with the TMA-im2col gather) ending in a ReLU
         depthwise = groups > 1 and groups == C == K
-        fast_dw = depthwise and relu and bn is not None and len(kds) == 1 and not f16 and not f32 and residual is None \
-            and x.cp % 16 == 0 and mod.bias is None
-        ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and x.cp % 16 == 0 and (groups == 1 or fast_dw)) else self.afmt
+        fused_dw = depthwise and bn is not None and len(kds) == 1 and not f16 and not f32 and residual is None \
+            and x.cp % 16 == 0 and mod.bias is None and not layerout
+        fast_dw = fused_dw and relu
+        # depthwise conv -> BN -> (no ReLU) -> next quantizer: sign bit + 7-bit magnitude code (SFP<3,3> only)
+        sfast_dw = fused_dw and not relu and signed_fast and self.afmt == nv.FMT_SFP33 and kp == x.cp
+        # 3x3 RGB stems (c_phys = 4) run the CUDA-core direct kernel, which writes the fused pipeline's fast code formats
+        stem_direct = (dense and x.cp == 4 and (R, S) == (3, 3) and tuple(dil) == (1, 1) and K in (24, 32, 64) and bn is not None
+                       and not f16 and not f32 and residual is None and not layerout and stride[0] == stride[1] and pad[0] == pad[1])
+        if sfast_dw:
+            ofmt = nv.FMT_SFP33_SFAST
+        elif stem_direct and relu and relu_codes:
+            ofmt = nv.relu_fmt(self.afmt)
+        elif stem_direct and not relu and signed_fast and self.afmt == nv.FMT_SFP33:
+            ofmt = nv.FMT_SFP33_SFAST
+        else:
+            ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and x.cp % 16 == 0 and (groups == 1 or fast_dw)) else self.afmt
         for i, kd in enumerate(kds):
             t = self._alloc(x.n, Ho, Wo, K, "codes", kd, cp=kp, fmt=ofmt)
             out["codes"][kd] = t
@@ -215,11 +251,13 @@ class Plan:
             else:
                 epi.y_codes2, epi.next_k_div2 = t.buf.data_ptr(), kd
         epi.next_fmt, epi.k_phys_out = ofmt, kp
+        assert Kk == K or not kds or kp == Kk
         if f16:
-            out["f16"] = self._alloc(x.n, Ho, Wo, K, "f16")
+            out["f16"] = self._alloc(x.n, Ho, Wo, Kk, "f16")      # physical channels (pad channels hold 0.0)
+            out["f16"].c_logical = K
             epi.y_f16 = out["f16"].buf.data_ptr()
         if f32:
-            out["f32"] = self._alloc(x.n, Ho, Wo, K, "f32")
+            out["f32"] = self._alloc(x.n, Ho, Wo, Kk, "f32")
             epi.y_f32 = out["f32"].buf.data_ptr()
         self.keep += [d, epi, wbuf]
         self.ops.append(self._call(self.lib.slfp_conv2d_fwd, ctypes.byref(d), x.buf.data_ptr(), wbuf.data_ptr(),
@@ -314,6 +352,24 @@ class Plan:
         by = x1.buf.numel() + x2.buf.numel() + wbuf.numel() * 2 + sum(t.buf.numel() for t in out["codes"].values()) + \
             (out["f16"].buf.numel() * 2 if out["f16"] is not None else 0)
         self.conv_flops.append((fl, True, f"{C1}+{C2}->{K} 1x1 dual @{x1.h}", by))
+        return out
+
+    def gather_quantize(self, chans, kdiv):
+        """Codes of a LOGICAL tensor given as a channel list [(float16 _T, channel), ...]: the consumer-side form of
+        torch.split / torch.cat / channel_shuffle (nets_cifar/shufflenet_v2.py:20-45, 100-115) - no data is moved for the
+        shuffle itself, the activation quantizer reads each logical channel from wherever it lives."""
+        t0 = chans[0][0]
+        assert all(t.kind == "f16" and (t.n, t.h, t.w) == (t0.n, t0.h, t0.w) for t, _ in chans)
+        c = len(chans)
+        out = self._alloc(t0.n, t0.h, t0.w, c, "codes", kdiv, cp=self._cp(c))
+        tab = (nv.SlfpGatherChan * c)()
+        for e, (t, ch) in zip(tab, chans):
+            assert 0 <= ch < t.c_logical
+            e.src, e.stride, e.ch = t.buf.data_ptr(), t.c, ch
+        dtab = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(self.dev)
+        self.keep.append(dtab)
+        self.ops.append(self._call(self.lib.slfp_gather_quantize_f16, dtab.data_ptr(), t0.n * t0.h * t0.w, c, out.cp, kdiv,
+                                   self.afmt, out.buf.data_ptr()))
         return out
 
     def maxpool(self, x, k, stride, pad):
@@ -525,4 +581,80 @@ def compile_mobilenetv1(model, batch, size, device="cuda", static_weights=False)
         P.keep.append(out)
         P.torch_op(lambda: torch.addmm(model.fc.bias, feat, model.fc.weight.t(), out=out))
         P.output = out
+    return P
+
+
+def compile_shufflenetv2(model, batch, size, device="cuda", static_weights=False, nan_at_zero=False):
+    """nets_cifar.ShuffleNetV2 -> Plan (BASELINE config 5's second net; reference nets_cifar/shufflenet_v2.py:47-252).
+
+    A ShuffleUnit is  out = channel_shuffle(cat(shortcut(x1), residual(x2)), 2)  with (x1, x2) = split(x) in a basic
+    unit and x1 = x2 = x in a down-sampling unit.  Here split / cat / shuffle never move data: a unit's output is kept as
+    a LOGICAL channel list [(float16 tensor, channel)] - the pass-through half keeps pointing at the tensors that hold
+    its values (float16 is an exact carrier for post-layerout, post-ReLU SFP<4,4> values), the branch output is one new
+    float16 tensor - and the next consumer's activation quantizer gathers its input channels through that list
+    (Plan.gather_quantize).  Inside a branch the layers exchange 8-bit codes:
+        1x1 conv -> BN -> layerout -> ReLU -> [quantize]  ->  dw 3x3 -> BN -> [quantize]  ->  1x1 conv -> BN -> layerout -> ReLU
+    with BN, quantize_layerout (SFP<4,4>), ReLU and the next layer's quantizer in the producing conv's epilogue.
+    Output-channel counts that are not multiples of 16 (24 / 58 / 116 / 232) are padded for the kernels (zero weight
+    rows), the depthwise layers - which have no ReLU - write the signed fast code format.
+    nan_at_zero: the reference's quantize_layerout returns NaN for an exact 0 (its `2^(-8)` is an XOR,
+    utils/sfp_quant.py:122-123); the fast epilogues map 0 to 0.  True selects the generic, bug-compatible epilogues
+    (several times slower); the module-level drop-in is always bug-compatible."""
+    assert not model.training
+    from .utils import sfp_quant
+    lo = 1 if (nan_at_zero and not getattr(sfp_quant, "LAYEROUT_ZERO_IS_ZERO", False)) else 2
+    fast = lo == 2
+    pre_conv, pre_bn = model.pre[0], model.pre[1]
+    P = Plan(batch, device, pre_conv.q_bit, static_weights)
+    x = P.input_nchw(3, size, size)
+    units = [u for si in (2, 3, 4) for u in getattr(model, f"stage{si}")]
+
+    def is_down(u):
+        return len(u.shortcut) > 0
+
+    def residual_branch(xc, mods):
+        c0, b0, dw, b1, c2, b2 = mods[0], mods[1], mods[4], mods[5], mods[6], mods[7]
+        k1, k2 = _k32(dw.Ka), _k32(c2.Ka)
+        t = P.conv(xc, c0, bn=b0, relu=True, layerout=lo, codes=[k1], pad_k=fast)["codes"][k1]
+        t = P.conv(t, dw, bn=b1, relu=False, codes=[k2], relu_codes=False, signed_fast=fast)["codes"][k2]
+        return P.conv(t, c2, bn=b2, relu=True, layerout=lo, f16=True, pad_k=fast)["f16"]
+
+    def shortcut_branch(xc, mods):
+        dw, b0, c1, b1 = mods[0], mods[1], mods[2], mods[3]
+        k1 = _k32(c1.Ka)
+        t = P.conv(xc, dw, bn=b0, relu=False, codes=[k1], relu_codes=False, signed_fast=fast)["codes"][k1]
+        return P.conv(t, c1, bn=b1, relu=True, layerout=lo, f16=True, pad_k=fast)["f16"]
+
+    # stem: conv -> BN (no ReLU, no layerout); its output is consumed only by the first unit's two quantizers
+    first = units[0]
+    assert is_down(first)
+    kr, ks = _k32(first.residual[0].Ka), _k32(first.shortcut[0].Ka)
+    xc = P.quantize_input(x, _k32(pre_conv.Ka))
+    stem = P.conv(xc, pre_conv, bn=pre_bn, relu=False, codes=[kr, ks], relu_codes=False, signed_fast=fast)
+    direct = stem["codes"]                 # {Ka: code tensor} of the whole stem output
+    chans = None
+    for u in units:
+        if is_down(u):
+            kr, ks = _k32(u.residual[0].Ka), _k32(u.shortcut[0].Ka)
+            if chans is None:
+                xr, xs = direct[kr], direct[ks]
+            else:
+                xr = P.gather_quantize(chans, kr)
+                xs = xr if ks == kr else P.gather_quantize(chans, ks)
+            sc = shortcut_branch(xs, list(u.shortcut))
+            rs = residual_branch(xr, list(u.residual))
+            half = rs.c_logical
+            assert sc.c_logical == half
+            chans = [(sc, j // 2) if j % 2 == 0 else (rs, j // 2) for j in range(2 * half)]
+        else:
+            c = len(chans)
+            x1, x2 = chans[:c // 2], chans[c // 2:]
+            rs = residual_branch(P.gather_quantize(x2, _k32(u.residual[0].Ka)), list(u.residual))
+            assert rs.c_logical == c // 2
+            chans = [x1[j // 2] if j % 2 == 0 else (rs, j // 2) for j in range(c)]
+    c5, b5 = model.conv5[0], model.conv5[1]
+    feat_map = P.conv(P.gather_quantize(chans, _k32(c5.Ka)), c5, bn=b5, relu=True, layerout=lo, f16=True)["f16"]
+    feat = P.avgpool(feat_map)
+    fcq = P.quantize_flat(feat, model.fc.in_features, _k32(model.fc.Ka))
+    P.output = P.conv(fcq, model.fc, f32=True, linear=True)["f32"].buf.view(batch, -1)
     return P

@@ -56,7 +56,11 @@ enum {
     /* Unsigned post-ReLU activation codes exchanged by FUSED layers (quantize-on-store of a conv
      * whose epilogue ends in a ReLU; see "post-ReLU codes" below).  Same grids as SLFP34_ACT / SFP33. */
     SLFP_FMT_SLFP34_RELU = 4,
-    SLFP_FMT_SFP33_RELU = 5
+    SLFP_FMT_SFP33_RELU = 5,
+    /* Signed variant of SFP33_RELU for fused layers WITHOUT a ReLU (ShuffleNetV2's depthwise conv -> BN -> next conv):
+     * bit 7 = sign, low 7 bits = min(c, 127) of the post-ReLU code of |q| (c = 127 and 128 both decode to the top
+     * value 15, so nothing is lost).  SFP<3,3> only - the SLFP<3,4> half-step code needs 9 bits with a sign. */
+    SLFP_FMT_SFP33_SFAST = 6
 };
 
 enum { SLFP_ACT_STL = 0, SLFP_ACT_SWISH = 1, SLFP_ACT_SIGMOID = 2 };
@@ -118,6 +122,19 @@ int slfp_quantize_nchw_f32(const float *x, int n, int c, size_t hw, int c_phys, 
 int slfp_quantize_nchw_s2d_f32(const float *x, int n, int c, int h, int w, int c_phys, float k_div, int fmt,
                                uint8_t *codes, slfp_stream_t stream);
 
+/* Gather + quantize: the activation quantizer fed from SEVERAL float16 NHWC tensors through a per-channel table -
+ * codes[p, j] = encode(float(src_j[p * stride_j + ch_j]) / k_div) for j < c, code 0 for c <= j < c_phys.  This is how
+ * the fused pipeline evaluates torch.split / torch.cat / channel_shuffle (nets_cifar/shufflenet_v2.py:20-45, 100-115)
+ * without moving data: the logical channel order is an index map resolved by the consumer's quantizer.  `table` is a
+ * DEVICE array of c entries. */
+typedef struct {
+    const void *src;     /* float16 NHWC tensor                       */
+    int stride;          /* its channels per pixel (elements)         */
+    int ch;              /* the channel to read                       */
+} SlfpGatherChan;
+int slfp_gather_quantize_f16(const SlfpGatherChan *table, size_t npix, int c, int c_phys, float k_div, int fmt,
+                             uint8_t *codes, slfp_stream_t stream);
+
 /* codes -> float32 (exactly the value the reference's fake-quant tensor would hold) */
 int slfp_dequantize(const uint8_t *codes, size_t n, int fmt, float *out, slfp_stream_t stream);
 
@@ -171,6 +188,11 @@ typedef struct {
      * differs from the unfolded order by float32 rounding only. */
     const float *ch_mul;
     const float *ch_add;
+    /* quantize_layerout (SFP<4,4>, utils/sfp_quant.py:105-127) applied to y after the affine / residual and BEFORE the
+     * ReLU - the reference's conv -> BatchNorm -> layerout_quantize_func -> ReLU chains (nets_cifar/shufflenet_v2.py:
+     * 64-72, MobileNetV1_swish, VGG16_gelu).  0 = off; 1 = the reference's arithmetic including NaN at exact 0 (its
+     * `2^(-8)` is XOR: no low clamp, 0 * NaN); 2 = exact 0 stays 0 (the evidently intended value).  Generic epilogue. */
+    int layerout;
 } SlfpEpilogue;
 
 /* Weight preparation: replaces `self.quantize_weight(self.weight/self.Kw)` (conv2d_func.py:22):

@@ -138,3 +138,29 @@ extern "C" size_t hostcheck_encode_wgt_bucket_mismatches(const float* v, size_t 
     for (size_t i = 0; i < n; ++i) bad += encode_wgt_bucket(v[i], tbl) != encode<SLFP_FMT_SLFP34_WGT>(v[i]);
     return bad;
 }
+
+// layerout_relu (fast epilogues: three FMA-pipe operations) against relu(quantize_layerout(y)) with exact 0 -> 0;
+// returns the mismatch count
+extern "C" size_t hostcheck_layerout_relu_mismatches(const float* y, size_t n) {
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float a = layerout_relu(y[i]);
+        float b = layerout_quantize(y[i], true);
+        b = b > 0.0f ? b : 0.0f;
+        bad += f2u(a) != f2u(b);
+    }
+    return bad;
+}
+
+// signed fast SFP<3,3> codes (SLFP_FMT_SFP33_SFAST; the depthwise kernels' encoder) and their decoded values
+extern "C" void hostcheck_sfast_codes(const float* q, size_t n, uint8_t* codes, float* values) {
+    for (size_t i = 0; i < n; ++i) {
+        float a16 = fabsf(q[i]) * 0.0625f;
+        a16 = a16 > 1.f ? 1.f : a16;
+        int32_t m = encode_relu_fast_raw16<true>(a16);
+        m = m < 0 ? 0 : (m > 127 ? 127 : m);
+        const uint32_t c = (uint32_t)m | ((f2u(q[i]) >> 24) & 0x80u);
+        codes[i] = (uint8_t)c;
+        values[i] = decode_act_any(c, SLFP_FMT_SFP33_SFAST, h_pow2frac);
+    }
+}

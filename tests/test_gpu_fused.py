@@ -362,3 +362,122 @@ def test_plan_is_stable_and_deterministic_over_many_steps():
             assert torch.equal(plan.output, first), f"logits changed at replay {i}"
     torch.cuda.synchronize()
     assert torch.equal(plan.output, first)
+
+
+def _decode_any(orc, codes, fmt):
+    from cnns_slfp_quantization_b200 import _native as nv
+    if fmt in (nv.FMT_SLFP34_RELU, nv.FMT_SFP33_RELU):
+        return orc.decode_relu(codes, fmt == nv.FMT_SFP33_RELU)
+    if fmt == nv.FMT_SFP33_SFAST:
+        m = orc.decode_relu(codes & 0x7f, True)
+        return np.where(codes & 0x80, -m, m).astype(np.float32)
+    return orc.decode(codes, fmt)
+
+
+@pytest.mark.parametrize("K,stride,qbit,relu,two", [(32, 2, 7, True, False), (24, 1, 7, False, True), (64, 1, 8, True, False),
+                                                    (32, 1, 8, True, False), (24, 1, 8, False, True)])
+def test_direct_stem_kernel(orc, K, stride, qbit, relu, two):
+    """3x3 RGB stems through the CUDA-core direct kernel (conv_stem_direct.cu; MobileNetV1 3->32, ShuffleNetV2 3->24,
+    VGG-16 3->64): float32 operands and accumulation, folded affine (+ ReLU), quantize-on-store in the fused code formats
+    (post-ReLU codes, signed fast SFP<3,3>, exact signed codes; one or two consumers) against a float64 convolution of
+    the decoded operands pushed through the reference quantizer."""
+    import torch.nn as nn
+    from cnns_slfp_quantization_b200 import engine, _native as nv
+    from cnns_slfp_quantization_b200.utils import conv2d_func as cf
+    torch.manual_seed(K + stride)
+    dev = torch.device("cuda:0")
+    N, H = 3, 21
+    x = torch.randn(N, 3, H, H, device=dev) * 2
+    ka = float(x.abs().max() / 15.5)
+    conv = cf.conv2d_Q(qbit, 0.02, ka)(3, K, 3, stride=stride, padding=1).to(dev)
+    conv.Kw = torch.tensor(float(conv.weight.detach().abs().max() / 15.5))
+    bn = nn.BatchNorm2d(K).to(dev).eval()
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.5); bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
+    P = engine.Plan(N, dev, qbit)
+    xin = P.input_nchw(3, H, H)
+    xin.copy_(x)
+    xc = P.quantize_input(xin, engine._k32(conv.Ka))
+    assert xc.cp == 4
+    ks = [0.23, 0.31] if two else [0.23]
+    out = P.conv(xc, conv, bn=bn, relu=relu, codes=ks, relu_codes=True, signed_fast=True)
+    P.run()
+    torch.cuda.synchronize()
+    afmt, wfmt = orc.fmt_for(qbit, "act"), orc.fmt_for(qbit, "weight")
+    _, xq = orc.quantize(x.cpu().numpy(), afmt, engine._k32(conv.Ka), want_codes=False)
+    _, wq = orc.quantize(conv.weight.detach().cpu().numpy(), wfmt, engine._k32(conv.Kw), want_codes=False)
+    wq = wq.astype(np.float16).astype(np.float64)                    # the kernel reads the float16 image of weight_q
+    acc = torch.nn.functional.conv2d(torch.from_numpy(xq).double(), torch.from_numpy(wq), None, stride, 1).numpy()
+    mul, add = P._affine(conv, bn, K)
+    y = acc * mul.cpu().numpy()[None, :, None, None] + add.cpu().numpy()[None, :, None, None]
+    if relu:
+        y = np.maximum(y, 0)
+    y = y.transpose(0, 2, 3, 1)
+    for kd in ks:
+        t = out["codes"][kd]
+        if qbit == 7:
+            assert t.fmt == (nv.FMT_SFP33_RELU if relu else nv.FMT_SFP33_SFAST)
+        elif relu:
+            assert t.fmt == nv.FMT_SLFP34_RELU
+        codes = t.buf.cpu().numpy()
+        assert (codes[..., K:] == 0).all()
+        got = _h(_decode_any(orc, codes[..., :K], t.fmt))
+        q = y / float(np.float32(kd))
+        ok = np.zeros(q.shape, bool)
+        for eps in (0.0, -3e-6, 3e-6):
+            _, want = orc.quantize((q * (1.0 + eps)).astype(np.float32), afmt, want_codes=False)
+            ok |= got == _h(want)
+        assert ok.all(), (kd, int((~ok).sum()), ok.size)
+
+
+@pytest.mark.parametrize("C,H,stride", [(58, 14, 1), (24, 20, 2), (116, 9, 1), (232, 6, 2), (116, 28, 1)])
+def test_shufflenet_branch_fast_forms_equal_generic_forms(orc, C, H, stride):
+    """One ShuffleNetV2 residual branch (1x1 -> BN -> layerout -> ReLU -> dw 3x3 -> BN -> 1x1 -> BN -> layerout -> ReLU,
+    58 channels: not a multiple of 16) through the fast forms - output channels padded to 64 for the vectorised
+    epilogues, relu(quantize_layerout(.)) as three FMA-pipe operations, signed fast codes out of the depthwise conv -
+    against the generic exact epilogues: the float16 branch output must agree (identical up to the code-boundary
+    slivers of the two fast encoders)."""
+    import torch.nn as nn
+    from cnns_slfp_quantization_b200 import engine, _native as nv
+    from cnns_slfp_quantization_b200.utils import conv2d_func as cf
+    torch.manual_seed(11)
+    dev = torch.device("cuda:0")
+    N = 2
+    Cs = engine.Plan._cp(C)
+
+    def mk(kind):
+        m = (cf.conv2d_Q(7, 0.05, 0.2)(C, C, 1) if kind == "pw" else cf.conv2d_Q(7, 0.05, 0.2)(C, C, 3, stride=stride, padding=1, groups=C)).to(dev)
+        m.Kw = torch.tensor(float(m.weight.detach().abs().max() / 15.5))
+        return m
+
+    def mkbn():
+        bn = nn.BatchNorm2d(C).to(dev).eval()
+        bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.5); bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
+        return bn
+    c0, dw, c2 = mk("pw"), mk("dw"), mk("pw")
+    b0, b1, b2 = mkbn(), mkbn(), mkbn()
+    src = torch.rand(N, H, H, Cs, device=dev).half() * 3
+    outs = []
+    for fast in (True, False):
+        P = engine.Plan(N, dev, 7)
+        t = engine._T(src, N, H, H, Cs, Cs, "f16")
+        t.c_logical = C
+        xc = P.gather_quantize([(t, (j * 7) % C) for j in range(C)], engine._k32(c0.Ka))
+        lo = 2 if fast else 1
+        kd = engine._k32(0.2)
+        a = P.conv(xc, c0, bn=b0, relu=True, layerout=lo, codes=[kd], pad_k=fast)["codes"][kd]
+        b = P.conv(a, dw, bn=b1, relu=False, codes=[kd], relu_codes=False, signed_fast=fast)["codes"][kd]
+        if fast:
+            assert a.fmt == nv.FMT_SFP33 and b.fmt == nv.FMT_SFP33_SFAST
+        y = P.conv(b, c2, bn=b2, relu=True, layerout=lo, f16=True, pad_k=fast)["f16"]
+        P.run()
+        torch.cuda.synchronize()
+        outs.append((_decode_any(orc, a.buf.cpu().numpy()[..., :C], a.fmt), _decode_any(orc, b.buf.cpu().numpy()[..., :C], b.fmt),
+                     y.buf.float().cpu().numpy()[..., :C]))
+    (af, bf, yf), (ag, bg, yg) = outs
+    assert np.isfinite(yg).all() and np.isfinite(yf).all()
+    assert (_h(af) == _h(ag)).mean() > 0.999                       # same grid values but for boundary slivers (reciprocal, ties)
+    assert (_h(bf) == _h(bg)).mean() > 0.99
+    # layer-out values live on the SFP<4,4> grid: float16 holds them exactly
+    _, lq = orc.quantize(yf, 3, want_codes=False, bugcompat=False)
+    assert (lq == yf).all()
+    assert (yf == yg).mean() > 0.97 and np.abs(yf - yg).max() <= 0.15 * np.abs(yg).max()

@@ -93,8 +93,8 @@ def stats(y, ref):
 
 # logit RMS bounds: ~1.5x the values measured on a B200 with this tree (profiles/r02_parity.md)
 CASES = [("resnet50_224", "resnet50", 8, 0.06), ("vgg16", "vgg16", None, 0.33), ("mobilenetv1_cifar", "mobilenetv1_cifar", None, 0.46),
-         ("mobilenetv1_imgnet", "mobilenetv1_imgnet", None, 0.035), ("shufflenetv2", "shufflenetv2", None, 0.05),
-         ("shufflenetv2_224", "shufflenetv2", None, 0.37)]
+         ("mobilenetv1_imgnet", "mobilenetv1_imgnet", None, 0.035), ("shufflenetv2", "shufflenetv2", None, 0.16),
+         ("shufflenetv2_224", "shufflenetv2", None, 0.63)]
 
 
 @pytest.mark.parametrize("key,net,chunk,rms_bound", CASES)

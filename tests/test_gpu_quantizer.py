@@ -198,3 +198,58 @@ def test_dynamic_max_scaling_quantizer(orc, qbit, kind):
     k2_want = np.float32(np.float64(np.abs(x2).max()) / 15.5)
     assert np.float32(kd.item()) == k2_want
     assert (out.cpu().numpy() == orc.quantize(x2, orc.fmt_for(qbit, kind), float(k2_want))[0]).all()
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_s2d_input_quantizer_fast_path_with_special_values(orc, fmt):
+    """The stem's NCHW -> space-to-depth quantizer (two folded pixels per thread, table encoder, one group probe per
+    thread for the general path): bit-exact codes against the oracle, including threads whose 24 elements contain
+    NaN / Inf / -0 / denormal-range values (they take the general encoder)."""
+    import torch
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    rng = np.random.default_rng(77)
+    N, C, H, W = 3, 3, 16, 24
+    x = (rng.standard_normal((N, C, H, W)) * 3).astype(np.float32)
+    flat = x.reshape(-1)
+    specials = np.array([np.inf, -np.inf, -0.0, 0.0, 1e-40, -1e-40, 3e-38, 1e30, -1e30, 0.0625 * 0.37, 15.32165 * 0.37], np.float32)
+    pos = rng.choice(flat.size, specials.size * 4, replace=False)
+    flat[pos] = np.tile(specials, 4)
+    k = np.float32(0.37)
+    xt = torch.from_numpy(x).cuda()
+    out = torch.empty((N, H // 2, W // 2, 16), dtype=torch.uint8, device="cuda")
+    nv.check(lib.slfp_quantize_nchw_s2d_f32(xt.data_ptr(), N, C, H, W, 16, float(k), fmt, out.data_ptr(), nv.stream()))
+    torch.cuda.synchronize()
+    codes, _ = orc.quantize(x, fmt, float(k))
+    want = np.zeros((N, H // 2, W // 2, 16), np.uint8)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(C):
+                want[..., (dy * 2 + dx) * C + c] = codes[:, c, dy::2, dx::2]
+    assert (out.cpu().numpy() == want).all()
+
+
+def test_gather_quantize_matches_plain_quantizer(orc):
+    """slfp_gather_quantize_f16 (split / cat / channel_shuffle as an index map): codes equal the oracle's quantizer of
+    the gathered float16 values, pad channels are code 0."""
+    import ctypes
+    import torch
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    rng = np.random.default_rng(5)
+    npix = 1000
+    a = torch.from_numpy((rng.standard_normal((npix, 58)) * 3).astype(np.float16)).cuda()
+    b = torch.from_numpy((rng.standard_normal((npix, 24)) * 3).astype(np.float16)).cuda()
+    chans = [(a, j // 2) if j % 2 == 0 else (b, (j // 2) % 24) for j in range(58)]
+    tab = (nv.SlfpGatherChan * 58)()
+    for e, (t, ch) in zip(tab, chans):
+        e.src, e.stride, e.ch = t.data_ptr(), t.shape[1], ch
+    dtab = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).cuda()
+    for fmt in (0, 1):
+        out = torch.full((npix, 64), 9, dtype=torch.uint8, device="cuda")
+        nv.check(lib.slfp_gather_quantize_f16(dtab.data_ptr(), npix, 58, 64, 0.21, fmt, out.data_ptr(), nv.stream()))
+        torch.cuda.synchronize()
+        g = np.stack([(a if t is a else b).cpu().numpy()[:, ch] for t, ch in chans], 1).astype(np.float32)
+        want, _ = orc.quantize(g, fmt, 0.21)
+        got = out.cpu().numpy()
+        assert (got[:, :58] == want).all() and (got[:, 58:] == 0).all()

@@ -164,3 +164,38 @@ def test_weight_bucket_encoder_equals_reference_encoder(hostcheck):
             v = np.ascontiguousarray((x.view(np.uint32) | np.uint32(sgn << 31)).view(np.float32))
             bad = hostcheck.hostcheck_encode_wgt_bucket_mismatches(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size))
             assert bad == 0, (e, sgn, bad)
+
+
+def test_layerout_relu_fast_form_equals_reference_form(hostcheck):
+    """relu(quantize_layerout(y)) as the fused fast epilogues compute it (Veltkamp split, min / max) is bit-exact with the
+    generic routine for every mantissa at a spread of exponents (both signs, the 248 clamp, values around it)."""
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    fn = hostcheck.hostcheck_layerout_relu_mismatches
+    fn.restype = ctypes.c_size_t
+    for e in (-20, -8, -4, -1, 0, 3, 6, 7, 8, 9, 20):
+        for sign in (0, 1):
+            x = (mant | np.uint32((e + 127) << 23) | np.uint32(sign << 31)).view(np.float32)
+            assert fn(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(x.size)) == 0, (e, sign)
+    edge = np.array([0.0, -0.0, 247.9, 248.0, 248.1, 252.0, 1e30, -1e30, 1e-30, np.inf, -np.inf], np.float32)
+    assert fn(edge.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(edge.size)) == 0
+
+
+def test_signed_fast_sfp33_codes(hostcheck):
+    """SLFP_FMT_SFP33_SFAST (sign bit + 7-bit magnitude code, written by the fused depthwise kernels that have no ReLU):
+    value == sign(q) * value of the post-ReLU code of |q| for every mantissa / octave, i.e. the same grid and rounding
+    as the (already swept) unsigned format, and the 7-bit clamp loses nothing."""
+    mant = np.arange(0, 1 << 23, 7, dtype=np.uint32)
+    for e in (-6, -5, -4, -3, 0, 2, 3, 4, 6):
+        for sign in (0, 1):
+            q = (mant | np.uint32((e + 127) << 23) | np.uint32(sign << 31)).view(np.float32)
+            c = np.empty(q.shape, np.uint8); v = np.empty_like(q)
+            hostcheck.hostcheck_sfast_codes(q.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(q.size), c.ctypes.data_as(ctypes.c_void_p),
+                                            v.ctypes.data_as(ctypes.c_void_p))
+            cu = np.empty(q.shape, np.uint8); vu = np.empty_like(q); c16 = np.empty(q.shape, np.uint8)
+            aq = np.abs(q)
+            hostcheck.hostcheck_relu_codes(aq.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(q.size), ctypes.c_int(1),
+                                           cu.ctypes.data_as(ctypes.c_void_p), vu.ctypes.data_as(ctypes.c_void_p),
+                                           c16.ctypes.data_as(ctypes.c_void_p))
+            want = np.where(sign == 1, -vu, vu)
+            assert (v == want).all(), (e, sign)
+            assert ((c >> 7) == sign).all()
