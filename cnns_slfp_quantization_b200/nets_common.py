@@ -77,12 +77,21 @@ def synth_state_dict(model, seed=0):
 
 
 def classifier_module(model):
-    """The final classifier layer (quantized or plain nn.Linear)."""
+    """The final classifier layer: the last nn.Linear (quantized or plain), or - SqueezeNet, whose classifier is a 1x1
+    convolution followed by ReLU and a global average pool (nets_imgnet/squeezenet1_0.py:87-93) - the last 1x1 conv."""
     last = None
     for m in model.modules():
         if isinstance(m, nn.Linear):
             last = m
+    if last is None:
+        for m in model.modules():
+            if isinstance(m, nn.Conv2d) and tuple(m.kernel_size) == (1, 1):
+                last = m
     return last
+
+
+def classifier_dims(fc):
+    return (fc.out_features, fc.in_features) if isinstance(fc, nn.Linear) else (fc.out_channels, fc.in_channels)
 
 
 def classifier_weight(fc, scale, seed=7):
@@ -129,13 +138,15 @@ def synth_images(batch, size, seed=1234, channels=3):
     return x + 1.5 * pat * (0.5 + ph[..., 2:3, None] / 6.28318)
 
 
-def prototype_classifier(feats, out_features, target=8.0, seed=11):
+def prototype_classifier(feats, out_features, target=8.0, seed=11, offset=0.0):
     """Nearest-prototype classifier for decisive whole-net fixtures: class i (i < batch) is image i.
 
     Row i = target * d_i / |d_i|^2 with d_i = f_i - mean(f) (so image i scores `target` on its own class and
     target * <d_i, d_j> / |d_i|^2 on the others), rows >= batch are seeded random directions of comparable norm,
-    bias = -W . mean(f).  `feats` are the REFERENCE net's classifier inputs on the fixture batch; the fixture stores
-    the prototype rows, the scalar for the random rows and the bias (tests/golden/make_golden_net224.py).
+    bias = -W . mean(f) + offset.  `feats` are the REFERENCE net's classifier inputs on the fixture batch (averaged over
+    the pixels when the classifier is SqueezeNet's 1x1 convolution; `offset` then lifts every pre-activation above its
+    ReLU so that the pooled logits stay linear in the features); the fixture stores the prototype rows, the scalar for
+    the random rows and the bias (tests/golden/make_golden_net224.py).
     Returns (protos [batch, in] float32, rest_scale float, bias [out] float32)."""
     f = torch.as_tensor(feats).double()
     fbar = f.mean(0, keepdim=True)
@@ -144,7 +155,7 @@ def prototype_classifier(feats, out_features, target=8.0, seed=11):
     protos = (target * d / n2).float()
     rest_scale = float(0.5 * target / n2.sqrt().median())
     w = prototype_weight(protos, out_features, rest_scale, seed)
-    bias = -(w.double() @ fbar[0]).float()
+    bias = (-(w.double() @ fbar[0]) + offset).float()
     return protos, rest_scale, bias
 
 
@@ -162,6 +173,7 @@ def prototype_weight(protos, out_features, rest_scale, seed=11):
 
 def apply_prototype_classifier(model, protos, rest_scale, bias, seed=11):
     fc = classifier_module(model)
+    out_f, _ = classifier_dims(fc)
     with torch.no_grad():
-        fc.weight.copy_(prototype_weight(protos, fc.out_features, rest_scale, seed).to(fc.weight.device))
+        fc.weight.copy_(prototype_weight(protos, out_f, rest_scale, seed).to(fc.weight.device).view_as(fc.weight))
         fc.bias.copy_(torch.as_tensor(bias, dtype=torch.float32).to(fc.bias.device))

@@ -44,7 +44,10 @@ def features_and_logits(m, x, chunk=8):
         for i in range(0, x.shape[0], chunk):
             outs.append(m(x[i:i + chunk]).detach().clone())
     h.remove()
-    return torch.cat(feats).reshape(x.shape[0], -1), torch.cat(outs)
+    f = torch.cat(feats)
+    if f.dim() == 4:                                   # SqueezeNet: the classifier is a 1x1 conv -> ReLU -> global average pool
+        f = f.mean((2, 3))
+    return f.reshape(x.shape[0], -1), torch.cat(outs)
 
 
 def calibrate(name, sd, x, chunk=8):
@@ -73,9 +76,12 @@ def make_case(out, key, name, qbit, batch, size, taps=False):
     m.load_state_dict(sd, strict=False)
     nc.set_scales(m, ka, kw)
     feats, _ = features_and_logits(m, x)
-    protos, rest_scale, bias = nc.prototype_classifier(feats, nc.classifier_module(m).out_features)
-    w = nc.prototype_weight(protos, nc.classifier_module(m).out_features, rest_scale)
-    sd[fc_name + ".weight"], sd[fc_name + ".bias"] = w, bias
+    out_f, _ = nc.classifier_dims(nc.classifier_module(m))
+    conv_cls = isinstance(nc.classifier_module(m), torch.nn.Conv2d)
+    # conv classifier (SqueezeNet): +24 keeps every pre-activation above the ReLU that precedes the average pool
+    protos, rest_scale, bias = nc.prototype_classifier(feats, out_f, offset=24.0 if conv_cls else 0.0)
+    w = nc.prototype_weight(protos, out_f, rest_scale)
+    sd[fc_name + ".weight"], sd[fc_name + ".bias"] = w.view_as(sd[fc_name + ".weight"]), bias
     # pass 2: the classifier's Kw from the prototype weight (the other scales do not change)
     layers = nc.quantized_layers(m)
     fc = nc.classifier_module(m)
@@ -115,7 +121,9 @@ def make_case(out, key, name, qbit, batch, size, taps=False):
           "logit std", float(y.std()), flush=True)
 
 
-CASES = [("resnet50_224", "resnet50", 8, 32, 224, False),
+CASES = [("alexnet", "alexnet", 8, 4, 224, True),
+         ("squeezenet", "squeezenet", 8, 4, 224, False),
+         ("resnet50_224", "resnet50", 8, 32, 224, False),
          ("resnet50_taps", "resnet50", 8, 2, 64, True),
          ("vgg16", "vgg16", 8, 16, 32, True),
          ("mobilenetv1_cifar", "mobilenetv1_cifar", 8, 16, 32, True),

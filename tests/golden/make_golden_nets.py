@@ -39,6 +39,12 @@ def ref_net(name, qbit):
     if name == "mobilenetv1_imgnet":
         from nets_imgnet.mobilenetv1 import MobileNetV1_Q
         return MobileNetV1_Q(3, qbit)
+    if name == "alexnet":
+        from nets_imgnet.alexnet import AlexNet
+        return AlexNet(qbit)
+    if name == "squeezenet":
+        from nets_imgnet.squeezenet1_0 import SqueezeNet
+        return SqueezeNet(qbit)
     if name == "shufflenetv2":
         from nets_cifar.shufflenet_v2 import ShuffleNetV2
         m = ShuffleNetV2(qbit)

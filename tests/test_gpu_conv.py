@@ -83,6 +83,39 @@ SHAPES = [
 ]
 
 
+# The distinct layer shapes of the BASELINE configs at batch 2: full channel counts and K depths
+# (up to K = 4 608), spatial sizes of the 224x224 / 32x32 nets.  N, C, H, W, K, k, stride, pad, dil
+CONFIG_SHAPES = [
+    (2, 64, 56, 56, 64, 1, 1, 0, 1), (2, 64, 56, 56, 64, 3, 1, 1, 1), (2, 64, 56, 56, 256, 1, 1, 0, 1), (2, 256, 56, 56, 64, 1, 1, 0, 1),
+    (2, 256, 56, 56, 128, 1, 1, 0, 1), (2, 128, 56, 56, 128, 3, 2, 1, 1), (2, 128, 28, 28, 512, 1, 1, 0, 1), (2, 256, 56, 56, 512, 1, 2, 0, 1),
+    (2, 512, 28, 28, 128, 1, 1, 0, 1), (2, 128, 28, 28, 128, 3, 1, 1, 1), (2, 512, 28, 28, 256, 1, 1, 0, 1), (2, 256, 28, 28, 256, 3, 2, 1, 1),
+    (2, 256, 14, 14, 1024, 1, 1, 0, 1), (2, 512, 28, 28, 1024, 1, 2, 0, 1), (2, 1024, 14, 14, 256, 1, 1, 0, 1), (2, 256, 14, 14, 256, 3, 1, 1, 1),
+    (2, 1024, 14, 14, 512, 1, 1, 0, 1), (2, 512, 14, 14, 512, 3, 2, 1, 1), (2, 512, 7, 7, 2048, 1, 1, 0, 1), (2, 1024, 14, 14, 2048, 1, 2, 0, 1),
+    (2, 2048, 7, 7, 512, 1, 1, 0, 1), (2, 512, 7, 7, 512, 3, 1, 1, 1), (4, 2048, 1, 1, 1000, 1, 1, 0, 1),          # ResNet-50
+    (2, 3, 224, 224, 64, 7, 2, 3, 1),                                                                              # its 7x7 / 2 stem
+    (4, 3, 32, 32, 64, 3, 1, 1, 1), (4, 64, 32, 32, 64, 3, 1, 1, 1), (4, 128, 16, 16, 256, 3, 1, 1, 1), (4, 256, 8, 8, 512, 3, 1, 1, 1),
+    (8, 512, 2, 2, 512, 3, 1, 1, 1),                                                                               # VGG-16 CIFAR
+    (2, 3, 224, 224, 32, 3, 2, 1, 1), (2, 32, 112, 112, 64, 1, 1, 0, 1), (2, 512, 14, 14, 512, 1, 1, 0, 1), (2, 1024, 7, 7, 1024, 1, 1, 0, 1),  # MobileNetV1
+    (2, 3, 224, 224, 64, 11, 4, 2, 1), (2, 64, 27, 27, 192, 5, 1, 2, 1), (2, 192, 13, 13, 384, 3, 1, 1, 1), (4, 9216, 1, 1, 4096, 1, 1, 0, 1),  # AlexNet
+    (2, 3, 224, 224, 96, 7, 2, 0, 1), (2, 96, 54, 54, 16, 1, 1, 0, 1), (2, 16, 54, 54, 64, 3, 1, 1, 1), (2, 512, 13, 13, 1000, 1, 1, 0, 1),     # SqueezeNet 1.0
+    (2, 24, 56, 56, 58, 1, 1, 0, 1), (2, 116, 28, 28, 116, 1, 1, 0, 1), (2, 464, 7, 7, 1024, 1, 1, 0, 1),          # ShuffleNetV2 (odd channel counts)
+]
+
+
+@pytest.mark.parametrize("shape", CONFIG_SHAPES)
+def test_config_layer_shapes_vs_oracle(orc, shape):
+    """Every distinct layer shape of the BASELINE configs through the C ABI against
+    the oracle's double-accumulating convolution of the reference's fake-quant operands: 1.2e-3 * L1 (SLFP-8), and
+    2e-6 * L1 against the same convolution of the float16-rounded operands (accumulation order only)."""
+    N, C, H, W, K, k, st, pad, dil = shape
+    rng = np.random.default_rng(abs(hash(shape)) % (1 << 31))
+    x = (rng.standard_normal((N, C, H, W)) * 2).astype(np.float32)
+    w = (rng.standard_normal((K, C, k, k)) * 0.3).astype(np.float32)
+    b = (rng.standard_normal(K) * 0.5).astype(np.float32) if (k in (5, 11) or C == 9216) else None
+    ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+    _check_fwd(orc, x, w, b, ka, kw, 8, st, pad, dil, 1, None, str(shape))
+
+
 @pytest.mark.parametrize("qbit", [8, 7])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_dense_shapes_vs_oracle(orc, shape, qbit):
@@ -243,6 +276,33 @@ def test_tensor_core_backward_matches_direct(orc, qbit, shape):
     dxa, dwa = _bwd_both(out, gy.abs(), N, H, W, C, K, k, 1, qbit, ka, kw, False)
     assert np.isfinite(dx1).all() and np.isfinite(dw1).all()
     for got, want, l1, what in ((dx1, dx0, dxa, "dx"), (dw1, dw0, dwa, "dw")):
+        err = np.abs(got - want)
+        assert (err <= 1.2e-3 * l1 + 1e-30).all(), (what, shape, float((err / (l1 + 1e-30)).max()))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 56, 56, 64, 3, 1, 1), (2, 256, 14, 14, 256, 3, 1, 1), (2, 128, 56, 56, 128, 3, 2, 1),
+                                   (2, 64, 56, 56, 256, 1, 1, 0), (2, 512, 7, 7, 512, 3, 1, 1), (2, 64, 27, 27, 192, 5, 1, 2)])
+def test_tensor_core_backward_config_shapes_vs_oracle(orc, shape):
+    """dgrad / wgrad implicit GEMMs (tcgen05, float16 operands, STE = identity) at layer shapes of the BASELINE configs
+    against the ORACLE's backward (double accumulation over the reference's fake-quant operands):
+    |d - d_ref| <= 1.2e-3 * the same sums over magnitudes."""
+    from gpu_util import conv_fwd_gpu
+    N, C, H, W, K, k, st, pad = shape
+    rng = np.random.default_rng(hash(shape) % (2 ** 31))
+    x = (rng.standard_normal((N, C, H, W)) * 2).astype(np.float32)
+    w = (rng.standard_normal((K, C, k, k)) * 0.3).astype(np.float32)
+    ka, kw = float(np.abs(x).max() / 15.5), float(np.abs(w).max() / 15.5)
+    out = conv_fwd_gpu(x, w, None, ka, kw, 8, st, pad, 1, 1)
+    Ho, Wo = out["y"].shape[2], out["y"].shape[3]
+    gy_np = (rng.standard_normal((N, K, Ho, Wo)) * 1e-3).astype(np.float32)
+    gy = torch.from_numpy(np.ascontiguousarray(gy_np.transpose(0, 2, 3, 1))).cuda()
+    dx, dw = _bwd_both(out, gy, N, H, W, C, K, k, 1, 8, ka, kw, True)
+    _, xq = orc.quantize(x, 1, ka, want_codes=False)
+    _, wq = orc.quantize(w, 2, kw, want_codes=False)
+    dx_r, dw_r, _ = orc.conv2d_q_bwd(xq, wq, gy_np, st, pad, 1, 1, ka, kw)
+    dx_a, dw_a, _ = orc.conv2d_q_bwd(np.abs(xq), np.abs(wq), np.abs(gy_np), st, pad, 1, 1, ka, kw)
+    dx_r, dx_a = dx_r.transpose(0, 2, 3, 1), dx_a.transpose(0, 2, 3, 1)          # the C ABI's dx is NHWC
+    for got, want, l1, what in ((dx, dx_r, dx_a, "dx"), (dw, dw_r, dw_a, "dw")):
         err = np.abs(got - want)
         assert (err <= 1.2e-3 * l1 + 1e-30).all(), (what, shape, float((err / (l1 + 1e-30)).max()))
 

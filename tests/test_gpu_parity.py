@@ -39,7 +39,7 @@ def _report(key, val):
 
 def build(net, qbit, **kw):
     from cnns_slfp_quantization_b200 import engine
-    from cnns_slfp_quantization_b200.nets_imgnet import ResNet50, MobileNetV1_Q as MobileNetImg
+    from cnns_slfp_quantization_b200.nets_imgnet import ResNet50, MobileNetV1_Q as MobileNetImg, AlexNet, SqueezeNet
     from cnns_slfp_quantization_b200.nets_cifar import VGG16_Q, MobileNetV1_Q as MobileNetCifar, ShuffleNetV2
     if net == "resnet50":
         return ResNet50(qbit), lambda m, b, s: engine.compile_resnet50(m, b, s, **kw)
@@ -49,6 +49,10 @@ def build(net, qbit, **kw):
         return MobileNetCifar(3, qbit), lambda m, b, s: engine.compile_mobilenetv1(m, b, s, **kw)
     if net == "mobilenetv1_imgnet":
         return MobileNetImg(3, qbit), lambda m, b, s: engine.compile_mobilenetv1(m, b, s, **kw)
+    if net == "alexnet":
+        return AlexNet(qbit), None                  # module-level drop-in (SURVEY f-3: caller with 11x11 / 5x5 / 4096-wide layers)
+    if net == "squeezenet":
+        return SqueezeNet(qbit), None
     if net == "shufflenetv2":
         comp = getattr(engine, "compile_shufflenetv2", None)
         return ShuffleNetV2(qbit), (None if comp is None else (lambda m, b, s: comp(m, b, s, **kw)))
@@ -94,7 +98,7 @@ def stats(y, ref):
 # logit RMS bounds: ~1.5x the values measured on a B200 with this tree (profiles/r02_parity.md)
 CASES = [("resnet50_224", "resnet50", 8, 0.06), ("vgg16", "vgg16", None, 0.33), ("mobilenetv1_cifar", "mobilenetv1_cifar", None, 0.46),
          ("mobilenetv1_imgnet", "mobilenetv1_imgnet", None, 0.035), ("shufflenetv2", "shufflenetv2", None, 0.16),
-         ("shufflenetv2_224", "shufflenetv2", None, 0.63)]
+         ("shufflenetv2_224", "shufflenetv2", None, 0.63), ("alexnet", "alexnet", None, 0.025), ("squeezenet", "squeezenet", None, 0.12)]
 
 
 @pytest.mark.parametrize("key,net,chunk,rms_bound", CASES)
