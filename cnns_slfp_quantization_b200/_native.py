@@ -14,6 +14,7 @@ FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_S
 ACT_STL, ACT_SWISH, ACT_SIGMOID = 0, 1, 2
 SGD_NORMAL, SGD_DSGD, SGD_SSGD = 0, 1, 2
 Q_LAYEROUT_ZERO_IS_ZERO = 1
+CONV_SPLIT_OPERANDS = 1
 
 c_vp, c_sz, c_f, c_i, c_ll, c_d = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
                                    ctypes.c_longlong, ctypes.c_double)
@@ -21,7 +22,7 @@ c_vp, c_sz, c_f, c_i, c_ll, c_d = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_fl
 
 class SlfpConvDesc(ctypes.Structure):
     _fields_ = [(n, c_i) for n in ("n", "h", "w", "c", "c_phys", "k", "r", "s", "stride_h", "stride_w", "pad_h",
-                                   "pad_w", "dil_h", "dil_w", "groups", "fmt", "pad_h_extra", "pad_w_extra")]
+                                   "pad_w", "dil_h", "dil_w", "groups", "fmt", "pad_h_extra", "pad_w_extra", "flags")]
 
 
 class SlfpEpilogue(ctypes.Structure):
@@ -37,7 +38,7 @@ class SlfpGatherChan(ctypes.Structure):
 
 class SlfpWeightJob(ctypes.Structure):
     _fields_ = [("desc", ctypes.POINTER(SlfpConvDesc)), ("w", c_vp), ("w_stride", c_ll * 4), ("kw", c_f), ("w_f16", c_vp),
-                ("w_codes", c_vp), ("out_pitch", c_sz), ("out_offset", c_sz), ("row_scale", c_vp)]
+                ("w_codes", c_vp), ("out_pitch", c_sz), ("out_offset", c_sz), ("row_scale", c_vp), ("lo_offset", c_sz)]
 
 
 _SIGS = {

@@ -77,6 +77,8 @@ struct Params {
     int act_fmt;
     int plain_1x1;              // 1x1 / stride 1 / no padding: the code tile is a plain 2-D tile of the [M, C] matrix
     int nkb1;                   // K blocks taken from input 1 (== num_kb unless a second input is concatenated along K)
+    int kb_base;                // K blocks of ONE pass over K (== num_kb; num_kb / 3 in the split-operand mode)
+    int w_lo_col;               // split-operand mode: first column of the lo weights inside a weight row (= the row pitch)
     int sh2, sw2;               // second input (fused downsample branch): 1x1, stride (sh2, sw2), no padding, Cp % 64 == 0
     SlfpEpilogue epi;
     DivK next_div, next_div2;   // exact quantize-on-store (signed code formats)
@@ -602,12 +604,16 @@ struct OutMaps {
     CUtensorMap res, y16, c1, c2;
 };
 
-template <int BLOCK_N, int GRAN, int DW, bool STG>
+// HIFI (SLFP_CONV_SPLIT_OPERANDS): three passes over K into the same accumulator - pass 0: x_hi * w_hi, pass 1: x_hi * w_lo,
+// pass 2: x_lo * w_hi - with (hi, lo) the float16 pair of a value.  The decode table holds hi in the low and lo in the
+// high half of an entry, the decode warps pick the half per K block; the weight rows are [hi | lo].
+template <int BLOCK_N, int GRAN, int DW, bool STG, bool HIFI = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ OutMaps omaps, const Params p) {
     using C = Cfg<BLOCK_N, STG>;
     static_assert(!STG || (BLOCK_N == 128 && DW == 8 && GRAN == 64), "staged epilogue: 128-column tiles, 16 epilogue warps");
+    static_assert(!HIFI || !STG, "the split-operand mode uses the generic epilogue");
     using R = Roles<DW>;
     constexpr int kCodeStages = C::kCodeStages;
     constexpr int kDecWarps = R::kDecWarps, kEpiWarps = R::kEpiWarps, kEpiWarp0 = R::kEpiWarp0, kGroups = R::kGroups;
@@ -646,7 +652,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // ---- one-time setup ---------------------------------------------------------------------------
     for (int i = tid; i < 256 * 32; i += kThreads) {
         const float f = decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac);
-        s_lut[i] = (uint32_t)__half_as_ushort(__float2half_rn(f));
+        const __half hi = __float2half_rn(f);
+        uint32_t e = (uint32_t)__half_as_ushort(hi);
+        if (HIFI) e |= (uint32_t)__half_as_ushort(__float2half_rn(f - __half2float(hi))) << 16;
+        s_lut[i] = e;
     }
     if (warp == kWarpCode && lane == 0) {
         ptx::prefetch_tmap(&tmap_x);
@@ -710,7 +719,9 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
                 const int w0 = wo * p.sw - p.pw, h0 = ho * p.sh - p.ph;
                 int tap = 0, r = 0, s = 0, cb = 0;       // GRAN 64: cb = 64-channel block; GRAN 16: 16-channel block
-                for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+                int kb = 0;                               // K block inside ONE pass over K (the split-operand mode makes three)
+                for (int kbt = 0; kbt < p.num_kb; ++kbt, ++kb, ++g) {
+                    if (HIFI && kb == p.kb_base) { kb = 0; tap = 0; r = 0; s = 0; cb = 0; }
                     if ((g & 1u) != mine) {                 // the other producer's K block: only advance the counters
                         if (GRAN == 64) {
                             if (++cb == p.cblocks) { cb = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
@@ -764,7 +775,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             // K block s % num_kb of the same filter - after the first pass over the ring the producer only arrives on the
             // barrier.  Every TMA load costs >= ~190 cycles of the TMA unit whatever its size (tools/ubench/tma_box.cu), and
             // the space-to-depth stem, at 4 code loads + 1 weight load per K block, ran exactly at that floor.
-            const bool w_res = p.n_tiles == 1 && p.num_kb <= C::kStages && (C::kStages % p.num_kb) == 0;
+            const bool w_res = !HIFI && p.n_tiles == 1 && p.num_kb <= C::kStages && (C::kStages % p.num_kb) == 0;
             uint32_t issued = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -776,7 +787,12 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         if (ptx::elect_one()) ptx::mbar_arrive(full);
                     } else if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kBBytes);
-                        ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, kb * kBK, n0);
+                        int wcol = kb * kBK;
+                        if (HIFI) {                     // pass 0 / 2: w_hi, pass 1: w_lo (second half of the weight row)
+                            const int pass = kb / p.kb_base, kbb = kb - pass * p.kb_base;
+                            wcol = kbb * kBK + (pass == 1 ? p.w_lo_col : 0);
+                        }
+                        ptx::tma_load_2d(ptx::smem_u32(s_b + stage * C::kBBytes), &tmap_w, full, wcol, n0);
                     }
                     __syncwarp();
                     if (++stage == (uint32_t)C::kStages) { stage = 0; phase ^= 1u; }
@@ -880,12 +896,14 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const long long prof_t = clock64();
 #endif
             if (C::kATmem) ptx::tc_fence_after();
+            const uint32_t hsel = (HIFI && kb >= 2 * p.kb_base) ? 0x7632u : 0x5410u;
             const uint32_t a_dst = a_base + stage * kABytes;
 #pragma unroll
             for (int qi = 0; qi < kQPW; ++qi) {
                 const int q = q0 + qi;
                 // 16-channel pieces beyond the last filter tap (K padding) are not loaded: zeros
-                const bool valid = GRAN == 64 || (kb * 4 + q < k16_total);
+                const int kbb = HIFI ? kb % p.kb_base : kb;
+                const bool valid = GRAN == 64 || (kbb * 4 + q < k16_total);
                 uint4 cw = make_uint4(0u, 0u, 0u, 0u);
                 if (valid) cw = ptx::lds128_volatile(code_s + cs * kCodeBytes + c_off[qi]);
                 const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
@@ -899,8 +917,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     const uint32_t e1 = ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base);
                     const uint32_t e2 = ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base);
                     const uint32_t e3 = ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base);
-                    h[2 * i] = ptx::pack16_fma(e0, e1);
-                    h[2 * i + 1] = ptx::pack16_fma(e2, e3);
+                    if (HIFI) {                          // hi halves (passes 0, 1) or lo halves (pass 2) of two entries
+                        h[2 * i] = __byte_perm(e0, e1, hsel);
+                        h[2 * i + 1] = __byte_perm(e2, e3, hsel);
+                    } else {
+                        h[2 * i] = ptx::pack16_fma(e0, e1);
+                        h[2 * i + 1] = ptx::pack16_fma(e2, e3);
+                    }
                 }
                 if (C::kATmem) {
                     ptx::tmem_st8(a_tmem_lane + stage * 32u + (uint32_t)q * 8u, h);
@@ -1161,10 +1184,10 @@ static PFN driver_fn(const char* name) {
     return nullptr;
 }
 
-template <int BLOCK_N, int GRAN, int DW, bool STG = false>
+template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false>
 static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const OutMaps& om, const Params& p, cudaStream_t st) {
     using C = Cfg<BLOCK_N, STG>;
-    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG>;
+    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -1265,7 +1288,12 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         pitch += slfp_conv_wpitch(d2);
         p.sh2 = d2->stride_h; p.sw2 = d2->stride_w;
     }
-    p.num_kb = (int)(pitch / kBK);
+    const bool hifi = (d->flags & SLFP_CONV_SPLIT_OPERANDS) != 0;
+    if (hifi && d2) return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd_dual: no split-operand mode for the fused block tail");
+    p.kb_base = (int)(pitch / kBK);
+    p.num_kb = hifi ? 3 * p.kb_base : p.kb_base;
+    p.w_lo_col = (int)pitch;
+    const size_t wrow = hifi ? 2 * pitch : pitch;             // halves per weight row ([hi | lo] in the split-operand mode)
     p.cblocks = (d->c_phys % 64 == 0) ? d->c_phys / 64 : 0;
     p.c16s = d->c_phys / 16;
     p.act_fmt = d->fmt;
@@ -1290,7 +1318,7 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     }
     // Staged (TMA) epilogue for the epilogue-bound mode-2 layers (block tails, short-K fused tails): 128-column tiles.
     static const int stg_max_kb = getenv("SLFP_STG_MAXKB") ? atoi(getenv("SLFP_STG_MAXKB")) : 8;
-    const bool stg = p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
+    const bool stg = !hifi && p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
                      (((uintptr_t)epi->residual) & 15u) == 0;
     const int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
@@ -1303,8 +1331,8 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     if (!enc_tiled || !enc_im2col) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncode{Tiled,Im2col} not available");
     CUtensorMap tmap_w, tmap_x;
     {
-        const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)d->k};
-        const cuuint64_t gstr[1] = {(cuuint64_t)pitch * 2};
+        const cuuint64_t gdim[2] = {(cuuint64_t)wrow, (cuuint64_t)d->k};
+        const cuuint64_t gstr[1] = {(cuuint64_t)wrow * 2};
         const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn};
         const cuuint32_t estr[2] = {1, 1};
         CUresult cr = enc_tiled(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_f16), gdim, gstr, box, estr,
@@ -1380,6 +1408,15 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         if (!ok) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled(outputs) failed");
         return launch<128, 64, 8, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
     }
+#define SLFP_V2_HIFI(BN)                                                                                         \
+    if (hifi && bn == BN) {                                                                                      \
+        if (p.cblocks) return launch<BN, 64, 16, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);               \
+        return launch<BN, 16, 16, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);                              \
+    }
+    SLFP_V2_HIFI(64)
+    SLFP_V2_HIFI(128)
+    SLFP_V2_HIFI(256)
+#undef SLFP_V2_HIFI
 #define SLFP_V2_CASE(BN)                                                                                         \
     if (bn == BN) {                                                                                              \
         if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, tmap_x2, om, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, tmap_x2, om, p, st); \

@@ -668,6 +668,7 @@ struct WPrepArgs {
     // placement of the row inside a wider (concatenated-K) operand and an optional per-output-channel factor
     // applied to the float16 operand only (fused block tails, see slfp_conv2d_fwd_dual)
     size_t out_pitch, out_off;
+    size_t lo_off;                                           // != 0: the lo half of the split operand goes to o + lo_off
     const float* row_scale;
     uint32_t mg_pitch, sh_pitch, mg_cp, sh_cp, mg_s, sh_s;   // n / d == umulhi(n, mg) >> sh for n < 2^31 (d > 1)
     DivK dk;                                                 // kw with its reciprocal: exact x / kw without the division sequence
@@ -713,7 +714,12 @@ __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, cons
         if (a.w_fakeq) a.w_fakeq[(((size_t)k * a.C + c) * a.R + r) * a.S + s] = fq;
     }
     const size_t o = (size_t)k * a.out_pitch + a.out_off + j;
-    if (a.w_f16) a.w_f16[o] = __float2half_rn(a.row_scale ? fq * __ldg(a.row_scale + k) : fq);
+    if (a.w_f16) {
+        const float val = a.row_scale ? fq * __ldg(a.row_scale + k) : fq;
+        const __half hi = __float2half_rn(val);
+        a.w_f16[o] = hi;
+        if (a.lo_off) a.w_f16[o + a.lo_off] = __float2half_rn(val - __half2float(hi));
+    }
     if (a.w_codes) a.w_codes[o] = (uint8_t)code;
 }
 
@@ -736,7 +742,7 @@ __device__ __forceinline__ void wprep_vec8(const WPrepArgs& a, size_t i, const W
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = (tap_in && c0 + e < a.C) ? __ldg(src + (c0 + e) * a.sc) : 0.0f;
     const float rsk = a.row_scale ? __ldg(a.row_scale + k) : 1.0f;
-    uint32_t hw[4], cw[2] = {0u, 0u};
+    uint32_t hw[4], lw[4], cw[2] = {0u, 0u};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const float v = div_k(x[e], a.dk);                   // == IEEE x / kw
@@ -747,12 +753,16 @@ __device__ __forceinline__ void wprep_vec8(const WPrepArgs& a, size_t i, const W
             fq = tb.dec[code];
         }
         if (a.w_fakeq && tap_in && c0 + e < a.C) a.w_fakeq[(((size_t)k * a.C + c0 + e) * a.R + r) * a.S + s_] = fq;
-        const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(a.row_scale ? fq * rsk : fq));
-        if (e & 1) hw[e >> 1] |= h << 16; else hw[e >> 1] = h;
+        const float val = a.row_scale ? fq * rsk : fq;
+        const __half hh = __float2half_rn(val);
+        const uint32_t h = (uint32_t)__half_as_ushort(hh);
+        const uint32_t l = (uint32_t)__half_as_ushort(__float2half_rn(val - __half2float(hh)));   // split-operand lo part
+        if (e & 1) { hw[e >> 1] |= h << 16; lw[e >> 1] |= l << 16; } else { hw[e >> 1] = h; lw[e >> 1] = l; }
         cw[e >> 2] |= code << (8 * (e & 3));
     }
     const size_t o = (size_t)k * a.out_pitch + a.out_off + j;
     if (a.w_f16) *reinterpret_cast<uint4*>(a.w_f16 + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (a.w_f16 && a.lo_off) *reinterpret_cast<uint4*>(a.w_f16 + o + a.lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     if (a.w_codes) *reinterpret_cast<uint2*>(a.w_codes + o) = make_uint2(cw[0], cw[1]);
 }
 
@@ -1042,7 +1052,7 @@ static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long 
     else { a.C = d->c; a.Cp = d->c_phys; }
     a.pitch = slfp_conv_wpitch(d);
     a.kw = kw; a.dk = make_divk(kw); a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
-    a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr;
+    a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr; a.lo_off = 0;
     a.vec8_ok = ((a.Cp & 7) == 0 && (a.pitch & 7) == 0 && (((uintptr_t)a.w_f16) & 15u) == 0 && (((uintptr_t)a.w_codes) & 7u) == 0 &&
                  getenv("SLFP_WPREP_SCALAR") == nullptr) ? 1 : 0;
     if ((size_t)a.K * a.pitch >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^31 or more elements");
@@ -1091,9 +1101,12 @@ extern "C" int slfp_prepare_weights_jobs(int n, const SlfpWeightJob* host_jobs, 
                     return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_jobs: out_pitch %zu < out_offset %zu + row %zu", jb.out_pitch,
                                      jb.out_offset, a.pitch);
                 a.out_pitch = jb.out_pitch; a.out_off = jb.out_offset;
+                if (jb.lo_offset && jb.out_pitch < jb.out_offset + jb.lo_offset + a.pitch)
+                    return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_jobs: out_pitch %zu too small for the lo part", jb.out_pitch);
             }
             a.row_scale = jb.row_scale;
-            a.vec8_ok = ((a.Cp & 7) == 0 && (a.pitch & 7) == 0 && (a.out_pitch & 7) == 0 && (a.out_off & 7) == 0 &&
+            a.lo_off = jb.out_pitch ? jb.lo_offset : 0;
+            a.vec8_ok = ((a.Cp & 7) == 0 && (a.pitch & 7) == 0 && (a.out_pitch & 7) == 0 && (a.out_off & 7) == 0 && (a.lo_off & 7) == 0 &&
                          (((uintptr_t)a.w_f16) & 15u) == 0 && (((uintptr_t)a.w_codes) & 7u) == 0 &&
                          getenv("SLFP_WPREP_SCALAR") == nullptr) ? 1 : 0;
             const size_t total = (size_t)a.K * a.pitch;

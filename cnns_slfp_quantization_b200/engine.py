@@ -56,8 +56,12 @@ def fold_bn(bn):
 
 
 class Plan:
-    def __init__(self, batch, device, q_bit, static_weights=False):
+    def __init__(self, batch, device, q_bit, static_weights=False, high_fidelity=False):
         self.lib = nv.lib()
+        # high_fidelity: split-operand tensor-core mode (SLFP_CONV_SPLIT_OPERANDS: float16 hi + lo pairs, three passes over K)
+        # for every dense layer with c_phys % 16 == 0, the exact signed code formats and float32 instead of float16 value
+        # tensors - the plan then differs from the reference's float32 arithmetic by accumulation order only
+        self.high_fidelity = high_fidelity
         self.batch, self.dev, self.q_bit = batch, device, q_bit
         self.afmt, self.wfmt = nv.fmt_for(q_bit, "act"), nv.fmt_for(q_bit, "weight")
         self.static_weights = static_weights
@@ -84,10 +88,10 @@ class Plan:
         self.keep.append(buf)               # the pre-bound calls hold raw pointers: the plan owns the storage
         return _T(buf, n, h, w, c, cp, kind, kdiv, (fmt if fmt is not None else self.afmt) if kind == "codes" else None)
 
-    def _weight_job(self, d, wview, kw, wbuf, dense, out_pitch=0, out_offset=0, row_scale=None):
+    def _weight_job(self, d, wview, kw, wbuf, dense, out_pitch=0, out_offset=0, row_scale=None, lo_offset=0):
         self.weight_table.append((d, wview.data_ptr(), tuple(wview.stride()), kw, wbuf.data_ptr() if dense else None,
                                   None if dense else wbuf.data_ptr(), out_pitch, out_offset,
-                                  None if row_scale is None else row_scale.data_ptr()))
+                                  None if row_scale is None else row_scale.data_ptr(), lo_offset))
         self._wbatch = None
 
     def _call(self, fn, *args):
@@ -188,16 +192,24 @@ class Plan:
         # 232) to the kernel with K rounded up - weight rows and affine entries of the pad channels are zero, so they
         # produce exact zeros (code 0 / 0.0) - which makes it eligible for the vectorised fast epilogues.
         Kk = self._cp(K) if (pad_k and dense and K % 16 != 0) else K
+        hifi = self.high_fidelity and dense and x.cp % 16 == 0
+        flags = nv.CONV_SPLIT_OPERANDS if hifi else 0
         d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, Kk, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
-                            x.fmt, pex[0], pex[1])
+                            x.fmt, pex[0], pex[1], flags)
         dw_ = d if Kk == K else nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0],
-                                                 dil[1], groups, x.fmt, pex[0], pex[1])       # the weight job writes K rows
+                                                 dil[1], groups, x.fmt, pex[0], pex[1], flags)       # the weight job writes K rows
         Ho = (x.h + 2 * pad[0] + pex[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
         Wo = (x.w + 2 * pad[1] + pex[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
         pitch = self.lib.slfp_conv_wpitch(ctypes.byref(d))
-        wbuf = torch.zeros((Kk * pitch,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
+        wrow = 2 * pitch if hifi else pitch                    # split operands: rows of [hi | lo]
+        wbuf = torch.zeros((Kk * wrow,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
         # weight re-quantization: one table entry; Plan.prepare_weights() runs the whole table in ONE launch
-        self._weight_job(dw_, wview, kw, wbuf, dense)
+        if hifi:
+            self._weight_job(dw_, wview, kw, wbuf, dense, out_pitch=wrow, out_offset=0, lo_offset=pitch)
+        else:
+            self._weight_job(dw_, wview, kw, wbuf, dense)
+        if self.high_fidelity:
+            relu_codes, signed_fast = False, False          # exact quantizer codes everywhere
         epi = nv.SlfpEpilogue()
         # Fold bias, post-scale and eval BatchNorm into one per-channel affine y = acc * mul + add
         # (float64, rounded once): mul = Ka*Kw*bn_scale, add = bias_q*Ka*Kw*bn_scale + bn_shift.
@@ -403,10 +415,10 @@ class Plan:
             op()
         if self._wbatch is None:
             jobs = (nv.SlfpWeightJob * n)()
-            for j, (d, w, strides, kw, f16, codes, out_pitch, out_offset, row_scale) in zip(jobs, self.weight_table):
+            for j, (d, w, strides, kw, f16, codes, out_pitch, out_offset, row_scale, lo_offset) in zip(jobs, self.weight_table):
                 j.desc, j.w, j.kw, j.w_f16, j.w_codes = ctypes.pointer(d), w, kw, f16, codes
                 j.w_stride[:] = strides
-                j.out_pitch, j.out_offset, j.row_scale = out_pitch, out_offset, row_scale
+                j.out_pitch, j.out_offset, j.row_scale, j.lo_offset = out_pitch, out_offset, row_scale, lo_offset
             self._wbatch = jobs
         nv.check(self.lib.slfp_prepare_weights_jobs(n, self._wbatch, self.wfmt, nv.stream()))
 
@@ -445,10 +457,15 @@ class Plan:
 
 
 # ---- per-architecture compilers -------------------------------------------------------------------------------
-def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", static_weights=False, fuse_downsample=True):
-    """nets_imgnet.ResNet50 (or the reference's own class: same attribute names) -> Plan."""
+def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", static_weights=False, fuse_downsample=True,
+                     high_fidelity=False):
+    """nets_imgnet.ResNet50 (or the reference's own class: same attribute names) -> Plan.
+    high_fidelity: split-operand tensor-core mode, exact signed codes, float32 residual stream, no fused block tails -
+    about 3x the tensor work; the parity instrument (tests/test_gpu_parity.py), not the benchmark path."""
     assert not model.training, "the fused pipeline folds BatchNorm: call model.eval() first"
-    P = Plan(batch, device, model.qbit if hasattr(model, "qbit") else model.conv1.q_bit, static_weights)
+    if high_fidelity:
+        residual, fuse_downsample = "f32", False
+    P = Plan(batch, device, model.qbit if hasattr(model, "qbit") else model.conv1.q_bit, static_weights, high_fidelity)
     res_f16 = residual == "f16"
     x = P.input_nchw(3, size, size)
     blocks = [b for li in range(1, 5) for b in getattr(model, f"layer{li}")]

@@ -27,6 +27,14 @@ from .sfp_quant import *
 from .. import _native as _nv
 
 
+# High-fidelity switch of the drop-in modules: True runs every dense layer in the split-operand tensor-core mode
+# (include/slfp_b200.h SLFP_CONV_SPLIT_OPERANDS: float16 hi + lo operand pairs, three passes over K; conv outputs agree
+# with the reference's float32 arithmetic to accumulation order) at about 3x the tensor work.  Forward only - the
+# backward keeps single float16 operands.  Also settable with the environment variable SLFP_HIGH_FIDELITY=1.
+import os as _os
+HIGH_FIDELITY = bool(_os.environ.get("SLFP_HIGH_FIDELITY"))
+
+
 def _ceil_to(v, m):
     return (v + m - 1) // m * m
 
@@ -61,10 +69,11 @@ class _QConvNHWC(torch.autograd.Function):
         if Cg * groups != C:
             raise RuntimeError(f"Conv2d_Q: weight {tuple(weight.shape)} does not match input channels {C} (groups={groups})")
         dense = groups == 1
-        Cp = (4 if C <= 4 else _ceil_to(C, 16)) if dense else _ceil_to(C, 4)
+        hifi = HIGH_FIDELITY and dense
+        Cp = ((4 if (C <= 4 and not hifi) else _ceil_to(C, 16))) if dense else _ceil_to(C, 4)
         afmt, wfmt = _nv.fmt_for(cfg.q_bit, "act"), _nv.fmt_for(cfg.q_bit, "weight")
         d = _nv.SlfpConvDesc(N, H, W, C, Cp, K, R, S, cfg.stride[0], cfg.stride[1], cfg.padding[0], cfg.padding[1],
-                             cfg.dilation[0], cfg.dilation[1], groups, afmt)
+                             cfg.dilation[0], cfg.dilation[1], groups, afmt, 0, 0, _nv.CONV_SPLIT_OPERANDS if hifi else 0)
         Ho = (H + 2 * cfg.padding[0] - cfg.dilation[0] * (R - 1) - 1) // cfg.stride[0] + 1
         Wo = (W + 2 * cfg.padding[1] - cfg.dilation[1] * (S - 1) - 1) // cfg.stride[1] + 1
         if Ho <= 0 or Wo <= 0:
@@ -76,10 +85,21 @@ class _QConvNHWC(torch.autograd.Function):
         # 2. weights: w / Kw -> codes (+ the float16 tensor-core operand), KRSC
         pitch = lib.slfp_conv_wpitch(ctypes_byref(d))
         w_codes = torch.empty((K * pitch,), dtype=torch.uint8, device=x.device)
-        w_f16 = torch.empty((K * pitch,), dtype=torch.float16, device=x.device) if dense else None
+        w_f16 = torch.empty((K * pitch * (2 if hifi else 1),), dtype=torch.float16, device=x.device) if dense else None
         so, sc, sr, ss = weight.stride()
-        _nv.check(lib.slfp_prepare_weights(ctypes_byref(d), weight.data_ptr(), so, sc, sr, ss, cfg.kw, wfmt,
-                                           _nv.ptr(w_f16), w_codes.data_ptr(), None, st))
+        if hifi:
+            # split operands: rows of [hi | lo] halves - the jobs entry point carries the lo placement
+            job = (_nv.SlfpWeightJob * 1)()
+            job[0].desc, job[0].w, job[0].kw = _ctypes.pointer(d), weight.data_ptr(), cfg.kw
+            job[0].w_stride[:] = (so, sc, sr, ss)
+            job[0].w_f16, job[0].w_codes = w_f16.data_ptr(), None
+            job[0].out_pitch, job[0].out_offset, job[0].lo_offset = 2 * pitch, 0, pitch
+            _nv.check(lib.slfp_prepare_weights_jobs(1, job, wfmt, st))
+            _nv.check(lib.slfp_prepare_weights(ctypes_byref(d), weight.data_ptr(), so, sc, sr, ss, cfg.kw, wfmt,
+                                               None, w_codes.data_ptr(), None, st))          # codes (backward, taps): own pitch
+        else:
+            _nv.check(lib.slfp_prepare_weights(ctypes_byref(d), weight.data_ptr(), so, sc, sr, ss, cfg.kw, wfmt,
+                                               _nv.ptr(w_f16), w_codes.data_ptr(), None, st))
         # 3. convolution with the reference's post-scale (and bias) in the epilogue
         y = torch.empty((N, Ho, Wo, K), dtype=torch.float32, device=x.device)
         epi = _nv.SlfpEpilogue()

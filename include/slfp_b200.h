@@ -161,7 +161,16 @@ typedef struct {
     int pad_h_extra;      /* bottom / right padding minus top / left padding (0 = symmetric, as in      */
     int pad_w_extra;      /* PyTorch).  Non-zero only for the space-to-depth form of a strided stem:     */
                           /* dense, c_phys % 16 == 0.                                                   */
+    int flags;            /* SLFP_CONV_* bits, 0 = default                                               */
 } SlfpConvDesc;
+
+/* High-fidelity (split-operand) mode of the dense forward: both tensor-core operands are float16 PAIRS hi + lo
+ * (hi = float16(v), lo = float16(v - hi): 2^-21 .. 2^-22 relative instead of 2^-12 for the irrational SLFP grid values)
+ * and the GEMM runs as three passes over K, x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, into the same float32 accumulator -
+ * conv outputs then agree with the reference's float32 arithmetic to accumulation order.  About 3x the tensor and
+ * decode work; dense layers with c_phys % 16 == 0 only.  The weight operand has rows of 2 * slfp_conv_wpitch() halves,
+ * [hi | lo] (SlfpWeightJob.lo_offset = slfp_conv_wpitch()). */
+#define SLFP_CONV_SPLIT_OPERANDS 1
 
 typedef struct {
     const float *bias_q;   /* [k] added to the accumulator BEFORE the post-scale (bias/Ka/Kw,
@@ -221,6 +230,8 @@ typedef struct {
     uint8_t *w_codes;
     size_t out_pitch, out_offset;
     const float *row_scale;
+    size_t lo_offset;          /* != 0: also write lo = float16(w_q - float(w_f16)) at out_offset + lo_offset inside the
+                                  row (the split-operand mode, SLFP_CONV_SPLIT_OPERANDS); 0 = no lo part             */
 } SlfpWeightJob;
 int slfp_prepare_weights_jobs(int n, const SlfpWeightJob *host_jobs, int wfmt, slfp_stream_t stream);
 

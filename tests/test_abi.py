@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from cnns_slfp_quantization_b200 import _native
-    assert ctypes.sizeof(_native.SlfpConvDesc) == 18 * 4
+    assert ctypes.sizeof(_native.SlfpConvDesc) == 19 * 4
     # pointers 8-byte aligned, ints/floats 4: computed by the C compiler for the same field order
     import subprocess, tempfile, textwrap
     src = textwrap.dedent('''
