@@ -530,6 +530,9 @@ def main():
             with open(os.environ["SLFP_BENCH_LAYERS"], "w") as f:
                 for ms_, fl, is_dense, desc, by in rows:
                     f.write(f"{desc:34s} {'dense' if is_dense else 'dw   '} {ms_ * 1e3:9.1f} us {fl / ms_ / 1e9:8.1f} TFLOP/s {by / ms_ / 1e6:8.1f} GB/s\n")
+                for k, v in prof.items():                       # every other entry point, launch by launch
+                    if k not in ("slfp_conv2d_fwd", "slfp_conv2d_fwd_dual"):
+                        f.write(f"# {k}: " + " ".join(f"{a.elapsed_time(b) * 1e3:.1f}" for a, b, _ in v) + " us\n")
         dense = [r for r in rows if r[2]]
         dw = [r for r in rows if not r[2]]
         step_ms = ms / args.steps

@@ -10,11 +10,12 @@ import torch
 
 from .build import LIB_PATH, source_hash
 
-FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU, FMT_SFP33_SFAST = 0, 1, 2, 3, 4, 5, 6
+FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU, FMT_SFP33_SFAST, FMT_E4M3 = 0, 1, 2, 3, 4, 5, 6, 7
 ACT_STL, ACT_SWISH, ACT_SIGMOID = 0, 1, 2
 SGD_NORMAL, SGD_DSGD, SGD_SSGD = 0, 1, 2
 Q_LAYEROUT_ZERO_IS_ZERO = 1
 CONV_SPLIT_OPERANDS = 1
+CONV_E4M3_OPERANDS = 2
 
 c_vp, c_sz, c_f, c_i, c_ll, c_d = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
                                    ctypes.c_longlong, ctypes.c_double)
@@ -36,6 +37,11 @@ class SlfpGatherChan(ctypes.Structure):
     _fields_ = [("src", c_vp), ("stride", c_i), ("ch", c_i)]
 
 
+class SlfpGatherRun(ctypes.Structure):
+    _fields_ = [("src", c_vp), ("stride", c_i), ("ch0", c_i), ("len", c_i), ("dst_start", c_i), ("dst_step", c_i),
+                ("magic", ctypes.c_uint), ("shift", ctypes.c_uint)]
+
+
 class SlfpWeightJob(ctypes.Structure):
     _fields_ = [("desc", ctypes.POINTER(SlfpConvDesc)), ("w", c_vp), ("w_stride", c_ll * 4), ("kw", c_f), ("w_f16", c_vp),
                 ("w_codes", c_vp), ("out_pitch", c_sz), ("out_offset", c_sz), ("row_scale", c_vp), ("lo_offset", c_sz)]
@@ -52,6 +58,8 @@ _SIGS = {
     "slfp_quantize_nchw_s2d_f32": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_vp, c_vp]),
     "slfp_dequantize": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp]),
     "slfp_gather_quantize_f16": (c_i, [c_vp, c_sz, c_i, c_i, c_f, c_i, c_vp, c_vp]),
+    "slfp_gather_quantize_runs_f16": (c_i, [c_vp, c_i, c_sz, c_i, c_i, c_i, c_f, c_i, c_vp, c_vp]),
+    "slfp_magic_u32": (None, [ctypes.c_uint, ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint)]),
     "slfp_absmax_f32": (c_i, [c_vp, c_sz, c_vp, c_i, c_vp]),
     "slfp_conv_wpitch": (c_sz, [ctypes.POINTER(SlfpConvDesc)]),
     "slfp_prepare_weights": (c_i, [ctypes.POINTER(SlfpConvDesc), c_vp, c_ll, c_ll, c_ll, c_ll, c_f, c_i, c_vp, c_vp,
@@ -80,7 +88,7 @@ _lib = None
 # Every entry point that launches kernels on the caller's stream.  The proxy below counts those calls
 # (bench.py reports them as `gpu_launches`) and, when a profile dict is installed, brackets each call
 # with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
-_LAUNCHING = {"slfp_gather_quantize_f16", "slfp_quantize_dyn_f32", "slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
+_LAUNCHING = {"slfp_gather_quantize_runs_f16", "slfp_gather_quantize_f16", "slfp_quantize_dyn_f32", "slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
               "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_conv2d_bwd_ws", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
               "slfp_avgpool_nhwc", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32"}
 launch_count = 0

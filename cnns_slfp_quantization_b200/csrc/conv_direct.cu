@@ -40,13 +40,13 @@ __device__ __forceinline__ void epilogue_store(const SlfpEpilogue& e, float t, s
     if (e.y_f16) reinterpret_cast<__half*>(e.y_f16)[off] = __float2half_rn(t);
     if (e.y_codes) {
         const float q = div_rn(t, e.next_k_div);
-        e.y_codes[pix * e.k_phys_out + k] =
-            (uint8_t)((e.next_fmt == SLFP_FMT_SFP33) ? encode<SLFP_FMT_SFP33>(q) : encode<SLFP_FMT_SLFP34_ACT>(q));
+        e.y_codes[pix * e.k_phys_out + k] = (uint8_t)(e.next_fmt == SLFP_FMT_E4M3 ? encode_e4m3(q)
+            : (e.next_fmt == SLFP_FMT_SFP33) ? encode<SLFP_FMT_SFP33>(q) : encode<SLFP_FMT_SLFP34_ACT>(q));
     }
     if (e.y_codes2) {
         const float q = div_rn(t, e.next_k_div2);
-        e.y_codes2[pix * e.k_phys_out + k] =
-            (uint8_t)((e.next_fmt == SLFP_FMT_SFP33) ? encode<SLFP_FMT_SFP33>(q) : encode<SLFP_FMT_SLFP34_ACT>(q));
+        e.y_codes2[pix * e.k_phys_out + k] = (uint8_t)(e.next_fmt == SLFP_FMT_E4M3 ? encode_e4m3(q)
+            : (e.next_fmt == SLFP_FMT_SFP33) ? encode<SLFP_FMT_SFP33>(q) : encode<SLFP_FMT_SLFP34_ACT>(q));
     }
 }
 
@@ -109,6 +109,9 @@ struct DwFastParams {
     int N, H, W, Cp, C, R, S, sh, sw, ph, pw, dh, dw, Ho, Wo;
     int act_fmt, wgt_sfp33, out_sfp33;
     int out_signed;            // 1: SLFP_FMT_SFP33_SFAST (no ReLU: sign bit + 7-bit magnitude code), 0: post-ReLU codes
+    int out_e4m3;              // 1: SLFP_FMT_E4M3 (round-half-even e4m3 bytes; `relu` tells whether a ReLU precedes)
+    int relu;
+    float rk;                  // 1 / Ka_next
     const float* ch_mul;
     const float* ch_add;
     float sc;                  // 1 / (16 Ka_next)
@@ -192,7 +195,12 @@ __global__ void __launch_bounds__(256) dwconv_fast_kernel(const DwFastParams p) 
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.ch_add + c0) + g);
             const float v0 = fmaf(acc[4 * g + 0], m4.x, a4.x), v1 = fmaf(acc[4 * g + 1], m4.y, a4.y);
             const float v2 = fmaf(acc[4 * g + 2], m4.z, a4.z), v3 = fmaf(acc[4 * g + 3], m4.w, a4.w);
-            if (p.out_signed) {
+            if (p.out_e4m3) {
+                const uint32_t lo = p.relu ? encode_e4m3x2_relu(v0 * p.rk, v1 * p.rk) : encode_e4m3x2(v0 * p.rk, v1 * p.rk);
+                const uint32_t hi = p.relu ? encode_e4m3x2_relu(v2 * p.rk, v3 * p.rk) : encode_e4m3x2(v2 * p.rk, v3 * p.rk);
+                tq[4 * g + 0] = (int32_t)(lo & 0xffu); tq[4 * g + 1] = (int32_t)(lo >> 8);
+                tq[4 * g + 2] = (int32_t)(hi & 0xffu); tq[4 * g + 3] = (int32_t)(hi >> 8);
+            } else if (p.out_signed) {
                 const float vv[4] = {v0, v1, v2, v3};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -222,7 +230,8 @@ __global__ void __launch_bounds__(256) dwconv_fast_kernel(const DwFastParams p) 
 // Both forms hold 64 accumulators in 128 registers (two CTAs = 16 warps per SM, one resident wave): VEC = 4 is 4 outputs x 16
 // channels (16-byte vectors); VEC = 2 is 8 channels (8-byte vectors) x 8 outputs at stride 1 (3.75 instead of 4.5 table decodes and
 // half the weight reads per output) or x 4 outputs at stride 2 (no spills, where the 16-channel form spills its 9-column window).
-template <int STRIDE, int VEC>
+// OUT: 0 = post-ReLU fast codes, 1 = signed fast SFP<3,3>, 2 = e4m3 bytes (compile-time: the run-time form spilled)
+template <int STRIDE, int VEC, int OUT>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastParams p) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(dsm);
@@ -320,19 +329,33 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
         for (int g = 0; g < VEC; ++g) {
             m4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_mul + c0) + g);
             a4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_add + c0) + g);
+            if ((OUT == 2)) {                                   // fold 1 / Ka_next into the affine: one FFMA yields the quotient
+                m4[g].x *= p.rk; m4[g].y *= p.rk; m4[g].z *= p.rk; m4[g].w *= p.rk;
+                a4[g].x *= p.rk; a4[g].y *= p.rk; a4[g].z *= p.rk; a4[g].w *= p.rk;
+            }
         }
         const size_t pix0 = ((size_t)n * p.Ho + ho) * p.Wo + wo0;
 #pragma unroll
         for (int o = 0; o < kOut; ++o) {
             if (wo0 + o >= p.Wo) break;
             int32_t tq[CH];
+            uint32_t e4w[VEC];
 #pragma unroll
             for (int g = 0; g < VEC; ++g) {
                 const float mm[4] = {m4[g].x, m4[g].y, m4[g].z, m4[g].w}, aa[4] = {a4[g].x, a4[g].y, a4[g].z, a4[g].w};
+                if ((OUT == 2)) {
+                    float y4[4];                                // (m4 / a4 carry 1 / Ka_next: see above)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) y4[e] = fmaf(acc[o][4 * g + e], mm[e], aa[e]);
+                    const uint32_t lo = p.relu ? encode_e4m3x2_relu(y4[0], y4[1]) : encode_e4m3x2(y4[0], y4[1]);
+                    const uint32_t hi = p.relu ? encode_e4m3x2_relu(y4[2], y4[3]) : encode_e4m3x2(y4[2], y4[3]);
+                    e4w[g] = lo | (hi << 16);
+                    continue;
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float y = fmaf(acc[o][4 * g + e], mm[e], aa[e]);
-                    if (p.out_signed) {                 // sign bit + min(code(|y|), 127); a negative zero keeps magnitude code 0
+                    if ((OUT == 1)) {                 // sign bit + min(code(|y|), 127); a negative zero keeps magnitude code 0
                         const int32_t m = ((int32_t)__float_as_uint(__saturatef(fabsf(y) * p.sc)) >> 19) - 0x76F;
                         tq[4 * g + e] = (m < 0 ? 0 : (m > 127 ? 127 : m)) | (int32_t)((__float_as_uint(y) >> 24) & 0x80u);
                     } else {
@@ -346,8 +369,20 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
                 for (int j = 0; j < CH; ++j) tq[j] = (c0 + j < p.C) ? tq[j] : 0;
             }
             uint32_t pk[VEC];
+            if ((OUT == 2)) {
+#pragma unroll
+                for (int g = 0; g < VEC; ++g) {
+                    pk[g] = e4w[g];
+                    if (pad_channels) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c0 + 4 * g + e >= p.C) pk[g] &= ~(0xffu << (8 * e));
+                    }
+                }
+            } else {
 #pragma unroll
             for (int g = 0; g < VEC; ++g) pk[g] = ptx::pack_sat_u8x4(tq[4 * g], tq[4 * g + 1], tq[4 * g + 2], tq[4 * g + 3]);
+            }
             uint8_t* dst = p.y + (pix0 + o) * p.Cp + c0;
             if (VEC == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[VEC - 2], pk[VEC - 1]);
             else *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[1]);
@@ -403,7 +438,8 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd(grouped): asymmetric padding is a dense-path feature");
     {
         // fused-pipeline depthwise: folded affine + ReLU + post-ReLU codes only, 16-channel vectors
-        const bool sfast = epi->next_fmt == SLFP_FMT_SFP33_SFAST && !epi->relu;
+        const bool e4 = epi->next_fmt == SLFP_FMT_E4M3;
+        const bool sfast = (epi->next_fmt == SLFP_FMT_SFP33_SFAST && !epi->relu) || e4;
         const bool relu_out = (epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU) && epi->relu;
         const bool dw = d->groups == d->c && d->k == d->c;
         const size_t smem = 256 * 32 * 4 + (size_t)d->r * d->s * d->c_phys * 4;
@@ -416,9 +452,12 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
             q.sh = d->stride_h; q.sw = d->stride_w; q.ph = d->pad_h; q.pw = d->pad_w; q.dh = d->dil_h; q.dw = d->dil_w;
             q.Ho = p.Ho; q.Wo = p.Wo;
             q.act_fmt = d->fmt;
-            q.wgt_sfp33 = (d->fmt == SLFP_FMT_SFP33 || d->fmt == SLFP_FMT_SFP33_RELU || d->fmt == SLFP_FMT_SFP33_SFAST) ? 1 : 0;    // weights: the q_bit's weight format
+            q.wgt_sfp33 = (d->fmt == SLFP_FMT_SFP33 || d->fmt == SLFP_FMT_SFP33_RELU || d->fmt == SLFP_FMT_SFP33_SFAST || d->fmt == SLFP_FMT_E4M3) ? 1 : 0;    // weights: the q_bit's weight format
             q.out_sfp33 = (epi->next_fmt == SLFP_FMT_SFP33_RELU || sfast) ? 1 : 0;
-            q.out_signed = sfast ? 1 : 0;
+            q.out_signed = (sfast && !e4) ? 1 : 0;
+            q.out_e4m3 = e4 ? 1 : 0;
+            q.relu = epi->relu;
+            q.rk = (float)(1.0 / (double)epi->next_k_div);
             q.ch_mul = epi->ch_mul; q.ch_add = epi->ch_add;
             q.sc = (float)(1.0 / (16.0 * (double)epi->next_k_div));
             q.y = epi->y_codes;
@@ -442,30 +481,30 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
                 if (!vec) {
                     const char* ev = getenv("SLFP_DW_VEC");
                     vec = (ev && ev[0] == '4') ? 4 : 2;
-                    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-                    if (e != cudaSuccess) { vec = 0; return set_error((int)e, "dwconv3x3_strip: smem attribute: %s", cudaGetErrorString(e)); }
                 }
-                // exactly one resident wave: the occupancy the kernel really gets with this layer's shared memory
-                int per_sm = 0;
-                cudaError_t eo;
-                if (vec == 4) eo = d->stride_h == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<1, 4>, 256, smem)
-                                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<2, 4>, 256, smem);
-                else eo = d->stride_h == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<1, 2>, 256, smem)
-                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv3x3_strip_kernel<2, 2>, 256, smem);
-                if (eo != cudaSuccess || per_sm < 1) return set_error((int)eo, "dwconv3x3_strip: occupancy query failed");
+                const int om = q.out_e4m3 ? 2 : (q.out_signed ? 1 : 0);
                 const int k_out = (vec == 2 && d->stride_h == 1) ? 8 : 4;                     // kOut of the kernel
                 const size_t tot4 = (size_t)d->n * p.Ho * ((p.Wo + k_out - 1) / k_out) * (d->c_phys / (4 * vec));
-                const int g4 = (int)min((size_t)num_sms() * per_sm, ceil_div_sz(tot4, 256));
-                if (vec == 4) {
-                    if (d->stride_h == 1) dwconv3x3_strip_kernel<1, 4><<<g4, 256, smem, st>>>(q);
-                    else dwconv3x3_strip_kernel<2, 4><<<g4, 256, smem, st>>>(q);
-                } else {
-                    if (d->stride_h == 1) dwconv3x3_strip_kernel<1, 2><<<g4, 256, smem, st>>>(q);
-                    else dwconv3x3_strip_kernel<2, 2><<<g4, 256, smem, st>>>(q);
+                // exactly one resident wave: the occupancy the kernel really gets with this layer's shared memory
+#define SLFP_STRIP(S_, V_, O_)                                                                                          \
+                if (d->stride_h == S_ && vec == V_ && om == O_) {                                                       \
+                    auto kern = dwconv3x3_strip_kernel<S_, V_, O_>;                                                     \
+                    static bool attr = false;                                                                           \
+                    if (!attr) {                                                                                        \
+                        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)); \
+                        if (e != cudaSuccess) return set_error((int)e, "dwconv3x3_strip: smem attribute: %s", cudaGetErrorString(e)); \
+                        attr = true;                                                                                    \
+                    }                                                                                                   \
+                    int per_sm = 0;                                                                                     \
+                    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);            \
+                    if (eo != cudaSuccess || per_sm < 1) return set_error((int)eo, "dwconv3x3_strip: occupancy query failed"); \
+                    const int g4 = (int)min((size_t)num_sms() * per_sm, ceil_div_sz(tot4, 256));                       \
+                    kern<<<g4, 256, smem, st>>>(q);                                                                     \
+                    return check_launch("dwconv3x3_strip_kernel");                                                      \
                 }
+                SLFP_STRIP(1, 2, 0) SLFP_STRIP(1, 2, 1) SLFP_STRIP(1, 2, 2) SLFP_STRIP(2, 2, 0) SLFP_STRIP(2, 2, 1) SLFP_STRIP(2, 2, 2)
+                SLFP_STRIP(1, 4, 0) SLFP_STRIP(1, 4, 1) SLFP_STRIP(1, 4, 2) SLFP_STRIP(2, 4, 0) SLFP_STRIP(2, 4, 1) SLFP_STRIP(2, 4, 2)
+#undef SLFP_STRIP
                 return check_launch("dwconv3x3_strip_kernel");
             }
             if (d->r == 3 && d->s == 3) dwconv_fast_kernel<9><<<g, 256, smem, st>>>(q);

@@ -77,6 +77,7 @@ struct Params {
     int act_fmt;
     int plain_1x1;              // 1x1 / stride 1 / no padding: the code tile is a plain 2-D tile of the [M, C] matrix
     int nkb1;                   // K blocks taken from input 1 (== num_kb unless a second input is concatenated along K)
+    int e4m3_out;               // next_fmt == SLFP_FMT_E4M3: quantize-on-store writes e4m3 bytes (round-half-even)
     int kb_base;                // K blocks of ONE pass over K (== num_kb; num_kb / 3 in the split-operand mode)
     int w_lo_col;               // split-operand mode: first column of the lo weights inside a weight row (= the row pitch)
     int sh2, sw2;               // second input (fused downsample branch): 1x1, stride (sh2, sw2), no padding, Cp % 64 == 0
@@ -87,18 +88,22 @@ struct Params {
     float sc1, sc2;             // rk / 16 (fast paths quantize clamp(q/16, 0, 1))
 };
 
-template <int BLOCK_N, bool STG = false>
+// NODEC (SLFP_CONV_E4M3_OPERANDS): activation codes and weights are e4m3 bytes - the TMA-loaded code tile IS the A
+// operand of tcgen05.mma kind::f8f6f4 (64-byte swizzle, two K = 32 instructions per 64-channel K block): no decode
+// table, no decode warps, no A staging; the code ring and the weight ring share one barrier pair per stage.
+template <int BLOCK_N, bool STG = false, bool NODEC = false>
 struct Cfg {
     // BLOCK_N <= 128: the decoded A tile goes to TENSOR memory (tcgen05.st; the MMA reads A from TMEM), which takes
     // the A tile's write (16 KB) and the MMA's read of it (16 KB) per K block off the shared-memory pipe - the
     // measured bottleneck of the decode-heavy layers (profiles/r01_conv_v2.md).  BLOCK_N = 256 needs all 512 TMEM
     // columns for the double-buffered accumulator and keeps the A tile in shared memory.
-    static constexpr bool kATmem = BLOCK_N <= 128;
-    static constexpr int kBBytes = BLOCK_N * kBK * 2;
+    static constexpr bool kATmem = !NODEC && BLOCK_N <= 128;
+    static constexpr int kBBytes = NODEC ? BLOCK_N * kBK : BLOCK_N * kBK * 2;
     // Ring depths.  The code tiles and weight tiles arrive through TMA with ~1.5-2 us of latency under load; the
     // first version's 4 x 8 KB of codes in flight per SM left the decode warps waiting on the code barrier most
     // of the time (profiles/r01_conv_v2.md).  With A in TMEM the freed shared memory deepens both rings.
-    static constexpr int kStages = (BLOCK_N >= 256 || STG) ? 3 : 4;          // weight (and A) stages
+    static constexpr int kStages = NODEC ? ((BLOCK_N >= 256 || STG) ? 6 : 8)
+                                         : ((BLOCK_N >= 256 || STG) ? 3 : 4);          // weight (and A) stages
     // The code ring depth must be a MULTIPLE of the number of decode groups (2 or 4), so that a code stage is always
     // consumed by the same group: TMA loads of different stages may land out of order, and a group that moved on to
     // K block j + CS while the load of K block j (same stage, other group) was still in flight would find the stage's
@@ -113,8 +118,59 @@ struct Cfg {
     static constexpr int kATmemCol = 2 * BLOCK_N;           // first TMEM column of the A ring (32 columns per stage)
     static constexpr int kTmemCols = kATmem ? (2 * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
     static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
-    static constexpr int kSmemBytes = kStages * ((kATmem ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kStageBytes + kLutBytes + kParBytes + 1024;
+    static constexpr int kLutB = NODEC ? 0 : kLutBytes;
+    static constexpr int kSmemBytes = kStages * (((kATmem || NODEC) ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kStageBytes + kLutB + kParBytes + 1024;
 };
+
+// sixteen relu'd values -> sixteen codes.  fast: the post-ReLU formats (saturating scale, re-based bit pattern, pack).
+// exact: the signed quantizer formats through the exact encoder (IEEE quotient, round-half-even) - used after
+// quantize_layerout, whose 5-bit values divided by a scale that is itself max / 15.5 of such values land EXACTLY on
+// rounding ties of the next grid (e.g. v = vmax / 2 -> 7.75), where the fast formats' ties-up would differ from the
+// reference's round-half-even on a visible share of the elements instead of a sliver.
+template <bool SFP33>
+__device__ __forceinline__ uint4 encode16_fast(const float (&v)[16], float sc) {
+    int32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i] * sc));
+    return make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
+                      ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
+}
+// sixteen values -> sixteen e4m3 bytes (SLFP_FMT_E4M3): exact quotient, the reference's clamps, round-half-even in the cvt
+__device__ __forceinline__ uint4 encode16_e4m3(const float (&v)[16], const DivK& kd, bool relu) {
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float a = relu ? fmaxf(v[2 * i], 0.0f) : v[2 * i], b = relu ? fmaxf(v[2 * i + 1], 0.0f) : v[2 * i + 1];
+        h[i] = encode_e4m3x2(div_k_fused(a, kd), div_k_fused(b, kd));
+    }
+    return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+}
+// fast forms for the fused epilogues that end in a ReLU: q = v * rk (reciprocal multiply like the other fast formats;
+// rk = 1 when the affine vectors were pre-scaled), ReLU folded into the low clamp
+__device__ __forceinline__ uint4 encode16_e4m3_relu(const float (&v)[16], float rk) {
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = encode_e4m3x2_relu(v[2 * i] * rk, v[2 * i + 1] * rk);
+    return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+}
+__device__ __forceinline__ uint4 encode16_e4m3_relu_prescaled(const float (&v)[16]) {
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = encode_e4m3x2_relu(v[2 * i], v[2 * i + 1]);
+    return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+}
+template <bool SFP33>
+__device__ __forceinline__ uint4 encode16_exact(const float (&v)[16], const DivK& kd) {
+    uint32_t c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        c[i] = SFP33 ? encode_relu<SLFP_FMT_SFP33>(div_k_fused(v[i], kd)) : encode_relu<SLFP_FMT_SLFP34_ACT>(div_k_fused(v[i], kd));
+    uint32_t pk[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        pk[g] = __byte_perm(__byte_perm(c[4 * g], c[4 * g + 1], 0x0040), __byte_perm(c[4 * g + 2], c[4 * g + 3], 0x0040), 0x5410);
+    return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
 
 // ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
 template <int BLOCK_N, int G>
@@ -256,7 +312,17 @@ __device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_
                 uint8_t* yc = pass ? e.y_codes2 : e.y_codes;
                 if (!yc) continue;
                 uint32_t pk[4];
-                if (fast_codes) {
+                if (p.e4m3_out) {
+                    const uint4 q4 = encode16_e4m3(v, pass ? p.next_div2 : p.next_div, false);     // v is already relu'd when asked
+                    pk[0] = q4.x; pk[1] = q4.y; pk[2] = q4.z; pk[3] = q4.w;
+                    if (!full) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+#pragma unroll
+                            for (int bte = 0; bte < 4; ++bte)
+                                if (n0 + 4 * g + bte >= Kout) pk[g] &= ~(0xffu << (8 * bte));     // zero code in pad channels
+                    }
+                } else if (fast_codes) {
                     // post-ReLU codes (v >= +0 here: the host requires relu for these formats): re-based
                     // rounded bit pattern, saturating pack.  slfp_common.cuh encode_relu_fast.
                     const float rk = pass ? p.rk2 : p.rk1;
@@ -322,32 +388,6 @@ __device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_
 // (tools/ubench/store_pattern.cu).  Lane pairs therefore swap one 16-byte piece (4 SHFL) so that every store
 // instruction writes 32 contiguous bytes per row: lanes 2i / 2i+1 hold pieces (A, B) = 32 contiguous bytes of
 // rows 2i / 2i+1; afterwards `first` belongs to row 2i and `second` to row 2i+1, both at piece index lane & 1.
-// sixteen relu'd values -> sixteen codes.  fast: the post-ReLU formats (saturating scale, re-based bit pattern, pack).
-// exact: the signed quantizer formats through the exact encoder (IEEE quotient, round-half-even) - used after
-// quantize_layerout, whose 5-bit values divided by a scale that is itself max / 15.5 of such values land EXACTLY on
-// rounding ties of the next grid (e.g. v = vmax / 2 -> 7.75), where the fast formats' ties-up would differ from the
-// reference's round-half-even on a visible share of the elements instead of a sliver.
-template <bool SFP33>
-__device__ __forceinline__ uint4 encode16_fast(const float (&v)[16], float sc) {
-    int32_t t[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i] * sc));
-    return make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
-                      ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
-}
-template <bool SFP33>
-__device__ __forceinline__ uint4 encode16_exact(const float (&v)[16], const DivK& kd) {
-    uint32_t c[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        c[i] = SFP33 ? encode_relu<SLFP_FMT_SFP33>(div_k_fused(v[i], kd)) : encode_relu<SLFP_FMT_SLFP34_ACT>(div_k_fused(v[i], kd));
-    uint32_t pk[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-        pk[g] = __byte_perm(__byte_perm(c[4 * g], c[4 * g + 1], 0x0040), __byte_perm(c[4 * g + 2], c[4 * g + 3], 0x0040), 0x5410);
-    return make_uint4(pk[0], pk[1], pk[2], pk[3]);
-}
-
 __device__ __forceinline__ void pair_exchange(const uint4& A, const uint4& B, bool odd, uint4& first, uint4& second) {
     uint4 send, recv;
     send.x = odd ? A.x : B.x; send.y = odd ? A.y : B.y; send.z = odd ? A.z : B.z; send.w = odd ? A.w : B.w;
@@ -420,7 +460,9 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
                 v[4 * g + 2] = fmaf(__uint_as_float(acc[o + 4 * g + 2]), m4.z, a4.z);
                 v[4 * g + 3] = fmaf(__uint_as_float(acc[o + 4 * g + 3]), m4.w, a4.w);
             }
-            if (MODE == 1) {
+            if (MODE == 1 && p.e4m3_out) {
+                pk1[o / 16] = encode16_e4m3_relu_prescaled(v);       // the staged affine carries 1 / Ka_next
+            } else if (MODE == 1) {
                 int32_t t[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i]));
@@ -455,8 +497,9 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     if ((pass ? yc2 : yc1) == nullptr) continue;
-                    const uint4 pk = p.epi.layerout ? encode16_exact<SFP33>(v, pass ? p.next_div2 : p.next_div)
-                                                    : encode16_fast<SFP33>(v, pass ? sc2 : sc1);
+                    const uint4 pk = p.e4m3_out ? encode16_e4m3_relu(v, pass ? p.rk2 : p.rk1)
+                                     : p.epi.layerout ? encode16_exact<SFP33>(v, pass ? p.next_div2 : p.next_div)
+                                                      : encode16_fast<SFP33>(v, pass ? sc2 : sc1);
                     if (pass) pk2[o / 16] = pk; else pk1[o / 16] = pk;
                 }
             }
@@ -536,7 +579,9 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
             v[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), m4.w, a4.w);
         }
         uint4 pk1, pk2 = make_uint4(0u, 0u, 0u, 0u);
-        if (MODE == 1) {
+        if (MODE == 1 && p.e4m3_out) {
+            pk1 = encode16_e4m3_relu_prescaled(v);                   // the staged affine carries 1 / Ka_next
+        } else if (MODE == 1) {
             int32_t t[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i]));
@@ -572,8 +617,9 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 if ((pass ? yc2 : yc1) == nullptr) continue;
-                const uint4 pk = p.epi.layerout ? encode16_exact<SFP33>(v, pass ? p.next_div2 : p.next_div)
-                                                : encode16_fast<SFP33>(v, pass ? sc2 : sc1);
+                const uint4 pk = p.e4m3_out ? encode16_e4m3_relu(v, pass ? p.rk2 : p.rk1)
+                                 : p.epi.layerout ? encode16_exact<SFP33>(v, pass ? p.next_div2 : p.next_div)
+                                                  : encode16_fast<SFP33>(v, pass ? sc2 : sc1);
                 if (pass) pk2 = pk; else pk1 = pk;
             }
         }
@@ -607,11 +653,12 @@ struct OutMaps {
 // HIFI (SLFP_CONV_SPLIT_OPERANDS): three passes over K into the same accumulator - pass 0: x_hi * w_hi, pass 1: x_hi * w_lo,
 // pass 2: x_lo * w_hi - with (hi, lo) the float16 pair of a value.  The decode table holds hi in the low and lo in the
 // high half of an entry, the decode warps pick the half per K block; the weight rows are [hi | lo].
-template <int BLOCK_N, int GRAN, int DW, bool STG, bool HIFI = false>
+template <int BLOCK_N, int GRAN, int DW, bool STG, bool HIFI = false, bool NODEC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ OutMaps omaps, const Params p) {
-    using C = Cfg<BLOCK_N, STG>;
+    using C = Cfg<BLOCK_N, STG, NODEC>;
+    static_assert(!NODEC || (GRAN == 64 && !HIFI), "e4m3 operands: whole 64-channel K blocks");
     static_assert(!STG || (BLOCK_N == 128 && DW == 8 && GRAN == 64), "staged epilogue: 128-column tiles, 16 epilogue warps");
     static_assert(!HIFI || !STG, "the split-operand mode uses the generic epilogue");
     using R = Roles<DW>;
@@ -623,11 +670,11 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // this kernel is then a compile-time offset and the table look-up needs no base-address add.
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_a = smem;                                   // [stages][128 rows][128 B]   (absent when A lives in TMEM)
-    uint8_t* s_b = s_a + (C::kATmem ? 0 : C::kStages * kABytes);   // [stages][BLOCK_N rows][128 B]
+    uint8_t* s_b = s_a + ((C::kATmem || NODEC) ? 0 : C::kStages * kABytes);   // [stages][BLOCK_N rows][128 B] (NODEC: 64 B)
     uint8_t* s_code = s_b + C::kStages * C::kBBytes;       // [kCodeStages][128 pixels][64 B]
     uint8_t* s_stage = s_code + kCodeStages * kCodeBytes;  // STG: [2][4 groups][128][64 B] float16 + [2][4][128][32 B] codes
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stage + C::kStageBytes);
-    float* s_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_lut) + kLutBytes);   // [2][BLOCK_N]
+    float* s_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_lut) + C::kLutB);   // [2][BLOCK_N]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + C::kParBytes);
     uint64_t* bar_cfull = s_bar;                           // [kCodeStages]  1 arrive.expect_tx
     uint64_t* bar_cempty = bar_cfull + kCodeStages;        // [kCodeStages]  8 decode warps
@@ -650,7 +697,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();     // would break the swizzle: fail loudly, never silently
 
     // ---- one-time setup ---------------------------------------------------------------------------
-    for (int i = tid; i < 256 * 32; i += kThreads) {
+    for (int i = tid; i < (NODEC ? 0 : 256 * 32); i += kThreads) {
         const float f = decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac);
         const __half hi = __float2half_rn(f);
         uint32_t e = (uint32_t)__half_as_ushort(hi);
@@ -666,7 +713,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             ptx::mbar_init(ptx::smem_u32(&bar_cempty[s]), kDecGroupWarps);   // the warps of one decode group
         }
         for (int s = 0; s < C::kStages; ++s) {
-            ptx::mbar_init(ptx::smem_u32(&bar_full[s]), kDecGroupWarps + 1);  // decode group + the weight TMA's arrive
+            ptx::mbar_init(ptx::smem_u32(&bar_full[s]), NODEC ? 1 : kDecGroupWarps + 1);  // decode group + the weight TMA's arrive (NODEC: one producer)
             ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -734,12 +781,14 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         if (++cs == (uint32_t)kCodeStages) { cs = 0; cphase ^= 1u; }
                         continue;
                     }
-                    PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_cempty[cs]), cphase ^ 1u, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
-                    const uint32_t full = ptx::smem_u32(&bar_cfull[cs]);
+                    PROF(a, ptx::mbar_wait(ptx::smem_u32(NODEC ? &bar_empty[cs] : &bar_cempty[cs]), cphase ^ 1u, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
+                    const uint32_t full = ptx::smem_u32(NODEC ? &bar_full[cs] : &bar_cfull[cs]);
                     const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
                     if (GRAN == 64) {
                         if (ptx::elect_one()) {
-                            ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes);
+                            ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes + (NODEC ? (uint32_t)C::kBBytes : 0u));
+                            if (NODEC)                  // the e4m3 weight tile of this K block rides on the same barrier
+                                ptx::tma_load_2d(ptx::smem_u32(s_b + cs * C::kBBytes), &tmap_w, full, kbt * kBK, (tile % p.n_tiles) * BLOCK_N);
                             if (kb >= p.nkb1)           // concatenated second input: 1x1 window at (ho*sh2, wo*sw2)
                                 ptx::tma_load_im2col_4d(dst, &tmap_x2, full, (kb - p.nkb1) * 64, wo * p.sw2, ho * p.sh2, n, 0, 0);
                             else if (p.plain_1x1) ptx::tma_load_2d(dst, &tmap_x, full, cb * 64, (int)m0);
@@ -777,7 +826,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             // the space-to-depth stem, at 4 code loads + 1 weight load per K block, ran exactly at that floor.
             const bool w_res = !HIFI && p.n_tiles == 1 && p.num_kb <= C::kStages && (C::kStages % p.num_kb) == 0;
             uint32_t issued = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
+            for (int ti = 0; ti < (NODEC ? 0 : my_tiles); ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const int n0 = (tile % p.n_tiles) * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb, ++issued) {
@@ -809,8 +858,9 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         // per K block) made this thread the slowest stage of the pipeline - 51 % of its life between the first MMA
         // and the commit of a K block (tools/role_profile.py).  Descriptors differ only in their low word.
         constexpr uint32_t idesc = ptx::make_idesc(0u, kBM, BLOCK_N);
-        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
-        const uint32_t a_lo0 = ((ptx::smem_u32(s_a) >> 4) & 0x3fffu) | (1u << 16);
+        constexpr uint32_t kDescHi = NODEC ? ((512u >> 4) | (1u << 14) | (4u << 29))      // SBO 512 B, version 1, SWIZZLE_64B
+                                           : ((1024u >> 4) | (1u << 14) | (2u << 29));    // SBO 1024 B, version 1, SWIZZLE_128B
+        const uint32_t a_lo0 = ((ptx::smem_u32(NODEC ? s_code : s_a) >> 4) & 0x3fffu) | (1u << 16);
         const uint32_t b_lo0 = ((ptx::smem_u32(s_b) >> 4) & 0x3fffu) | (1u << 16);
         PROF_VARS;
         uint32_t stage = 0, phase = 0;
@@ -826,13 +876,15 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const long long prof_t = clock64();
 #endif
                 if (ptx::elect_one()) {
-                    const uint32_t a_lo = a_lo0 + stage * (uint32_t)(kABytes >> 4);
+                    const uint32_t a_lo = a_lo0 + stage * (uint32_t)((NODEC ? kCodeBytes : kABytes) >> 4);
                     const uint32_t b_lo = b_lo0 + stage * (uint32_t)(C::kBBytes >> 4);
                     const uint32_t a_tmem = tmem_base + (uint32_t)C::kATmemCol + stage * 32u;
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
+                    for (int k = 0; k < (NODEC ? kBK / 32 : kBK / 16); ++k) {
                         const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + 2u * k);
-                        if (C::kATmem)
+                        if (NODEC)                      // e4m3 x e4m3, K = 32 per instruction: 32 bytes = 2 descriptor units per step
+                            ptx::mma_f8_ss(d_tmem, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * k), bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        else if (C::kATmem)
                             ptx::mma_f16_ts(d_tmem, a_tmem + k * 8, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         else
                             ptx::mma_f16_ss(d_tmem, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * k), bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -866,6 +918,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         constexpr int kQPW = 16 / kWarpsPerGroup;              // 16-channel quarters per warp: 4 or 2
         static_assert(kDecGroups <= C::kStages && kDecGroups <= kCodeStages, "groups may not outrun the barrier phases");
         static_assert(kCodeStages % kDecGroups == 0, "a code stage must always be consumed by the same decode group");
+        if constexpr (!NODEC) {
         const int grp = (warp - kDecWarp0) / kWarpsPerGroup;
         const int q0 = (((warp - kDecWarp0) % kWarpsPerGroup) >> 2) * kQPW;   // first quarter of this warp
         const int row = (warp & 3) * 32 + lane;
@@ -950,6 +1003,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
 #endif
         }
         if (warp == kDecWarp0 && lane == 0) { PROF_FLUSH(20); }
+        }  // !NODEC
     } else {
         ptx::setmaxnreg_inc<R::kRegsEpi>();
         // =========================== epilogue ===================================================================
@@ -969,7 +1023,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const int n_tile0 = (tile % p.n_tiles) * BLOCK_N;
                 if (n_tile0 != staged_n0) {
                     ptx::bar_sync(1, kEpiWarps * 32);          // every epilogue warp is done with the previous vectors
-                    const float sc = mode == 1 ? p.sc1 : 1.0f;      // mode 2 keeps relu(y) itself for the float16 output
+                    const float sc = mode == 1 ? (p.e4m3_out ? p.rk1 : p.sc1) : 1.0f;      // mode 2 keeps relu(y) itself for the float16 output
                     for (int i = etid; i < BLOCK_N; i += kEpiWarps * 32) {
                         const int n = n_tile0 + i;
                         s_par[i] = n < p.Kout ? __ldg(p.epi.ch_mul + n) * sc : 0.0f;
@@ -1099,6 +1153,11 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     for (int pass = 0; pass < 2; ++pass) {
                         if (!(pass ? has_c2 : has_c1)) continue;
                         const float sc = pass ? sc2 : sc1;
+                        if (p.e4m3_out) {
+                            const uint4 q4 = encode16_e4m3_relu(v, pass ? p.rk2 : p.rk1);
+                            cw[pass][ch][0] = q4.x; cw[pass][ch][1] = q4.y; cw[pass][ch][2] = q4.z; cw[pass][ch][3] = q4.w;
+                            continue;
+                        }
                         int32_t t[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i)      // encode_relu_fast_raw16 with run-time format constants
@@ -1184,10 +1243,10 @@ static PFN driver_fn(const char* name) {
     return nullptr;
 }
 
-template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false>
+template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false, bool NODEC = false>
 static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const OutMaps& om, const Params& p, cudaStream_t st) {
-    using C = Cfg<BLOCK_N, STG>;
-    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI>;
+    using C = Cfg<BLOCK_N, STG, NODEC>;
+    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI, NODEC>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -1251,13 +1310,17 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     using namespace v2;
     const bool fast = epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU;
     if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_RELU && d->fmt != SLFP_FMT_SFP33_RELU &&
-        d->fmt != SLFP_FMT_SFP33_SFAST)
+        d->fmt != SLFP_FMT_SFP33_SFAST && d->fmt != SLFP_FMT_E4M3)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: activation code format %d", d->fmt);
     if (epi->y_codes && (epi->k_phys_out % 16 != 0 || epi->k_phys_out < d->k))
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: k_phys_out=%d", epi->k_phys_out);
     if (epi->y_codes && fast && !epi->relu)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: post-ReLU code formats need relu=1");
-    if (epi->y_codes && !fast && epi->next_fmt != SLFP_FMT_SLFP34_ACT && epi->next_fmt != SLFP_FMT_SFP33)
+    const bool e4m3_out = epi->y_codes && epi->next_fmt == SLFP_FMT_E4M3;
+    const bool nodec = (d->flags & SLFP_CONV_E4M3_OPERANDS) != 0;
+    if (nodec && (d->fmt != SLFP_FMT_E4M3 || d->c_phys % 64 != 0 || (d->flags & SLFP_CONV_SPLIT_OPERANDS) || d2))
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: e4m3 operands need SLFP_FMT_E4M3 codes, c_phys %% 64 == 0, no split operands, no second input");
+    if (epi->y_codes && !fast && !e4m3_out && epi->next_fmt != SLFP_FMT_SLFP34_ACT && epi->next_fmt != SLFP_FMT_SFP33)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: next_fmt=%d", epi->next_fmt);
     if ((((uintptr_t)x_codes | (uintptr_t)w_f16 | (uintptr_t)epi->y_f32 | (uintptr_t)epi->y_f16 |
           (uintptr_t)epi->y_codes | (uintptr_t)epi->y_codes2) & 15u) != 0)
@@ -1305,20 +1368,21 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
 
     p.sc1 = (float)(1.0 / (16.0 * (double)(epi->y_codes ? epi->next_k_div : 1.0f)));
     p.sc2 = (float)(1.0 / (16.0 * (double)(epi->y_codes2 ? epi->next_k_div2 : 1.0f)));
+    p.e4m3_out = e4m3_out ? 1 : 0;
     p.epi_mode = 0;
     {
         static const bool no_fast = getenv("SLFP_EPI_GENERIC") != nullptr;
         // layerout: the fast epilogues implement relu(quantize_layerout(y)) with exact 0 -> 0 (layerout == 2); the reference's
         // NaN at exact 0 (layerout == 1) stays with the generic epilogue
         const bool common = !no_fast && epi->layerout != 1 && epi->ch_mul && epi->ch_add && epi->relu && d->k % 16 == 0 && !epi->y_f32 &&
-                            (!epi->y_codes || ((fast != (epi->layerout != 0)) && epi->k_phys_out == d->k && epi->next_k_div > 0.f)) &&
+                            (!epi->y_codes || ((e4m3_out || (fast != (epi->layerout != 0))) && epi->k_phys_out == d->k && epi->next_k_div > 0.f)) &&
                             (!epi->y_codes2 || (epi->y_codes && epi->next_k_div2 > 0.f)) &&
                             (!epi->residual || epi->residual_f16);
         if (common) p.epi_mode = (epi->y_codes && !epi->y_codes2 && !epi->y_f16 && !epi->residual && !epi->layerout) ? 1 : 2;
     }
     // Staged (TMA) epilogue for the epilogue-bound mode-2 layers (block tails, short-K fused tails): 128-column tiles.
     static const int stg_max_kb = getenv("SLFP_STG_MAXKB") ? atoi(getenv("SLFP_STG_MAXKB")) : 8;
-    const bool stg = !hifi && p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
+    const bool stg = !hifi && !nodec && p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
                      (((uintptr_t)epi->residual) & 15u) == 0;
     const int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
@@ -1332,11 +1396,13 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     CUtensorMap tmap_w, tmap_x;
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)wrow, (cuuint64_t)d->k};
-        const cuuint64_t gstr[1] = {(cuuint64_t)wrow * 2};
+        const cuuint64_t gstr[1] = {(cuuint64_t)wrow * (nodec ? 1 : 2)};
         const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult cr = enc_tiled(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_f16), gdim, gstr, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        // e4m3 operands: byte rows of 64 with the 64-byte swizzle (the layout of the code tiles); float16: 128-byte rows
+        CUresult cr = enc_tiled(&tmap_w, nodec ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_f16),
+                                gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                nodec ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled failed (%d)", (int)cr);
     }
@@ -1417,6 +1483,12 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     SLFP_V2_HIFI(128)
     SLFP_V2_HIFI(256)
 #undef SLFP_V2_HIFI
+    if (nodec) {
+        // no decode role: every non-control warp may as well help the epilogue (DW = 8: 16 epilogue warps)
+        if (bn == 64) return launch<64, 64, 8, false, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
+        if (bn == 128) return launch<128, 64, 8, false, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
+        return launch<256, 64, 8, false, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
+    }
 #define SLFP_V2_CASE(BN)                                                                                         \
     if (bn == BN) {                                                                                              \
         if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, tmap_x2, om, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, tmap_x2, om, p, st); \

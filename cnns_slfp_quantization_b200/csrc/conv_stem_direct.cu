@@ -26,7 +26,7 @@ struct StemParams {
     const float* ch_mul;
     const float* ch_add;
     int relu;
-    int out_mode;              // 0: post-ReLU fast codes, 1: signed fast SFP<3,3>, 2: exact signed encoder
+    int out_mode;              // 0: post-ReLU fast codes, 1: signed fast SFP<3,3>, 2: exact signed encoder, 3: e4m3 bytes
     int out_sfp33;
     uint8_t* y1;
     uint8_t* y2;
@@ -96,6 +96,21 @@ __global__ void __launch_bounds__(256) stem3x3_direct_kernel(const StemParams p)
 #pragma unroll
             for (int ch = 0; ch < (KP + 15) / 16; ++ch) {
                 uint32_t pk[4] = {0u, 0u, 0u, 0u};
+                if (p.out_mode == 3) {
+                    // e4m3 bytes: two values per cvt, 1 / Ka_next folded into the affine (KP % 8 == 0: whole pairs)
+                    const float rk = kd.rk;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const int k = ch * 16 + i;
+                        if (k >= KP) continue;
+                        const float v0 = fmaf(acc[k], s_mul[k] * rk, s_add[k] * rk), v1 = fmaf(acc[k + 1], s_mul[k + 1] * rk, s_add[k + 1] * rk);
+                        uint32_t two = p.relu ? encode_e4m3x2_relu(v0, v1) : encode_e4m3x2(v0, v1);
+                        if (k >= p.K) two = 0u; else if (k + 1 >= p.K) two &= 0xffu;
+                        pk[i >> 2] |= two << (8 * (i & 3));
+                    }
+                    if (ch * 16 < p.k_phys_out) *reinterpret_cast<uint4*>(dst + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    continue;
+                }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int k = ch * 16 + i;
@@ -106,6 +121,8 @@ __global__ void __launch_bounds__(256) stem3x3_direct_kernel(const StemParams p)
                     if (p.out_mode == 0) {
                         const int32_t m = ((int32_t)__float_as_uint(__saturatef(v * sc)) >> enc_shift) - enc_bias;
                         code = (uint32_t)(m < 0 ? 0 : (m > 255 ? 255 : m));
+                    } else if (p.out_mode == 3) {
+                        code = encode_e4m3(div_k_fused(v, kd));
                     } else if (p.out_mode == 1) {
                         const int32_t m = ((int32_t)__float_as_uint(__saturatef(fabsf(v) * sc)) >> 19) - 0x76F;
                         code = (uint32_t)(m < 0 ? 0 : (m > 127 ? 127 : m)) | ((__float_as_uint(v) >> 24) & 0x80u);
@@ -131,7 +148,7 @@ bool conv2d_fwd_stem_direct_supported(const SlfpConvDesc* d, const SlfpEpilogue*
     if (e->k_phys_out % 16 != 0 || e->k_phys_out < d->k || e->k_phys_out > 64) return false;
     const int f = e->next_fmt;
     if (f == SLFP_FMT_SLFP34_RELU || f == SLFP_FMT_SFP33_RELU) return e->relu != 0 && e->next_k_div > 0.f;
-    if (f == SLFP_FMT_SFP33_SFAST) return e->next_k_div > 0.f;
+    if (f == SLFP_FMT_SFP33_SFAST || f == SLFP_FMT_E4M3) return e->next_k_div > 0.f;
     return f == SLFP_FMT_SFP33 || f == SLFP_FMT_SLFP34_ACT;
 }
 
@@ -148,7 +165,7 @@ int conv2d_fwd_stem_direct(const SlfpConvDesc* d, const uint8_t* x_codes, const 
     p.act_fmt = d->fmt;
     p.ch_mul = e->ch_mul; p.ch_add = e->ch_add; p.relu = e->relu;
     const int f = e->next_fmt;
-    p.out_mode = (f == SLFP_FMT_SLFP34_RELU || f == SLFP_FMT_SFP33_RELU) ? 0 : (f == SLFP_FMT_SFP33_SFAST ? 1 : 2);
+    p.out_mode = (f == SLFP_FMT_SLFP34_RELU || f == SLFP_FMT_SFP33_RELU) ? 0 : (f == SLFP_FMT_SFP33_SFAST ? 1 : (f == SLFP_FMT_E4M3 ? 3 : 2));
     p.out_sfp33 = (f == SLFP_FMT_SFP33_RELU || f == SLFP_FMT_SFP33_SFAST || f == SLFP_FMT_SFP33) ? 1 : 0;
     p.y1 = e->y_codes; p.y2 = e->y_codes2; p.k_phys_out = e->k_phys_out;
     p.sc1 = (float)(1.0 / (16.0 * (double)e->next_k_div));

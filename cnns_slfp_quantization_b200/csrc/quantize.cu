@@ -47,6 +47,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w) : "memory");
@@ -557,23 +562,29 @@ __global__ void __launch_bounds__(256) quantize_nchw_s2d_c3_kernel(const float* 
 // thread = (four consecutive output channels, a lane of pixels): its four table entries (source pointer, pixel
 // stride, channel) stay in registers while it walks down the pixels of its CTA, so the inner loop is four 2-byte
 // gathers (consecutive channels of a run come from consecutive addresses of one source tensor: a warp's loads fall into
-// a few 128-byte lines), the table encoder and one 32-bit store per pixel; a warp's stores cover 128 contiguous bytes.
+// a few 128-byte lines) and one 32-bit store per pixel; a warp's stores cover 128 contiguous bytes.
+// The quantizer itself is ONE byte look-up per element: the sources are float16 tensors of post-layerout, post-ReLU
+// values (non-negative, <= 248), so every possible input bit pattern below 0x5C00 gets its code from a table the CTA
+// builds once with the exact encoder (IEEE division by K, round-half-even) - 23.5 KB of shared memory, persistent
+// CTAs.  Anything else (negative, > 248, Inf / NaN) takes the exact encoder directly.
 // Pad channels (>= c) get code 0.  c_phys <= 1024.
-constexpr int kGatherPix = 64;                                   // pixels per thread
-template <int FMT>
+constexpr int kGatherPix = 64;                                   // pixels per thread and CTA pass
+constexpr int kGatherLut = 0x5C00;                               // float16 bit patterns of [0, 256)
+template <int FMT, bool E4M3 = false>
 __global__ void __launch_bounds__(256) gather_quantize_kernel(const SlfpGatherChan* __restrict__ table, size_t npix, int C, int Cp,
                                                               DivK k_div, uint8_t* __restrict__ codes) {
-    constexpr bool kLut = FMT == SLFP_FMT_SFP33 || FMT == SLFP_FMT_SLFP34_ACT;
-    constexpr int FL = FMT == SLFP_FMT_SFP33 ? SLFP_FMT_SFP33 : SLFP_FMT_SLFP34_ACT;
-    __shared__ uint8_t s_enc[kLut ? kEncLutBytes : 16];
-    if (kLut) {
-        for (int i = threadIdx.x; i < kEncLutBytes; i += 256) s_enc[i] = (uint8_t)enc_lut_entry<FL>((uint32_t)i);
-        __syncthreads();
+    __shared__ uint8_t s_code[kGatherLut];
+    for (int i = threadIdx.x; i < kGatherLut; i += 256) {
+        const float v = __half2float(__ushort_as_half((unsigned short)i));
+        uint32_t code = encode<FMT>(div_k(v, k_div));
+        if (E4M3) code = sfp33_code_to_e4m3(code);                // the exact SFP<3,3> code, re-spelled as the e4m3 byte
+        s_code[i] = (uint8_t)code;
     }
+    __syncthreads();
     const int cq = Cp >> 2, lanes = 256 / cq;                     // channel quads per pixel; pixels a CTA handles at once
     const int q = (int)threadIdx.x % cq, pl = (int)threadIdx.x / cq;
     if (pl >= lanes) return;                                      // c_phys / 4 does not divide 256: the last threads idle
-    const __half* src[4];
+    const unsigned short* src[4];
     size_t stride[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -581,7 +592,7 @@ __global__ void __launch_bounds__(256) gather_quantize_kernel(const SlfpGatherCh
         src[j] = nullptr; stride[j] = 0;
         if (c < C) {
             const SlfpGatherChan t = table[c];
-            src[j] = reinterpret_cast<const __half*>(t.src) + t.ch;
+            src[j] = reinterpret_cast<const unsigned short*>(t.src) + t.ch;
             stride[j] = (size_t)t.stride;
         }
     }
@@ -595,13 +606,138 @@ __global__ void __launch_bounds__(256) gather_quantize_kernel(const SlfpGatherCh
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (src[j] != nullptr) {
-                    const float v = __half2float(src[j][pix * stride[j]]);
-                    const uint32_t code = kLut ? encode_elem_lut<FL>(v, k_div, s_enc) : encode<FMT>(div_k(v, k_div));
+                    const uint32_t hb = __ldg(src[j] + pix * stride[j]);
+                    uint32_t code;
+                    if (hb < (uint32_t)kGatherLut) {
+                        code = s_code[hb];
+                    } else {
+                        code = encode<FMT>(div_k(__half2float(__ushort_as_half((unsigned short)hb)), k_div));
+                        if (E4M3) code = sfp33_code_to_e4m3(code);
+                    }
                     word |= code << (8 * j);
                 }
             }
             *reinterpret_cast<uint32_t*>(codes + pix * (size_t)Cp + q * 4) = word;
         }
+    }
+}
+
+// ---- run-based gather + quantize (see include/slfp_b200.h) ----------------------------------------------------------
+// Two phases per CTA tile, both free of shared-memory bank conflicts (the byte-scatter form spent 80 % of its
+// shared-memory wavefronts on conflict replays, profiles/r02_config5.md):
+//   1. per run, the 16-byte aligned chunks (8 channels) that cover it are copied for every pixel of the tile into a
+//      staging region [pixel][chunks] - sector-aligned 128-bit loads, four in flight per thread, 128-bit stores;
+//   2. a thread owns one 32-bit word of the output (four consecutive logical channels of a pixel), reads its four
+//      float16 inputs from the staging regions through a per-channel (offset, pitch) table - lanes of a warp walk
+//      consecutive channels of a run, i.e. consecutive banks - encodes them and writes the word straight to global
+//      memory (a warp writes 128 contiguous bytes).
+// e4m3 output: clamps + cvt on the FMA / ALU pipes (reciprocal multiply like the other fused encoders); the other
+// formats: one byte look-up in a value -> code table the CTA builds with the exact encoder (sources are non-negative
+// float16 <= 248: post-layerout, post-ReLU tensors; anything else takes the exact encoder directly).
+constexpr int kRunStageBytes = 32768;
+constexpr int kRunMaxC = 1024;
+template <int FMT, bool E4M3>
+__global__ void __launch_bounds__(256) gather_runs_kernel(const SlfpGatherRun* __restrict__ runs, int n_runs, size_t npix, int C, int Cp,
+                                                          int tile_pix, DivK k_div, uint8_t* __restrict__ codes) {
+    __shared__ uint8_t s_code[E4M3 ? 16 : kGatherLut];
+    __shared__ __align__(16) uint8_t s_stage[E4M3 ? kRunStageBytes : kRunStageBytes / 2];     // (the table variants: 48 KB static limit)
+    __shared__ uint32_t s_chan[kRunMaxC];                        // per logical channel: staging offset (low 20 bits) | row pitch / 16 (high 12)
+    if (!E4M3) {
+        for (int i = threadIdx.x; i < kGatherLut; i += 256)
+            s_code[i] = (uint8_t)encode<FMT>(div_k(__half2float(__ushort_as_half((unsigned short)i)), k_div));
+    }
+    {   // staging layout: run r occupies [tile_pix][nck_r * 16 B] starting at off_r; channel table
+        int off = 0;
+        for (int r = 0; r < n_runs; ++r) {
+            const SlfpGatherRun run = runs[r];
+            const int c_lo = run.ch0 & ~7, nck = (((run.ch0 + run.len + 7) & ~7) - c_lo) >> 3;
+            for (int i = threadIdx.x; i < run.len; i += 256)
+                s_chan[run.dst_start + i * run.dst_step] = (uint32_t)(off + (run.ch0 - c_lo + i) * 2) | ((uint32_t)nck << 20);
+            off += tile_pix * nck * 16;
+        }
+    }
+    __syncthreads();
+    const float rk = k_div.rk;
+    const int cq = Cp >> 2;
+    const bool fixed_quad = cq <= 256 && (256 % cq) == 0;
+    const uint32_t my_lanes = fixed_quad ? 256u / (uint32_t)cq : 1u, my_w = threadIdx.x % (uint32_t)cq, my_pl = threadIdx.x / (uint32_t)cq;
+    uint32_t my_off[4] = {0u, 0u, 0u, 0u}, my_pitch[4] = {0u, 0u, 0u, 0u};        // pitch 0 = pad channel
+    if (fixed_quad) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int c = (int)my_w * 4 + jj;
+            if (c < C) { const uint32_t e = s_chan[c]; my_off[jj] = e & 0xfffffu; my_pitch[jj] = (e >> 20) << 4; }
+        }
+    }
+    for (size_t p0 = (size_t)blockIdx.x * tile_pix; p0 < npix; p0 += (size_t)gridDim.x * tile_pix) {
+        const int np = (int)(npix - p0 < (size_t)tile_pix ? npix - p0 : (size_t)tile_pix);
+        // ---- phase 1: stage the covering chunks of every run ----------------------------------------------------
+        int off = 0;
+        for (int r = 0; r < n_runs; ++r) {
+            const SlfpGatherRun run = runs[r];
+            const int c_lo = run.ch0 & ~7, nck = (((run.ch0 + run.len + 7) & ~7) - c_lo) >> 3;
+            const unsigned short* src = reinterpret_cast<const unsigned short*>(run.src) + c_lo;
+            const uint32_t total = (uint32_t)np * (uint32_t)nck;
+            constexpr int kFly = 4;
+            for (uint32_t base = threadIdx.x; base < total; base += 256 * kFly) {
+                uint4 v[kFly];
+#pragma unroll
+                for (int u = 0; u < kFly; ++u) {
+                    const uint32_t idx = base + (uint32_t)u * 256u;
+                    const uint32_t pp = nck == 1 ? idx : (__umulhi(idx, run.magic) >> run.shift), ck = idx - pp * (uint32_t)nck;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (idx < total) v[u] = ldg_stream_u4(reinterpret_cast<const uint4*>(src + (p0 + pp) * (size_t)run.stride) + ck);
+                }
+#pragma unroll
+                for (int u = 0; u < kFly; ++u) {
+                    const uint32_t idx = base + (uint32_t)u * 256u;
+                    if (idx < total) *reinterpret_cast<uint4*>(s_stage + off + idx * 16u) = v[u];      // [pixel][chunk]: idx itself
+                }
+            }
+            off += tile_pix * nck * 16;
+        }
+        __syncthreads();
+        // ---- phase 2: one output word per thread ---------------------------------------------------------------------
+        // (256 % cq == 0: a thread keeps its channel quad for the whole kernel - its four staging offsets and pitches
+        // were loaded once, the loop is four LDS.U16 + the encoder + one store per pixel)
+        auto emit = [&](uint32_t pp, uint32_t w, const uint32_t (&eo)[4], const uint32_t (&ep)[4]) {
+            float f[4];
+            uint32_t hb[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                hb[jj] = ep[jj] ? (uint32_t)*reinterpret_cast<const unsigned short*>(s_stage + eo[jj] + pp * ep[jj]) : 0u;
+                f[jj] = __half2float(__ushort_as_half((unsigned short)hb[jj]));
+            }
+            uint32_t word;
+            if (E4M3) {
+                word = encode_e4m3x2_relu(f[0] * rk, f[1] * rk) | (encode_e4m3x2_relu(f[2] * rk, f[3] * rk) << 16);
+            } else {
+                word = 0u;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const uint32_t code = hb[jj] < (uint32_t)kGatherLut ? (uint32_t)s_code[hb[jj]] : encode<FMT>(div_k(f[jj], k_div));
+                    word |= (ep[jj] ? code : 0u) << (8 * jj);
+                }
+            }
+            reinterpret_cast<uint32_t*>(codes + (p0 + pp) * (size_t)Cp)[w] = word;
+        };
+        if (fixed_quad) {
+            for (uint32_t pp = my_pl; pp < (uint32_t)np; pp += my_lanes) emit(pp, my_w, my_off, my_pitch);
+        } else {
+            const uint32_t words = (uint32_t)np * (uint32_t)cq;
+            for (uint32_t wi = threadIdx.x; wi < words; wi += 256) {
+                const uint32_t pp = wi / (uint32_t)cq, w = wi - pp * (uint32_t)cq;
+                uint32_t eo[4], ep[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c = (int)w * 4 + jj;
+                    const uint32_t e = c < C ? s_chan[c] : 0u;
+                    eo[jj] = e & 0xfffffu; ep[jj] = (e >> 20) << 4;
+                }
+                emit(pp, w, eo, ep);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -669,6 +805,7 @@ struct WPrepArgs {
     // applied to the float16 operand only (fused block tails, see slfp_conv2d_fwd_dual)
     size_t out_pitch, out_off;
     size_t lo_off;                                           // != 0: the lo half of the split operand goes to o + lo_off
+    int e4m3;                                                // SLFP_CONV_E4M3_OPERANDS: w_f16 receives e4m3 BYTES (SFP<3,3> only)
     const float* row_scale;
     uint32_t mg_pitch, sh_pitch, mg_cp, sh_cp, mg_s, sh_s;   // n / d == umulhi(n, mg) >> sh for n < 2^31 (d > 1)
     DivK dk;                                                 // kw with its reciprocal: exact x / kw without the division sequence
@@ -714,7 +851,9 @@ __device__ __forceinline__ void wprep_element(const WPrepArgs& a, size_t i, cons
         if (a.w_fakeq) a.w_fakeq[(((size_t)k * a.C + c) * a.R + r) * a.S + s] = fq;
     }
     const size_t o = (size_t)k * a.out_pitch + a.out_off + j;
-    if (a.w_f16) {
+    if (a.w_f16 && a.e4m3) {
+        reinterpret_cast<uint8_t*>(a.w_f16)[o] = (uint8_t)sfp33_code_to_e4m3(code);
+    } else if (a.w_f16) {
         const float val = a.row_scale ? fq * __ldg(a.row_scale + k) : fq;
         const __half hi = __float2half_rn(val);
         a.w_f16[o] = hi;
@@ -761,6 +900,15 @@ __device__ __forceinline__ void wprep_vec8(const WPrepArgs& a, size_t i, const W
         cw[e >> 2] |= code << (8 * (e & 3));
     }
     const size_t o = (size_t)k * a.out_pitch + a.out_off + j;
+    if (a.w_f16 && a.e4m3) {
+        uint32_t e0 = 0u, e1 = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            e0 |= sfp33_code_to_e4m3((cw[0] >> (8 * e)) & 0xffu) << (8 * e);
+            e1 |= sfp33_code_to_e4m3((cw[1] >> (8 * e)) & 0xffu) << (8 * e);
+        }
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.w_f16) + o) = make_uint2(e0, e1);
+    } else
     if (a.w_f16) *reinterpret_cast<uint4*>(a.w_f16 + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     if (a.w_f16 && a.lo_off) *reinterpret_cast<uint4*>(a.w_f16 + o + a.lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     if (a.w_codes) *reinterpret_cast<uint2*>(a.w_codes + o) = make_uint2(cw[0], cw[1]);
@@ -994,22 +1142,52 @@ extern "C" int slfp_gather_quantize_f16(const SlfpGatherChan* table, size_t npix
     if (!table || !codes || c <= 0 || c_phys < c || (c_phys & 3) || ((uintptr_t)codes & 3u) || c_phys > 1024)
         return set_error(SLFP_ERR_BAD_ARG, "slfp_gather_quantize_f16: bad arguments (c <= c_phys <= 1024, c_phys %% 4 == 0; codes 4-byte aligned)");
     const size_t per_cta = (size_t)(256 / (c_phys / 4)) * kGatherPix;
-    const int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(npix, per_cta));
+    const int grid = (int)min((size_t)num_sms() * 4, ceil_div_sz(npix, per_cta));      // persistent: each CTA builds the value table once
     cudaStream_t st = (cudaStream_t)stream;
     const DivK dk = make_divk(k_div);
     switch (fmt) {
         case SLFP_FMT_SFP33: gather_quantize_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(table, npix, c, c_phys, dk, codes); break;
         case SLFP_FMT_SLFP34_ACT: gather_quantize_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, 0, st>>>(table, npix, c, c_phys, dk, codes); break;
+        case SLFP_FMT_E4M3: gather_quantize_kernel<SLFP_FMT_SFP33, true><<<grid, 256, 0, st>>>(table, npix, c, c_phys, dk, codes); break;
         default: return set_error(SLFP_ERR_BAD_ARG, "slfp_gather_quantize_f16: format %d", fmt);
     }
     return check_launch("gather_quantize_kernel");
+}
+
+extern "C" void slfp_magic_u32(unsigned d, unsigned* magic, unsigned* shift) {
+    uint32_t mg, sh;
+    magic_u32(d, mg, sh);
+    if (magic) *magic = mg;
+    if (shift) *shift = sh;
+}
+
+extern "C" int slfp_gather_quantize_runs_f16(const SlfpGatherRun* runs, int n_runs, size_t npix, int c, int c_phys,
+                                             int stage_bytes_per_pixel, float k_div, int fmt, uint8_t* codes, slfp_stream_t stream) {
+    if (npix == 0) return 0;
+    if (!runs || n_runs <= 0 || !codes || c <= 0 || c_phys < c || (c_phys & 3) || c_phys > kRunMaxC || ((uintptr_t)codes & 3u) ||
+        stage_bytes_per_pixel <= 0 || (stage_bytes_per_pixel & 15) || stage_bytes_per_pixel > kRunStageBytes)
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_gather_quantize_runs_f16: bad arguments (c <= c_phys <= 1024, c_phys %% 4 == 0, stage bytes per pixel: multiple of 16, <= 32768)");
+    if (npix >= (1ull << 31) / 256) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_gather_quantize_runs_f16: too many pixels");
+    int tile_pix = (fmt == SLFP_FMT_E4M3 ? kRunStageBytes : kRunStageBytes / 2) / stage_bytes_per_pixel;
+    if (tile_pix < 1) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_gather_quantize_runs_f16: %d staging bytes per pixel do not fit", stage_bytes_per_pixel);
+    tile_pix = tile_pix > 1024 ? 1024 : tile_pix;
+    const int grid = (int)min((size_t)num_sms() * 4, ceil_div_sz(npix, (size_t)tile_pix));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DivK dk = make_divk(k_div);
+    switch (fmt) {
+        case SLFP_FMT_SFP33: gather_runs_kernel<SLFP_FMT_SFP33, false><<<grid, 256, 0, st>>>(runs, n_runs, npix, c, c_phys, tile_pix, dk, codes); break;
+        case SLFP_FMT_SLFP34_ACT: gather_runs_kernel<SLFP_FMT_SLFP34_ACT, false><<<grid, 256, 0, st>>>(runs, n_runs, npix, c, c_phys, tile_pix, dk, codes); break;
+        case SLFP_FMT_E4M3: gather_runs_kernel<SLFP_FMT_SFP33, true><<<grid, 256, 0, st>>>(runs, n_runs, npix, c, c_phys, tile_pix, dk, codes); break;
+        default: return set_error(SLFP_ERR_BAD_ARG, "slfp_gather_quantize_runs_f16: format %d", fmt);
+    }
+    return check_launch("gather_runs_kernel");
 }
 
 extern "C" int slfp_dequantize(const uint8_t* codes, size_t n, int fmt, float* out, slfp_stream_t stream) {
     if (n == 0) return 0;
     if (!codes || !out) return set_error(SLFP_ERR_BAD_ARG, "slfp_dequantize: null pointer");
     int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(n, 1024));
-    if (fmt == SLFP_FMT_SLFP34_RELU || fmt == SLFP_FMT_SFP33_RELU) {
+    if (fmt == SLFP_FMT_SLFP34_RELU || fmt == SLFP_FMT_SFP33_RELU || fmt == SLFP_FMT_SFP33_SFAST || fmt == SLFP_FMT_E4M3) {
         dequantize_any_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(codes, n, fmt, out);
         return check_launch("dequantize_any_kernel");
     }
@@ -1053,6 +1231,7 @@ static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long 
     a.pitch = slfp_conv_wpitch(d);
     a.kw = kw; a.dk = make_divk(kw); a.w_f16 = (__half*)w_f16; a.w_codes = w_codes; a.w_fakeq = w_fakeq;
     a.out_pitch = a.pitch; a.out_off = 0; a.row_scale = nullptr; a.lo_off = 0;
+    a.e4m3 = (d->flags & SLFP_CONV_E4M3_OPERANDS) ? 1 : 0;
     a.vec8_ok = ((a.Cp & 7) == 0 && (a.pitch & 7) == 0 && (((uintptr_t)a.w_f16) & 15u) == 0 && (((uintptr_t)a.w_codes) & 7u) == 0 &&
                  getenv("SLFP_WPREP_SCALAR") == nullptr) ? 1 : 0;
     if ((size_t)a.K * a.pitch >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^31 or more elements");
@@ -1106,6 +1285,8 @@ extern "C" int slfp_prepare_weights_jobs(int n, const SlfpWeightJob* host_jobs, 
             }
             a.row_scale = jb.row_scale;
             a.lo_off = jb.out_pitch ? jb.lo_offset : 0;
+            if (a.e4m3 && (wfmt != SLFP_FMT_SFP33 || a.row_scale || a.lo_off))
+                return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights_jobs: e4m3 operands are SFP<3,3> weights without row scale / lo part");
             a.vec8_ok = ((a.Cp & 7) == 0 && (a.pitch & 7) == 0 && (a.out_pitch & 7) == 0 && (a.out_off & 7) == 0 && (a.lo_off & 7) == 0 &&
                          (((uintptr_t)a.w_f16) & 15u) == 0 && (((uintptr_t)a.w_codes) & 7u) == 0 &&
                          getenv("SLFP_WPREP_SCALAR") == nullptr) ? 1 : 0;

@@ -498,12 +498,72 @@ __host__ __device__ __forceinline__ float layerout_relu(float y) {
     return fminf(t - d, 248.0f);
 }
 
+// ---- e4m3 storage of SFP<3,3> values (SLFP_FMT_E4M3) -----------------------------------------------------------------
+// decode: [s][e:4][m:3], bias 7 (sub-normals m * 2^-9; the encoders only ever produce +-0 of them)
+__host__ __device__ __forceinline__ float decode_e4m3(uint32_t c) {
+    const uint32_t e = (c >> 3) & 15u, m = c & 7u, s = (c & 0x80u) << 24;
+    if (e == 0u) return u2f(s | f2u((float)m * 0.001953125f));
+    return u2f(s | ((e + 120u) << 23) | (m << 20));
+}
+// the SFP<3,3> quantizer (utils/sfp_quant.py:63-78) of an already pre-scaled value q, as an e4m3 byte:
+// |q| < 0.0625 -> +-0 (the reference's +-1e-10), [0.0625, 0.125) -> 0.125, >= 15 -> 15, else round-half-even to 3
+// mantissa bits.  NaN -> 0x7f.
+__host__ __device__ __forceinline__ uint32_t encode_e4m3(float q) {
+    const uint32_t b = f2u(q), s = (b >> 24) & 0x80u;
+    uint32_t a = b & 0x7fffffffu;
+    if (a > kBitsInf) return 0x7fu;
+    if (a < 0x3d800000u) return s;                            // < 0.0625
+    if (a < 0x3e000000u) a = 0x3e000000u;                     // [0.0625, 0.125) -> 0.125
+    if (a >= kBits15) a = kBits15;
+    const uint32_t r = (a + 0x7ffffu + ((a >> 20) & 1u)) >> 20;     // round half even to 3 mantissa bits: (exp << 3) | m
+    const uint32_t top = (130u << 3) | 7u;                    // 15 = 1.875 * 2^3
+    return s | ((r > top ? top : r) - (120u << 3));
+}
+// two pre-scaled values -> two e4m3 bytes (lo in bits 0-7): the clamps on the FMA / ALU pipes, the rounding in ONE
+// cvt.rn.satfinite.e4m3x2.f32 (round-half-even).  Bit-exact with encode_e4m3 (tests/test_gpu_quantizer.py sweeps it).
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t encode_e4m3x2(float lo, float hi) {
+#if defined(__CUDA_ARCH__)
+    float al = fminf(fabsf(lo), 15.0f), ah = fminf(fabsf(hi), 15.0f);
+    al = al < 0.0625f ? 0.0f : fmaxf(al, 0.125f);
+    ah = ah < 0.0625f ? 0.0f : fmaxf(ah, 0.125f);
+    uint16_t d;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(copysignf(ah, hi)), "f"(copysignf(al, lo)));
+    return (uint32_t)d;
+#else
+    return encode_e4m3(lo) | (encode_e4m3(hi) << 8);
+#endif
+}
+#endif
+// the same after a ReLU (negative inputs -> 0): no sign handling, ~4 clamp instructions per element + half a cvt
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t encode_e4m3x2_relu(float lo, float hi) {
+#if defined(__CUDA_ARCH__)
+    float al = fminf(lo, 15.0f), ah = fminf(hi, 15.0f);
+    al = al < 0.0625f ? 0.0f : fmaxf(al, 0.125f);               // also sends negatives (and -0) to +0
+    ah = ah < 0.0625f ? 0.0f : fmaxf(ah, 0.125f);
+    uint16_t d;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(ah), "f"(al));
+    return (uint32_t)d;
+#else
+    return encode_e4m3(lo > 0.f ? lo : 0.f) | (encode_e4m3(hi > 0.f ? hi : 0.f) << 8);
+#endif
+}
+#endif
+// SFP<3,3> weight / activation code ([s][E:3][m:3], escapes below 8) -> the e4m3 byte of the same value
+__host__ __device__ __forceinline__ uint32_t sfp33_code_to_e4m3(uint32_t code) {
+    const uint32_t u = code & 0x7fu;
+    if (u < 8u) return code & 0x80u;                          // 0 and +-1e-10 -> +-0 (NaN never reaches a weight operand)
+    return (code & 0x80u) | (u + 24u);                        // E + 3 in the exponent field: ((E + 3) << 3) | m
+}
+
 // value of an activation code in any of the code formats a dense conv accepts
 __host__ __device__ __forceinline__ float decode_act_any(uint32_t code, int fmt, const uint32_t* __restrict__ tab) {
     switch (fmt) {
         case SLFP_FMT_SFP33: return decode<true>(code, tab);
         case SLFP_FMT_SLFP34_RELU: return decode_relu<false>(code, tab);
         case SLFP_FMT_SFP33_RELU: return decode_relu<true>(code, tab);
+        case SLFP_FMT_E4M3: return decode_e4m3(code);
         case SLFP_FMT_SFP33_SFAST: {
             const float m = decode_relu<true>(code & 0x7fu, tab);
             return (code & 0x80u) ? -m : m;

@@ -20,6 +20,7 @@ a CUDA graph.  Weights are re-quantized on every forward like the reference does
 (utils/conv2d_func.py:22) unless `static_weights=True`.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -56,12 +57,15 @@ def fold_bn(bn):
 
 
 class Plan:
-    def __init__(self, batch, device, q_bit, static_weights=False, high_fidelity=False):
+    def __init__(self, batch, device, q_bit, static_weights=False, high_fidelity=False, e4m3=None):
         self.lib = nv.lib()
         # high_fidelity: split-operand tensor-core mode (SLFP_CONV_SPLIT_OPERANDS: float16 hi + lo pairs, three passes over K)
         # for every dense layer with c_phys % 16 == 0, the exact signed code formats and float32 instead of float16 value
         # tensors - the plan then differs from the reference's float32 arithmetic by accumulation order only
         self.high_fidelity = high_fidelity
+        # SFP-7 plans exchange e4m3 bytes (SLFP_FMT_E4M3): every SFP<3,3> value is an e4m3 number, so the codes ARE the
+        # tensor-core operand (kind::f8f6f4, no decode) and the encoder is an exact round-half-even cvt
+        self.e4m3 = (q_bit == 7 and not high_fidelity and not os.environ.get("SLFP_NO_E4M3")) if e4m3 is None else bool(e4m3)
         self.batch, self.dev, self.q_bit = batch, device, q_bit
         self.afmt, self.wfmt = nv.fmt_for(q_bit, "act"), nv.fmt_for(q_bit, "weight")
         self.static_weights = static_weights
@@ -193,7 +197,8 @@ class Plan:
         # produce exact zeros (code 0 / 0.0) - which makes it eligible for the vectorised fast epilogues.
         Kk = self._cp(K) if (pad_k and dense and K % 16 != 0) else K
         hifi = self.high_fidelity and dense and x.cp % 16 == 0
-        flags = nv.CONV_SPLIT_OPERANDS if hifi else 0
+        nodec = dense and not hifi and x.fmt == nv.FMT_E4M3 and x.cp % 64 == 0      # the codes are the tensor-core operand
+        flags = nv.CONV_SPLIT_OPERANDS if hifi else (nv.CONV_E4M3_OPERANDS if nodec else 0)
         d = nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, Kk, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], groups,
                             x.fmt, pex[0], pex[1], flags)
         dw_ = d if Kk == K else nv.SlfpConvDesc(x.n, x.h, x.w, C, x.cp, K, R, S, stride[0], stride[1], pad[0], pad[1], dil[0],
@@ -202,7 +207,7 @@ class Plan:
         Wo = (x.w + 2 * pad[1] + pex[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
         pitch = self.lib.slfp_conv_wpitch(ctypes.byref(d))
         wrow = 2 * pitch if hifi else pitch                    # split operands: rows of [hi | lo]
-        wbuf = torch.zeros((Kk * wrow,), dtype=torch.float16 if dense else torch.uint8, device=self.dev)
+        wbuf = torch.zeros((Kk * wrow,), dtype=torch.float16 if (dense and not nodec) else torch.uint8, device=self.dev)
         # weight re-quantization: one table entry; Plan.prepare_weights() runs the whole table in ONE launch
         if hifi:
             self._weight_job(dw_, wview, kw, wbuf, dense, out_pitch=wrow, out_offset=0, lo_offset=pitch)
@@ -247,7 +252,9 @@ class Plan:
         # 3x3 RGB stems (c_phys = 4) run the CUDA-core direct kernel, which writes the fused pipeline's fast code formats
         stem_direct = (dense and x.cp == 4 and (R, S) == (3, 3) and tuple(dil) == (1, 1) and K in (24, 32, 64) and bn is not None
                        and not f16 and not f32 and residual is None and not layerout and stride[0] == stride[1] and pad[0] == pad[1])
-        if sfast_dw:
+        if self.e4m3 and (x.cp % 16 == 0 or stem_direct):
+            ofmt = nv.FMT_E4M3                 # every producer of an SFP-7 plan (dense, depthwise, direct stem) writes e4m3 bytes
+        elif sfast_dw:
             ofmt = nv.FMT_SFP33_SFAST
         elif stem_direct and relu and relu_codes:
             ofmt = nv.relu_fmt(self.afmt)
@@ -373,19 +380,42 @@ class Plan:
         t0 = chans[0][0]
         assert all(t.kind == "f16" and (t.n, t.h, t.w) == (t0.n, t0.h, t0.w) for t, _ in chans)
         c = len(chans)
-        out = self._alloc(t0.n, t0.h, t0.w, c, "codes", kdiv, cp=self._cp(c))
-        tab = (nv.SlfpGatherChan * c)()
-        for e, (t, ch) in zip(tab, chans):
+        fmt = nv.FMT_E4M3 if self.e4m3 else self.afmt
+        out = self._alloc(t0.n, t0.h, t0.w, c, "codes", kdiv, cp=self._cp(c) if not self.e4m3 else _ceil(c, 64), fmt=fmt)
+        # runs: per source tensor, consecutive channels whose logical positions form an arithmetic sequence
+        by_src = {}
+        for j, (t, ch) in enumerate(chans):
             assert 0 <= ch < t.c_logical
-            e.src, e.stride, e.ch = t.buf.data_ptr(), t.c, ch
+            by_src.setdefault(id(t), (t, []))[1].append((ch, j))
+        runs = []
+        for t, lst in by_src.values():
+            lst.sort()
+            i = 0
+            while i < len(lst):
+                k, step = i + 1, None
+                while k < len(lst) and lst[k][0] == lst[k - 1][0] + 1 and (step is None or lst[k][1] - lst[k - 1][1] == step) \
+                        and lst[k][1] > lst[k - 1][1]:
+                    step = lst[k][1] - lst[k - 1][1]
+                    k += 1
+                runs.append((t, lst[i][0], k - i, lst[i][1], step or 1))
+                i = k
+        tab = (nv.SlfpGatherRun * len(runs))()
+        mg, sh = ctypes.c_uint(), ctypes.c_uint()
+        stage_bpp = 0
+        for e, (t, ch0, ln, d0, st_) in zip(tab, runs):
+            assert t.c % 8 == 0, "source rows must be 16-byte multiples (8 float16)"
+            nck = (((ch0 + ln + 7) & ~7) - (ch0 & ~7)) >> 3        # 16-byte chunks that cover the run: the kernel divides by this
+            stage_bpp += 16 * nck
+            self.lib.slfp_magic_u32(max(nck, 1), ctypes.byref(mg), ctypes.byref(sh))
+            e.src, e.stride, e.ch0, e.len, e.dst_start, e.dst_step, e.magic, e.shift = t.buf.data_ptr(), t.c, ch0, ln, d0, st_, mg.value, sh.value
         dtab = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(self.dev)
         self.keep.append(dtab)
-        self.ops.append(self._call(self.lib.slfp_gather_quantize_f16, dtab.data_ptr(), t0.n * t0.h * t0.w, c, out.cp, kdiv,
-                                   self.afmt, out.buf.data_ptr()))
+        self.ops.append(self._call(self.lib.slfp_gather_quantize_runs_f16, dtab.data_ptr(), len(runs), t0.n * t0.h * t0.w, c, out.cp,
+                                   stage_bpp, kdiv, fmt, out.buf.data_ptr()))
         return out
 
     def maxpool(self, x, k, stride, pad):
-        assert x.kind == "codes"
+        assert x.kind == "codes" and x.fmt != nv.FMT_E4M3
         Ho = (x.h + 2 * pad - k) // stride + 1
         Wo = (x.w + 2 * pad - k) // stride + 1
         t = self._alloc(x.n, Ho, Wo, x.c, "codes", x.kdiv, cp=x.cp, fmt=x.fmt)

@@ -60,7 +60,14 @@ enum {
     /* Signed variant of SFP33_RELU for fused layers WITHOUT a ReLU (ShuffleNetV2's depthwise conv -> BN -> next conv):
      * bit 7 = sign, low 7 bits = min(c, 127) of the post-ReLU code of |q| (c = 127 and 128 both decode to the top
      * value 15, so nothing is lost).  SFP<3,3> only - the SLFP<3,4> half-step code needs 9 bits with a sign. */
-    SLFP_FMT_SFP33_SFAST = 6
+    SLFP_FMT_SFP33_SFAST = 6,
+    /* SFP<3,3> activations stored as OCP e4m3 bytes [s:1][e:4][m:3] (bias 7).  Every SFP<3,3> value (1 + m/8) * 2^e,
+     * e in [-3, 3], and the clamps 0.125 / 15 are exactly representable, +-1e-10 is stored as +-0
+     * (what it becomes as a tensor-core operand anyway).  The code IS the tensor-core operand: dense layers with
+     * c_phys % 64 == 0 run tcgen05.mma kind::f8f6f4 straight on the TMA-loaded code tile (no decode warps, no operand
+     * rounding, 2x the f16 rate - SLFP_CONV_E4M3_OPERANDS); the encoder is one cvt.rn.satfinite.e4m3x2.f32 behind the
+     * reference's clamps, i.e. round-half-EVEN like utils/sfp_quant.py:69 (the other fused formats round ties up). */
+    SLFP_FMT_E4M3 = 7
 };
 
 enum { SLFP_ACT_STL = 0, SLFP_ACT_SWISH = 1, SLFP_ACT_SIGMOID = 2 };
@@ -135,6 +142,29 @@ typedef struct {
 int slfp_gather_quantize_f16(const SlfpGatherChan *table, size_t npix, int c, int c_phys, float k_div, int fmt,
                              uint8_t *codes, slfp_stream_t stream);
 
+/* The same gather-quantizer driven by RUNS instead of single channels - the form the fused ShuffleNetV2 plan uses: after
+ * split / cat / shuffle every source tensor contributes ONE run of consecutive channels whose logical positions are an
+ * arithmetic sequence (dst_start + i * dst_step, the step doubling with every unit the values were passed through).
+ * A CTA stages the runs' covering 16-byte chunks for a tile of pixels in shared memory (sector-aligned 128-bit loads), then
+ * every thread assembles one 32-bit word of codes from the staged float16 values and writes it straight to global memory.
+ * Sources hold post-layerout, post-ReLU values (non-negative float16 <= 248).  `runs` is a DEVICE array; positions not
+ * covered by a run (the pad channels) get code 0. */
+typedef struct {
+    const void *src;     /* float16 NHWC tensor                                          */
+    int stride;          /* its channels per pixel (elements)                            */
+    int ch0;             /* first channel of the run                                     */
+    int len;             /* channels in the run                                          */
+    int dst_start;       /* logical (output) channel of the run's first element          */
+    int dst_step;        /* distance between consecutive elements in the output          */
+    unsigned magic, shift; /* magic-number division by nck = the number of 16-byte (8-channel) aligned chunks that cover
+                              [ch0, ch0 + len): idx / nck == umulhi(idx, magic) >> shift; the caller fills them with
+                              slfp_magic_u32(nck, ...).  stride must be a multiple of 8, src 16-byte aligned. */
+} SlfpGatherRun;
+void slfp_magic_u32(unsigned d, unsigned *magic, unsigned *shift);
+/* c: logical channels (the union of the runs' positions); stage_bytes_per_pixel: 16 * the sum of the runs' chunk counts. */
+int slfp_gather_quantize_runs_f16(const SlfpGatherRun *runs, int n_runs, size_t npix, int c, int c_phys,
+                                  int stage_bytes_per_pixel, float k_div, int fmt, uint8_t *codes, slfp_stream_t stream);
+
 /* codes -> float32 (exactly the value the reference's fake-quant tensor would hold) */
 int slfp_dequantize(const uint8_t *codes, size_t n, int fmt, float *out, slfp_stream_t stream);
 
@@ -171,6 +201,10 @@ typedef struct {
  * decode work; dense layers with c_phys % 16 == 0 only.  The weight operand has rows of 2 * slfp_conv_wpitch() halves,
  * [hi | lo] (SlfpWeightJob.lo_offset = slfp_conv_wpitch()). */
 #define SLFP_CONV_SPLIT_OPERANDS 1
+/* The weight operand is e4m3 BYTES (KRSC, row pitch slfp_conv_wpitch() bytes) instead of float16, the activation codes
+ * are SLFP_FMT_E4M3: kind::f8f6f4 MMA on the codes themselves.  q_bit 7 (SFP<3,3>) only, dense, c_phys % 64 == 0.
+ * slfp_prepare_weights* writes that operand through the w_f16 pointer when the descriptor carries this flag. */
+#define SLFP_CONV_E4M3_OPERANDS 2
 
 typedef struct {
     const float *bias_q;   /* [k] added to the accumulator BEFORE the post-scale (bias/Ka/Kw,

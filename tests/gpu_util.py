@@ -92,3 +92,25 @@ def conv_fwd_gpu(x_nchw, w_oihw, bias_q, ka, kw, q_bit, stride, pad, dil, groups
     out["desc"] = d
     out["dev"] = dict(xc=xc, wc=wc)
     return out
+
+
+def decode_e4m3(codes):
+    """Value of OCP e4m3 bytes [s][e:4][m:3], bias 7 (SLFP_FMT_E4M3: SFP<3,3> values stored as the fp8 number itself)."""
+    c = np.asarray(codes).astype(np.int64)
+    e, m = (c >> 3) & 15, c & 7
+    mag = np.where(e == 0, m * 2.0 ** -9, (1.0 + m / 8.0) * np.exp2(e - 7.0))
+    mag = np.where((c & 0x7f) == 0x7f, np.nan, mag)
+    return np.where(c & 0x80, -mag, mag).astype(np.float32)
+
+
+def decode_codes(orc, codes, fmt):
+    """Value of activation codes in ANY of the formats the kernels exchange (include/slfp_b200.h)."""
+    codes = np.asarray(codes)
+    if fmt in (nv.FMT_SLFP34_RELU, nv.FMT_SFP33_RELU):
+        return orc.decode_relu(codes, fmt == nv.FMT_SFP33_RELU)
+    if fmt == nv.FMT_SFP33_SFAST:
+        m = orc.decode_relu(codes & 0x7f, True)
+        return np.where(codes & 0x80, -m, m).astype(np.float32)
+    if fmt == nv.FMT_E4M3:
+        return decode_e4m3(codes)
+    return orc.decode(codes, fmt)

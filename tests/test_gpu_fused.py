@@ -365,18 +365,14 @@ def test_plan_is_stable_and_deterministic_over_many_steps():
 
 
 def _decode_any(orc, codes, fmt):
-    from cnns_slfp_quantization_b200 import _native as nv
-    if fmt in (nv.FMT_SLFP34_RELU, nv.FMT_SFP33_RELU):
-        return orc.decode_relu(codes, fmt == nv.FMT_SFP33_RELU)
-    if fmt == nv.FMT_SFP33_SFAST:
-        m = orc.decode_relu(codes & 0x7f, True)
-        return np.where(codes & 0x80, -m, m).astype(np.float32)
-    return orc.decode(codes, fmt)
+    from gpu_util import decode_codes
+    return decode_codes(orc, codes, fmt)
 
 
-@pytest.mark.parametrize("K,stride,qbit,relu,two", [(32, 2, 7, True, False), (24, 1, 7, False, True), (64, 1, 8, True, False),
-                                                    (32, 1, 8, True, False), (24, 1, 8, False, True)])
-def test_direct_stem_kernel(orc, K, stride, qbit, relu, two):
+@pytest.mark.parametrize("K,stride,qbit,relu,two,e4m3", [(32, 2, 7, True, False, False), (24, 1, 7, False, True, False), (64, 1, 8, True, False, False),
+                                                         (32, 1, 8, True, False, False), (24, 1, 8, False, True, False),
+                                                         (32, 2, 7, True, False, True), (24, 1, 7, False, True, True)])
+def test_direct_stem_kernel(orc, K, stride, qbit, relu, two, e4m3):
     """3x3 RGB stems through the CUDA-core direct kernel (conv_stem_direct.cu; MobileNetV1 3->32, ShuffleNetV2 3->24,
     VGG-16 3->64): float32 operands and accumulation, folded affine (+ ReLU), quantize-on-store in the fused code formats
     (post-ReLU codes, signed fast SFP<3,3>, exact signed codes; one or two consumers) against a float64 convolution of
@@ -393,7 +389,7 @@ def test_direct_stem_kernel(orc, K, stride, qbit, relu, two):
     conv.Kw = torch.tensor(float(conv.weight.detach().abs().max() / 15.5))
     bn = nn.BatchNorm2d(K).to(dev).eval()
     bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.5); bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5)
-    P = engine.Plan(N, dev, qbit)
+    P = engine.Plan(N, dev, qbit, e4m3=e4m3)
     xin = P.input_nchw(3, H, H)
     xin.copy_(x)
     xc = P.quantize_input(xin, engine._k32(conv.Ka))
@@ -414,7 +410,9 @@ def test_direct_stem_kernel(orc, K, stride, qbit, relu, two):
     y = y.transpose(0, 2, 3, 1)
     for kd in ks:
         t = out["codes"][kd]
-        if qbit == 7:
+        if e4m3:
+            assert t.fmt == nv.FMT_E4M3
+        elif qbit == 7:
             assert t.fmt == (nv.FMT_SFP33_RELU if relu else nv.FMT_SFP33_SFAST)
         elif relu:
             assert t.fmt == nv.FMT_SLFP34_RELU
@@ -429,8 +427,9 @@ def test_direct_stem_kernel(orc, K, stride, qbit, relu, two):
         assert ok.all(), (kd, int((~ok).sum()), ok.size)
 
 
+@pytest.mark.parametrize("e4m3", [False, True])
 @pytest.mark.parametrize("C,H,stride", [(58, 14, 1), (24, 20, 2), (116, 9, 1), (232, 6, 2), (116, 28, 1)])
-def test_shufflenet_branch_fast_forms_equal_generic_forms(orc, C, H, stride):
+def test_shufflenet_branch_fast_forms_equal_generic_forms(orc, C, H, stride, e4m3):
     """One ShuffleNetV2 residual branch (1x1 -> BN -> layerout -> ReLU -> dw 3x3 -> BN -> 1x1 -> BN -> layerout -> ReLU,
     58 channels: not a multiple of 16) through the fast forms - output channels padded to 64 for the vectorised
     epilogues, relu(quantize_layerout(.)) as three FMA-pipe operations, signed fast codes out of the depthwise conv -
@@ -458,7 +457,7 @@ def test_shufflenet_branch_fast_forms_equal_generic_forms(orc, C, H, stride):
     src = torch.rand(N, H, H, Cs, device=dev).half() * 3
     outs = []
     for fast in (True, False):
-        P = engine.Plan(N, dev, 7)
+        P = engine.Plan(N, dev, 7, e4m3=e4m3)
         t = engine._T(src, N, H, H, Cs, Cs, "f16")
         t.c_logical = C
         xc = P.gather_quantize([(t, (j * 7) % C) for j in range(C)], engine._k32(c0.Ka))
@@ -466,7 +465,9 @@ def test_shufflenet_branch_fast_forms_equal_generic_forms(orc, C, H, stride):
         kd = engine._k32(0.2)
         a = P.conv(xc, c0, bn=b0, relu=True, layerout=lo, codes=[kd], pad_k=fast)["codes"][kd]
         b = P.conv(a, dw, bn=b1, relu=False, codes=[kd], relu_codes=False, signed_fast=fast)["codes"][kd]
-        if fast:
+        if e4m3:
+            assert a.fmt == nv.FMT_E4M3 and b.fmt == nv.FMT_E4M3
+        elif fast:
             assert a.fmt == nv.FMT_SFP33 and b.fmt == nv.FMT_SFP33_SFAST
         y = P.conv(b, c2, bn=b2, relu=True, layerout=lo, f16=True, pad_k=fast)["f16"]
         P.run()

@@ -137,8 +137,9 @@ def _tap_views(key, mod, t, layers, orc, qbit, nv):
     target = getattr(mod, "orig", mod)
     li = layers.index(target)
     ref = orc.decode(G[f"{key}.tap{li:02d}"], fmt)                      # NCHW (or [n, c] for a linear layer)
+    from gpu_util import decode_codes
     codes = t.buf.cpu().numpy()
-    got = orc.decode_relu(codes, qbit == 7) if t.fmt in (nv.FMT_SLFP34_RELU, nv.FMT_SFP33_RELU) else orc.decode(codes, t.fmt)
+    got = decode_codes(orc, codes, t.fmt)
     if hasattr(mod, "orig"):                                           # space-to-depth stem: [n, h/2, w/2, (dy, dx, c)]
         n, h2, w2, _ = got.shape
         c = ref.shape[1]
@@ -153,16 +154,19 @@ def _tap_views(key, mod, t, layers, orc, qbit, nv):
 
 def _encode_like(t, ref, mod, orc, qbit, nv):
     """The reference's input_q as codes in tensor t's own layout and code format (teacher forcing)."""
+    from gpu_util import decode_codes
     relu_fmt = t.fmt in (nv.FMT_SLFP34_RELU, nv.FMT_SFP33_RELU)
-    table = (orc.decode_relu(np.arange(256, dtype=np.uint8), qbit == 7) if relu_fmt
-             else orc.decode(np.arange(256, dtype=np.uint8), t.fmt)).astype(np.float64)
+    table = decode_codes(orc, np.arange(256, dtype=np.uint8), t.fmt).astype(np.float64)
+    if t.fmt == nv.FMT_E4M3:
+        table[(np.arange(256) & 0x78) == 0] = np.inf          # sub-normal e4m3 patterns are never produced (0 is code 0 / 0x80)
+        table[0] = 0.0
     table = np.where(np.isfinite(table), table, np.inf)
     order = np.argsort(table, kind="stable")
     tv = table[order]
     v = ref.astype(np.float64)
     if relu_fmt:
         assert (v >= 0).all()
-    v = np.where(np.abs(v) <= 1e-9, 0.0, v) if relu_fmt else v           # +-1e-10 is code 0 (0.0) in the post-ReLU formats
+    v = np.where(np.abs(v) <= 1e-9, 0.0, v) if (relu_fmt or t.fmt == nv.FMT_E4M3) else v    # +-1e-10 is code 0 (0.0) in the fused formats
     pos = np.clip(np.searchsorted(tv, v * (1 - 1e-7) if relu_fmt else v - np.abs(v) * 1e-7), 0, 255)
     codes = order[pos].astype(np.uint8)
     assert np.allclose(table[codes], v, rtol=1e-6, atol=0), "reference value without a code"

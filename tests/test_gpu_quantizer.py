@@ -253,3 +253,84 @@ def test_gather_quantize_matches_plain_quantizer(orc):
         want, _ = orc.quantize(g, fmt, 0.21)
         got = out.cpu().numpy()
         assert (got[:, :58] == want).all() and (got[:, 58:] == 0).all()
+
+
+def test_e4m3_encoder_is_the_sfp33_quantizer(orc):
+    """SLFP_FMT_E4M3: the cvt-based device encoder (depthwise kernel epilogue) produces, for every float32 mantissa at every
+    octave of the SFP<3,3> range and both signs, the e4m3 byte whose value IS the reference quantizer's value
+    (utils/sfp_quant.py:63-78: round-half-even, 0.0625 / 0.125 / 15 clamps; +-1e-10 is stored as +-0)."""
+    import ctypes
+    import torch
+    from cnns_slfp_quantization_b200 import _native as nv
+    from gpu_util import decode_e4m3
+    lib = nv.lib()
+    dev = torch.device("cuda:0")
+    C = 16
+    mant = np.arange(0, 1 << 23, 3, dtype=np.uint32)
+    n = (mant.size // C) * C
+    mant = mant[:n]
+    wt = torch.zeros((C, 1, 1, 1), dtype=torch.float32, device=dev) + 1.0          # depthwise 1x1 with unit weights: y = x_q
+    for e in (-6, -5, -4, -3, -1, 0, 2, 3, 4, 5):
+        for sign in (0, 1):
+            x = (mant | np.uint32((e + 127) << 23) | np.uint32(sign << 31)).view(np.float32)
+            # route the values through the gather-quantizer's e4m3 output (exact table encoder + re-spelling)
+            src = torch.from_numpy(x.astype(np.float16)).to(dev).reshape(-1, C)
+            tab = (nv.SlfpGatherChan * C)()
+            for j, t_ in enumerate(tab):
+                t_.src, t_.stride, t_.ch = src.data_ptr(), C, j
+            dtab = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(dev)
+            out = torch.empty((src.shape[0], C), dtype=torch.uint8, device=dev)
+            nv.check(lib.slfp_gather_quantize_f16(dtab.data_ptr(), src.shape[0], C, C, 1.0, nv.FMT_E4M3, out.data_ptr(), nv.stream()))
+            torch.cuda.synchronize()
+            xh = src.float().cpu().numpy().reshape(-1)
+            _, want = orc.quantize(xh, 0, 1.0, want_codes=False)
+            want = np.where(np.abs(want) <= 1e-9, 0.0, want)
+            got = decode_e4m3(out.cpu().numpy().reshape(-1))
+            assert (got == want).all(), (e, sign, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 7])
+def test_gather_quantize_runs(orc, fmt):
+    """slfp_gather_quantize_runs_f16 (the run-based, shared-memory-staged form the ShuffleNetV2 plan uses): three source
+    tensors with runs of different lengths and output steps (1, 2, 4 - the shuffle's interleaving), a ragged pixel count,
+    values that include 0, the 248 clamp and out-of-table entries (negative, 300, inf): codes equal the oracle's quantizer."""
+    import ctypes
+    import torch
+    from cnns_slfp_quantization_b200 import _native as nv
+    from gpu_util import decode_e4m3
+    lib = nv.lib()
+    rng = np.random.default_rng(9)
+    npix = 1000 + 7
+    a = np.abs(rng.standard_normal((npix, 64)) * 3).astype(np.float16)
+    b = np.abs(rng.standard_normal((npix, 128)) * 40).astype(np.float16)
+    c = np.abs(rng.standard_normal((npix, 64)) * 0.5).astype(np.float16)
+    a[::7, 3] = 0; b[::5, 70] = 248; b[1::5, 71] = 300
+    if fmt != 7:                       # the e4m3 form folds the ReLU into its low clamp: sources are non-negative by contract
+        c[::11, 5] = -2.0; c[3::11, 6] = np.inf
+    ta, tb, tc = (torch.from_numpy(t).cuda() for t in (a, b, c))
+    # output channel j (58 logical channels, c_phys 64): even j <- a[29 + j/2]; j = 1 mod 4 <- b[64 + j//4]; j = 3 mod 4 <- c[j//4]
+    runs_spec = [(ta, 64, 29, 29, 0, 2), (tb, 128, 64, 15, 1, 4), (tc, 64, 0, 14, 3, 4)]
+    tab = (nv.SlfpGatherRun * 3)()
+    mg, sh = ctypes.c_uint(), ctypes.c_uint()
+    want_vals = np.zeros((npix, 64), np.float32)
+    covered = np.zeros(64, bool)
+    for e, (t, stride, ch0, ln, d0, st_) in zip(tab, runs_spec):
+        lib.slfp_magic_u32((((ch0 + ln + 7) & ~7) - (ch0 & ~7)) >> 3, ctypes.byref(mg), ctypes.byref(sh))
+        e.src, e.stride, e.ch0, e.len, e.dst_start, e.dst_step, e.magic, e.shift = t.data_ptr(), stride, ch0, ln, d0, st_, mg.value, sh.value
+        for i in range(ln):
+            want_vals[:, d0 + i * st_] = t.float().cpu().numpy()[:, ch0 + i]
+            covered[d0 + i * st_] = True
+    assert covered[:58].all() and not covered[58:].any()
+    dtab = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).cuda()
+    out = torch.full((npix, 64), 9, dtype=torch.uint8, device="cuda")
+    bpp = 16 * sum((((ch0 + ln + 7) & ~7) - (ch0 & ~7)) >> 3 for _, _, ch0, ln, _, _ in runs_spec)
+    nv.check(lib.slfp_gather_quantize_runs_f16(dtab.data_ptr(), 3, npix, 58, 64, bpp, 0.21, fmt, out.data_ptr(), nv.stream()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert (got[:, 58:] == 0).all()
+    wc, wq = orc.quantize(want_vals[:, :58], 0 if fmt == 7 else fmt, 0.21)
+    if fmt == 7:
+        wq = np.where(np.abs(wq) <= 1e-9, 0.0, wq)
+        assert (decode_e4m3(got[:, :58]) == wq).all()
+    else:
+        assert (got[:, :58] == wc).all()
