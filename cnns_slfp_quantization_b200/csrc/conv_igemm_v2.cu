@@ -1384,8 +1384,24 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     static const int stg_max_kb = getenv("SLFP_STG_MAXKB") ? atoi(getenv("SLFP_STG_MAXKB")) : 8;
     const bool stg = !hifi && !nodec && p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
                      (((uintptr_t)epi->residual) & 15u) == 0;
-    const int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
+    int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
+    if (!stg && !nodec && bn > 64) {
+        // Tile width against wave quantisation (small-M layers: VGG-16 @2x2 / @4x4, ResNet-50 stage 4).  One CTA per SM works
+        // through ceil(tiles / SMs) tiles; a tile costs ~num_kb x (cycles per K block), measured ~1 180 for the 256-column
+        // form (A staged in shared memory) and ~640 for 128 / 64 columns (A in tensor memory) - the decode side, not the
+        // MMA, sets the pace (profiles/r02_final.md).  Pick the width with the smallest modelled time; ties keep the wider tile.
+        static const bool fixed = getenv("SLFP_BN_FIXED") != nullptr;
+        const int sms = num_sms();
+        double best = 1e30;
+        int best_bn = bn;
+        for (int cand = bn; cand >= 64 && !fixed; cand >>= 1) {
+            const long tiles = (long)p.m_tiles * ((d->k + cand - 1) / cand);
+            const double t = (double)((tiles + sms - 1) / sms) * (cand == 256 ? 1180.0 : 640.0);
+            if (t < best * 0.97) { best = t; best_bn = cand; }
+        }
+        bn = best_bn;
+    }
     p.n_tiles = (d->k + bn - 1) / bn;
     p.num_tiles = p.m_tiles * p.n_tiles;
 

@@ -143,7 +143,7 @@ bool conv2d_fwd_stem_direct_supported(const SlfpConvDesc* d, const SlfpEpilogue*
     static const bool off = getenv("SLFP_NO_STEM_DIRECT") != nullptr;
     if (off || d->groups != 1 || d->c_phys != 4 || d->c > 3 || d->r != 3 || d->s != 3 || d->dil_h != 1 || d->dil_w != 1) return false;
     if (d->stride_h != d->stride_w || d->pad_h != d->pad_w || d->pad_h_extra || d->pad_w_extra) return false;
-    if (d->k != 24 && d->k != 32 && d->k != 64) return false;
+    if (d->k != 24 && d->k != 32 && !(d->k == 64 && getenv("SLFP_STEM_DIRECT_64"))) return false;   // K = 64 (VGG-16): the 4-channel tcgen05 kernel is faster (measured)
     if (!e->ch_mul || !e->ch_add || e->residual || e->y_f32 || e->y_f16 || !e->y_codes || e->layerout) return false;
     if (e->k_phys_out % 16 != 0 || e->k_phys_out < d->k || e->k_phys_out > 64) return false;
     const int f = e->next_fmt;

@@ -250,7 +250,7 @@ class Plan:
         # depthwise conv -> BN -> (no ReLU) -> next quantizer: sign bit + 7-bit magnitude code (SFP<3,3> only)
         sfast_dw = fused_dw and not relu and signed_fast and self.afmt == nv.FMT_SFP33 and kp == x.cp
         # 3x3 RGB stems (c_phys = 4) run the CUDA-core direct kernel, which writes the fused pipeline's fast code formats
-        stem_direct = (dense and x.cp == 4 and (R, S) == (3, 3) and tuple(dil) == (1, 1) and K in (24, 32, 64) and bn is not None
+        stem_direct = (dense and x.cp == 4 and (R, S) == (3, 3) and tuple(dil) == (1, 1) and K in (24, 32) and bn is not None
                        and not f16 and not f32 and residual is None and not layerout and stride[0] == stride[1] and pad[0] == pad[1])
         if self.e4m3 and (x.cp % 16 == 0 or stem_direct):
             ofmt = nv.FMT_E4M3                 # every producer of an SFP-7 plan (dense, depthwise, direct stem) writes e4m3 bytes
