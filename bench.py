@@ -360,14 +360,16 @@ def run_qat(args, rank, world, local, dev, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * batch * args.steps / float(t.item())
+    # one instrumented step on EVERY rank (it contains the gradient collectives), recorded on rank 0
+    nv.profile = {} if rank == 0 else None
+    step(x, y)
+    torch.cuda.synchronize()
+    prof, nv.profile = nv.profile, None
+    barrier()
     if rank == 0:
         pk = peaks()
         fwd_flops = 8.178e9 * batch                      # 2 * 4 089.2 M MAC per image
         tf = 3.0 * fwd_flops / (ms / args.steps * 1e-3) / 1e12
-        nv.profile = {}
-        step(x, y)
-        torch.cuda.synchronize()
-        prof, nv.profile = nv.profile, None
         per = {k: round(sum(a.elapsed_time(b) for a, b, _ in v), 3) for k, v in prof.items()}
         ours_ms = sum(per.values())
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -424,7 +426,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))     # a desynchronised collective fails fast
 
     def barrier():
         if world > 1:
