@@ -10,7 +10,7 @@ import torch
 
 from .build import LIB_PATH, source_hash
 
-FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU, FMT_SFP33_SFAST, FMT_E4M3 = 0, 1, 2, 3, 4, 5, 6, 7
+FMT_SFP33, FMT_SLFP34_ACT, FMT_SLFP34_WGT, FMT_SFP44_OUT, FMT_SLFP34_RELU, FMT_SFP33_RELU, FMT_SFP33_SFAST, FMT_E4M3, FMT_F16Q = 0, 1, 2, 3, 4, 5, 6, 7, 8
 ACT_STL, ACT_SWISH, ACT_SIGMOID = 0, 1, 2
 SGD_NORMAL, SGD_DSGD, SGD_SSGD = 0, 1, 2
 Q_LAYEROUT_ZERO_IS_ZERO = 1
@@ -30,7 +30,7 @@ class SlfpEpilogue(ctypes.Structure):
     _fields_ = [("bias_q", c_vp), ("post_a", c_f), ("post_b", c_f), ("ch_scale", c_vp), ("ch_shift", c_vp),
                 ("residual", c_vp), ("residual_f16", c_i), ("relu", c_i), ("y_f32", c_vp), ("y_f16", c_vp),
                 ("y_codes", c_vp), ("next_k_div", c_f), ("next_fmt", c_i), ("k_phys_out", c_i),
-                ("y_codes2", c_vp), ("next_k_div2", c_f), ("ch_mul", c_vp), ("ch_add", c_vp), ("layerout", c_i)]
+                ("y_codes2", c_vp), ("next_k_div2", c_f), ("ch_mul", c_vp), ("ch_add", c_vp), ("layerout", c_i), ("store_f16", c_i)]
 
 
 class SlfpGatherChan(ctypes.Structure):

@@ -33,6 +33,9 @@ extern "C" int slfp_conv2d_fwd(const SlfpConvDesc* desc, const uint8_t* x_codes,
     if (rc) return rc;
     if (!x_codes || !w_prepared || !epi) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_fwd: null pointer");
     if (!epi->y_f32 && !epi->y_f16 && !epi->y_codes) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_fwd: no output");
+    // SLFP_FMT_F16Q in / store_f16 out exist in the warp-specialised dense kernel only (conv_igemm_v2.cu)
+    if ((desc->fmt == SLFP_FMT_F16Q || epi->store_f16) && (desc->groups != 1 || !conv2d_fwd_dense_v2_supported(desc)))
+        return set_error(SLFP_ERR_UNSUPPORTED, "slfp_conv2d_fwd: float16-image activations need a dense layer with c_phys %% 16 == 0");
     if (desc->groups == 1) return conv2d_fwd_dense(desc, x_codes, w_prepared, epi, (cudaStream_t)stream);
     return conv2d_fwd_grouped(desc, x_codes, w_prepared, epi, (cudaStream_t)stream);
 }

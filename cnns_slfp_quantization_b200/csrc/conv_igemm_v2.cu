@@ -49,6 +49,7 @@ constexpr int kBK = 64;
 constexpr int kCodeBytes = kBM * kBK;                  // 8 KB of codes per K block
 constexpr int kABytes = kBM * kBK * 2;                 // 16 KB float16 A tile
 constexpr int kLutBytes = 256 * 32 * 4;                // code -> f16, one copy per bank
+constexpr int kOutLutEntries = 258;                    // post-ReLU codes 0..257 (before the byte saturation) -> f16
 constexpr int kWarpCode = 0, kWarpWgt = 1, kWarpMma = 2, kWarpCode2 = 3;
 // 28 warps: 4 control (2 producers, MMA issuer, spare) + DW decode + (24 - DW) epilogue.  Two role splits, chosen
 // per layer on the host: DW = 16 for decode-heavy layers (3x3, large K), DW = 8 for epilogue-heavy ones (the 1x1
@@ -91,18 +92,25 @@ struct Params {
 // NODEC (SLFP_CONV_E4M3_OPERANDS): activation codes and weights are e4m3 bytes - the TMA-loaded code tile IS the A
 // operand of tcgen05.mma kind::f8f6f4 (64-byte swizzle, two K = 32 instructions per 64-channel K block): no decode
 // table, no decode warps, no A staging; the code ring and the weight ring share one barrier pair per stage.
-template <int BLOCK_N, bool STG = false, bool NODEC = false>
+// A16 (SLFP_FMT_F16Q input): the activation tensor already holds the float16 image of the quantized values, so the TMA-loaded
+// [128 pixels x 64 channels] tile (128-byte rows, 128-byte swizzle) IS the A operand of tcgen05.mma kind::f16 - the NODEC
+// structure with 2-byte elements.  Trades 1 B/element of HBM traffic for the decode work of the consumer.
+template <int BLOCK_N, bool STG = false, bool NODEC = false, bool A16 = false>
 struct Cfg {
+    static_assert(!A16 || NODEC, "A16 is a no-decode variant");
     // BLOCK_N <= 128: the decoded A tile goes to TENSOR memory (tcgen05.st; the MMA reads A from TMEM), which takes
     // the A tile's write (16 KB) and the MMA's read of it (16 KB) per K block off the shared-memory pipe - the
     // measured bottleneck of the decode-heavy layers (profiles/r01_conv_v2.md).  BLOCK_N = 256 needs all 512 TMEM
     // columns for the double-buffered accumulator and keeps the A tile in shared memory.
     static constexpr bool kATmem = !NODEC && BLOCK_N <= 128;
-    static constexpr int kBBytes = NODEC ? BLOCK_N * kBK : BLOCK_N * kBK * 2;
+    static constexpr int kBBytes = (NODEC && !A16) ? BLOCK_N * kBK : BLOCK_N * kBK * 2;
+    static constexpr int kCodeTile = A16 ? kABytes : kCodeBytes;      // bytes of one [128 x 64] activation tile in the code ring
     // Ring depths.  The code tiles and weight tiles arrive through TMA with ~1.5-2 us of latency under load; the
     // first version's 4 x 8 KB of codes in flight per SM left the decode warps waiting on the code barrier most
     // of the time (profiles/r01_conv_v2.md).  With A in TMEM the freed shared memory deepens both rings.
-    static constexpr int kStages = NODEC ? ((BLOCK_N >= 256 || STG) ? 6 : 8)
+    static constexpr int kA16Stages = STG ? 4 : (BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8));      // 16 KB + BLOCK_N x 128 B per stage
+    static constexpr int kStages = A16 ? kA16Stages
+                                 : NODEC ? ((BLOCK_N >= 256 || STG) ? 6 : 8)
                                          : ((BLOCK_N >= 256 || STG) ? 3 : 4);          // weight (and A) stages
     // The code ring depth must be a MULTIPLE of the number of decode groups (2 or 4), so that a code stage is always
     // consumed by the same group: TMA loads of different stages may land out of order, and a group that moved on to
@@ -110,7 +118,8 @@ struct Cfg {
     // `full` barrier one phase behind - a parity wait then passes immediately (it cannot tell "phase n - 1 done" from
     // "phase n + 1 done"), the group decodes stale codes and its arrivals desynchronise the ring (seen as a rare
     // `unspecified launch failure` once the weights were re-quantized between steps, ~1 step in 1000).
-    static constexpr int kCodeStages = (BLOCK_N >= 256 || STG) ? 6 : 8;
+    static constexpr int kCodeStages = A16 ? kA16Stages : ((BLOCK_N >= 256 || STG) ? 6 : 8);
+    static_assert(!NODEC || kCodeStages == kStages, "no-decode variants: one ring, one barrier pair per stage");
     // STG: the epilogue's global traffic goes through shared-memory staging + TMA (see the staged epilogue below):
     // two float16 [128 x BLOCK_N] buffers (residual in / float16 out, in place) and two code tiles.
     static constexpr int kIoBytes = kBM * BLOCK_N * 2, kCoBytes = kBM * BLOCK_N;
@@ -119,7 +128,14 @@ struct Cfg {
     static constexpr int kTmemCols = kATmem ? (2 * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
     static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
     static constexpr int kLutB = NODEC ? 0 : kLutBytes;
-    static constexpr int kSmemBytes = kStages * (((kATmem || NODEC) ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeBytes + kStageBytes + kLutB + kParBytes + 1024;
+    // SlfpEpilogue.store_f16: code -> float16 table of the NEXT layer's format for the epilogue.  Decode variants: one copy per
+    // bank like the decode table (their decode warps already load the shared-memory pipe); no-decode variants: 16 copies
+    // (lanes l and l + 16 share a bank, at worst a 2-way conflict) so that it also fits next to the 256-column rings.
+    // The staged and the 256-column decode variants have no room for it.
+    static constexpr int kOutLutCopies = NODEC ? 16 : 32;
+    static constexpr int kOutLutB = (STG || (!NODEC && BLOCK_N >= 256)) ? 0 : kOutLutEntries * kOutLutCopies * 4;
+    static constexpr int kSmemBytes = kStages * (((kATmem || NODEC) ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeTile + kStageBytes + kLutB + kOutLutB + kParBytes + 1024;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // sixteen relu'd values -> sixteen codes.  fast: the post-ReLU formats (saturating scale, re-based bit pattern, pack).
@@ -170,6 +186,25 @@ __device__ __forceinline__ uint4 encode16_exact(const float (&v)[16], const DivK
     for (int g = 0; g < 4; ++g)
         pk[g] = __byte_perm(__byte_perm(c[4 * g], c[4 * g + 1], 0x0040), __byte_perm(c[4 * g + 2], c[4 * g + 3], 0x0040), 0x5410);
     return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// sixteen pre-scaled relu inputs u = v / (16 Ka_next) -> the float16 images of their post-ReLU codes (SlfpEpilogue.store_f16):
+// the code is formed exactly like encode16_fast (saturating clamp, truncated bit pattern) and looked up in the kernel's
+// output table instead of being packed to a byte.  olut_rel = table base + (lane % copies) * 4 - base_code * copies * 4; bit 0
+// of it (the address is 4-byte aligned) flags the 16-copy table.
+template <bool SFP33>
+__device__ __forceinline__ void encode16_q16(const float (&u)[16], uint32_t olut_rel_f, uint32_t (&h)[8]) {
+    const uint32_t half = olut_rel_f & 1u, olut_rel = olut_rel_f & ~1u;                 // warp-uniform
+    const uint32_t sh = (SFP33 ? 12u : 11u) + half, mask = half ? 0xffffffc0u : 0xffffff80u;
+    const float lo = __uint_as_float(SFP33 ? (0x76Fu << 19) : (0xEDFu << 18));      // raw code 0
+    uint32_t e[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t b = __float_as_uint(fmaxf(__saturatef(u[i]), lo));
+        e[i] = ptx::lds32_off((b >> sh) & mask, olut_rel);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = ptx::pack16_fma(e[2 * i], e[2 * i + 1]);
 }
 
 // ---- epilogue of one 32-row x (BLOCK_N/2)-column slab -----------------------------------------------------
@@ -401,7 +436,7 @@ __device__ __forceinline__ void pair_exchange(const uint4& A, const uint4& B, bo
 
 template <int BLOCK_N, int G, int MODE, bool SFP33>
 __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int next_tile, uint32_t tmem_acc, int quad, int half,
-                                              int lane, uint32_t s_mul, uint32_t s_add) {
+                                              int lane, uint32_t s_mul, uint32_t s_add, uint32_t olut_rel) {
     static_assert(BLOCK_N / G >= 32, "32-column steps");
     constexpr int kCols = BLOCK_N / G;
     const int Kout = p.Kout;
@@ -462,6 +497,16 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
             }
             if (MODE == 1 && p.e4m3_out) {
                 pk1[o / 16] = encode16_e4m3_relu_prescaled(v);       // the staged affine carries 1 / Ka_next
+            } else if (MODE == 1 && p.epi.store_f16) {
+                // float16 images of the codes: 32 contiguous bytes (one sector) of this lane's row
+                uint32_t hq[8];
+                encode16_q16<SFP33>(v, olut_rel, hq);
+                // lane pairs swap 16-byte pieces: every store instruction writes whole 32-byte sectors
+                uint4 f1, f2;
+                pair_exchange(make_uint4(hq[0], hq[1], hq[2], hq[3]), make_uint4(hq[4], hq[5], hq[6], hq[7]), odd, f1, f2);
+                __half* yh = reinterpret_cast<__half*>(yc1);
+                if (ok_first) *reinterpret_cast<uint4*>(yh + row_first + n0 + o + (odd ? 8 : 0)) = f1;
+                if (ok_second) *reinterpret_cast<uint4*>(yh + row_second + n0 + o + (odd ? 8 : 0)) = f2;
             } else if (MODE == 1) {
                 int32_t t[16];
 #pragma unroll
@@ -504,6 +549,7 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
                 }
             }
         }
+        if (MODE == 1 && p.epi.store_f16) continue;             // stored above
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
             uint8_t* yc = pass ? yc2 : yc1;
@@ -526,7 +572,7 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
 // processed, code pieces of two consecutive chunks pair up for the full-sector stores.
 template <int BLOCK_N, int G, int MODE, bool SFP33>
 __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int next_tile, uint32_t tmem_acc, int quad, int cg,
-                                                int lane, uint32_t s_mul, uint32_t s_add) {
+                                                int lane, uint32_t s_mul, uint32_t s_add, uint32_t olut_rel) {
     constexpr int kCols = BLOCK_N / G;
     constexpr int kChunks = kCols / 16;
     const int Kout = p.Kout;
@@ -581,6 +627,15 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
         uint4 pk1, pk2 = make_uint4(0u, 0u, 0u, 0u);
         if (MODE == 1 && p.e4m3_out) {
             pk1 = encode16_e4m3_relu_prescaled(v);                   // the staged affine carries 1 / Ka_next
+        } else if (MODE == 1 && p.epi.store_f16) {
+            uint32_t hq[8];
+            encode16_q16<SFP33>(v, olut_rel, hq);
+            uint4 f1, f2;
+            pair_exchange(make_uint4(hq[0], hq[1], hq[2], hq[3]), make_uint4(hq[4], hq[5], hq[6], hq[7]), odd, f1, f2);
+            __half* yh = reinterpret_cast<__half*>(yc1);
+            if (ok_first) *reinterpret_cast<uint4*>(yh + row_first + ch * 16 + (odd ? 8 : 0)) = f1;
+            if (ok_second) *reinterpret_cast<uint4*>(yh + row_second + ch * 16 + (odd ? 8 : 0)) = f2;
+            continue;
         } else if (MODE == 1) {
             int32_t t[16];
 #pragma unroll
@@ -653,12 +708,12 @@ struct OutMaps {
 // HIFI (SLFP_CONV_SPLIT_OPERANDS): three passes over K into the same accumulator - pass 0: x_hi * w_hi, pass 1: x_hi * w_lo,
 // pass 2: x_lo * w_hi - with (hi, lo) the float16 pair of a value.  The decode table holds hi in the low and lo in the
 // high half of an entry, the decode warps pick the half per K block; the weight rows are [hi | lo].
-template <int BLOCK_N, int GRAN, int DW, bool STG, bool HIFI = false, bool NODEC = false>
+template <int BLOCK_N, int GRAN, int DW, bool STG, bool HIFI = false, bool NODEC = false, bool A16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ OutMaps omaps, const Params p) {
-    using C = Cfg<BLOCK_N, STG, NODEC>;
-    static_assert(!NODEC || (GRAN == 64 && !HIFI), "e4m3 operands: whole 64-channel K blocks");
+    using C = Cfg<BLOCK_N, STG, NODEC, A16>;
+    static_assert(!NODEC || (GRAN == 64 && !HIFI), "e4m3 / float16 operands: whole 64-channel K blocks");
     static_assert(!STG || (BLOCK_N == 128 && DW == 8 && GRAN == 64), "staged epilogue: 128-column tiles, 16 epilogue warps");
     static_assert(!HIFI || !STG, "the split-operand mode uses the generic epilogue");
     using R = Roles<DW>;
@@ -671,10 +726,11 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_a = smem;                                   // [stages][128 rows][128 B]   (absent when A lives in TMEM)
     uint8_t* s_b = s_a + ((C::kATmem || NODEC) ? 0 : C::kStages * kABytes);   // [stages][BLOCK_N rows][128 B] (NODEC: 64 B)
-    uint8_t* s_code = s_b + C::kStages * C::kBBytes;       // [kCodeStages][128 pixels][64 B]
-    uint8_t* s_stage = s_code + kCodeStages * kCodeBytes;  // STG: [2][4 groups][128][64 B] float16 + [2][4][128][32 B] codes
+    uint8_t* s_code = s_b + C::kStages * C::kBBytes;       // [kCodeStages][128 pixels][64 B]   (A16: 128 B rows)
+    uint8_t* s_stage = s_code + kCodeStages * C::kCodeTile;  // STG: [2][4 groups][128][64 B] float16 + [2][4][128][32 B] codes
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stage + C::kStageBytes);
-    float* s_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_lut) + C::kLutB);   // [2][BLOCK_N]
+    uint32_t* s_olut = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_lut) + C::kLutB);   // [258][32] (store_f16)
+    float* s_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_olut) + C::kOutLutB);   // [2][BLOCK_N]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + C::kParBytes);
     uint64_t* bar_cfull = s_bar;                           // [kCodeStages]  1 arrive.expect_tx
     uint64_t* bar_cempty = bar_cfull + kCodeStages;        // [kCodeStages]  8 decode warps
@@ -703,6 +759,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         uint32_t e = (uint32_t)__half_as_ushort(hi);
         if (HIFI) e |= (uint32_t)__half_as_ushort(__float2half_rn(f - __half2float(hi))) << 16;
         s_lut[i] = e;
+    }
+    if (C::kOutLutB != 0 && p.epi.store_f16) {
+        // raw post-ReLU codes 0..257 (the byte path saturates at 255) -> float16 of the value the consumer's table would decode
+        for (int i = tid; i < kOutLutEntries * C::kOutLutCopies; i += kThreads) {
+            const uint32_t c = (uint32_t)(i / C::kOutLutCopies);
+            s_olut[i] = (uint32_t)__half_as_ushort(__float2half_rn(decode_act_any(c > 255u ? 255u : c, p.epi.next_fmt, c_pow2frac)));
+        }
     }
     if (warp == kWarpCode && lane == 0) {
         ptx::prefetch_tmap(&tmap_x);
@@ -783,10 +846,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     }
                     PROF(a, ptx::mbar_wait(ptx::smem_u32(NODEC ? &bar_empty[cs] : &bar_cempty[cs]), cphase ^ 1u, 1u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                     const uint32_t full = ptx::smem_u32(NODEC ? &bar_full[cs] : &bar_cfull[cs]);
-                    const uint32_t dst = ptx::smem_u32(s_code + cs * kCodeBytes);
+                    const uint32_t dst = ptx::smem_u32(s_code + cs * C::kCodeTile);
                     if (GRAN == 64) {
                         if (ptx::elect_one()) {
-                            ptx::mbar_arrive_expect_tx(full, (uint32_t)kCodeBytes + (NODEC ? (uint32_t)C::kBBytes : 0u));
+                            ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kCodeTile + (NODEC ? (uint32_t)C::kBBytes : 0u));
                             if (NODEC)                  // the e4m3 weight tile of this K block rides on the same barrier
                                 ptx::tma_load_2d(ptx::smem_u32(s_b + cs * C::kBBytes), &tmap_w, full, kbt * kBK, (tile % p.n_tiles) * BLOCK_N);
                             if (kb >= p.nkb1)           // concatenated second input: 1x1 window at (ho*sh2, wo*sw2)
@@ -858,8 +921,8 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         // per K block) made this thread the slowest stage of the pipeline - 51 % of its life between the first MMA
         // and the commit of a K block (tools/role_profile.py).  Descriptors differ only in their low word.
         constexpr uint32_t idesc = ptx::make_idesc(0u, kBM, BLOCK_N);
-        constexpr uint32_t kDescHi = NODEC ? ((512u >> 4) | (1u << 14) | (4u << 29))      // SBO 512 B, version 1, SWIZZLE_64B
-                                           : ((1024u >> 4) | (1u << 14) | (2u << 29));    // SBO 1024 B, version 1, SWIZZLE_128B
+        constexpr uint32_t kDescHi = (NODEC && !A16) ? ((512u >> 4) | (1u << 14) | (4u << 29))      // SBO 512 B, version 1, SWIZZLE_64B
+                                                     : ((1024u >> 4) | (1u << 14) | (2u << 29));    // SBO 1024 B, version 1, SWIZZLE_128B
         const uint32_t a_lo0 = ((ptx::smem_u32(NODEC ? s_code : s_a) >> 4) & 0x3fffu) | (1u << 16);
         const uint32_t b_lo0 = ((ptx::smem_u32(s_b) >> 4) & 0x3fffu) | (1u << 16);
         PROF_VARS;
@@ -876,13 +939,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 const long long prof_t = clock64();
 #endif
                 if (ptx::elect_one()) {
-                    const uint32_t a_lo = a_lo0 + stage * (uint32_t)((NODEC ? kCodeBytes : kABytes) >> 4);
+                    const uint32_t a_lo = a_lo0 + stage * (uint32_t)((NODEC ? C::kCodeTile : kABytes) >> 4);
                     const uint32_t b_lo = b_lo0 + stage * (uint32_t)(C::kBBytes >> 4);
                     const uint32_t a_tmem = tmem_base + (uint32_t)C::kATmemCol + stage * 32u;
 #pragma unroll
-                    for (int k = 0; k < (NODEC ? kBK / 32 : kBK / 16); ++k) {
+                    for (int k = 0; k < ((NODEC && !A16) ? kBK / 32 : kBK / 16); ++k) {
                         const uint64_t bd = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + 2u * k);
-                        if (NODEC)                      // e4m3 x e4m3, K = 32 per instruction: 32 bytes = 2 descriptor units per step
+                        if (NODEC && !A16)              // e4m3 x e4m3, K = 32 per instruction: 32 bytes = 2 descriptor units per step
                             ptx::mma_f8_ss(d_tmem, ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * k), bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         else if (C::kATmem)
                             ptx::mma_f16_ts(d_tmem, a_tmem + k * 8, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -1013,6 +1076,9 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int mode = p.epi_mode;
         const bool sfp33 = p.epi.next_fmt == SLFP_FMT_SFP33_RELU || (p.epi.layerout && p.epi.next_fmt == SLFP_FMT_SFP33);
         const uint32_t s_mul = ptx::smem_u32(s_par), s_add = s_mul + BLOCK_N * 4;
+        // output table of store_f16: entry address = (raw code << 6) + this, raw code = (bits >> 18 | 19) - base
+        const uint32_t olut_rel = (ptx::smem_u32(s_olut) + (uint32_t)(lane % C::kOutLutCopies) * 4u -
+                                   (sfp33 ? 0x76Fu : 0xEDFu) * (uint32_t)(C::kOutLutCopies * 4)) | (C::kOutLutCopies == 16 ? 1u : 0u);
         int staged_n0 = -1;
         PROF_VARS;
         // per tile: stage the per-channel vectors when the channel tile changes, then wait for the accumulator
@@ -1199,21 +1265,21 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const uint32_t tacc = tile_begin(ti, tile);
             if (kGroups == 2) {
                 if (mode == 1) {
-                    if (sfp33) epilogue_fast<BLOCK_N, 2, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
-                    else epilogue_fast<BLOCK_N, 2, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    if (sfp33) epilogue_fast<BLOCK_N, 2, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
+                    else epilogue_fast<BLOCK_N, 2, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
                 } else if (mode == 2) {
-                    if (sfp33) epilogue_fast<BLOCK_N, 2, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
-                    else epilogue_fast<BLOCK_N, 2, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    if (sfp33) epilogue_fast<BLOCK_N, 2, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
+                    else epilogue_fast<BLOCK_N, 2, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
                 } else {
                     epilogue_slab<BLOCK_N, 2>(p, tile, tacc, quad, half, lane);
                 }
             } else {
                 if (mode == 1) {
-                    if (sfp33) epilogue_fast16<BLOCK_N, 4, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
-                    else epilogue_fast16<BLOCK_N, 4, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    if (sfp33) epilogue_fast16<BLOCK_N, 4, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
+                    else epilogue_fast16<BLOCK_N, 4, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
                 } else if (mode == 2) {
-                    if (sfp33) epilogue_fast16<BLOCK_N, 4, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
-                    else epilogue_fast16<BLOCK_N, 4, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add);
+                    if (sfp33) epilogue_fast16<BLOCK_N, 4, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
+                    else epilogue_fast16<BLOCK_N, 4, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
                 } else {
                     epilogue_slab<BLOCK_N, 4>(p, tile, tacc, quad, half, lane);
                 }
@@ -1243,10 +1309,10 @@ static PFN driver_fn(const char* name) {
     return nullptr;
 }
 
-template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false, bool NODEC = false>
+template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false, bool NODEC = false, bool A16 = false>
 static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const OutMaps& om, const Params& p, cudaStream_t st) {
-    using C = Cfg<BLOCK_N, STG, NODEC>;
-    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI, NODEC>;
+    using C = Cfg<BLOCK_N, STG, NODEC, A16>;
+    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI, NODEC, A16>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -1310,13 +1376,18 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     using namespace v2;
     const bool fast = epi->next_fmt == SLFP_FMT_SLFP34_RELU || epi->next_fmt == SLFP_FMT_SFP33_RELU;
     if (d->fmt != SLFP_FMT_SLFP34_ACT && d->fmt != SLFP_FMT_SFP33 && d->fmt != SLFP_FMT_SLFP34_RELU && d->fmt != SLFP_FMT_SFP33_RELU &&
-        d->fmt != SLFP_FMT_SFP33_SFAST && d->fmt != SLFP_FMT_E4M3)
+        d->fmt != SLFP_FMT_SFP33_SFAST && d->fmt != SLFP_FMT_E4M3 && d->fmt != SLFP_FMT_F16Q)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: activation code format %d", d->fmt);
     if (epi->y_codes && (epi->k_phys_out % 16 != 0 || epi->k_phys_out < d->k))
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: k_phys_out=%d", epi->k_phys_out);
     if (epi->y_codes && fast && !epi->relu)
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: post-ReLU code formats need relu=1");
     const bool e4m3_out = epi->y_codes && epi->next_fmt == SLFP_FMT_E4M3;
+    const bool a16 = d->fmt == SLFP_FMT_F16Q;       // the activation tensor is the float16 A operand itself
+    if (a16 && (d->c_phys % 64 != 0 || d->flags != 0 || d2))
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: SLFP_FMT_F16Q input needs c_phys %% 64 == 0, no flags, no second input");
+    if (epi->store_f16 && (!epi->y_codes || !fast || epi->y_codes2 || epi->y_f16 || epi->y_f32 || epi->residual || epi->layerout))
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: store_f16 is a form of the codes-only epilogue (post-ReLU format, one consumer)");
     const bool nodec = (d->flags & SLFP_CONV_E4M3_OPERANDS) != 0;
     if (nodec && (d->fmt != SLFP_FMT_E4M3 || d->c_phys % 64 != 0 || (d->flags & SLFP_CONV_SPLIT_OPERANDS) || d2))
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: e4m3 operands need SLFP_FMT_E4M3 codes, c_phys %% 64 == 0, no split operands, no second input");
@@ -1382,11 +1453,27 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     }
     // Staged (TMA) epilogue for the epilogue-bound mode-2 layers (block tails, short-K fused tails): 128-column tiles.
     static const int stg_max_kb = getenv("SLFP_STG_MAXKB") ? atoi(getenv("SLFP_STG_MAXKB")) : 8;
+    if (epi->store_f16 && p.epi_mode != 1)
+        return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: store_f16 needs the codes-only fast epilogue (folded affine, relu, k %% 16 == 0)");
     const bool stg = !hifi && !nodec && p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
                      (((uintptr_t)epi->residual) & 15u) == 0;
     int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
-    if (!stg && !nodec && bn > 64) {
+    if (epi->store_f16 && !a16 && bn > 128) bn = 128;       // the 256-column decode variant has no room for the output table
+    if (a16 && !stg && bn > 64) {
+        // same wave-quantisation model for the no-decode float16 form: a K block costs about its MMA time
+        // (256 / 128 / 64 cycles) plus a fixed ~60
+        const int sms = num_sms();
+        double best = 1e30;
+        int best_bn = bn;
+        for (int cand = bn; cand >= 64; cand >>= 1) {
+            const long tiles = (long)p.m_tiles * ((d->k + cand - 1) / cand);
+            const double t = (double)((tiles + sms - 1) / sms) * (cand + 60.0);
+            if (t < best * 0.97) { best = t; best_bn = cand; }
+        }
+        bn = best_bn;
+    }
+    if (!stg && !nodec && !a16 && bn > 64) {
         // Tile width against wave quantisation (small-M layers: VGG-16 @2x2 / @4x4, ResNet-50 stage 4).  One CTA per SM works
         // through ceil(tiles / SMs) tiles; a tile costs ~num_kb x (cycles per K block), measured ~1 180 for the 256-column
         // form (A staged in shared memory) and ~640 for 128 / 64 columns (A in tensor memory) - the decode side, not the
@@ -1424,14 +1511,18 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     }
     p.plain_1x1 = (d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0 &&
                    d->pad_h_extra == 0 && d->pad_w_extra == 0 && p.cblocks && getenv("SLFP_NO_PLAIN_1X1") == nullptr) ? 1 : 0;
+    // SLFP_FMT_F16Q: 2-byte elements, 128-byte rows with the 128-byte swizzle (the MMA's canonical K-major operand layout)
+    const cuuint64_t esz = a16 ? 2u : 1u;
+    const CUtensorMapDataType x_type = a16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    const CUtensorMapSwizzle x_swz64 = a16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     if (p.plain_1x1) {
         // 1x1 / stride 1: A is the [M, C] code matrix itself - a tiled 2-D load (rows beyond M zero-filled)
         const cuuint64_t gdim[2] = {(cuuint64_t)d->c_phys, (cuuint64_t)p.M};
-        const cuuint64_t gstr[1] = {(cuuint64_t)d->c_phys};
+        const cuuint64_t gstr[1] = {(cuuint64_t)d->c_phys * esz};
         const cuuint32_t box[2] = {64u, (cuuint32_t)kBM};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult cr = enc_tiled(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(x_codes), gdim, gstr, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+        CUresult cr = enc_tiled(&tmap_x, x_type, 2, const_cast<uint8_t*>(x_codes), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, x_swz64, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled(codes) failed (%d)", (int)cr);
     } else {
@@ -1439,15 +1530,15 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         // lower corner = -pad, upper corner = pad - (filter - 1) * dilation (relative to the tensor's far edge),
         // traversed with the convolution stride; the filter tap (r, s) is the per-load offset.
         const cuuint64_t gdim[4] = {(cuuint64_t)d->c_phys, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
-        const cuuint64_t gstr[3] = {(cuuint64_t)d->c_phys, (cuuint64_t)d->c_phys * d->w, (cuuint64_t)d->c_phys * d->w * d->h};
+        const cuuint64_t gstr[3] = {(cuuint64_t)d->c_phys * esz, (cuuint64_t)d->c_phys * d->w * esz, (cuuint64_t)d->c_phys * d->w * d->h * esz};
         const int lower[2] = {-d->pad_w, -d->pad_h};
         const int upper[2] = {d->pad_w + d->pad_w_extra - (d->s - 1) * d->dil_w, d->pad_h + d->pad_h_extra - (d->r - 1) * d->dil_h};
         const cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
-        CUresult cr = enc_im2col(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x_codes), gdim, gstr, lower, upper,
+        CUresult cr = enc_im2col(&tmap_x, x_type, 4, const_cast<uint8_t*>(x_codes), gdim, gstr, lower, upper,
                                  (cuuint32_t)(p.cblocks ? 64 : 16), (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  // a decode thread owns a pixel row: 64-byte rows are swizzled so that the 16-byte chunks
                                  // of 8 consecutive rows fall into 8 different bank groups
-                                 p.cblocks ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 p.cblocks ? x_swz64 : CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeIm2col failed (%d)", (int)cr);
     }
@@ -1488,7 +1579,13 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         if (epi->y_codes) ok = ok && out_map(&om.c1, epi->y_codes, false);
         if (epi->y_codes2) ok = ok && out_map(&om.c2, epi->y_codes2, false);
         if (!ok) return set_error(SLFP_ERR_DRIVER, "conv2d_fwd: cuTensorMapEncodeTiled(outputs) failed");
+        if (a16) return launch<128, 64, 8, true, false, true, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
         return launch<128, 64, 8, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
+    }
+    if (a16) {
+        if (bn == 64) return launch<64, 64, 8, false, false, true, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
+        if (bn == 128) return launch<128, 64, 8, false, false, true, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
+        return launch<256, 64, 8, false, false, true, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
     }
 #define SLFP_V2_HIFI(BN)                                                                                         \
     if (hifi && bn == BN) {                                                                                      \

@@ -34,13 +34,15 @@ def _k32(K):
 
 
 class _T:
-    """A device tensor of the plan: NHWC, kind in {'codes', 'f16', 'f32'}."""
-    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt", "c_logical")
+    """A device tensor of the plan: NHWC, kind in {'codes', 'q16', 'f16', 'f32'}.  'q16' (SLFP_FMT_F16Q) holds the float16
+    image of the codes of format `qfmt` - the tensor-core operand itself - for a decode-bound dense consumer."""
+    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt", "c_logical", "qfmt")
 
     def __init__(self, buf, n, h, w, c, cp, kind, kdiv=None, fmt=None):
         self.buf, self.n, self.h, self.w, self.c, self.cp, self.kind, self.kdiv = buf, n, h, w, c, cp, kind, kdiv
         self.fmt = fmt                  # code format of a 'codes' tensor (signed quantizer codes or post-ReLU codes)
         self.c_logical = c              # float16 outputs of a pad_k layer: c is the physical channel count
+        self.qfmt = None                # 'q16': the code format whose values the halves are
 
 
 def _ceil(v, m):
@@ -66,6 +68,10 @@ class Plan:
         # SFP-7 plans exchange e4m3 bytes (SLFP_FMT_E4M3): every SFP<3,3> value is an e4m3 number, so the codes ARE the
         # tensor-core operand (kind::f8f6f4, no decode) and the encoder is an exact round-half-even cvt
         self.e4m3 = (q_bit == 7 and not high_fidelity and not os.environ.get("SLFP_NO_E4M3")) if e4m3 is None else bool(e4m3)
+        # SLFP-8 plans: a dense producer whose only consumer is a decode-bound dense layer (3x3, or a short-K block tail)
+        # stores the float16 image of its codes (SLFP_FMT_F16Q, SlfpEpilogue.store_f16) and the consumer's TMA drops that
+        # straight into the MMA's operand layout - no decode table, no decode warps, bit-identical results
+        self.f16q = q_bit == 8 and not high_fidelity and not os.environ.get("SLFP_NO_F16Q")
         self.batch, self.dev, self.q_bit = batch, device, q_bit
         self.afmt, self.wfmt = nv.fmt_for(q_bit, "act"), nv.fmt_for(q_bit, "weight")
         self.static_weights = static_weights
@@ -85,6 +91,15 @@ class Plan:
         if kind == "codes":
             cp = cp or _ceil(c, 16)
             buf = torch.zeros((n, h, w, cp), dtype=torch.uint8, device=self.dev)
+        elif kind == "q16":
+            cp = cp or c
+            assert cp % 64 == 0
+            buf = torch.zeros((n, h, w, cp), dtype=torch.float16, device=self.dev)
+            self.bytes_hbm += buf.numel() * 2
+            self.keep.append(buf)
+            t = _T(buf, n, h, w, c, cp, kind, kdiv, nv.FMT_F16Q)
+            t.qfmt = fmt
+            return t
         else:
             cp = c
             buf = torch.empty((n, h, w, c), dtype=torch.float16 if kind == "f16" else torch.float32, device=self.dev)
@@ -170,12 +185,13 @@ class Plan:
         return _ceil(k, 16) if k < 48 else _ceil(k, 64)
 
     def conv(self, x, mod, bn=None, relu=False, residual=None, codes=(), f16=False, f32=False, linear=False,
-             relu_codes=True, layerout=0, pad_k=False, signed_fast=False):
+             relu_codes=True, layerout=0, pad_k=False, signed_fast=False, q16=False):
         """One fused convolution / linear layer.  `codes`: divisors (Ka of the consumers) to quantize-on-store
         with (at most two distinct).  Returns {'codes': {kdiv: _T}, 'f16': _T | None, 'f32': _T | None}.
         relu_codes: the consumers are dense layers / max-pools (which read the unsigned post-ReLU code format,
-        written by the 2-instruction encoder); pass False when a depthwise / grouped layer consumes the codes."""
-        assert x.kind == "codes"
+        written by the 2-instruction encoder); pass False when a depthwise / grouped layer consumes the codes.
+        q16: the single consumer is a dense layer that should read the float16 image of the codes (Plan.f16q)."""
+        assert x.kind in ("codes", "q16")
         if linear:
             K, C = mod.weight.shape
             R = S = 1
@@ -262,14 +278,22 @@ class Plan:
             ofmt = nv.FMT_SFP33_SFAST
         else:
             ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and x.cp % 16 == 0 and (groups == 1 or fast_dw)) else self.afmt
+        # store_f16: the codes-only fast epilogue of the warp-specialised dense kernel (relu, one consumer, post-ReLU format)
+        # Storing halves instead of bytes costs the PRODUCER ~0.5 us per 2^20 output elements (measured on the 1x1 reduce
+        # layers, whose 8 epilogue warps are their critical path) against a flat ~12-18 us the 3x3 consumer saves by not
+        # decoding: worth it below ~16 M elements (ResNet-50 stages 3-4 at batch 256)
+        q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS", 16 << 20))
+        as_q16 = (q16 and self.f16q and dense and x.cp % 16 == 0 and len(kds) == 1 and relu and bn is not None and K % 64 == 0
+                  and Kk == K and ofmt == nv.relu_fmt(self.afmt) and not f16 and not f32 and residual is None and not layerout
+                  and x.n * Ho * Wo * K <= q16_max)
         for i, kd in enumerate(kds):
-            t = self._alloc(x.n, Ho, Wo, K, "codes", kd, cp=kp, fmt=ofmt)
+            t = self._alloc(x.n, Ho, Wo, K, "q16" if as_q16 else "codes", kd, cp=kp, fmt=ofmt)
             out["codes"][kd] = t
             if i == 0:
                 epi.y_codes, epi.next_k_div = t.buf.data_ptr(), kd
             else:
                 epi.y_codes2, epi.next_k_div2 = t.buf.data_ptr(), kd
-        epi.next_fmt, epi.k_phys_out = ofmt, kp
+        epi.next_fmt, epi.k_phys_out, epi.store_f16 = ofmt, kp, 1 if as_q16 else 0
         assert Kk == K or not kds or kp == Kk
         if f16:
             out["f16"] = self._alloc(x.n, Ho, Wo, Kk, "f16")      # physical channels (pad channels hold 0.0)
@@ -286,8 +310,8 @@ class Plan:
             fl = 2.0 * x.n * Ho * Wo * K * float(np.prod(mod.orig.weight.shape[1:]))
         self.flops += fl
         # algorithmic HBM bytes of the launch: codes in, everything written, the weight operand, the residual read
-        by = x.buf.numel() + wbuf.numel() * wbuf.element_size() + (residual.buf.numel() * residual.buf.element_size() if residual is not None else 0)
-        by += sum(t.buf.numel() for t in out["codes"].values()) + sum(out[k].buf.numel() * out[k].buf.element_size() for k in ("f16", "f32") if out[k] is not None)
+        by = x.buf.numel() * x.buf.element_size() + wbuf.numel() * wbuf.element_size() + (residual.buf.numel() * residual.buf.element_size() if residual is not None else 0)
+        by += sum(t.buf.numel() * t.buf.element_size() for t in out["codes"].values()) + sum(out[k].buf.numel() * out[k].buf.element_size() for k in ("f16", "f32") if out[k] is not None)
         self.conv_flops.append((fl, groups == 1, f"{C}->{K} {R}x{S} s{stride[0]} @{x.h}", by))
         return out
 
@@ -497,6 +521,7 @@ def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", stat
         residual, fuse_downsample = "f32", False
     P = Plan(batch, device, model.qbit if hasattr(model, "qbit") else model.conv1.q_bit, static_weights, high_fidelity)
     res_f16 = residual == "f16"
+    q16_edges = P.f16q
     x = P.input_nchw(3, size, size)
     blocks = [b for li in range(1, 5) for b in getattr(model, f"layer{li}")]
 
@@ -525,13 +550,15 @@ def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", stat
     cur_res = None
     for i, b in enumerate(blocks):
         nxt = blocks[i + 1] if i + 1 < len(blocks) else None
-        o1 = P.conv(cur_codes[_k32(b.conv1.Ka)], b.conv1, bn=b.bn1, relu=True, codes=[_k32(b.conv2.Ka)])
-        o2 = P.conv(o1["codes"][_k32(b.conv2.Ka)], b.conv2, bn=b.bn2, relu=True, codes=[_k32(b.conv3.Ka)])
-        need_val = nxt is None or nxt.downsample is None        # someone adds / pools the un-quantized value
         ds0 = b.downsample[0] if b.downsample is not None else None
         fuse = (fuse_downsample and ds0 is not None and res_f16 and ds0.kernel_size == (1, 1) and ds0.padding == (0, 0)
                 and ds0.bias is None and b.conv3.bias is None and cur_codes[_k32(ds0.Ka)].cp % 64 == 0
-                and o2["codes"][_k32(b.conv3.Ka)].cp % 64 == 0 and b.conv3.out_channels % 16 == 0)
+                and b.conv2.out_channels % 64 == 0 and b.conv3.out_channels % 16 == 0)
+        # conv1 -> conv2 (3x3: nine taps x N tiles of table look-ups per input code) and conv2 -> conv3 (short K) exchange
+        # float16 images; the dual-input tail of a down-sampling block reads codes on both inputs
+        o1 = P.conv(cur_codes[_k32(b.conv1.Ka)], b.conv1, bn=b.bn1, relu=True, codes=[_k32(b.conv2.Ka)], q16=q16_edges)
+        o2 = P.conv(o1["codes"][_k32(b.conv2.Ka)], b.conv2, bn=b.bn2, relu=True, codes=[_k32(b.conv3.Ka)], q16=q16_edges and not fuse)
+        need_val = nxt is None or nxt.downsample is None        # someone adds / pools the un-quantized value
         if fuse:
             # block tail and downsample branch as ONE GEMM: no downsample launch, no float16 round trip of its output
             o3 = P.conv_dual(o2["codes"][_k32(b.conv3.Ka)], b.conv3, b.bn3, cur_codes[_k32(ds0.Ka)], ds0, b.downsample[1],
@@ -576,7 +603,9 @@ def compile_vgg16(model, batch, size=32, device="cuda", static_weights=False):
             assert isinstance(bn, nn.BatchNorm2d) and isinstance(seq[i + 2], nn.ReLU)
             ci = convs.index(m)
             nxt_k = _k32(convs[ci + 1].Ka) if ci + 1 < len(convs) else _k32(fcs[0].Ka)
-            cur = P.conv(cur, m, bn=bn, relu=True, codes=[nxt_k])["codes"][nxt_k]
+            # conv -> conv edges (no pool in between) hand over float16 images: the 3x3 consumer skips its decode stage
+            to_conv = i + 3 < len(seq) and isinstance(seq[i + 3], nn.Conv2d)
+            cur = P.conv(cur, m, bn=bn, relu=True, codes=[nxt_k], q16=to_conv)["codes"][nxt_k]
             i += 3
         elif isinstance(m, nn.MaxPool2d):
             cur = P.maxpool(cur, m.kernel_size, m.stride, m.padding)

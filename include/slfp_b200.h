@@ -67,7 +67,14 @@ enum {
      * c_phys % 64 == 0 run tcgen05.mma kind::f8f6f4 straight on the TMA-loaded code tile (no decode warps, no operand
      * rounding, 2x the f16 rate - SLFP_CONV_E4M3_OPERANDS); the encoder is one cvt.rn.satfinite.e4m3x2.f32 behind the
      * reference's clamps, i.e. round-half-EVEN like utils/sfp_quant.py:69 (the other fused formats round ties up). */
-    SLFP_FMT_E4M3 = 7
+    SLFP_FMT_E4M3 = 7,
+    /* Activations stored as the float16 IMAGE of the quantized value - float16_rn(decode(code)), the very number the
+     * dense kernel's decode table hands to the tensor core - 2 bytes per element, NHWC, c_phys % 64 == 0.  The tensor IS
+     * the tcgen05 kind::f16 A operand: TMA im2col drops it into 128-byte-swizzled shared memory and the MMA reads it
+     * there (no decode table, no decode warps).  Written by a fused epilogue with SlfpEpilogue.store_f16; a layer's
+     * result is bit-identical to the same layer fed with the codes.  Trades 1 B/element of HBM traffic for the
+     * per-(tap x output-tile) table look-ups of the consumer - used where the consumer is decode-bound (3x3 layers). */
+    SLFP_FMT_F16Q = 8
 };
 
 enum { SLFP_ACT_STL = 0, SLFP_ACT_SWISH = 1, SLFP_ACT_SIGMOID = 2 };
@@ -236,6 +243,9 @@ typedef struct {
      * 64-72, MobileNetV1_swish, VGG16_gelu).  0 = off; 1 = the reference's arithmetic including NaN at exact 0 (its
      * `2^(-8)` is XOR: no low clamp, 0 * NaN); 2 = exact 0 stays 0 (the evidently intended value).  Generic epilogue. */
     int layerout;
+    /* bit 0: y_codes receives SLFP_FMT_F16Q halves (k_phys_out per pixel) instead of the code bytes of next_fmt - the
+     * float16 image of exactly the code the byte path would have stored (post-ReLU formats, codes-only fast epilogue). */
+    int store_f16;
 } SlfpEpilogue;
 
 /* Weight preparation: replaces `self.quantize_weight(self.weight/self.Kw)` (conv2d_func.py:22):

@@ -114,3 +114,23 @@ def decode_codes(orc, codes, fmt):
     if fmt == nv.FMT_E4M3:
         return decode_e4m3(codes)
     return orc.decode(codes, fmt)
+
+
+def decode_q16(orc, halves, qfmt):
+    """SLFP_FMT_F16Q tensor (float16 images of the codes of format qfmt) -> the exact grid values: every half must BE the
+    float16 image of a code's value (asserted), and is mapped back to that value."""
+    table = decode_codes(orc, np.arange(256, dtype=np.uint8), qfmt).astype(np.float32)
+    table = table[np.isfinite(table)]
+    img = table.astype(np.float16)
+    order = np.argsort(img, kind="stable")
+    img_s, tab_s = img[order], table[order]
+    h = np.asarray(halves)
+    pos = np.clip(np.searchsorted(img_s, h), 0, len(img_s) - 1)
+    assert (img_s[pos] == h).all(), "a float16 activation that is not the image of any code"
+    return tab_s[pos]
+
+
+def decode_tensor(orc, t):
+    """Values of an engine tensor of kind 'codes' or 'q16'."""
+    arr = t.buf.cpu().numpy()
+    return decode_q16(orc, arr, t.qfmt) if t.fmt == nv.FMT_F16Q else decode_codes(orc, arr, t.fmt)

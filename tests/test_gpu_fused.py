@@ -482,3 +482,65 @@ def test_shufflenet_branch_fast_forms_equal_generic_forms(orc, C, H, stride, e4m
     _, lq = orc.quantize(yf, 3, want_codes=False, bugcompat=False)
     assert (lq == yf).all()
     assert (yf == yg).mean() > 0.97 and np.abs(yf - yg).max() <= 0.15 * np.abs(yg).max()
+
+
+@pytest.mark.parametrize("N,C,H,K,k,stride,pad,res", [
+    (2, 64, 14, 64, 3, 1, 1, False),        # stage-1 3x3 (64-column tiles)
+    (2, 128, 12, 128, 3, 2, 1, False),      # strided 3x3
+    (1, 256, 9, 256, 3, 1, 1, False),       # 36 K blocks
+    (2, 64, 11, 256, 1, 1, 0, True),        # block tail: residual in, float16 + two code tensors out (staged epilogue)
+    (2, 512, 7, 2048, 1, 1, 0, True),       # 8 K blocks, 16 N tiles
+    (1, 1024, 5, 256, 1, 1, 0, False),      # 1x1 reduce, 16 K blocks
+    (2, 192, 6, 320, 3, 1, 1, False),       # ragged N (2.5 tiles of 128), 27 K blocks
+    (3, 64, 7, 1024, 1, 1, 0, True),        # M tail (147 rows)
+])
+def test_f16_image_activations_equal_the_codes_path(orc, N, C, H, K, k, stride, pad, res):
+    """SLFP_FMT_F16Q: a dense layer fed with the float16 image of its input codes (TMA -> swizzled shared memory -> MMA, no
+    decode stage) produces bit-identical outputs to the same layer fed with the codes; SlfpEpilogue.store_f16 writes
+    exactly float16(decode(code)) of the code the byte path stores."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib, dev, st = nv.lib(), torch.device("cuda:0"), nv.stream()
+    rng = np.random.default_rng(N * 1000 + C + K)
+    rfmt = nv.FMT_SLFP34_RELU
+    codes_in = rng.integers(0, 256, (N, H, H, C), dtype=np.uint8)
+    codes_in[rng.random(codes_in.shape) < 0.3] = 0
+    xv = orc.decode_relu(codes_in, False)
+    xc = torch.from_numpy(codes_in).to(dev)
+    xh = torch.from_numpy(_h(xv)).to(dev)
+    w = torch.from_numpy((rng.standard_normal((K, C, k, k)) * 0.2).astype(np.float32)).to(dev)
+    kw = float(w.abs().max() / 15.5)
+    Ho = (H + 2 * pad - (k - 1) - 1) // stride + 1
+    mul_t = torch.from_numpy((rng.uniform(0.5, 1.5, K) * kw * 0.05).astype(np.float32)).to(dev)
+    add_t = torch.from_numpy((rng.standard_normal(K) * 0.3).astype(np.float32)).to(dev)
+    res_t = torch.from_numpy(np.abs(rng.standard_normal((N, Ho, Ho, K))).astype(np.float16)).to(dev) if res else None
+
+    def run(f16_in, store_f16):
+        d = nv.SlfpConvDesc(N, H, H, C, C, K, k, k, stride, stride, pad, pad, 1, 1, 1, nv.FMT_F16Q if f16_in else rfmt, 0, 0)
+        pitch = lib.slfp_conv_wpitch(ctypes.byref(d))
+        wh = torch.empty((K * pitch,), dtype=torch.float16, device=dev)
+        so, sc, sr, ss = w.stride()
+        nv.check(lib.slfp_prepare_weights(ctypes.byref(d), w.data_ptr(), so, sc, sr, ss, float(np.float32(kw)), nv.FMT_SLFP34_WGT,
+                                          wh.data_ptr(), None, None, st))
+        e = nv.SlfpEpilogue()
+        e.ch_mul, e.ch_add, e.relu = mul_t.data_ptr(), add_t.data_ptr(), 1
+        outs = {}
+        outs["c1"] = torch.full((N, Ho, Ho, K), 7, dtype=torch.float16 if store_f16 else torch.uint8, device=dev)
+        e.y_codes, e.next_k_div, e.next_fmt, e.k_phys_out, e.store_f16 = outs["c1"].data_ptr(), 0.23, rfmt, K, 1 if store_f16 else 0
+        if res:
+            outs["c2"] = torch.full((N, Ho, Ho, K), 7, dtype=torch.uint8, device=dev)
+            outs["y16"] = torch.full((N, Ho, Ho, K), 7, dtype=torch.float16, device=dev)
+            e.y_codes2, e.next_k_div2, e.y_f16 = outs["c2"].data_ptr(), 0.37, outs["y16"].data_ptr()
+            e.residual, e.residual_f16 = res_t.data_ptr(), 1
+        nv.check(lib.slfp_conv2d_fwd(ctypes.byref(d), (xh if f16_in else xc).data_ptr(), wh.data_ptr(), ctypes.byref(e), st))
+        torch.cuda.synchronize()
+        return {k_: v.cpu().numpy() for k_, v in outs.items()}
+
+    a, b = run(False, False), run(True, False)
+    assert a["c1"].std() > 10, "degenerate case: the output codes barely vary"
+    for key in a:
+        assert (a[key].view(np.uint8) == b[key].view(np.uint8)).all(), (key, float((a[key] != b[key]).mean()))
+    if not res:
+        want = _h(orc.decode_relu(a["c1"], False))
+        c_, d_ = run(False, True), run(True, True)
+        assert (c_["c1"].view(np.uint16) == want.view(np.uint16)).all()
+        assert (d_["c1"].view(np.uint16) == want.view(np.uint16)).all()

@@ -137,9 +137,8 @@ def _tap_views(key, mod, t, layers, orc, qbit, nv):
     target = getattr(mod, "orig", mod)
     li = layers.index(target)
     ref = orc.decode(G[f"{key}.tap{li:02d}"], fmt)                      # NCHW (or [n, c] for a linear layer)
-    from gpu_util import decode_codes
-    codes = t.buf.cpu().numpy()
-    got = decode_codes(orc, codes, t.fmt)
+    from gpu_util import decode_tensor
+    got = decode_tensor(orc, t)
     if hasattr(mod, "orig"):                                           # space-to-depth stem: [n, h/2, w/2, (dy, dx, c)]
         n, h2, w2, _ = got.shape
         c = ref.shape[1]
@@ -155,9 +154,11 @@ def _tap_views(key, mod, t, layers, orc, qbit, nv):
 def _encode_like(t, ref, mod, orc, qbit, nv):
     """The reference's input_q as codes in tensor t's own layout and code format (teacher forcing)."""
     from gpu_util import decode_codes
-    relu_fmt = t.fmt in (nv.FMT_SLFP34_RELU, nv.FMT_SFP33_RELU)
-    table = decode_codes(orc, np.arange(256, dtype=np.uint8), t.fmt).astype(np.float64)
-    if t.fmt == nv.FMT_E4M3:
+    q16 = t.fmt == nv.FMT_F16Q                              # float16 images of the codes of format t.qfmt
+    tfmt = t.qfmt if q16 else t.fmt
+    relu_fmt = tfmt in (nv.FMT_SLFP34_RELU, nv.FMT_SFP33_RELU)
+    table = decode_codes(orc, np.arange(256, dtype=np.uint8), tfmt).astype(np.float64)
+    if tfmt == nv.FMT_E4M3:
         table[(np.arange(256) & 0x78) == 0] = np.inf          # sub-normal e4m3 patterns are never produced (0 is code 0 / 0x80)
         table[0] = 0.0
     table = np.where(np.isfinite(table), table, np.inf)
@@ -166,12 +167,14 @@ def _encode_like(t, ref, mod, orc, qbit, nv):
     v = ref.astype(np.float64)
     if relu_fmt:
         assert (v >= 0).all()
-    v = np.where(np.abs(v) <= 1e-9, 0.0, v) if (relu_fmt or t.fmt == nv.FMT_E4M3) else v    # +-1e-10 is code 0 (0.0) in the fused formats
+    v = np.where(np.abs(v) <= 1e-9, 0.0, v) if (relu_fmt or tfmt == nv.FMT_E4M3) else v    # +-1e-10 is code 0 (0.0) in the fused formats
     pos = np.clip(np.searchsorted(tv, v * (1 - 1e-7) if relu_fmt else v - np.abs(v) * 1e-7), 0, 255)
     codes = order[pos].astype(np.uint8)
     assert np.allclose(table[codes], v, rtol=1e-6, atol=0), "reference value without a code"
     n = ref.shape[0]
-    out = np.zeros(tuple(t.buf.shape), np.uint8)
+    out = np.zeros(tuple(t.buf.shape), np.float16 if q16 else np.uint8)
+    if q16:
+        codes = table[codes].astype(np.float16)
     if hasattr(mod, "orig"):
         c, hh, ww = ref.shape[1:]
         out[..., :4 * c] = codes.reshape(n, c, hh // 2, 2, ww // 2, 2).transpose(0, 2, 4, 3, 5, 1).reshape(n, hh // 2, ww // 2, 4 * c)

@@ -73,15 +73,24 @@ RESNET50_LAYERS = [
 
 
 def bench_conv(batch=256, mode="f32", only=None, iters=10):
+    """mode: f32 | codes | rcodes | res; a trailing "16" (rcodes16, res16) feeds the layer with SLFP_FMT_F16Q float16 images;
+    "rq16" = rcodes with store_f16 (the producer side of that format)."""
     lib = nv.lib()
+    a16 = mode.endswith("16") and mode != "rq16"
+    store16 = mode == "rq16"
+    mode = "rcodes" if store16 else (mode[:-2] if a16 else mode)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for name, C, K, k, st, pad, H in RESNET50_LAYERS:
         if only and only not in name:
             continue
         Cp = 4 if C <= 4 else (C + 15) // 16 * 16
-        d = nv.SlfpConvDesc(batch, H, H, C, Cp, K, k, k, st, st, pad, pad, 1, 1, 1, nv.FMT_SLFP34_ACT)
+        if (a16 and Cp % 64) or (store16 and (Cp % 16 or K % 64)):
+            continue
+        d = nv.SlfpConvDesc(batch, H, H, C, Cp, K, k, k, st, st, pad, pad, 1, 1, 1, nv.FMT_F16Q if a16 else nv.FMT_SLFP34_ACT)
         Ho = (H + 2 * pad - (k - 1) - 1) // st + 1
         xc = torch.randint(16, 128, (batch, H, H, Cp), dtype=torch.uint8, device="cuda")
+        if a16:
+            xc = (xc.to(torch.float16) / 64).contiguous()
         pitch = lib.slfp_conv_wpitch(ctypes.byref(d))
         w = torch.randn(K, C, k, k, device="cuda") * 0.1
         wh = torch.empty(K * pitch, dtype=torch.float16, device="cuda")
@@ -104,18 +113,19 @@ def bench_conv(batch=256, mode="f32", only=None, iters=10):
             epi.y_codes, epi.next_k_div, epi.next_fmt, epi.k_phys_out, epi.relu = y.data_ptr(), 0.2, 4, K, 1
             out_b = 5
         else:
-            y = torch.empty((batch, Ho, Ho, K), dtype=torch.uint8, device="cuda")
+            y = torch.empty((batch, Ho, Ho, K), dtype=torch.float16 if store16 else torch.uint8, device="cuda")
+            epi.store_f16 = 1 if store16 else 0
             nfmt = 4 if (mode == "rcodes" and Cp >= 16) else nv.FMT_SLFP34_ACT
             epi.y_codes, epi.next_k_div, epi.next_fmt, epi.k_phys_out, epi.relu = y.data_ptr(), 0.2, nfmt, K, 1
             if mode == "rcodes":            # the fused pipeline's form: folded per-channel affine, post-ReLU codes
                 mul = torch.full((K,), 0.006, device="cuda"); add = torch.zeros(K, device="cuda")
                 epi.ch_mul, epi.ch_add = mul.data_ptr(), add.data_ptr()
-            out_b = 1
+            out_b = 2 if store16 else 1
         fn = lambda: nv.check(lib.slfp_conv2d_fwd(ctypes.byref(d), xc.data_ptr(), wh.data_ptr(), ctypes.byref(epi), nv.stream()))
         med, best = timeit(fn, iters=iters, flush=flush)
         flops = 2.0 * batch * Ho * Ho * K * C * k * k
-        byts = xc.numel() + y.numel() * out_b + wh.numel() * 2
-        print(json.dumps({"kernel": "conv_igemm", "layer": name, "out": mode, "ms": round(med, 4),
+        byts = xc.numel() * xc.element_size() + y.numel() * out_b + wh.numel() * 2
+        print(json.dumps({"kernel": "conv_igemm", "layer": name, "out": mode + ("16" if a16 else "") + ("+store_f16" if store16 else ""), "ms": round(med, 4),
                           "TFLOPs": round(flops / med / 1e9, 1), "frac_tensor": round(flops / med / 1e9 / PEAKS["bf16_tflops"], 3),
                           "GBps": round(byts / med / 1e6, 1), "frac_hbm": round(byts / med / 1e6 / PEAKS["hbm_gbs"], 3)}), flush=True)
 
