@@ -564,13 +564,17 @@ def main():
                     "avg_launch_ms": conv_ms * scale / max(len(dense), 1), "share_of_step": conv_ms / eager_ms,
                     "eager_instrumented_ms": round(eager_ms, 4), "graph_step_ms": round(step_ms, 4),
                     "per_entry_point_ms": {k: round(v, 4) for k, v in all_ms.items()}}
-        iq = prof.get("slfp_quantize_nchw_s2d_f32") or prof.get("slfp_quantize_nchw_f32")
+        iq = prof.get("slfp_quantize_nchw_s2d_f16q") or prof.get("slfp_quantize_nchw_s2d_f32") or prof.get("slfp_quantize_nchw_f32")
         if iq:
             a, b, _ = iq[0]
             iq_ms = a.elapsed_time(b)
-            by = plan.input.numel() * 4 + plan.taps[0][1].buf.numel()
+            t0 = plan.taps[0][1]
+            # algorithmic bytes: the float32 image read once + the INTERIOR of the output written once (8-bit codes, or the
+            # float16 images of the width-folded stem; its zero border is written once at plan build, not per step)
+            by = plan.input.numel() * 4 + t0.n * t0.h * t0.w * t0.cp * t0.buf.element_size()
             gbs = by / (iq_ms * 1e-3) / 1e9
-            roof_iq = {"kernel": "input quantizer inside the step (NCHW float32 -> NHWC / space-to-depth 8-bit codes)", "bound": "hbm",
+            roof_iq = {"kernel": "input quantizer inside the step (NCHW float32 -> space-to-depth " +
+                                 ("float16 images, SLFP_FMT_F16Q)" if t0.buf.element_size() == 2 else "8-bit codes)"), "bound": "hbm",
                        "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "launch_ms": iq_ms,
                        "algorithmic_bytes": by, "traffic": None}
         if not args.no_extras and args.config == "resnet50":

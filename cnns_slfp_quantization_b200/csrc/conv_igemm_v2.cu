@@ -126,7 +126,7 @@ struct Cfg {
     static constexpr int kStageBytes = STG ? 2 * kIoBytes + 2 * kCoBytes : 0;
     static constexpr int kATmemCol = 2 * BLOCK_N;           // first TMEM column of the A ring (32 columns per stage)
     static constexpr int kTmemCols = kATmem ? (2 * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
-    static constexpr int kParBytes = 2 * BLOCK_N * 4;       // this tile's per-channel mul / add (fast epilogues)
+    static constexpr int kParBytes = (STG ? 2 : 1) * 2 * BLOCK_N * 4;   // this tile's per-channel mul / add (fast epilogues; staged: double buffered)
     static constexpr int kLutB = NODEC ? 0 : kLutBytes;
     // SlfpEpilogue.store_f16: code -> float16 table of the NEXT layer's format for the epilogue.  Decode variants: one copy per
     // bank like the decode table (their decode warps already load the shared-memory pipe); no-decode variants: 16 copies
@@ -821,6 +821,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             static_assert(kCodeStages % 2 == 0, "the two producers alternate K blocks: a stage must always be filled by the same one");
             const uint32_t mine = warp == kWarpCode ? 0u : 1u;
             uint32_t cs = 0, cphase = 0, g = 0;
+            // no-decode variants, resident weights: with one N tile and a K-block count that divides the ring depth, stage s
+            // always holds the weight tile of K block s % num_kb - after the first trip round the ring only the activation
+            // tile is loaded (the width-folded stem re-read its 32 KB filter 170 times per CTA: a third of its L2 traffic)
+            const bool w_res_nd = NODEC && p.n_tiles == 1 && p.num_kb <= kCodeStages && (kCodeStages % p.num_kb) == 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const uint32_t m0 = (uint32_t)(tile / p.n_tiles) * kBM;
@@ -848,9 +852,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     const uint32_t full = ptx::smem_u32(NODEC ? &bar_full[cs] : &bar_cfull[cs]);
                     const uint32_t dst = ptx::smem_u32(s_code + cs * C::kCodeTile);
                     if (GRAN == 64) {
+                        const bool load_b = NODEC && !(w_res_nd && g >= (uint32_t)kCodeStages);
                         if (ptx::elect_one()) {
-                            ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kCodeTile + (NODEC ? (uint32_t)C::kBBytes : 0u));
-                            if (NODEC)                  // the e4m3 weight tile of this K block rides on the same barrier
+                            ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kCodeTile + (load_b ? (uint32_t)C::kBBytes : 0u));
+                            if (load_b)                 // the weight tile of this K block rides on the same barrier
                                 ptx::tma_load_2d(ptx::smem_u32(s_b + cs * C::kBBytes), &tmap_w, full, kbt * kBK, (tile % p.n_tiles) * BLOCK_N);
                             if (kb >= p.nkb1)           // concatenated second input: 1x1 window at (ho*sh2, wo*sw2)
                                 ptx::tma_load_im2col_4d(dst, &tmap_x2, full, (kb - p.nkb1) * 64, wo * p.sw2, ho * p.sh2, n, 0, 0);
@@ -1145,10 +1150,29 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 if (two) ptx::tma_load_2d(io0 + buf * C::kIoBytes + kHalfIo, &omaps.res, bres + buf * 8u, c0 + 64, r0);
             };
             if (my_tiles > 0 && SLFP_LEADER) load_res((int)blockIdx.x, 0u);
+            // The folded per-channel affine of a tile's 128 columns is staged in shared memory ONE TILE AHEAD by 64 threads (one
+            // float4 of mul or add each): read straight from global memory inside the tile it was the largest single stall
+            // of the epilogue warps (long-scoreboard waits on 16 LDG.128 per thread and tile, profiles/r03_ncu_tail.md).
+            // s_par: [2 buffers][mul 128 | add 128]; the writes for tile ti + 1 happen during tile ti, whose two CTA-wide
+            // epilogue barriers order them before the reads.
+            auto stage_affine = [&](int tile, uint32_t buf) {
+                if (etid < 64) {
+                    const int c = (tile % p.n_tiles) * BLOCK_N + (etid & 31) * 4;
+                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < p.Kout) v4 = __ldg(reinterpret_cast<const float4*>((etid < 32 ? p.epi.ch_mul : p.epi.ch_add) + c));
+                    *reinterpret_cast<float4*>(s_par + buf * 2 * BLOCK_N + (etid >> 5) * BLOCK_N + (etid & 31) * 4) = v4;
+                }
+            };
+            if (my_tiles > 0) {
+                stage_affine((int)blockIdx.x, 0u);
+                ptx::bar_sync(1, kEpiWarps * 32);
+            }
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                 const uint32_t buf = (uint32_t)ti & 1u;
+                if (ti + 1 < my_tiles) stage_affine(tile + (int)gridDim.x, buf ^ 1u);
                 const uint32_t tacc = tile_begin(ti, tile);
+                const uint32_t s_mul_t = s_mul + buf * (uint32_t)(2 * BLOCK_N * 4) + (uint32_t)(cg * 32) * 4u, s_add_t = s_mul_t + BLOCK_N * 4;
                 const int n_slab = (tile % p.n_tiles) * BLOCK_N + cg * 32;
                 int nvalid = (p.Kout - n_slab) >> 4;                                 // 16-column chunks of this group inside Kout
                 nvalid = nvalid > 2 ? 2 : (nvalid < 0 ? 0 : nvalid);
@@ -1171,12 +1195,11 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     if (live) {
                         uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
                         if (has_res) { ra = ptx::lds128_volatile(ioa); rb = ptx::lds128_volatile(iob); }
-                        // per-channel affine: warp-uniform 16-byte loads (L1 broadcast; L1TEX is idle in this variant)
-                        const float4* mp = reinterpret_cast<const float4*>(p.epi.ch_mul + n_slab + ch * 16);
-                        const float4* ap = reinterpret_cast<const float4*>(p.epi.ch_add + n_slab + ch * 16);
+                        // per-channel affine: warp-uniform 16-byte shared-memory loads (broadcast) of the staged vectors
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            const float4 m4 = __ldg(mp + g), a4 = __ldg(ap + g);
+                            const float4 m4 = ptx::lds128_f4(s_mul_t + (uint32_t)(ch * 16 + 4 * g) * 4u);
+                            const float4 a4 = ptx::lds128_f4(s_add_t + (uint32_t)(ch * 16 + 4 * g) * 4u);
                             v[4 * g + 0] = fmaf(__uint_as_float(acc[ch][4 * g + 0]), m4.x, a4.x);
                             v[4 * g + 1] = fmaf(__uint_as_float(acc[ch][4 * g + 1]), m4.y, a4.y);
                             v[4 * g + 2] = fmaf(__uint_as_float(acc[ch][4 * g + 2]), m4.z, a4.z);
@@ -1384,8 +1407,12 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: post-ReLU code formats need relu=1");
     const bool e4m3_out = epi->y_codes && epi->next_fmt == SLFP_FMT_E4M3;
     const bool a16 = d->fmt == SLFP_FMT_F16Q;       // the activation tensor is the float16 A operand itself
-    if (a16 && (d->c_phys % 64 != 0 || d->flags != 0 || d2))
-        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: SLFP_FMT_F16Q input needs c_phys %% 64 == 0, no flags, no second input");
+    const bool fold_w = (d->flags & SLFP_CONV_FOLD_W) != 0;
+    if (a16 && (d->c_phys % 64 != 0 || (d->flags & ~SLFP_CONV_FOLD_W) != 0 || d2))
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: SLFP_FMT_F16Q input needs c_phys %% 64 == 0, no operand flags, no second input");
+    if (fold_w && (!a16 || d->c_phys != 64 || d->s != 1 || d->stride_h != 1 || d->stride_w != 1 || d->pad_h || d->pad_w || d->pad_h_extra ||
+                   d->pad_w_extra || d->dil_h != 1 || d->dil_w != 1))
+        return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: SLFP_CONV_FOLD_W needs SLFP_FMT_F16Q, c_phys == 64, an R x 1 filter, stride 1, no padding");
     if (epi->store_f16 && (!epi->y_codes || !fast || epi->y_codes2 || epi->y_f16 || epi->y_f32 || epi->residual || epi->layerout))
         return set_error(SLFP_ERR_BAD_ARG, "conv2d_fwd: store_f16 is a form of the codes-only epilogue (post-ReLU format, one consumer)");
     const bool nodec = (d->flags & SLFP_CONV_E4M3_OPERANDS) != 0;
@@ -1530,7 +1557,9 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         // lower corner = -pad, upper corner = pad - (filter - 1) * dilation (relative to the tensor's far edge),
         // traversed with the convolution stride; the filter tap (r, s) is the per-load offset.
         const cuuint64_t gdim[4] = {(cuuint64_t)d->c_phys, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
-        const cuuint64_t gstr[3] = {(cuuint64_t)d->c_phys * esz, (cuuint64_t)d->c_phys * d->w * esz, (cuuint64_t)d->c_phys * d->w * d->h * esz};
+        // SLFP_CONV_FOLD_W: virtual pixels of 64 channels every 16 elements of a row of w + 3 physical pixels (they overlap)
+        const cuuint64_t pix = fold_w ? 16u * esz : (cuuint64_t)d->c_phys * esz, rowb = fold_w ? (cuuint64_t)(d->w + 3) * pix : (cuuint64_t)d->w * pix;
+        const cuuint64_t gstr[3] = {pix, rowb, rowb * d->h};
         const int lower[2] = {-d->pad_w, -d->pad_h};
         const int upper[2] = {d->pad_w + d->pad_w_extra - (d->s - 1) * d->dil_w, d->pad_h + d->pad_h_extra - (d->r - 1) * d->dil_h};
         const cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};

@@ -495,13 +495,18 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t n, uint32_t d, uint32_t m
 // streaming loads in flight, 512 contiguous bytes per warp and load) and writes their 2 x 16 bytes of codes side by
 // side; 32-bit index arithmetic with magic-number division (the generic kernel's three 64-bit divisions per pixel made
 // it issue-bound at 0.34-0.46 of the HBM peak), table encoder with ONE group probe per thread for the rare general path.
-template <int FL>
+// OUT16 (slfp_quantize_nchw_s2d_f16q): instead of the code bytes the kernel stores the float16 image of each code's value
+// (SLFP_FMT_F16Q, 32 bytes per folded pixel) into a physically zero-padded [n, hp, wp, 16] tensor at (pad_top, pad_left).
+template <int FL, bool OUT16 = false>
 __global__ void __launch_bounds__(256) quantize_nchw_s2d_c3_kernel(const float* __restrict__ x, uint32_t total_pairs, int H, int W,
                                                                    uint32_t Wp, uint32_t mg_wp, uint32_t sh_wp, uint32_t H2,
                                                                    uint32_t mg_h2, uint32_t sh_h2, DivK k_div,
-                                                                   uint8_t* __restrict__ codes) {
+                                                                   uint8_t* __restrict__ codes, int pad_top = 0, int pad_left = 0,
+                                                                   int hp = 0, int wp = 0) {
     __shared__ uint8_t s_enc[kEncLutBytes];
+    __shared__ unsigned short s_dec[OUT16 ? 256 : 1];
     for (int i = threadIdx.x; i < kEncLutBytes; i += 256) s_enc[i] = (uint8_t)enc_lut_entry<FL>((uint32_t)i);
+    if (OUT16) s_dec[threadIdx.x] = __half_as_ushort(__float2half_rn(decode<FL == SLFP_FMT_SFP33>((uint32_t)threadIdx.x, c_pow2frac)));
     __syncthreads();
     const size_t plane = (size_t)H * W;
     for (uint32_t j = blockIdx.x * 256u + threadIdx.x; j < total_pairs; j += gridDim.x * 256u) {
@@ -547,11 +552,21 @@ __global__ void __launch_bounds__(256) quantize_nchw_s2d_c3_kernel(const float* 
 #pragma unroll
                 for (int e = 0; e < 12; ++e) c8[e] = encode<FL>(div_k(xs[p][e], k_div));
             }
+            if (OUT16) {
+                uint32_t hw[6];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) hw[e] = (uint32_t)s_dec[c8[2 * e]] | ((uint32_t)s_dec[c8[2 * e + 1]] << 16);
+                uint4* d16 = reinterpret_cast<uint4*>(codes + (((size_t)n * hp + y2 + pad_top) * wp + 2 * px + p + pad_left) * 32);
+                d16[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                d16[1] = make_uint4(hw[4], hw[5], 0u, 0u);           // pad channels 12..15: 0.0
+                continue;
+            }
 #pragma unroll
             for (int g = 0; g < 3; ++g)
                 w[p][g] = __byte_perm(__byte_perm(c8[4 * g], c8[4 * g + 1], 0x0040), __byte_perm(c8[4 * g + 2], c8[4 * g + 3], 0x0040), 0x5410);
             w[p][3] = 0u;                                        // pad channels 12..15: code 0 = exact zero
         }
+        if (OUT16) continue;
         uint4* dst = reinterpret_cast<uint4*>(codes + (size_t)j * 32);
         dst[0] = make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]);
         dst[1] = make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]);
@@ -1134,6 +1149,30 @@ extern "C" int slfp_quantize_nchw_s2d_f32(const float* x, int n, int c, int h, i
         default: return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_s2d_f32: format %d", fmt);
     }
     return check_launch("quantize_nchw_s2d_kernel");
+}
+
+extern "C" int slfp_quantize_nchw_s2d_f16q(const float* x, int n, int h, int w, float k_div, int fmt, int pad_top, int pad_left,
+                                           int hp, int wp, void* out_f16, slfp_stream_t stream) {
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    if (!x || !out_f16 || (h & 1) || (w & 3) || (((uintptr_t)x | (uintptr_t)out_f16) & 15u) || pad_top < 0 || pad_left < 0 ||
+        hp < h / 2 + pad_top || wp < w / 2 + pad_left || (fmt != SLFP_FMT_SFP33 && fmt != SLFP_FMT_SLFP34_ACT))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_s2d_f16q: RGB input, h even, w %% 4 == 0, 16-byte aligned pointers, padded extents >= pad + h/2, w/2");
+    const size_t total = (size_t)n * (h / 2) * (w / 2);
+    if (total / 2 >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_quantize_nchw_s2d_f16q: more than 2^32 pixels");
+    const uint32_t pairs = (uint32_t)(total / 2), Wp = (uint32_t)(w / 4), H2 = (uint32_t)(h / 2);
+    uint32_t mg_wp, sh_wp, mg_h2, sh_h2;
+    magic_u32(Wp, mg_wp, sh_wp);
+    magic_u32(H2, mg_h2, sh_h2);
+    const DivK dk = make_divk(k_div);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)min((size_t)num_sms() * 6, ceil_div_sz(pairs, 256));
+    if (fmt == SLFP_FMT_SFP33)
+        quantize_nchw_s2d_c3_kernel<SLFP_FMT_SFP33, true><<<grid, 256, 0, st>>>(x, pairs, h, w, Wp, mg_wp, sh_wp, H2, mg_h2, sh_h2, dk,
+                                                                                 (uint8_t*)out_f16, pad_top, pad_left, hp, wp);
+    else
+        quantize_nchw_s2d_c3_kernel<SLFP_FMT_SLFP34_ACT, true><<<grid, 256, 0, st>>>(x, pairs, h, w, Wp, mg_wp, sh_wp, H2, mg_h2, sh_h2, dk,
+                                                                                      (uint8_t*)out_f16, pad_top, pad_left, hp, wp);
+    return check_launch("quantize_nchw_s2d_c3_kernel<f16q>");
 }
 
 extern "C" int slfp_gather_quantize_f16(const SlfpGatherChan* table, size_t npix, int c, int c_phys, float k_div, int fmt,

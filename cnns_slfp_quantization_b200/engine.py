@@ -36,13 +36,14 @@ def _k32(K):
 class _T:
     """A device tensor of the plan: NHWC, kind in {'codes', 'q16', 'f16', 'f32'}.  'q16' (SLFP_FMT_F16Q) holds the float16
     image of the codes of format `qfmt` - the tensor-core operand itself - for a decode-bound dense consumer."""
-    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt", "c_logical", "qfmt")
+    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt", "c_logical", "qfmt", "pad")
 
     def __init__(self, buf, n, h, w, c, cp, kind, kdiv=None, fmt=None):
         self.buf, self.n, self.h, self.w, self.c, self.cp, self.kind, self.kdiv = buf, n, h, w, c, cp, kind, kdiv
         self.fmt = fmt                  # code format of a 'codes' tensor (signed quantizer codes or post-ReLU codes)
         self.c_logical = c              # float16 outputs of a pad_k layer: c is the physical channel count
         self.qfmt = None                # 'q16': the code format whose values the halves are
+        self.pad = None                 # (top, left, hp, wp): buf is physically zero-padded [n, hp, wp, cp]; h, w stay logical
 
 
 def _ceil(v, m):
@@ -138,6 +139,21 @@ class Plan:
         t = self._alloc(n, h // 2, w // 2, 4 * c, "codes", kdiv, cp=cp)
         self.ops.append(self._call(self.lib.slfp_quantize_nchw_s2d_f32, x_nchw.data_ptr(), n, c, h, w, cp, kdiv, self.afmt,
                                    t.buf.data_ptr()))
+        return t
+
+    def quantize_input_s2d_f16q(self, x_nchw, kdiv, pad_top, pad_left, pad_bottom, pad_right):
+        """Network input -> SLFP_FMT_F16Q halves of the 2x2 space-to-depth image inside a zero-padded buffer
+        [n, h/2 + pads, w/2 + pads, 16]: the input of the width-folded stem (SLFP_CONV_FOLD_W)."""
+        n, c, h, w = x_nchw.shape
+        assert c == 3 and w % 4 == 0 and h % 2 == 0
+        hp, wp = h // 2 + pad_top + pad_bottom, w // 2 + pad_left + pad_right
+        buf = torch.zeros((n, hp, wp, 16), dtype=torch.float16, device=self.dev)      # the border stays zero
+        self.bytes_hbm += buf.numel() * 2
+        self.keep.append(buf)
+        t = _T(buf, n, h // 2, w // 2, 4 * c, 16, "q16", kdiv, nv.FMT_F16Q)
+        t.qfmt, t.pad = self.afmt, (pad_top, pad_left, hp, wp)
+        self.ops.append(self._call(self.lib.slfp_quantize_nchw_s2d_f16q, x_nchw.data_ptr(), n, h, w, kdiv, self.afmt, pad_top, pad_left,
+                                   hp, wp, buf.data_ptr()))
         return t
 
     def s2d_stem(self, conv):
@@ -302,8 +318,15 @@ class Plan:
         if f32:
             out["f32"] = self._alloc(x.n, Ho, Wo, Kk, "f32")
             epi.y_f32 = out["f32"].buf.data_ptr()
-        self.keep += [d, epi, wbuf]
-        self.ops.append(self._call(self.lib.slfp_conv2d_fwd, ctypes.byref(d), x.buf.data_ptr(), wbuf.data_ptr(),
+        d_launch = d
+        if x.pad is not None:
+            # width-folded stem: R x 4 taps on 16 channels presented as R x 1 on 64 over the physically padded input
+            top, left, hp, wp = x.pad
+            assert dense and x.fmt == nv.FMT_F16Q and x.cp == 16 and S == 4 and wp == Wo + 3 and hp == Ho + R - 1 and tuple(stride) == (1, 1)
+            d_launch = nv.SlfpConvDesc(x.n, hp, Wo, 64, 64, Kk, R, 1, 1, 1, 0, 0, 1, 1, 1, nv.FMT_F16Q, 0, 0, nv.CONV_FOLD_W)
+            assert self.lib.slfp_conv_wpitch(ctypes.byref(d_launch)) == pitch
+        self.keep += [d, d_launch, epi, wbuf]
+        self.ops.append(self._call(self.lib.slfp_conv2d_fwd, ctypes.byref(d_launch), x.buf.data_ptr(), wbuf.data_ptr(),
                                    ctypes.byref(epi)))
         fl = 2.0 * x.n * Ho * Wo * K * (C // groups) * R * S
         if hasattr(mod, "orig"):        # space-to-depth stem: count the ALGORITHMIC taps (7x7x3 = 147), not the folded 4x4x12 = 192
@@ -539,7 +562,12 @@ def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", stat
         ho = (size + 2 * c1.padding[0] - (c1.kernel_size[0] - 1) - 1) // 2 + 1
         wo = (size + 2 * c1.padding[1] - (c1.kernel_size[1] - 1) - 1) // 2 + 1
         shim.pad_extra = (ho - size // 2 + (R2 - 1) - 2 * lo[0], wo - size // 2 + (S2 - 1) - 2 * lo[1])
-        xc = P.quantize_input_s2d(x, _k32(c1.Ka))
+        if P.f16q and R2 == 4 and S2 == 4 and size % 4 == 0 and not os.environ.get("SLFP_NO_FOLD_STEM"):
+            # float16 images in a zero-padded buffer: the stem runs without a decode stage, one 128-byte TMA row per
+            # pixel and filter row (SLFP_CONV_FOLD_W)
+            xc = P.quantize_input_s2d_f16q(x, _k32(c1.Ka), lo[0], lo[1], lo[0] + shim.pad_extra[0], lo[1] + shim.pad_extra[1])
+        else:
+            xc = P.quantize_input_s2d(x, _k32(c1.Ka))
         stem = P.conv(xc, shim, bn=model.bn1, relu=True, codes=consumers(blocks[0]))
     else:
         xc = P.quantize_input(x, _k32(c1.Ka))

@@ -136,6 +136,13 @@ int slfp_quantize_nchw_f32(const float *x, int n, int c, size_t hw, int c_phys, 
 int slfp_quantize_nchw_s2d_f32(const float *x, int n, int c, int h, int w, int c_phys, float k_div, int fmt,
                                uint8_t *codes, slfp_stream_t stream);
 
+/* The same space-to-depth input quantizer for an RGB image (c = 3, c_phys = 16) writing SLFP_FMT_F16Q - the float16 image
+ * of each code's value, 32 bytes per folded pixel - into a physically ZERO-PADDED tensor [n, hp, wp, 16] at offset
+ * (pad_top, pad_left); the caller zeroes the buffer once, the kernel only writes the interior.  This is the input of the
+ * SLFP_CONV_FOLD_W stem (below): padding is materialised because the folded rows overlap.  w % 4 == 0, h even. */
+int slfp_quantize_nchw_s2d_f16q(const float *x, int n, int h, int w, float k_div, int fmt, int pad_top, int pad_left,
+                                int hp, int wp, void *out_f16, slfp_stream_t stream);
+
 /* Gather + quantize: the activation quantizer fed from SEVERAL float16 NHWC tensors through a per-channel table -
  * codes[p, j] = encode(float(src_j[p * stride_j + ch_j]) / k_div) for j < c, code 0 for c <= j < c_phys.  This is how
  * the fused pipeline evaluates torch.split / torch.cat / channel_shuffle (nets_cifar/shufflenet_v2.py:20-45, 100-115)
@@ -212,6 +219,13 @@ typedef struct {
  * are SLFP_FMT_E4M3: kind::f8f6f4 MMA on the codes themselves.  q_bit 7 (SFP<3,3>) only, dense, c_phys % 64 == 0.
  * slfp_prepare_weights* writes that operand through the w_f16 pointer when the descriptor carries this flag. */
 #define SLFP_CONV_E4M3_OPERANDS 2
+/* Width-folded input (the ResNet stem after space-to-depth): the descriptor describes a VIRTUAL tensor [n, h, w, c_phys = 64]
+ * whose pixel (y, x) is the concatenation of the four physical pixels (y, x .. x + 3) of a zero-padded SLFP_FMT_F16Q tensor
+ * [n, h, w + 3, 16] - pixel pitch 16 elements, so consecutive virtual pixels OVERLAP.  An R x 4 stride-1 convolution on 16
+ * channels becomes an R x 1 convolution on 64: one 128-byte TMA row carries the four horizontal taps of a pixel, K blocks
+ * are whole filter rows, and the A tile needs no decode.  The weight operand is the KRSC tensor of the R x 4 filter on 16
+ * channels (same memory).  Requires fmt == SLFP_FMT_F16Q, c_phys == 64, s == 1, stride 1, no padding, no dilation. */
+#define SLFP_CONV_FOLD_W 4
 
 typedef struct {
     const float *bias_q;   /* [k] added to the accumulator BEFORE the post-scale (bias/Ka/Kw,

@@ -133,4 +133,8 @@ def decode_q16(orc, halves, qfmt):
 def decode_tensor(orc, t):
     """Values of an engine tensor of kind 'codes' or 'q16'."""
     arr = t.buf.cpu().numpy()
+    if getattr(t, "pad", None) is not None:                 # physically zero-padded buffer: the interior is the tensor
+        top, left, _, _ = t.pad
+        assert (np.delete(arr, np.s_[top:top + t.h], axis=1) == 0).all() and (np.delete(arr, np.s_[left:left + t.w], axis=2) == 0).all()
+        arr = arr[:, top:top + t.h, left:left + t.w]
     return decode_q16(orc, arr, t.qfmt) if t.fmt == nv.FMT_F16Q else decode_codes(orc, arr, t.fmt)

@@ -177,7 +177,9 @@ def _encode_like(t, ref, mod, orc, qbit, nv):
         codes = table[codes].astype(np.float16)
     if hasattr(mod, "orig"):
         c, hh, ww = ref.shape[1:]
-        out[..., :4 * c] = codes.reshape(n, c, hh // 2, 2, ww // 2, 2).transpose(0, 2, 4, 3, 5, 1).reshape(n, hh // 2, ww // 2, 4 * c)
+        top, left = (t.pad[0], t.pad[1]) if getattr(t, "pad", None) is not None else (0, 0)
+        out[:, top:top + hh // 2, left:left + ww // 2, :4 * c] = \
+            codes.reshape(n, c, hh // 2, 2, ww // 2, 2).transpose(0, 2, 4, 3, 5, 1).reshape(n, hh // 2, ww // 2, 4 * c)
     elif ref.ndim == 2:
         out.reshape(n, -1)[:, :ref.shape[1]] = codes
     else:
