@@ -1151,6 +1151,69 @@ extern "C" int slfp_quantize_nchw_s2d_f32(const float* x, int n, int c, int h, i
     return check_launch("quantize_nchw_s2d_kernel");
 }
 
+// Network input of a 3x3 / stride 1 / padding 1 RGB stem as an explicit im2col matrix of float16 images (SLFP_FMT_F16Q):
+// row = output pixel, 64 halves = tap (r * 3 + s) * 4 + c for the 9 taps x 3 channels, zeros elsewhere - exactly the KRSC
+// weight row of the c_phys = 4 stem (36 of 64 entries).  The stem then runs as a plain 1x1 layer of the no-decode dense kernel
+// (ONE K block per tile) instead of the 4-channel gather kernel.  A CTA takes a band of kIm2colRows image rows: it quantizes
+// the band + halo ONCE into shared memory ([rows + 2][W + 2] pixels of 4 halves, zero border = the padding) with the exact
+// encoder, then writes the im2col rows - eight lanes per pixel, 16 bytes = two taps each, 512 contiguous bytes per warp.
+constexpr int kIm2colRows = 8;
+template <int FL>
+__global__ void __launch_bounds__(256) quantize_nchw_im2col3x3_kernel(const float* __restrict__ x, int N, int H, int W, int bands,
+                                                                      DivK k_div, uint4* __restrict__ out) {
+    extern __shared__ uint2 s_q[];
+    const int Wp = W + 2;
+    const size_t HW = (size_t)H * W;
+    for (int blk = blockIdx.x; blk < N * bands; blk += gridDim.x) {
+        const int n = blk / bands, y0 = (blk - n * bands) * kIm2colRows;
+        const int rows = min(kIm2colRows, H - y0);
+        for (int i = threadIdx.x; i < (rows + 2) * Wp; i += 256) {
+            const int ry = i / Wp, rx = i - ry * Wp;
+            const int yy = y0 + ry - 1, xs = rx - 1;
+            uint2 v = make_uint2(0u, 0u);
+            if (yy >= 0 && yy < H && xs >= 0 && xs < W) {
+                const float* src = x + (size_t)n * 3 * HW + (size_t)yy * W + xs;
+                unsigned short h3[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    h3[c] = __half_as_ushort(__float2half_rn(decode<FL == SLFP_FMT_SFP33>(encode<FL>(div_k(__ldg(src + (size_t)c * HW), k_div)), c_pow2frac)));
+                v = make_uint2((uint32_t)h3[0] | ((uint32_t)h3[1] << 16), (uint32_t)h3[2]);
+            }
+            s_q[i] = v;
+        }
+        __syncthreads();
+        uint4* dst = out + ((size_t)n * H + y0) * W * 8;
+        for (int i = threadIdx.x; i < rows * W * 8; i += 256) {
+            const int pix = i >> 3, j = i & 7;                     // chunk j: halves 8j .. 8j+7 = taps 2j, 2j+1
+            const int ly = pix / W, lx = pix - ly * W;
+            uint2 e0 = make_uint2(0u, 0u), e1 = e0;
+            if (2 * j < 9) e0 = s_q[(ly + (2 * j) / 3) * Wp + lx + (2 * j) % 3];
+            if (2 * j + 1 < 9) e1 = s_q[(ly + (2 * j + 1) / 3) * Wp + lx + (2 * j + 1) % 3];
+            dst[i] = make_uint4(e0.x, e0.y, e1.x, e1.y);
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int slfp_quantize_nchw_im2col3x3_f16q(const float* x, int n, int h, int w, float k_div, int fmt, void* out_f16,
+                                                 slfp_stream_t stream) {
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    if (!x || !out_f16 || ((uintptr_t)out_f16 & 15u) || (fmt != SLFP_FMT_SFP33 && fmt != SLFP_FMT_SLFP34_ACT))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_quantize_nchw_im2col3x3_f16q: bad arguments");
+    const size_t smem = (size_t)(kIm2colRows + 2) * (w + 2) * sizeof(uint2);
+    if (smem > 48 * 1024) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_quantize_nchw_im2col3x3_f16q: image wider than 612 pixels");
+    const int bands = (h + kIm2colRows - 1) / kIm2colRows;
+    if ((long long)n * bands >= (1ll << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_quantize_nchw_im2col3x3_f16q: too many row bands");
+    const DivK dk = make_divk(k_div);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)min((long long)num_sms() * 8, (long long)n * bands);
+    if (fmt == SLFP_FMT_SFP33)
+        quantize_nchw_im2col3x3_kernel<SLFP_FMT_SFP33><<<grid, 256, smem, st>>>(x, n, h, w, bands, dk, (uint4*)out_f16);
+    else
+        quantize_nchw_im2col3x3_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 256, smem, st>>>(x, n, h, w, bands, dk, (uint4*)out_f16);
+    return check_launch("quantize_nchw_im2col3x3_kernel");
+}
+
 extern "C" int slfp_quantize_nchw_s2d_f16q(const float* x, int n, int h, int w, float k_div, int fmt, int pad_top, int pad_left,
                                            int hp, int wp, void* out_f16, slfp_stream_t stream) {
     if (n <= 0 || h <= 0 || w <= 0) return 0;

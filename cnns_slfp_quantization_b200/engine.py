@@ -36,13 +36,14 @@ def _k32(K):
 class _T:
     """A device tensor of the plan: NHWC, kind in {'codes', 'q16', 'f16', 'f32'}.  'q16' (SLFP_FMT_F16Q) holds the float16
     image of the codes of format `qfmt` - the tensor-core operand itself - for a decode-bound dense consumer."""
-    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt", "c_logical", "qfmt", "pad")
+    __slots__ = ("buf", "n", "h", "w", "c", "cp", "kind", "kdiv", "fmt", "c_logical", "qfmt", "pad", "im2col")
 
     def __init__(self, buf, n, h, w, c, cp, kind, kdiv=None, fmt=None):
         self.buf, self.n, self.h, self.w, self.c, self.cp, self.kind, self.kdiv = buf, n, h, w, c, cp, kind, kdiv
         self.fmt = fmt                  # code format of a 'codes' tensor (signed quantizer codes or post-ReLU codes)
         self.c_logical = c              # float16 outputs of a pad_k layer: c is the physical channel count
         self.qfmt = None                # 'q16': the code format whose values the halves are
+        self.im2col = False             # buf is the 3x3 / pad 1 im2col matrix [n, h, w, 64] of a 3-channel input (q16)
         self.pad = None                 # (top, left, hp, wp): buf is physically zero-padded [n, hp, wp, cp]; h, w stay logical
 
 
@@ -139,6 +140,19 @@ class Plan:
         t = self._alloc(n, h // 2, w // 2, 4 * c, "codes", kdiv, cp=cp)
         self.ops.append(self._call(self.lib.slfp_quantize_nchw_s2d_f32, x_nchw.data_ptr(), n, c, h, w, cp, kdiv, self.afmt,
                                    t.buf.data_ptr()))
+        return t
+
+    def quantize_input_im2col3x3(self, x_nchw, kdiv):
+        """Network input -> the im2col matrix of a 3x3 / stride 1 / padding 1 RGB stem as SLFP_FMT_F16Q halves [n, h, w, 64]
+        (entry (r * 3 + s) * 4 + c): the stem becomes a plain 1x1 layer of the no-decode dense kernel."""
+        n, c, h, w = x_nchw.shape
+        assert c == 3
+        buf = torch.zeros((n, h, w, 64), dtype=torch.float16, device=self.dev)
+        self.bytes_hbm += buf.numel() * 2
+        self.keep.append(buf)
+        t = _T(buf, n, h, w, c, 4, "q16", kdiv, nv.FMT_F16Q)
+        t.qfmt, t.im2col = self.afmt, True
+        self.ops.append(self._call(self.lib.slfp_quantize_nchw_im2col3x3_f16q, x_nchw.data_ptr(), n, h, w, kdiv, self.afmt, buf.data_ptr()))
         return t
 
     def quantize_input_s2d_f16q(self, x_nchw, kdiv, pad_top, pad_left, pad_bottom, pad_right):
@@ -282,7 +296,7 @@ class Plan:
         # depthwise conv -> BN -> (no ReLU) -> next quantizer: sign bit + 7-bit magnitude code (SFP<3,3> only)
         sfast_dw = fused_dw and not relu and signed_fast and self.afmt == nv.FMT_SFP33 and kp == x.cp
         # 3x3 RGB stems (c_phys = 4) run the CUDA-core direct kernel, which writes the fused pipeline's fast code formats
-        stem_direct = (dense and x.cp == 4 and (R, S) == (3, 3) and tuple(dil) == (1, 1) and K in (24, 32) and bn is not None
+        stem_direct = (dense and x.cp == 4 and not x.im2col and (R, S) == (3, 3) and tuple(dil) == (1, 1) and K in (24, 32) and bn is not None
                        and not f16 and not f32 and residual is None and not layerout and stride[0] == stride[1] and pad[0] == pad[1])
         if self.e4m3 and (x.cp % 16 == 0 or stem_direct):
             ofmt = nv.FMT_E4M3                 # every producer of an SFP-7 plan (dense, depthwise, direct stem) writes e4m3 bytes
@@ -293,13 +307,13 @@ class Plan:
         elif stem_direct and not relu and signed_fast and self.afmt == nv.FMT_SFP33:
             ofmt = nv.FMT_SFP33_SFAST
         else:
-            ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and x.cp % 16 == 0 and (groups == 1 or fast_dw)) else self.afmt
+            ofmt = nv.relu_fmt(self.afmt) if (relu_codes and relu and (x.cp % 16 == 0 or x.im2col) and (groups == 1 or fast_dw)) else self.afmt
         # store_f16: the codes-only fast epilogue of the warp-specialised dense kernel (relu, one consumer, post-ReLU format)
         # Storing halves instead of bytes costs the PRODUCER ~0.5 us per 2^20 output elements (measured on the 1x1 reduce
         # layers, whose 8 epilogue warps are their critical path) against a flat ~12-18 us the 3x3 consumer saves by not
         # decoding: worth it below ~16 M elements (ResNet-50 stages 3-4 at batch 256)
         q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS", 16 << 20))
-        as_q16 = (q16 and self.f16q and dense and x.cp % 16 == 0 and len(kds) == 1 and relu and bn is not None and K % 64 == 0
+        as_q16 = (q16 and self.f16q and dense and (x.cp % 16 == 0 or x.im2col) and len(kds) == 1 and relu and bn is not None and K % 64 == 0
                   and Kk == K and ofmt == nv.relu_fmt(self.afmt) and not f16 and not f32 and residual is None and not layerout
                   and x.n * Ho * Wo * K <= q16_max)
         for i, kd in enumerate(kds):
@@ -319,6 +333,11 @@ class Plan:
             out["f32"] = self._alloc(x.n, Ho, Wo, Kk, "f32")
             epi.y_f32 = out["f32"].buf.data_ptr()
         d_launch = d
+        if x.im2col:
+            # 3x3 RGB stem on its explicit im2col matrix: a 1x1 layer with 64 input channels (36 used), same weight operand
+            assert dense and x.cp == 4 and (R, S) == (3, 3) and tuple(stride) == (1, 1) and tuple(pad) == (1, 1) and tuple(dil) == (1, 1)
+            assert pitch == 64
+            d_launch = nv.SlfpConvDesc(x.n, x.h, x.w, 64, 64, Kk, 1, 1, 1, 1, 0, 0, 1, 1, 1, nv.FMT_F16Q, 0, 0, 0)
         if x.pad is not None:
             # width-folded stem: R x 4 taps on 16 channels presented as R x 1 on 64 over the physically padded input
             top, left, hp, wp = x.pad
@@ -622,7 +641,12 @@ def compile_vgg16(model, batch, size=32, device="cuda", static_weights=False):
         seq += list(getattr(model, f"layer{li}"))
     fcs = [model.fc1[2], model.fc2[0], model.fc3]
     convs = [m for m in seq if isinstance(m, nn.Conv2d)]
-    cur = P.quantize_input(x, _k32(convs[0].Ka))
+    c0 = convs[0]
+    if (P.f16q and c0.kernel_size == (3, 3) and c0.stride == (1, 1) and c0.padding == (1, 1) and c0.dilation == (1, 1) and c0.groups == 1
+            and c0.in_channels == 3 and not os.environ.get("SLFP_NO_IM2COL_STEM")):
+        cur = P.quantize_input_im2col3x3(x, _k32(c0.Ka))      # the 3 -> 64 stem as a 1x1 layer on its im2col matrix
+    else:
+        cur = P.quantize_input(x, _k32(c0.Ka))
     i = 0
     while i < len(seq):
         m = seq[i]

@@ -143,6 +143,13 @@ int slfp_quantize_nchw_s2d_f32(const float *x, int n, int c, int h, int w, int c
 int slfp_quantize_nchw_s2d_f16q(const float *x, int n, int h, int w, float k_div, int fmt, int pad_top, int pad_left,
                                 int hp, int wp, void *out_f16, slfp_stream_t stream);
 
+/* Input quantizer of a 3x3 / stride 1 / padding 1 RGB stem (the CIFAR nets) writing the layer's im2col matrix directly:
+ * out[n, h, w, 64] SLFP_FMT_F16Q halves, entry (r * 3 + s) * 4 + c = quantize(x[n, c, y + r - 1, x + s - 1] / k_div) (0 outside
+ * the image and in the unused entries) - the order of the KRSC weight row of the c_phys = 4 stem, so the stem runs as a plain
+ * 1x1 SLFP_FMT_F16Q layer with c_phys = 64 (one K block, no decode) on the weight operand slfp_prepare_weights writes for it. */
+int slfp_quantize_nchw_im2col3x3_f16q(const float *x, int n, int h, int w, float k_div, int fmt, void *out_f16,
+                                      slfp_stream_t stream);
+
 /* Gather + quantize: the activation quantizer fed from SEVERAL float16 NHWC tensors through a per-channel table -
  * codes[p, j] = encode(float(src_j[p * stride_j + ch_j]) / k_div) for j < c, code 0 for c <= j < c_phys.  This is how
  * the fused pipeline evaluates torch.split / torch.cat / channel_shuffle (nets_cifar/shufflenet_v2.py:20-45, 100-115)

@@ -137,4 +137,18 @@ def decode_tensor(orc, t):
         top, left, _, _ = t.pad
         assert (np.delete(arr, np.s_[top:top + t.h], axis=1) == 0).all() and (np.delete(arr, np.s_[left:left + t.w], axis=2) == 0).all()
         arr = arr[:, top:top + t.h, left:left + t.w]
+    if getattr(t, "im2col", False):                         # im2col matrix of a 3x3 / pad 1 RGB stem: entry (r * 3 + s) * 4 + c
+        v = decode_q16(orc, arr, t.qfmt)
+        n, h, w, _ = v.shape
+        center = v[..., 16:19]
+        for r in range(3):                                  # every tap is the shifted centre tap, zero outside the image
+            for s_ in range(3):
+                want = np.zeros_like(center)
+                ys, xs = slice(max(0, 1 - r), min(h, h + 1 - r)), slice(max(0, 1 - s_), min(w, w + 1 - s_))
+                yd, xd = slice(max(0, r - 1), min(h, h + r - 1)), slice(max(0, s_ - 1), min(w, w + s_ - 1))
+                want[:, ys, xs] = center[:, yd, xd]
+                e = (r * 3 + s_) * 4
+                assert (v[..., e:e + 3] == want).all() and (v[..., e + 3] == 0).all()
+        assert (v[..., 36:] == 0).all()
+        return center
     return decode_q16(orc, arr, t.qfmt) if t.fmt == nv.FMT_F16Q else decode_codes(orc, arr, t.fmt)

@@ -175,6 +175,13 @@ def _encode_like(t, ref, mod, orc, qbit, nv):
     out = np.zeros(tuple(t.buf.shape), np.float16 if q16 else np.uint8)
     if q16:
         codes = table[codes].astype(np.float16)
+    if getattr(t, "im2col", False):                         # 3x3 / pad 1 im2col matrix [n, h, w, 64]: entry (r * 3 + s) * 4 + c
+        vp = np.pad(codes.transpose(0, 2, 3, 1), ((0, 0), (1, 1), (1, 1), (0, 0)))
+        hh, ww = codes.shape[2:]
+        for r in range(3):
+            for s_ in range(3):
+                out[..., (r * 3 + s_) * 4:(r * 3 + s_) * 4 + 3] = vp[:, r:r + hh, s_:s_ + ww]
+        return torch.from_numpy(out)
     if hasattr(mod, "orig"):
         c, hh, ww = ref.shape[1:]
         top, left = (t.pad[0], t.pad[1]) if getattr(t, "pad", None) is not None else (0, 0)
