@@ -417,7 +417,8 @@ template <int BN, int MODE>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t st) {
     using C = Cfg<BN, MODE>;
     auto kern = conv_bwd_kernel<BN, MODE>;
-    static bool attr_done = false;
+    static DeviceOnce attr_once;
+    bool& attr_done = attr_once.flag();
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return set_error((int)e, "conv_bwd: smem attribute (%d B): %s", C::kSmemBytes, cudaGetErrorString(e));

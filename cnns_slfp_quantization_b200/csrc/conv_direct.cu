@@ -461,7 +461,8 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
             q.ch_mul = epi->ch_mul; q.ch_add = epi->ch_add;
             q.sc = (float)(1.0 / (16.0 * (double)epi->next_k_div));
             q.y = epi->y_codes;
-            static bool attr_done = false;
+            static DeviceOnce attr_once;
+    bool& attr_done = attr_once.flag();
             if (!attr_done) {
                 cudaError_t e = cudaFuncSetAttribute(dwconv_fast_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));

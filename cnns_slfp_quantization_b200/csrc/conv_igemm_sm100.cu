@@ -541,7 +541,8 @@ template <int BLOCK_N, int GRAN>
 static int launch_igemm(const CUtensorMap& tmap, const IgemmParams& p, cudaStream_t st) {
     using C = Cfg<BLOCK_N>;
     auto kern = conv_igemm_kernel<BLOCK_N, GRAN>;
-    static bool attr_done = false;
+    static DeviceOnce attr_once;
+    bool& attr_done = attr_once.flag();
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return set_error((int)e, "conv_igemm: smem attribute (%d B): %s", C::kSmemBytes, cudaGetErrorString(e));

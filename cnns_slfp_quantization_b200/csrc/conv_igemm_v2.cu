@@ -41,6 +41,8 @@
 #define PROF_FLUSH(slot)
 #endif
 
+#include <type_traits>
+
 namespace slfp {
 namespace v2 {
 
@@ -1124,6 +1126,13 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             // tile is two [128 rows x 64 columns] halves, a code tile one [128 x 128] box, all with the 128-byte
             // swizzle (16-byte chunk ^= row & 7), which also keeps the per-row shared accesses conflict free.
             // Rows >= M and columns >= Kout are clipped by TMA.
+            //
+            // The tails are bound by the epilogue warps' instruction issue (profiles/r03_final.md: 479 SASS instructions per
+            // warp and tile, of which only ~250 were arithmetic - the rest re-tested run-time flags per chunk and divided
+            // tile indices by n_tiles five times per tile).  Hence: (1) the loop is instantiated per combination of
+            // (residual, float16 output, second code tensor) with the flags as compile-time constants - one generic
+            // instantiation keeps the run-time tests for e4m3 / layerout outputs; (2) the tile's (m, n) coordinates advance
+            // incrementally (no division inside the loop).
             const int cg = half;                                                      // 32-column group 0..3
             const int r = quad * 32 + lane;
             // the staging TMA traffic is issued by ONE elected lane of the first epilogue warp, which reaches these points
@@ -1141,145 +1150,170 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const float sc1 = p.sc1, sc2 = p.sc2;
             const uint32_t enc_sh = sfp33 ? 19u : 18u;
             const int32_t enc_base = sfp33 ? 0x76F : 0xEDF;
-            auto load_res = [&](int tile, uint32_t buf) {
-                if (!has_res) return;
-                const int c0 = (tile % p.n_tiles) * BLOCK_N, r0 = (tile / p.n_tiles) * kBM;
-                const bool two = c0 + 64 < p.Kout;
-                ptx::mbar_arrive_expect_tx(bres + buf * 8u, two ? 2u * kHalfIo : kHalfIo);
-                ptx::tma_load_2d(io0 + buf * C::kIoBytes, &omaps.res, bres + buf * 8u, c0, r0);
-                if (two) ptx::tma_load_2d(io0 + buf * C::kIoBytes + kHalfIo, &omaps.res, bres + buf * 8u, c0 + 64, r0);
-            };
-            if (my_tiles > 0 && SLFP_LEADER) load_res((int)blockIdx.x, 0u);
-            // The folded per-channel affine of a tile's 128 columns is staged in shared memory ONE TILE AHEAD by 64 threads (one
-            // float4 of mul or add each): read straight from global memory inside the tile it was the largest single stall
-            // of the epilogue warps (long-scoreboard waits on 16 LDG.128 per thread and tile, profiles/r03_ncu_tail.md).
-            // s_par: [2 buffers][mul 128 | add 128]; the writes for tile ti + 1 happen during tile ti, whose two CTA-wide
-            // epilogue barriers order them before the reads.
-            auto stage_affine = [&](int tile, uint32_t buf) {
-                if (etid < 64) {
-                    const int c = (tile % p.n_tiles) * BLOCK_N + (etid & 31) * 4;
-                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c < p.Kout) v4 = __ldg(reinterpret_cast<const float4*>((etid < 32 ? p.epi.ch_mul : p.epi.ch_add) + c));
-                    *reinterpret_cast<float4*>(s_par + buf * 2 * BLOCK_N + (etid >> 5) * BLOCK_N + (etid & 31) * 4) = v4;
+            const int n_tiles = p.n_tiles, Kout = p.Kout;
+            const int step_m = (int)gridDim.x / n_tiles, step_n = (int)gridDim.x % n_tiles;
+            auto run = [&](auto res_c, auto y16_c, auto c2_c, auto gen_c) {
+                constexpr bool GEN = decltype(gen_c)::value;
+                const bool h_res = GEN ? has_res : decltype(res_c)::value;
+                const bool h_y16 = GEN ? has_y16 : decltype(y16_c)::value;
+                const bool h_c1 = GEN ? has_c1 : true;
+                const bool h_c2 = GEN ? has_c2 : decltype(c2_c)::value;
+                const bool e4m3 = GEN ? (p.e4m3_out != 0) : false;
+                const bool lay = GEN ? (p.epi.layerout != 0) : false;
+                auto advance = [&](int& m, int& n) { m += step_m; n += step_n; if (n >= n_tiles) { n -= n_tiles; ++m; } };
+                auto load_res = [&](int m, int n, uint32_t buf) {
+                    const int c0 = n * BLOCK_N, r0 = m * kBM;
+                    const bool two = c0 + 64 < Kout;
+                    ptx::mbar_arrive_expect_tx(bres + buf * 8u, two ? 2u * kHalfIo : kHalfIo);
+                    ptx::tma_load_2d(io0 + buf * C::kIoBytes, &omaps.res, bres + buf * 8u, c0, r0);
+                    if (two) ptx::tma_load_2d(io0 + buf * C::kIoBytes + kHalfIo, &omaps.res, bres + buf * 8u, c0 + 64, r0);
+                };
+                // The folded per-channel affine of a tile's 128 columns is staged in shared memory ONE TILE AHEAD by 64 threads
+                // (one float4 of mul or add each): read straight from global memory inside the tile it was the largest single
+                // stall of the epilogue warps (long-scoreboard waits on 16 LDG.128 per thread and tile).  s_par: [2 buffers]
+                // [mul 128 | add 128]; the writes for tile ti + 1 happen during tile ti, whose two CTA-wide epilogue barriers
+                // order them before the reads.
+                auto stage_affine = [&](int n, uint32_t buf) {
+                    if (etid < 64) {
+                        const int c = n * BLOCK_N + (etid & 31) * 4;
+                        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c < Kout) v4 = __ldg(reinterpret_cast<const float4*>((etid < 32 ? p.epi.ch_mul : p.epi.ch_add) + c));
+                        *reinterpret_cast<float4*>(s_par + buf * 2 * BLOCK_N + (etid >> 5) * BLOCK_N + (etid & 31) * 4) = v4;
+                    }
+                };
+                int tm = (int)blockIdx.x / n_tiles, tn = (int)blockIdx.x % n_tiles;    // the only division: once per CTA
+                if (my_tiles > 0) {
+                    if (h_res && SLFP_LEADER) load_res(tm, tn, 0u);
+                    stage_affine(tn, 0u);
+                    ptx::bar_sync(1, kEpiWarps * 32);
                 }
-            };
-            if (my_tiles > 0) {
-                stage_affine((int)blockIdx.x, 0u);
-                ptx::bar_sync(1, kEpiWarps * 32);
-            }
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const uint32_t buf = (uint32_t)ti & 1u;
-                if (ti + 1 < my_tiles) stage_affine(tile + (int)gridDim.x, buf ^ 1u);
-                const uint32_t tacc = tile_begin(ti, tile);
-                const uint32_t s_mul_t = s_mul + buf * (uint32_t)(2 * BLOCK_N * 4) + (uint32_t)(cg * 32) * 4u, s_add_t = s_mul_t + BLOCK_N * 4;
-                const int n_slab = (tile % p.n_tiles) * BLOCK_N + cg * 32;
-                int nvalid = (p.Kout - n_slab) >> 4;                                 // 16-column chunks of this group inside Kout
-                nvalid = nvalid > 2 ? 2 : (nvalid < 0 ? 0 : nvalid);
-                const uint32_t io = io0 + buf * C::kIoBytes + io_t;
-                // both 16-column chunks leave TMEM at once; the accumulator buffer is released before any arithmetic
-                uint32_t acc[2][16];
-                uint32_t cw[2][2][4];                                                // packed codes [consumer][chunk]
-                const uint32_t tcol = tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32);
-                if (nvalid > 0) ptx::tmem_ld16(tcol, acc[0]);
-                if (nvalid > 1) ptx::tmem_ld16(tcol + 16u, acc[1]);
-                if (has_res) ptx::mbar_wait(bres + buf * 8u, ((uint32_t)ti >> 1) & 1u, 8u | ((uint32_t)ti << 16));
-                ptx::tmem_ld_wait();
-                tile_end(ti);
+                for (int ti = 0; ti < my_tiles; ++ti) {
+                    const uint32_t buf = (uint32_t)ti & 1u;
+                    int nm = tm, nn = tn;
+                    advance(nm, nn);                                                     // the next tile of this CTA
+                    if (ti + 1 < my_tiles) stage_affine(nn, buf ^ 1u);
+                    const uint32_t tacc = tile_begin(ti, 0);
+                    const uint32_t s_mul_t = s_mul + buf * (uint32_t)(2 * BLOCK_N * 4) + (uint32_t)(cg * 32) * 4u, s_add_t = s_mul_t + BLOCK_N * 4;
+                    const int n_slab = tn * BLOCK_N + cg * 32;
+                    int nvalid = (Kout - n_slab) >> 4;                                   // 16-column chunks of this group inside Kout
+                    nvalid = nvalid > 2 ? 2 : (nvalid < 0 ? 0 : nvalid);
+                    const uint32_t io = io0 + buf * C::kIoBytes + io_t;
+                    // both 16-column chunks leave TMEM at once; the accumulator buffer is released before any arithmetic
+                    uint32_t acc[2][16];
+                    uint32_t cw[2][2][4];                                                // packed codes [consumer][chunk]
+                    const uint32_t tcol = tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg * 32);
+                    if (nvalid > 0) ptx::tmem_ld16(tcol, acc[0]);
+                    if (nvalid > 1) ptx::tmem_ld16(tcol + 16u, acc[1]);
+                    if (h_res) ptx::mbar_wait(bres + buf * 8u, ((uint32_t)ti >> 1) & 1u, 8u | ((uint32_t)ti << 16));
+                    ptx::tmem_ld_wait();
+                    tile_end(ti);
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    const bool live = ch < nvalid;                                   // group-uniform
-                    const uint32_t ci = (uint32_t)((cg & 1) * 4 + 2 * ch);          // chunk index inside the 128-byte row
-                    const uint32_t ioa = io + ((ci ^ sw) << 4), iob = io + (((ci + 1u) ^ sw) << 4);
-                    float v[16];
-                    if (live) {
-                        uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
-                        if (has_res) { ra = ptx::lds128_volatile(ioa); rb = ptx::lds128_volatile(iob); }
-                        // per-channel affine: warp-uniform 16-byte shared-memory loads (broadcast) of the staged vectors
+                    for (int ch = 0; ch < 2; ++ch) {
+                        const bool live = ch < nvalid;                                   // group-uniform
+                        const uint32_t ci = (uint32_t)((cg & 1) * 4 + 2 * ch);          // chunk index inside the 128-byte row
+                        const uint32_t ioa = io + ((ci ^ sw) << 4), iob = io + (((ci + 1u) ^ sw) << 4);
+                        float v[16];
+                        if (live) {
+                            uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+                            if (h_res) { ra = ptx::lds128_volatile(ioa); rb = ptx::lds128_volatile(iob); }
+                            // per-channel affine: warp-uniform 16-byte shared-memory loads (broadcast) of the staged vectors
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const float4 m4 = ptx::lds128_f4(s_mul_t + (uint32_t)(ch * 16 + 4 * g) * 4u);
-                            const float4 a4 = ptx::lds128_f4(s_add_t + (uint32_t)(ch * 16 + 4 * g) * 4u);
-                            v[4 * g + 0] = fmaf(__uint_as_float(acc[ch][4 * g + 0]), m4.x, a4.x);
-                            v[4 * g + 1] = fmaf(__uint_as_float(acc[ch][4 * g + 1]), m4.y, a4.y);
-                            v[4 * g + 2] = fmaf(__uint_as_float(acc[ch][4 * g + 2]), m4.z, a4.z);
-                            v[4 * g + 3] = fmaf(__uint_as_float(acc[ch][4 * g + 3]), m4.w, a4.w);
-                        }
-                        if (has_res) {
-                            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 m4 = ptx::lds128_f4(s_mul_t + (uint32_t)(ch * 16 + 4 * g) * 4u);
+                                const float4 a4 = ptx::lds128_f4(s_add_t + (uint32_t)(ch * 16 + 4 * g) * 4u);
+                                v[4 * g + 0] = fmaf(__uint_as_float(acc[ch][4 * g + 0]), m4.x, a4.x);
+                                v[4 * g + 1] = fmaf(__uint_as_float(acc[ch][4 * g + 1]), m4.y, a4.y);
+                                v[4 * g + 2] = fmaf(__uint_as_float(acc[ch][4 * g + 2]), m4.z, a4.z);
+                                v[4 * g + 3] = fmaf(__uint_as_float(acc[ch][4 * g + 3]), m4.w, a4.w);
+                            }
+                            if (h_res) {
+                                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
-                                v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                                for (int i = 0; i < 8; ++i) {
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                                    v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                                }
+                            }
+                            if (lay) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = layerout_relu(v[i]);
                             }
                         }
-                        if (p.epi.layerout) {
+                        if (ch == 0) {
+                            // The previous tile's stores must have drained the other float16 buffer before the next tile's
+                            // residual lands in it, and the code staging tiles before this tile's codes are written.  Only the
+                            // leader's warp waits here; everybody else goes on with the arithmetic and the in-place float16
+                            // update (this tile's float16 buffer is not read by any pending store) and meets the leader at the
+                            // barrier below, by which time the drain is long over.
+                            if (SLFP_LEADER) {
+                                PROF(b, ptx::bulk_wait_read0());
+                                if (h_res && ti + 1 < my_tiles) load_res(nm, nn, buf ^ 1u);
+                            }
+                            __syncwarp();
+                        }
+                        if (!live) continue;
+                        if (h_y16) {
+                            uint32_t hw[8];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = layerout_relu(v[i]);
+                            for (int i = 0; i < 8; ++i) hw[i] = ptx::pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
+                            ptx::sts128(ioa, hw[0], hw[1], hw[2], hw[3]);
+                            ptx::sts128(iob, hw[4], hw[5], hw[6], hw[7]);
+                        }
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            if (!(pass ? h_c2 : h_c1)) continue;
+                            const float sc = pass ? sc2 : sc1;
+                            if (e4m3) {
+                                const uint4 q4 = encode16_e4m3_relu(v, pass ? p.rk2 : p.rk1);
+                                cw[pass][ch][0] = q4.x; cw[pass][ch][1] = q4.y; cw[pass][ch][2] = q4.z; cw[pass][ch][3] = q4.w;
+                                continue;
+                            }
+                            int32_t t[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)      // encode_relu_fast_raw16 with run-time format constants
+                                t[i] = (int32_t)(__float_as_uint(__saturatef(v[i] * sc)) >> enc_sh) - enc_base;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) cw[pass][ch][i] = ptx::pack_sat_u8x4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
                         }
                     }
-                    if (ch == 0) {
-                        // The previous tile's stores must have drained the other float16 buffer before the next tile's
-                        // residual lands in it, and the code staging tiles before this tile's codes are written.  Only the
-                        // leader's warp waits here; everybody else goes on with the arithmetic and the in-place float16
-                        // update (this tile's float16 buffer is not read by any pending store) and meets the leader at the
-                        // barrier below, by which time the drain is long over.
-                        if (SLFP_LEADER) {
-                            PROF(b, ptx::bulk_wait_read0());
-                            if (ti + 1 < my_tiles) load_res(tile + (int)gridDim.x, buf ^ 1u);
+                    PROF(c, ptx::bar_sync(1, kEpiWarps * 32));          // the leader has seen the code staging tiles drained
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        if (ch >= nvalid) continue;
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            if (!(pass ? h_c2 : h_c1)) continue;
+                            ptx::sts128((pass ? co2 : co1) + row_off + (((uint32_t)(cg * 2 + ch) ^ sw) << 4), cw[pass][ch][0], cw[pass][ch][1],
+                                        cw[pass][ch][2], cw[pass][ch][3]);
                         }
-                        __syncwarp();
                     }
-                    if (!live) continue;
-                    if (has_y16) {
-                        uint32_t hw[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) hw[i] = ptx::pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
-                        ptx::sts128(ioa, hw[0], hw[1], hw[2], hw[3]);
-                        ptx::sts128(iob, hw[4], hw[5], hw[6], hw[7]);
-                    }
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        if (!(pass ? has_c2 : has_c1)) continue;
-                        const float sc = pass ? sc2 : sc1;
-                        if (p.e4m3_out) {
-                            const uint4 q4 = encode16_e4m3_relu(v, pass ? p.rk2 : p.rk1);
-                            cw[pass][ch][0] = q4.x; cw[pass][ch][1] = q4.y; cw[pass][ch][2] = q4.z; cw[pass][ch][3] = q4.w;
-                            continue;
+                    ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
+                    PROF(c, ptx::bar_sync(1, kEpiWarps * 32));
+                    if (SLFP_LEADER) {
+                        const int c0 = tn * BLOCK_N, r0 = tm * kBM;
+                        if (h_y16) {
+                            ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes, c0, r0);
+                            if (c0 + 64 < Kout) ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes + kHalfIo, c0 + 64, r0);
                         }
-                        int32_t t[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)      // encode_relu_fast_raw16 with run-time format constants
-                            t[i] = (int32_t)(__float_as_uint(__saturatef(v[i] * sc)) >> enc_sh) - enc_base;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) cw[pass][ch][i] = ptx::pack_sat_u8x4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+                        if (h_c1) ptx::tma_store_2d(&omaps.c1, co1, c0, r0);
+                        if (h_c2) ptx::tma_store_2d(&omaps.c2, co2, c0, r0);
+                        ptx::bulk_commit();
                     }
+                    tm = nm; tn = nn;
                 }
-                PROF(c, ptx::bar_sync(1, kEpiWarps * 32));          // the leader has seen the code staging tiles drained
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    if (ch >= nvalid) continue;
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        if (!(pass ? has_c2 : has_c1)) continue;
-                        ptx::sts128((pass ? co2 : co1) + row_off + (((uint32_t)(cg * 2 + ch) ^ sw) << 4), cw[pass][ch][0], cw[pass][ch][1],
-                                    cw[pass][ch][2], cw[pass][ch][3]);
-                    }
-                }
-                ptx::fence_proxy_async_smem();             // staging writes -> async proxy (TMA store)
-                PROF(c, ptx::bar_sync(1, kEpiWarps * 32));
-                if (SLFP_LEADER) {
-                    const int c0 = (tile % p.n_tiles) * BLOCK_N, r0 = (tile / p.n_tiles) * kBM;
-                    if (has_y16) {
-                        ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes, c0, r0);
-                        if (c0 + 64 < p.Kout) ptx::tma_store_2d(&omaps.y16, io0 + buf * C::kIoBytes + kHalfIo, c0 + 64, r0);
-                    }
-                    if (has_c1) ptx::tma_store_2d(&omaps.c1, co1, c0, r0);
-                    if (has_c2) ptx::tma_store_2d(&omaps.c2, co2, c0, r0);
-                    ptx::bulk_commit();
-                }
-            }
-            if (SLFP_LEADER) ptx::bulk_wait0();
+                if (SLFP_LEADER) ptx::bulk_wait0();
+            };
+            using T = std::true_type;
+            using F = std::false_type;
+            if (p.e4m3_out || p.epi.layerout || !has_c1) run(F{}, F{}, F{}, T{});        // generic: run-time flags
+            else if (has_res && has_y16 && !has_c2) run(T{}, T{}, F{}, F{});              // block tail inside a stage
+            else if (has_res && !has_y16 && has_c2) run(T{}, F{}, T{}, F{});              // last tail of a stage (two consumers)
+            else if (has_res && has_y16 && has_c2) run(T{}, T{}, T{}, F{});
+            else if (has_res && !has_y16 && !has_c2) run(T{}, F{}, F{}, F{});
+            else if (!has_res && has_y16 && !has_c2) run(F{}, T{}, F{}, F{});             // fused dual tail
+            else if (!has_res && has_y16 && has_c2) run(F{}, T{}, T{}, F{});
+            else if (!has_res && !has_y16 && has_c2) run(F{}, F{}, T{}, F{});
+            else run(F{}, F{}, F{}, F{});
 #undef SLFP_LEADER
         } else
         for (int ti = 0; ti < my_tiles; ++ti) {
@@ -1336,7 +1370,8 @@ template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false, bo
 static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const OutMaps& om, const Params& p, cudaStream_t st) {
     using C = Cfg<BLOCK_N, STG, NODEC, A16>;
     auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI, NODEC, A16>;
-    static bool attr_done = false;
+    static DeviceOnce attr_once;
+    bool& attr_done = attr_once.flag();
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return set_error((int)e, "conv_igemm_v2: smem attribute (%d B): %s", C::kSmemBytes, cudaGetErrorString(e));

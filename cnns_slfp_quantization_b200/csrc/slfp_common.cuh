@@ -577,6 +577,18 @@ int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
 int num_sms();
 
+// "done once PER DEVICE" flag: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device property, and one process may
+// drive several GPUs (the deployment model is one process per GPU, but nothing may break otherwise).  Racing threads at
+// worst set the attribute twice.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool& flag() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = 0; }
+        return done[dev];
+    }
+};
+
 static inline __host__ __device__ size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
 
 }  // namespace slfp

@@ -227,6 +227,31 @@ def test_s2d_input_quantizer_fast_path_with_special_values(orc, fmt):
             for c in range(C):
                 want[..., (dy * 2 + dx) * C + c] = codes[:, c, dy::2, dx::2]
     assert (out.cpu().numpy() == want).all()
+    # SLFP_FMT_F16Q forms of the input quantizers (round 2): float16 images of exactly those codes' values
+    _, fq = orc.quantize(x, fmt, float(k), want_codes=False)
+    with np.errstate(over="ignore", invalid="ignore"):
+        img = fq.astype(np.float16)                                                      # [n, c, h, w]
+    # (a) width-folded stem input: zero-padded [n, hp, wp, 16] buffer, interior at (2, 2)
+    hp, wp = H // 2 + 3, W // 2 + 3
+    o16 = torch.zeros((N, hp, wp, 16), dtype=torch.float16, device="cuda")
+    nv.check(lib.slfp_quantize_nchw_s2d_f16q(xt.data_ptr(), N, H, W, float(k), fmt, 2, 2, hp, wp, o16.data_ptr(), nv.stream()))
+    torch.cuda.synchronize()
+    want16 = np.zeros((N, hp, wp, 16), np.float16)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(C):
+                want16[:, 2:2 + H // 2, 2:2 + W // 2, (dy * 2 + dx) * C + c] = img[:, c, dy::2, dx::2]
+    assert (o16.cpu().numpy().view(np.uint16) == want16.view(np.uint16)).all()
+    # (b) 3x3 / pad 1 im2col matrix [n, h, w, 64], entry (r * 3 + s) * 4 + c
+    oi = torch.full((N, H, W, 64), 7.0, dtype=torch.float16, device="cuda")
+    nv.check(lib.slfp_quantize_nchw_im2col3x3_f16q(xt.data_ptr(), N, H, W, float(k), fmt, oi.data_ptr(), nv.stream()))
+    torch.cuda.synchronize()
+    wanti = np.zeros((N, H, W, 64), np.float16)
+    pad = np.pad(img.transpose(0, 2, 3, 1), ((0, 0), (1, 1), (1, 1), (0, 0)))
+    for r in range(3):
+        for s_ in range(3):
+            wanti[..., (r * 3 + s_) * 4:(r * 3 + s_) * 4 + 3] = pad[:, r:r + H, s_:s_ + W]
+    assert (oi.cpu().numpy().view(np.uint16) == wanti.view(np.uint16)).all()
 
 
 def test_gather_quantize_matches_plain_quantizer(orc):
