@@ -68,7 +68,27 @@ template <int DW> struct Roles {
     static constexpr int kChunksPerThread = 512 / (32 * DW);           // 16-byte code chunks per decode thread per K block
 };
 
+// n / d for n < 2^31 as umulhi(n, mg) >> sh (d > 1): the kernel divides tile indices by n_tiles / Ho*Wo / Wo several times per tile
+// in every role; a hardware-less 32-bit division is ~30 dependent instructions each (the single-thread producer roles and
+// the epilogue warps of the short-K layers were paying 100-150 of them per tile).
+struct Magic {
+    uint32_t d, mg, sh;
+};
+static Magic make_magic(uint32_t d) {
+    Magic k{d, 0u, 0u};
+    if (d > 1) {
+        uint32_t lg = 31 - (uint32_t)__builtin_clz(d);
+        if (d & (d - 1)) ++lg;
+        const uint32_t pw = 31 + lg;
+        k.mg = (uint32_t)(((1ull << pw) + d - 1) / d);
+        k.sh = pw - 32;
+    }
+    return k;
+}
+__device__ __forceinline__ uint32_t mdiv(uint32_t n, const Magic& k) { return k.d == 1u ? n : (__umulhi(n, k.mg) >> k.sh); }
+
 struct Params {
+    Magic k_ntiles, k_howo, k_wo;
     uint32_t M;
     int Kout;
     int HoWo, Wo;
@@ -216,8 +236,9 @@ __device__ __forceinline__ void epilogue_slab(const Params& p, int tile, uint32_
     const int Kout = p.Kout;
     const bool vec4 = (Kout & 3) == 0, vec8 = (Kout & 7) == 0;
     constexpr int kCols = BLOCK_N / G;
-    const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
-    const int n_base = (tile % p.n_tiles) * BLOCK_N + half * kCols;
+    const uint32_t tile_m = mdiv((uint32_t)tile, p.k_ntiles);
+    const uint32_t m = tile_m * kBM + (uint32_t)(quad * 32 + lane);
+    const int n_base = (int)((uint32_t)tile - tile_m * (uint32_t)p.n_tiles) * BLOCK_N + half * kCols;
     const bool row_ok = m < p.M;
     const bool folded = e.ch_mul != nullptr;
     const bool fast_codes = e.next_fmt == SLFP_FMT_SLFP34_RELU || e.next_fmt == SLFP_FMT_SFP33_RELU;
@@ -442,8 +463,9 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
     static_assert(BLOCK_N / G >= 32, "32-column steps");
     constexpr int kCols = BLOCK_N / G;
     const int Kout = p.Kout;
-    const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
-    const int n_tile0 = (tile % p.n_tiles) * BLOCK_N;
+    const uint32_t tile_m = mdiv((uint32_t)tile, p.k_ntiles);
+    const uint32_t m = tile_m * kBM + (uint32_t)(quad * 32 + lane);
+    const int n_tile0 = (int)((uint32_t)tile - tile_m * (uint32_t)p.n_tiles) * BLOCK_N;
     const bool odd = (lane & 1) != 0;
     // rows this lane STORES to after the pair exchange (m's parity is the lane's)
     const uint32_t m_first = m & ~1u, m_second = m | 1u;
@@ -457,8 +479,9 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
     const float sc1 = p.sc1, sc2 = p.sc2;
     if (MODE == 2 && resp != nullptr && next_tile < p.num_tiles) {
         // push this lane's row segment of the NEXT tile's residual towards L2 (no register, no scoreboard)
-        const uint32_t mn = (uint32_t)(next_tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
-        const int nb = (next_tile % p.n_tiles) * BLOCK_N + half * kCols;
+        const uint32_t next_m = mdiv((uint32_t)next_tile, p.k_ntiles);
+        const uint32_t mn = next_m * kBM + (uint32_t)(quad * 32 + lane);
+        const int nb = (int)((uint32_t)next_tile - next_m * (uint32_t)p.n_tiles) * BLOCK_N + half * kCols;
         if (mn < p.M) {
 #pragma unroll
             for (int c = 0; c < kCols; c += 64)
@@ -578,8 +601,9 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
     constexpr int kCols = BLOCK_N / G;
     constexpr int kChunks = kCols / 16;
     const int Kout = p.Kout;
-    const uint32_t m = (uint32_t)(tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
-    const int n_base = (tile % p.n_tiles) * BLOCK_N + cg * kCols;
+    const uint32_t tile_m = mdiv((uint32_t)tile, p.k_ntiles);
+    const uint32_t m = tile_m * kBM + (uint32_t)(quad * 32 + lane);
+    const int n_base = (int)((uint32_t)tile - tile_m * (uint32_t)p.n_tiles) * BLOCK_N + cg * kCols;
     const bool odd = (lane & 1) != 0;
     const uint32_t m_first = m & ~1u, m_second = m | 1u;
     const bool ok_first = m_first < p.M, ok_second = m_second < p.M, row_ok = m < p.M;
@@ -593,8 +617,9 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
     int nvalid = (Kout - n_base) >> 4;                           // chunks of this slab inside Kout
     nvalid = nvalid > kChunks ? kChunks : nvalid;
     if (MODE == 2 && resp != nullptr && next_tile < p.num_tiles) {
-        const uint32_t mn = (uint32_t)(next_tile / p.n_tiles) * kBM + (uint32_t)(quad * 32 + lane);
-        const int nb = (next_tile % p.n_tiles) * BLOCK_N + cg * kCols;
+        const uint32_t next_m = mdiv((uint32_t)next_tile, p.k_ntiles);
+        const uint32_t mn = next_m * kBM + (uint32_t)(quad * 32 + lane);
+        const int nb = (int)((uint32_t)next_tile - next_m * (uint32_t)p.n_tiles) * BLOCK_N + cg * kCols;
         if (mn < p.M && nb < Kout) ptx::prefetch_l2(resp + (size_t)mn * Kout + nb);     // 32..128 bytes of one row
     }
     uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra, na = ra, nb4 = ra;
@@ -829,10 +854,12 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const bool w_res_nd = NODEC && p.n_tiles == 1 && p.num_kb <= kCodeStages && (kCodeStages % p.num_kb) == 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const uint32_t m0 = (uint32_t)(tile / p.n_tiles) * kBM;
-                const int n = (int)(m0 / (uint32_t)p.HoWo);
+                const uint32_t tile_m = mdiv((uint32_t)tile, p.k_ntiles);
+                const int tile_n = (int)((uint32_t)tile - tile_m * (uint32_t)p.n_tiles);
+                const uint32_t m0 = tile_m * kBM;
+                const int n = (int)mdiv(m0, p.k_howo);
                 const int rem = (int)(m0 - (uint32_t)n * (uint32_t)p.HoWo);
-                const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
+                const int ho = (int)mdiv((uint32_t)rem, p.k_wo), wo = rem - ho * p.Wo;
                 const int w0 = wo * p.sw - p.pw, h0 = ho * p.sh - p.ph;
                 int tap = 0, r = 0, s = 0, cb = 0;       // GRAN 64: cb = 64-channel block; GRAN 16: 16-channel block
                 int kb = 0;                               // K block inside ONE pass over K (the split-operand mode makes three)
@@ -858,7 +885,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                         if (ptx::elect_one()) {
                             ptx::mbar_arrive_expect_tx(full, (uint32_t)C::kCodeTile + (load_b ? (uint32_t)C::kBBytes : 0u));
                             if (load_b)                 // the weight tile of this K block rides on the same barrier
-                                ptx::tma_load_2d(ptx::smem_u32(s_b + cs * C::kBBytes), &tmap_w, full, kbt * kBK, (tile % p.n_tiles) * BLOCK_N);
+                                ptx::tma_load_2d(ptx::smem_u32(s_b + cs * C::kBBytes), &tmap_w, full, kbt * kBK, tile_n * BLOCK_N);
                             if (kb >= p.nkb1)           // concatenated second input: 1x1 window at (ho*sh2, wo*sw2)
                                 ptx::tma_load_im2col_4d(dst, &tmap_x2, full, (kb - p.nkb1) * 64, wo * p.sw2, ho * p.sh2, n, 0, 0);
                             else if (p.plain_1x1) ptx::tma_load_2d(dst, &tmap_x, full, cb * 64, (int)m0);
@@ -898,7 +925,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             uint32_t issued = 0;
             for (int ti = 0; ti < (NODEC ? 0 : my_tiles); ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const int n0 = (tile % p.n_tiles) * BLOCK_N;
+                const int n0 = (int)((uint32_t)tile - mdiv((uint32_t)tile, p.k_ntiles) * (uint32_t)p.n_tiles) * BLOCK_N;
                 for (int kb = 0; kb < p.num_kb; ++kb, ++issued) {
                     PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1u, 2u | ((uint32_t)kb << 8) | ((uint32_t)ti << 16)));
                     const uint32_t full = ptx::smem_u32(&bar_full[stage]);
@@ -1093,7 +1120,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const uint32_t buf = (uint32_t)ti & 1u;
             if (!STG && mode != 0) {
                 // the fast modes read the folded affine from shared memory (mode 1: pre-scaled by 1/(16 Ka_next))
-                const int n_tile0 = (tile % p.n_tiles) * BLOCK_N;
+                const int n_tile0 = (int)((uint32_t)tile - mdiv((uint32_t)tile, p.k_ntiles) * (uint32_t)p.n_tiles) * BLOCK_N;
                 if (n_tile0 != staged_n0) {
                     ptx::bar_sync(1, kEpiWarps * 32);          // every epilogue warp is done with the previous vectors
                     const float sc = mode == 1 ? (p.e4m3_out ? p.rk1 : p.sc1) : 1.0f;      // mode 2 keeps relu(y) itself for the float16 output
@@ -1553,6 +1580,9 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     }
     p.n_tiles = (d->k + bn - 1) / bn;
     p.num_tiles = p.m_tiles * p.n_tiles;
+    p.k_ntiles = make_magic((uint32_t)p.n_tiles);
+    p.k_howo = make_magic((uint32_t)p.HoWo);
+    p.k_wo = make_magic((uint32_t)p.Wo);
 
     CUtensorMap tmap_x2;
     static auto enc_tiled = driver_fn<PFN_cuTensorMapEncodeTiled_v12000>("cuTensorMapEncodeTiled");
