@@ -214,7 +214,7 @@ __device__ __forceinline__ uint4 encode16_exact(const float (&v)[16], const DivK
 // the code is formed exactly like encode16_fast (saturating clamp, truncated bit pattern) and looked up in the kernel's
 // output table instead of being packed to a byte.  olut_rel = table base + (lane % copies) * 4 - base_code * copies * 4; bit 0
 // of it (the address is 4-byte aligned) flags the 16-copy table.
-template <bool SFP33>
+template <bool SFP33, bool PRESAT = false>
 __device__ __forceinline__ void encode16_q16(const float (&u)[16], uint32_t olut_rel_f, uint32_t (&h)[8]) {
     const uint32_t half = olut_rel_f & 1u, olut_rel = olut_rel_f & ~1u;                 // warp-uniform
     const uint32_t sh = (SFP33 ? 12u : 11u) + half, mask = half ? 0xffffffc0u : 0xffffff80u;
@@ -222,7 +222,7 @@ __device__ __forceinline__ void encode16_q16(const float (&u)[16], uint32_t olut
     uint32_t e[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const uint32_t b = __float_as_uint(fmaxf(__saturatef(u[i]), lo));
+        const uint32_t b = __float_as_uint(fmaxf(PRESAT ? u[i] : __saturatef(u[i]), lo));
         e[i] = ptx::lds32_off((b >> sh) & mask, olut_rel);
     }
 #pragma unroll
@@ -457,12 +457,16 @@ __device__ __forceinline__ void pair_exchange(const uint4& A, const uint4& B, bo
     second.x = odd ? B.x : recv.x; second.y = odd ? B.y : recv.y; second.z = odd ? B.z : recv.z; second.w = odd ? B.w : recv.w;
 }
 
-template <int BLOCK_N, int G, int MODE, bool SFP33>
+// OUT (MODE 1): what the single output tensor receives - 0 post-ReLU code bytes, 1 e4m3 bytes, 2 float16 images of the codes
+// (store_f16); -1 = decided at run time (MODE 2).  A compile-time OUT lets the clamp fold into the affine (FFMA.SAT) and drops
+// the per-chunk flag tests: the 1x1 reduce layers are bound by the instruction issue of their epilogue warps.
+template <int BLOCK_N, int G, int MODE, bool SFP33, int OUT = -1>
 __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int next_tile, uint32_t tmem_acc, int quad, int half,
                                               int lane, uint32_t s_mul, uint32_t s_add, uint32_t olut_rel) {
     static_assert(BLOCK_N / G >= 32, "32-column steps");
     constexpr int kCols = BLOCK_N / G;
     const int Kout = p.Kout;
+    const bool kE4m3 = OUT < 0 ? (p.e4m3_out != 0) : OUT == 1, kQ16 = OUT < 0 ? (p.epi.store_f16 != 0) : OUT == 2;
     const uint32_t tile_m = mdiv((uint32_t)tile, p.k_ntiles);
     const uint32_t m = tile_m * kBM + (uint32_t)(quad * 32 + lane);
     const int n_tile0 = (int)((uint32_t)tile - tile_m * (uint32_t)p.n_tiles) * BLOCK_N;
@@ -519,13 +523,17 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
                 v[4 * g + 1] = fmaf(__uint_as_float(acc[o + 4 * g + 1]), m4.y, a4.y);
                 v[4 * g + 2] = fmaf(__uint_as_float(acc[o + 4 * g + 2]), m4.z, a4.z);
                 v[4 * g + 3] = fmaf(__uint_as_float(acc[o + 4 * g + 3]), m4.w, a4.w);
+                if (MODE == 1 && (OUT == 0 || OUT == 2)) {           // the clamp to [0, 1] folds into the FMA
+                    v[4 * g + 0] = __saturatef(v[4 * g + 0]); v[4 * g + 1] = __saturatef(v[4 * g + 1]);
+                    v[4 * g + 2] = __saturatef(v[4 * g + 2]); v[4 * g + 3] = __saturatef(v[4 * g + 3]);
+                }
             }
-            if (MODE == 1 && p.e4m3_out) {
+            if (MODE == 1 && kE4m3) {
                 pk1[o / 16] = encode16_e4m3_relu_prescaled(v);       // the staged affine carries 1 / Ka_next
-            } else if (MODE == 1 && p.epi.store_f16) {
+            } else if (MODE == 1 && kQ16) {
                 // float16 images of the codes: 32 contiguous bytes (one sector) of this lane's row
                 uint32_t hq[8];
-                encode16_q16<SFP33>(v, olut_rel, hq);
+                encode16_q16<SFP33, OUT == 2>(v, olut_rel, hq);
                 // lane pairs swap 16-byte pieces: every store instruction writes whole 32-byte sectors
                 uint4 f1, f2;
                 pair_exchange(make_uint4(hq[0], hq[1], hq[2], hq[3]), make_uint4(hq[4], hq[5], hq[6], hq[7]), odd, f1, f2);
@@ -535,7 +543,7 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
             } else if (MODE == 1) {
                 int32_t t[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i]));
+                for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(OUT == 0 ? v[i] : __saturatef(v[i]));
                 pk1[o / 16] = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
                                          ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
             } else {
@@ -574,11 +582,11 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
                 }
             }
         }
-        if (MODE == 1 && p.epi.store_f16) continue;             // stored above
+        if (MODE == 1 && kQ16) continue;                        // stored above
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
             uint8_t* yc = pass ? yc2 : yc1;
-            if (yc == nullptr) continue;
+            if (MODE == 1 ? pass == 1 : yc == nullptr) continue;
             const uint4 pa = pass ? pk2[0] : pk1[0];
             if (two) {
                 uint4 f1, f2;
@@ -595,12 +603,13 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, int tile, int nex
 // The same epilogues in 16-column steps for the 16-epilogue-warp role split (88 registers per thread, 4 column
 // groups of BLOCK_N / 4 columns): the residual of the next chunk is requested before the current one is
 // processed, code pieces of two consecutive chunks pair up for the full-sector stores.
-template <int BLOCK_N, int G, int MODE, bool SFP33>
+template <int BLOCK_N, int G, int MODE, bool SFP33, int OUT = -1>
 __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int next_tile, uint32_t tmem_acc, int quad, int cg,
                                                 int lane, uint32_t s_mul, uint32_t s_add, uint32_t olut_rel) {
     constexpr int kCols = BLOCK_N / G;
     constexpr int kChunks = kCols / 16;
     const int Kout = p.Kout;
+    const bool kE4m3 = OUT < 0 ? (p.e4m3_out != 0) : OUT == 1, kQ16 = OUT < 0 ? (p.epi.store_f16 != 0) : OUT == 2;
     const uint32_t tile_m = mdiv((uint32_t)tile, p.k_ntiles);
     const uint32_t m = tile_m * kBM + (uint32_t)(quad * 32 + lane);
     const int n_base = (int)((uint32_t)tile - tile_m * (uint32_t)p.n_tiles) * BLOCK_N + cg * kCols;
@@ -650,13 +659,17 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
             v[4 * g + 1] = fmaf(__uint_as_float(acc[4 * g + 1]), m4.y, a4.y);
             v[4 * g + 2] = fmaf(__uint_as_float(acc[4 * g + 2]), m4.z, a4.z);
             v[4 * g + 3] = fmaf(__uint_as_float(acc[4 * g + 3]), m4.w, a4.w);
+            if (MODE == 1 && (OUT == 0 || OUT == 2)) {               // the clamp to [0, 1] folds into the FMA
+                v[4 * g + 0] = __saturatef(v[4 * g + 0]); v[4 * g + 1] = __saturatef(v[4 * g + 1]);
+                v[4 * g + 2] = __saturatef(v[4 * g + 2]); v[4 * g + 3] = __saturatef(v[4 * g + 3]);
+            }
         }
         uint4 pk1, pk2 = make_uint4(0u, 0u, 0u, 0u);
-        if (MODE == 1 && p.e4m3_out) {
+        if (MODE == 1 && kE4m3) {
             pk1 = encode16_e4m3_relu_prescaled(v);                   // the staged affine carries 1 / Ka_next
-        } else if (MODE == 1 && p.epi.store_f16) {
+        } else if (MODE == 1 && kQ16) {
             uint32_t hq[8];
-            encode16_q16<SFP33>(v, olut_rel, hq);
+            encode16_q16<SFP33, OUT == 2>(v, olut_rel, hq);
             uint4 f1, f2;
             pair_exchange(make_uint4(hq[0], hq[1], hq[2], hq[3]), make_uint4(hq[4], hq[5], hq[6], hq[7]), odd, f1, f2);
             __half* yh = reinterpret_cast<__half*>(yc1);
@@ -666,7 +679,7 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
         } else if (MODE == 1) {
             int32_t t[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(__saturatef(v[i]));
+            for (int i = 0; i < 16; ++i) t[i] = encode_relu_fast_raw16<SFP33>(OUT == 0 ? v[i] : __saturatef(v[i]));
             pk1 = make_uint4(ptx::pack_sat_u8x4(t[0], t[1], t[2], t[3]), ptx::pack_sat_u8x4(t[4], t[5], t[6], t[7]),
                              ptx::pack_sat_u8x4(t[8], t[9], t[10], t[11]), ptx::pack_sat_u8x4(t[12], t[13], t[14], t[15]));
         } else {
@@ -710,7 +723,7 @@ __device__ __forceinline__ void epilogue_fast16(const Params& p, int tile, int n
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
             uint8_t* yc = pass ? yc2 : yc1;
-            if (yc == nullptr) continue;
+            if (MODE == 1 ? pass == 1 : yc == nullptr) continue;
             const uint4 cur = pass ? pk2 : pk1;
             if (ch & 1) {
                 uint4 f1, f2;
@@ -1108,6 +1121,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int half = (warp - kEpiWarp0) >> 2;
         const int etid = (warp - kEpiWarp0) * 32 + lane;
         const int mode = p.epi_mode;
+        const int out_kind = p.e4m3_out ? 1 : (p.epi.store_f16 ? 2 : 0);      // what a codes-only epilogue writes (warp-uniform)
         const bool sfp33 = p.epi.next_fmt == SLFP_FMT_SFP33_RELU || (p.epi.layerout && p.epi.next_fmt == SLFP_FMT_SFP33);
         const uint32_t s_mul = ptx::smem_u32(s_par), s_add = s_mul + BLOCK_N * 4;
         // output table of store_f16: entry address = (raw code << 6) + this, raw code = (bits >> 18 | 19) - base
@@ -1349,8 +1363,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             const uint32_t tacc = tile_begin(ti, tile);
             if (kGroups == 2) {
                 if (mode == 1) {
-                    if (sfp33) epilogue_fast<BLOCK_N, 2, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
-                    else epilogue_fast<BLOCK_N, 2, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
+#define SLFP_EPI1(SF, O) epilogue_fast<BLOCK_N, 2, 1, SF, O>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel)
+                    if (sfp33) { if (out_kind == 0) SLFP_EPI1(true, 0); else if (out_kind == 1) SLFP_EPI1(true, 1); else SLFP_EPI1(true, 2); }
+                    else { if (out_kind == 0) SLFP_EPI1(false, 0); else if (out_kind == 1) SLFP_EPI1(false, 1); else SLFP_EPI1(false, 2); }
+#undef SLFP_EPI1
                 } else if (mode == 2) {
                     if (sfp33) epilogue_fast<BLOCK_N, 2, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
                     else epilogue_fast<BLOCK_N, 2, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
@@ -1359,8 +1375,10 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
             } else {
                 if (mode == 1) {
-                    if (sfp33) epilogue_fast16<BLOCK_N, 4, 1, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
-                    else epilogue_fast16<BLOCK_N, 4, 1, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
+#define SLFP_EPI1(SF, O) epilogue_fast16<BLOCK_N, 4, 1, SF, O>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel)
+                    if (sfp33) { if (out_kind == 0) SLFP_EPI1(true, 0); else if (out_kind == 1) SLFP_EPI1(true, 1); else SLFP_EPI1(true, 2); }
+                    else { if (out_kind == 0) SLFP_EPI1(false, 0); else if (out_kind == 1) SLFP_EPI1(false, 1); else SLFP_EPI1(false, 2); }
+#undef SLFP_EPI1
                 } else if (mode == 2) {
                     if (sfp33) epilogue_fast16<BLOCK_N, 4, 2, true>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
                     else epilogue_fast16<BLOCK_N, 4, 2, false>(p, tile, next_tile, tacc, quad, half, lane, s_mul, s_add, olut_rel);
