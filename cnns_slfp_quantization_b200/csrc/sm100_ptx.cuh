@@ -56,10 +56,21 @@ static __device__ __noinline__ void mbar_timeout(uint32_t tag) {
     __trap();
 }
 // Bounded wait: a pipeline bug must trap (-> a CUDA error the host reports), never hang the GPU.
+#ifndef SLFP_SPIN_PROBES
+#define SLFP_SPIN_PROBES 12
+#endif
+#ifndef SLFP_SPIN_SLEEP_NS
+#define SLFP_SPIN_SLEEP_NS 48
+#endif
+constexpr uint32_t kSpinProbes = SLFP_SPIN_PROBES, kSpinSleepNs = SLFP_SPIN_SLEEP_NS;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
+    // A waiter that is about to be served probes back to back; one that has been waiting for a while (a role with slack:
+    // the decode warps of an epilogue-bound block tail issued 15 % of the kernel's instructions doing this) sleeps between
+    // probes so that its spinning does not take issue slots from the warps everybody is waiting for.
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) mbar_timeout(tag);
+        if (++spins > kSpinProbes) __nanosleep(kSpinSleepNs);
+        if (spins > (1u << 22)) mbar_timeout(tag);
     }
 }
 
