@@ -312,7 +312,8 @@ class Plan:
         # Storing halves instead of bytes costs the PRODUCER ~0.5 us per 2^20 output elements (measured on the 1x1 reduce
         # layers, whose 8 epilogue warps are their critical path) against a flat ~12-18 us the 3x3 consumer saves by not
         # decoding: worth it below ~16 M elements (ResNet-50 stages 3-4 at batch 256)
-        q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS", 16 << 20))
+        # (a producer that itself reads float16 images has no decode warps competing with its epilogue's table look-ups: 64 M)
+        q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS", (64 << 20) if x.kind == "q16" else (16 << 20)))
         as_q16 = (q16 and self.f16q and dense and (x.cp % 16 == 0 or x.im2col) and len(kds) == 1 and relu and bn is not None and K % 64 == 0
                   and Kk == K and ofmt == nv.relu_fmt(self.afmt) and not f16 and not f32 and residual is None and not layerout
                   and x.n * Ho * Wo * K <= q16_max)
