@@ -116,7 +116,21 @@ struct DwFastParams {
     const float* ch_add;
     float sc;                  // 1 / (16 Ka_next)
     uint8_t* y;
+    // strip kernel: 32-bit work-item index split by magic-number division (n / d == umulhi(n, mg) >> sh for n < 2^31, d > 1);
+    // the three 64-bit divisions + two modulos per work item were ~500 of its ~3 000 instructions
+    unsigned total32, cg_mg, cg_sh, ws_mg, ws_sh, ho_mg, ho_sh;
 };
+static void dw_magic(unsigned d, unsigned& mg, unsigned& sh) {
+    mg = 0; sh = 0;
+    if (d > 1) {
+        unsigned lg = 31 - (unsigned)__builtin_clz(d);
+        if (d & (d - 1)) ++lg;
+        const unsigned pw = 31 + lg;
+        mg = (unsigned)(((1ull << pw) + d - 1) / d);
+        sh = pw - 32;
+    }
+}
+__device__ __forceinline__ unsigned dw_div(unsigned n, unsigned d, unsigned mg, unsigned sh) { return d == 1u ? n : (__umulhi(n, mg) >> sh); }
 
 // weight of (tap t, channel c = 16 q + 4 g + e) lives at s_w[t * Cp + (g * (Cp / 16) + q) * 4 + e]: the threads of a
 // warp differ in q, so their 16-byte weight loads for a fixed g are consecutive (bank-conflict free)
@@ -230,7 +244,9 @@ __global__ void __launch_bounds__(256) dwconv_fast_kernel(const DwFastParams p) 
 // Both forms hold 64 accumulators in 128 registers (two CTAs = 16 warps per SM, one resident wave): VEC = 4 is 4 outputs x 16
 // channels (16-byte vectors); VEC = 2 is 8 channels (8-byte vectors) x 8 outputs at stride 1 (3.75 instead of 4.5 table decodes and
 // half the weight reads per output) or x 4 outputs at stride 2 (no spills, where the 16-channel form spills its 9-column window).
-// OUT: 0 = post-ReLU fast codes, 1 = signed fast SFP<3,3>, 2 = e4m3 bytes (compile-time: the run-time form spilled)
+// OUT: 0 = post-ReLU fast codes, 1 = signed fast SFP<3,3>, 2 = e4m3 bytes (compile-time: the run-time form spilled),
+// 3 = e4m3 bytes out AND in: the input bytes are decoded by the hardware converter (cvt.rn.f16x2.e4m3x2: two values per
+// instruction + one float16 -> float32 each, exact) instead of the shared-memory table (shift + LOP3 + LDS per value)
 template <int STRIDE, int VEC, int OUT>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastParams p) {
     extern __shared__ __align__(128) uint8_t dsm[];
@@ -262,15 +278,18 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
     // strip length: 4 outputs of 16 channels, or (VEC = 2) 8 outputs of 8 channels at stride 1 - the same 64 accumulators,
     // 10 instead of 12 decoded input columns per 8 outputs and half the weight reads per output
     constexpr int kOut = (VEC == 2 && STRIDE == 1) ? 8 : 4, kCols = (kOut - 1) * STRIDE + 3;
+    constexpr bool kHwDecode = OUT == 3;
+    constexpr bool kE4m3Out = OUT == 2 || OUT == 3;
     const int wstrips = (p.Wo + kOut - 1) / kOut;
-    const size_t total = (size_t)p.N * p.Ho * wstrips * cg;
     const int enc_shift = p.out_sfp33 ? 19 : 18, enc_bias = p.out_sfp33 ? 0x76F : 0xEDF;    // encode_relu_fast_raw16<>
     const bool pad_channels = p.C != p.Cp;
-    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
-        const int q = (int)(idx % cg), c0 = q * CH;
-        size_t rest = idx / cg;
-        const int ws = (int)(rest % wstrips); rest /= wstrips;
-        const int ho = (int)(rest % p.Ho), n = (int)(rest / p.Ho);
+    for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < p.total32; idx += gridDim.x * 256u) {
+        unsigned rest = dw_div(idx, (unsigned)cg, p.cg_mg, p.cg_sh);
+        const int q = (int)(idx - rest * (unsigned)cg), c0 = q * CH;
+        const unsigned r1 = dw_div(rest, (unsigned)wstrips, p.ws_mg, p.ws_sh);
+        const int ws = (int)(rest - r1 * (unsigned)wstrips);
+        const unsigned r2 = dw_div(r1, (unsigned)p.Ho, p.ho_mg, p.ho_sh);
+        const int ho = (int)(r1 - r2 * (unsigned)p.Ho), n = (int)r2;
         const int wo0 = ws * kOut;
         float acc[kOut][CH];
 #pragma unroll
@@ -307,10 +326,20 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
 #pragma unroll
                 for (int cidx = 0; cidx < kCols; ++cidx) {
                     const uint32_t c = cw[cidx][g];
-                    const float x0 = __uint_as_float(ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base));
-                    const float x1 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base));
-                    const float x2 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base));
-                    const float x3 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base));
+                    float x0, x1, x2, x3;
+                    if (kHwDecode) {
+                        uint32_t h01, h23;
+                        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
+                            "cvt.rn.f16x2.e4m3x2 %0, lo;\n\tcvt.rn.f16x2.e4m3x2 %1, hi;\n\t}\n" : "=r"(h01), "=r"(h23) : "r"(c));
+                        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+                        const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+                        x0 = f01.x; x1 = f01.y; x2 = f23.x; x3 = f23.y;
+                    } else {
+                        x0 = __uint_as_float(ptx::lds32_off(ptx::and_or(c << 7, 0x7f80u, lane4), lut_base));
+                        x1 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 1, 0x7f80u, lane4), lut_base));
+                        x2 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 9, 0x7f80u, lane4), lut_base));
+                        x3 = __uint_as_float(ptx::lds32_off(ptx::and_or(c >> 17, 0x7f80u, lane4), lut_base));
+                    }
 #pragma unroll
                     for (int o = 0; o < kOut; ++o) {
                         const int s = cidx - o * STRIDE;                    // filter column this input column has for output o
@@ -329,7 +358,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
         for (int g = 0; g < VEC; ++g) {
             m4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_mul + c0) + g);
             a4[g] = __ldg(reinterpret_cast<const float4*>(p.ch_add + c0) + g);
-            if ((OUT == 2)) {                                   // fold 1 / Ka_next into the affine: one FFMA yields the quotient
+            if (kE4m3Out) {                                   // fold 1 / Ka_next into the affine: one FFMA yields the quotient
                 m4[g].x *= p.rk; m4[g].y *= p.rk; m4[g].z *= p.rk; m4[g].w *= p.rk;
                 a4[g].x *= p.rk; a4[g].y *= p.rk; a4[g].z *= p.rk; a4[g].w *= p.rk;
             }
@@ -343,7 +372,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
 #pragma unroll
             for (int g = 0; g < VEC; ++g) {
                 const float mm[4] = {m4[g].x, m4[g].y, m4[g].z, m4[g].w}, aa[4] = {a4[g].x, a4[g].y, a4[g].z, a4[g].w};
-                if ((OUT == 2)) {
+                if (kE4m3Out) {
                     float y4[4];                                // (m4 / a4 carry 1 / Ka_next: see above)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) y4[e] = fmaf(acc[o][4 * g + e], mm[e], aa[e]);
@@ -369,7 +398,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const DwFastPar
                 for (int j = 0; j < CH; ++j) tq[j] = (c0 + j < p.C) ? tq[j] : 0;
             }
             uint32_t pk[VEC];
-            if ((OUT == 2)) {
+            if (kE4m3Out) {
 #pragma unroll
                 for (int g = 0; g < VEC; ++g) {
                     pk[g] = e4w[g];
@@ -483,9 +512,15 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
                     const char* ev = getenv("SLFP_DW_VEC");
                     vec = (ev && ev[0] == '4') ? 4 : 2;
                 }
-                const int om = q.out_e4m3 ? 2 : (q.out_signed ? 1 : 0);
+                static const bool no_hw = getenv("SLFP_DW_LUT_DECODE") != nullptr;
+                const int om = q.out_e4m3 ? ((d->fmt == SLFP_FMT_E4M3 && !no_hw) ? 3 : 2) : (q.out_signed ? 1 : 0);
                 const int k_out = (vec == 2 && d->stride_h == 1) ? 8 : 4;                     // kOut of the kernel
                 const size_t tot4 = (size_t)d->n * p.Ho * ((p.Wo + k_out - 1) / k_out) * (d->c_phys / (4 * vec));
+                if (tot4 >= (1ull << 31)) return set_error(SLFP_ERR_UNSUPPORTED, "dwconv3x3_strip: more than 2^31 work items");
+                q.total32 = (unsigned)tot4;
+                dw_magic((unsigned)(d->c_phys / (4 * vec)), q.cg_mg, q.cg_sh);
+                dw_magic((unsigned)((p.Wo + k_out - 1) / k_out), q.ws_mg, q.ws_sh);
+                dw_magic((unsigned)p.Ho, q.ho_mg, q.ho_sh);
                 // exactly one resident wave: the occupancy the kernel really gets with this layer's shared memory
 #define SLFP_STRIP(S_, V_, O_)                                                                                          \
                 if (d->stride_h == S_ && vec == V_ && om == O_) {                                                       \
@@ -504,6 +539,7 @@ int conv2d_fwd_grouped(const SlfpConvDesc* d, const uint8_t* x_codes, const void
                     return check_launch("dwconv3x3_strip_kernel");                                                      \
                 }
                 SLFP_STRIP(1, 2, 0) SLFP_STRIP(1, 2, 1) SLFP_STRIP(1, 2, 2) SLFP_STRIP(2, 2, 0) SLFP_STRIP(2, 2, 1) SLFP_STRIP(2, 2, 2)
+                SLFP_STRIP(1, 2, 3) SLFP_STRIP(2, 2, 3) SLFP_STRIP(1, 4, 3) SLFP_STRIP(2, 4, 3)
                 SLFP_STRIP(1, 4, 0) SLFP_STRIP(1, 4, 1) SLFP_STRIP(1, 4, 2) SLFP_STRIP(2, 4, 0) SLFP_STRIP(2, 4, 1) SLFP_STRIP(2, 4, 2)
 #undef SLFP_STRIP
                 return check_launch("dwconv3x3_strip_kernel");
