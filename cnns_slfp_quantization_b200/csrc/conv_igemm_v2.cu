@@ -107,6 +107,7 @@ struct Params {
     SlfpEpilogue epi;
     DivK next_div, next_div2;   // exact quantize-on-store (signed code formats)
     float rk1, rk2;             // 1 / next_k_div{,2} for the post-ReLU formats
+    int stg_groups;             // staged epilogue: 2 = two groups of 8 epilogue warps work on alternate tiles (see run2), else 1
     int epi_mode;               // 0 generic; 1 codes-only fast path; 2 fast path with float16 residual / float16 output / two consumers
     float sc1, sc2;             // rk / 16 (fast paths quantize clamp(q/16, 0, 1))
 };
@@ -821,7 +822,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(ptx::smem_u32(&bar_tfull[b]), 1);
-            ptx::mbar_init(ptx::smem_u32(&bar_tempty[b]), kEpiWarps);
+            ptx::mbar_init(ptx::smem_u32(&bar_tempty[b]), (STG && p.stg_groups == 2) ? kEpiWarps / 2 : kEpiWarps);
         }
         for (int b = 0; b < 8; ++b) ptx::mbar_init(ptx::smem_u32(&bar_res[b]), 1);
         ptx::fence_mbar_init();
@@ -1344,8 +1345,163 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                 }
                 if (SLFP_LEADER) ptx::bulk_wait0();
             };
+            // Two-group form (one code tensor, the common block tail): the 16 epilogue warps split into two groups of 8 that work
+            // on ALTERNATE tiles - group g owns accumulator buffer g, float16 staging tile g (residual in, float16 out, in place),
+            // code staging tile g and named barrier 1 + g.  A thread takes 64 columns of its row (four 16-column chunks).  With one
+            // group per tile the whole epilogue marched in lock step through wait -> TMEM load -> math -> barrier -> staging ->
+            // barrier -> TMA store, and the ncu source view showed the issue slots 44-57 % busy with every phase's latency
+            // exposed (profiles/r03_final.md); now one group's math overlaps the other's TMEM / TMA latencies.  The residual of
+            // the group's NEXT tile can only be requested once this tile's float16 store has read the shared buffer (in-place
+            // update), so its latency is covered by the other group's tile, and the tile after that is prefetched into L2.
+            auto run2 = [&](auto res_c, auto y16_c) {
+                constexpr bool h_res = decltype(res_c)::value, h_y16 = decltype(y16_c)::value;
+                const int grp = (warp - kEpiWarp0) >> 3, gw = (warp - kEpiWarp0) & 7;
+                const int chalf = gw >> 2;                                                // 64-column half of the tile
+                const bool glead = gw == 0;
+#define SLFP_GLEADER (glead && ptx::elect_one())
+                const int gtid = gw * 32 + lane;
+                const uint32_t iob = io0 + (uint32_t)grp * C::kIoBytes;                   // this group's float16 tile
+                const uint32_t cob = grp ? co2 : co1;                                     // this group's code tile
+                const uint32_t io_r = iob + (uint32_t)chalf * kHalfIo + row_off;
+                const uint32_t brs = bres + (uint32_t)grp * 8u;
+                const uint32_t par = s_mul + (uint32_t)grp * (uint32_t)(2 * BLOCK_N * 4); // [mul 128 | add 128] of the group's tile
+                const uint32_t par_t = par + (uint32_t)(chalf * 64) * 4u;
+                const int bar_id = 1 + grp;
+                auto advance = [&](int& m, int& n) { m += step_m; n += step_n; if (n >= n_tiles) { n -= n_tiles; ++m; } };
+                auto load_res = [&](int m, int n) {
+                    const int c0 = n * BLOCK_N, r0 = m * kBM;
+                    const bool two = c0 + 64 < Kout;
+                    ptx::mbar_arrive_expect_tx(brs, two ? 2u * kHalfIo : kHalfIo);
+                    ptx::tma_load_2d(iob, &omaps.res, brs, c0, r0);
+                    if (two) ptx::tma_load_2d(iob + kHalfIo, &omaps.res, brs, c0 + 64, r0);
+                };
+                auto load_affine = [&](int n) -> float4 {
+                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gtid < 64) {
+                        const int c = n * BLOCK_N + (gtid & 31) * 4;
+                        if (c < Kout) v4 = __ldg(reinterpret_cast<const float4*>((gtid < 32 ? p.epi.ch_mul : p.epi.ch_add) + c));
+                    }
+                    return v4;
+                };
+                auto store_affine = [&](const float4& v4) {
+                    if (gtid < 64) *reinterpret_cast<float4*>(s_par + grp * 2 * BLOCK_N + (gtid >> 5) * BLOCK_N + (gtid & 31) * 4) = v4;
+                };
+                int tm = (int)blockIdx.x / n_tiles, tn = (int)blockIdx.x % n_tiles;
+                if (grp) advance(tm, tn);                                                 // group 1 starts with the CTA's second tile
+                if (grp < my_tiles) {
+                    if (h_res && SLFP_GLEADER) load_res(tm, tn);
+                    store_affine(load_affine(tn));
+                    ptx::bar_sync(bar_id, 256);
+                }
+                for (int ti = grp; ti < my_tiles; ti += 2) {
+                    int nm = tm, nn = tn;
+                    advance(nm, nn); advance(nm, nn);                                     // this group's next tile
+                    const bool has_next = ti + 2 < my_tiles;
+                    const float4 aff_next = has_next ? load_affine(nn) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!h_res && h_y16) {
+                        // no residual load orders the previous float16 store against this tile's in-place writes: wait for it here
+                        if (SLFP_GLEADER) ptx::bulk_wait_read0();
+                        ptx::bar_sync(bar_id, 256);
+                    }
+                    const uint32_t tacc = tile_begin(ti, 0);
+                    const int n_half = tn * BLOCK_N + chalf * 64;
+                    int nvalid = (Kout - n_half) >> 4;                                   // 16-column chunks of this thread inside Kout
+                    nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
+                    const uint32_t tcol = tacc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 64);
+                    uint32_t cw[4][4];                                                   // packed codes per chunk
+                    if (h_res) ptx::mbar_wait(brs, ((uint32_t)ti >> 1) & 1u, 8u | ((uint32_t)ti << 16));
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {
+                        uint32_t acc[2][16];
+                        if (2 * pr < nvalid) ptx::tmem_ld16(tcol + (uint32_t)(32 * pr), acc[0]);
+                        if (2 * pr + 1 < nvalid) ptx::tmem_ld16(tcol + (uint32_t)(32 * pr + 16), acc[1]);
+                        ptx::tmem_ld_wait();
+                        if (pr == 1) tile_end(ti);                                       // the accumulator buffer is free again
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int ch = 2 * pr + c;
+                            if (ch >= nvalid) continue;                                  // warp-uniform
+                            const uint32_t ci = (uint32_t)(2 * ch);                      // 16-byte chunk inside the 128-byte row
+                            const uint32_t ioa = io_r + ((ci ^ sw) << 4), iob2 = io_r + (((ci + 1u) ^ sw) << 4);
+                            float v[16];
+                            uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+                            if (h_res) { ra = ptx::lds128_volatile(ioa); rb = ptx::lds128_volatile(iob2); }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 m4 = ptx::lds128_f4(par_t + (uint32_t)(ch * 16 + 4 * g) * 4u);
+                                const float4 a4 = ptx::lds128_f4(par_t + (uint32_t)(BLOCK_N + ch * 16 + 4 * g) * 4u);
+                                v[4 * g + 0] = fmaf(__uint_as_float(acc[c][4 * g + 0]), m4.x, a4.x);
+                                v[4 * g + 1] = fmaf(__uint_as_float(acc[c][4 * g + 1]), m4.y, a4.y);
+                                v[4 * g + 2] = fmaf(__uint_as_float(acc[c][4 * g + 2]), m4.z, a4.z);
+                                v[4 * g + 3] = fmaf(__uint_as_float(acc[c][4 * g + 3]), m4.w, a4.w);
+                            }
+                            if (h_res) {
+                                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                                    v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                                }
+                            }
+                            if (h_y16) {
+                                uint32_t hw[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) hw[i] = ptx::pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
+                                ptx::sts128(ioa, hw[0], hw[1], hw[2], hw[3]);
+                                ptx::sts128(iob2, hw[4], hw[5], hw[6], hw[7]);
+                            }
+                            int32_t t[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                t[i] = (int32_t)(__float_as_uint(__saturatef(v[i] * sc1)) >> enc_sh) - enc_base;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) cw[ch][i] = ptx::pack_sat_u8x4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+                        }
+                    }
+                    // the code staging tile must have been read by the previous tile's store before it is rewritten
+                    if (SLFP_GLEADER) ptx::bulk_wait_read0();
+                    ptx::bar_sync(bar_id, 256);
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        if (ch >= nvalid) continue;
+                        ptx::sts128(cob + row_off + (((uint32_t)(chalf * 4 + ch) ^ sw) << 4), cw[ch][0], cw[ch][1], cw[ch][2], cw[ch][3]);
+                    }
+                    if (has_next) store_affine(aff_next);                                // everybody is done reading this tile's vectors
+                    ptx::fence_proxy_async_smem();                                       // staging writes -> async proxy (TMA store)
+                    ptx::bar_sync(bar_id, 256);
+                    if (SLFP_GLEADER) {
+                        const int c0 = tn * BLOCK_N, r0 = tm * kBM;
+                        if (h_y16) {
+                            ptx::tma_store_2d(&omaps.y16, iob, c0, r0);
+                            if (c0 + 64 < Kout) ptx::tma_store_2d(&omaps.y16, iob + kHalfIo, c0 + 64, r0);
+                        }
+                        ptx::tma_store_2d(&omaps.c1, cob, c0, r0);
+                        ptx::bulk_commit();
+                        if (h_res && has_next) {
+                            if (h_y16) ptx::bulk_wait_read0();                           // in place: the store must have read the tile
+                            load_res(nm, nn);
+                            int pm = nm, pn = nn;
+                            advance(pm, pn); advance(pm, pn);
+                            if (ti + 4 < my_tiles) {                                     // the tile after that: towards L2
+                                ptx::tma_prefetch_2d(&omaps.res, pn * BLOCK_N, pm * kBM);
+                                if (pn * BLOCK_N + 64 < Kout) ptx::tma_prefetch_2d(&omaps.res, pn * BLOCK_N + 64, pm * kBM);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    tm = nm; tn = nn;
+                }
+                if (SLFP_GLEADER) ptx::bulk_wait0();
+#undef SLFP_GLEADER
+            };
             using T = std::true_type;
             using F = std::false_type;
+            if (p.stg_groups == 2) {                                                     // (host: one code tensor, no e4m3 / layerout)
+                if (has_res && has_y16) run2(T{}, T{});
+                else if (has_res) run2(T{}, F{});
+                else if (has_y16) run2(F{}, T{});
+                else run2(F{}, F{});
+            } else
             if (p.e4m3_out || p.epi.layerout || !has_c1) run(F{}, F{}, F{}, T{});        // generic: run-time flags
             else if (has_res && has_y16 && !has_c2) run(T{}, T{}, F{}, F{});              // block tail inside a stage
             else if (has_res && !has_y16 && has_c2) run(T{}, F{}, T{}, F{});              // last tail of a stage (two consumers)
@@ -1564,6 +1720,8 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         return set_error(SLFP_ERR_UNSUPPORTED, "conv2d_fwd: store_f16 needs the codes-only fast epilogue (folded affine, relu, k %% 16 == 0)");
     const bool stg = !hifi && !nodec && p.epi_mode == 2 && !(epi->layerout && epi->y_codes) && p.cblocks && d->k > 64 && p.num_kb <= stg_max_kb &&
                      (((uintptr_t)epi->residual) & 15u) == 0;
+    static const bool stg_one = getenv("SLFP_STG_ONE_GROUP") != nullptr;
+    p.stg_groups = (stg && !stg_one && epi->y_codes && !epi->y_codes2 && !e4m3_out && !epi->layerout) ? 2 : 1;
     int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
     if (epi->store_f16 && !a16 && bn > 128) bn = 128;       // the 256-column decode variant has no room for the output table
