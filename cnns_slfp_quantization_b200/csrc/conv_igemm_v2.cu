@@ -794,18 +794,25 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();     // would break the swizzle: fail loudly, never silently
 
     // ---- one-time setup ---------------------------------------------------------------------------
-    for (int i = tid; i < (NODEC ? 0 : 256 * 32); i += kThreads) {
-        const float f = decode_act_any((uint32_t)(i >> 5), p.act_fmt, c_pow2frac);
+    // Decode tables: every code is decoded ONCE (a lane per code) and broadcast into its lane copies by shuffles - filling
+    // all 8 192 words with their own decode_act_any (a divergent constant-table walk) was 1-2 us of every launch's prologue.
+    const int pw0 = tid >> 5;
+    if (!NODEC && pw0 < 8) {
+        const float f = decode_act_any((uint32_t)(pw0 * 32 + lane), p.act_fmt, c_pow2frac);
         const __half hi = __float2half_rn(f);
         uint32_t e = (uint32_t)__half_as_ushort(hi);
         if (HIFI) e |= (uint32_t)__half_as_ushort(__float2half_rn(f - __half2float(hi))) << 16;
-        s_lut[i] = e;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) s_lut[(pw0 * 32 + j) * 32 + lane] = __shfl_sync(0xffffffffu, e, j);
     }
-    if (C::kOutLutB != 0 && p.epi.store_f16) {
+    if (C::kOutLutB != 0 && p.epi.store_f16 && pw0 >= 8 && pw0 < 8 + (kOutLutEntries + 31) / 32) {
         // raw post-ReLU codes 0..257 (the byte path saturates at 255) -> float16 of the value the consumer's table would decode
-        for (int i = tid; i < kOutLutEntries * C::kOutLutCopies; i += kThreads) {
-            const uint32_t c = (uint32_t)(i / C::kOutLutCopies);
-            s_olut[i] = (uint32_t)__half_as_ushort(__float2half_rn(decode_act_any(c > 255u ? 255u : c, p.epi.next_fmt, c_pow2frac)));
+        const uint32_t c0 = (uint32_t)(pw0 - 8) * 32u, c = c0 + (uint32_t)lane;
+        const uint32_t e = (uint32_t)__half_as_ushort(__float2half_rn(decode_act_any(c > 255u ? 255u : c, p.epi.next_fmt, c_pow2frac)));
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+            if (c0 + (uint32_t)j < (uint32_t)kOutLutEntries && lane < C::kOutLutCopies) s_olut[(c0 + j) * C::kOutLutCopies + lane] = ej;
         }
     }
     if (warp == kWarpCode && lane == 0) {
