@@ -594,7 +594,7 @@ def main():
                                  if args.batch * args.size * args.size * 12 > (126 << 20) else
                                  "the whole working set fits the 126 MB L2 (small CIFAR batch): L2-resident by nature of the config",
                            "cuda_graph": not args.no_graph, "weights_requantized_every_step": not plan.static_weights,
-                           "arithmetic": "u8 SLFP<3,4> / SFP<3,3> codes between layers -> f16 tensor-core operands, f32 accumulate",
+                           "arithmetic": "u8 SLFP<3,4> / SFP<3,3> codes (float16 images of them on decode-bound edges) between layers -> f16 tensor-core operands, f32 accumulate",
                            "residual_stream": "f16" if args.config == "resnet50" else "none",
                            "host_cpus_rank0": (f"{len(bound)} CPUs local to the GPU" if bound else "unbound")},
                 "clocks": clocks,
