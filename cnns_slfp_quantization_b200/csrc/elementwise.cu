@@ -159,8 +159,17 @@ extern "C" int slfp_sgd_step(int n_tensors, float* const* host_params, float* co
     static thread_local SgdTensor* h_tab = nullptr;
     static thread_local int cap = 0;
     static thread_local cudaEvent_t ev = nullptr;
+    static thread_local int tab_dev = -1;                  // the device the table (and the event) belong to
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    if (dev != tab_dev && d_tab) {                         // the caller switched devices: the table must live on the current one
+        if (ev) { cudaEventSynchronize(ev); cudaEventDestroy(ev); ev = nullptr; }
+        cudaFree(d_tab); cudaFreeHost(h_tab);
+        d_tab = nullptr; h_tab = nullptr; cap = 0;
+    }
+    tab_dev = dev;
     if (n_tensors > cap) {
         if (d_tab) cudaFree(d_tab);
         if (h_tab) cudaFreeHost(h_tab);
