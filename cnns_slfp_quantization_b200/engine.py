@@ -87,6 +87,10 @@ class Plan:
         self.taps = []                # (module, input code tensor _T, op index) of every quantized layer (parity tests)
         self.conv_flops = []          # per conv launch, in launch order (bench.py's roofline pass)
         self.bytes_hbm = 0
+        # what the plan froze at compile time: weight storage and scales are checked by verify(), the folded
+        # bias / BatchNorm vectors can be recomputed in place by refresh()
+        self._guards = []             # (module, weight view, its data_ptr, Ka, Kw)
+        self._affines = []            # (module, bn, K, linear, mul32, add32) of single-branch layers
 
     # ---- buffers ----------------------------------------------------------------------------------------
     def _alloc(self, n, h, w, c, kind, kdiv=None, cp=None, fmt=None):
@@ -269,6 +273,8 @@ class Plan:
         mul32, add32 = torch.zeros(Kk, dtype=torch.float32, device=self.dev), torch.zeros(Kk, dtype=torch.float32, device=self.dev)
         mul32[:K], add32[:K] = mul.float(), add.float()
         self.keep += [mul32, add32]
+        self._guards.append((mod, wview, wview.data_ptr(), float(mod.Ka), float(mod.Kw)))
+        self._affines.append((mod, bn, K, linear, mul32, add32))
         epi.ch_mul, epi.ch_add = mul32.data_ptr(), add32.data_ptr()
         epi.post_a, epi.post_b = pa, pb
         if residual is not None:
@@ -431,6 +437,8 @@ class Plan:
             out["f16"] = self._alloc(x1.n, Ho, Wo, K, "f16")
             epi.y_f16 = out["f16"].buf.data_ptr()
         self.keep += [d1, d2, epi, wbuf, mul32, add32, r1, r2]
+        self._guards += [(mod1, mod1.weight, mod1.weight.data_ptr(), float(mod1.Ka), float(mod1.Kw)),
+                         (mod2, mod2.weight, mod2.weight.data_ptr(), float(mod2.Ka), float(mod2.Kw))]
         self.ops.append(self._call(self.lib.slfp_conv2d_fwd_dual, ctypes.byref(d1), x1.buf.data_ptr(), ctypes.byref(d2),
                                    x2.buf.data_ptr(), wbuf.data_ptr(), ctypes.byref(epi)))
         fl = 2.0 * x1.n * Ho * Wo * K * (C1 + C2)
@@ -482,6 +490,13 @@ class Plan:
         return out
 
     def maxpool(self, x, k, stride, pad):
+        # nn.MaxPool2d accepts ints or pairs; the kernel takes square windows
+        def one(v):
+            if isinstance(v, (tuple, list)):
+                assert len(v) == 2 and v[0] == v[1], "square max-pool windows / strides / paddings only"
+                return int(v[0])
+            return int(v)
+        k, stride, pad = one(k), one(stride if stride is not None else k), one(pad)
         assert x.kind == "codes" and x.fmt != nv.FMT_E4M3
         Ho = (x.h + 2 * pad - k) // stride + 1
         Wo = (x.w + 2 * pad - k) // stride + 1
@@ -501,6 +516,29 @@ class Plan:
     def torch_op(self, fn):
         """Escape hatch for plain (un-quantized) library layers of the caller net, e.g. MobileNetV1's nn.Linear."""
         self.ops.append(lambda st: fn())
+
+    # ---- consistency with the model the plan was compiled from ---------------------------------------------------
+    def verify(self):
+        """Raise if the model changed in a way the pre-bound calls cannot follow: a weight tensor that moved (model.to(),
+        .half(), a re-assigned Parameter) or a scale (Ka / Kw, e.g. after set_scales()) that differs from the compiled one -
+        both are baked into descriptors and epilogues, so the plan has to be compiled again."""
+        for mod, wview, ptr, ka, kw in self._guards:
+            # (the space-to-depth stem shim owns a derived weight tensor that is refreshed before every re-quantization)
+            if not hasattr(mod, "orig") and mod.weight.data_ptr() != ptr:
+                raise RuntimeError("engine.Plan: a weight tensor was re-allocated after the plan was compiled; compile the plan again")
+            if float(mod.Ka) != ka or float(mod.Kw) != kw:
+                raise RuntimeError("engine.Plan: Ka / Kw changed after the plan was compiled (set_scales?); compile the plan again")
+
+    @torch.no_grad()
+    def refresh(self):
+        """Recompute the folded per-channel vectors (bias, eval BatchNorm) IN PLACE from the modules' current parameters - the
+        buffers keep their addresses, so a captured CUDA graph sees the new values.  Weights are re-quantized on every run
+        anyway; scales need a new plan (verify())."""
+        self.verify()
+        for mod, bn, K, linear, mul32, add32 in self._affines:
+            mul, add = self._affine(mod, bn, K, linear)
+            mul32[:K].copy_(mul.float())
+            add32[:K].copy_(add.float())
 
     # ---- execution ----------------------------------------------------------------------------------------
     def prepare_weights(self):
@@ -534,6 +572,7 @@ class Plan:
 
     def capture(self):
         """Record the plan into a CUDA graph (after one eager warm-up so kernel attributes are set)."""
+        self.verify()
         self.prepare_weights()
         self.run()
         torch.cuda.synchronize()

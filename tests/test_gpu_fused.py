@@ -362,6 +362,23 @@ def test_plan_is_stable_and_deterministic_over_many_steps():
             assert torch.equal(plan.output, first), f"logits changed at replay {i}"
     torch.cuda.synchronize()
     assert torch.equal(plan.output, first)
+    # Plan.refresh(): BatchNorm / bias updates reach the captured graph through the in-place folded vectors ...
+    with torch.no_grad():
+        model.layer3[2].bn2.bias.add_(0.25)
+        model.bn1.weight.mul_(1.1)
+    plan.refresh()
+    plan()
+    torch.cuda.synchronize()
+    changed = plan.output.clone()
+    fresh = engine.compile_resnet50(model, 64, 224, device=dev)
+    fresh.input.copy_(plan.input)
+    fresh.run()
+    torch.cuda.synchronize()
+    assert not torch.equal(changed, first) and torch.equal(changed, fresh.output)
+    # ... while a changed scale (baked into descriptors and epilogues) is refused
+    model.layer2[0].conv1.Ka = model.layer2[0].conv1.Ka * 1.5
+    with pytest.raises(RuntimeError, match="Ka / Kw changed"):
+        plan.verify()
 
 
 def _decode_any(orc, codes, fmt):
