@@ -118,14 +118,21 @@ struct Params {
 // A16 (SLFP_FMT_F16Q input): the activation tensor already holds the float16 image of the quantized values, so the TMA-loaded
 // [128 pixels x 64 channels] tile (128-byte rows, 128-byte swizzle) IS the A operand of tcgen05.mma kind::f16 - the NODEC
 // structure with 2-byte elements.  Trades 1 B/element of HBM traffic for the decode work of the consumer.
-template <int BLOCK_N, bool STG = false, bool NODEC = false, bool A16 = false>
+// ACC1 (256-column decode tiles): ONE accumulator buffer of 256 TMEM columns + the decoded A ring in the remaining columns.
+// The double-buffered 256-column form needs all 512 columns for accumulators and stages A in shared memory (measured ~1 180
+// cycles per K block against ~640 with A in tensor memory); with a single buffer the epilogue of a tile no longer overlaps
+// the next tile's MMAs, but a tile of a K-heavy layer (>= 16 K blocks) spends ~10x longer in its main loop than in its
+// epilogue, and every decoded A tile now feeds 256 instead of 128 output columns: half the table look-ups per output.
+template <int BLOCK_N, bool STG = false, bool NODEC = false, bool A16 = false, bool ACC1 = false>
 struct Cfg {
     static_assert(!A16 || NODEC, "A16 is a no-decode variant");
+    static_assert(!ACC1 || (BLOCK_N == 256 && !NODEC && !STG), "single accumulator buffer: the 256-column decode variant");
+    static constexpr int kAccBufs = ACC1 ? 1 : 2;
     // BLOCK_N <= 128: the decoded A tile goes to TENSOR memory (tcgen05.st; the MMA reads A from TMEM), which takes
     // the A tile's write (16 KB) and the MMA's read of it (16 KB) per K block off the shared-memory pipe - the
     // measured bottleneck of the decode-heavy layers (profiles/r01_conv_v2.md).  BLOCK_N = 256 needs all 512 TMEM
     // columns for the double-buffered accumulator and keeps the A tile in shared memory.
-    static constexpr bool kATmem = !NODEC && BLOCK_N <= 128;
+    static constexpr bool kATmem = !NODEC && (BLOCK_N <= 128 || ACC1);
     static constexpr int kBBytes = (NODEC && !A16) ? BLOCK_N * kBK : BLOCK_N * kBK * 2;
     static constexpr int kCodeTile = A16 ? kABytes : kCodeBytes;      // bytes of one [128 x 64] activation tile in the code ring
     // Ring depths.  The code tiles and weight tiles arrive through TMA with ~1.5-2 us of latency under load; the
@@ -134,7 +141,7 @@ struct Cfg {
     static constexpr int kA16Stages = STG ? 4 : (BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8));      // 16 KB + BLOCK_N x 128 B per stage
     static constexpr int kStages = A16 ? kA16Stages
                                  : NODEC ? ((BLOCK_N >= 256 || STG) ? 6 : 8)
-                                         : ((BLOCK_N >= 256 || STG) ? 3 : 4);          // weight (and A) stages
+                                         : ((BLOCK_N >= 256 || STG) ? 3 : 4);          // weight (and A) stages (ACC1: 3 x 32 KB of weights)
     // The code ring depth must be a MULTIPLE of the number of decode groups (2 or 4), so that a code stage is always
     // consumed by the same group: TMA loads of different stages may land out of order, and a group that moved on to
     // K block j + CS while the load of K block j (same stage, other group) was still in flight would find the stage's
@@ -147,16 +154,16 @@ struct Cfg {
     // two float16 [128 x BLOCK_N] buffers (residual in / float16 out, in place) and two code tiles.
     static constexpr int kIoBytes = kBM * BLOCK_N * 2, kCoBytes = kBM * BLOCK_N;
     static constexpr int kStageBytes = STG ? 2 * kIoBytes + 2 * kCoBytes : 0;
-    static constexpr int kATmemCol = 2 * BLOCK_N;           // first TMEM column of the A ring (32 columns per stage)
-    static constexpr int kTmemCols = kATmem ? (2 * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
+    static constexpr int kATmemCol = kAccBufs * BLOCK_N;    // first TMEM column of the A ring (32 columns per stage)
+    static constexpr int kTmemCols = kATmem ? (kAccBufs * BLOCK_N + kStages * 32 <= 256 ? 256 : 512) : 2 * BLOCK_N;
     static constexpr int kParBytes = (STG ? 2 : 1) * 2 * BLOCK_N * 4;   // this tile's per-channel mul / add (fast epilogues; staged: double buffered)
     static constexpr int kLutB = NODEC ? 0 : kLutBytes;
     // SlfpEpilogue.store_f16: code -> float16 table of the NEXT layer's format for the epilogue.  Decode variants: one copy per
     // bank like the decode table (their decode warps already load the shared-memory pipe); no-decode variants: 16 copies
     // (lanes l and l + 16 share a bank, at worst a 2-way conflict) so that it also fits next to the 256-column rings.
     // The staged and the 256-column decode variants have no room for it.
-    static constexpr int kOutLutCopies = NODEC ? 16 : 32;
-    static constexpr int kOutLutB = (STG || (!NODEC && BLOCK_N >= 256)) ? 0 : kOutLutEntries * kOutLutCopies * 4;
+    static constexpr int kOutLutCopies = (NODEC || ACC1) ? 16 : 32;
+    static constexpr int kOutLutB = (STG || (!NODEC && BLOCK_N >= 256 && !ACC1)) ? 0 : kOutLutEntries * kOutLutCopies * 4;
     static constexpr int kSmemBytes = kStages * (((kATmem || NODEC) ? 0 : kABytes) + kBBytes) + kCodeStages * kCodeTile + kStageBytes + kLutB + kOutLutB + kParBytes + 1024;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -749,11 +756,12 @@ struct OutMaps {
 // HIFI (SLFP_CONV_SPLIT_OPERANDS): three passes over K into the same accumulator - pass 0: x_hi * w_hi, pass 1: x_hi * w_lo,
 // pass 2: x_lo * w_hi - with (hi, lo) the float16 pair of a value.  The decode table holds hi in the low and lo in the
 // high half of an entry, the decode warps pick the half per K block; the weight rows are [hi | lo].
-template <int BLOCK_N, int GRAN, int DW, bool STG, bool HIFI = false, bool NODEC = false, bool A16 = false>
+template <int BLOCK_N, int GRAN, int DW, bool STG, bool HIFI = false, bool NODEC = false, bool A16 = false, bool ACC1 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ OutMaps omaps, const Params p) {
-    using C = Cfg<BLOCK_N, STG, NODEC, A16>;
+    using C = Cfg<BLOCK_N, STG, NODEC, A16, ACC1>;
+    constexpr uint32_t kAccBufs = (uint32_t)C::kAccBufs;
     static_assert(!NODEC || (GRAN == 64 && !HIFI), "e4m3 / float16 operands: whole 64-channel K blocks");
     static_assert(!STG || (BLOCK_N == 128 && DW == 8 && GRAN == 64), "staged epilogue: 128-column tiles, 16 epilogue warps");
     static_assert(!HIFI || !STG, "the split-operand mode uses the generic epilogue");
@@ -983,8 +991,8 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         PROF_VARS;
         uint32_t stage = 0, phase = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
-            const uint32_t buf = (uint32_t)ti & 1u;
-            PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_tempty[buf]), (((uint32_t)ti >> 1) & 1u) ^ 1u, 3u | ((uint32_t)ti << 16)));
+            const uint32_t buf = (uint32_t)ti % kAccBufs;
+            PROF(a, ptx::mbar_wait(ptx::smem_u32(&bar_tempty[buf]), ((((uint32_t)ti / kAccBufs) & 1u)) ^ 1u, 3u | ((uint32_t)ti << 16)));
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
             for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -1139,7 +1147,7 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         PROF_VARS;
         // per tile: stage the per-channel vectors when the channel tile changes, then wait for the accumulator
         auto tile_begin = [&](int ti, int tile) -> uint32_t {
-            const uint32_t buf = (uint32_t)ti & 1u;
+            const uint32_t buf = (uint32_t)ti % kAccBufs;
             if (!STG && mode != 0) {
                 // the fast modes read the folded affine from shared memory (mode 1: pre-scaled by 1/(16 Ka_next))
                 const int n_tile0 = (int)((uint32_t)tile - mdiv((uint32_t)tile, p.k_ntiles) * (uint32_t)p.n_tiles) * BLOCK_N;
@@ -1155,14 +1163,14 @@ conv_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                     staged_n0 = n_tile0;
                 }
             }
-            PROF(a, ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti >> 1) & 1u, 64, 7u | ((uint32_t)ti << 16)));
+            PROF(a, ptx::mbar_wait_backoff(ptx::smem_u32(&bar_tfull[buf]), ((uint32_t)ti / kAccBufs) & 1u, 64, 7u | ((uint32_t)ti << 16)));
             ptx::tc_fence_after();
             return tmem_base + buf * BLOCK_N;
         };
         auto tile_end = [&](int ti) {
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_tempty[(uint32_t)ti & 1u]));
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_tempty[(uint32_t)ti % kAccBufs]));
         };
         if constexpr (STG) {
             // ---- staged epilogue (mode 2 only): every global access of the epilogue is a TMA transfer ----------
@@ -1574,10 +1582,10 @@ static PFN driver_fn(const char* name) {
     return nullptr;
 }
 
-template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false, bool NODEC = false, bool A16 = false>
+template <int BLOCK_N, int GRAN, int DW, bool STG = false, bool HIFI = false, bool NODEC = false, bool A16 = false, bool ACC1 = false>
 static int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tx2, const OutMaps& om, const Params& p, cudaStream_t st) {
-    using C = Cfg<BLOCK_N, STG, NODEC, A16>;
-    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI, NODEC, A16>;
+    using C = Cfg<BLOCK_N, STG, NODEC, A16, ACC1>;
+    auto kern = conv_igemm_v2_kernel<BLOCK_N, GRAN, DW, STG, HIFI, NODEC, A16, ACC1>;
     static DeviceOnce attr_once;
     bool& attr_done = attr_once.flag();
     if (!attr_done) {
@@ -1731,7 +1739,11 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
     p.stg_groups = (stg && !stg_one && epi->y_codes && !epi->y_codes2 && !e4m3_out && !epi->layerout) ? 2 : 1;
     int bn = stg ? 128 : (d->k > 128 ? 256 : (d->k > 64 ? 128 : 64));
     p.m_tiles = (int)((p.M + kBM - 1) / kBM);
-    if (epi->store_f16 && !a16 && bn > 128) bn = 128;       // the 256-column decode variant has no room for the output table
+    // single-accumulator 256-column decode variant (ACC1): whole 64-channel K blocks, K-heavy layers (the epilogue of a tile is
+    // not overlapped: >= 8 K blocks keep it below ~15 % of the tile)
+    static const bool no_acc1 = getenv("SLFP_NO_ACC1") != nullptr;
+    const bool acc1_ok = !no_acc1 && !hifi && !nodec && !a16 && !stg && p.cblocks && p.num_kb >= 8 && p.epi_mode != 0;
+    if (epi->store_f16 && !a16 && !acc1_ok && bn > 128) bn = 128;   // the double-buffered 256-column decode variant has no room for the output table
     if (a16 && !stg && bn > 64) {
         // same wave-quantisation model for the no-decode float16 form: a K block costs about its MMA time
         // (256 / 128 / 64 cycles) plus a fixed ~60
@@ -1756,7 +1768,7 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         int best_bn = bn;
         for (int cand = bn; cand >= 64 && !fixed; cand >>= 1) {
             const long tiles = (long)p.m_tiles * ((d->k + cand - 1) / cand);
-            const double t = (double)((tiles + sms - 1) / sms) * (cand == 256 ? 1180.0 : 640.0);
+            const double t = (double)((tiles + sms - 1) / sms) * (cand == 256 ? (acc1_ok ? 640.0 + 2200.0 / p.num_kb : 1180.0) : 640.0);
             if (t < best * 0.97) { best = t; best_bn = cand; }
         }
         bn = best_bn;
@@ -1879,6 +1891,7 @@ int conv2d_fwd_dense_v2_impl(const SlfpConvDesc* d, const uint8_t* x_codes, cons
         if (bn == 128) return launch<128, 64, 8, false, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
         return launch<256, 64, 8, false, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
     }
+    if (bn == 256 && acc1_ok) return launch<256, 64, 16, false, false, false, false, true>(tmap_x, tmap_w, tmap_x2, om, p, st);
 #define SLFP_V2_CASE(BN)                                                                                         \
     if (bn == BN) {                                                                                              \
         if (p.cblocks) return epi_heavy ? launch<BN, 64, 8>(tmap_x, tmap_w, tmap_x2, om, p, st) : launch<BN, 64, 16>(tmap_x, tmap_w, tmap_x2, om, p, st); \
