@@ -862,19 +862,45 @@ __global__ void __launch_bounds__(256) maxpool_ucodes_kernel(const uint8_t* __re
 // The ResNet stem pool (3x3, stride 2, padding 1) on post-ReLU codes: a thread produces TWO horizontally adjacent
 // outputs of 16 channels from one 3 x 5 window - 15 independent 16-byte loads in flight per thread (the generic
 // kernel's runtime-bounded tap loop kept one or two) and 7.5 instead of 9 loads per output.
-__device__ __forceinline__ uint4 vmax16(uint4 a, uint4 b) {
-    return make_uint4(__vmaxu4(a.x, b.x), __vmaxu4(a.y, b.y), __vmaxu4(a.z, b.z), __vmaxu4(a.w, b.w));
+// Byte-wise unsigned max has no native instruction (__vmaxu4 is a ~10-instruction emulation: the first version of this
+// kernel spent 560 of its 770 SASS instructions per thread there and was issue-bound at 3.5 TB/s, ncu
+// profiles/r04_final.md); 16-bit lanes do (max.u16x2 = VIMNMX.U16x2).  Each loaded word is split once into its even and
+// odd bytes (two PRMT), all maxima run on those halves, and one PRMT per word re-interleaves the result.
+struct U16x8 { uint32_t e[4], o[4]; };                                  // 16 bytes as 8 + 8 zero-extended 16-bit lanes
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ U16x8 split16(uint4 v) {
+    U16x8 r;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r.e[i] = __byte_perm(w[i], 0u, 0x4240); r.o[i] = __byte_perm(w[i], 0u, 0x4341); }
+    return r;
+}
+__device__ __forceinline__ U16x8 max16(const U16x8& a, const U16x8& b) {
+    U16x8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r.e[i] = max_u16x2(a.e[i], b.e[i]); r.o[i] = max_u16x2(a.o[i], b.o[i]); }
+    return r;
+}
+__device__ __forceinline__ uint4 join16(const U16x8& a) {
+    return make_uint4(__byte_perm(a.e[0], a.o[0], 0x6240), __byte_perm(a.e[1], a.o[1], 0x6240),
+                      __byte_perm(a.e[2], a.o[2], 0x6240), __byte_perm(a.e[3], a.o[3], 0x6240));
 }
 __global__ void __launch_bounds__(256) maxpool3x3s2_ucodes_kernel(const uint8_t* __restrict__ x, int N, int H, int W, int Cp,
                                                                   int Ho, int Wo, uint8_t* __restrict__ y) {
-    const int cq = Cp >> 4, Wp = (Wo + 1) >> 1;
-    const size_t total = (size_t)N * Ho * Wp * cq;
-    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
-        const int c0 = (int)(idx % cq) * 16;
-        size_t t = idx / cq;
-        const int wp = (int)(t % Wp); t /= Wp;
-        const int ho = (int)(t % Ho);
-        const int n = (int)(t / Ho);
+    // work items < 2^31 (host): 32-bit index arithmetic
+    const uint32_t cq = (uint32_t)Cp >> 4, Wp = ((uint32_t)Wo + 1u) >> 1;
+    const uint32_t total = (uint32_t)N * Ho * Wp * cq;
+    for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+        uint32_t t = idx / cq;
+        const int c0 = (int)(idx - t * cq) * 16;
+        const uint32_t t2 = t / Wp;
+        const int wp = (int)(t - t2 * Wp);
+        const int n = (int)(t2 / (uint32_t)Ho);
+        const int ho = (int)(t2 - (uint32_t)n * Ho);
         const int wo = 2 * wp, wi0 = 2 * wo - 1, hi0 = 2 * ho - 1;
         uint4 v[3][5];
 #pragma unroll
@@ -888,12 +914,12 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_ucodes_kernel(const uint8_t*
                 v[r][s] = (rok && wi >= 0 && wi < W) ? __ldg(reinterpret_cast<const uint4*>(row + (size_t)wi * Cp)) : make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        uint4 col[5];
+        U16x8 col[5];
 #pragma unroll
-        for (int s = 0; s < 5; ++s) col[s] = vmax16(vmax16(v[0][s], v[1][s]), v[2][s]);
+        for (int s = 0; s < 5; ++s) col[s] = max16(max16(split16(v[0][s]), split16(v[1][s])), split16(v[2][s]));
         uint8_t* dst = y + (((size_t)n * Ho + ho) * Wo + wo) * Cp + c0;
-        *reinterpret_cast<uint4*>(dst) = vmax16(vmax16(col[0], col[1]), col[2]);
-        if (wo + 1 < Wo) *reinterpret_cast<uint4*>(dst + Cp) = vmax16(vmax16(col[2], col[3]), col[4]);
+        *reinterpret_cast<uint4*>(dst) = join16(max16(max16(col[0], col[1]), col[2]));
+        if (wo + 1 < Wo) *reinterpret_cast<uint4*>(dst + Cp) = join16(max16(max16(col[2], col[3]), col[4]));
     }
 }
 
@@ -906,6 +932,47 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, i
     const T* xp = x + (size_t)n * hw * C + c;
     for (int i = 0; i < hw; ++i) acc += (float)xp[(size_t)i * C];
     y[(size_t)n * C + c] = acc / (float)hw;
+}
+
+// Global average pool of float16 images, 8 channels per thread (one 16-byte load per pixel, seven in flight), with the
+// classifier's activation quantizer fused: mean -> float32 [n, c] (optional) and -> encode(mean / K) code bytes.  The
+// sum runs over the pixels in order, like avgpool_kernel (same float32 bits); the codes are encode<FMT>(div_k(mean)),
+// i.e. what slfp_quantize_nhwc_f32 produces from the float32 means.  FMT < 0: no codes.
+template <int FMT>
+__global__ void __launch_bounds__(128) avgpool8_quantize_kernel(const __half* __restrict__ x, int hw, int C, float* __restrict__ y,
+                                                                DivK dk, uint8_t* __restrict__ codes) {
+    const int n = blockIdx.y;
+    const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    if (c0 >= C) return;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)n * hw * C + c0);
+    const size_t pitch = (size_t)(C >> 3);
+#pragma unroll 7
+    for (int i = 0; i < hw; ++i) {
+        const uint4 v = __ldg(xp + (size_t)i * pitch);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            acc[2 * j] += f.x;
+            acc[2 * j + 1] += f.y;
+        }
+    }
+    const float fhw = (float)hw;
+    uint32_t cw[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] = acc[j] / fhw;
+        if (FMT >= 0) cw[j >> 2] |= encode<FMT < 0 ? 0 : FMT>(div_k(acc[j], dk)) << (8 * (j & 3));
+    }
+    if (y) {
+        float4* yp = reinterpret_cast<float4*>(y + (size_t)n * C + c0);
+        yp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        yp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (FMT >= 0) *reinterpret_cast<uint2*>(codes + (size_t)n * C + c0) = make_uint2(cw[0], cw[1]);
 }
 
 }  // namespace slfp
@@ -922,8 +989,8 @@ extern "C" int slfp_maxpool_codes(const uint8_t* x, int n, int h, int w, int c_p
             return set_error(SLFP_ERR_BAD_ARG, "slfp_maxpool_codes: post-ReLU codes need c_phys %% 16 == 0 and 16-byte alignment");
         const size_t tot = (size_t)n * Ho * Wo * (c_phys / 16);
         if (tot == 0) return 0;
-        if (kh == 3 && kw_ == 3 && stride == 2 && pad == 1 && getenv("SLFP_POOL_GENERIC") == nullptr) {
-            const size_t tot2 = (size_t)n * Ho * ((Wo + 1) / 2) * (c_phys / 16);
+        const size_t tot2 = (size_t)n * Ho * ((Wo + 1) / 2) * (c_phys / 16);
+        if (kh == 3 && kw_ == 3 && stride == 2 && pad == 1 && tot2 < (1ull << 31) && getenv("SLFP_POOL_GENERIC") == nullptr) {
             const int g2 = (int)min((size_t)num_sms() * 8, ceil_div_sz(tot2, 256));
             maxpool3x3s2_ucodes_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c_phys, Ho, Wo, y);
             return check_launch("maxpool3x3s2_ucodes_kernel");
@@ -946,4 +1013,20 @@ extern "C" int slfp_avgpool_nhwc(const void* x, int is_f16, int n, int hw, int c
     if (is_f16) avgpool_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, hw, c, y);
     else avgpool_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, hw, c, y);
     return check_launch("avgpool_kernel");
+}
+
+extern "C" int slfp_avgpool_quantize_nhwc_f16(const void* x, int n, int hw, int c, float* y, float k_div, int fmt, uint8_t* codes,
+                                              slfp_stream_t stream) {
+    if (!x || (!y && !codes)) return set_error(SLFP_ERR_BAD_ARG, "slfp_avgpool_quantize_nhwc_f16: null pointer");
+    if (n <= 0 || c <= 0) return 0;
+    if (hw <= 0 || (c & 7) || (((uintptr_t)x | (uintptr_t)y) & 15u) || (((uintptr_t)codes) & 7u))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_avgpool_quantize_nhwc_f16: needs c %% 8 == 0 and 16-byte aligned tensors");
+    dim3 grid((c / 8 + 127) / 128, n);
+    const DivK dk = make_divk(codes ? k_div : 1.0f);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!codes) avgpool8_quantize_kernel<-1><<<grid, 128, 0, st>>>((const __half*)x, hw, c, y, dk, nullptr);
+    else if (fmt == SLFP_FMT_SFP33) avgpool8_quantize_kernel<SLFP_FMT_SFP33><<<grid, 128, 0, st>>>((const __half*)x, hw, c, y, dk, codes);
+    else if (fmt == SLFP_FMT_SLFP34_ACT) avgpool8_quantize_kernel<SLFP_FMT_SLFP34_ACT><<<grid, 128, 0, st>>>((const __half*)x, hw, c, y, dk, codes);
+    else return set_error(SLFP_ERR_BAD_ARG, "slfp_avgpool_quantize_nhwc_f16: format %d (SFP<3,3> / SLFP<3,4> activation codes only)", fmt);
+    return check_launch("avgpool8_quantize_kernel");
 }

@@ -995,6 +995,206 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const __grid_constant_
     }
 }
 
+// ---- weight preparation, row-staged form ------------------------------------------------------------------------
+// The gather form above spends ~105 SASS instructions per weight (ncu, profiles/r04_final.md: 845 per 8-element thread
+// of which 214 IMAD / 119 ISETP / 74 LDC are index arithmetic, strided 64-bit source addresses and kernel-parameter
+// reads) and was issue-bound at 85 % of the issue slots, 0.16 of the HBM peak.  For the common case - a contiguous OIHW
+// tensor, whole float4 groups per filter row - a CTA instead takes a CONTIGUOUS run of source floats (several whole
+// filter rows, or a channel range of one long row), reads it with coalesced 16-byte loads in source order, encodes each
+// element once, scatters value / code into a shared-memory image of the KRSC destination rows ([tap][channel]) and
+// writes that image out with 16-byte stores.  The (channel, tap) split of the source index is one magic division per
+// float4 plus carries; the parameters are read once per CTA.
+constexpr int kWFastCap = 4608;                   // source elements per CTA (512 channels x 9 taps = one ResNet-50 / VGG row)
+constexpr int kWFastMaxTaps = 32;                 // staging rows
+struct WFastJob {
+    const float* w;                               // [K][C][R*S] contiguous, 16-byte aligned
+    __half* w_f16;                                // float16 operand or (e4m3 != 0) e4m3 bytes; may be null
+    uint8_t* w_codes;                             // may be null
+    const float* row_scale;
+    size_t out_pitch, out_off;
+    uint32_t K, C, Cp, RS, pitch;                 // pitch: elements per destination row that must be written (>= RS * Cp)
+    uint32_t nrows, cc, n_cchunks;                // rows per CTA (C == Cp, whole rows) | channels per CTA of a split row
+    uint32_t mg_rs, sh_rs, mg_cch, sh_cch, mg_c, sh_c;
+    DivK dk;
+    int e4m3;
+};
+constexpr int kWFastMax = 200;
+struct WFastBatch {
+    int n;
+    unsigned blk_end[kWFastMax];
+    WFastJob j[kWFastMax];
+};
+static_assert(sizeof(WFastBatch) <= 32000, "kernel parameter space");
+
+// SLFP<3,4> weight encoder as ONE table look-up (wprep_rows_kernel, quotients known to be finite and non-zero): entry
+// (|q| bits >> 18) - clamped to [below 0.0625 | the 8 x 32 buckets of [0.0625, 16) | 16 and above] - holds the bucket's
+// only decision threshold on the full bit pattern (a rounding threshold 2^((2j-1)/32) of sfp_quant.py:40, or the
+// saturation bound 15.32165 of :46 - never both: the bound lies in bucket 29 of [8, 16), the nearest thresholds in 27
+// and 30), the unsigned codes below / at-and-above it and their float16 images.  11 instead of 26 instructions per
+// weight; bit-exact with encode_wgt_bucket() on that domain (tests/test_gpu_fused.py sweeps every mantissa).
+constexpr int kWgtLutEntries = 258;
+__device__ __forceinline__ uint4 wgt_lut_entry(uint32_t i, const uint32_t* __restrict__ s_tab) {
+    uint32_t thr = 0xffffffffu, lo, hi;
+    if (i == 0u) lo = hi = kCodeTiny;
+    else if (i == kWgtLutEntries - 1) lo = hi = kCodeSat;
+    else {
+        const uint32_t e = (i - 1u) >> 5, m5 = (i - 1u) & 31u;             // |q| in 2^(e-4) * [1 + m5/32, 1 + (m5+1)/32)
+        if (e == 0u) lo = hi = 16u;                                        // [0.0625, 0.125) -> 0.125
+        else {
+            uint32_t cnt, t;
+            wgt_bucket_entry(m5, cnt, t);
+            lo = (e << 4) + cnt; hi = lo + 1u;                             // L == 16 carries into the exponent
+            if (t != 0xffffffffu) thr = ((123u + e) << 23) | (t & 0x007fffffu);
+            const uint32_t b0 = ((123u + e) << 23) | (m5 << 18);
+            if (b0 > kBitsSat8) lo = hi = kCodeSat;                        // whole bucket above 15.32165
+            else if (b0 + (1u << 18) > kBitsSat8) { thr = kBitsSat8 + 1u; hi = kCodeSat; }
+        }
+    }
+    const uint32_t hl = (uint32_t)__half_as_ushort(__float2half_rn(decode<false>(lo, s_tab)));
+    const uint32_t hh = (uint32_t)__half_as_ushort(__float2half_rn(decode<false>(hi, s_tab)));
+    return make_uint4(thr, lo, hi, hl | (hh << 16));
+}
+// OUT: 0 float16 operand, 1 code bytes, 2 e4m3 bytes (through w_f16), 3 float16 operand and code bytes
+template <int FMT, int OUT>
+__global__ void __launch_bounds__(256) wprep_rows_kernel(const __grid_constant__ WFastBatch b) {
+    constexpr bool kH = OUT == 0 || OUT == 3, kB = OUT != 0;          // float16 image / byte image
+    __shared__ uint32_t s_tab[16];
+    __shared__ WPrepTables tb;
+    // staging images of the destination rows: [tap][channel slot], row pitch = slots + 8 | 16 (16-byte rows, banks skewed per tap)
+    __shared__ __align__(16) __half s_h[kH ? kWFastCap + kWFastMaxTaps * 8 : 8];
+    __shared__ __align__(16) uint8_t s_c[kB ? kWFastCap + kWFastMaxTaps * 16 : 16];
+    constexpr bool kLut = FMT == SLFP_FMT_SLFP34_WGT;
+    __shared__ uint4 s_lut[kLut ? kWgtLutEntries : 1];
+    // persistent CTAs: the tables are built once, then the CTA walks over pieces blockIdx.x, + gridDim.x, ...
+    if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
+    __syncthreads();
+    wprep_tables_init<FMT>(tb, s_tab);
+    if (kLut) for (uint32_t i = threadIdx.x; i < kWgtLutEntries; i += 256) s_lut[i] = wgt_lut_entry(i, s_tab);
+    const uint32_t n_pieces = b.blk_end[b.n - 1];
+#pragma unroll 1
+    for (uint32_t piece = blockIdx.x; piece < n_pieces; piece += gridDim.x) {
+    int lo = 0, hi = b.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (b.blk_end[mid] > piece) hi = mid; else lo = mid + 1;
+    }
+    const WFastJob& a = b.j[lo];
+    const uint32_t q = piece - (lo ? b.blk_end[lo - 1] : 0u);
+    const uint32_t C = a.C, Cp = a.Cp, RS = a.RS;
+    // this CTA's piece: rows [k0, k0 + nr) x channels [c_lo, c_lo + cn); slots = channel positions it owns per tap
+    uint32_t k0, nr, c_lo, cn, slots;
+    if (a.n_cchunks > 1) {
+        k0 = div_magic(q, a.n_cchunks, a.mg_cch, a.sh_cch);
+        const uint32_t ci = q - k0 * a.n_cchunks;
+        nr = 1; c_lo = ci * a.cc;
+        cn = c_lo < C ? min(a.cc, C - c_lo) : 0u;
+        slots = (ci + 1 == a.n_cchunks) ? Cp - c_lo : a.cc;               // the last piece also owns the padding channels
+    } else {
+        k0 = q * a.nrows; nr = min(a.nrows, a.K - k0); c_lo = 0; cn = C;
+        slots = nr > 1 ? nr * C : Cp;                                     // nrows > 1 only when C == Cp
+    }
+    // the first 16-byte load of the piece is issued before the staging set-up; the loop below keeps one load ahead
+    const float* src = a.w + ((size_t)k0 * C + c_lo) * RS;
+    const uint32_t n_src = nr * cn * RS;                                  // multiple of 4, <= kWFastCap (host)
+    uint32_t u0 = threadIdx.x * 4;
+    float4 cur = u0 < n_src ? ldg_stream(reinterpret_cast<const float4*>(src + u0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t ph = slots + 8, pc = slots + 16;
+    if (nr == 1 && slots != cn) {                                         // padding channels read as 0 / code 0
+        if (kH) for (uint32_t i = threadIdx.x; i < RS * ph / 2; i += 256) reinterpret_cast<uint32_t*>(s_h)[i] = 0u;
+        if (kB) for (uint32_t i = threadIdx.x; i < RS * pc / 4; i += 256) reinterpret_cast<uint32_t*>(s_c)[i] = 0u;
+    }
+    __syncthreads();
+    const DivK dk = a.dk;
+    const float* rsc = a.row_scale;
+    const uint32_t mg_rs = a.mg_rs, sh_rs = a.sh_rs;
+#pragma unroll 1
+    for (; u0 < n_src; u0 += 256 * 4) {
+        const uint32_t un = u0 + 256 * 4;
+        const float4 nxt = un < n_src ? ldg_stream(reinterpret_cast<const float4*>(src + un)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float x[4] = {cur.x, cur.y, cur.z, cur.w};
+        cur = nxt;
+        uint32_t ch = div_magic(u0, RS, mg_rs, sh_rs);                    // channel slot (row_local * C + c when nr > 1)
+        uint32_t rs = u0 - ch * RS;
+        uint32_t at_h = rs * ph + ch, at_c = rs * pc + ch;                // staging positions, advanced with (rs, ch)
+        // magnitudes as integers: NaN and Inf order above every finite value
+        const uint32_t a0 = f2u(x[0]) & 0x7fffffffu, a1 = f2u(x[1]) & 0x7fffffffu, a2 = f2u(x[2]) & 0x7fffffffu, a3 = f2u(x[3]) & 0x7fffffffu;
+        const uint32_t amax = max(max(a0, a1), max(a2, a3)), amin = min(min(a0, a1), min(a2, a3));
+        const bool fast = dk.fast && amin >= 0x21800000u && amax < 0x5d800000u;       // 2^-60 <= |x| < 2^60: reciprocal sequence
+        if (kLut && fast && rsc == nullptr) {
+            // the common group: finite non-zero quotients, one table look-up per weight
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float q0 = x[e] * dk.rk;
+                const float r = fmaf(-q0, dk.k, x[e]);
+                const uint32_t qb = f2u(fmaf(r, dk.rk, q0)), qa = qb & 0x7fffffffu;   // == IEEE x / kw
+                int t = (int)(qa >> 18) - (123 * 32 - 1);
+                t = min(max(t, 0), kWgtLutEntries - 1);
+                const uint4 en = s_lut[t];
+                const bool up = qa >= en.x;
+                if (kH) s_h[at_h] = __ushort_as_half((unsigned short)(__byte_perm(en.w, 0u, up ? 0x4432u : 0x4410u) | ((qb >> 16) & 0x8000u)));
+                if (kB) s_c[at_c] = (uint8_t)((up ? en.z : en.y) | ((qb >> 24) & 0x80u));
+                at_h += ph; at_c += pc;
+                if (++rs == RS) { rs = 0; ++ch; at_h = ch; at_c = ch; }
+            }
+        } else {
+            float rsk = 1.0f;
+            if (kH && rsc) rsk = __ldg(rsc + k0 + (nr > 1 ? div_magic(ch, C, a.mg_c, a.sh_c) : 0u));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float qv;
+                if (fast) {
+                    const float q0 = x[e] * dk.rk;
+                    const float r = fmaf(-q0, dk.k, x[e]);
+                    qv = fmaf(r, dk.rk, q0);
+                } else {
+                    qv = div_rn(x[e], dk.k);
+                }
+                const uint32_t code = FMT == SLFP_FMT_SLFP34_WGT ? encode_wgt_bucket(qv, tb.bucket) : encode<FMT>(qv);
+                if (kH) {
+                    float val = tb.dec[code];
+                    if (rsc) val *= rsk;
+                    s_h[at_h] = __float2half_rn(val);
+                }
+                if (kB) s_c[at_c] = (uint8_t)(OUT == 2 ? sfp33_code_to_e4m3(code) : code);
+                at_h += ph; at_c += pc;
+                if (++rs == RS) {
+                    rs = 0; ++ch; at_h = ch; at_c = ch;
+                    if (kH && rsc && nr > 1) rsk = __ldg(rsc + k0 + div_magic(ch, C, a.mg_c, a.sh_c));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // copy-out: 8-element vectors; vector v -> (tap, slot8) -> (row_local, channel) -> destination element
+    const uint32_t v_per_tap = slots >> 3;                                // slots % 8 == 0 (host)
+    const uint32_t n_vec = RS * v_per_tap;
+    const uint32_t c8 = C >> 3;                                           // vectors per row inside a tap (nr > 1)
+    uint8_t* const out_b = OUT == 2 ? reinterpret_cast<uint8_t*>(a.w_f16) : a.w_codes;
+    // (v < 1 024 and divisors < 1 024: floor((v + 0.5) * (1 / d)) in float32 is the exact quotient)
+    const float inv_vpt = 1.0f / (float)v_per_tap, inv_c8 = 1.0f / (float)(c8 ? c8 : 1u);
+    for (uint32_t v = threadIdx.x; v < n_vec; v += 256) {
+        const uint32_t tap = __float2uint_rz(((float)v + 0.5f) * inv_vpt), sv = v - tap * v_per_tap;
+        uint32_t rl = 0, cv = sv;
+        if (nr > 1) { rl = __float2uint_rz(((float)sv + 0.5f) * inv_c8); cv = sv - rl * c8; }
+        const size_t o = (size_t)(k0 + rl) * a.out_pitch + a.out_off + (size_t)tap * Cp + c_lo + cv * 8;
+        if (kH) *reinterpret_cast<uint4*>(a.w_f16 + o) = *reinterpret_cast<const uint4*>(s_h + tap * ph + sv * 8);
+        if (kB) *reinterpret_cast<uint2*>(out_b + o) = *reinterpret_cast<const uint2*>(s_c + tap * pc + sv * 8);
+    }
+    // K-padding taps [RS * Cp, pitch) of the rows this CTA starts
+    const uint32_t tail0 = RS * Cp;
+    if (c_lo == 0 && a.pitch > tail0) {
+        const uint32_t tv = (a.pitch - tail0) >> 3;
+        for (uint32_t v = threadIdx.x; v < nr * tv; v += 256) {
+            const uint32_t rl = v / tv, t8 = v - rl * tv;
+            const size_t o = (size_t)(k0 + rl) * a.out_pitch + a.out_off + tail0 + t8 * 8;
+            if (kH) *reinterpret_cast<uint4*>(a.w_f16 + o) = make_uint4(0u, 0u, 0u, 0u);
+            if (kB) *reinterpret_cast<uint2*>(out_b + o) = make_uint2(0u, 0u);
+        }
+    }
+    __syncthreads();                                                      // the staging images are reused by the next piece
+    }
+}
+
 }  // namespace slfp
 
 namespace slfp {
@@ -1343,6 +1543,63 @@ static int fill_wprep(const SlfpConvDesc* d, const float* w, long long so, long 
     return 0;
 }
 
+// Row-staged fast path (wprep_rows_kernel): fills f and returns the number of CTAs, or 0 when the job needs the gather form.
+static unsigned fill_wfast(const WPrepArgs& a, int wfmt, WFastJob& f) {
+    if (getenv("SLFP_WPREP_GATHER") != nullptr || wfmt < 0 || a.w_fakeq || a.lo_off || (a.e4m3 && a.w_codes) || (!a.w_f16 && !a.w_codes)) return 0;
+    const long long RS = (long long)a.R * a.S, C = a.C;
+    if (RS < 1 || RS > kWFastMaxTaps || C < 1 || a.K < 1) return 0;
+    const bool contiguous = (RS == 1 || ((a.S == 1 || a.ss == 1) && (a.R == 1 || a.sr == a.S))) && (C == 1 || a.sc == RS) && a.so == C * RS;
+    if (!contiguous || (C * RS) % 4 || (a.Cp & 7) || (a.pitch & 7) || (a.out_pitch & 7) || (a.out_off & 7) || a.pitch < (size_t)RS * a.Cp) return 0;
+    if ((((uintptr_t)a.w) & 15u) || (((uintptr_t)a.w_f16) & 15u) || (((uintptr_t)a.w_codes) & 7u)) return 0;
+    f.w = a.w; f.w_f16 = a.w_f16; f.w_codes = a.w_codes; f.row_scale = a.row_scale;
+    f.out_pitch = a.out_pitch; f.out_off = a.out_off;
+    f.K = (uint32_t)a.K; f.C = (uint32_t)C; f.Cp = (uint32_t)a.Cp; f.RS = (uint32_t)RS; f.pitch = (uint32_t)a.pitch;
+    f.dk = a.dk; f.e4m3 = a.e4m3;
+    unsigned blocks;
+    if (RS * a.Cp <= kWFastCap) {
+        f.n_cchunks = 1; f.cc = f.Cp;
+        f.nrows = (a.C == a.Cp) ? (uint32_t)(kWFastCap / (C * RS)) : 1u;
+        if (f.nrows < 1) f.nrows = 1;
+        blocks = (f.K + f.nrows - 1) / f.nrows;
+    } else {
+        f.cc = (uint32_t)(kWFastCap / RS) & ~7u;
+        if (f.cc < 8) return 0;
+        f.n_cchunks = (f.Cp + f.cc - 1) / f.cc;
+        f.nrows = 1;
+        blocks = f.K * f.n_cchunks;
+    }
+    magic_u32(f.RS, f.mg_rs, f.sh_rs);
+    magic_u32(f.n_cchunks, f.mg_cch, f.sh_cch);
+    magic_u32(f.C, f.mg_c, f.sh_c);
+    return blocks;
+}
+
+template <int FMT>
+static void launch_wfast_fmt(const WFastBatch& b, unsigned blocks, int out, cudaStream_t st) {
+    const unsigned grid = min(blocks, (unsigned)num_sms() * 6u);          // persistent CTAs (6 resident per SM at 40 registers)
+    switch (out) {
+        case 0: wprep_rows_kernel<FMT, 0><<<grid, 256, 0, st>>>(b); break;
+        case 1: wprep_rows_kernel<FMT, 1><<<grid, 256, 0, st>>>(b); break;
+        case 2: wprep_rows_kernel<FMT, 2><<<grid, 256, 0, st>>>(b); break;
+        default: wprep_rows_kernel<FMT, 3><<<grid, 256, 0, st>>>(b); break;
+    }
+}
+static int launch_wfast(const WFastBatch& b, unsigned blocks, int wfmt, int out, cudaStream_t st) {
+    switch (wfmt) {
+        case SLFP_FMT_SFP33: launch_wfast_fmt<SLFP_FMT_SFP33>(b, blocks, out, st); break;
+        case SLFP_FMT_SLFP34_WGT: launch_wfast_fmt<SLFP_FMT_SLFP34_WGT>(b, blocks, out, st); break;
+        case SLFP_FMT_SLFP34_ACT: launch_wfast_fmt<SLFP_FMT_SLFP34_ACT>(b, blocks, out, st); break;
+        default: return set_error(SLFP_ERR_BAD_ARG, "slfp_prepare_weights: bad weight format %d", wfmt);
+    }
+    return check_launch("wprep_rows_kernel");
+}
+// output kind of a row-staged job (template argument OUT of wprep_rows_kernel)
+static int wfast_out_kind(const WPrepArgs& a) {
+    if (a.w_f16 && a.e4m3) return 2;
+    if (a.w_f16) return a.w_codes ? 3 : 0;
+    return 1;
+}
+
 extern "C" int slfp_prepare_weights(const SlfpConvDesc* d, const float* w, long long so, long long sc,
                                     long long sr, long long ss, float kw, int wfmt, void* w_f16,
                                     uint8_t* w_codes, float* w_fakeq, slfp_stream_t stream) {
@@ -1353,6 +1610,13 @@ extern "C" int slfp_prepare_weights(const SlfpConvDesc* d, const float* w, long 
     if (total >= (1ull << 32)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights: tensor with 2^32 or more elements");
     int grid = (int)min((size_t)num_sms() * 8, ceil_div_sz(total, 256));
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        static thread_local WFastBatch fb;
+        if (unsigned blocks = fill_wfast(a, wfmt, fb.j[0])) {
+            fb.n = 1; fb.blk_end[0] = blocks;
+            return launch_wfast(fb, blocks, wfmt, wfast_out_kind(a), st);
+        }
+    }
     switch (wfmt) {
         case SLFP_FMT_SFP33: wprep_kernel<SLFP_FMT_SFP33><<<grid, 256, 0, st>>>(a); break;
         case SLFP_FMT_SLFP34_WGT: wprep_kernel<SLFP_FMT_SLFP34_WGT><<<grid, 256, 0, st>>>(a); break;
@@ -1369,8 +1633,10 @@ extern "C" int slfp_prepare_weights_jobs(int n, const SlfpWeightJob* host_jobs, 
     cudaStream_t st = (cudaStream_t)stream;
     for (int t0 = 0; t0 < n; t0 += kWBatchMax) {
         static thread_local WPrepBatch b;
+        static thread_local WFastBatch fb[4];                                 // one batch per output kind
         b.n = 0;
-        unsigned blocks = 0;
+        unsigned blocks = 0, fblocks[4] = {0u, 0u, 0u, 0u};
+        for (int o = 0; o < 4; ++o) fb[o].n = 0;
         for (int t = t0; t < n && t < t0 + kWBatchMax; ++t) {
             const SlfpWeightJob& jb = host_jobs[t];
             WPrepArgs& a = b.a[b.n];
@@ -1395,8 +1661,20 @@ extern "C" int slfp_prepare_weights_jobs(int n, const SlfpWeightJob* host_jobs, 
             const size_t total = (size_t)a.K * a.pitch;
             if (total == 0) continue;
             if (total >= (1ull << 32)) return set_error(SLFP_ERR_UNSUPPORTED, "slfp_prepare_weights_jobs: tensor with 2^32 or more elements");
+            WFastBatch& f = fb[wfast_out_kind(a)];
+            if (unsigned fbk = fill_wfast(a, wfmt, f.j[f.n])) {                // row-staged form; the slot in b is reused
+                unsigned& fbl = fblocks[wfast_out_kind(a)];
+                fbl += fbk;
+                f.blk_end[f.n++] = fbl;
+                continue;
+            }
             blocks += (unsigned)ceil_div_sz(total, kWBatchChunk);
             b.blk_end[b.n++] = blocks;
+        }
+        for (int o = 0; o < 4; ++o) {
+            if (fb[o].n == 0) continue;
+            int rc = launch_wfast(fb[o], fblocks[o], wfmt, o, st);
+            if (rc) return rc;
         }
         if (b.n == 0) continue;
         switch (wfmt) {

@@ -319,7 +319,10 @@ class Plan:
         # layers, whose 8 epilogue warps are their critical path) against a flat ~12-18 us the 3x3 consumer saves by not
         # decoding: worth it below ~16 M elements (ResNet-50 stages 3-4 at batch 256)
         # (a producer that itself reads float16 images has no decode warps competing with its epilogue's table look-ups: 64 M)
-        q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS", (64 << 20) if x.kind == "q16" else (16 << 20)))
+        if R * S == 1 and x.kind != "q16":
+            q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS_1X1", 4 << 20))
+        else:
+            q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS", (64 << 20) if x.kind == "q16" else (16 << 20)))
         as_q16 = (q16 and self.f16q and dense and (x.cp % 16 == 0 or x.im2col) and len(kds) == 1 and relu and bn is not None and K % 64 == 0
                   and Kk == K and ofmt == nv.relu_fmt(self.afmt) and not f16 and not f32 and residual is None and not layerout
                   and x.n * Ho * Wo * K <= q16_max)
@@ -513,6 +516,17 @@ class Plan:
                                    x.h * x.w, x.c, out.data_ptr()))
         return out
 
+    def avgpool_quantize(self, x, kdiv):
+        """Global average pool + the classifier's activation quantizer: [n, h, w, c] float16 -> codes [n, 1, 1, c].  One
+        launch (slfp_avgpool_quantize_nhwc_f16) when the formats allow it, else avgpool() + quantize_flat() - same bits."""
+        if (x.kind == "f16" and x.c % 16 == 0 and self.afmt in (nv.FMT_SFP33, nv.FMT_SLFP34_ACT)
+                and not os.environ.get("SLFP_NO_FUSED_AVGPOOL")):
+            t = self._alloc(x.n, 1, 1, x.c, "codes", kdiv)
+            self.ops.append(self._call(self.lib.slfp_avgpool_quantize_nhwc_f16, x.buf.data_ptr(), x.n, x.h * x.w, x.c, None, kdiv,
+                                       self.afmt, t.buf.data_ptr()))
+            return t
+        return self.quantize_flat(self.avgpool(x), x.c, kdiv)
+
     def torch_op(self, fn):
         """Escape hatch for plain (un-quantized) library layers of the caller net, e.g. MobileNetV1's nn.Linear."""
         self.ops.append(lambda st: fn())
@@ -663,8 +677,7 @@ def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", stat
                     codes=consumers(nxt) if nxt is not None else [], f16=need_val and res_f16, f32=need_val and not res_f16)
         cur_codes = o3["codes"]
         cur_res = o3["f16"] if res_f16 else o3["f32"]
-    feat = P.avgpool(cur_res)
-    fcq = P.quantize_flat(feat, model.fc.in_features, _k32(model.fc.Ka))
+    fcq = P.avgpool_quantize(cur_res, _k32(model.fc.Ka))
     out = P.conv(fcq, model.fc, f32=True, linear=True)
     P.output = out["f32"].buf.view(batch, -1)
     return P
@@ -740,11 +753,11 @@ def compile_mobilenetv1(model, batch, size, device="cuda", static_weights=False)
             cur = P.conv(cur, conv, bn=bn, relu=True, codes=[nk])["codes"][nk]
     if isinstance(pool, nn.AvgPool2d):
         assert cur.h == pool.kernel_size and cur.w == pool.kernel_size, "AvgPool2d(7) expects a 7x7 map (224x224 input)"
-    feat = P.avgpool(cur)
     if quant_fc:
-        fcq = P.quantize_flat(feat, model.fc.in_features, _k32(model.fc.Ka))
+        fcq = P.avgpool_quantize(cur, _k32(model.fc.Ka))
         P.output = P.conv(fcq, model.fc, f32=True, linear=True)["f32"].buf.view(batch, -1)
     else:
+        feat = P.avgpool(cur)
         out = torch.empty((batch, model.fc.out_features), dtype=torch.float32, device=device)
         P.keep.append(out)
         P.torch_op(lambda: torch.addmm(model.fc.bias, feat, model.fc.weight.t(), out=out))
@@ -822,7 +835,6 @@ def compile_shufflenetv2(model, batch, size, device="cuda", static_weights=False
             chans = [x1[j // 2] if j % 2 == 0 else (rs, j // 2) for j in range(c)]
     c5, b5 = model.conv5[0], model.conv5[1]
     feat_map = P.conv(P.gather_quantize(chans, _k32(c5.Ka)), c5, bn=b5, relu=True, layerout=lo, f16=True)["f16"]
-    feat = P.avgpool(feat_map)
-    fcq = P.quantize_flat(feat, model.fc.in_features, _k32(model.fc.Ka))
+    fcq = P.avgpool_quantize(feat_map, _k32(model.fc.Ka))
     P.output = P.conv(fcq, model.fc, f32=True, linear=True)["f32"].buf.view(batch, -1)
     return P

@@ -372,6 +372,13 @@ int slfp_maxpool_codes(const uint8_t *x, int n, int h, int w, int c_phys, int fm
                        int stride, int pad, uint8_t *y, slfp_stream_t stream);
 /* global average pool NHWC float16/float32 -> [n, c] float32 */
 int slfp_avgpool_nhwc(const void *x, int is_f16, int n, int hw, int c, float *y, slfp_stream_t stream);
+/* The same pool on a float16 NHWC tensor with the classifier's activation quantizer fused (replaces
+ * `x = avgpool(x); x = flatten(x, 1)` followed by the act quantizer of `fc`, nets_imgnet/resnet50.py:242-244 and
+ * utils/conv2d_func.py:61): y (optional) receives the float32 means [n, c], codes (optional) encode(mean / k_div) in
+ * fmt = SLFP_FMT_SFP33 | SLFP_FMT_SLFP34_ACT, [n, c] bytes - bit-identical to slfp_avgpool_nhwc + slfp_quantize_nhwc_f32.
+ * c % 8 == 0, 16-byte aligned tensors. */
+int slfp_avgpool_quantize_nhwc_f16(const void *x, int n, int hw, int c, float *y, float k_div, int fmt, uint8_t *codes,
+                                   slfp_stream_t stream);
 
 /* Debug aid: a host-mapped buffer (>= 16 bytes) into which a timed-out barrier wait of the dense conv kernel
  * records which wait it was before it traps (the kernels never hang: every wait is bounded).  NULL removes it. */

@@ -561,3 +561,140 @@ def test_f16_image_activations_equal_the_codes_path(orc, N, C, H, K, k, stride, 
         c_, d_ = run(False, True), run(True, True)
         assert (c_["c1"].view(np.uint16) == want.view(np.uint16)).all()
         assert (d_["c1"].view(np.uint16) == want.view(np.uint16)).all()
+
+
+def _wprep_case(nv, lib, dev, w, Cp, fmt, out_kind, groups=1, row_scale=None, out_pitch=0, out_off=0):
+    """One slfp_prepare_weights_jobs call; returns (float16 / e4m3-byte operand, codes) as numpy arrays."""
+    K, Cg, R, S = w.shape
+    C = Cg * groups
+    flags = nv.CONV_E4M3_OPERANDS if out_kind == "e4m3" else 0
+    d = nv.SlfpConvDesc(1, 8, 8, C, Cp, K, R, S, 1, 1, 0, 0, 1, 1, groups, nv.FMT_SLFP34_ACT, 0, 0, flags)
+    pitch = lib.slfp_conv_wpitch(ctypes.byref(d))
+    rowlen = out_pitch or pitch
+    f16 = torch.full((K * rowlen,), 7.0, dtype=torch.float16, device=dev) if out_kind in ("f16", "both", "e4m3") else None
+    codes = torch.full((K * rowlen,), 0x55, dtype=torch.uint8, device=dev) if out_kind in ("codes", "both") else None
+    job = (nv.SlfpWeightJob * 1)()
+    job[0].desc, job[0].w, job[0].kw = ctypes.pointer(d), w.data_ptr(), float(np.float32(0.07))
+    job[0].w_stride[:] = w.stride()
+    job[0].w_f16 = f16.data_ptr() if f16 is not None else None
+    job[0].w_codes = codes.data_ptr() if codes is not None else None
+    job[0].out_pitch, job[0].out_offset = out_pitch, out_off
+    job[0].row_scale = row_scale.data_ptr() if row_scale is not None else None
+    nv.check(lib.slfp_prepare_weights_jobs(1, job, fmt, nv.stream()))
+    torch.cuda.synchronize()
+    return (None if f16 is None else f16.view(torch.int16).cpu().numpy().copy(),
+            None if codes is None else codes.cpu().numpy().copy(), pitch)
+
+
+@pytest.mark.parametrize("shape", [
+    # K, C/groups, R, S, c_phys, groups
+    (64, 64, 1, 1, 64, 1),            # many rows per CTA
+    (70, 64, 3, 3, 64, 1),            # 8 rows per CTA, ragged last group
+    (24, 256, 3, 3, 256, 1),          # two rows per CTA
+    (9, 512, 3, 3, 512, 1),           # one row per CTA (4 608 elements)
+    (5, 1024, 3, 3, 1024, 1),         # a row split over channel pieces
+    (6, 2048, 1, 1, 2048, 1),         # 1x1, two rows per CTA
+    (3, 9216, 1, 1, 9216, 1),         # linear row longer than a CTA's capacity
+    (16, 24, 3, 3, 32, 1),            # padding channels + K-padding taps
+    (12, 20, 5, 5, 32, 1),            # 25 taps, padding channels
+    (40, 1, 3, 3, 4, 40),             # depthwise: not eligible (one channel per group) -> gather form on both sides
+    (32, 8, 3, 3, 8, 4),              # grouped, 8 channels per group
+    (8, 3, 7, 7, 4, 1),               # the RGB stem: gather form
+])
+@pytest.mark.parametrize("fmt_name,out_kind", [("wgt", "f16"), ("wgt", "both"), ("wgt", "codes"), ("sfp33", "e4m3"), ("sfp33", "both"),
+                                               ("act", "f16")])
+def test_row_staged_weight_preparation_equals_gather_form(orc, shape, fmt_name, out_kind):
+    """wprep_rows_kernel (coalesced source rows staged through shared memory) against the per-element gather kernels on
+    the same jobs (SLFP_WPREP_GATHER=1), bit for bit, and the codes against the oracle's encoder; special values
+    (zeros, NaN, infinities, tiny and huge magnitudes) are sprinkled into the weights."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    dev = torch.device("cuda:0")
+    K, Cg, R, S, Cp, groups = shape
+    fmt = {"wgt": nv.FMT_SLFP34_WGT, "sfp33": nv.FMT_SFP33, "act": nv.FMT_SLFP34_ACT}[fmt_name]
+    if out_kind == "e4m3" and (groups > 1 or Cp % 16):
+        pytest.skip("e4m3 operands are dense")
+    rng = np.random.default_rng(K * 131 + Cg)
+    w_np = (rng.standard_normal((K, Cg, R, S)) * 0.05).astype(np.float32)
+    flat = w_np.reshape(-1)
+    special = np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1e-30, -1e-30, 3e30, 1e-12, 0.07 * 15.32165, 0.07 * 0.0625, 0.07 * 0.125],
+                       np.float32)
+    pos = rng.choice(flat.size, size=min(flat.size // 2, 96), replace=False)
+    flat[pos] = special[np.arange(pos.size) % special.size]
+    w = torch.from_numpy(w_np).to(dev)
+    row_scale = torch.from_numpy(rng.uniform(0.5, 2.0, K).astype(np.float32)).to(dev) if out_kind == "f16" and K % 2 == 0 else None
+    pitch0 = R * S * (Cp if groups == 1 else Cg)
+    pitch0 = pitch0 if groups > 1 else (pitch0 + 63) // 64 * 64
+    out_pitch, out_off = (pitch0 + 128, 64) if (out_kind == "f16" and groups == 1) else (0, 0)
+    try:
+        os.environ.pop("SLFP_WPREP_GATHER", None)
+        fast = _wprep_case(nv, lib, dev, w, Cp, fmt, out_kind, groups, row_scale, out_pitch, out_off)
+        os.environ["SLFP_WPREP_GATHER"] = "1"
+        gather = _wprep_case(nv, lib, dev, w, Cp, fmt, out_kind, groups, row_scale, out_pitch, out_off)
+    finally:
+        os.environ.pop("SLFP_WPREP_GATHER", None)
+    for a, b in zip(fast[:2], gather[:2]):
+        assert (a is None) == (b is None)
+        if a is not None:
+            if out_pitch:                                   # bytes outside [out_off, out_off + pitch) stay untouched on both sides
+                assert (a.reshape(K, out_pitch)[:, :out_off] == 0x4700).all()
+            assert np.array_equal(a, b), int((a != b).sum())
+    if fast[1] is not None and groups == 1:
+        codes = fast[1].reshape(K, fast[2])[:, :R * S * Cp].reshape(K, R * S, Cp)[..., :Cg]
+        want, _ = orc.quantize(np.ascontiguousarray(w_np.reshape(K, Cg, R * S).transpose(0, 2, 1)),
+                               {"wgt": 2, "sfp33": 0, "act": 1}[fmt_name], 0.07)
+        assert np.array_equal(codes, want)
+
+
+@pytest.mark.parametrize("fmt_name", ["act", "sfp33"])
+def test_fused_avgpool_quantizer_equals_two_launches(orc, fmt_name):
+    """slfp_avgpool_quantize_nhwc_f16 against slfp_avgpool_nhwc + slfp_quantize_nhwc_f32: same float32 means, same code
+    bytes, and the codes equal the oracle's quantizer of the means."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    dev = torch.device("cuda:0")
+    fmt = {"act": nv.FMT_SLFP34_ACT, "sfp33": nv.FMT_SFP33}[fmt_name]
+    rng = np.random.default_rng(77)
+    for (n, hw, c) in [(5, 49, 2048), (3, 16, 1024), (2, 1, 64), (4, 7, 24)]:
+        x = torch.from_numpy((np.abs(rng.standard_normal((n, hw, c))) * 2).astype(np.float16)).to(dev)
+        x[0, :, :8] = 0
+        kdiv = float(np.float32(0.21))
+        mean_a = torch.empty((n, c), dtype=torch.float32, device=dev)
+        codes_a = torch.empty((n, c), dtype=torch.uint8, device=dev)
+        nv.check(lib.slfp_avgpool_nhwc(x.data_ptr(), 1, n, hw, c, mean_a.data_ptr(), nv.stream()))
+        nv.check(lib.slfp_quantize_nhwc_f32(mean_a.data_ptr(), n, c, c, kdiv, fmt, codes_a.data_ptr(), nv.stream()))
+        mean_b = torch.full((n, c), -1.0, dtype=torch.float32, device=dev)
+        codes_b = torch.full((n, c), 0x55, dtype=torch.uint8, device=dev)
+        nv.check(lib.slfp_avgpool_quantize_nhwc_f16(x.data_ptr(), n, hw, c, mean_b.data_ptr(), kdiv, fmt, codes_b.data_ptr(), nv.stream()))
+        codes_c = torch.full((n, c), 0x55, dtype=torch.uint8, device=dev)
+        nv.check(lib.slfp_avgpool_quantize_nhwc_f16(x.data_ptr(), n, hw, c, None, kdiv, fmt, codes_c.data_ptr(), nv.stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(mean_a.view(torch.int32), mean_b.view(torch.int32))
+        assert torch.equal(codes_a, codes_b) and torch.equal(codes_a, codes_c)
+        want, _ = orc.quantize(mean_a.cpu().numpy(), {"act": 1, "sfp33": 0}[fmt_name], kdiv)
+        assert np.array_equal(codes_b.cpu().numpy(), want)
+
+
+def test_row_staged_weight_encoder_every_mantissa(orc):
+    """The one-look-up SLFP<3,4> weight encoder of wprep_rows_kernel against the oracle for EVERY float32 mantissa of the
+    exponents around and inside the code range (2^-6 .. 2^4), both signs: codes bit-exact, float16 operand = float16 of
+    the decoded value."""
+    from cnns_slfp_quantization_b200 import _native as nv
+    lib = nv.lib()
+    dev = torch.device("cuda:0")
+    K, C = 2048, 4096                                        # 2^23 weights per tensor = one binade
+    d = nv.SlfpConvDesc(1, 1, 1, C, C, K, 1, 1, 1, 1, 0, 0, 1, 1, 1, nv.FMT_SLFP34_ACT)
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    codes = torch.empty(K * C, dtype=torch.uint8, device=dev)
+    f16 = torch.empty(K * C, dtype=torch.float16, device=dev)
+    for e in range(120, 132):
+        bits = mant | np.uint32(e << 23)
+        bits[1::2] |= np.uint32(0x80000000)
+        w = torch.from_numpy(bits.view(np.float32).reshape(K, C, 1, 1)).to(dev)
+        nv.check(lib.slfp_prepare_weights(ctypes.byref(d), w.data_ptr(), *w.stride(), 1.0, nv.FMT_SLFP34_WGT, f16.data_ptr(), codes.data_ptr(),
+                                          None, nv.stream()))
+        torch.cuda.synchronize()
+        want, fq = orc.quantize(bits.view(np.float32), 2, 1.0)
+        got = codes.cpu().numpy()
+        assert np.array_equal(got, want), (e, int((got != want).sum()))
+        assert np.array_equal(f16.view(torch.int16).cpu().numpy(), fq.astype(np.float16).view(np.int16)), e
