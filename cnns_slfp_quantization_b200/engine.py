@@ -224,7 +224,8 @@ class Plan:
         with (at most two distinct).  Returns {'codes': {kdiv: _T}, 'f16': _T | None, 'f32': _T | None}.
         relu_codes: the consumers are dense layers / max-pools (which read the unsigned post-ReLU code format,
         written by the 2-instruction encoder); pass False when a depthwise / grouped layer consumes the codes.
-        q16: the single consumer is a dense layer that should read the float16 image of the codes (Plan.f16q)."""
+        q16: the single consumer is a dense layer that should read the float16 image of the codes (Plan.f16q); pass the
+        consumer's tap count (1 for a 1x1 layer, 9 for a 3x3) - the size limit of the edge depends on it."""
         assert x.kind in ("codes", "q16")
         if linear:
             K, C = mod.weight.shape
@@ -319,7 +320,9 @@ class Plan:
         # layers, whose 8 epilogue warps are their critical path) against a flat ~12-18 us the 3x3 consumer saves by not
         # decoding: worth it below ~16 M elements (ResNet-50 stages 3-4 at batch 256)
         # (a producer that itself reads float16 images has no decode warps competing with its epilogue's table look-ups: 64 M)
-        if R * S == 1 and x.kind != "q16":
+        # (measured per edge kind, SLFP_F16Q_MAX_ELEMS A/B on one box: a 1x1 CONSUMER decodes each element once anyway and pays double
+        # the bytes - ResNet-50 3.80 -> 3.74 ms with those edges on codes; a 3x3 consumer saves nine decodes - VGG-16 0.521 -> 0.504 ms)
+        if int(q16) == 1 or (R * S == 1 and x.kind != "q16"):
             q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS_1X1", 4 << 20))
         else:
             q16_max = int(os.environ.get("SLFP_F16Q_MAX_ELEMS", (64 << 20) if x.kind == "q16" else (16 << 20)))
@@ -657,8 +660,8 @@ def compile_resnet50(model, batch, size=224, device="cuda", residual="f16", stat
                 and b.conv2.out_channels % 64 == 0 and b.conv3.out_channels % 16 == 0)
         # conv1 -> conv2 (3x3: nine taps x N tiles of table look-ups per input code) and conv2 -> conv3 (short K) exchange
         # float16 images; the dual-input tail of a down-sampling block reads codes on both inputs
-        o1 = P.conv(cur_codes[_k32(b.conv1.Ka)], b.conv1, bn=b.bn1, relu=True, codes=[_k32(b.conv2.Ka)], q16=q16_edges)
-        o2 = P.conv(o1["codes"][_k32(b.conv2.Ka)], b.conv2, bn=b.bn2, relu=True, codes=[_k32(b.conv3.Ka)], q16=q16_edges and not fuse)
+        o1 = P.conv(cur_codes[_k32(b.conv1.Ka)], b.conv1, bn=b.bn1, relu=True, codes=[_k32(b.conv2.Ka)], q16=9 if q16_edges else 0)
+        o2 = P.conv(o1["codes"][_k32(b.conv2.Ka)], b.conv2, bn=b.bn2, relu=True, codes=[_k32(b.conv3.Ka)], q16=1 if (q16_edges and not fuse) else 0)
         need_val = nxt is None or nxt.downsample is None        # someone adds / pools the un-quantized value
         if fuse:
             # block tail and downsample branch as ONE GEMM: no downsample launch, no float16 round trip of its output
@@ -710,7 +713,7 @@ def compile_vgg16(model, batch, size=32, device="cuda", static_weights=False):
             nxt_k = _k32(convs[ci + 1].Ka) if ci + 1 < len(convs) else _k32(fcs[0].Ka)
             # conv -> conv edges (no pool in between) hand over float16 images: the 3x3 consumer skips its decode stage
             to_conv = i + 3 < len(seq) and isinstance(seq[i + 3], nn.Conv2d)
-            cur = P.conv(cur, m, bn=bn, relu=True, codes=[nxt_k], q16=to_conv)["codes"][nxt_k]
+            cur = P.conv(cur, m, bn=bn, relu=True, codes=[nxt_k], q16=9 if to_conv else 0)["codes"][nxt_k]
             i += 3
         elif isinstance(m, nn.MaxPool2d):
             cur = P.maxpool(cur, m.kernel_size, m.stride, m.padding)
