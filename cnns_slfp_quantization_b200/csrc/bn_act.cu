@@ -1,0 +1,261 @@
+// Training-mode BatchNorm2d + residual add + ReLU of the QAT step (BASELINE config 4), fused, on float32 NHWC
+// tensors (the layout Conv2d_Q returns).  Replaces the caller net's stock sequence
+//     out = relu(bn(conv(x)))            nets_imgnet/resnet50.py:71-77
+//     out = bn3(conv3(out)); out += identity; out = relu(out)      :79-88
+// which PyTorch runs as BatchNorm (2 reads + 1 write), add (2 reads + 1 write) and ReLU (1 read + 1 write) forward and
+// again backward - half of the 34.6 ms QAT step (profiles/r01_final.md section 2).  Here:
+//   forward   bn_reduce_kernel<0>  1 read   per-channel sum / sum of squares; the last CTA turns the sums into
+//                                        mean, 1/sqrt(var + eps), the folded scale / shift and the running statistics
+//             bn_apply_kernel   1-2 reads + 1 write   y = relu(x * scale + shift + residual)
+//   backward  bn_reduce_kernel<1>  3 reads   g = gy * (y > 0); sum g, sum g (x - mean); last CTA -> dgamma, dbeta and
+//                                             the three per-channel coefficients of dx
+//             bn_bwd_apply_kernel   3 reads + 1-2 writes   dx = a (g - b - (x - mean) c);  d_residual = g
+// Reductions: float32 per thread and CTA, then one double-precision atomicAdd per CTA and channel (600 float32 partials in
+// double: the float32 results do not depend on the arrival order except for ties at the 1e-13 level); the last CTA to
+// arrive turns the sums into the per-channel coefficients and clears the accumulators for the next launch.
+// HBM-bound; algorithmic bytes per element: forward 12 (16 with a residual), backward 28 (32).
+#include "slfp_common.cuh"
+
+namespace slfp {
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+constexpr int kBnThreads = 256;
+constexpr int kBnMaxBlocks = 592;                       // 148 SMs x 4
+
+// Thread geometry: a row of C floats is covered by CT = min(C / 4, 256) threads with one float4 each (grid.y walks
+// over further 1 024-channel chunks), RT = 256 / CT rows are in flight per CTA iteration.
+struct BnGeom {
+    int C, C4, CT, RT;
+    size_t M;
+};
+
+// workspace layout: [0] arrival counter (uint, 16 bytes reserved), double acc[2][C] - everything zero between launches
+// whatever C the previous launch had.  The per-channel coefficients (forward: scale, shift | backward: a, b, c) go
+// to a separate caller-provided scratch vector `coef` [4][C] that needs no initialisation.
+__host__ __device__ __forceinline__ double* ws_acc(float* ws) { return reinterpret_cast<double*>(ws + 4); }
+
+template <int MODE>   // 0: forward statistics of x; 1: backward sums of g and g (x - mean)
+__global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                               const float* __restrict__ y, BnGeom g, int relu,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float eps, float momentum, float* __restrict__ running_mean,
+                                                               float* __restrict__ running_var, float* __restrict__ save_mean,
+                                                               float* __restrict__ save_invstd, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, float* __restrict__ ws,
+                                                               float* __restrict__ coef) {
+    __shared__ float4 s_a[kBnThreads], s_b[kBnThreads];
+    __shared__ bool s_last;
+    const int tx = threadIdx.x % g.CT, ty = threadIdx.x / g.CT;
+    const int c4 = blockIdx.y * 256 + tx;                                  // float4 column
+    const bool active = ty < g.RT && c4 < g.C4;
+    float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    float4 mean4 = sa, sc4 = sa, sh4 = sa;
+    const bool remask = MODE == 1 && relu && y == nullptr;                // ReLU mask recomputed from x (no residual): y is not read
+    if (MODE == 1 && active) {
+        mean4 = *reinterpret_cast<const float4*>(save_mean + 4 * c4);
+        if (remask) {                                                     // the forward's own scale / shift, bit for bit
+            const float4 gm = *reinterpret_cast<const float4*>(gamma + 4 * c4), bt = *reinterpret_cast<const float4*>(beta + 4 * c4);
+            const float4 is = *reinterpret_cast<const float4*>(save_invstd + 4 * c4);
+            sc4 = make_float4(gm.x * is.x, gm.y * is.y, gm.z * is.z, gm.w * is.w);
+            sh4 = make_float4(bt.x - mean4.x * sc4.x, bt.y - mean4.y * sc4.y, bt.z - mean4.z * sc4.z, bt.w - mean4.w * sc4.w);
+        }
+    }
+    if (active) {
+        const size_t stride = (size_t)gridDim.x * g.RT;
+#pragma unroll 4
+        for (size_t r = (size_t)blockIdx.x * g.RT + ty; r < g.M; r += stride) {
+            const size_t o = r * g.C4 + c4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + o);
+            if (MODE == 0) {
+                sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
+                sb.x += v.x * v.x; sb.y += v.y * v.y; sb.z += v.z * v.z; sb.w += v.w * v.w;
+            } else {
+                float4 gg = __ldg(reinterpret_cast<const float4*>(gy) + o);
+                if (remask) {
+                    gg.x = v.x * sc4.x + sh4.x > 0.f ? gg.x : 0.f; gg.y = v.y * sc4.y + sh4.y > 0.f ? gg.y : 0.f;
+                    gg.z = v.z * sc4.z + sh4.z > 0.f ? gg.z : 0.f; gg.w = v.w * sc4.w + sh4.w > 0.f ? gg.w : 0.f;
+                } else if (relu) {
+                    const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + o);
+                    gg.x = yy.x > 0.f ? gg.x : 0.f; gg.y = yy.y > 0.f ? gg.y : 0.f;
+                    gg.z = yy.z > 0.f ? gg.z : 0.f; gg.w = yy.w > 0.f ? gg.w : 0.f;
+                }
+                sa.x += gg.x; sa.y += gg.y; sa.z += gg.z; sa.w += gg.w;
+                sb.x += gg.x * (v.x - mean4.x); sb.y += gg.y * (v.y - mean4.y);
+                sb.z += gg.z * (v.z - mean4.z); sb.w += gg.w * (v.w - mean4.w);
+            }
+        }
+    }
+    s_a[threadIdx.x] = sa; s_b[threadIdx.x] = sb;
+    __syncthreads();
+    double* acc = ws_acc(ws);
+    if (ty == 0 && c4 < g.C4) {                                           // fixed order over the rows of the CTA
+        for (int j = 1; j < g.RT; ++j) {
+            const float4 a = s_a[j * g.CT + tx], b = s_b[j * g.CT + tx];
+            sa.x += a.x; sa.y += a.y; sa.z += a.z; sa.w += a.w;
+            sb.x += b.x; sb.y += b.y; sb.z += b.z; sb.w += b.w;
+        }
+        double* pa = acc + 4 * c4;
+        double* pb = acc + g.C + 4 * c4;
+        atomicAdd(pa + 0, (double)sa.x); atomicAdd(pa + 1, (double)sa.y); atomicAdd(pa + 2, (double)sa.z); atomicAdd(pa + 3, (double)sa.w);
+        atomicAdd(pb + 0, (double)sb.x); atomicAdd(pb + 1, (double)sb.y); atomicAdd(pb + 2, (double)sb.z); atomicAdd(pb + 3, (double)sb.w);
+    }
+    // last CTA to arrive (over the whole grid) finishes the reduction
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+        s_last = prev + 1 == total;
+        if (s_last) *reinterpret_cast<unsigned*>(ws) = 0u;                // self-cleaning for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double inv_m = 1.0 / (double)g.M;
+    for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
+        const double a = __ldcg(acc + c), b = __ldcg(acc + g.C + c);
+        acc[c] = 0.0; acc[g.C + c] = 0.0;                                 // self-cleaning
+        if (MODE == 0) {
+            const double mean = a * inv_m;
+            double var = b * inv_m - mean * mean;
+            var = var < 0.0 ? 0.0 : var;
+            const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+            save_mean[c] = (float)mean;
+            save_invstd[c] = invstd;
+            const float sc = gamma[c] * invstd;
+            coef[c] = sc;
+            coef[g.C + c] = beta[c] - (float)mean * sc;
+            if (running_mean) {                                           // nn.BatchNorm2d: unbiased variance into the running estimate
+                const double unb = g.M > 1 ? var * ((double)g.M / (double)(g.M - 1)) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+            }
+        } else {
+            const float invstd = save_invstd[c];
+            dbeta[c] = (float)a;
+            dgamma[c] = (float)(b * (double)invstd);
+            coef[c] = gamma[c] * invstd;                                       // a
+            coef[g.C + c] = (float)(a * inv_m);                                // b = mean(g)
+            coef[2 * g.C + c] = (float)(b * inv_m * (double)invstd * (double)invstd);   // c = mean(g (x - mean)) / var
+            if (remask) coef[3 * g.C + c] = beta[c] - save_mean[c] * (gamma[c] * invstd);   // the forward's shift (its scale is a)
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, size_t n4,
+                                                              int C4, int relu, const float* __restrict__ coef, int C,
+                                                              float* __restrict__ y) {
+    for (size_t i = (size_t)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kBnThreads) {
+        const int c4 = (C4 & (C4 - 1)) == 0 ? (int)(i & (size_t)(C4 - 1)) : (int)(i % (size_t)C4);
+        const float4 v = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(coef) + c4);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(coef + C) + c4);
+        float4 o = make_float4(v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w);
+        if (res) {
+            const float4 r = ldg_stream(reinterpret_cast<const float4*>(res) + i);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        reinterpret_cast<float4*>(y)[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                                  const float* __restrict__ y, size_t n4, int C4, int relu,
+                                                                  const float* __restrict__ coef, int C,
+                                                                  const float* __restrict__ save_mean, float* __restrict__ dx,
+                                                                  float* __restrict__ dres) {
+    for (size_t i = (size_t)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kBnThreads) {
+        const int c4 = (C4 & (C4 - 1)) == 0 ? (int)(i & (size_t)(C4 - 1)) : (int)(i % (size_t)C4);
+        float4 g = ldg_stream(reinterpret_cast<const float4*>(gy) + i);
+        const float4 v = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(coef) + c4);
+        if (relu && y == nullptr) {
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(coef + 3 * C) + c4);
+            g.x = v.x * a.x + sh.x > 0.f ? g.x : 0.f; g.y = v.y * a.y + sh.y > 0.f ? g.y : 0.f;
+            g.z = v.z * a.z + sh.z > 0.f ? g.z : 0.f; g.w = v.w * a.w + sh.w > 0.f ? g.w : 0.f;
+        } else if (relu) {
+            const float4 yy = ldg_stream(reinterpret_cast<const float4*>(y) + i);
+            g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
+            g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+        }
+        const float4 b = __ldg(reinterpret_cast<const float4*>(coef + C) + c4);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(coef + 2 * C) + c4);
+        const float4 m = __ldg(reinterpret_cast<const float4*>(save_mean) + c4);
+        float4 o;
+        o.x = a.x * ((g.x - b.x) - (v.x - m.x) * c.x);
+        o.y = a.y * ((g.y - b.y) - (v.y - m.y) * c.y);
+        o.z = a.z * ((g.z - b.z) - (v.z - m.z) * c.z);
+        o.w = a.w * ((g.w - b.w) - (v.w - m.w) * c.w);
+        reinterpret_cast<float4*>(dx)[i] = o;
+        if (dres) reinterpret_cast<float4*>(dres)[i] = g;
+    }
+}
+
+static bool bn_geom(size_t m, int c, BnGeom& g, dim3& grid) {
+    if (c <= 0 || (c & 3) || m == 0) return false;
+    g.C = c; g.C4 = c / 4; g.M = m;
+    g.CT = g.C4 < 256 ? g.C4 : 256;
+    g.RT = kBnThreads / g.CT;
+    const size_t want = (m + (size_t)g.RT * 4 - 1) / ((size_t)g.RT * 4);  // >= 4 rows per thread before another CTA pays off
+    const int gy_ = (g.C4 + 255) / 256;
+    int gx = kBnMaxBlocks / gy_;
+    if ((size_t)gx > want) gx = (int)want;
+    if (gx < 1) gx = 1;
+    grid = dim3((unsigned)gx, (unsigned)gy_);
+    return true;
+}
+
+}  // namespace slfp
+
+using namespace slfp;
+
+extern "C" size_t slfp_bn_act_workspace_floats(int c) {
+    return 4 + (size_t)4 * (c > 0 ? c : 0);
+}
+
+extern "C" int slfp_bn_act_fwd_train(const float* x, size_t m, int c, const float* gamma, const float* beta, const float* residual,
+                                     int relu, float eps, float momentum, float* running_mean, float* running_var, float* y,
+                                     float* save_mean, float* save_invstd, float* workspace, float* coef, slfp_stream_t stream) {
+    if (m == 0) return 0;
+    if (!x || !gamma || !beta || !y || !save_mean || !save_invstd || !workspace || !coef)
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: null pointer");
+    BnGeom g; dim3 grid;
+    if (!bn_geom(m, c, g, grid) || ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)workspace | (uintptr_t)save_mean | (uintptr_t)coef) & 15u)))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: needs c %% 4 == 0 and 16-byte aligned tensors");
+    if ((running_mean == nullptr) != (running_var == nullptr)) return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: running statistics come in pairs");
+    cudaStream_t st = (cudaStream_t)stream;
+    bn_reduce_kernel<0><<<grid, kBnThreads, 0, st>>>(x, nullptr, nullptr, g, 0, gamma, beta, eps, momentum, running_mean, running_var,
+                                                     save_mean, save_invstd, nullptr, nullptr, workspace, coef);
+    if (int rc = check_launch("bn_reduce_kernel<0>")) return rc;
+    const size_t n4 = m * (size_t)g.C4;
+    const int ag = (int)min((size_t)num_sms() * 8, (n4 + kBnThreads - 1) / kBnThreads);
+    bn_apply_kernel<<<ag, kBnThreads, 0, st>>>(x, residual, n4, g.C4, relu, coef, c, y);
+    return check_launch("bn_apply_kernel");
+}
+
+extern "C" int slfp_bn_act_bwd(const float* gy, const float* x, const float* y, size_t m, int c, const float* gamma, const float* beta,
+                               const float* save_mean, const float* save_invstd, int relu, float* dx, float* d_residual,
+                               float* dgamma, float* dbeta, float* workspace, float* coef, slfp_stream_t stream) {
+    if (m == 0) return 0;
+    if (!gy || !x || (relu && !y && !beta) || !gamma || !save_mean || !save_invstd || !dx || !dgamma || !dbeta || !workspace || !coef)
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_bwd: null pointer");
+    BnGeom g; dim3 grid;
+    if (!bn_geom(m, c, g, grid) ||
+        ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gy | (uintptr_t)dx | (uintptr_t)d_residual | (uintptr_t)workspace | (uintptr_t)save_mean | (uintptr_t)coef) & 15u)))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_bwd: needs c %% 4 == 0 and 16-byte aligned tensors");
+    cudaStream_t st = (cudaStream_t)stream;
+    bn_reduce_kernel<1><<<grid, kBnThreads, 0, st>>>(x, gy, y, g, relu, gamma, beta, 0.f, 0.f, nullptr, nullptr,
+                                                     const_cast<float*>(save_mean), const_cast<float*>(save_invstd), dgamma, dbeta, workspace, coef);
+    if (int rc = check_launch("bn_reduce_kernel<1>")) return rc;
+    const size_t n4 = m * (size_t)g.C4;
+    const int ag = (int)min((size_t)num_sms() * 8, (n4 + kBnThreads - 1) / kBnThreads);
+    bn_bwd_apply_kernel<<<ag, kBnThreads, 0, st>>>(gy, x, y, n4, g.C4, relu, coef, c, save_mean, dx, d_residual);
+    return check_launch("bn_bwd_apply_kernel");
+}

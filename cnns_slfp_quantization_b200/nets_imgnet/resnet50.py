@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from ..nets_common import product_ops, reference_scales
+from ..utils.bn_act import bn_act
 
 _STAGES = ((64, 3, 1, 1), (128, 4, 2, 11), (256, 6, 2, 24), (512, 3, 2, 43))   # planes, blocks, stride, scale offset
 
@@ -34,14 +35,14 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
+        # relu(bn(conv)) / relu(bn3(conv3) + identity) as in the reference (nets_imgnet/resnet50.py:71-88); in training mode on
+        # the GPU each BatchNorm (+ add) (+ ReLU) group is one fused op (utils/bn_act.py), otherwise the stock modules run
         identity = x
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
+        out = bn_act(self.conv1(x), self.bn1)
+        out = bn_act(self.conv2(out), self.bn2)
         if self.downsample is not None:
-            identity = self.downsample(x)
-        out += identity
-        return self.relu(out)
+            identity = bn_act(self.downsample[0](x), self.downsample[1], relu=False)
+        return bn_act(self.conv3(out), self.bn3, relu=True, residual=identity)
 
 
 class ResNet50(nn.Module):
@@ -72,7 +73,7 @@ class ResNet50(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(bn_act(self.conv1(x), self.bn1))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
         return self.fc(x)

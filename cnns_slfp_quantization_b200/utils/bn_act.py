@@ -1,0 +1,93 @@
+"""Fused training-mode BatchNorm2d (+ residual add) (+ ReLU) around the quantized convolutions of a QAT step.
+
+The reference's nets run `relu(bn(conv(x)))` and `relu(bn3(conv3(out)) + identity)` as separate PyTorch modules
+(nets_imgnet/resnet50.py:71-88); in the SLFP-8 QAT step (cifar100_train_eval.py:170-179) those stock kernels were half
+of the step time.  `bn_act(x, bn, relu, residual)` computes the same function of the same nn.BatchNorm2d module - its
+weight / bias / running statistics / num_batches_tracked are used and updated in place, so state_dict keys and the
+optimizer's parameter list do not change - with two HBM passes forward and two backward (csrc/bn_act.cu) on the
+channels-last float32 tensors Conv2d_Q returns.  Anything the kernels do not cover (eval mode, CPU tensors, no affine /
+no running statistics, momentum=None, channel counts that are not multiples of 4, SLFP_NO_FUSED_BN=1) takes the stock
+modules, so the function is always safe to call.
+"""
+import os
+
+import torch
+import torch.nn.functional as F
+
+from .. import _native as _nv
+
+_workspaces = {}
+
+
+def _workspace(dev, c):
+    """One zero-initialised workspace per (device, stream); the kernels leave it zeroed."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    need = _nv.lib().slfp_bn_act_workspace_floats(c)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 4 + 4 * 4096), dtype=torch.float32, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+class _BnAct(torch.autograd.Function):
+    """x, residual: [N, H, W, C] float32 contiguous (NHWC).  Returns y of the same shape."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu):
+        lib = _nv.lib()
+        x = x.contiguous()
+        res = residual.contiguous() if residual is not None else None
+        c = x.shape[-1]
+        m = x.numel() // c
+        y = torch.empty_like(x)
+        mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        ws = _workspace(x.device, c)
+        coef = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+        _nv.check(lib.slfp_bn_act_fwd_train(x.data_ptr(), m, c, weight.data_ptr(), bias.data_ptr(), _nv.ptr(res), int(relu), eps,
+                                            momentum, _nv.ptr(running_mean), _nv.ptr(running_var), y.data_ptr(), mean.data_ptr(),
+                                            invstd.data_ptr(), ws.data_ptr(), coef.data_ptr(), _nv.stream()))
+        # the ReLU mask of a layer without residual is recomputed from x in the backward: y is not kept alive
+        ctx.save_for_backward(x, y if (relu and res is not None) else None, weight, bias, mean, invstd)
+        ctx.relu, ctx.has_res = bool(relu), res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _nv.lib()
+        x, y, weight, bias, mean, invstd = ctx.saved_tensors
+        gy = gy.contiguous()
+        c = x.shape[-1]
+        m = x.numel() // c
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+        ws = _workspace(x.device, c)
+        coef = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+        _nv.check(lib.slfp_bn_act_bwd(gy.data_ptr(), x.data_ptr(), _nv.ptr(y), m, c, weight.data_ptr(), bias.data_ptr(), mean.data_ptr(),
+                                      invstd.data_ptr(), int(ctx.relu), dx.data_ptr(), _nv.ptr(dres), dgamma.data_ptr(),
+                                      dbeta.data_ptr(), ws.data_ptr(), coef.data_ptr(), _nv.stream()))
+        return dx, dgamma, dbeta, dres, None, None, None, None, None
+
+
+def fused_ok(bn, x):
+    return (bn.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and bn.affine and bn.track_running_stats
+            and bn.momentum is not None and bn.num_features % 4 == 0 and bn.weight.dtype == torch.float32
+            and not os.environ.get("SLFP_NO_FUSED_BN"))
+
+
+def bn_act(x, bn, relu=True, residual=None):
+    """relu?(bn(x) + residual?) for an nn.BatchNorm2d module `bn` and NCHW-shaped tensors (channels-last memory is used
+    as is; other layouts are converted)."""
+    if not fused_ok(bn, x):
+        out = bn(x)
+        if residual is not None:
+            out = out + residual
+        return F.relu(out) if relu else out
+    bn.num_batches_tracked.add_(1)
+    xn = x.permute(0, 2, 3, 1)
+    rn = residual.permute(0, 2, 3, 1) if residual is not None else None
+    y = _BnAct.apply(xn, bn.weight, bn.bias, rn, bn.running_mean, bn.running_var, float(bn.eps), float(bn.momentum), bool(relu))
+    return y.permute(0, 3, 1, 2)

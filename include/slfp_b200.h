@@ -380,6 +380,27 @@ int slfp_avgpool_nhwc(const void *x, int is_f16, int n, int hw, int c, float *y,
 int slfp_avgpool_quantize_nhwc_f16(const void *x, int n, int hw, int c, float *y, float k_div, int fmt, uint8_t *codes,
                                    slfp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * QAT step (BASELINE config 4): training-mode BatchNorm2d + residual add + ReLU of the caller net, fused, float32 NHWC
+ * [m = n*h*w rows, c channels], c % 4 == 0.  Replaces the stock sequences of nets_imgnet/resnet50.py:71-88
+ * (`relu(bn(conv(x)))`, `bn3(conv3(out)); out += identity; relu(out)`) around the quantized convolutions
+ * (cifar100_train_eval.py:170-179 runs them forward and backward every step).
+ *   y = relu?( (x - mean_c) / sqrt(var_c + eps) * gamma_c + beta_c + residual? )     batch statistics over the m rows
+ * running_mean / running_var (optional pair) are updated like nn.BatchNorm2d (momentum, unbiased variance).
+ * save_mean / save_invstd [c] are outputs for the backward.  workspace: slfp_bn_act_workspace_floats(c) floats, 16-byte
+ * aligned, ZERO-FILLED once by the caller (the kernels leave it zeroed); one workspace per stream.  coef: scratch
+ * vector of 4 * c floats, 16-byte aligned, no initialisation (per call: it is read by the second kernel of the call).
+ * Backward: dx [m, c], d_residual [m, c] (optional: the gradient of the residual input), dgamma / dbeta [c].  The ReLU
+ * mask comes from y; for a layer without residual y may be NULL and beta given instead: the mask is then recomputed
+ * from x with the forward's own scale / shift arithmetic (one read pass less, y need not be kept). */
+size_t slfp_bn_act_workspace_floats(int c);
+int slfp_bn_act_fwd_train(const float *x, size_t m, int c, const float *gamma, const float *beta, const float *residual,
+                          int relu, float eps, float momentum, float *running_mean, float *running_var, float *y,
+                          float *save_mean, float *save_invstd, float *workspace, float *coef, slfp_stream_t stream);
+int slfp_bn_act_bwd(const float *gy, const float *x, const float *y, size_t m, int c, const float *gamma, const float *beta,
+                    const float *save_mean, const float *save_invstd, int relu, float *dx, float *d_residual,
+                    float *dgamma, float *dbeta, float *workspace, float *coef, slfp_stream_t stream);
+
 /* Debug aid: a host-mapped buffer (>= 16 bytes) into which a timed-out barrier wait of the dense conv kernel
  * records which wait it was before it traps (the kernels never hang: every wait is bounded).  NULL removes it. */
 int slfp_debug_set_buffer(void *host_mapped_device_ptr);
