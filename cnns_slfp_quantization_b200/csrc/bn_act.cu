@@ -148,9 +148,19 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const float* __re
     }
 }
 
+// up to two consumers of y with their own activation scales (a block output feeds the next block's conv1 and its
+// downsample conv): each gets the 8-bit codes of the reference quantizer of y / K (utils/conv2d_func.py:21) - what
+// slfp_quantize_nhwc_f32 would produce from y in a pass of its own.  Post-ReLU values only (y >= 0): encode_relu<>.
+struct BnQuantOut {
+    uint8_t* codes[2];
+    DivK dk[2];
+    int n;
+};
+
+template <int FMT>    // activation code format of the quantized outputs, or -1: none
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, size_t n4,
                                                               int C4, int relu, const float* __restrict__ coef, int C,
-                                                              float* __restrict__ y) {
+                                                              float* __restrict__ y, BnQuantOut q) {
     for (size_t i = (size_t)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kBnThreads) {
         const int c4 = (C4 & (C4 - 1)) == 0 ? (int)(i & (size_t)(C4 - 1)) : (int)(i % (size_t)C4);
         const float4 v = ldg_stream(reinterpret_cast<const float4*>(x) + i);
@@ -163,6 +173,23 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float* __res
         }
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         reinterpret_cast<float4*>(y)[i] = o;
+        if (FMT >= 0) {
+            constexpr int F = FMT < 0 ? 0 : FMT;
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+            const bool has_nan = !(o.x == o.x && o.y == o.y && o.z == o.z && o.w == o.w);     // fmaxf(NaN, 0) = 0, but a NaN residual ...
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j < q.n) {
+                    uint32_t w = 0u;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float qv = div_k_fused(ov[e], q.dk[j]);
+                        w |= (has_nan ? encode<F>(div_k(ov[e], q.dk[j])) : encode_relu<F>(qv)) << (8 * e);
+                    }
+                    reinterpret_cast<uint32_t*>(q.codes[j])[i] = w;
+                }
+            }
+        }
     }
 }
 
@@ -220,9 +247,10 @@ extern "C" size_t slfp_bn_act_workspace_floats(int c) {
     return 4 + (size_t)4 * (c > 0 ? c : 0);
 }
 
-extern "C" int slfp_bn_act_fwd_train(const float* x, size_t m, int c, const float* gamma, const float* beta, const float* residual,
-                                     int relu, float eps, float momentum, float* running_mean, float* running_var, float* y,
-                                     float* save_mean, float* save_invstd, float* workspace, float* coef, slfp_stream_t stream) {
+static int bn_act_fwd_impl(const float* x, size_t m, int c, const float* gamma, const float* beta, const float* residual,
+                           int relu, float eps, float momentum, float* running_mean, float* running_var, float* y,
+                           float* save_mean, float* save_invstd, float* workspace, float* coef, int fmt, const BnQuantOut& q,
+                           slfp_stream_t stream) {
     if (m == 0) return 0;
     if (!x || !gamma || !beta || !y || !save_mean || !save_invstd || !workspace || !coef)
         return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: null pointer");
@@ -236,8 +264,36 @@ extern "C" int slfp_bn_act_fwd_train(const float* x, size_t m, int c, const floa
     if (int rc = check_launch("bn_reduce_kernel<0>")) return rc;
     const size_t n4 = m * (size_t)g.C4;
     const int ag = (int)min((size_t)num_sms() * 8, (n4 + kBnThreads - 1) / kBnThreads);
-    bn_apply_kernel<<<ag, kBnThreads, 0, st>>>(x, residual, n4, g.C4, relu, coef, c, y);
+    if (q.n == 0) bn_apply_kernel<-1><<<ag, kBnThreads, 0, st>>>(x, residual, n4, g.C4, relu, coef, c, y, q);
+    else if (fmt == SLFP_FMT_SFP33) bn_apply_kernel<SLFP_FMT_SFP33><<<ag, kBnThreads, 0, st>>>(x, residual, n4, g.C4, relu, coef, c, y, q);
+    else bn_apply_kernel<SLFP_FMT_SLFP34_ACT><<<ag, kBnThreads, 0, st>>>(x, residual, n4, g.C4, relu, coef, c, y, q);
     return check_launch("bn_apply_kernel");
+}
+
+extern "C" int slfp_bn_act_fwd_train(const float* x, size_t m, int c, const float* gamma, const float* beta, const float* residual,
+                                     int relu, float eps, float momentum, float* running_mean, float* running_var, float* y,
+                                     float* save_mean, float* save_invstd, float* workspace, float* coef, slfp_stream_t stream) {
+    BnQuantOut q;
+    q.n = 0; q.codes[0] = q.codes[1] = nullptr; q.dk[0] = q.dk[1] = make_divk(1.0f);
+    return bn_act_fwd_impl(x, m, c, gamma, beta, residual, relu, eps, momentum, running_mean, running_var, y, save_mean, save_invstd,
+                           workspace, coef, -1, q, stream);
+}
+
+extern "C" int slfp_bn_act_fwd_train_quant(const float* x, size_t m, int c, const float* gamma, const float* beta, const float* residual,
+                                           float eps, float momentum, float* running_mean, float* running_var, float* y,
+                                           float* save_mean, float* save_invstd, float* workspace, float* coef, int fmt, int n_codes,
+                                           const float* k_div, uint8_t* const* codes, slfp_stream_t stream) {
+    if (n_codes < 1 || n_codes > 2 || !k_div || !codes || (fmt != SLFP_FMT_SFP33 && fmt != SLFP_FMT_SLFP34_ACT))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train_quant: 1 or 2 code outputs in SFP<3,3> / SLFP<3,4> activation format");
+    BnQuantOut q;
+    q.n = n_codes; q.codes[1] = nullptr; q.dk[1] = make_divk(1.0f);
+    for (int j = 0; j < n_codes; ++j) {
+        if (!codes[j] || (((uintptr_t)codes[j]) & 3u) || !(k_div[j] > 0.f))
+            return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train_quant: code tensors are 4-byte aligned, scales positive");
+        q.codes[j] = codes[j]; q.dk[j] = make_divk(k_div[j]);
+    }
+    return bn_act_fwd_impl(x, m, c, gamma, beta, residual, /*relu=*/1, eps, momentum, running_mean, running_var, y, save_mean, save_invstd,
+                           workspace, coef, fmt, q, stream);
 }
 
 extern "C" int slfp_bn_act_bwd(const float* gy, const float* x, const float* y, size_t m, int c, const float* gamma, const float* beta,

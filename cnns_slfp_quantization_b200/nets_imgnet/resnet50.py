@@ -37,12 +37,13 @@ class Bottleneck(nn.Module):
     def forward(self, x):
         # relu(bn(conv)) / relu(bn3(conv3) + identity) as in the reference (nets_imgnet/resnet50.py:71-88); in training mode on
         # the GPU each BatchNorm (+ add) (+ ReLU) group is one fused op (utils/bn_act.py), otherwise the stock modules run
+        # (`consumers`: the fused op also writes the activation codes its readers would otherwise compute in a pass of their own)
         identity = x
-        out = bn_act(self.conv1(x), self.bn1)
-        out = bn_act(self.conv2(out), self.bn2)
+        out = bn_act(self.conv1(x), self.bn1, consumers=(self.conv2,))
+        out = bn_act(self.conv2(out), self.bn2, consumers=(self.conv3,))
         if self.downsample is not None:
             identity = bn_act(self.downsample[0](x), self.downsample[1], relu=False)
-        return bn_act(self.conv3(out), self.bn3, relu=True, residual=identity)
+        return bn_act(self.conv3(out), self.bn3, relu=True, residual=identity, consumers=self.__dict__.get("_readers", ()))
 
 
 class ResNet50(nn.Module):
@@ -63,6 +64,9 @@ class ResNet50(nn.Module):
                                         downsample_idx=off if b == 0 else None))
                 inplanes = planes * Bottleneck.expansion
             setattr(self, f"layer{li}", nn.Sequential(*layer))
+        blocks = [b for li in range(1, 5) for b in getattr(self, f"layer{li}")]
+        for b, nxt in zip(blocks, blocks[1:]):                     # readers of a block's output (kept out of the module tree)
+            b.__dict__["_readers"] = (nxt.conv1,) + ((nxt.downsample[0],) if nxt.downsample is not None else ())
         self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
         self.fc = ops.linear_Q(q_bit=qbit, Kw=Kw[53], Ka=Ka[53])(inplanes, num_classes)
         for m in self.modules():                                   # nets_imgnet/resnet50.py:149-154

@@ -9,6 +9,7 @@ channels-last float32 tensors Conv2d_Q returns.  Anything the kernels do not cov
 no running statistics, momentum=None, channel counts that are not multiples of 4, SLFP_NO_FUSED_BN=1) takes the stock
 modules, so the function is always safe to call.
 """
+import ctypes
 import os
 
 import torch
@@ -34,7 +35,9 @@ class _BnAct(torch.autograd.Function):
     """x, residual: [N, H, W, C] float32 contiguous (NHWC).  Returns y of the same shape."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps, momentum, relu, quant=None):
+        """quant: None or (fmt, [k_div, ...]) - the kernel also writes the codes of y / k_div for each scale (returned
+        through quant[2], a list: code tensors are not autograd outputs)."""
         lib = _nv.lib()
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
@@ -45,9 +48,20 @@ class _BnAct(torch.autograd.Function):
         invstd = torch.empty(c, dtype=torch.float32, device=x.device)
         ws = _workspace(x.device, c)
         coef = torch.empty(4 * c, dtype=torch.float32, device=x.device)
-        _nv.check(lib.slfp_bn_act_fwd_train(x.data_ptr(), m, c, weight.data_ptr(), bias.data_ptr(), _nv.ptr(res), int(relu), eps,
-                                            momentum, _nv.ptr(running_mean), _nv.ptr(running_var), y.data_ptr(), mean.data_ptr(),
-                                            invstd.data_ptr(), ws.data_ptr(), coef.data_ptr(), _nv.stream()))
+        if quant is not None and relu:
+            fmt, kdivs, out = quant
+            codes = [torch.empty(x.shape, dtype=torch.uint8, device=x.device) for _ in kdivs]
+            ks = (ctypes.c_float * len(kdivs))(*kdivs)
+            ps = (ctypes.c_void_p * len(kdivs))(*[t.data_ptr() for t in codes])
+            _nv.check(lib.slfp_bn_act_fwd_train_quant(x.data_ptr(), m, c, weight.data_ptr(), bias.data_ptr(), _nv.ptr(res), eps, momentum,
+                                                      _nv.ptr(running_mean), _nv.ptr(running_var), y.data_ptr(), mean.data_ptr(),
+                                                      invstd.data_ptr(), ws.data_ptr(), coef.data_ptr(), fmt, len(kdivs), ks, ps,
+                                                      _nv.stream()))
+            out.extend(codes)
+        else:
+            _nv.check(lib.slfp_bn_act_fwd_train(x.data_ptr(), m, c, weight.data_ptr(), bias.data_ptr(), _nv.ptr(res), int(relu), eps,
+                                                momentum, _nv.ptr(running_mean), _nv.ptr(running_var), y.data_ptr(), mean.data_ptr(),
+                                                invstd.data_ptr(), ws.data_ptr(), coef.data_ptr(), _nv.stream()))
         # the ReLU mask of a layer without residual is recomputed from x in the backward: y is not kept alive
         ctx.save_for_backward(x, y if (relu and res is not None) else None, weight, bias, mean, invstd)
         ctx.relu, ctx.has_res = bool(relu), res is not None
@@ -69,7 +83,7 @@ class _BnAct(torch.autograd.Function):
         _nv.check(lib.slfp_bn_act_bwd(gy.data_ptr(), x.data_ptr(), _nv.ptr(y), m, c, weight.data_ptr(), bias.data_ptr(), mean.data_ptr(),
                                       invstd.data_ptr(), int(ctx.relu), dx.data_ptr(), _nv.ptr(dres), dgamma.data_ptr(),
                                       dbeta.data_ptr(), ws.data_ptr(), coef.data_ptr(), _nv.stream()))
-        return dx, dgamma, dbeta, dres, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
 def fused_ok(bn, x):
@@ -78,9 +92,21 @@ def fused_ok(bn, x):
             and not os.environ.get("SLFP_NO_FUSED_BN"))
 
 
-def bn_act(x, bn, relu=True, residual=None):
+def _consumer_key(conv):
+    """(k_div as float32, activation format) of a Conv2d_Q that can take ready-made codes, else None."""
+    import numpy as np
+    if getattr(conv, "q_bit", None) not in (7, 8) or getattr(conv, "groups", 1) != 1 or conv.in_channels % 16:
+        return None
+    return float(np.float32(float(conv.Ka))), _nv.fmt_for(conv.q_bit, "act")
+
+
+def bn_act(x, bn, relu=True, residual=None, consumers=()):
     """relu?(bn(x) + residual?) for an nn.BatchNorm2d module `bn` and NCHW-shaped tensors (channels-last memory is used
-    as is; other layouts are converted)."""
+    as is; other layouts are converted).
+
+    consumers: the Conv2d_Q modules that will read the result.  With relu=True the fused kernel also writes their
+    activation codes (quantize_act(y / Ka), one code tensor per distinct Ka, at most two) and attaches them to the
+    returned tensor (`._slfp_codes`); Conv2d_Q.forward picks them up instead of quantizing y again."""
     if not fused_ok(bn, x):
         out = bn(x)
         if residual is not None:
@@ -89,5 +115,16 @@ def bn_act(x, bn, relu=True, residual=None):
     bn.num_batches_tracked.add_(1)
     xn = x.permute(0, 2, 3, 1)
     rn = residual.permute(0, 2, 3, 1) if residual is not None else None
-    y = _BnAct.apply(xn, bn.weight, bn.bias, rn, bn.running_mean, bn.running_var, float(bn.eps), float(bn.momentum), bool(relu))
-    return y.permute(0, 3, 1, 2)
+    quant, keys = None, []
+    if relu and consumers and not os.environ.get("SLFP_NO_FUSED_ACT_QUANT"):
+        for cv in consumers:
+            k = _consumer_key(cv)
+            if k is not None and k not in keys:
+                keys.append(k)
+        if keys and len(keys) <= 2 and len({f for _, f in keys}) == 1 and x.shape[1] % 16 == 0:
+            quant = (keys[0][1], [k for k, _ in keys], [])
+    y = _BnAct.apply(xn, bn.weight, bn.bias, rn, bn.running_mean, bn.running_var, float(bn.eps), float(bn.momentum), bool(relu), quant)
+    out = y.permute(0, 3, 1, 2)
+    if quant is not None and quant[2]:
+        out._slfp_codes = {key: t for key, t in zip(keys, quant[2])}
+    return out

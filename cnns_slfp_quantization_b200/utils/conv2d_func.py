@@ -58,7 +58,7 @@ class _QConvNHWC(torch.autograd.Function):
     Returns y: [N,Ho,Wo,K] float32 contiguous."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias_q, cfg):
+    def forward(ctx, x, weight, bias_q, cfg, x_codes=None):
         lib = _nv.lib()
         _nv.require_cuda(x, "Conv2d_Q / Linear_Q input")
         _nv.require_cuda(weight, "Conv2d_Q / Linear_Q weight")
@@ -80,8 +80,10 @@ class _QConvNHWC(torch.autograd.Function):
             raise RuntimeError("Conv2d_Q: output size is too small")
         st = _nv.stream()
         # 1. activations: x / Ka -> 8-bit codes (NHWC, channel-padded)
-        x_codes = torch.empty((N, H, W, Cp), dtype=torch.uint8, device=x.device)
-        _nv.check(lib.slfp_quantize_nhwc_f32(x.data_ptr(), N * H * W, C, Cp, cfg.ka, afmt, x_codes.data_ptr(), st))
+        # (codes that the producer of x already wrote - utils/bn_act.py, same quantizer, same Ka - are used as they are)
+        if x_codes is None or tuple(x_codes.shape) != (N, H, W, Cp) or x_codes.dtype != torch.uint8:
+            x_codes = torch.empty((N, H, W, Cp), dtype=torch.uint8, device=x.device)
+            _nv.check(lib.slfp_quantize_nhwc_f32(x.data_ptr(), N * H * W, C, Cp, cfg.ka, afmt, x_codes.data_ptr(), st))
         # 2. weights: w / Kw -> codes (+ the float16 tensor-core operand), KRSC
         pitch = lib.slfp_conv_wpitch(ctypes_byref(d))
         w_codes = torch.empty((K * pitch,), dtype=torch.uint8, device=x.device)
@@ -123,7 +125,7 @@ class _QConvNHWC(torch.autograd.Function):
         cfg, d = ctx.cfg, ctx.desc
         gy = gy.contiguous()
         K, Cg, R, S = ctx.wshape
-        need_x, need_w, _, _ = ctx.needs_input_grad
+        need_x, need_w = ctx.needs_input_grad[:2]
         dx = torch.empty((d.n, d.h, d.w, d.c), dtype=torch.float32, device=gy.device) if need_x else None
         dw = torch.empty(ctx.wshape, dtype=torch.float32, device=gy.device) if need_w else None
         db = torch.empty((K,), dtype=torch.float32, device=gy.device) if ctx.has_bias else None
@@ -143,7 +145,7 @@ class _QConvNHWC(torch.autograd.Function):
                                           _nv.ptr(db), _nv.stream()))
         if db is not None:                             # y = (acc + bias_q) * post_a * post_b
             db = (db * cfg.post_b) * cfg.post_a
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 def ctypes_byref(obj):
@@ -214,7 +216,9 @@ def _conv_forward(self, input, bias_q):
     ka, kw = _k32(self.Ka), _k32(self.Kw)
     cfg = _ConvCfg(self.q_bit, ka, kw, tuple(self.stride), tuple(self.padding), tuple(self.dilation), self.groups,
                    ka, kw, keep)
-    y = _QConvNHWC.apply(input.permute(0, 2, 3, 1), self.weight, bias_q, cfg)
+    ready = getattr(input, "_slfp_codes", None)                 # written by the fused BatchNorm + ReLU that produced `input`
+    x_codes = ready.get((ka, _nv.fmt_for(self.q_bit, "act"))) if (ready and self.groups == 1 and not HIGH_FIDELITY) else None
+    y = _QConvNHWC.apply(input.permute(0, 2, 3, 1), self.weight, bias_q, cfg, x_codes)
     return y.permute(0, 3, 1, 2)
 
 

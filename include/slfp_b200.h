@@ -397,6 +397,14 @@ size_t slfp_bn_act_workspace_floats(int c);
 int slfp_bn_act_fwd_train(const float *x, size_t m, int c, const float *gamma, const float *beta, const float *residual,
                           int relu, float eps, float momentum, float *running_mean, float *running_var, float *y,
                           float *save_mean, float *save_invstd, float *workspace, float *coef, slfp_stream_t stream);
+/* The same forward (ReLU always applied) that ALSO emits the activation codes of y for its consumers - the quantizer
+ * `quantize_act(y / Ka)` of the next Conv2d_Q (utils/conv2d_func.py:21), bit-identical to slfp_quantize_nhwc_f32(y) -
+ * for n_codes = 1 or 2 scales k_div[j] (a block output feeds conv1 and the downsample conv of the next block):
+ * codes[j] is [m, c] bytes (c_phys == c), fmt = SLFP_FMT_SFP33 | SLFP_FMT_SLFP34_ACT.  k_div / codes are HOST arrays. */
+int slfp_bn_act_fwd_train_quant(const float *x, size_t m, int c, const float *gamma, const float *beta, const float *residual,
+                                float eps, float momentum, float *running_mean, float *running_var, float *y,
+                                float *save_mean, float *save_invstd, float *workspace, float *coef, int fmt, int n_codes,
+                                const float *k_div, uint8_t *const *codes, slfp_stream_t stream);
 int slfp_bn_act_bwd(const float *gy, const float *x, const float *y, size_t m, int c, const float *gamma, const float *beta,
                     const float *save_mean, const float *save_invstd, int relu, float *dx, float *d_residual,
                     float *dgamma, float *dbeta, float *workspace, float *coef, slfp_stream_t stream);
