@@ -133,6 +133,8 @@ class _QConvNHWC(torch.autograd.Function):
         # dgrad / wgrad as tcgen05 implicit GEMMs (csrc/conv_bwd_sm100.cu); the library never allocates, so the
         # float16 operand images and the split-K accumulator live in a scratch tensor from torch's caching allocator.
         # Shapes the tensor-core path does not cover (grouped, > 32 taps) report 0 bytes and run the direct kernels.
+        if need_w and not need_x and db is None and _folded_stem_wgrad(lib, cfg, d, ctx.wfmt, gy, x_codes, w_codes, dw):
+            return None, dw, None, None, None
         ws_bytes = lib.slfp_conv2d_bwd_workspace_size(ctypes_byref(d), int(need_x), int(need_w))
         if ws_bytes:
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device)
@@ -146,6 +148,48 @@ class _QConvNHWC(torch.autograd.Function):
         if db is not None:                             # y = (acc + bias_q) * post_a * post_b
             db = (db * cfg.post_b) * cfg.post_a
         return dx, dw, db, None, None
+
+
+def _folded_stem_wgrad(lib, cfg, d, wfmt, gy, x_codes, w_codes, dw):
+    """wgrad of a network stem (<= 4 input channels, stride 2, more than 32 taps: ResNet's 7x7/2) on the tensor cores.
+
+    The tensor-core wgrad covers <= 32 taps on c_phys % 64 == 0 channels, so the stem used to fall to a CUDA-core kernel
+    (1.8 ms of the batch-128 QAT step).  A stride-2 RxR convolution on c channels is a stride-1 R2xR2 convolution
+    (R2 = 4 for 7x7 / padding 3) on the 2x2 space-to-depth image with 4c channels - the fold engine.Plan.s2d_stem uses
+    forward: input row 2*ho - P + r = 2*(ho - lo) + (r + off) with lo = ceil(P / 2), off = 2*lo - P, folded tap
+    a = (r + off) // 2, parity dy = (r + off) % 2.  The folded code image is built from the saved codes (byte copies),
+    zero-padded in space (so the folded layer needs no padding) and to 64 channels; the folded gradient is scattered
+    back to [K, c, R, R].  Same function of (gy, codes) as the direct kernel.  Returns False when the shape does not
+    qualify (the caller then takes the generic paths)."""
+    if _os.environ.get("SLFP_NO_FOLDED_STEM_WGRAD"):
+        return False
+    N, H, W, C, Cp, K, R, S = d.n, d.h, d.w, d.c, d.c_phys, d.k, d.r, d.s
+    if not (d.groups == 1 and Cp == 4 and R * S > 32 and R == S and cfg.stride == (2, 2) and cfg.dilation == (1, 1)
+            and cfg.padding[0] == cfg.padding[1] and H % 2 == 0 and W % 2 == 0 and dw.is_contiguous()):
+        return False
+    P = cfg.padding[0]
+    lo = (P + 1) // 2
+    off = 2 * lo - P
+    R2 = (R - 1 + off) // 2 + 1
+    Ho, Wo = gy.shape[1], gy.shape[2]
+    Hp, Wp = Ho + R2 - 1, Wo + R2 - 1
+    if R2 * R2 > 32 or Hp - H // 2 - lo < 0 or Wp - W // 2 - lo < 0:
+        return False
+    d2 = _nv.SlfpConvDesc(N, Hp, Wp, 16, 64, K, R2, R2, 1, 1, 0, 0, 1, 1, 1, d.fmt, 0, 0, 0)
+    ws_bytes = lib.slfp_conv2d_bwd_workspace_size(ctypes_byref(d2), 0, 1)
+    if not ws_bytes:
+        return False
+    # [n, h/2, dy, w/2, dx, 4] -> [n, h/2, w/2, (dy, dx, c4)] inside the zero frame (code 0 decodes to 0)
+    x2 = torch.zeros((N, Hp, Wp, 64), dtype=torch.uint8, device=gy.device)
+    x2[:, lo:lo + H // 2, lo:lo + W // 2, :16] = x_codes.view(N, H // 2, 2, W // 2, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 16)
+    dw2 = torch.empty((K, 16, R2, R2), dtype=torch.float32, device=gy.device)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device)
+    _nv.check(lib.slfp_conv2d_bwd_ws(ctypes_byref(d2), gy.data_ptr(), x2.data_ptr(), w_codes.data_ptr(), wfmt, cfg.ka, cfg.kw, None,
+                                     dw2.data_ptr(), *dw2.stride(), None, ws.data_ptr(), ws_bytes, _nv.stream()))
+    # dw2[k, (dy, dx, c4), a, b] = gradient of wp[k, c4, 2a + dy, 2b + dx];  w = wp[:, :c, off:off + R, off:off + R]
+    wp = dw2.view(K, 2, 2, 4, R2, R2).permute(0, 3, 4, 1, 5, 2).reshape(K, 4, 2 * R2, 2 * R2)
+    dw.copy_(wp[:, :C, off:off + R, off:off + S])
+    return True
 
 
 def ctypes_byref(obj):
