@@ -13,7 +13,7 @@ int conv2d_bwd_direct(const SlfpConvDesc* d, const float* gy, const uint8_t* x_c
 size_t conv2d_bwd_tc_workspace(const SlfpConvDesc* d, int need_dx, int need_dw);
 int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes, int wfmt,
                   float ka, float kw, float* dx, float* dwt, long long so, long long sc, long long sr, long long ss,
-                  float* db, void* workspace, size_t ws_bytes, cudaStream_t st);
+                  float* db, void* workspace, size_t ws_bytes, cudaStream_t st, const float* gy_absmax);
 }  // namespace slfp
 
 using namespace slfp;
@@ -74,5 +74,16 @@ extern "C" int slfp_conv2d_bwd_ws(const SlfpConvDesc* desc, const float* gy, con
     if (rc) return rc;
     if (!gy) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_bwd_ws: null gy");
     return conv2d_bwd_tc(desc, gy, x_codes, w_codes, wfmt, ka, kw, dx, dw, so, sc, sr, ss, db, workspace, workspace_bytes,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int slfp_conv2d_bwd_ws_absmax(const SlfpConvDesc* desc, const float* gy, const float* gy_absmax, const uint8_t* x_codes,
+                                         const uint8_t* w_codes, int wfmt, float ka, float kw, float* dx, float* dw, long long so,
+                                         long long sc, long long sr, long long ss, float* db, void* workspace, size_t workspace_bytes,
+                                         slfp_stream_t stream) {
+    int rc = check_desc(desc, "slfp_conv2d_bwd_ws_absmax");
+    if (rc) return rc;
+    if (!gy) return set_error(SLFP_ERR_BAD_ARG, "slfp_conv2d_bwd_ws_absmax: null gy");
+    return conv2d_bwd_tc(desc, gy, x_codes, w_codes, wfmt, ka, kw, dx, dw, so, sc, sr, ss, db, workspace, workspace_bytes,
+                         (cudaStream_t)stream, gy_absmax);
 }

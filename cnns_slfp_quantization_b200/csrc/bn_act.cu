@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const float* __re
                                                                float* __restrict__ running_var, float* __restrict__ save_mean,
                                                                float* __restrict__ save_invstd, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, float* __restrict__ ws,
-                                                               float* __restrict__ coef) {
+                                                               float* __restrict__ coef, float* __restrict__ dx_absmax) {
     __shared__ float4 s_a[kBnThreads], s_b[kBnThreads];
     __shared__ bool s_last;
     const int tx = threadIdx.x % g.CT, ty = threadIdx.x / g.CT;
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const float* __re
     if (!s_last) return;
     __threadfence();
     const double inv_m = 1.0 / (double)g.M;
+    if (MODE == 1 && dx_absmax && threadIdx.x == 0) *dx_absmax = 0.f;     // bn_bwd_apply_kernel accumulates max |dx| into it
     for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
         const double a = __ldcg(acc + c), b = __ldcg(acc + g.C + c);
         acc[c] = 0.0; acc[g.C + c] = 0.0;                                 // self-cleaning
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* _
                                                                   const float* __restrict__ y, size_t n4, int C4, int relu,
                                                                   const float* __restrict__ coef, int C,
                                                                   const float* __restrict__ save_mean, float* __restrict__ dx,
-                                                                  float* __restrict__ dres) {
+                                                                  float* __restrict__ dres, float* __restrict__ dx_absmax) {
+    float amax = 0.f;
     for (size_t i = (size_t)blockIdx.x * kBnThreads + threadIdx.x; i < n4; i += (size_t)gridDim.x * kBnThreads) {
         const int c4 = (C4 & (C4 - 1)) == 0 ? (int)(i & (size_t)(C4 - 1)) : (int)(i % (size_t)C4);
         float4 g = ldg_stream(reinterpret_cast<const float4*>(gy) + i);
@@ -222,6 +224,17 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* _
         o.w = a.w * ((g.w - b.w) - (v.w - m.w) * c.w);
         reinterpret_cast<float4*>(dx)[i] = o;
         if (dres) reinterpret_cast<float4*>(dres)[i] = g;
+        // max |dx| on the bit patterns (non-negative floats order like unsigned integers; NaN / Inf order above everything,
+        // like slfp_absmax_f32): the convolution that receives dx as its gy skips its own abs-max pass
+        const uint32_t m01 = max(__float_as_uint(o.x) & 0x7fffffffu, __float_as_uint(o.y) & 0x7fffffffu);
+        const uint32_t m23 = max(__float_as_uint(o.z) & 0x7fffffffu, __float_as_uint(o.w) & 0x7fffffffu);
+        amax = __uint_as_float(max(__float_as_uint(amax), max(m01, m23)));
+    }
+    if (dx_absmax) {
+        uint32_t m = __float_as_uint(amax);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned int*>(dx_absmax), m);
     }
 }
 
@@ -260,7 +273,7 @@ static int bn_act_fwd_impl(const float* x, size_t m, int c, const float* gamma, 
     if ((running_mean == nullptr) != (running_var == nullptr)) return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: running statistics come in pairs");
     cudaStream_t st = (cudaStream_t)stream;
     bn_reduce_kernel<0><<<grid, kBnThreads, 0, st>>>(x, nullptr, nullptr, g, 0, gamma, beta, eps, momentum, running_mean, running_var,
-                                                     save_mean, save_invstd, nullptr, nullptr, workspace, coef);
+                                                     save_mean, save_invstd, nullptr, nullptr, workspace, coef, nullptr);
     if (int rc = check_launch("bn_reduce_kernel<0>")) return rc;
     const size_t n4 = m * (size_t)g.C4;
     const int ag = (int)min((size_t)num_sms() * 8, (n4 + kBnThreads - 1) / kBnThreads);
@@ -298,7 +311,7 @@ extern "C" int slfp_bn_act_fwd_train_quant(const float* x, size_t m, int c, cons
 
 extern "C" int slfp_bn_act_bwd(const float* gy, const float* x, const float* y, size_t m, int c, const float* gamma, const float* beta,
                                const float* save_mean, const float* save_invstd, int relu, float* dx, float* d_residual,
-                               float* dgamma, float* dbeta, float* workspace, float* coef, slfp_stream_t stream) {
+                               float* dgamma, float* dbeta, float* workspace, float* coef, float* dx_absmax, slfp_stream_t stream) {
     if (m == 0) return 0;
     if (!gy || !x || (relu && !y && !beta) || !gamma || !save_mean || !save_invstd || !dx || !dgamma || !dbeta || !workspace || !coef)
         return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_bwd: null pointer");
@@ -308,10 +321,10 @@ extern "C" int slfp_bn_act_bwd(const float* gy, const float* x, const float* y, 
         return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_bwd: needs c %% 4 == 0 and 16-byte aligned tensors");
     cudaStream_t st = (cudaStream_t)stream;
     bn_reduce_kernel<1><<<grid, kBnThreads, 0, st>>>(x, gy, y, g, relu, gamma, beta, 0.f, 0.f, nullptr, nullptr,
-                                                     const_cast<float*>(save_mean), const_cast<float*>(save_invstd), dgamma, dbeta, workspace, coef);
+                                                     const_cast<float*>(save_mean), const_cast<float*>(save_invstd), dgamma, dbeta, workspace, coef, dx_absmax);
     if (int rc = check_launch("bn_reduce_kernel<1>")) return rc;
     const size_t n4 = m * (size_t)g.C4;
     const int ag = (int)min((size_t)num_sms() * 8, (n4 + kBnThreads - 1) / kBnThreads);
-    bn_bwd_apply_kernel<<<ag, kBnThreads, 0, st>>>(gy, x, y, n4, g.C4, relu, coef, c, save_mean, dx, d_residual);
+    bn_bwd_apply_kernel<<<ag, kBnThreads, 0, st>>>(gy, x, y, n4, g.C4, relu, coef, c, save_mean, dx, d_residual, dx_absmax);
     return check_launch("bn_bwd_apply_kernel");
 }

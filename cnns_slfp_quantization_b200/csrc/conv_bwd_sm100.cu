@@ -476,7 +476,7 @@ size_t conv2d_bwd_tc_workspace(const SlfpConvDesc* d, int need_dx, int need_dw) 
 
 int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes, const uint8_t* w_codes, int wfmt,
                   float ka, float kw, float* dx, float* dwt, long long so, long long sc, long long sr, long long ss,
-                  float* db, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                  float* db, void* workspace, size_t ws_bytes, cudaStream_t st, const float* gy_absmax) {
     using namespace bwd;
     const Layout L = plan(d, dx != nullptr, dwt != nullptr);
     if (L.total == 0 || !workspace || ws_bytes < L.total || (((uintptr_t)workspace) & 255u))
@@ -492,7 +492,10 @@ int conv2d_bwd_tc(const SlfpConvDesc* d, const float* gy, const uint8_t* x_codes
     const size_t mout = (size_t)d->n * Ho * Wo;
     int rc;
     // G = float16(gy * 2^e)
-    if ((rc = slfp_absmax_f32(gy, mout * d->k, scale, 1, (slfp_stream_t)st))) return rc;
+    if (gy_absmax) {                                         // max |gy| already known on the device (the kernel that wrote gy tracked it)
+        cudaError_t e = cudaMemcpyAsync(scale, gy_absmax, sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return set_error((int)e, "conv2d_bwd: copy of the gradient abs-max: %s", cudaGetErrorString(e));
+    } else if ((rc = slfp_absmax_f32(gy, mout * d->k, scale, 1, (slfp_stream_t)st))) return rc;
     {
         const size_t tot = mout * (Kp / 8);
         const int grid = (int)std::min<size_t>((size_t)num_sms() * 16, ceil_div_sz(tot, 256));

@@ -80,9 +80,11 @@ class _BnAct(torch.autograd.Function):
         dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
         ws = _workspace(x.device, c)
         coef = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+        amax = torch.empty(1, dtype=torch.float32, device=x.device)           # zeroed by the reduce kernel
         _nv.check(lib.slfp_bn_act_bwd(gy.data_ptr(), x.data_ptr(), _nv.ptr(y), m, c, weight.data_ptr(), bias.data_ptr(), mean.data_ptr(),
                                       invstd.data_ptr(), int(ctx.relu), dx.data_ptr(), _nv.ptr(dres), dgamma.data_ptr(),
-                                      dbeta.data_ptr(), ws.data_ptr(), coef.data_ptr(), _nv.stream()))
+                                      dbeta.data_ptr(), ws.data_ptr(), coef.data_ptr(), amax.data_ptr(), _nv.stream()))
+        _nv.pending_grad_absmax = (dx.data_ptr(), dx.numel(), amax)
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
 

@@ -133,14 +133,18 @@ class _QConvNHWC(torch.autograd.Function):
         # dgrad / wgrad as tcgen05 implicit GEMMs (csrc/conv_bwd_sm100.cu); the library never allocates, so the
         # float16 operand images and the split-K accumulator live in a scratch tensor from torch's caching allocator.
         # Shapes the tensor-core path does not cover (grouped, > 32 taps) report 0 bytes and run the direct kernels.
-        if need_w and not need_x and db is None and _folded_stem_wgrad(lib, cfg, d, ctx.wfmt, gy, x_codes, w_codes, dw):
+        # max |gy| tracked by the kernel that wrote gy (fused BatchNorm backward): the tensor-core paths skip their abs-max pass
+        hint, _nv.pending_grad_absmax = _nv.pending_grad_absmax, None
+        amax = hint[2] if (hint is not None and hint[0] == gy.data_ptr() and hint[1] == gy.numel()
+                           and not _os.environ.get("SLFP_NO_ABSMAX_HINT")) else None
+        if need_w and not need_x and db is None and _folded_stem_wgrad(lib, cfg, d, ctx.wfmt, gy, amax, x_codes, w_codes, dw):
             return None, dw, None, None, None
         ws_bytes = lib.slfp_conv2d_bwd_workspace_size(ctypes_byref(d), int(need_x), int(need_w))
         if ws_bytes:
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device)
-            _nv.check(lib.slfp_conv2d_bwd_ws(ctypes_byref(d), gy.data_ptr(), x_codes.data_ptr(), w_codes.data_ptr(), ctx.wfmt,
-                                             cfg.ka, cfg.kw, _nv.ptr(dx), _nv.ptr(dw), so, sc, sr, ss,
-                                             _nv.ptr(db), ws.data_ptr(), ws_bytes, _nv.stream()))
+            _nv.check(lib.slfp_conv2d_bwd_ws_absmax(ctypes_byref(d), gy.data_ptr(), _nv.ptr(amax), x_codes.data_ptr(), w_codes.data_ptr(),
+                                                    ctx.wfmt, cfg.ka, cfg.kw, _nv.ptr(dx), _nv.ptr(dw), so, sc, sr, ss,
+                                                    _nv.ptr(db), ws.data_ptr(), ws_bytes, _nv.stream()))
         else:
             _nv.check(lib.slfp_conv2d_bwd(ctypes_byref(d), gy.data_ptr(), x_codes.data_ptr(), w_codes.data_ptr(), ctx.wfmt,
                                           cfg.ka, cfg.kw, _nv.ptr(dx), _nv.ptr(dw), so, sc, sr, ss,
@@ -150,7 +154,7 @@ class _QConvNHWC(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
-def _folded_stem_wgrad(lib, cfg, d, wfmt, gy, x_codes, w_codes, dw):
+def _folded_stem_wgrad(lib, cfg, d, wfmt, gy, gy_absmax, x_codes, w_codes, dw):
     """wgrad of a network stem (<= 4 input channels, stride 2, more than 32 taps: ResNet's 7x7/2) on the tensor cores.
 
     The tensor-core wgrad covers <= 32 taps on c_phys % 64 == 0 channels, so the stem used to fall to a CUDA-core kernel
@@ -184,8 +188,9 @@ def _folded_stem_wgrad(lib, cfg, d, wfmt, gy, x_codes, w_codes, dw):
     x2[:, lo:lo + H // 2, lo:lo + W // 2, :16] = x_codes.view(N, H // 2, 2, W // 2, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 16)
     dw2 = torch.empty((K, 16, R2, R2), dtype=torch.float32, device=gy.device)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device)
-    _nv.check(lib.slfp_conv2d_bwd_ws(ctypes_byref(d2), gy.data_ptr(), x2.data_ptr(), w_codes.data_ptr(), wfmt, cfg.ka, cfg.kw, None,
-                                     dw2.data_ptr(), *dw2.stride(), None, ws.data_ptr(), ws_bytes, _nv.stream()))
+    _nv.check(lib.slfp_conv2d_bwd_ws_absmax(ctypes_byref(d2), gy.data_ptr(), _nv.ptr(gy_absmax), x2.data_ptr(), w_codes.data_ptr(), wfmt,
+                                            cfg.ka, cfg.kw, None, dw2.data_ptr(), *dw2.stride(), None, ws.data_ptr(), ws_bytes,
+                                            _nv.stream()))
     # dw2[k, (dy, dx, c4), a, b] = gradient of wp[k, c4, 2a + dy, 2b + dx];  w = wp[:, :c, off:off + R, off:off + R]
     wp = dw2.view(K, 2, 2, 4, R2, R2).permute(0, 3, 4, 1, 5, 2).reshape(K, 4, 2 * R2, 2 * R2)
     dw.copy_(wp[:, :C, off:off + R, off:off + S])

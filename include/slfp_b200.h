@@ -340,6 +340,13 @@ int slfp_conv2d_bwd_ws(const SlfpConvDesc *desc, const float *gy, const uint8_t 
                        long long dw_stride_o, long long dw_stride_c, long long dw_stride_r,
                        long long dw_stride_s, float *db, void *workspace, size_t workspace_bytes,
                        slfp_stream_t stream);
+/* slfp_conv2d_bwd_ws with max |gy| supplied by the caller (device scalar written by the kernel that produced gy, e.g.
+ * slfp_bn_act_bwd): the tensor-core path scales gy by it for its float16 operand and skips its own abs-max pass.
+ * gy_absmax == NULL: same as slfp_conv2d_bwd_ws. */
+int slfp_conv2d_bwd_ws_absmax(const SlfpConvDesc *desc, const float *gy, const float *gy_absmax, const uint8_t *x_codes,
+                              const uint8_t *w_codes, int wfmt, float ka, float kw, float *dx, float *dw, long long so,
+                              long long sc, long long sr, long long ss, float *db, void *workspace, size_t workspace_bytes,
+                              slfp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Activations: STLFunction / STL, Swish, Sigmoid (utils/activation_func.py:6-36).
@@ -392,7 +399,9 @@ int slfp_avgpool_quantize_nhwc_f16(const void *x, int n, int hw, int c, float *y
  * vector of 4 * c floats, 16-byte aligned, no initialisation (per call: it is read by the second kernel of the call).
  * Backward: dx [m, c], d_residual [m, c] (optional: the gradient of the residual input), dgamma / dbeta [c].  The ReLU
  * mask comes from y; for a layer without residual y may be NULL and beta given instead: the mask is then recomputed
- * from x with the forward's own scale / shift arithmetic (one read pass less, y need not be kept). */
+ * from x with the forward's own scale / shift arithmetic (one read pass less, y need not be kept).  dx_absmax
+ * (optional device scalar) receives max |dx| - what slfp_absmax_f32(dx) would compute in a pass of its own - for
+ * slfp_conv2d_bwd_ws_absmax of the convolution that produced x. */
 size_t slfp_bn_act_workspace_floats(int c);
 int slfp_bn_act_fwd_train(const float *x, size_t m, int c, const float *gamma, const float *beta, const float *residual,
                           int relu, float eps, float momentum, float *running_mean, float *running_var, float *y,
@@ -407,7 +416,7 @@ int slfp_bn_act_fwd_train_quant(const float *x, size_t m, int c, const float *ga
                                 const float *k_div, uint8_t *const *codes, slfp_stream_t stream);
 int slfp_bn_act_bwd(const float *gy, const float *x, const float *y, size_t m, int c, const float *gamma, const float *beta,
                     const float *save_mean, const float *save_invstd, int relu, float *dx, float *d_residual,
-                    float *dgamma, float *dbeta, float *workspace, float *coef, slfp_stream_t stream);
+                    float *dgamma, float *dbeta, float *workspace, float *coef, float *dx_absmax, slfp_stream_t stream);
 
 /* Debug aid: a host-mapped buffer (>= 16 bytes) into which a timed-out barrier wait of the dense conv kernel
  * records which wait it was before it traps (the kernels never hang: every wait is bounded).  NULL removes it. */
