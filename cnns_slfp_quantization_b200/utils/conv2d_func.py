@@ -58,7 +58,7 @@ class _QConvNHWC(torch.autograd.Function):
     Returns y: [N,Ho,Wo,K] float32 contiguous."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias_q, cfg, x_codes=None):
+    def forward(ctx, x, weight, bias_q, cfg, x_codes=None, prepared=None):
         lib = _nv.lib()
         _nv.require_cuda(x, "Conv2d_Q / Linear_Q input")
         _nv.require_cuda(weight, "Conv2d_Q / Linear_Q weight")
@@ -86,10 +86,17 @@ class _QConvNHWC(torch.autograd.Function):
             _nv.check(lib.slfp_quantize_nhwc_f32(x.data_ptr(), N * H * W, C, Cp, cfg.ka, afmt, x_codes.data_ptr(), st))
         # 2. weights: w / Kw -> codes (+ the float16 tensor-core operand), KRSC
         pitch = lib.slfp_conv_wpitch(ctypes_byref(d))
-        w_codes = torch.empty((K * pitch,), dtype=torch.uint8, device=x.device)
-        w_f16 = torch.empty((K * pitch * (2 if hifi else 1),), dtype=torch.float16, device=x.device) if dense else None
+        # (weights re-quantized for the whole net in one launch at the top of its forward: prepare_weights_batched)
+        ready = prepared is not None and dense and not hifi and prepared[2] == Cp and prepared[3] == pitch and prepared[4] == cfg.kw
+        if ready:
+            w_f16, w_codes = prepared[0], prepared[1]
+        else:
+            w_codes = torch.empty((K * pitch,), dtype=torch.uint8, device=x.device)
+            w_f16 = torch.empty((K * pitch * (2 if hifi else 1),), dtype=torch.float16, device=x.device) if dense else None
         so, sc, sr, ss = weight.stride()
-        if hifi:
+        if ready:
+            pass
+        elif hifi:
             # split operands: rows of [hi | lo] halves - the jobs entry point carries the lo placement
             job = (_nv.SlfpWeightJob * 1)()
             job[0].desc, job[0].w, job[0].kw = _ctypes.pointer(d), weight.data_ptr(), cfg.kw
@@ -138,7 +145,7 @@ class _QConvNHWC(torch.autograd.Function):
         amax = hint[2] if (hint is not None and hint[0] == gy.data_ptr() and hint[1] == gy.numel()
                            and not _os.environ.get("SLFP_NO_ABSMAX_HINT")) else None
         if need_w and not need_x and db is None and _folded_stem_wgrad(lib, cfg, d, ctx.wfmt, gy, amax, x_codes, w_codes, dw):
-            return None, dw, None, None, None
+            return None, dw, None, None, None, None
         ws_bytes = lib.slfp_conv2d_bwd_workspace_size(ctypes_byref(d), int(need_x), int(need_w))
         if ws_bytes:
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=gy.device)
@@ -151,7 +158,52 @@ class _QConvNHWC(torch.autograd.Function):
                                           _nv.ptr(db), _nv.stream()))
         if db is not None:                             # y = (acc + bias_q) * post_a * post_b
             db = (db * cfg.post_b) * cfg.post_a
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
+
+
+def prepare_weights_batched(model):
+    """Re-quantize the weights of every dense Conv2d_Q / Linear_Q of `model` in ONE launch (slfp_prepare_weights_jobs)
+    instead of one launch per layer inside each forward (54 launches = 0.69 ms of the ResNet-50 QAT step).  Called by a
+    net at the top of its forward; each layer's next forward consumes its entry exactly once (weights may change
+    between forwards through raw pointers - the revised-SGD kernel - so nothing is cached across forwards).  Layers the
+    job form does not cover (grouped, high-fidelity mode, q_bit 32) prepare their weights themselves as before."""
+    if HIGH_FIDELITY or _os.environ.get("SLFP_NO_BATCHED_WPREP"):
+        return
+    lib = _nv.lib()
+    cache = model.__dict__.get("_slfp_wprep")
+    mods = cache[0] if cache else [m for m in model.modules() if isinstance(m, _QuantTapsMixin) and getattr(m, "q_bit", 32) in (7, 8)
+                                   and getattr(m, "groups", 1) == 1]
+    if not mods or not mods[0].weight.is_cuda:
+        return
+    sig = tuple((m.weight.data_ptr(), float(m.Kw)) for m in mods)
+    if cache is None or cache[1] != sig:
+        wfmt = _nv.fmt_for(mods[0].q_bit, "weight")
+        if any(_nv.fmt_for(m.q_bit, "weight") != wfmt for m in mods):
+            return
+        jobs = (_nv.SlfpWeightJob * len(mods))()
+        descs, metas, off = [], [], 0
+        for m in mods:
+            w = m.weight if m.weight.dim() == 4 else m.weight.view(m.weight.shape[0], m.weight.shape[1], 1, 1)
+            K, C, R, S = w.shape
+            Cp = 4 if C <= 4 else _ceil_to(C, 16)
+            d = _nv.SlfpConvDesc(1, R, S, C, Cp, K, R, S, 1, 1, 0, 0, 1, 1, 1, _nv.fmt_for(m.q_bit, "act"), 0, 0, 0)
+            pitch = lib.slfp_conv_wpitch(ctypes_byref(d))
+            descs.append(d)
+            metas.append((w, K, Cp, pitch, off))
+            off += _ceil_to(K * pitch, 128)
+        dev = mods[0].weight.device
+        f16 = torch.empty((off,), dtype=torch.float16, device=dev)
+        codes = torch.empty((off,), dtype=torch.uint8, device=dev)
+        for j, d, m, (w, K, Cp, pitch, o) in zip(jobs, descs, mods, metas):
+            j.desc, j.w, j.kw = _ctypes.pointer(d), w.data_ptr(), _k32(m.Kw)
+            j.w_stride[:] = w.stride()
+            j.w_f16, j.w_codes = f16[o:o + K * pitch].data_ptr(), codes[o:o + K * pitch].data_ptr()
+        cache = (mods, sig, jobs, descs, metas, f16, codes, wfmt)
+        model.__dict__["_slfp_wprep"] = cache
+    mods, sig, jobs, descs, metas, f16, codes, wfmt = cache
+    _nv.check(lib.slfp_prepare_weights_jobs(len(mods), jobs, wfmt, _nv.stream()))
+    for m, (w, K, Cp, pitch, o) in zip(mods, metas):
+        m.__dict__["_prepared_w"] = (f16[o:o + K * pitch], codes[o:o + K * pitch], Cp, pitch, _k32(m.Kw))
 
 
 def _folded_stem_wgrad(lib, cfg, d, wfmt, gy, gy_absmax, x_codes, w_codes, dw):
@@ -267,7 +319,7 @@ def _conv_forward(self, input, bias_q):
                    ka, kw, keep)
     ready = getattr(input, "_slfp_codes", None)                 # written by the fused BatchNorm + ReLU that produced `input`
     x_codes = ready.get((ka, _nv.fmt_for(self.q_bit, "act"))) if (ready and self.groups == 1 and not HIGH_FIDELITY) else None
-    y = _QConvNHWC.apply(input.permute(0, 2, 3, 1), self.weight, bias_q, cfg, x_codes)
+    y = _QConvNHWC.apply(input.permute(0, 2, 3, 1), self.weight, bias_q, cfg, x_codes, self.__dict__.pop("_prepared_w", None))
     return y.permute(0, 3, 1, 2)
 
 
@@ -341,6 +393,7 @@ def linear_Q(q_bit, Kw, Ka):
             lead = tuple(input.shape[:-1])
             keep["lead"] = lead
             x = input.reshape(-1, 1, 1, self.in_features)
-            y = _QConvNHWC.apply(x, self.weight.view(self.out_features, self.in_features, 1, 1), self.bias_q, cfg)
+            y = _QConvNHWC.apply(x, self.weight.view(self.out_features, self.in_features, 1, 1), self.bias_q, cfg, None,
+                                 self.__dict__.pop("_prepared_w", None))
             return y.reshape(*lead, self.out_features)
     return Linear_Q
