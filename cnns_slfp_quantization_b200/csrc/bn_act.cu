@@ -68,26 +68,42 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const float* __re
     }
     if (active) {
         const size_t stride = (size_t)gridDim.x * g.RT;
-#pragma unroll 4
-        for (size_t r = (size_t)blockIdx.x * g.RT + ty; r < g.M; r += stride) {
-            const size_t o = r * g.C4 + c4;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + o);
-            if (MODE == 0) {
-                sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
-                sb.x += v.x * v.x; sb.y += v.y * v.y; sb.z += v.z * v.z; sb.w += v.w * v.w;
-            } else {
-                float4 gg = __ldg(reinterpret_cast<const float4*>(gy) + o);
-                if (remask) {
-                    gg.x = v.x * sc4.x + sh4.x > 0.f ? gg.x : 0.f; gg.y = v.y * sc4.y + sh4.y > 0.f ? gg.y : 0.f;
-                    gg.z = v.z * sc4.z + sh4.z > 0.f ? gg.z : 0.f; gg.w = v.w * sc4.w + sh4.w > 0.f ? gg.w : 0.f;
-                } else if (relu) {
-                    const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + o);
-                    gg.x = yy.x > 0.f ? gg.x : 0.f; gg.y = yy.y > 0.f ? gg.y : 0.f;
-                    gg.z = yy.z > 0.f ? gg.z : 0.f; gg.w = yy.w > 0.f ? gg.w : 0.f;
+        // U rows per round, every load of a round issued before the arithmetic (a plain unrolled loop keeps its exit test
+        // between the loads: ONE 16-byte load in flight per thread, 3.6 TB/s on the statistics pass - ncu, profiles/r04_final.md);
+        // rows past the end read as zeros, which add nothing to either sum
+        constexpr int U = MODE == 0 ? 8 : 4;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (size_t r0 = (size_t)blockIdx.x * g.RT + ty; r0 < g.M; r0 += stride * U) {
+            float4 v[U], gg[U], yy[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t r = r0 + (size_t)u * stride;
+                const bool in = r < g.M;
+                const size_t o = (in ? r : r0) * g.C4 + c4;
+                v[u] = in ? __ldg(reinterpret_cast<const float4*>(x) + o) : zero4;
+                if (MODE == 1) {
+                    gg[u] = in ? __ldg(reinterpret_cast<const float4*>(gy) + o) : zero4;
+                    if (relu && !remask) yy[u] = in ? __ldg(reinterpret_cast<const float4*>(y) + o) : zero4;
                 }
-                sa.x += gg.x; sa.y += gg.y; sa.z += gg.z; sa.w += gg.w;
-                sb.x += gg.x * (v.x - mean4.x); sb.y += gg.y * (v.y - mean4.y);
-                sb.z += gg.z * (v.z - mean4.z); sb.w += gg.w * (v.w - mean4.w);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (MODE == 0) {
+                    sa.x += v[u].x; sa.y += v[u].y; sa.z += v[u].z; sa.w += v[u].w;
+                    sb.x += v[u].x * v[u].x; sb.y += v[u].y * v[u].y; sb.z += v[u].z * v[u].z; sb.w += v[u].w * v[u].w;
+                } else {
+                    float4 q = gg[u];
+                    if (remask) {
+                        q.x = v[u].x * sc4.x + sh4.x > 0.f ? q.x : 0.f; q.y = v[u].y * sc4.y + sh4.y > 0.f ? q.y : 0.f;
+                        q.z = v[u].z * sc4.z + sh4.z > 0.f ? q.z : 0.f; q.w = v[u].w * sc4.w + sh4.w > 0.f ? q.w : 0.f;
+                    } else if (relu) {
+                        q.x = yy[u].x > 0.f ? q.x : 0.f; q.y = yy[u].y > 0.f ? q.y : 0.f;
+                        q.z = yy[u].z > 0.f ? q.z : 0.f; q.w = yy[u].w > 0.f ? q.w : 0.f;
+                    }
+                    sa.x += q.x; sa.y += q.y; sa.z += q.z; sa.w += q.w;
+                    sb.x += q.x * (v[u].x - mean4.x); sb.y += q.y * (v[u].y - mean4.y);
+                    sb.z += q.z * (v[u].z - mean4.z); sb.w += q.w * (v[u].w - mean4.w);
+                }
             }
         }
     }
@@ -119,32 +135,51 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const float* __re
     __threadfence();
     const double inv_m = 1.0 / (double)g.M;
     if (MODE == 1 && dx_absmax && threadIdx.x == 0) *dx_absmax = 0.f;     // bn_bwd_apply_kernel accumulates max |dx| into it
-    for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
-        const double a = __ldcg(acc + c), b = __ldcg(acc + g.C + c);
-        acc[c] = 0.0; acc[g.C + c] = 0.0;                                 // self-cleaning
-        if (MODE == 0) {
-            const double mean = a * inv_m;
-            double var = b * inv_m - mean * mean;
-            var = var < 0.0 ? 0.0 : var;
-            const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-            save_mean[c] = (float)mean;
-            save_invstd[c] = invstd;
-            const float sc = gamma[c] * invstd;
-            coef[c] = sc;
-            coef[g.C + c] = beta[c] - (float)mean * sc;
-            if (running_mean) {                                           // nn.BatchNorm2d: unbiased variance into the running estimate
-                const double unb = g.M > 1 ? var * ((double)g.M / (double)(g.M - 1)) : var;
-                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    // four channels per thread and round, every load of a round issued before the arithmetic (the loop used to expose
+    // three dependent L2 latencies per channel: 24 us for 2 048 channels, all other SMs idle)
+    for (int c0 = threadIdx.x; c0 < g.C; c0 += 4 * kBnThreads) {
+        double sa[4], sb[4];
+        float gm[4], bt[4], rm[4], rv[4], is[4], sm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * kBnThreads;
+            if (c < g.C) {
+                sa[j] = __ldcg(acc + c); sb[j] = __ldcg(acc + g.C + c);
+                gm[j] = __ldg(gamma + c);
+                bt[j] = (MODE == 0 || remask) ? __ldg(beta + c) : 0.f;
+                if (MODE == 0 && running_mean) { rm[j] = running_mean[c]; rv[j] = running_var[c]; }
+                if (MODE == 1) { is[j] = save_invstd[c]; sm[j] = save_mean[c]; }
             }
-        } else {
-            const float invstd = save_invstd[c];
-            dbeta[c] = (float)a;
-            dgamma[c] = (float)(b * (double)invstd);
-            coef[c] = gamma[c] * invstd;                                       // a
-            coef[g.C + c] = (float)(a * inv_m);                                // b = mean(g)
-            coef[2 * g.C + c] = (float)(b * inv_m * (double)invstd * (double)invstd);   // c = mean(g (x - mean)) / var
-            if (remask) coef[3 * g.C + c] = beta[c] - save_mean[c] * (gamma[c] * invstd);   // the forward's shift (its scale is a)
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * kBnThreads;
+            if (c >= g.C) continue;
+            acc[c] = 0.0; acc[g.C + c] = 0.0;                             // self-cleaning
+            if (MODE == 0) {
+                const double mean = sa[j] * inv_m;
+                double var = sb[j] * inv_m - mean * mean;
+                var = var < 0.0 ? 0.0 : var;
+                const float invstd = 1.0f / sqrtf((float)(var + (double)eps));
+                save_mean[c] = (float)mean;
+                save_invstd[c] = invstd;
+                const float sc = gm[j] * invstd;
+                coef[c] = sc;
+                coef[g.C + c] = bt[j] - (float)mean * sc;
+                if (running_mean) {                                       // nn.BatchNorm2d: unbiased variance into the running estimate
+                    const double unb = g.M > 1 ? var * ((double)g.M / (double)(g.M - 1)) : var;
+                    running_mean[c] = (1.f - momentum) * rm[j] + momentum * (float)mean;
+                    running_var[c] = (1.f - momentum) * rv[j] + momentum * (float)unb;
+                }
+            } else {
+                const float invstd = is[j];
+                dbeta[c] = (float)sa[j];
+                dgamma[c] = (float)(sb[j] * (double)invstd);
+                coef[c] = gm[j] * invstd;                                                       // a
+                coef[g.C + c] = (float)(sa[j] * inv_m);                                         // b = mean(g)
+                coef[2 * g.C + c] = (float)(sb[j] * inv_m * (double)invstd * (double)invstd);   // c = mean(g (x - mean)) / var
+                if (remask) coef[3 * g.C + c] = bt[j] - sm[j] * (gm[j] * invstd);               // the forward's shift (its scale is a)
+            }
         }
     }
 }
