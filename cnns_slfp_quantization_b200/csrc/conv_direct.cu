@@ -949,15 +949,23 @@ __global__ void __launch_bounds__(128) avgpool8_quantize_kernel(const __half* __
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)n * hw * C + c0);
     const size_t pitch = (size_t)(C >> 3);
-#pragma unroll 7
-    for (int i = 0; i < hw; ++i) {
-        const uint4 v = __ldg(xp + (size_t)i * pitch);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // seven pixels per round, all seven loads issued before the adds (an unrolled loop with its exit test between the
+    // iterations keeps ONE load in flight); the sum still runs over the pixels in order
+    for (int i0 = 0; i0 < hw; i0 += 7) {
+        uint4 v[7];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-            acc[2 * j] += f.x;
-            acc[2 * j + 1] += f.y;
+        for (int u = 0; u < 7; ++u) v[u] = i0 + u < hw ? __ldg(xp + (size_t)(i0 + u) * pitch) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            if (i0 + u < hw) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
+            }
         }
     }
     const float fhw = (float)hw;

@@ -135,6 +135,7 @@ class Plan:
         t = self._alloc(n, h, w, c, "codes", kdiv, cp=cp)
         self.ops.append(self._call(self.lib.slfp_quantize_nchw_f32, x_nchw.data_ptr(), n, c, h * w, cp, kdiv, self.afmt,
                                    t.buf.data_ptr()))
+        self._head_ops = len(self.ops)          # Plan.submit_host: everything up to here reads self.input
         return t
 
     def quantize_input_s2d(self, x_nchw, kdiv):
@@ -144,6 +145,7 @@ class Plan:
         t = self._alloc(n, h // 2, w // 2, 4 * c, "codes", kdiv, cp=cp)
         self.ops.append(self._call(self.lib.slfp_quantize_nchw_s2d_f32, x_nchw.data_ptr(), n, c, h, w, cp, kdiv, self.afmt,
                                    t.buf.data_ptr()))
+        self._head_ops = len(self.ops)          # Plan.submit_host: everything up to here reads self.input
         return t
 
     def quantize_input_im2col3x3(self, x_nchw, kdiv):
@@ -157,6 +159,7 @@ class Plan:
         t = _T(buf, n, h, w, c, 4, "q16", kdiv, nv.FMT_F16Q)
         t.qfmt, t.im2col = self.afmt, True
         self.ops.append(self._call(self.lib.slfp_quantize_nchw_im2col3x3_f16q, x_nchw.data_ptr(), n, h, w, kdiv, self.afmt, buf.data_ptr()))
+        self._head_ops = len(self.ops)          # Plan.submit_host: everything up to here reads self.input
         return t
 
     def quantize_input_s2d_f16q(self, x_nchw, kdiv, pad_top, pad_left, pad_bottom, pad_right):
@@ -172,6 +175,7 @@ class Plan:
         t.qfmt, t.pad = self.afmt, (pad_top, pad_left, hp, wp)
         self.ops.append(self._call(self.lib.slfp_quantize_nchw_s2d_f16q, x_nchw.data_ptr(), n, h, w, kdiv, self.afmt, pad_top, pad_left,
                                    hp, wp, buf.data_ptr()))
+        self._head_ops = len(self.ops)          # Plan.submit_host: everything up to here reads self.input
         return t
 
     def s2d_stem(self, conv):
@@ -598,6 +602,56 @@ class Plan:
             self.run()
         self.graph = g
         return g
+
+    # ---- host-buffer pipeline -----------------------------------------------------------------------------------------
+    def capture_host_pipeline(self):
+        """Two CUDA graphs for submit_host(): HEAD = weight re-quantization + the input quantizer (the only reader of
+        self.input), TAIL = every other layer."""
+        h = getattr(self, "_head_ops", 0)
+        if h == 0:
+            raise RuntimeError("engine.Plan: the plan has no input quantizer")
+        self.verify()
+        self.prepare_weights()
+        self.run()
+        torch.cuda.synchronize()
+        gh, gt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.no_grad():
+            with torch.cuda.graph(gh):
+                if not self.static_weights:
+                    self.prepare_weights()
+                for op in self.ops[:h]:
+                    op(nv.stream())
+            with torch.cuda.graph(gt):
+                for op in self.ops[h:]:
+                    op(nv.stream())
+        self._host_graphs = (gh, gt)
+        self._copy_stream = torch.cuda.Stream(device=self.dev)
+        self._ev_ready, self._ev_free = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_free_valid = False
+
+    def submit_host(self, x_host, out_host=None):
+        """One forward from a PINNED host batch [batch, c, h, w] float32, fully asynchronous: the host -> device copy goes
+        straight into the plan's input buffer on a copy stream and only waits for the PREVIOUS submit's input quantizer
+        (the buffer's only reader), so it overlaps that submit's remaining layers; then head graph, tail graph and - if
+        out_host (pinned) is given - the device -> host copy of the logits on the caller's stream.  No staging copy on
+        the device.  Call torch.cuda.synchronize() (or wait on your own event) before reading out_host."""
+        if getattr(self, "_host_graphs", None) is None:
+            self.capture_host_pipeline()
+        gh, gt = self._host_graphs
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self._copy_stream):
+            if self._ev_free_valid:
+                self._copy_stream.wait_event(self._ev_free)
+            self.input.copy_(x_host, non_blocking=True)
+            self._ev_ready.record(self._copy_stream)
+        main.wait_event(self._ev_ready)
+        gh.replay()
+        self._ev_free.record(main)
+        self._ev_free_valid = True
+        gt.replay()
+        if out_host is not None:
+            out_host.copy_(self.output, non_blocking=True)
+        return self.output
 
     def __call__(self, x=None):
         if x is not None and x.data_ptr() != self.input.data_ptr():

@@ -698,3 +698,31 @@ def test_row_staged_weight_encoder_every_mantissa(orc):
         got = codes.cpu().numpy()
         assert np.array_equal(got, want), (e, int((got != want).sum()))
         assert np.array_equal(f16.view(torch.int16).cpu().numpy(), fq.astype(np.float16).view(np.int16)), e
+
+
+def test_host_pipeline_equals_the_single_graph():
+    """Plan.submit_host (H2D straight into the input buffer on a copy stream, head / tail graphs, logits D2H) gives the logits
+    of the single-graph path bit for bit, for a sequence of DIFFERENT batches submitted back to back (the copy of batch i+1
+    overlaps the layers of batch i and must not disturb them)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from cnns_slfp_quantization_b200 import engine, nets_common as nc
+    dev = torch.device("cuda", 0)
+    model = bench.build_model_gpu(224, dev)
+    plan = engine.compile_resnet50(model, 32, 224, device=dev)
+    batches = [nc.synth_images(32, 224, seed=100 + i) for i in range(5)]
+    plan.capture()
+    want = []
+    for b in batches:
+        plan(b.to(dev))
+        torch.cuda.synchronize()
+        want.append(plan.output.clone())
+    assert not torch.equal(want[0], want[1])
+    hosts = [b.pin_memory() for b in batches]
+    outs = [torch.empty(tuple(plan.output.shape), dtype=torch.float32).pin_memory() for _ in batches]
+    for rep in range(3):
+        for h, o in zip(hosts, outs):
+            plan.submit_host(h, o)
+        torch.cuda.synchronize()
+        for i, (o, w) in enumerate(zip(outs, want)):
+            assert torch.equal(o, w.cpu()), (rep, i)
