@@ -89,6 +89,8 @@ _SIGS = {
     "slfp_bn_act_fwd_train_quant": (c_i, [c_vp, c_sz, c_i, c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i,
                                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_void_p), c_vp]),
     "slfp_bn_act_bwd": (c_i, [c_vp, c_vp, c_vp, c_sz, c_i, c_vp, c_vp, c_vp, c_vp, c_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "slfp_maxpool3x3s2_fwd_f32": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_vp, c_vp, c_vp]),
+    "slfp_maxpool3x3s2_bwd_f32": (c_i, [c_vp, c_vp, c_i, c_i, c_i, c_i, c_vp, c_vp]),
     "slfp_debug_set_buffer": (c_i, [c_vp]),
     "slfp_quantize_host_f32": (c_i, [c_vp, c_sz, c_f, c_i, c_vp, c_vp]),
 }
@@ -101,7 +103,7 @@ _lib = None
 # with CUDA events on the launching stream (bench.py's per-kernel roofline pass).
 _LAUNCHING = {"slfp_gather_quantize_runs_f16", "slfp_gather_quantize_f16", "slfp_quantize_dyn_f32", "slfp_prepare_weights_jobs", "slfp_conv2d_fwd_dual", "slfp_quantize_f32", "slfp_quantize_nhwc_f32", "slfp_dequantize", "slfp_absmax_f32", "slfp_prepare_weights",
               "slfp_conv2d_fwd", "slfp_conv2d_bwd", "slfp_conv2d_bwd_ws", "slfp_conv2d_bwd_ws_absmax", "slfp_act_fwd", "slfp_act_bwd", "slfp_sgd_step", "slfp_maxpool_codes",
-              "slfp_avgpool_nhwc", "slfp_avgpool_quantize_nhwc_f16", "slfp_bn_act_fwd_train", "slfp_bn_act_fwd_train_quant", "slfp_bn_act_bwd", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32", "slfp_quantize_nchw_s2d_f16q", "slfp_quantize_nchw_im2col3x3_f16q"}
+              "slfp_avgpool_nhwc", "slfp_avgpool_quantize_nhwc_f16", "slfp_bn_act_fwd_train", "slfp_bn_act_fwd_train_quant", "slfp_bn_act_bwd", "slfp_maxpool3x3s2_fwd_f32", "slfp_maxpool3x3s2_bwd_f32", "slfp_quantize_nchw_f32", "slfp_quantize_nchw_s2d_f32", "slfp_quantize_nchw_s2d_f16q", "slfp_quantize_nchw_im2col3x3_f16q"}
 launch_count = 0
 # (data_ptr, numel, device scalar) of the most recent gradient tensor whose producer tracked max |.| while writing it
 # (utils/bn_act.py backward); the Conv2d_Q backward that receives exactly that tensor uses it and clears the slot

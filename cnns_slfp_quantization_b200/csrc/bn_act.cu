@@ -273,14 +273,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* _
     }
 }
 
-static bool bn_geom(size_t m, int c, BnGeom& g, dim3& grid) {
+// max_blocks: one resident wave of the kernel that runs on the grid (the statistics pass holds 2 CTAs per SM at 89 registers)
+static bool bn_geom(size_t m, int c, BnGeom& g, dim3& grid, int max_blocks = kBnMaxBlocks) {
     if (c <= 0 || (c & 3) || m == 0) return false;
     g.C = c; g.C4 = c / 4; g.M = m;
     g.CT = g.C4 < 256 ? g.C4 : 256;
     g.RT = kBnThreads / g.CT;
     const size_t want = (m + (size_t)g.RT * 4 - 1) / ((size_t)g.RT * 4);  // >= 4 rows per thread before another CTA pays off
     const int gy_ = (g.C4 + 255) / 256;
-    int gx = kBnMaxBlocks / gy_;
+    int gx = max_blocks / gy_;
     if ((size_t)gx > want) gx = (int)want;
     if (gx < 1) gx = 1;
     grid = dim3((unsigned)gx, (unsigned)gy_);
@@ -303,7 +304,7 @@ static int bn_act_fwd_impl(const float* x, size_t m, int c, const float* gamma, 
     if (!x || !gamma || !beta || !y || !save_mean || !save_invstd || !workspace || !coef)
         return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: null pointer");
     BnGeom g; dim3 grid;
-    if (!bn_geom(m, c, g, grid) || ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)workspace | (uintptr_t)save_mean | (uintptr_t)coef) & 15u)))
+    if (!bn_geom(m, c, g, grid, kBnMaxBlocks / 2) || ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)workspace | (uintptr_t)save_mean | (uintptr_t)coef) & 15u)))
         return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: needs c %% 4 == 0 and 16-byte aligned tensors");
     if ((running_mean == nullptr) != (running_var == nullptr)) return set_error(SLFP_ERR_BAD_ARG, "slfp_bn_act_fwd_train: running statistics come in pairs");
     cudaStream_t st = (cudaStream_t)stream;
@@ -362,4 +363,101 @@ extern "C" int slfp_bn_act_bwd(const float* gy, const float* x, const float* y, 
     const int ag = (int)min((size_t)num_sms() * 8, (n4 + kBnThreads - 1) / kBnThreads);
     bn_bwd_apply_kernel<<<ag, kBnThreads, 0, st>>>(gy, x, y, n4, g.C4, relu, coef, c, save_mean, dx, d_residual, dx_absmax);
     return check_launch("bn_bwd_apply_kernel");
+}
+
+// ---- 3x3 / stride 2 / padding 1 max-pool of the QAT step (the ResNet stem pool, nets_imgnet/resnet50.py:237) on float32 NHWC
+// The stock NHWC kernels write 8-byte indices and their backward ran at 0.8 TB/s (0.44 + 0.88 ms of the batch-128 step).
+// Forward: one thread = 4 channels of one output pixel, nine predicated 16-byte loads, the window position of the maximum
+// (PyTorch's rule: scan rows then columns, strict '>', NaN wins; ties keep the first) as ONE byte per element.  Backward:
+// a gather - an input pixel lies in at most 2 x 2 windows; it takes gy of those whose recorded position is its own -
+// deterministic, no atomics, no zero-fill.
+namespace slfp {
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_fwd_f32_kernel(const float* __restrict__ x, int N, int H, int W, int C4, int Ho, int Wo,
+                                                                   float* __restrict__ y, uint32_t* __restrict__ idx) {
+    const size_t total = (size_t)N * Ho * Wo * C4;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int c4 = (int)(i % (size_t)C4);
+        size_t t = i / (size_t)C4;
+        const int wo = (int)(t % (size_t)Wo); t /= (size_t)Wo;
+        const int ho = (int)(t % (size_t)Ho);
+        const int n = (int)(t / (size_t)Ho);
+        float4 v[9];
+        bool ok[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int h = 2 * ho - 1 + r, w = 2 * wo - 1 + s;
+                ok[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
+                v[r * 3 + s] = ok[r * 3 + s] ? __ldg(reinterpret_cast<const float4*>(x) + (((size_t)n * H + h) * W + w) * C4 + c4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        uint32_t k[4] = {9u, 9u, 9u, 9u};
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            if (!ok[p]) continue;
+            const float e[4] = {v[p].x, v[p].y, v[p].z, v[p].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k[j] == 9u || e[j] > m[j] || e[j] != e[j]) { m[j] = e[j]; k[j] = (uint32_t)p; }
+        }
+        reinterpret_cast<float4*>(y)[i] = make_float4(m[0], m[1], m[2], m[3]);
+        idx[i] = k[0] | (k[1] << 8) | (k[2] << 16) | (k[3] << 24);
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_bwd_f32_kernel(const float* __restrict__ gy, const uint32_t* __restrict__ idx, int N,
+                                                                   int H, int W, int C4, int Ho, int Wo, float* __restrict__ dx) {
+    const size_t total = (size_t)N * H * W * C4;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int c4 = (int)(i % (size_t)C4);
+        size_t t = i / (size_t)C4;
+        const int w = (int)(t % (size_t)W); t /= (size_t)W;
+        const int h = (int)(t % (size_t)H);
+        const int n = (int)(t / (size_t)H);
+        // windows whose rows 2 ho - 1 .. 2 ho + 1 contain h: even h -> ho = h / 2 (r = 1); odd h -> (h - 1) / 2 (r = 2), (h + 1) / 2 (r = 0)
+        int hos[2], rs[2], nh = 0, wos[2], ss[2], nw = 0;
+        if (h & 1) { hos[nh] = (h - 1) >> 1; rs[nh++] = 2; if (((h + 1) >> 1) < Ho) { hos[nh] = (h + 1) >> 1; rs[nh++] = 0; } }
+        else if ((h >> 1) < Ho) { hos[nh] = h >> 1; rs[nh++] = 1; }
+        if (w & 1) { wos[nw] = (w - 1) >> 1; ss[nw++] = 2; if (((w + 1) >> 1) < Wo) { wos[nw] = (w + 1) >> 1; ss[nw++] = 0; } }
+        else if ((w >> 1) < Wo) { wos[nw] = w >> 1; ss[nw++] = 1; }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b) {
+                if (hos[a] >= Ho || wos[b] >= Wo) continue;
+                const size_t o = (((size_t)n * Ho + hos[a]) * Wo + wos[b]) * C4 + c4;
+                const uint32_t kk = __ldg(idx + o);
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gy) + o);
+                const uint32_t me = (uint32_t)(rs[a] * 3 + ss[b]);
+                if ((kk & 0xffu) == me) acc.x += g.x;
+                if (((kk >> 8) & 0xffu) == me) acc.y += g.y;
+                if (((kk >> 16) & 0xffu) == me) acc.z += g.z;
+                if ((kk >> 24) == me) acc.w += g.w;
+            }
+        reinterpret_cast<float4*>(dx)[i] = acc;
+    }
+}
+
+}  // namespace slfp
+
+extern "C" int slfp_maxpool3x3s2_fwd_f32(const float* x, int n, int h, int w, int c, float* y, uint8_t* idx, slfp_stream_t stream) {
+    if (!x || !y || !idx || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 3) || ((((uintptr_t)x | (uintptr_t)y) & 15u)) || (((uintptr_t)idx) & 3u))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_maxpool3x3s2_fwd_f32: needs c %% 4 == 0 and aligned tensors");
+    const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
+    const size_t total = (size_t)n * Ho * Wo * (c / 4);
+    const int grid = (int)min((size_t)num_sms() * 8, (total + 255) / 256);
+    maxpool3x3s2_fwd_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, h, w, c / 4, Ho, Wo, y, reinterpret_cast<uint32_t*>(idx));
+    return check_launch("maxpool3x3s2_fwd_f32_kernel");
+}
+
+extern "C" int slfp_maxpool3x3s2_bwd_f32(const float* gy, const uint8_t* idx, int n, int h, int w, int c, float* dx, slfp_stream_t stream) {
+    if (!gy || !dx || !idx || n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 3) || ((((uintptr_t)gy | (uintptr_t)dx) & 15u)) || (((uintptr_t)idx) & 3u))
+        return set_error(SLFP_ERR_BAD_ARG, "slfp_maxpool3x3s2_bwd_f32: needs c %% 4 == 0 and aligned tensors");
+    const int Ho = (h + 2 - 3) / 2 + 1, Wo = (w + 2 - 3) / 2 + 1;
+    const size_t total = (size_t)n * h * w * (c / 4);
+    const int grid = (int)min((size_t)num_sms() * 8, (total + 255) / 256);
+    maxpool3x3s2_bwd_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, reinterpret_cast<const uint32_t*>(idx), n, h, w, c / 4, Ho, Wo, dx);
+    return check_launch("maxpool3x3s2_bwd_f32_kernel");
 }

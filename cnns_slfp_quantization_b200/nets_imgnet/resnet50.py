@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from ..nets_common import product_ops, reference_scales
-from ..utils.bn_act import bn_act
+from ..utils.bn_act import bn_act, flush_batch_counters, maxpool_train
 from ..utils.conv2d_func import prepare_weights_batched
 
 _STAGES = ((64, 3, 1, 1), (128, 4, 2, 11), (256, 6, 2, 24), (512, 3, 2, 43))   # planes, blocks, stride, scale offset
@@ -80,7 +80,8 @@ class ResNet50(nn.Module):
     def forward(self, x):
         if x.is_cuda and self.qbit in (7, 8):
             prepare_weights_batched(self)                          # all 54 layers' weight re-quantization in one launch
-        x = self.maxpool(bn_act(self.conv1(x), self.bn1))
+        x = maxpool_train(bn_act(self.conv1(x), self.bn1), self.maxpool)
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         x = torch.flatten(self.avgpool(x), 1)
+        flush_batch_counters()                                     # the BatchNorm layers' num_batches_tracked, one launch
         return self.fc(x)

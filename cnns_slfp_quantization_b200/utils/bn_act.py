@@ -88,6 +88,19 @@ class _BnAct(torch.autograd.Function):
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
+_pending_counters = {}
+
+
+def flush_batch_counters():
+    """nn.BatchNorm2d increments num_batches_tracked once per training forward - 53 one-element launches per ResNet-50
+    step when done layer by layer.  bn_act() queues the counters; the net calls this once at the end of its forward (any
+    reader of the counters - state_dict(), a checkpoint - after a forward that did not flush should call it first)."""
+    global _pending_counters
+    if _pending_counters:
+        todo, _pending_counters = list(_pending_counters.values()), {}
+        torch._foreach_add_([t for t, _ in todo], [k for _, k in todo])
+
+
 def fused_ok(bn, x):
     return (bn.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and bn.affine and bn.track_running_stats
             and bn.momentum is not None and bn.num_features % 4 == 0 and bn.weight.dtype == torch.float32
@@ -114,7 +127,14 @@ def bn_act(x, bn, relu=True, residual=None, consumers=()):
         if residual is not None:
             out = out + residual
         return F.relu(out) if relu else out
-    bn.num_batches_tracked.add_(1)
+    t = bn.num_batches_tracked                               # += 1, flushed in one launch (flush_batch_counters)
+    ent = _pending_counters.get(id(t))
+    if ent is None:
+        _pending_counters[id(t)] = [t, 1]
+    else:
+        ent[1] += 1
+    if len(_pending_counters) >= 512:
+        flush_batch_counters()
     xn = x.permute(0, 2, 3, 1)
     rn = residual.permute(0, 2, 3, 1) if residual is not None else None
     quant, keys = None, []
@@ -130,3 +150,45 @@ def bn_act(x, bn, relu=True, residual=None, consumers=()):
     if quant is not None and quant[2]:
         out._slfp_codes = {key: t for key, t in zip(keys, quant[2])}
     return out
+
+
+class _MaxPool3x3s2(torch.autograd.Function):
+    """x: [N, H, W, C] float32 contiguous -> [N, Ho, Wo, C]; the window positions of the maxima (one byte each) are kept
+    for the gather backward (csrc/bn_act.cu)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _nv.lib()
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        y = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device)
+        idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+        _nv.check(lib.slfp_maxpool3x3s2_fwd_f32(x.data_ptr(), n, h, w, c, y.data_ptr(), idx.data_ptr(), _nv.stream()))
+        ctx.save_for_backward(idx)
+        ctx.shape = (n, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _nv.lib()
+        (idx,) = ctx.saved_tensors
+        n, h, w, c = ctx.shape
+        gy = gy.contiguous()
+        dx = torch.empty((n, h, w, c), dtype=torch.float32, device=gy.device)
+        _nv.check(lib.slfp_maxpool3x3s2_bwd_f32(gy.data_ptr(), idx.data_ptr(), n, h, w, c, dx.data_ptr(), _nv.stream()))
+        _nv.pending_grad_absmax = None
+        return dx
+
+
+def maxpool_train(x, pool):
+    """`pool(x)` for an nn.MaxPool2d; a 3x3 / stride 2 / padding 1 pool of a float32 CUDA tensor that needs a gradient runs
+    through the pair of kernels above (NCHW shape, channels-last memory), everything else through the stock module."""
+    def _pair(v):
+        return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.requires_grad and torch.is_grad_enabled() and x.shape[1] % 4 == 0
+            and _pair(pool.kernel_size) == (3, 3) and _pair(pool.stride) == (2, 2) and _pair(pool.padding) == (1, 1)
+            and _pair(pool.dilation) == (1, 1) and not pool.ceil_mode and not pool.return_indices
+            and not os.environ.get("SLFP_NO_FUSED_BN")):
+        return _MaxPool3x3s2.apply(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+    return pool(x)

@@ -418,6 +418,13 @@ int slfp_bn_act_bwd(const float *gy, const float *x, const float *y, size_t m, i
                     const float *save_mean, const float *save_invstd, int relu, float *dx, float *d_residual,
                     float *dgamma, float *dbeta, float *workspace, float *coef, float *dx_absmax, slfp_stream_t stream);
 
+/* The 3x3 / stride 2 / padding 1 max-pool of a training step on float32 NHWC [n, h, w, c] (c % 4 == 0): replaces
+ * `self.maxpool` (nn.MaxPool2d(3, 2, 1), nets_imgnet/resnet50.py:237) forward and backward.  idx [n, ho, wo, c] bytes:
+ * the window position (row * 3 + column) of each maximum, PyTorch's tie / NaN rule.  The backward is a deterministic
+ * gather (no atomics, dx needs no zero-fill). */
+int slfp_maxpool3x3s2_fwd_f32(const float *x, int n, int h, int w, int c, float *y, uint8_t *idx, slfp_stream_t stream);
+int slfp_maxpool3x3s2_bwd_f32(const float *gy, const uint8_t *idx, int n, int h, int w, int c, float *dx, slfp_stream_t stream);
+
 /* Debug aid: a host-mapped buffer (>= 16 bytes) into which a timed-out barrier wait of the dense conv kernel
  * records which wait it was before it traps (the kernels never hang: every wait is bounded).  NULL removes it. */
 int slfp_debug_set_buffer(void *host_mapped_device_ptr);
