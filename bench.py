@@ -378,7 +378,7 @@ def run_qat(args, rank, world, local, dev, barrier):
                 "config": {"workload": workload, "images_per_gpu": batch, "parallelism": f"dp{world}",
                            "optimizer": "DSGD (revised SGD, one multi-tensor launch)",
                            "gradient_allreduce": "bucketed ~25 MB, launched from grad hooks during backward (GradientArena)" if world > 1 else "none (1 GPU)",
-                           "between_layers": "float32 (stock BatchNorm / ReLU / add of the caller net)",
+                           "between_layers": "float32 tensors (reference semantics); training BatchNorm + add + ReLU fused (csrc/bn_act.cu), stem max-pool own kernels",
                            "l2": "activations of a 128-image step exceed the 126 MB L2; no explicit flush"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
