@@ -578,12 +578,34 @@ class Plan:
             self._wbatch = jobs
         nv.check(self.lib.slfp_prepare_weights_jobs(n, self._wbatch, self.wfmt, nv.stream()))
 
+    def _run_head(self):
+        """Weight re-quantization and the input quantizer do not depend on each other: the first runs on a side stream
+        (a fork / join that a CUDA-graph capture records as two parallel branches) while the second - HBM-bound, where
+        the weight kernel is latency-bound - runs on the caller's stream.  Returns the number of ops issued."""
+        h = getattr(self, "_head_ops", 0)
+        if self.static_weights or not self.weight_table:
+            return 0
+        if h == 0 or os.environ.get("SLFP_NO_WPREP_OVERLAP"):
+            self.prepare_weights()
+            return 0
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.dev)
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.prepare_weights()
+        st = nv.stream()
+        for op in self.ops[:h]:
+            op(st)
+        main.wait_stream(side)
+        return h
+
     @torch.no_grad()
     def run(self):
+        done = self._run_head()
         st = nv.stream()
-        if not self.static_weights:
-            self.prepare_weights()
-        for op in self.ops:
+        for op in self.ops[done:]:
             op(st)
         return self.output
 
@@ -617,9 +639,8 @@ class Plan:
         gh, gt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.no_grad():
             with torch.cuda.graph(gh):
-                if not self.static_weights:
-                    self.prepare_weights()
-                for op in self.ops[:h]:
+                done = self._run_head()
+                for op in self.ops[done:h]:
                     op(nv.stream())
             with torch.cuda.graph(gt):
                 for op in self.ops[h:]:
