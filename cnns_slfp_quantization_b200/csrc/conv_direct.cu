@@ -832,37 +832,7 @@ __global__ void __launch_bounds__(256) maxpool_codes_kernel(const uint8_t* __res
     }
 }
 
-// Post-ReLU (unsigned, monotone) codes: byte-wise unsigned max, 16 channels per thread.  HBM-bound: each
-// input byte is read once from DRAM (window overlap hits L1/L2), one 16-byte store per thread.
-__global__ void __launch_bounds__(256) maxpool_ucodes_kernel(const uint8_t* __restrict__ x, int N, int H, int W, int Cp,
-                                                             int kh, int kw, int stride, int pad, int Ho, int Wo,
-                                                             uint8_t* __restrict__ y) {
-    const int cq = Cp >> 4;
-    const size_t total = (size_t)N * Ho * Wo * cq;
-    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
-        const int c0 = (int)(idx % cq) * 16;
-        const size_t pix = idx / cq;
-        const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
-        uint4 best = make_uint4(0u, 0u, 0u, 0u);
-        for (int r = 0; r < kh; ++r) {
-            const int hi = ho * stride - pad + r;
-            if (hi < 0 || hi >= H) continue;
-            for (int s = 0; s < kw; ++s) {
-                const int wi = wo * stride - pad + s;
-                if (wi < 0 || wi >= W) continue;
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * Cp + c0));
-                best.x = __vmaxu4(best.x, v.x); best.y = __vmaxu4(best.y, v.y);
-                best.z = __vmaxu4(best.z, v.z); best.w = __vmaxu4(best.w, v.w);
-            }
-        }
-        *reinterpret_cast<uint4*>(y + pix * Cp + c0) = best;
-    }
-}
-
-// The ResNet stem pool (3x3, stride 2, padding 1) on post-ReLU codes: a thread produces TWO horizontally adjacent
-// outputs of 16 channels from one 3 x 5 window - 15 independent 16-byte loads in flight per thread (the generic
-// kernel's runtime-bounded tap loop kept one or two) and 7.5 instead of 9 loads per output.
-// Byte-wise unsigned max has no native instruction (__vmaxu4 is a ~10-instruction emulation: the first version of this
+// Byte-wise unsigned max has no native instruction (__vmaxu4 is a ~10-instruction emulation: the first version of the 3x3 / 2
 // kernel spent 560 of its 770 SASS instructions per thread there and was issue-bound at 3.5 TB/s, ncu
 // profiles/r04_final.md); 16-bit lanes do (max.u16x2 = VIMNMX.U16x2).  Each loaded word is split once into its even and
 // odd bytes (two PRMT), all maxima run on those halves, and one PRMT per word re-interleaves the result.
@@ -889,6 +859,34 @@ __device__ __forceinline__ uint4 join16(const U16x8& a) {
     return make_uint4(__byte_perm(a.e[0], a.o[0], 0x6240), __byte_perm(a.e[1], a.o[1], 0x6240),
                       __byte_perm(a.e[2], a.o[2], 0x6240), __byte_perm(a.e[3], a.o[3], 0x6240));
 }
+// Post-ReLU (unsigned, monotone) codes: byte-wise unsigned max, 16 channels per thread.  HBM-bound: each
+// input byte is read once from DRAM (window overlap hits L1/L2), one 16-byte store per thread.
+__global__ void __launch_bounds__(256) maxpool_ucodes_kernel(const uint8_t* __restrict__ x, int N, int H, int W, int Cp,
+                                                             int kh, int kw, int stride, int pad, int Ho, int Wo,
+                                                             uint8_t* __restrict__ y) {
+    const int cq = Cp >> 4;
+    const size_t total = (size_t)N * Ho * Wo * cq;
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+        const int c0 = (int)(idx % cq) * 16;
+        const size_t pix = idx / cq;
+        const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
+        U16x8 best = split16(make_uint4(0u, 0u, 0u, 0u));               // maxima on 16-bit lanes (max.u16x2), see above
+        for (int r = 0; r < kh; ++r) {
+            const int hi = ho * stride - pad + r;
+            if (hi < 0 || hi >= H) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int wi = wo * stride - pad + s;
+                if (wi < 0 || wi >= W) continue;
+                best = max16(best, split16(__ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * Cp + c0))));
+            }
+        }
+        *reinterpret_cast<uint4*>(y + pix * Cp + c0) = join16(best);
+    }
+}
+
+// The ResNet stem pool (3x3, stride 2, padding 1) on post-ReLU codes: a thread produces TWO horizontally adjacent
+// outputs of 16 channels from one 3 x 5 window - 15 independent 16-byte loads in flight per thread (the generic
+// kernel's runtime-bounded tap loop kept one or two) and 7.5 instead of 9 loads per output.
 __global__ void __launch_bounds__(256) maxpool3x3s2_ucodes_kernel(const uint8_t* __restrict__ x, int N, int H, int W, int Cp,
                                                                   int Ho, int Wo, uint8_t* __restrict__ y) {
     // work items < 2^31 (host): 32-bit index arithmetic
