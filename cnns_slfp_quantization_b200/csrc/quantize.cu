@@ -1026,34 +1026,6 @@ struct WFastBatch {
 };
 static_assert(sizeof(WFastBatch) <= 32000, "kernel parameter space");
 
-// SLFP<3,4> weight encoder as ONE table look-up (wprep_rows_kernel, quotients known to be finite and non-zero): entry
-// (|q| bits >> 18) - clamped to [below 0.0625 | the 8 x 32 buckets of [0.0625, 16) | 16 and above] - holds the bucket's
-// only decision threshold on the full bit pattern (a rounding threshold 2^((2j-1)/32) of sfp_quant.py:40, or the
-// saturation bound 15.32165 of :46 - never both: the bound lies in bucket 29 of [8, 16), the nearest thresholds in 27
-// and 30), the unsigned codes below / at-and-above it and their float16 images.  11 instead of 26 instructions per
-// weight; bit-exact with encode_wgt_bucket() on that domain (tests/test_gpu_fused.py sweeps every mantissa).
-constexpr int kWgtLutEntries = 258;
-__device__ __forceinline__ uint4 wgt_lut_entry(uint32_t i, const uint32_t* __restrict__ s_tab) {
-    uint32_t thr = 0xffffffffu, lo, hi;
-    if (i == 0u) lo = hi = kCodeTiny;
-    else if (i == kWgtLutEntries - 1) lo = hi = kCodeSat;
-    else {
-        const uint32_t e = (i - 1u) >> 5, m5 = (i - 1u) & 31u;             // |q| in 2^(e-4) * [1 + m5/32, 1 + (m5+1)/32)
-        if (e == 0u) lo = hi = 16u;                                        // [0.0625, 0.125) -> 0.125
-        else {
-            uint32_t cnt, t;
-            wgt_bucket_entry(m5, cnt, t);
-            lo = (e << 4) + cnt; hi = lo + 1u;                             // L == 16 carries into the exponent
-            if (t != 0xffffffffu) thr = ((123u + e) << 23) | (t & 0x007fffffu);
-            const uint32_t b0 = ((123u + e) << 23) | (m5 << 18);
-            if (b0 > kBitsSat8) lo = hi = kCodeSat;                        // whole bucket above 15.32165
-            else if (b0 + (1u << 18) > kBitsSat8) { thr = kBitsSat8 + 1u; hi = kCodeSat; }
-        }
-    }
-    const uint32_t hl = (uint32_t)__half_as_ushort(__float2half_rn(decode<false>(lo, s_tab)));
-    const uint32_t hh = (uint32_t)__half_as_ushort(__float2half_rn(decode<false>(hi, s_tab)));
-    return make_uint4(thr, lo, hi, hl | (hh << 16));
-}
 // OUT: 0 float16 operand, 1 code bytes, 2 e4m3 bytes (through w_f16), 3 float16 operand and code bytes
 template <int FMT, int OUT>
 __global__ void __launch_bounds__(256) wprep_rows_kernel(const __grid_constant__ WFastBatch b) {
@@ -1064,7 +1036,7 @@ __global__ void __launch_bounds__(256) wprep_rows_kernel(const __grid_constant__
     __shared__ __align__(16) __half s_h[kH ? kWFastCap + kWFastMaxTaps * 8 : 8];
     __shared__ __align__(16) uint8_t s_c[kB ? kWFastCap + kWFastMaxTaps * 16 : 16];
     constexpr bool kLut = FMT == SLFP_FMT_SLFP34_WGT;
-    __shared__ uint4 s_lut[kLut ? kWgtLutEntries : 1];
+    __shared__ WgtLutEntry s_lut[kLut ? kWgtLutEntries : 1];
     // persistent CTAs: the tables are built once, then the CTA walks over pieces blockIdx.x, + gridDim.x, ...
     if (threadIdx.x < 16) s_tab[threadIdx.x] = c_pow2frac[threadIdx.x];
     __syncthreads();
@@ -1127,12 +1099,10 @@ __global__ void __launch_bounds__(256) wprep_rows_kernel(const __grid_constant__
                 const float q0 = x[e] * dk.rk;
                 const float r = fmaf(-q0, dk.k, x[e]);
                 const uint32_t qb = f2u(fmaf(r, dk.rk, q0)), qa = qb & 0x7fffffffu;   // == IEEE x / kw
-                int t = (int)(qa >> 18) - (123 * 32 - 1);
-                t = min(max(t, 0), kWgtLutEntries - 1);
-                const uint4 en = s_lut[t];
-                const bool up = qa >= en.x;
-                if (kH) s_h[at_h] = __ushort_as_half((unsigned short)(__byte_perm(en.w, 0u, up ? 0x4432u : 0x4410u) | ((qb >> 16) & 0x8000u)));
-                if (kB) s_c[at_c] = (uint8_t)((up ? en.z : en.y) | ((qb >> 24) & 0x80u));
+                uint32_t h16;
+                const uint32_t code = encode_wgt_lut(qb, s_lut[wgt_lut_index(qa)], h16);
+                if (kH) s_h[at_h] = __ushort_as_half((unsigned short)h16);
+                if (kB) s_c[at_c] = (uint8_t)code;
                 at_h += ph; at_c += pc;
                 if (++rs == RS) { rs = 0; ++ch; at_h = ch; at_c = ch; }
             }

@@ -557,6 +557,51 @@ __host__ __device__ __forceinline__ uint32_t sfp33_code_to_e4m3(uint32_t code) {
     return (code & 0x80u) | (u + 24u);                        // E + 3 in the exponent field: ((E + 3) << 3) | m
 }
 
+// ---- SLFP<3,4> weight encoder as ONE table look-up (wprep_rows_kernel in quantize.cu) ---------------------------------
+// Domain: finite non-zero quotients (the kernel's group probe guarantees it).  Entry (|q| bits >> 18) - clamped to
+// [below 0.0625 | the 8 x 32 buckets of [0.0625, 16) | 16 and above] - holds the bucket's only decision threshold on the
+// full bit pattern (a rounding threshold 2^((2j-1)/32) of sfp_quant.py:40, or the saturation bound 15.32165 of :46 - never
+// both: the bound lies in bucket 29 of [8, 16), the nearest thresholds in 27 and 30), the unsigned codes below /
+// at-and-above it and the float16 images of their values.  11 instead of 26 instructions per weight; bit-exact with
+// encode_wgt_bucket() / encode<SLFP34_WGT>() on that domain: swept for every mantissa on the host
+// (tests/test_host_compiled_kernels.py::test_weight_lut_encoder_equals_reference_encoder) and on the GPU against the oracle.
+constexpr int kWgtLutEntries = 258;
+struct WgtLutEntry { uint32_t thr, lo, hi, halves; };        // halves: float16(decode(lo)) | float16(decode(hi)) << 16
+__host__ __device__ __forceinline__ uint32_t f16_bits_rn(float v) { return (uint32_t)__half_as_ushort(__float2half_rn(v)); }
+__host__ __device__ inline WgtLutEntry wgt_lut_entry(uint32_t i, const uint32_t* __restrict__ tab) {
+    uint32_t thr = 0xffffffffu, lo, hi;
+    if (i == 0u) lo = hi = kCodeTiny;
+    else if (i == (uint32_t)kWgtLutEntries - 1u) lo = hi = kCodeSat;
+    else {
+        const uint32_t e = (i - 1u) >> 5, m5 = (i - 1u) & 31u;             // |q| in 2^(e-4) * [1 + m5/32, 1 + (m5+1)/32)
+        if (e == 0u) lo = hi = 16u;                                        // [0.0625, 0.125) -> 0.125
+        else {
+            uint32_t cnt, t;
+            wgt_bucket_entry(m5, cnt, t);
+            lo = (e << 4) + cnt; hi = lo + 1u;                             // L == 16 carries into the exponent
+            if (t != 0xffffffffu) thr = ((123u + e) << 23) | (t & 0x007fffffu);
+            const uint32_t b0 = ((123u + e) << 23) | (m5 << 18);
+            if (b0 > kBitsSat8) lo = hi = kCodeSat;                        // whole bucket above 15.32165
+            else if (b0 + (1u << 18) > kBitsSat8) { thr = kBitsSat8 + 1u; hi = kCodeSat; }
+        }
+    }
+    WgtLutEntry en;
+    en.thr = thr; en.lo = lo; en.hi = hi;
+    en.halves = f16_bits_rn(decode<false>(lo, tab)) | (f16_bits_rn(decode<false>(hi, tab)) << 16);
+    return en;
+}
+__host__ __device__ __forceinline__ uint32_t wgt_lut_index(uint32_t qa) {
+    int t = (int)(qa >> 18) - (123 * 32 - 1);
+    t = t < 0 ? 0 : t;
+    return (uint32_t)(t > kWgtLutEntries - 1 ? kWgtLutEntries - 1 : t);
+}
+// signed code of the quotient with bit pattern qb; half16: float16 image of its value (sign included)
+__host__ __device__ __forceinline__ uint32_t encode_wgt_lut(uint32_t qb, const WgtLutEntry& en, uint32_t& half16) {
+    const bool up = (qb & 0x7fffffffu) >= en.thr;
+    half16 = (up ? (en.halves >> 16) : (en.halves & 0xffffu)) | ((qb >> 16) & 0x8000u);
+    return (up ? en.hi : en.lo) | ((qb >> 24) & 0x80u);
+}
+
 // value of an activation code in any of the code formats a dense conv accepts
 __host__ __device__ __forceinline__ float decode_act_any(uint32_t code, int fmt, const uint32_t* __restrict__ tab) {
     switch (fmt) {

@@ -164,3 +164,26 @@ extern "C" void hostcheck_sfast_codes(const float* q, size_t n, uint8_t* codes, 
         values[i] = decode_act_any(c, SLFP_FMT_SFP33_SFAST, h_pow2frac);
     }
 }
+
+// encode_wgt_lut (the one-look-up weight encoder of wprep_rows_kernel) against encode<SLFP34_WGT> on its domain: finite
+// non-zero values.  Also checks the float16 image: float16(decode(code)).
+extern "C" size_t hostcheck_encode_wgt_lut_mismatches(const float* v, size_t n) {
+    static WgtLutEntry lut[kWgtLutEntries];
+    static bool built = false;
+    if (!built) {
+        for (uint32_t i = 0; i < (uint32_t)kWgtLutEntries; ++i) lut[i] = wgt_lut_entry(i, h_pow2frac);
+        built = true;
+    }
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t qb = f2u(v[i]), qa = qb & 0x7fffffffu;
+        if (qa == 0u || qa >= 0x7f800000u) continue;                       // outside the look-up's domain
+        uint32_t h16;
+        const uint32_t code = encode_wgt_lut(qb, lut[wgt_lut_index(qa)], h16);
+        const uint32_t want = encode<SLFP_FMT_SLFP34_WGT>(v[i]);
+        const uint32_t hw = f16_bits_rn(decode<false>(want, h_pow2frac));
+        bad += (code != want) || (h16 != hw);
+    }
+    return bad;
+}
+

@@ -166,6 +166,21 @@ def test_weight_bucket_encoder_equals_reference_encoder(hostcheck):
             assert bad == 0, (e, sgn, bad)
 
 
+def test_weight_lut_encoder_equals_reference_encoder(hostcheck):
+    """encode_wgt_lut (ONE table look-up per weight in wprep_rows_kernel: bucket threshold, codes on both sides and their
+    float16 images; csrc/slfp_common.cuh) == encode<SLFP34_WGT> and float16(decode(code)) for every float32 mantissa of
+    every binade that matters (below, inside and above the code range) plus far-out exponents, both signs."""
+    fn = hostcheck.hostcheck_encode_wgt_lut_mismatches
+    fn.restype = ctypes.c_size_t
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    for e in [1, 60, 100, 120, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 132, 190, 254]:
+        x = (mant | np.uint32(e << 23)).view(np.float32)
+        for sgn in (0, 1):
+            v = np.ascontiguousarray((x.view(np.uint32) | np.uint32(sgn << 31)).view(np.float32))
+            bad = fn(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(v.size))
+            assert bad == 0, (e, sgn, bad)
+
+
 def test_layerout_relu_fast_form_equals_reference_form(hostcheck):
     """relu(quantize_layerout(y)) as the fused fast epilogues compute it (Veltkamp split, min / max) is bit-exact with the
     generic routine for every mantissa at a spread of exponents (both signs, the 248 clamp, values around it)."""
